@@ -1,0 +1,215 @@
+"""numpy-level wrapper of the device arena (the C-ABI of include/b2cuda.h).
+
+This is the host-side mirror used from Python: scenes are described as plain SoA numpy arrays
+(the same arrays a maintainer's binding inside the reference would hand over),
+uploaded once, and stepped on the GPU.  No oracle code is reachable from here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import f32, i32, u32
+
+
+def body_flags(btype, awake=True, allow_sleep=True, enabled=True, fixed_rotation=False):
+    f = (int(btype) << capi.BODY_TYPE_SHIFT)
+    if awake and btype != capi.STATIC:
+        f |= capi.BODY_AWAKE
+    if allow_sleep:
+        f |= capi.BODY_AUTOSLEEP
+    if enabled:
+        f |= capi.BODY_ENABLED
+    if fixed_rotation:
+        f |= capi.BODY_FIXED_ROTATION
+    return f
+
+
+class Arena:
+    def __init__(self, max_bodies, max_fixtures, max_shape_quads, max_contacts, num_worlds=1, max_joints=0, device=0):
+        self.lib = capi.load_cuda()
+        d = capi.ArenaDef(device, num_worlds, max_bodies, max_fixtures, max_shape_quads, max_contacts, max_joints, 0)
+        self.h = C.c_void_p()
+        capi.check(self.lib.b2g_arena_create(C.byref(d), C.byref(self.h)), "b2g_arena_create")
+        self.num_bodies = 0
+        self.num_fixtures = 0
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.b2g_arena_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- uploads ---------------------------------------------------------------------------
+    def upload_bodies(self, first=0, pos=None, vel=None, xf=None, mass=None, center=None, force=None, flags=None,
+                      world=None):
+        arrs = dict(pos=pos, vel=vel, xf=xf, mass=mass, center=center, force=force)
+        n = None
+        a = capi.BodyArrays()
+        keep = []
+        for k, v in arrs.items():
+            if v is not None:
+                v = f32(v).reshape(-1, 4)
+                n = len(v)
+                keep.append(v)
+                setattr(a, k, capi.fp(v))
+        if flags is not None:
+            flags = u32(flags)
+            n = len(flags)
+            keep.append(flags)
+            a.flags = capi.up(flags)
+        if world is not None:
+            world = i32(world)
+            n = len(world)
+            keep.append(world)
+            a.world = capi.ip(world)
+        capi.check(self.lib.b2g_upload_bodies(self.h, first, n, C.byref(a)), "b2g_upload_bodies")
+        self.num_bodies = max(self.num_bodies, first + n)
+
+    def upload_fixtures(self, first=0, body=None, shape_off=None, type_flags=None, filter=None, material=None):
+        a = capi.FixtureArrays()
+        keep = []
+        n = None
+        if body is not None:
+            body = i32(body); n = len(body); keep.append(body); a.body = capi.ip(body)
+        if shape_off is not None:
+            shape_off = i32(shape_off); n = len(shape_off); keep.append(shape_off); a.shape_off = capi.ip(shape_off)
+        if type_flags is not None:
+            type_flags = u32(type_flags); n = len(type_flags); keep.append(type_flags)
+            a.type_flags = capi.up(type_flags)
+        if filter is not None:
+            filter = u32(filter).reshape(-1, 2); n = len(filter); keep.append(filter); a.filter = capi.up(filter)
+        if material is not None:
+            material = f32(material).reshape(-1, 4); n = len(material); keep.append(material)
+            a.material = capi.fp(material)
+        capi.check(self.lib.b2g_upload_fixtures(self.h, first, n, C.byref(a)), "b2g_upload_fixtures")
+        self.num_fixtures = max(self.num_fixtures, first + n)
+
+    def upload_shapes(self, quads, first=0):
+        quads = f32(quads).reshape(-1, 4)
+        capi.check(self.lib.b2g_upload_shapes(self.h, first, len(quads), capi.fp(quads)), "b2g_upload_shapes")
+
+    def upload_joints(self, bodies, anchors, params, first=0):
+        bodies = i32(bodies).reshape(-1, 2)
+        anchors = f32(anchors).reshape(-1, 4)
+        params = f32(params).reshape(-1, 8)
+        a = capi.JointArrays(capi.ip(bodies), capi.fp(anchors), capi.fp(params))
+        capi.check(self.lib.b2g_upload_joints(self.h, first, len(bodies), C.byref(a)), "b2g_upload_joints")
+
+    def upload_forces(self, force_ptr, first, count):
+        capi.check(self.lib.b2g_upload_forces(self.h, first, count, force_ptr), "b2g_upload_forces")
+
+    # ---- stepping --------------------------------------------------------------------------
+    @staticmethod
+    def params(dt=1.0 / 60.0, vel_iters=8, pos_iters=3, gravity=(0.0, -10.0), warm_starting=True, allow_sleep=True,
+               clear_forces=True, solver_mode=capi.SOLVER_COLOURED, record_events=False):
+        return capi.StepParams(dt, vel_iters, pos_iters, gravity[0], gravity[1], int(warm_starting),
+                               int(allow_sleep), int(clear_forces), int(solver_mode), int(record_events))
+
+    def find_new_contacts(self):
+        capi.check(self.lib.b2g_find_new_contacts(self.h), "b2g_find_new_contacts")
+
+    def step(self, params, stats=None):
+        capi.check(self.lib.b2g_step(self.h, C.byref(params), C.byref(stats) if stats is not None else None),
+                   "b2g_step")
+
+    def synchronize(self):
+        capi.check(self.lib.b2g_synchronize(self.h), "b2g_synchronize")
+
+    def stream(self):
+        return self.lib.b2g_stream(self.h)
+
+    def set_profiling(self, on=True):
+        self.lib.b2g_set_profiling(self.h, int(on))
+
+    def set_inv_dt0(self, v):
+        self.lib.b2g_set_inv_dt0(self.h, float(v))
+
+    # ---- readback --------------------------------------------------------------------------
+    def download_bodies(self, first=0, count=None, what=("pos", "vel", "xf", "flags", "force")):
+        n = self.num_bodies - first if count is None else count
+        out = {}
+        a = capi.BodyArrays()
+        for k in what:
+            if k == "flags":
+                out[k] = np.zeros(n, np.uint32)
+                a.flags = capi.up(out[k])
+            elif k == "world":
+                out[k] = np.zeros(n, np.int32)
+                a.world = capi.ip(out[k])
+            else:
+                out[k] = np.zeros((n, 4), np.float32)
+                setattr(a, k, capi.fp(out[k]))
+        if n:
+            capi.check(self.lib.b2g_download_bodies(self.h, first, n, C.byref(a)), "b2g_download_bodies")
+        return out
+
+    def download_aabbs(self):
+        out = np.zeros((self.num_fixtures, 4), np.float32)
+        if len(out):
+            capi.check(self.lib.b2g_download_fixture_aabbs(self.h, 0, len(out), capi.fp(out)), "aabbs")
+        return out
+
+    def contact_count(self):
+        n = C.c_int32()
+        capi.check(self.lib.b2g_contact_count(self.h, C.byref(n)), "b2g_contact_count")
+        return n.value
+
+    def download_contacts(self):
+        n = self.contact_count()
+        d = dict(fix_a=np.zeros(n, np.int32), fix_b=np.zeros(n, np.int32), flags=np.zeros(n, np.uint32),
+                 manifold=np.zeros((n, 16), np.float32), material=np.zeros((n, 4), np.float32),
+                 colour=np.zeros(n, np.int32))
+        if n:
+            a = capi.ContactArrays(capi.ip(d["fix_a"]), capi.ip(d["fix_b"]), capi.up(d["flags"]),
+                                   capi.fp(d["manifold"]), capi.fp(d["material"]), capi.ip(d["colour"]))
+            capi.check(self.lib.b2g_download_contacts(self.h, 0, n, C.byref(a)), "b2g_download_contacts")
+        return d
+
+
+def arena_from_scene(scene, max_contacts=None, device=0, num_worlds=1, copies=1):
+    """Builds an arena holding `copies` replicas of a (reference or drop-in) scene's bodies and
+    fixtures, each replica in its own world when num_worlds > 1.  Body state is taken bit-for-bit
+    from the scene, so the arena starts exactly where that scene currently is."""
+    b = scene.bodies()
+    p = scene.body_params()
+    fx = scene.fixtures()
+    nb, nf, nq = len(b), len(fx["body"]), len(fx["quads"])
+    if max_contacts is None:
+        max_contacts = max(1024, 8 * nb * copies)
+    A = Arena(nb * copies, nf * copies, nq * copies, max_contacts, num_worlds=num_worlds, device=device)
+    btype = b[:, 11].astype(np.int32)
+    mass = p[:, 0]
+    inertia_origin = p[:, 1]
+    lc = p[:, 2:4]
+    inv_mass = np.where(mass > 0, np.float32(1.0) / np.where(mass > 0, mass, 1).astype(np.float32), 0).astype(np.float32)
+    # b2Body keeps I about the centre of mass: GetInertia() = I + m*|lc|^2 (b2_body.h:693-696)
+    i_center = (inertia_origin - mass * (lc[:, 0] * lc[:, 0] + lc[:, 1] * lc[:, 1])).astype(np.float32)
+    inv_i = np.where(i_center > 0, np.float32(1.0) / np.where(i_center > 0, i_center, 1).astype(np.float32), 0).astype(np.float32)
+    z = np.zeros(nb, np.float32)
+    pos = np.stack([b[:, 4], b[:, 5], b[:, 6], z], 1)
+    vel = np.stack([b[:, 7], b[:, 8], b[:, 9], z], 1)
+    xf = b[:, 0:4]
+    massq = np.stack([inv_mass, inv_i, mass, p[:, 6]], 1)
+    center = np.stack([lc[:, 0], lc[:, 1], p[:, 4], p[:, 5]], 1)
+    force = np.zeros((nb, 4), np.float32)
+    flags = np.array([body_flags(int(t), awake=bool(a), allow_sleep=bool(s)) for t, a, s in
+                      zip(btype, b[:, 10], p[:, 7])], np.uint32)
+    tf = fx["type"].astype(np.uint32) | np.where(fx["sensor"] != 0, capi.FIX_SENSOR, 0).astype(np.uint32)
+    filt = np.stack([(fx["filter"][:, 0].astype(np.uint32) & 0xffff) | ((fx["filter"][:, 1].astype(np.uint32) & 0xffff) << 16),
+                     fx["filter"][:, 2].astype(np.int32).view(np.uint32)], 1)
+    for k in range(copies):
+        A.upload_bodies(k * nb, pos=pos, vel=vel, xf=xf, mass=massq, center=center, force=force, flags=flags,
+                        world=np.full(nb, k if num_worlds > 1 else 0, np.int32))
+        A.upload_shapes(fx["quads"], first=k * nq)
+        A.upload_fixtures(k * nf, body=fx["body"] + k * nb, shape_off=fx["shape_off"] + k * nq, type_flags=tf,
+                          filter=filt, material=fx["material"])
+    A.scene_inv = (inv_mass, inv_i)
+    return A

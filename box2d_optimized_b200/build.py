@@ -1,0 +1,86 @@
+"""Build recipe for the native libraries (sm_100a only, no other targets).
+
+  libb2cuda.so        CUDA kernels + the C-ABI of include/b2cuda.h        (nvcc)
+  libb2gpu_scenes.so  drop-in C++ API (include/box2d) + scene shim over it  (g++)
+
+Both are built IN-TREE next to this file so they travel with a gpurun snapshot.
+nvcc cross-compiles without a GPU, so build() works on the CPU-only container.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # bit-parity with the reference's x86-64 build: no FMA contraction, IEEE div/sqrt
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    print("[build]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+
+
+def _find(tool, fallback):
+    return shutil.which(tool) or fallback
+
+
+def build_cuda(force=False):
+    out = os.path.join(HERE, "libb2cuda.so")
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "b2cuda.h")]
+    if force or _newer(out, srcs):
+        nvcc = _find("nvcc", "/usr/local/cuda/bin/nvcc")
+        _run([nvcc] + NVCC_FLAGS + ["-o", out, os.path.join(CSRC, "b2g_capi.cu")])
+    return out
+
+
+def build_host(force=False):
+    out = os.path.join(HERE, "libb2gpu_scenes.so")
+    srcs = [os.path.join(HOST, f) for f in ("b2_world_host.cpp", "b2_shapes.cpp", "gpu_scene_shim.cpp")]
+    deps = srcs + [os.path.join(ROOT, "scenes", f) for f in os.listdir(os.path.join(ROOT, "scenes"))]
+    deps += [os.path.join(ROOT, "include", "box2d", f) for f in os.listdir(os.path.join(ROOT, "include", "box2d"))]
+    deps += [os.path.join(HERE, "libb2cuda.so")]
+    if force or _newer(out, deps):
+        gxx = _find("g++", "g++")
+        _run([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wl,-Bsymbolic",
+              "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "scenes")] + srcs +
+             ["-L" + HERE, "-lb2cuda", "-Wl,-rpath,$ORIGIN", "-o", out])
+    return out
+
+
+def build_oracle(force=False):
+    """Builds the checker (test infrastructure): the C restatement always, the compiled
+    reference only where /root/reference exists (this container; the GPU box uses the prebuilt
+    oracle/_ref/libb2ref.so that travelled with the snapshot)."""
+    odir = os.path.join(ROOT, "oracle")
+    built = []
+    if os.path.exists(os.path.join(odir, "b2_oracle.c")):
+        _run(["make", "-C", odir, "port"])
+        built.append(os.path.join(odir, "libb2oracle.so"))
+    if os.path.isdir("/root/reference/src"):
+        _run(["make", "-C", odir, "ref", "-j8"])
+        built.append(os.path.join(odir, "_ref", "libb2ref.so"))
+    return built
+
+
+def build_all(force=False):
+    return [build_cuda(force), build_host(force)] + build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)

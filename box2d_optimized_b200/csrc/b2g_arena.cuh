@@ -1,0 +1,122 @@
+// b2g_arena.cuh — the device-resident world state (structure-of-arrays in HBM).
+//
+// Replaces the pointer-linked AoS state of the reference: b2Body (include/box2d/b2_body.h:498-547),
+// b2Fixture (include/box2d/b2_fixture.h:243-268), b2Contact (include/box2d/b2_contact.h:176-230),
+// the broadphase node pool (include/box2d/b2_broad_phase.h:32-42) and the per-island solver
+// scratch (src/dynamics/b2_island.h:57-95).  SURVEY.md Appendix A lists the field mapping.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b2cuda.h"
+#include "b2g_solver.cuh"
+
+#define B2G_MAX_COLOURS 24          // colours solved by parallel launches
+#define B2G_OVERFLOW_COLOUR B2G_MAX_COLOURS  // serial overflow bucket
+#define B2G_MAX_POS_ITERS 16
+
+// device-side counters, zeroed at the start of every step; mirrored to pinned host memory
+struct StepCounts {
+  int numPairs;      // candidate pairs emitted by the broadphase traversal
+  int numActive;     // solver constraints this step
+  int remaining;     // constraints still uncoloured after the rounds launched so far
+  int numTouching;
+  int numAwake;
+  int beginCount, endCount;
+  int pad;
+  int colourCount[B2G_MAX_COLOURS + 1];
+  unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
+};
+
+// contacts are rebuilt in sorted-key order after every broadphase, so they are double buffered
+struct ContactBuf {
+  unsigned long long* key;  // [bucket | fixLo | fixHi], sorted ascending
+  int2* fix;                // fixtureA, fixtureB (A/B by the type table, b2_contact.cpp:58-77)
+  int2* body;               // bodyA, bodyB
+  uint32_t* flags;          // B2G_CONTACT_*
+  float4* material;         // friction, restitution, restitutionThreshold, tangentSpeed
+  float4* m0;               // manifold planes, see b2gContactArrays.manifold
+  float4* m1;
+  float4* m2;
+  float4* m3;
+  int* colour;              // persistent solver colour, -1 = none
+};
+
+struct b2gArena {
+  int device;
+  cudaStream_t stream;
+  cudaEvent_t ev[5];
+  int profiling;
+  int numWorlds, worldBits;
+  int capBodies, capFixtures, capQuads, capContacts, capJoints;
+  int nBodies, nFixtures, nJoints, nContacts;
+  int fixBits;        // bits per fixture index in the pair key
+  int aabbAllDirty;   // recompute static AABBs too (after fixture / body upload)
+  int recolour;       // drop persistent colours (after mass / type edits)
+  int roundsHint;     // colouring rounds to launch before the first check
+  float invDt0;
+  long long launches;
+  long long launchesAtStepStart;
+
+  // bodies
+  float4 *pos, *vel, *xf, *mass, *center, *force;
+  uint32_t* bflags;
+  int* bworld;
+  int* island;             // union-find parent, flattened to the island root
+  uint32_t* islandAwake;   // per root: some member is awake
+  uint32_t* islandMinSleep;  // per root: float bits of min sleepTime
+  uint32_t* islandPen;     // [B2G_MAX_POS_ITERS][capBodies] float bits of max penetration per iteration
+  unsigned long long* colourMask;  // per body: colours used by its constraints
+  unsigned long long* bodyBest;    // per body: best proposal this round
+
+  // fixtures + shapes
+  int* fBody;
+  int* fShapeOff;
+  uint32_t* fTypeFlags;
+  uint2* fFilter;
+  float4* fMaterial;
+  float4* fAabb;
+  float* fRadius;
+  float4* shapes;
+
+  // joints (revolute)
+  int2* jBodies;
+  float4* jAnchors;
+  float4* jParams0;  // referenceAngle, lower, upper, maxMotorTorque
+  float4* jParams1;  // motorSpeed, bits(flags), 0, 0
+  float4* jState;    // impulse.x, impulse.y, motorImpulse, lowerImpulse/upperImpulse packed later
+
+  // contacts
+  ContactBuf cb[2];
+  int cur;
+  uint8_t* oldPersist;
+
+  // broadphase scratch
+  unsigned long long *mortonKeys, *mortonKeysSorted;
+  int *leafFixture, *leafFixtureSorted;
+  float4* leafBox;
+  int4* leafInfo;
+  int* leafWorldEnd;
+  int* worldLast;
+  int4* nodeRange;  // first, split, last, parent
+  float4 *nodeBoxL, *nodeBoxR;
+  int* leafParent;
+  int* nodeVisit;
+  unsigned long long *pairKeys;
+
+  // solver scratch
+  uint8_t* activeFlag;
+  int* activeList;
+  int* sortedList;
+  uint8_t *colourKey, *colourKeySorted;
+  int* croot;
+  SolverPlanes planes;
+
+  // events
+  int2 *beginEvents, *endEvents;
+
+  StepCounts* dCounts;
+  StepCounts* hCounts;  // pinned
+  void* cubTemp;
+  size_t cubTempBytes;
+  float* hostStage;  // pinned staging for small downloads
+};

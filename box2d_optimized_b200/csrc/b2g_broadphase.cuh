@@ -1,0 +1,388 @@
+// b2g_broadphase.cuh — pair finding on the device.
+//
+// Replaces b2BroadPhase::UpdateAndQuery / BuildAndQuery / QueryAll
+// (include/box2d/b2_broad_phase.h:252-511, 587-620), the pair sink
+// b2ContactManager::QueryCallback (src/dynamics/b2_contact_manager.cpp:136-188) with its filters
+// (b2Body::ShouldCollide b2_body.cpp:459-480, b2ContactFilter::ShouldCollide
+// b2_world_callbacks.cpp:28-40, the b2Contact::Create type table b2_contact.cpp:58-77) and the
+// persist / dead-contact protocol (b2_contact_manager.cpp:97,123-134; b2_world.cpp:125-138).
+//
+// The reference rebuilds a median-split BVH top-down and queries it during the build; the pair
+// SET it reports is exactly "all fixture pairs with inclusive tight-AABB overlap" (SURVEY
+// Appendix B.20), independent of tree shape.  The device path therefore builds a linear BVH
+// (Karras 2012) over Morton-sorted fixture AABBs every step and lets every leaf traverse it,
+// reporting each pair once (only partners later in the sorted order), with warp-aggregated
+// compaction into a key list that is then sorted and merged against the previous contacts.
+#pragma once
+#include "b2g_step_kernels.cuh"
+
+// tight AABBs for fixtures of non-static bodies (b2_broad_phase.h:265-276); static AABBs are
+// frozen at creation and only recomputed when `all` is set.  Also reduces
+// the bounds of 2*centre for the Morton normalisation.
+__global__ void __launch_bounds__(256)
+k_update_aabbs(int nf, const int* __restrict__ fBody, const int* __restrict__ fShapeOff,
+               const uint32_t* __restrict__ fTypeFlags, const float4* __restrict__ shapes,
+               const uint32_t* __restrict__ bflags, const float4* __restrict__ xf, float4* fAabb, float* fRadius,
+               int all, StepCounts* counts) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  float cx = 0.0f, cy = 0.0f;
+  bool valid = false;
+  if (f < nf) {
+    uint32_t tf = fTypeFlags[f];
+    if (!(tf & B2G_FIX_DEAD)) {
+      int b = fBody[f];
+      uint32_t bf = bflags[b];
+      float4 box;
+      // all: 0 = refresh non-static fixtures, 1 = refresh everything, 2 = boxes given, refresh nothing
+      if (all == 1 || (all == 0 && B2G_BODY_TYPE(bf) != B2G_STATIC)) {
+        int type = (int)(tf & 3u), off = fShapeOff[f];
+        box = shape_aabb(shapes, type, off, xf_from4(xf[b]));
+        fAabb[f] = box;
+        if (all == 1) {
+          float r;
+          if (type == 0) r = __ldg(shapes + off).z;
+          else if (type == 1) r = __ldg(shapes + off + 2).x;
+          else r = __ldg(shapes + off).z;
+          fRadius[f] = r;
+        }
+      } else {
+        box = fAabb[f];
+      }
+      cx = box.x + box.z;
+      cy = box.y + box.w;
+      valid = true;
+    }
+  }
+  // block reduce min/max of the doubled centres, then 4 atomics per block
+  unsigned int lox = valid ? float_flip(cx) : 0xffffffffu, loy = valid ? float_flip(cy) : 0xffffffffu;
+  unsigned int hix = valid ? float_flip(cx) : 0u, hiy = valid ? float_flip(cy) : 0u;
+  for (int o = 16; o > 0; o >>= 1) {
+    lox = min(lox, __shfl_xor_sync(0xffffffffu, lox, o));
+    loy = min(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+    hix = max(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+    hiy = max(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+  }
+  __shared__ unsigned int sm[4][8];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    sm[0][wid] = lox;
+    sm[1][wid] = loy;
+    sm[2][wid] = hix;
+    sm[3][wid] = hiy;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nw = blockDim.x >> 5;
+    for (int k = 1; k < nw; ++k) {
+      lox = min(lox, sm[0][k]);
+      loy = min(loy, sm[1][k]);
+      hix = max(hix, sm[2][k]);
+      hiy = max(hiy, sm[3][k]);
+    }
+    lox = min(sm[0][0], lox);
+    loy = min(sm[1][0], loy);
+    hix = max(sm[2][0], hix);
+    hiy = max(sm[3][0], hiy);
+    atomicMin(&counts->boundsLo[0], lox);
+    atomicMin(&counts->boundsLo[1], loy);
+    atomicMax(&counts->boundsHi[0], hix);
+    atomicMax(&counts->boundsHi[1], hiy);
+  }
+}
+
+__device__ __forceinline__ unsigned int expand_bits16(unsigned int v) {
+  v &= 0xffffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+// sort key = world id (high) | 32-bit Morton code of the AABB centre (low); dead fixtures sort last
+__global__ void k_morton_keys(int nf, const float4* __restrict__ fAabb, const uint32_t* __restrict__ fTypeFlags,
+                              const int* __restrict__ fBody, const int* __restrict__ bworld,
+                              const StepCounts* __restrict__ counts, unsigned long long* keys, int* leafFixture,
+                              int numWorlds) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  leafFixture[f] = f;
+  if (fTypeFlags[f] & B2G_FIX_DEAD) {
+    keys[f] = ((unsigned long long)numWorlds << 32) | 0xffffffffull;
+    return;
+  }
+  float lox = float_unflip(counts->boundsLo[0]), loy = float_unflip(counts->boundsLo[1]);
+  float hix = float_unflip(counts->boundsHi[0]), hiy = float_unflip(counts->boundsHi[1]);
+  float ex = hix - lox, ey = hiy - loy;
+  float sx = ex > 0.0f ? 65535.0f / ex : 0.0f;
+  float sy = ey > 0.0f ? 65535.0f / ey : 0.0f;
+  float4 box = fAabb[f];
+  float cx = box.x + box.z, cy = box.y + box.w;
+  unsigned int qx = (unsigned int)fminf(fmaxf((cx - lox) * sx, 0.0f), 65535.0f);
+  unsigned int qy = (unsigned int)fminf(fmaxf((cy - loy) * sy, 0.0f), 65535.0f);
+  unsigned int morton = (expand_bits16(qx) << 1) | expand_bits16(qy);
+  unsigned long long w = numWorlds > 1 ? (unsigned long long)bworld[fBody[f]] : 0ull;
+  keys[f] = (w << 32) | morton;
+}
+
+// leaves in sorted order: box + everything the pair filter needs in one int4
+//   x = fixture, y = body, z = type | sensor<<2 | dynamic<<3 | dead<<4 | group<<16, w = category | mask<<16
+__global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
+                              const unsigned long long* __restrict__ keysSorted, const float4* __restrict__ fAabb,
+                              const int* __restrict__ fBody, const uint32_t* __restrict__ fTypeFlags,
+                              const uint2* __restrict__ fFilter, const uint32_t* __restrict__ bflags, float4* leafBox,
+                              int4* leafInfo, int* worldLast, int numWorlds) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nf) return;
+  int f = leafFixtureSorted[p];
+  uint32_t tf = fTypeFlags[f];
+  int b = fBody[f];
+  uint32_t bf = bflags[b];
+  uint2 fl = fFilter[f];
+  bool dead = (tf & B2G_FIX_DEAD) != 0;
+  leafBox[p] = dead ? make_float4(B2G_MAX_FLOAT, B2G_MAX_FLOAT, -B2G_MAX_FLOAT, -B2G_MAX_FLOAT) : fAabb[f];
+  unsigned int z = (tf & 3u) | ((tf & B2G_FIX_SENSOR) ? 4u : 0u) | (B2G_BODY_TYPE(bf) == B2G_DYNAMIC ? 8u : 0u) |
+                   (dead ? 16u : 0u) | ((fl.y & 0xffffu) << 16);
+  leafInfo[p] = make_int4(f, b, (int)z, (int)fl.x);
+  if (numWorlds > 1) {
+    unsigned int w = (unsigned int)(keysSorted[p] >> 32);
+    bool lastOfWorld = (p == nf - 1) || ((unsigned int)(keysSorted[p + 1] >> 32) != w);
+    if (lastOfWorld && w < (unsigned int)numWorlds) worldLast[w] = p;
+  }
+}
+
+// ---- Karras 2012: one thread per internal node -------------------------------------------------
+__device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_lbvh_build(int n, const unsigned long long* __restrict__ keys, int4* nodeRange, int* leafParent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = lbvh_delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = lbvh_delta(keys, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  int split = i + s * d + min(d, 0);
+  int first = min(i, j), last = max(i, j);
+  // children: [first, split] and [split+1, last]; a one-element range is a leaf
+  nodeRange[i].x = first;
+  nodeRange[i].y = split;
+  nodeRange[i].z = last;
+  if (first == split) leafParent[split] = i; else nodeRange[split].w = i;
+  if (split + 1 == last) leafParent[last] = i; else nodeRange[split + 1].w = i;
+  if (i == 0) nodeRange[0].w = -1;
+}
+
+// bottom-up refit: the second thread to reach a node carries the union upward; child boxes are
+// stored IN the parent so the traversal tests both children with one node fetch
+__global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const int* __restrict__ leafParent,
+                             const int4* __restrict__ nodeRange, float4* nodeBoxL, float4* nodeBoxR, int* nodeVisit) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float4 box = leafBox[p];
+  int idx = p;
+  int parent = leafParent[p];
+  while (parent >= 0) {
+    int4 nr = nodeRange[parent];
+    bool isLeft = (idx == nr.y);
+    if (isLeft) nodeBoxL[parent] = box; else nodeBoxR[parent] = box;
+    __threadfence();
+    int old = atomicAdd(&nodeVisit[parent], 1);
+    if (old == 0) return;
+    float4 sib = isLeft ? __ldcg(&nodeBoxR[parent]) : __ldcg(&nodeBoxL[parent]);
+    box = make_float4(fminf(box.x, sib.x), fminf(box.y, sib.y), fmaxf(box.z, sib.z), fmaxf(box.w, sib.w));
+    idx = parent;
+    parent = nr.w;
+  }
+}
+
+// inclusive AABB overlap, b2TestOverlap (include/box2d/b2_collision.h:270-276)
+__device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
+  return (a.z >= b.x) & (a.x <= b.z) & (a.w >= b.y) & (a.y <= b.w);
+}
+
+// QueryCallback's filters, without the user-filter virtual call (default b2ContactFilter only)
+__device__ __forceinline__ bool pair_passes(int4 a, int4 b) {
+  if (a.y == b.y) return false;                          // same body
+  unsigned int za = (unsigned int)a.z, zb = (unsigned int)b.z;
+  if (((za | zb) & 8u) == 0) return false;               // at least one dynamic body
+  if ((za | zb) & 16u) return false;                     // dead fixture
+  unsigned int ta = za & 3u, tb = zb & 3u;
+  if (ta == B2G_SHAPE_EDGE && tb == B2G_SHAPE_EDGE) return false;  // no edge-edge function
+  short ga = (short)(za >> 16), gb = (short)(zb >> 16);
+  if (ga == gb && ga != 0) return ga > 0;
+  unsigned int fa = (unsigned int)a.w, fb = (unsigned int)b.w;
+  unsigned int catA = fa & 0xffffu, maskA = fa >> 16, catB = fb & 0xffffu, maskB = fb >> 16;
+  return (maskA & catB) != 0 && (catA & maskB) != 0;
+}
+
+// contacts are bucketed by shape-type pair so narrowphase warps stay uniform
+__device__ __forceinline__ unsigned int type_bucket(unsigned int ta, unsigned int tb) {
+  unsigned int lo = min(ta, tb), hi = max(ta, tb);
+  // (0,0) circles=0, (0,2) polygon-circle=1, (2,2) polygons=2, (0,1) edge-circle=3, (1,2) edge-polygon=4
+  if (lo == 0 && hi == 0) return 0;
+  if (lo == 0 && hi == 2) return 1;
+  if (lo == 2) return 2;
+  if (lo == 0 && hi == 1) return 3;
+  return 4;
+}
+
+__device__ __forceinline__ void emit_pair(int4 a, int4 b, unsigned long long* pairKeys, int capacity, int fixBits,
+                                          StepCounts* counts) {
+  bool ok = pair_passes(a, b);
+  if (!ok) return;
+  auto g = cg::coalesced_threads();
+  int base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&counts->numPairs, (int)g.size());
+  base = g.shfl(base, 0);
+  int k = base + (int)g.thread_rank();
+  if (k < capacity) {
+    unsigned long long lo = (unsigned long long)min(a.x, b.x), hi = (unsigned long long)max(a.x, b.x);
+    unsigned long long bucket = type_bucket((unsigned int)a.z & 3u, (unsigned int)b.z & 3u);
+    pairKeys[k] = (bucket << (2 * fixBits)) | (lo << fixBits) | hi;
+  }
+}
+
+// one thread per query leaf; reports partners later in sorted order (each pair once) and never
+// leaves the query's own world segment
+__global__ void __launch_bounds__(128)
+k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo,
+              const int4* __restrict__ nodeRange, const float4* __restrict__ nodeBoxL,
+              const float4* __restrict__ nodeBoxR, const int* __restrict__ worldLast,
+              const unsigned long long* __restrict__ keysSorted, int numWorlds, unsigned long long* pairKeys,
+              int capacity, int fixBits, StepCounts* counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || n < 2) return;
+  int4 me = leafInfo[i];
+  if ((unsigned int)me.z & 16u) return;
+  float4 qbox = leafBox[i];
+  int we = n - 1;
+  if (numWorlds > 1) {
+    unsigned int w = (unsigned int)(keysSorted[i] >> 32);
+    we = worldLast[w];
+  }
+  int stack[64];
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    int node = stack[--sp];
+    int4 nr = nodeRange[node];
+    float4 bl = nodeBoxL[node], br = nodeBoxR[node];
+    // left child covers [first, split]
+    if (nr.y > i && nr.x <= we && aabb_overlap(qbox, bl)) {
+      if (nr.x == nr.y) emit_pair(me, leafInfo[nr.y], pairKeys, capacity, fixBits, counts);
+      else stack[sp++] = nr.y;
+    }
+    // right child covers [split+1, last]
+    if (nr.z > i && nr.y + 1 <= we && aabb_overlap(qbox, br)) {
+      if (nr.y + 1 == nr.z) emit_pair(me, leafInfo[nr.z], pairKeys, capacity, fixBits, counts);
+      else stack[sp++] = nr.y + 1;
+    }
+  }
+}
+
+// ---- pair list -> contact list ---------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restrict__ a, int n,
+                                               unsigned long long key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// new contact i takes its persistent state from the old contact with the same key (the
+// e_persistFlag protocol) or is created fresh (b2Contact ctor, b2_contact.cpp:96-122)
+__global__ void __launch_bounds__(256)
+k_contact_merge(int nNew, const unsigned long long* __restrict__ newKeys, int nOld, ContactBuf O, ContactBuf N,
+                uint8_t* oldPersist, int fixBits, const int* __restrict__ fBody,
+                const uint32_t* __restrict__ fTypeFlags, const float4* __restrict__ fMaterial) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nNew) return;
+  unsigned long long key = newKeys[i];
+  N.key[i] = key;
+  int j = lower_bound_u64(O.key, nOld, key);
+  if (j < nOld && O.key[j] == key) {
+    oldPersist[j] = 1;
+    N.fix[i] = O.fix[j];
+    N.body[i] = O.body[j];
+    N.flags[i] = O.flags[j];
+    N.material[i] = O.material[j];
+    N.m0[i] = O.m0[j];
+    N.m1[i] = O.m1[j];
+    N.m2[i] = O.m2[j];
+    N.m3[i] = O.m3[j];
+    N.colour[i] = O.colour[j];
+    return;
+  }
+  unsigned long long maskBits = (1ull << fixBits) - 1ull;
+  int lo = (int)((key >> fixBits) & maskBits), hi = (int)(key & maskBits);
+  unsigned int tl = fTypeFlags[lo] & 3u, th = fTypeFlags[hi] & 3u;
+  // A/B order from the function table: [circle][circle] [polygon][circle] [polygon][polygon]
+  // [edge][circle] [edge][polygon]; same-type pairs keep the lower fixture index as A
+  bool loFirst = (tl == th) || (tl == B2G_SHAPE_POLYGON && th == B2G_SHAPE_CIRCLE) ||
+                 (tl == B2G_SHAPE_EDGE && th == B2G_SHAPE_CIRCLE) || (tl == B2G_SHAPE_EDGE && th == B2G_SHAPE_POLYGON);
+  int fa = loFirst ? lo : hi, fb = loFirst ? hi : lo;
+  N.fix[i] = make_int2(fa, fb);
+  N.body[i] = make_int2(fBody[fa], fBody[fb]);
+  N.flags[i] = B2G_CONTACT_ENABLED;
+  float4 ma = fMaterial[fa], mb = fMaterial[fb];
+  // mixing laws, include/box2d/b2_contact.h:42-60
+  float friction = sqrtf(ma.x * mb.x);
+  float restitution = ma.y > mb.y ? ma.y : mb.y;
+  float threshold = ma.z < mb.z ? ma.z : mb.z;
+  N.material[i] = make_float4(friction, restitution, threshold, 0.0f);
+  float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  N.m0[i] = z;
+  N.m1[i] = z;
+  N.m2[i] = z;
+  N.m3[i] = z;
+  N.colour[i] = -1;
+}
+
+// contacts that were not re-reported die: b2ContactManager::Destroy (b2_contact_manager.cpp:48-61)
+// fires EndContact if touching, b2Contact::Destroy (b2_contact.cpp:79-94) wakes both bodies if the
+// manifold had points
+__global__ void k_contact_dead(int nOld, ContactBuf O, const uint8_t* __restrict__ oldPersist,
+                               const uint32_t* __restrict__ fTypeFlags, uint32_t* bflags, float4* force,
+                               StepCounts* counts, int recordEvents, int2* endEvents, int eventCap) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nOld) return;
+  if (oldPersist[j]) return;
+  int2 fx = O.fix[j];
+  uint32_t flags = O.flags[j];
+  if (recordEvents && (flags & B2G_CONTACT_TOUCHING)) {
+    int k = atomicAdd(&counts->endCount, 1);
+    if (k < eventCap) endEvents[k] = fx;
+  }
+  int pointCount = __float_as_int(O.m3[j].w);
+  if (pointCount > 0 && !((fTypeFlags[fx.x] | fTypeFlags[fx.y]) & B2G_FIX_SENSOR)) {
+    // SetAwake(true) takes effect immediately (the next Collide must see the body awake);
+    // concurrent writers all store the same values
+    int2 bd = O.body[j];
+    if (B2G_BODY_TYPE(bflags[bd.x]) != B2G_STATIC) {
+      atomicOr(&bflags[bd.x], B2G_BODY_AWAKE);
+      force[bd.x].w = 0.0f;
+    }
+    if (B2G_BODY_TYPE(bflags[bd.y]) != B2G_STATIC) {
+      atomicOr(&bflags[bd.y], B2G_BODY_AWAKE);
+      force[bd.y].w = 0.0f;
+    }
+  }
+}

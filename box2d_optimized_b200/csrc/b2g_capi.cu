@@ -1,0 +1,805 @@
+// b2g_capi.cu — arena management, the per-step launch sequence and the C-ABI of include/b2cuda.h.
+//
+// b2g_step() is b2World::Step (src/dynamics/b2_world.cpp:1108-1171) re-expressed as a fixed
+// sequence of kernels on one CUDA stream; see b2g_step_kernels.cuh / b2g_broadphase.cuh for the
+// kernel <-> reference-loop mapping.  There is no CPU fallback anywhere in this file.
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "b2g_broadphase.cuh"
+
+static thread_local char g_err[512] = "";
+static int set_err(const char* what, const char* detail) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, detail ? detail : "");
+  return 0;
+}
+#define CK(call)                                              \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) {                                  \
+      set_err(#call, cudaGetErrorString(e_));                 \
+      return B2G_ERR_CUDA;                                    \
+    }                                                         \
+  } while (0)
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+#define LAUNCH(A, kernel, grid, block, ...)                       \
+  do {                                                            \
+    kernel<<<(grid), (block), 0, (A)->stream>>>(__VA_ARGS__);     \
+    (A)->launches++;                                              \
+  } while (0)
+
+extern "C" const char* b2g_last_error(void) { return g_err; }
+
+extern "C" int b2g_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+  return e;
+}
+
+static int alloc_contact_buf(ContactBuf& c, int cap) {
+  CK(dalloc(&c.key, cap));
+  CK(dalloc(&c.fix, cap));
+  CK(dalloc(&c.body, cap));
+  CK(dalloc(&c.flags, cap));
+  CK(dalloc(&c.material, cap));
+  CK(dalloc(&c.m0, cap));
+  CK(dalloc(&c.m1, cap));
+  CK(dalloc(&c.m2, cap));
+  CK(dalloc(&c.m3, cap));
+  CK(dalloc(&c.colour, cap));
+  return B2G_OK;
+}
+static void free_contact_buf(ContactBuf& c) {
+  cudaFree(c.key);
+  cudaFree(c.fix);
+  cudaFree(c.body);
+  cudaFree(c.flags);
+  cudaFree(c.material);
+  cudaFree(c.m0);
+  cudaFree(c.m1);
+  cudaFree(c.m2);
+  cudaFree(c.m3);
+  cudaFree(c.colour);
+}
+
+static int bits_for(int n) {
+  int b = 1;
+  while ((1ll << b) < (long long)n) ++b;
+  return b;
+}
+
+extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
+  if (!def || !out || def->max_bodies <= 0 || def->max_fixtures <= 0 || def->max_contacts <= 0 ||
+      def->max_shape_quads <= 0 || def->num_worlds <= 0) {
+    set_err("b2g_arena_create", "invalid definition");
+    return B2G_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("b2g_arena_create", "no CUDA device: this library has no CPU fallback");
+    return B2G_ERR_NO_DEVICE;
+  }
+  if (def->device < 0 || def->device >= ndev) {
+    set_err("b2g_arena_create", "device ordinal out of range");
+    return B2G_ERR_INVALID;
+  }
+  CK(cudaSetDevice(def->device));
+  b2gArena* A = (b2gArena*)calloc(1, sizeof(b2gArena));
+  A->device = def->device;
+  A->numWorlds = def->num_worlds;
+  A->worldBits = bits_for(def->num_worlds + 1);
+  A->capBodies = def->max_bodies;
+  A->capFixtures = def->max_fixtures;
+  A->capQuads = def->max_shape_quads;
+  A->capContacts = def->max_contacts;
+  A->capJoints = def->max_joints > 0 ? def->max_joints : 1;
+  A->fixBits = bits_for(def->max_fixtures);
+  A->aabbAllDirty = 1;
+  A->recolour = 1;
+  A->roundsHint = 8;
+  CK(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&A->ev[i]));
+
+  const int nb = A->capBodies, nf = A->capFixtures, nc = A->capContacts, nj = A->capJoints;
+  CK(dalloc(&A->pos, nb));
+  CK(dalloc(&A->vel, nb));
+  CK(dalloc(&A->xf, nb));
+  CK(dalloc(&A->mass, nb));
+  CK(dalloc(&A->center, nb));
+  CK(dalloc(&A->force, nb));
+  CK(dalloc(&A->bflags, nb));
+  CK(dalloc(&A->bworld, nb));
+  CK(dalloc(&A->island, nb));
+  CK(dalloc(&A->islandAwake, nb));
+  CK(dalloc(&A->islandMinSleep, nb));
+  CK(dalloc(&A->islandPen, (size_t)nb * B2G_MAX_POS_ITERS));
+  CK(dalloc(&A->colourMask, nb));
+  CK(dalloc(&A->bodyBest, nb));
+
+  CK(dalloc(&A->fBody, nf));
+  CK(dalloc(&A->fShapeOff, nf));
+  CK(dalloc(&A->fTypeFlags, nf));
+  CK(dalloc(&A->fFilter, nf));
+  CK(dalloc(&A->fMaterial, nf));
+  CK(dalloc(&A->fAabb, nf));
+  CK(dalloc(&A->fRadius, nf));
+  CK(dalloc(&A->shapes, A->capQuads));
+
+  CK(dalloc(&A->jBodies, nj));
+  CK(dalloc(&A->jAnchors, nj));
+  CK(dalloc(&A->jParams0, nj));
+  CK(dalloc(&A->jParams1, nj));
+  CK(dalloc(&A->jState, nj));
+
+  int rc = alloc_contact_buf(A->cb[0], nc);
+  if (rc) return rc;
+  rc = alloc_contact_buf(A->cb[1], nc);
+  if (rc) return rc;
+  CK(dalloc(&A->oldPersist, nc));
+
+  CK(dalloc(&A->mortonKeys, nf));
+  CK(dalloc(&A->mortonKeysSorted, nf));
+  CK(dalloc(&A->leafFixture, nf));
+  CK(dalloc(&A->leafFixtureSorted, nf));
+  CK(dalloc(&A->leafBox, nf));
+  CK(dalloc(&A->leafInfo, nf));
+  CK(dalloc(&A->leafWorldEnd, nf));
+  CK(dalloc(&A->worldLast, A->numWorlds + 1));
+  CK(dalloc(&A->nodeRange, nf));
+  CK(dalloc(&A->nodeBoxL, nf));
+  CK(dalloc(&A->nodeBoxR, nf));
+  CK(dalloc(&A->leafParent, nf));
+  CK(dalloc(&A->nodeVisit, nf));
+  CK(dalloc(&A->pairKeys, nc));
+
+  CK(dalloc(&A->activeFlag, nc));
+  CK(dalloc(&A->activeList, nc));
+  CK(dalloc(&A->sortedList, nc));
+  CK(dalloc(&A->colourKey, nc));
+  CK(dalloc(&A->colourKeySorted, nc));
+  CK(dalloc(&A->croot, nc));
+  SolverPlanes& S = A->planes;
+  CK(dalloc(&S.nf, nc));
+  CK(dalloc(&S.r1, nc));
+  CK(dalloc(&S.r2, nc));
+  CK(dalloc(&S.m1, nc));
+  CK(dalloc(&S.m2, nc));
+  CK(dalloc(&S.kk, nc));
+  CK(dalloc(&S.mass, nc));
+  CK(dalloc(&S.idx, nc));
+  CK(dalloc(&S.imp, nc));
+  CK(dalloc(&S.pn, nc));
+  CK(dalloc(&S.pp, nc));
+  CK(dalloc(&S.pc, nc));
+  CK(dalloc(&S.pr, nc));
+
+  CK(dalloc(&A->beginEvents, nc));
+  CK(dalloc(&A->endEvents, nc));
+  CK(dalloc(&A->dCounts, 1));
+  CK(cudaMallocHost((void**)&A->hCounts, sizeof(StepCounts)));
+  memset(A->hCounts, 0, sizeof(StepCounts));
+  CK(cudaMallocHost((void**)&A->hostStage, 4096));
+
+  // one CUB scratch buffer, sized for the largest of the four primitives used per step
+  size_t need = 0, t = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t, A->mortonKeys, A->mortonKeysSorted, A->leafFixture,
+                                  A->leafFixtureSorted, nf, 0, 64, A->stream);
+  need = t > need ? t : need;
+  cub::DeviceRadixSort::SortKeys(nullptr, t, A->pairKeys, A->cb[0].key, nc, 0, 64, A->stream);
+  need = t > need ? t : need;
+  cub::DeviceRadixSort::SortPairs(nullptr, t, A->colourKey, A->colourKeySorted, A->activeList, A->sortedList, nc, 0, 8,
+                                  A->stream);
+  need = t > need ? t : need;
+  cub::DeviceSelect::Flagged(nullptr, t, thrust::counting_iterator<int>(0), A->activeFlag, A->activeList,
+                             &A->dCounts->numActive, nc, A->stream);
+  need = t > need ? t : need;
+  A->cubTempBytes = need + 256;
+  CK(cudaMalloc(&A->cubTemp, A->cubTempBytes));
+  CK(cudaStreamSynchronize(A->stream));
+  *out = A;
+  return B2G_OK;
+}
+
+extern "C" int b2g_arena_destroy(b2gArena* A) {
+  if (!A) return B2G_ERR_INVALID;
+  cudaSetDevice(A->device);
+  cudaStreamSynchronize(A->stream);
+  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island,
+                  A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->fBody,
+                  A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->oldPersist, A->mortonKeys,
+                  A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
+                  A->leafWorldEnd, A->worldLast, A->nodeRange, A->nodeBoxL, A->nodeBoxR, A->leafParent,
+                  A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
+                  A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
+                  A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
+                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->cubTemp};
+  for (void* p : ptrs) cudaFree(p);
+  free_contact_buf(A->cb[0]);
+  free_contact_buf(A->cb[1]);
+  cudaFreeHost(A->hCounts);
+  cudaFreeHost(A->hostStage);
+  for (int i = 0; i < 5; ++i) cudaEventDestroy(A->ev[i]);
+  cudaStreamDestroy(A->stream);
+  free(A);
+  return B2G_OK;
+}
+
+#define UP(dst, src, elems, type)                                                                      \
+  if (src) CK(cudaMemcpyAsync((dst) + (size_t)first * (elems), (src), (size_t)count * (elems) * sizeof(type), \
+                              cudaMemcpyHostToDevice, A->stream))
+
+extern "C" int b2g_upload_bodies(b2gArena* A, int32_t first, int32_t count, const b2gBodyArrays* s) {
+  if (!A || !s || first < 0 || count < 0) return B2G_ERR_INVALID;
+  if (first + count > A->capBodies) {
+    set_err("b2g_upload_bodies", "max_bodies exceeded");
+    return B2G_ERR_CAPACITY;
+  }
+  CK(cudaSetDevice(A->device));
+  UP((float*)A->pos, s->pos, 4, float);
+  UP((float*)A->vel, s->vel, 4, float);
+  UP((float*)A->xf, s->xf, 4, float);
+  UP((float*)A->mass, s->mass, 4, float);
+  UP((float*)A->center, s->center, 4, float);
+  UP((float*)A->force, s->force, 4, float);
+  UP(A->bflags, s->flags, 1, uint32_t);
+  UP(A->bworld, s->world, 1, int32_t);
+  CK(cudaStreamSynchronize(A->stream));
+  if (first + count > A->nBodies) A->nBodies = first + count;
+  A->aabbAllDirty = 1;
+  if (s->mass || s->flags) A->recolour = 1;
+  return B2G_OK;
+}
+
+extern "C" int b2g_upload_fixtures(b2gArena* A, int32_t first, int32_t count, const b2gFixtureArrays* s) {
+  if (!A || !s || first < 0 || count < 0) return B2G_ERR_INVALID;
+  if (first + count > A->capFixtures) {
+    set_err("b2g_upload_fixtures", "max_fixtures exceeded");
+    return B2G_ERR_CAPACITY;
+  }
+  CK(cudaSetDevice(A->device));
+  UP(A->fBody, s->body, 1, int32_t);
+  UP(A->fShapeOff, s->shape_off, 1, int32_t);
+  UP(A->fTypeFlags, s->type_flags, 1, uint32_t);
+  UP((uint32_t*)A->fFilter, s->filter, 2, uint32_t);
+  UP((float*)A->fMaterial, s->material, 4, float);
+  CK(cudaStreamSynchronize(A->stream));
+  if (first + count > A->nFixtures) A->nFixtures = first + count;
+  A->aabbAllDirty = 1;
+  return B2G_OK;
+}
+
+extern "C" int b2g_upload_shapes(b2gArena* A, int32_t first, int32_t count, const float* quads) {
+  if (!A || !quads || first < 0 || count < 0) return B2G_ERR_INVALID;
+  if (first + count > A->capQuads) {
+    set_err("b2g_upload_shapes", "max_shape_quads exceeded");
+    return B2G_ERR_CAPACITY;
+  }
+  CK(cudaSetDevice(A->device));
+  UP((float*)A->shapes, quads, 4, float);
+  CK(cudaStreamSynchronize(A->stream));
+  A->aabbAllDirty = 1;
+  return B2G_OK;
+}
+
+extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, const b2gJointArrays* s) {
+  if (!A || !s || first < 0 || count < 0) return B2G_ERR_INVALID;
+  if (first + count > A->capJoints) {
+    set_err("b2g_upload_joints", "max_joints exceeded");
+    return B2G_ERR_CAPACITY;
+  }
+  CK(cudaSetDevice(A->device));
+  UP((int32_t*)A->jBodies, s->bodies, 2, int32_t);
+  UP((float*)A->jAnchors, s->anchors, 4, float);
+  if (s->params) {
+    // split [n][8] into two float4 planes
+    std::vector<float> p0((size_t)count * 4), p1((size_t)count * 4);
+    for (int i = 0; i < count; ++i) {
+      for (int k = 0; k < 4; ++k) {
+        p0[(size_t)i * 4 + k] = s->params[(size_t)i * 8 + k];
+        p1[(size_t)i * 4 + k] = s->params[(size_t)i * 8 + 4 + k];
+      }
+    }
+    CK(cudaMemcpyAsync((float*)A->jParams0 + (size_t)first * 4, p0.data(), p0.size() * sizeof(float),
+                       cudaMemcpyHostToDevice, A->stream));
+    CK(cudaMemcpyAsync((float*)A->jParams1 + (size_t)first * 4, p1.data(), p1.size() * sizeof(float),
+                       cudaMemcpyHostToDevice, A->stream));
+    CK(cudaMemsetAsync((float*)A->jState + (size_t)first * 4, 0, (size_t)count * 4 * sizeof(float), A->stream));
+    CK(cudaStreamSynchronize(A->stream));
+  }
+  CK(cudaStreamSynchronize(A->stream));
+  if (first + count > A->nJoints) A->nJoints = first + count;
+  return B2G_OK;
+}
+
+extern "C" int b2g_set_counts(b2gArena* A, int32_t nb, int32_t nf, int32_t nj) {
+  if (!A || nb < 0 || nf < 0 || nj < 0 || nb > A->capBodies || nf > A->capFixtures || nj > A->capJoints)
+    return B2G_ERR_INVALID;
+  A->nBodies = nb;
+  A->nFixtures = nf;
+  A->nJoints = nj;
+  A->aabbAllDirty = 1;
+  return B2G_OK;
+}
+
+extern "C" int b2g_upload_forces(b2gArena* A, int32_t first, int32_t count, const float* force) {
+  if (!A || !force || first < 0 || count < 0 || first + count > A->nBodies) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  // columns 0-2 only: column 3 is the device-owned sleep timer
+  CK(cudaMemcpy2DAsync((float*)A->force + (size_t)first * 4, 16, force, 16, 12, count, cudaMemcpyHostToDevice,
+                       A->stream));
+  return B2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// broadphase + contact list rebuild: b2ContactManager::FindNewContacts + RemoveDeadContacts
+// ---------------------------------------------------------------------------------------------
+static int read_counts(b2gArena* A) {
+  CK(cudaMemcpyAsync(A->hCounts, A->dCounts, sizeof(StepCounts), cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+static int reset_bounds(b2gArena* A) {
+  CK(cudaMemsetAsync(A->dCounts->boundsLo, 0xff, sizeof(unsigned int) * 2, A->stream));
+  CK(cudaMemsetAsync(A->dCounts->boundsHi, 0x00, sizeof(unsigned int) * 2, A->stream));
+  return B2G_OK;
+}
+
+static int find_new_contacts(b2gArena* A, int recordEvents) {
+  const int nf = A->nFixtures;
+  ContactBuf& O = A->cb[A->cur];
+  ContactBuf& N = A->cb[A->cur ^ 1];
+  const int nOld = A->nContacts;
+  int nNew = 0;
+  if (nf > 0) {
+    int rc = reset_bounds(A);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(&A->dCounts->numPairs, 0, sizeof(int), A->stream));
+    LAUNCH(A, k_update_aabbs, div_up(nf, 256), 256, nf, A->fBody, A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags,
+           A->xf, A->fAabb, A->fRadius, A->aabbAllDirty, A->dCounts);
+    A->aabbAllDirty = 0;
+    LAUNCH(A, k_morton_keys, div_up(nf, 256), 256, nf, A->fAabb, A->fTypeFlags, A->fBody, A->bworld, A->dCounts,
+           A->mortonKeys, A->leafFixture, A->numWorlds);
+    size_t tb = A->cubTempBytes;
+    CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb, A->mortonKeys, A->mortonKeysSorted, A->leafFixture,
+                                       A->leafFixtureSorted, nf, 0, 32 + (A->numWorlds > 1 ? A->worldBits : 0),
+                                       A->stream));
+    LAUNCH(A, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted, A->fAabb, A->fBody,
+           A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->worldLast, A->numWorlds);
+    CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
+    CK(cudaMemsetAsync(A->nodeVisit, 0, sizeof(int) * nf, A->stream));
+    if (nf > 1) {
+      LAUNCH(A, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange, A->leafParent);
+      LAUNCH(A, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafParent, A->nodeRange, A->nodeBoxL,
+             A->nodeBoxR, A->nodeVisit);
+      LAUNCH(A, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->nodeRange, A->nodeBoxL,
+             A->nodeBoxR, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->pairKeys, A->capContacts, A->fixBits,
+             A->dCounts);
+    }
+    int rc2 = read_counts(A);  // the one mid-pipeline sync: the sort below needs the pair count
+    if (rc2) return rc2;
+    nNew = A->hCounts->numPairs;
+    if (nNew > A->capContacts) {
+      char msg[128];
+      snprintf(msg, sizeof(msg), "broadphase found %d pairs, max_contacts is %d", nNew, A->capContacts);
+      set_err("b2g_step", msg);
+      return B2G_ERR_CAPACITY;
+    }
+  }
+  if (nNew > 0) {
+    size_t tb = A->cubTempBytes;
+    // sorted straight into the new buffer's key array, then merged in place
+    CK(cub::DeviceRadixSort::SortKeys(A->cubTemp, tb, A->pairKeys, N.key, nNew, 0,
+                                      3 + 2 * A->fixBits, A->stream));
+    CK(cudaMemsetAsync(A->oldPersist, 0, nOld > 0 ? nOld : 1, A->stream));
+    LAUNCH(A, k_contact_merge, div_up(nNew, 256), 256, nNew, N.key, nOld, O, N, A->oldPersist, A->fixBits, A->fBody,
+           A->fTypeFlags, A->fMaterial);
+  } else if (nOld > 0) {
+    CK(cudaMemsetAsync(A->oldPersist, 0, nOld, A->stream));
+  }
+  if (nOld > 0) {
+    LAUNCH(A, k_contact_dead, div_up(nOld, 256), 256, nOld, O, A->oldPersist, A->fTypeFlags, A->bflags, A->force,
+           A->dCounts, recordEvents, A->endEvents, A->capContacts);
+  }
+  A->cur ^= 1;
+  A->nContacts = nNew;
+  return B2G_OK;
+}
+
+extern "C" int b2g_find_new_contacts(b2gArena* A) {
+  if (!A) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
+  int rc = find_new_contacts(A, 0);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------
+static int step_check(b2gArena* A, const b2gStepParams* P) {
+  if (!A || !P) return B2G_ERR_INVALID;
+  if (P->position_iterations > B2G_MAX_POS_ITERS || P->position_iterations < 0 || P->velocity_iterations < 0) {
+    set_err("b2g_step", "iteration counts out of range");
+    return B2G_ERR_INVALID;
+  }
+  return B2G_OK;
+}
+
+// first half of Step: b2ContactManager::Collide (b2_world.cpp:1134-1138)
+extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
+  int rc0 = step_check(A, P);
+  if (rc0) return rc0;
+  CK(cudaSetDevice(A->device));
+  A->launchesAtStepStart = A->launches;
+  const int nc = A->nContacts;
+  ContactBuf& C = A->cb[A->cur];
+  CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
+  if (A->profiling) CK(cudaEventRecord(A->ev[0], A->stream));
+  if (nc > 0) {
+    LAUNCH(A, k_narrowphase, div_up(nc, 128), 128, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
+           A->bflags, A->dCounts, P->record_events, A->beginEvents, A->endEvents, A->capContacts);
+  }
+  if (A->profiling) CK(cudaEventRecord(A->ev[1], A->stream));
+  return B2G_OK;
+}
+
+// second half of Step: Solve + FindNewContacts + ClearForces (b2_world.cpp:1140-1167)
+extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats* stats) {
+  int rc0 = step_check(A, P);
+  if (rc0) return rc0;
+  CK(cudaSetDevice(A->device));
+  const long long launches0 = A->launchesAtStepStart;
+  const int nb = A->nBodies, nc = A->nContacts, nj = A->nJoints;
+  const float h = P->dt;
+  const float inv_dt = h > 0.0f ? 1.0f / h : 0.0f;
+  const float dtRatio = A->invDt0 * h;
+  const int prof = A->profiling;
+  ContactBuf& C = A->cb[A->cur];
+  int numActive = 0, numColours = 0, numOverflow = 0, rounds = 0;
+  int colourFirst[B2G_MAX_COLOURS + 2];
+  memset(colourFirst, 0, sizeof(colourFirst));
+
+  if (h > 0.0f && nb > 0) {
+    // ---- islands ---------------------------------------------------------------------
+    LAUNCH(A, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->island, A->islandAwake,
+           A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest);
+    if (nc > 0) LAUNCH(A, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->island);
+    if (nj > 0) LAUNCH(A, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->island);
+    LAUNCH(A, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake);
+    LAUNCH(A, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->vel, A->mass,
+           A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y), A->dCounts);
+
+    // ---- constraint list + colouring -------------------------------------------------
+    if (nc > 0) {
+      LAUNCH(A, k_mark_active, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->island, A->islandAwake, A->activeFlag,
+             A->recolour);
+      A->recolour = 0;
+      size_t tb = A->cubTempBytes;
+      CK(cub::DeviceSelect::Flagged(A->cubTemp, tb, thrust::counting_iterator<int>(0), A->activeFlag, A->activeList,
+                                    &A->dCounts->numActive, nc, A->stream));
+      const int* nAct = &A->dCounts->numActive;
+      if (P->solver_mode == B2G_SOLVER_COLOURED) {
+        int grid = div_up(nc, 256);
+        if (grid > 148 * 8) grid = 148 * 8;
+        LAUNCH(A, k_colour_begin, grid, 256, nAct, A->activeList, C, A->mass, A->colourMask, A->dCounts);
+        int round = 0;
+        int batch = A->roundsHint;
+        while (true) {
+          CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
+          for (int r = 0; r < batch; ++r, ++round) {
+            LAUNCH(A, k_colour_propose, grid, 256, nAct, A->activeList, C, A->mass, A->bodyBest, round);
+            LAUNCH(A, k_colour_commit, grid, 256, nAct, A->activeList, C, A->mass, A->colourMask, A->bodyBest, round,
+                   A->dCounts, r == batch - 1);
+          }
+          int rc = read_counts(A);
+          if (rc) return rc;
+          if (A->hCounts->remaining == 0) break;
+          if (round > 250) {
+            set_err("b2g_step", "graph colouring did not converge");
+            return B2G_ERR_CUDA;
+          }
+          batch = 4;
+        }
+        rounds = round;
+        // adapt the first batch: steady state needs 1-2 rounds, a cold start ~10
+        A->roundsHint = round <= 2 ? 2 : (round < 16 ? round : 16);
+        numActive = A->hCounts->numActive;
+        int acc = 0;
+        for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {
+          colourFirst[c] = acc;
+          acc += A->hCounts->colourCount[c];
+          if (c < B2G_MAX_COLOURS && A->hCounts->colourCount[c] > 0) numColours = c + 1;
+        }
+        colourFirst[B2G_MAX_COLOURS + 1] = acc;
+        numOverflow = A->hCounts->colourCount[B2G_MAX_COLOURS];
+        if (numActive > 0) {
+          LAUNCH(A, k_colour_keys, grid, 256, nAct, A->activeList, C, A->colourKey);
+          size_t tb2 = A->cubTempBytes;
+          CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb2, A->colourKey, A->colourKeySorted, A->activeList,
+                                             A->sortedList, numActive, 0, 8, A->stream));
+        }
+      } else {
+        int rc = read_counts(A);
+        if (rc) return rc;
+        numActive = A->hCounts->numActive;
+        if (numActive > 0)
+          CK(cudaMemcpyAsync(A->sortedList, A->activeList, sizeof(int) * numActive, cudaMemcpyDeviceToDevice,
+                             A->stream));
+      }
+    }
+
+    // ---- contact solver --------------------------------------------------------------
+    SolverPlanes& S = A->planes;
+    const bool coloured = P->solver_mode == B2G_SOLVER_COLOURED;
+    if (numActive > 0) {
+      LAUNCH(A, k_prepare, div_up(numActive, 128), 128, numActive, A->sortedList, C, A->fRadius, A->bflags, A->island,
+             S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
+      if (P->warm_starting) {
+        if (coloured) {
+          for (int c = 0; c < numColours; ++c) {
+            int n = colourFirst[c + 1] - colourFirst[c];
+            if (n > 0) LAUNCH(A, k_warm_start, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
+          }
+          if (numOverflow > 0)
+            LAUNCH(A, k_warm_start_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
+                   A->vel);
+        } else {
+          LAUNCH(A, k_warm_start_seq, 1, 1, 0, numActive, S, A->vel);
+        }
+      }
+      for (int it = 0; it < P->velocity_iterations; ++it) {
+        if (coloured) {
+          for (int c = 0; c < numColours; ++c) {
+            int n = colourFirst[c + 1] - colourFirst[c];
+            if (n > 0)
+              LAUNCH(A, k_solve_velocity, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
+          }
+          if (numOverflow > 0)
+            LAUNCH(A, k_solve_velocity_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
+                   A->vel);
+        } else {
+          LAUNCH(A, k_solve_velocity_seq, 1, 1, 0, numActive, S, A->vel);
+        }
+      }
+      LAUNCH(A, k_store_impulses, div_up(numActive, 256), 256, numActive, S, C);
+    }
+    LAUNCH(A, k_integrate_positions, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
+           h);
+    if (numActive > 0) {
+      for (int it = 0; it < P->position_iterations; ++it) {
+        if (coloured) {
+          for (int c = 0; c < numColours; ++c) {
+            int n = colourFirst[c + 1] - colourFirst[c];
+            if (n > 0)
+              LAUNCH(A, k_solve_position, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->pos,
+                     A->croot, A->islandPen, A->capBodies, it);
+          }
+          if (numOverflow > 0)
+            LAUNCH(A, k_solve_position_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
+                   A->pos, A->croot, A->islandPen, A->capBodies, it);
+        } else {
+          LAUNCH(A, k_solve_position_seq, 1, 1, 0, numActive, S, A->pos, A->croot, A->islandPen, A->capBodies, it);
+        }
+      }
+    }
+    LAUNCH(A, k_finalize_bodies, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
+           A->center, A->xf, A->force, A->islandMinSleep, h, P->allow_sleep);
+    LAUNCH(A, k_sleep_and_clear, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->islandMinSleep,
+           A->islandPen, A->capBodies, P->position_iterations, A->vel, A->force, P->allow_sleep, P->clear_forces,
+           A->dCounts);
+    if (prof) CK(cudaEventRecord(A->ev[2], A->stream));
+
+    // ---- FindNewContacts (end of Solve, b2_world.cpp:663-669) ------------------------
+    int rc = find_new_contacts(A, P->record_events);
+    if (rc) return rc;
+    if (prof) CK(cudaEventRecord(A->ev[3], A->stream));
+    A->invDt0 = inv_dt;
+  } else {
+    if (prof) {
+      CK(cudaEventRecord(A->ev[2], A->stream));
+      CK(cudaEventRecord(A->ev[3], A->stream));
+    }
+    int rc = read_counts(A);
+    if (rc) return rc;
+  }
+
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    // hCounts was last read inside find_new_contacts, after every counter of this step was final
+    stats->num_bodies = nb;
+    stats->num_fixtures = A->nFixtures;
+    stats->num_contacts = A->nContacts;
+    stats->num_touching = A->hCounts->numTouching;
+    stats->num_constraints = numActive;
+    stats->num_colours = numColours;
+    stats->num_overflow = numOverflow;
+    stats->num_awake = A->hCounts->numAwake;
+    stats->num_pairs = A->hCounts->numPairs;
+    stats->colour_rounds = rounds;
+    stats->num_launches = (int)(A->launches - launches0);
+    if (prof) {
+      CK(cudaStreamSynchronize(A->stream));
+      cudaEventElapsedTime(&stats->ms_collide, A->ev[0], A->ev[1]);
+      cudaEventElapsedTime(&stats->ms_solve, A->ev[1], A->ev[2]);
+      cudaEventElapsedTime(&stats->ms_broadphase, A->ev[2], A->ev[3]);
+      cudaEventElapsedTime(&stats->ms_step, A->ev[0], A->ev[3]);
+    }
+  }
+  return B2G_OK;
+}
+
+extern "C" int b2g_step(b2gArena* A, const b2gStepParams* P, b2gStepStats* stats) {
+  int rc = b2g_step_collide(A, P);
+  if (rc) return rc;
+  return b2g_step_solve(A, P, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// readback
+// ---------------------------------------------------------------------------------------------
+#define DOWN(dst, src, elems, type)                                                                          \
+  if (dst) CK(cudaMemcpyAsync((dst), (src) + (size_t)first * (elems), (size_t)count * (elems) * sizeof(type), \
+                              cudaMemcpyDeviceToHost, A->stream))
+
+extern "C" int b2g_download_bodies(b2gArena* A, int32_t first, int32_t count, const b2gBodyArrays* d) {
+  if (!A || !d || first < 0 || count < 0 || first + count > A->nBodies) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  DOWN(d->pos, (float*)A->pos, 4, float);
+  DOWN(d->vel, (float*)A->vel, 4, float);
+  DOWN(d->xf, (float*)A->xf, 4, float);
+  DOWN(d->mass, (float*)A->mass, 4, float);
+  DOWN(d->center, (float*)A->center, 4, float);
+  DOWN(d->force, (float*)A->force, 4, float);
+  DOWN(d->flags, A->bflags, 1, uint32_t);
+  DOWN(d->world, A->bworld, 1, int32_t);
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+__global__ void k_pack_body_state(int first, int count, const float4* __restrict__ xf, const float4* __restrict__ vel,
+                                  float4* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[2 * i] = xf[first + i];
+  out[2 * i + 1] = vel[first + i];
+}
+
+extern "C" int b2g_download_body_state_async(b2gArena* A, int32_t first, int32_t count, float* dst) {
+  if (!A || !dst || first < 0 || count < 0 || first + count > A->nBodies) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  // pack into the (idle between steps) leafBox/nodeBox scratch is not safe for count > capFixtures/2,
+  // so copy the two planes with strided 2-D copies straight into the interleaved host layout
+  CK(cudaMemcpy2DAsync(dst, 32, (const float*)A->xf + (size_t)first * 4, 16, 16, count, cudaMemcpyDeviceToHost,
+                       A->stream));
+  CK(cudaMemcpy2DAsync(dst + 4, 32, (const float*)A->vel + (size_t)first * 4, 16, 16, count, cudaMemcpyDeviceToHost,
+                       A->stream));
+  return B2G_OK;
+}
+
+extern "C" int b2g_download_fixture_aabbs(b2gArena* A, int32_t first, int32_t count, float* aabb) {
+  if (!A || !aabb || first < 0 || count < 0 || first + count > A->nFixtures) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  CK(cudaMemcpyAsync(aabb, (float*)A->fAabb + (size_t)first * 4, (size_t)count * 16, cudaMemcpyDeviceToHost,
+                     A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+extern "C" int b2g_contact_count(b2gArena* A, int32_t* out) {
+  if (!A || !out) return B2G_ERR_INVALID;
+  *out = A->nContacts;
+  return B2G_OK;
+}
+
+__global__ void k_pack_manifolds(int first, int count, ContactBuf C, float4* out, int* fa, int* fb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int j = first + i;
+  out[4 * i] = C.m0[j];
+  out[4 * i + 1] = C.m1[j];
+  out[4 * i + 2] = C.m2[j];
+  out[4 * i + 3] = C.m3[j];
+  int2 fx = C.fix[j];
+  fa[i] = fx.x;
+  fb[i] = fx.y;
+}
+
+extern "C" int b2g_download_contacts(b2gArena* A, int32_t first, int32_t count, const b2gContactArrays* d) {
+  if (!A || !d || first < 0 || count < 0 || first + count > A->nContacts) return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
+  CK(cudaSetDevice(A->device));
+  ContactBuf& C = A->cb[A->cur];
+  float4* tmp = nullptr;
+  int *ta = nullptr, *tb = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)count * 64));
+  CK(cudaMalloc(&ta, (size_t)count * 4));
+  CK(cudaMalloc(&tb, (size_t)count * 4));
+  k_pack_manifolds<<<div_up(count, 256), 256, 0, A->stream>>>(first, count, C, tmp, ta, tb);
+  if (d->manifold) CK(cudaMemcpyAsync(d->manifold, tmp, (size_t)count * 64, cudaMemcpyDeviceToHost, A->stream));
+  if (d->fixture_a) CK(cudaMemcpyAsync(d->fixture_a, ta, (size_t)count * 4, cudaMemcpyDeviceToHost, A->stream));
+  if (d->fixture_b) CK(cudaMemcpyAsync(d->fixture_b, tb, (size_t)count * 4, cudaMemcpyDeviceToHost, A->stream));
+  DOWN(d->flags, C.flags, 1, uint32_t);
+  DOWN(d->material, (float*)C.material, 4, float);
+  DOWN(d->colour, C.colour, 1, int32_t);
+  CK(cudaStreamSynchronize(A->stream));
+  cudaFree(tmp);
+  cudaFree(ta);
+  cudaFree(tb);
+  return B2G_OK;
+}
+
+extern "C" int b2g_upload_contact_overrides(b2gArena* A, int32_t first, int32_t count, const uint32_t* flags,
+                                            const float* material) {
+  if (!A || first < 0 || count < 0 || first + count > A->nContacts) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  ContactBuf& C = A->cb[A->cur];
+  if (flags)
+    CK(cudaMemcpyAsync(C.flags + first, flags, (size_t)count * 4, cudaMemcpyHostToDevice, A->stream));
+  if (material)
+    CK(cudaMemcpyAsync((float*)C.material + (size_t)first * 4, material, (size_t)count * 16, cudaMemcpyHostToDevice,
+                       A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+extern "C" int b2g_download_events(b2gArena* A, int32_t* beginPairs, int32_t* beginCount, int32_t* endPairs,
+                                   int32_t* endCount, int32_t capacityEach) {
+  if (!A || !beginCount || !endCount) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  int nbg = A->hCounts->beginCount, nen = A->hCounts->endCount;
+  if (nbg > A->capContacts) nbg = A->capContacts;
+  if (nen > A->capContacts) nen = A->capContacts;
+  *beginCount = nbg;
+  *endCount = nen;
+  int cb = nbg < capacityEach ? nbg : capacityEach, ce = nen < capacityEach ? nen : capacityEach;
+  if (beginPairs && cb > 0)
+    CK(cudaMemcpyAsync(beginPairs, A->beginEvents, (size_t)cb * 8, cudaMemcpyDeviceToHost, A->stream));
+  if (endPairs && ce > 0)
+    CK(cudaMemcpyAsync(endPairs, A->endEvents, (size_t)ce * 8, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+extern "C" int b2g_synchronize(b2gArena* A) {
+  if (!A) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+extern "C" void* b2g_stream(b2gArena* A) { return A ? (void*)A->stream : nullptr; }
+extern "C" int b2g_set_profiling(b2gArena* A, int32_t on) {
+  if (!A) return B2G_ERR_INVALID;
+  A->profiling = on;
+  return B2G_OK;
+}
+extern "C" int b2g_set_inv_dt0(b2gArena* A, float v) {
+  if (!A) return B2G_ERR_INVALID;
+  A->invDt0 = v;
+  return B2G_OK;
+}
+extern "C" int b2g_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return B2G_ERR_INVALID;
+  CK(cudaMallocHost(out, bytes ? bytes : 1));
+  return B2G_OK;
+}
+extern "C" int b2g_host_free(void* p) {
+  CK(cudaFreeHost(p));
+  return B2G_OK;
+}
+
+#include "b2g_kernel_entries.cuh"

@@ -1,0 +1,1109 @@
+// b2_world_host.cpp — b2World / b2Body / b2Fixture / b2Contact host handles over the C-ABI.
+//
+// The reference keeps all state in these objects and walks it on one CPU thread
+// (src/dynamics/b2_world.cpp, b2_body.cpp, b2_fixture.cpp, b2_contact.cpp).  Here they are thin
+// mirrors: creation and edits write a host copy and mark it dirty, b2World::Step uploads what
+// changed and calls b2g_step(), and getters lazily pull device state back.  Semantics kept from
+// the reference: silent no-op / nullptr while locked (b2_world.cpp:142-146 etc.), non-static
+// bodies at the head of the body list and static ones at the tail (b2_world.cpp:153-171),
+// fixture lists in reverse creation order (b2_body.cpp:244-246), mass recomputation on fixture
+// changes (b2_body.cpp:352-416), process-global fixture ids (b2_fixture.cpp:40-41).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+#include "b2cuda.h"
+#include "box2d/box2d.h"
+
+static int32 g_defaultBodies = 1 << 16, g_defaultFixtures = 1 << 16, g_defaultContacts = 1 << 18;
+static int32 g_defaultDevice = -1;
+static uint32 g_fixtureIdCounter = 0;
+
+static void b2gCheck(int rc, const char* what) {
+  if (rc != B2G_OK) {
+    // error convention of the reference: assert in debug builds, log and carry on otherwise
+    fprintf(stderr, "[b2cuda] %s failed (%d): %s\n", what, rc, b2g_last_error());
+    b2Assert(false);
+    abort();  // never continue on a silently wrong device state
+  }
+}
+
+struct b2WorldImpl {
+  b2World* world = nullptr;
+  b2gArena* arena = nullptr;
+  int32 capBodies = 0, capFixtures = 0, capContacts = 0, capQuads = 0, capJoints = 0;
+  std::vector<b2Body*> bodies;      // by device index (creation order); nullptr once destroyed
+  std::vector<b2Fixture*> fixtures; // by device index
+  std::vector<b2Joint*> joints;
+  std::vector<float> shapePool;     // float4 records, append-only
+  int32 shapesUploaded = 0;         // quads already on the device
+  int32 bodyDirtyLo = INT32_MAX, bodyDirtyHi = 0;
+  int32 fixtureDirtyLo = INT32_MAX, fixtureDirtyHi = 0;
+  bool jointsDirty = false;
+  bool bodiesStale = false;    // device has newer body state than the host copies
+  bool contactsStale = true;   // host contact list does not reflect the device
+  bool profiling = false;
+  std::vector<b2Contact*> contacts;                       // current list, device order
+  std::unordered_map<uint64_t, b2Contact*> contactPool;   // (fixA,fixB) -> handle, stable across steps
+  b2Contact sentinel;
+  std::vector<b2Contact*> graveyard;  // dead handles, kept valid until the end of the step's callbacks
+  b2gStepStats lastStats;
+
+  void touchBody(int32 i) {
+    bodyDirtyLo = std::min(bodyDirtyLo, i);
+    bodyDirtyHi = std::max(bodyDirtyHi, i + 1);
+  }
+  void touchFixture(int32 i) {
+    fixtureDirtyLo = std::min(fixtureDirtyLo, i);
+    fixtureDirtyHi = std::max(fixtureDirtyHi, i + 1);
+  }
+  static uint64_t key(int32 a, int32 b) { return ((uint64_t)(uint32)a << 32) | (uint32)b; }
+
+  void ensureArena();
+  void flush();
+  void pullBodies();
+  void pullContacts();
+  b2Contact* findContact(int32 fa, int32 fb);
+  void pushContactOverrides();
+};
+
+void b2WorldImpl::ensureArena() {
+  int32 needBodies = (int32)bodies.size(), needFixtures = (int32)fixtures.size();
+  int32 needQuads = (int32)(shapePool.size() / 4), needJoints = (int32)joints.size();
+  if (arena && needBodies <= capBodies && needFixtures <= capFixtures && needQuads <= capQuads &&
+      needJoints <= capJoints)
+    return;
+  if (arena) {
+    // grow: pull everything the host does not own (body state, contacts are rebuilt), recreate
+    pullBodies();
+    b2gCheck(b2g_arena_destroy(arena), "b2g_arena_destroy");
+    arena = nullptr;
+    contactsStale = true;
+  }
+  auto grow = [](int32 cap, int32 need, int32 dflt) {
+    int32 c = std::max(cap, dflt);
+    while (c < need) c *= 2;
+    return c;
+  };
+  capBodies = grow(capBodies, needBodies, g_defaultBodies);
+  capFixtures = grow(capFixtures, needFixtures, g_defaultFixtures);
+  capQuads = grow(capQuads, needQuads, std::max(g_defaultFixtures * 5, 1024));
+  capContacts = std::max(capContacts, g_defaultContacts);
+  capJoints = grow(capJoints, needJoints, 64);
+  b2gArenaDef def;
+  memset(&def, 0, sizeof(def));
+  int dev = g_defaultDevice;
+  if (dev < 0) {
+    const char* e = getenv("B2G_DEVICE");
+    dev = e ? atoi(e) : 0;
+  }
+  def.device = dev;
+  def.num_worlds = 1;
+  def.max_bodies = capBodies;
+  def.max_fixtures = capFixtures;
+  def.max_shape_quads = capQuads;
+  def.max_contacts = capContacts;
+  def.max_joints = capJoints;
+  b2gCheck(b2g_arena_create(&def, &arena), "b2g_arena_create");
+  b2g_set_profiling(arena, profiling ? 1 : 0);
+  shapesUploaded = 0;
+  bodyDirtyLo = 0;
+  bodyDirtyHi = needBodies;
+  fixtureDirtyLo = 0;
+  fixtureDirtyHi = needFixtures;
+  jointsDirty = needJoints > 0;
+  world->m_newContacts = true;
+}
+
+// upload everything the host changed since the last step
+void b2WorldImpl::flush() {
+  ensureArena();
+  int32 nq = (int32)(shapePool.size() / 4);
+  if (nq > shapesUploaded) {
+    b2gCheck(b2g_upload_shapes(arena, shapesUploaded, nq - shapesUploaded, shapePool.data() + (size_t)shapesUploaded * 4),
+             "b2g_upload_shapes");
+    shapesUploaded = nq;
+  }
+  if (bodyDirtyHi > bodyDirtyLo) {
+    int32 lo = bodyDirtyLo, n = bodyDirtyHi - bodyDirtyLo;
+    std::vector<float> pos((size_t)n * 4), vel((size_t)n * 4), xf((size_t)n * 4), mass((size_t)n * 4),
+        center((size_t)n * 4), force((size_t)n * 4);
+    std::vector<uint32_t> flags(n);
+    std::vector<int32_t> wid(n, 0);
+    for (int32 k = 0; k < n; ++k) {
+      b2Body* b = bodies[lo + k];
+      float* p = &pos[(size_t)k * 4];
+      if (!b) {  // destroyed: a disabled static placeholder
+        flags[k] = 0;
+        continue;
+      }
+      p[0] = b->m_sweep.c.x; p[1] = b->m_sweep.c.y; p[2] = b->m_sweep.a; p[3] = 0.0f;
+      float* v = &vel[(size_t)k * 4];
+      v[0] = b->m_linearVelocity.x; v[1] = b->m_linearVelocity.y; v[2] = b->m_angularVelocity; v[3] = 0.0f;
+      float* x = &xf[(size_t)k * 4];
+      x[0] = b->m_xf.p.x; x[1] = b->m_xf.p.y; x[2] = b->m_xf.q.s; x[3] = b->m_xf.q.c;
+      float* m = &mass[(size_t)k * 4];
+      m[0] = b->m_invMass; m[1] = b->m_invI; m[2] = b->m_mass; m[3] = b->m_gravityScale;
+      float* c = &center[(size_t)k * 4];
+      c[0] = b->m_sweep.localCenter.x; c[1] = b->m_sweep.localCenter.y; c[2] = b->m_linearDamping;
+      c[3] = b->m_angularDamping;
+      float* f = &force[(size_t)k * 4];
+      f[0] = b->m_force.x; f[1] = b->m_force.y; f[2] = b->m_torque; f[3] = b->m_sleepTime;
+      flags[k] = (uint32_t)(b->m_flags & ~b2Body::e_islandFlag) | ((uint32_t)b->m_type << B2G_BODY_TYPE_SHIFT);
+    }
+    b2gBodyArrays a;
+    a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.mass = mass.data(); a.center = center.data();
+    a.force = force.data(); a.flags = flags.data(); a.world = wid.data();
+    b2gCheck(b2g_upload_bodies(arena, lo, n, &a), "b2g_upload_bodies");
+    bodyDirtyLo = INT32_MAX;
+    bodyDirtyHi = 0;
+  }
+  if (fixtureDirtyHi > fixtureDirtyLo) {
+    int32 lo = fixtureDirtyLo, n = fixtureDirtyHi - fixtureDirtyLo;
+    std::vector<int32_t> body(n), off(n);
+    std::vector<uint32_t> tf(n), filter((size_t)n * 2);
+    std::vector<float> mat((size_t)n * 4);
+    for (int32 k = 0; k < n; ++k) {
+      b2Fixture* f = fixtures[lo + k];
+      if (!f) {
+        body[k] = 0; off[k] = 0; tf[k] = B2G_FIX_DEAD;
+        continue;
+      }
+      body[k] = f->m_body->m_index;
+      off[k] = f->m_shapeOff;
+      tf[k] = (uint32_t)f->m_shape->GetType() | (f->m_isSensor ? B2G_FIX_SENSOR : 0u);
+      filter[(size_t)k * 2] = (uint32_t)f->m_filter.categoryBits | ((uint32_t)f->m_filter.maskBits << 16);
+      filter[(size_t)k * 2 + 1] = (uint32_t)(int32_t)f->m_filter.groupIndex;
+      mat[(size_t)k * 4] = f->m_friction; mat[(size_t)k * 4 + 1] = f->m_restitution;
+      mat[(size_t)k * 4 + 2] = f->m_restitutionThreshold; mat[(size_t)k * 4 + 3] = f->m_density;
+    }
+    b2gFixtureArrays a;
+    a.body = body.data(); a.shape_off = off.data(); a.type_flags = tf.data(); a.filter = filter.data();
+    a.material = mat.data();
+    b2gCheck(b2g_upload_fixtures(arena, lo, n, &a), "b2g_upload_fixtures");
+    fixtureDirtyLo = INT32_MAX;
+    fixtureDirtyHi = 0;
+  }
+  if (jointsDirty) {
+    int32 n = (int32)joints.size();
+    std::vector<int32_t> jb((size_t)n * 2);
+    std::vector<float> anchors((size_t)n * 4), params((size_t)n * 8, 0.0f);
+    for (int32 k = 0; k < n; ++k) {
+      b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(joints[k]);
+      jb[(size_t)k * 2] = j->m_bodyA->m_index;
+      jb[(size_t)k * 2 + 1] = j->m_bodyB->m_index;
+      anchors[(size_t)k * 4] = j->m_localAnchorA.x; anchors[(size_t)k * 4 + 1] = j->m_localAnchorA.y;
+      anchors[(size_t)k * 4 + 2] = j->m_localAnchorB.x; anchors[(size_t)k * 4 + 3] = j->m_localAnchorB.y;
+      float* p = &params[(size_t)k * 8];
+      p[0] = j->m_referenceAngle; p[1] = j->m_lowerAngle; p[2] = j->m_upperAngle; p[3] = j->m_maxMotorTorque;
+      p[4] = j->m_motorSpeed;
+      uint32_t fl = (j->m_enableLimit ? 1u : 0u) | (j->m_enableMotor ? 2u : 0u) | (j->m_collideConnected ? 4u : 0u);
+      memcpy(&p[5], &fl, 4);
+    }
+    b2gJointArrays a;
+    a.bodies = jb.data(); a.anchors = anchors.data(); a.params = params.data();
+    if (n > 0) b2gCheck(b2g_upload_joints(arena, 0, n, &a), "b2g_upload_joints");
+    jointsDirty = false;
+  }
+}
+
+void b2WorldImpl::pullBodies() {
+  if (!bodiesStale || !arena) return;
+  bodiesStale = false;
+  int32 n = (int32)bodies.size();
+  if (n == 0) return;
+  std::vector<float> pos((size_t)n * 4), vel((size_t)n * 4), xf((size_t)n * 4), force((size_t)n * 4);
+  std::vector<uint32_t> flags(n);
+  b2gBodyArrays a;
+  memset(&a, 0, sizeof(a));
+  a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.force = force.data(); a.flags = flags.data();
+  b2gCheck(b2g_download_bodies(arena, 0, n, &a), "b2g_download_bodies");
+  for (int32 i = 0; i < n; ++i) {
+    b2Body* b = bodies[i];
+    if (!b) continue;
+    b->m_sweep.c.Set(pos[(size_t)i * 4], pos[(size_t)i * 4 + 1]);
+    b->m_sweep.a = pos[(size_t)i * 4 + 2];
+    b->m_sweep.c0 = b->m_sweep.c;
+    b->m_sweep.a0 = b->m_sweep.a;
+    b->m_linearVelocity.Set(vel[(size_t)i * 4], vel[(size_t)i * 4 + 1]);
+    b->m_angularVelocity = vel[(size_t)i * 4 + 2];
+    b->m_xf.p.Set(xf[(size_t)i * 4], xf[(size_t)i * 4 + 1]);
+    b->m_xf.q.s = xf[(size_t)i * 4 + 2];
+    b->m_xf.q.c = xf[(size_t)i * 4 + 3];
+    b->m_force.Set(force[(size_t)i * 4], force[(size_t)i * 4 + 1]);
+    b->m_torque = force[(size_t)i * 4 + 2];
+    b->m_sleepTime = force[(size_t)i * 4 + 3];
+    uint16 keep = b->m_flags & ~(uint16)b2Body::e_awakeFlag;
+    b->m_flags = keep | (uint16)(flags[i] & B2G_BODY_AWAKE);
+  }
+}
+
+static void unpackManifold(b2Manifold& m, const float* q) {
+  m.localNormal.Set(q[0], q[1]);
+  m.localPoint.Set(q[2], q[3]);
+  for (int k = 0; k < 2; ++k) {
+    m.points[k].localPoint.Set(q[4 + 4 * k], q[5 + 4 * k]);
+    m.points[k].normalImpulse = q[6 + 4 * k];
+    m.points[k].tangentImpulse = q[7 + 4 * k];
+    memcpy(&m.points[k].id.key, &q[12 + k], 4);
+  }
+  int32 type, count;
+  memcpy(&type, &q[14], 4);
+  memcpy(&count, &q[15], 4);
+  m.type = (b2Manifold::Type)type;
+  m.pointCount = count;
+}
+
+// rebuild the host contact list (b2World::GetContactListStart, b2Body::GetContact) from the device
+void b2WorldImpl::pullContacts() {
+  if (!contactsStale) return;
+  contactsStale = false;
+  for (b2Body* b : bodies)
+    if (b) b->m_contacts.clear();
+  int32 n = 0;
+  if (arena) b2gCheck(b2g_contact_count(arena, &n), "b2g_contact_count");
+  std::vector<int32_t> fa(n), fb(n);
+  std::vector<uint32_t> flags(n);
+  std::vector<float> man((size_t)n * 16), mat((size_t)n * 4);
+  if (n > 0) {
+    b2gContactArrays a;
+    memset(&a, 0, sizeof(a));
+    a.fixture_a = fa.data(); a.fixture_b = fb.data(); a.flags = flags.data(); a.manifold = man.data();
+    a.material = mat.data();
+    b2gCheck(b2g_download_contacts(arena, 0, n, &a), "b2g_download_contacts");
+  }
+  std::unordered_map<uint64_t, b2Contact*> next;
+  next.reserve((size_t)n * 2 + 1);
+  contacts.assign(n, nullptr);
+  for (int32 i = 0; i < n; ++i) {
+    uint64_t k = key(fa[i], fb[i]);
+    b2Contact* c;
+    auto it = contactPool.find(k);
+    if (it != contactPool.end()) {
+      c = it->second;
+      contactPool.erase(it);
+    } else {
+      c = new b2Contact();
+      c->m_world = world;
+      c->m_fixtureA = fixtures[fa[i]];
+      c->m_fixtureB = fixtures[fb[i]];
+    }
+    c->m_flags = flags[i];
+    unpackManifold(c->m_manifold, &man[(size_t)i * 16]);
+    c->m_friction = mat[(size_t)i * 4];
+    c->m_restitution = mat[(size_t)i * 4 + 1];
+    c->m_restitutionThreshold = mat[(size_t)i * 4 + 2];
+    c->m_tangentSpeed = mat[(size_t)i * 4 + 3];
+    c->m_deviceIndex = i;
+    c->m_overridden = false;
+    contacts[i] = c;
+    next.emplace(k, c);
+    c->m_fixtureA->m_body->m_contacts.push_back(c);
+    c->m_fixtureB->m_body->m_contacts.push_back(c);
+  }
+  for (auto& kv : contactPool) graveyard.push_back(kv.second);  // contacts that died: freed by Step
+  contactPool.swap(next);
+  // ring: sentinel <-> c0 <-> c1 ... <-> sentinel (b2_contact_manager.h: Start()/End())
+  b2Contact* prev = &sentinel;
+  for (b2Contact* c : contacts) {
+    prev->m_next = c;
+    c->m_prev = prev;
+    prev = c;
+  }
+  prev->m_next = &sentinel;
+  sentinel.m_prev = prev;
+}
+
+b2Contact* b2WorldImpl::findContact(int32 fa, int32 fb) {
+  auto it = contactPool.find(key(fa, fb));
+  return it == contactPool.end() ? nullptr : it->second;
+}
+
+void b2WorldImpl::pushContactOverrides() {
+  int32 n = (int32)contacts.size();
+  int32 lo = n, hi = 0;
+  for (int32 i = 0; i < n; ++i)
+    if (contacts[i]->m_overridden) {
+      lo = std::min(lo, i);
+      hi = std::max(hi, i + 1);
+    }
+  if (hi <= lo) return;
+  std::vector<uint32_t> flags(hi - lo);
+  std::vector<float> mat((size_t)(hi - lo) * 4);
+  for (int32 i = lo; i < hi; ++i) {
+    b2Contact* c = contacts[i];
+    flags[i - lo] = c->m_flags;
+    float* m = &mat[(size_t)(i - lo) * 4];
+    m[0] = c->m_friction; m[1] = c->m_restitution; m[2] = c->m_restitutionThreshold; m[3] = c->m_tangentSpeed;
+    c->m_overridden = false;
+  }
+  b2gCheck(b2g_upload_contact_overrides(arena, lo, hi - lo, flags.data(), mat.data()), "b2g_upload_contact_overrides");
+}
+
+// ================================================================================================
+// b2World
+// ================================================================================================
+void b2World::SetDefaultCapacity(int32 bodies, int32 fixtures, int32 contacts) {
+  g_defaultBodies = std::max(bodies, 16);
+  g_defaultFixtures = std::max(fixtures, 16);
+  g_defaultContacts = std::max(contacts, 64);
+}
+void b2World::SetDefaultDevice(int32 device) { g_defaultDevice = device; }
+
+b2World::b2World(const b2Vec2& gravity) {
+  m_impl = new b2WorldImpl();
+  m_impl->world = this;
+  memset(&m_impl->lastStats, 0, sizeof(b2gStepStats));
+  m_impl->sentinel.m_next = m_impl->sentinel.m_prev = &m_impl->sentinel;
+  m_impl->sentinel.m_fixtureA = m_impl->sentinel.m_fixtureB = nullptr;
+  m_bodyListHead = m_bodyListTail = nullptr;
+  m_jointList = nullptr;
+  m_bodyCount = 0;
+  m_jointCount = 0;
+  m_gravity = gravity;
+  m_allowSleep = true;
+  m_destructionListener = nullptr;
+  m_contactFilter = nullptr;
+  m_contactListener = nullptr;
+  m_newContacts = false;
+  m_locked = false;
+  m_clearForces = true;
+  m_warmStarting = true;
+  m_continuousPhysics = true;
+  m_subStepping = false;
+  m_solverMode = B2G_SOLVER_COLOURED;
+  memset(&m_profile, 0, sizeof(m_profile));
+}
+
+b2World::~b2World() {
+  for (b2Body* b : m_impl->bodies) {
+    if (!b) continue;
+    b2Fixture* f = b->m_fixtureList;
+    while (f) {
+      b2Fixture* nx = f->m_next;
+      delete f->m_shape;
+      delete f;
+      f = nx;
+    }
+    delete b;
+  }
+  for (b2Joint* j : m_impl->joints) delete j;
+  for (auto& kv : m_impl->contactPool) delete kv.second;
+  for (b2Contact* c : m_impl->graveyard) delete c;
+  if (m_impl->arena) b2g_arena_destroy(m_impl->arena);
+  delete m_impl;
+}
+
+void b2World::SetProfiling(bool flag) {
+  m_impl->profiling = flag;
+  if (m_impl->arena) b2g_set_profiling(m_impl->arena, flag ? 1 : 0);
+}
+
+void b2World::SetAllowSleeping(bool flag) {
+  if (flag == m_allowSleep) return;
+  m_allowSleep = flag;
+  if (!m_allowSleep)
+    for (b2Body* b = m_bodyListHead; b; b = b->m_next) b->SetAwake(true);
+}
+
+b2Body* b2World::CreateBody(const b2BodyDef* def) {
+  if (IsLocked()) return nullptr;
+  b2Body* b = new b2Body(def, this);
+  b->m_index = (int32)m_impl->bodies.size();
+  m_impl->bodies.push_back(b);
+  m_impl->touchBody(b->m_index);
+  // static bodies go to the tail, everything else to the head (b2_world.cpp:153-171)
+  if (m_bodyListHead == nullptr) {
+    m_bodyListHead = m_bodyListTail = b;
+  } else if (def->type == b2_staticBody) {
+    b->m_prev = m_bodyListTail;
+    m_bodyListTail->m_next = b;
+    m_bodyListTail = b;
+  } else {
+    b->m_next = m_bodyListHead;
+    m_bodyListHead->m_prev = b;
+    m_bodyListHead = b;
+  }
+  ++m_bodyCount;
+  return b;
+}
+
+void b2World::DestroyBody(b2Body* b) {
+  if (IsLocked() || !b) return;
+  m_impl->pullBodies();
+  // joints attached to the body go first (b2_world.cpp:190-204)
+  b2JointEdge* je = b->m_jointList;
+  while (je) {
+    b2JointEdge* je0 = je;
+    je = je->next;
+    if (m_destructionListener) m_destructionListener->SayGoodbye(je0->joint);
+    DestroyJoint(je0->joint);
+  }
+  b2Fixture* f = b->m_fixtureList;
+  while (f) {
+    b2Fixture* nx = f->m_next;
+    if (m_destructionListener) m_destructionListener->SayGoodbye(f);
+    m_impl->fixtures[f->m_index] = nullptr;
+    m_impl->touchFixture(f->m_index);
+    delete f->m_shape;
+    delete f;
+    f = nx;
+  }
+  if (b->m_prev) b->m_prev->m_next = b->m_next;
+  if (b->m_next) b->m_next->m_prev = b->m_prev;
+  if (b == m_bodyListHead) m_bodyListHead = b->m_next;
+  if (b == m_bodyListTail) m_bodyListTail = b->m_prev;
+  m_impl->bodies[b->m_index] = nullptr;
+  m_impl->touchBody(b->m_index);
+  // host contact handles may point at the dead fixtures: drop them all, they are rebuilt lazily
+  for (auto& kv : m_impl->contactPool) delete kv.second;
+  m_impl->contactPool.clear();
+  m_impl->contacts.clear();
+  m_impl->contactsStale = true;
+  m_newContacts = true;
+  --m_bodyCount;
+  delete b;
+}
+
+b2Joint* b2World::CreateJoint(const b2JointDef* def) {
+  if (IsLocked()) return nullptr;
+  if (def->type != e_revoluteJoint) {
+    fprintf(stderr, "[b2cuda] only revolute joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
+            (int)def->type);
+    return nullptr;
+  }
+  b2RevoluteJoint* j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
+  j->m_index = (int32)m_impl->joints.size();
+  m_impl->joints.push_back(j);
+  m_impl->jointsDirty = true;
+  j->m_prev = nullptr;
+  j->m_next = m_jointList;
+  if (m_jointList) m_jointList->m_prev = j;
+  m_jointList = j;
+  ++m_jointCount;
+  // connect to the bodies' joint lists (b2_world.cpp:291-305)
+  j->m_edgeA.joint = j;
+  j->m_edgeA.other = j->m_bodyB;
+  j->m_edgeA.prev = nullptr;
+  j->m_edgeA.next = j->m_bodyA->m_jointList;
+  if (j->m_bodyA->m_jointList) j->m_bodyA->m_jointList->prev = &j->m_edgeA;
+  j->m_bodyA->m_jointList = &j->m_edgeA;
+  j->m_edgeB.joint = j;
+  j->m_edgeB.other = j->m_bodyA;
+  j->m_edgeB.prev = nullptr;
+  j->m_edgeB.next = j->m_bodyB->m_jointList;
+  if (j->m_bodyB->m_jointList) j->m_bodyB->m_jointList->prev = &j->m_edgeB;
+  j->m_bodyB->m_jointList = &j->m_edgeB;
+  return j;
+}
+
+void b2World::DestroyJoint(b2Joint* j) {
+  if (IsLocked() || !j) return;
+  if (j->m_prev) j->m_prev->m_next = j->m_next;
+  if (j->m_next) j->m_next->m_prev = j->m_prev;
+  if (j == m_jointList) m_jointList = j->m_next;
+  b2Body* bodyA = j->m_bodyA;
+  b2Body* bodyB = j->m_bodyB;
+  bodyA->SetAwake(true);
+  bodyB->SetAwake(true);
+  if (j->m_edgeA.prev) j->m_edgeA.prev->next = j->m_edgeA.next;
+  if (j->m_edgeA.next) j->m_edgeA.next->prev = j->m_edgeA.prev;
+  if (&j->m_edgeA == bodyA->m_jointList) bodyA->m_jointList = j->m_edgeA.next;
+  if (j->m_edgeB.prev) j->m_edgeB.prev->next = j->m_edgeB.next;
+  if (j->m_edgeB.next) j->m_edgeB.next->prev = j->m_edgeB.prev;
+  if (&j->m_edgeB == bodyB->m_jointList) bodyB->m_jointList = j->m_edgeB.next;
+  auto& js = m_impl->joints;
+  js.erase(std::find(js.begin(), js.end(), j));
+  for (int32 i = 0; i < (int32)js.size(); ++i) js[i]->m_index = i;
+  m_impl->jointsDirty = true;
+  if (m_impl->arena) b2g_set_counts(m_impl->arena, (int32)m_impl->bodies.size(), (int32)m_impl->fixtures.size(), (int32)js.size());
+  --m_jointCount;
+  delete j;
+}
+
+void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations, int32 particleIterations) {
+  B2_NOT_USED(particleIterations);
+  if (m_locked) return;
+  m_locked = true;
+  b2WorldImpl* I = m_impl;
+  I->flush();
+  if (I->arena == nullptr) {
+    m_locked = false;
+    return;
+  }
+  // new fixtures / moved bodies: refresh the pair list first (b2_world.cpp:1114-1122)
+  if (m_newContacts) {
+    b2gCheck(b2g_find_new_contacts(I->arena), "b2g_find_new_contacts");
+    m_newContacts = false;
+    I->contactsStale = true;
+  }
+  b2gStepParams P;
+  P.dt = dt;
+  P.velocity_iterations = velocityIterations;
+  P.position_iterations = positionIterations;
+  P.gravity_x = m_gravity.x;
+  P.gravity_y = m_gravity.y;
+  P.warm_starting = m_warmStarting ? 1 : 0;
+  P.allow_sleep = m_allowSleep ? 1 : 0;
+  P.clear_forces = m_clearForces ? 1 : 0;
+  P.solver_mode = m_solverMode;
+  P.record_events = m_contactListener ? 1 : 0;
+
+  if (m_contactListener == nullptr) {
+    b2gCheck(b2g_step(I->arena, &P, &I->lastStats), "b2g_step");
+  } else {
+    // callbacks need the contact list between Collide and Solve (b2_contact.cpp:197-209)
+    I->pullContacts();  // previous manifolds, for PreSolve's oldManifold
+    std::unordered_map<b2Contact*, b2Manifold> oldManifolds;
+    for (b2Contact* c : I->contacts) oldManifolds.emplace(c, c->m_manifold);
+    b2gCheck(b2g_step_collide(I->arena, &P), "b2g_step_collide");
+    b2gCheck(b2g_synchronize(I->arena), "b2g_synchronize");
+    std::vector<uint8_t> wasTouching(I->contacts.size());
+    for (size_t i = 0; i < I->contacts.size(); ++i) wasTouching[i] = I->contacts[i]->IsTouching();
+    I->contactsStale = true;
+    I->pullContacts();
+    I->bodiesStale = true;
+    for (size_t i = 0; i < I->contacts.size(); ++i) {
+      b2Contact* c = I->contacts[i];
+      bool touching = c->IsTouching();
+      bool sensor = c->m_fixtureA->IsSensor() || c->m_fixtureB->IsSensor();
+      if (!wasTouching[i] && touching) m_contactListener->BeginContact(c);
+      if (wasTouching[i] && !touching) m_contactListener->EndContact(c);
+      if (!sensor && touching) {
+        b2Body* bA = c->m_fixtureA->m_body;
+        b2Body* bB = c->m_fixtureB->m_body;
+        bool active = (bA->IsAwake() && bA->m_type != b2_staticBody) || (bB->IsAwake() && bB->m_type != b2_staticBody);
+        if (active) {
+          auto it = oldManifolds.find(c);
+          b2Manifold empty;
+          memset(&empty, 0, sizeof(empty));
+          m_contactListener->PreSolve(c, it != oldManifolds.end() ? &it->second : &empty);
+        }
+      }
+    }
+    I->pushContactOverrides();
+    b2gCheck(b2g_step_solve(I->arena, &P, &I->lastStats), "b2g_step_solve");
+    // the broadphase at the end of the step rebuilt the list; handles of contacts that died are
+    // parked in the graveyard (still valid) until the callbacks below have run
+    I->contactsStale = true;
+    I->pullContacts();
+    // PostSolve for the contacts the solver processed (b2_island.cpp:621-647), device order
+    for (b2Contact* c : I->contacts) {
+      if (c->IsTouching() && c->IsEnabled() && !c->m_fixtureA->IsSensor() && !c->m_fixtureB->IsSensor()) {
+        b2ContactImpulse imp;
+        imp.count = c->m_manifold.pointCount;
+        for (int32 k = 0; k < imp.count; ++k) {
+          imp.normalImpulses[k] = c->m_manifold.points[k].normalImpulse;
+          imp.tangentImpulses[k] = c->m_manifold.points[k].tangentImpulse;
+        }
+        m_contactListener->PostSolve(c, &imp);
+      }
+    }
+    // EndContact for touching contacts destroyed by the broadphase (b2_contact_manager.cpp:48-51)
+    for (b2Contact* c : I->graveyard)
+      if (c->IsTouching()) m_contactListener->EndContact(c);
+  }
+  for (b2Contact* c : I->graveyard) delete c;
+  I->graveyard.clear();
+  I->bodiesStale = true;
+  I->contactsStale = true;
+  if (I->profiling) {
+    m_profile.step = I->lastStats.ms_step;
+    m_profile.collide = I->lastStats.ms_collide;
+    m_profile.solve = I->lastStats.ms_solve + I->lastStats.ms_broadphase;  // the reference's solve includes it
+    m_profile.broadphase = I->lastStats.ms_broadphase;
+    m_profile.solveTOI = 0.0f;
+  }
+  m_locked = false;
+}
+
+void b2World::ClearForces() {
+  m_impl->pullBodies();
+  for (b2Body* b = m_bodyListHead; b; b = b->m_next) {
+    if (b->m_force.x != 0.0f || b->m_force.y != 0.0f || b->m_torque != 0.0f) {
+      b->m_force.SetZero();
+      b->m_torque = 0.0f;
+      m_impl->touchBody(b->m_index);
+    }
+  }
+}
+
+b2Contact* b2World::GetContactListStart() {
+  if (m_newContacts && !m_locked) {
+    // the reference creates contacts lazily at the next Step; the handles only exist after it
+  }
+  m_impl->pullContacts();
+  return m_impl->sentinel.m_next;
+}
+b2Contact* b2World::GetContactListEnd() { return &m_impl->sentinel; }
+int32 b2World::GetContactCount() const {
+  int32 n = 0;
+  if (m_impl->arena) b2g_contact_count(m_impl->arena, &n);
+  return n;
+}
+int32 b2World::GetProxyCount() const {
+  int32 n = 0;
+  for (b2Fixture* f : m_impl->fixtures)
+    if (f) ++n;
+  return n;
+}
+
+// ================================================================================================
+// b2Body
+// ================================================================================================
+b2Body::b2Body(const b2BodyDef* bd, b2World* world) {
+  m_flags = 0;
+  if (bd->bullet) m_flags |= e_bulletFlag;
+  if (bd->fixedRotation) m_flags |= e_fixedRotationFlag;
+  if (bd->allowSleep) m_flags |= e_autoSleepFlag;
+  if (bd->awake && bd->type != b2_staticBody) m_flags |= e_awakeFlag;
+  if (bd->enabled) m_flags |= e_enabledFlag;
+  m_world = world;
+  m_xf.p = bd->position;
+  m_xf.q.Set(bd->angle);
+  m_sweep.localCenter.SetZero();
+  m_sweep.c0 = m_xf.p;
+  m_sweep.c = m_xf.p;
+  m_sweep.a0 = bd->angle;
+  m_sweep.a = bd->angle;
+  m_sweep.alpha0 = 0.0f;
+  m_jointList = nullptr;
+  m_prev = nullptr;
+  m_next = nullptr;
+  m_linearVelocity = bd->linearVelocity;
+  m_angularVelocity = bd->angularVelocity;
+  m_linearDamping = bd->linearDamping;
+  m_angularDamping = bd->angularDamping;
+  m_gravityScale = bd->gravityScale;
+  m_force.SetZero();
+  m_torque = 0.0f;
+  m_sleepTime = 0.0f;
+  m_type = bd->type;
+  m_mass = 0.0f;
+  m_invMass = 0.0f;
+  m_I = 0.0f;
+  m_invI = 0.0f;
+  m_userData = bd->userData;
+  m_fixtureList = nullptr;
+  m_fixtureCount = 0;
+  m_index = -1;
+}
+
+void b2Body::SyncIn() const { m_world->m_impl->pullBodies(); }
+void b2Body::Touch() {
+  m_world->m_impl->pullBodies();
+  m_world->m_impl->touchBody(m_index);
+}
+
+b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
+  if (m_world->IsLocked()) return nullptr;
+  Touch();
+  b2WorldImpl* I = m_world->m_impl;
+  b2Fixture* f = new b2Fixture();
+  f->m_userData = def->userData;
+  f->m_friction = def->friction;
+  f->m_restitution = def->restitution;
+  f->m_restitutionThreshold = def->restitutionThreshold;
+  f->m_body = this;
+  f->m_filter = def->filter;
+  f->m_isSensor = def->isSensor;
+  f->m_shape = def->shape->Clone();
+  f->m_density = def->density;
+  f->m_id = g_fixtureIdCounter++;
+  f->m_index = (int32)I->fixtures.size();
+  I->fixtures.push_back(f);
+  I->touchFixture(f->m_index);
+  int32 nq = f->m_shape->DeviceQuadCount();
+  f->m_shapeOff = (int32)(I->shapePool.size() / 4);
+  I->shapePool.resize(I->shapePool.size() + (size_t)nq * 4);
+  f->m_shape->WriteDeviceQuads(&I->shapePool[(size_t)f->m_shapeOff * 4]);
+  f->m_next = m_fixtureList;
+  m_fixtureList = f;
+  ++m_fixtureCount;
+  if (f->m_density > 0.0f) ResetMassData();
+  f->m_shape->ComputeAABB(&f->m_aabb, m_xf);
+  m_world->m_newContacts = true;
+  return f;
+}
+
+b2Fixture* b2Body::CreateFixture(const b2Shape* shape, float density) {
+  b2FixtureDef def;
+  def.shape = shape;
+  def.density = density;
+  return CreateFixture(&def);
+}
+
+void b2Body::DestroyFixture(b2Fixture* fixture) {
+  if (fixture == nullptr || m_world->IsLocked()) return;
+  Touch();
+  b2WorldImpl* I = m_world->m_impl;
+  b2Fixture** node = &m_fixtureList;
+  while (*node != nullptr) {
+    if (*node == fixture) {
+      *node = fixture->m_next;
+      break;
+    }
+    node = &(*node)->m_next;
+  }
+  I->fixtures[fixture->m_index] = nullptr;
+  I->touchFixture(fixture->m_index);
+  for (auto& kv : I->contactPool) delete kv.second;
+  I->contactPool.clear();
+  I->contacts.clear();
+  I->contactsStale = true;
+  m_world->m_newContacts = true;
+  delete fixture->m_shape;
+  delete fixture;
+  --m_fixtureCount;
+  ResetMassData();
+}
+
+void b2Body::ResetMassData() {
+  Touch();
+  m_mass = 0.0f;
+  m_invMass = 0.0f;
+  m_I = 0.0f;
+  m_invI = 0.0f;
+  m_sweep.localCenter.SetZero();
+  if (m_type == b2_staticBody || m_type == b2_kinematicBody) {
+    m_sweep.c0 = m_xf.p;
+    m_sweep.c = m_xf.p;
+    m_sweep.a0 = m_sweep.a;
+    return;
+  }
+  b2Vec2 localCenter = b2Vec2_zero;
+  for (b2Fixture* f = m_fixtureList; f; f = f->m_next) {
+    if (f->m_density == 0.0f) continue;
+    b2MassData massData;
+    f->GetMassData(&massData);
+    m_mass += massData.mass;
+    localCenter += massData.mass * massData.center;
+    m_I += massData.I;
+  }
+  if (m_mass > 0.0f) {
+    m_invMass = 1.0f / m_mass;
+    localCenter *= m_invMass;
+  }
+  if (m_I > 0.0f && (m_flags & e_fixedRotationFlag) == 0) {
+    m_I -= m_mass * b2Dot(localCenter, localCenter);
+    m_invI = 1.0f / m_I;
+  } else {
+    m_I = 0.0f;
+    m_invI = 0.0f;
+  }
+  b2Vec2 oldCenter = m_sweep.c;
+  m_sweep.localCenter = localCenter;
+  m_sweep.c0 = m_sweep.c = b2Mul(m_xf, m_sweep.localCenter);
+  m_linearVelocity += b2Cross(m_angularVelocity, m_sweep.c - oldCenter);
+}
+
+void b2Body::SetMassData(const b2MassData* massData) {
+  if (m_world->IsLocked() || m_type != b2_dynamicBody) return;
+  Touch();
+  m_invMass = 0.0f;
+  m_I = 0.0f;
+  m_invI = 0.0f;
+  m_mass = massData->mass;
+  if (m_mass <= 0.0f) m_mass = 1.0f;
+  m_invMass = 1.0f / m_mass;
+  if (massData->I > 0.0f && (m_flags & e_fixedRotationFlag) == 0) {
+    m_I = massData->I - m_mass * b2Dot(massData->center, massData->center);
+    m_invI = 1.0f / m_I;
+  }
+  b2Vec2 oldCenter = m_sweep.c;
+  m_sweep.localCenter = massData->center;
+  m_sweep.c0 = m_sweep.c = b2Mul(m_xf, m_sweep.localCenter);
+  m_linearVelocity += b2Cross(m_angularVelocity, m_sweep.c - oldCenter);
+}
+
+void b2Body::GetMassData(b2MassData* data) const {
+  data->mass = m_mass;
+  data->I = m_I + m_mass * b2Dot(m_sweep.localCenter, m_sweep.localCenter);
+  data->center = m_sweep.localCenter;
+}
+float b2Body::GetInertia() const { return m_I + m_mass * b2Dot(m_sweep.localCenter, m_sweep.localCenter); }
+
+void b2Body::SetTransform(const b2Vec2& position, float angle) {
+  if (m_world->IsLocked()) return;
+  Touch();
+  m_xf.q.Set(angle);
+  m_xf.p = position;
+  m_sweep.c = b2Mul(m_xf, m_sweep.localCenter);
+  m_sweep.a = angle;
+  m_sweep.c0 = m_sweep.c;
+  m_sweep.a0 = angle;
+  UpdateAABBs();
+  m_world->m_newContacts = true;
+}
+
+void b2Body::UpdateAABBs() {
+  for (b2Fixture* f = m_fixtureList; f; f = f->m_next) f->m_shape->ComputeAABB(&f->m_aabb, m_xf);
+}
+
+const b2Transform& b2Body::GetTransform() const { SyncIn(); return m_xf; }
+const b2Vec2& b2Body::GetPosition() const { SyncIn(); return m_xf.p; }
+float b2Body::GetAngle() const { SyncIn(); return m_sweep.a; }
+const b2Vec2& b2Body::GetWorldCenter() const { SyncIn(); return m_sweep.c; }
+const b2Vec2& b2Body::GetLocalCenter() const { return m_sweep.localCenter; }
+const b2Vec2& b2Body::GetLinearVelocity() const { SyncIn(); return m_linearVelocity; }
+float b2Body::GetAngularVelocity() const { SyncIn(); return m_angularVelocity; }
+b2Vec2 b2Body::GetLinearVelocityFromWorldPoint(const b2Vec2& worldPoint) const {
+  SyncIn();
+  return m_linearVelocity + b2Cross(m_angularVelocity, worldPoint - m_sweep.c);
+}
+
+void b2Body::SetLinearVelocity(const b2Vec2& v) {
+  if (m_type == b2_staticBody) return;
+  Touch();
+  if (b2Dot(v, v) > 0.0f) SetAwake(true);
+  m_linearVelocity = v;
+}
+void b2Body::SetAngularVelocity(float w) {
+  if (m_type == b2_staticBody) return;
+  Touch();
+  if (w * w > 0.0f) SetAwake(true);
+  m_angularVelocity = w;
+}
+void b2Body::ApplyForce(const b2Vec2& force, const b2Vec2& point, bool wake) {
+  if (m_type != b2_dynamicBody) return;
+  Touch();
+  if (wake && (m_flags & e_awakeFlag) == 0) SetAwake(true);
+  if (m_flags & e_awakeFlag) {
+    m_force += force;
+    m_torque += b2Cross(point - m_sweep.c, force);
+  }
+}
+void b2Body::ApplyForceToCenter(const b2Vec2& force, bool wake) {
+  if (m_type != b2_dynamicBody) return;
+  Touch();
+  if (wake && (m_flags & e_awakeFlag) == 0) SetAwake(true);
+  if (m_flags & e_awakeFlag) m_force += force;
+}
+void b2Body::ApplyTorque(float torque, bool wake) {
+  if (m_type != b2_dynamicBody) return;
+  Touch();
+  if (wake && (m_flags & e_awakeFlag) == 0) SetAwake(true);
+  if (m_flags & e_awakeFlag) m_torque += torque;
+}
+void b2Body::ApplyLinearImpulse(const b2Vec2& impulse, const b2Vec2& point, bool wake) {
+  if (m_type != b2_dynamicBody) return;
+  Touch();
+  if (wake && (m_flags & e_awakeFlag) == 0) SetAwake(true);
+  if (m_flags & e_awakeFlag) {
+    m_linearVelocity += m_invMass * impulse;
+    m_angularVelocity += m_invI * b2Cross(point - m_sweep.c, impulse);
+  }
+}
+void b2Body::ApplyLinearImpulseToCenter(const b2Vec2& impulse, bool wake) {
+  if (m_type != b2_dynamicBody) return;
+  Touch();
+  if (wake && (m_flags & e_awakeFlag) == 0) SetAwake(true);
+  if (m_flags & e_awakeFlag) m_linearVelocity += m_invMass * impulse;
+}
+void b2Body::ApplyAngularImpulse(float impulse, bool wake) {
+  if (m_type != b2_dynamicBody) return;
+  Touch();
+  if (wake && (m_flags & e_awakeFlag) == 0) SetAwake(true);
+  if (m_flags & e_awakeFlag) m_angularVelocity += m_invI * impulse;
+}
+void b2Body::SetLinearDamping(float v) { Touch(); m_linearDamping = v; }
+void b2Body::SetAngularDamping(float v) { Touch(); m_angularDamping = v; }
+void b2Body::SetGravityScale(float v) { Touch(); m_gravityScale = v; }
+
+void b2Body::SetType(b2BodyType type) {
+  if (m_world->IsLocked() || m_type == type) return;
+  Touch();
+  b2World* w = m_world;
+  // keep static bodies at the tail of the list (b2_body.cpp:140-188)
+  if (m_prev) m_prev->m_next = m_next;
+  if (m_next) m_next->m_prev = m_prev;
+  if (this == w->m_bodyListHead) w->m_bodyListHead = m_next;
+  if (this == w->m_bodyListTail) w->m_bodyListTail = m_prev;
+  m_prev = m_next = nullptr;
+  if (w->m_bodyListHead == nullptr) {
+    w->m_bodyListHead = w->m_bodyListTail = this;
+  } else if (type == b2_staticBody) {
+    m_prev = w->m_bodyListTail;
+    w->m_bodyListTail->m_next = this;
+    w->m_bodyListTail = this;
+  } else {
+    m_next = w->m_bodyListHead;
+    w->m_bodyListHead->m_prev = this;
+    w->m_bodyListHead = this;
+  }
+  m_type = type;
+  ResetMassData();
+  if (m_type == b2_staticBody) {
+    m_linearVelocity.SetZero();
+    m_angularVelocity = 0.0f;
+    m_sweep.a0 = m_sweep.a;
+    m_sweep.c0 = m_sweep.c;
+    m_flags &= ~e_awakeFlag;
+    UpdateAABBs();
+  }
+  SetAwake(true);
+  m_force.SetZero();
+  m_torque = 0.0f;
+  w->m_newContacts = true;
+}
+
+void b2Body::SetBullet(bool flag) { if (flag) m_flags |= e_bulletFlag; else m_flags &= ~e_bulletFlag; }
+bool b2Body::IsBullet() const { return (m_flags & e_bulletFlag) == e_bulletFlag; }
+void b2Body::SetSleepingAllowed(bool flag) {
+  Touch();
+  if (flag) {
+    m_flags |= e_autoSleepFlag;
+  } else {
+    m_flags &= ~e_autoSleepFlag;
+    SetAwake(true);
+  }
+}
+bool b2Body::IsSleepingAllowed() const { return (m_flags & e_autoSleepFlag) == e_autoSleepFlag; }
+void b2Body::SetAwake(bool flag) {
+  if (m_type == b2_staticBody) return;
+  Touch();
+  if (flag) {
+    m_flags |= e_awakeFlag;
+    m_sleepTime = 0.0f;
+  } else {
+    m_flags &= ~e_awakeFlag;
+    m_sleepTime = 0.0f;
+    m_linearVelocity.SetZero();
+    m_angularVelocity = 0.0f;
+    m_force.SetZero();
+    m_torque = 0.0f;
+  }
+}
+bool b2Body::IsAwake() const { SyncIn(); return (m_flags & e_awakeFlag) == e_awakeFlag; }
+void b2Body::SetEnabled(bool flag) {
+  if (flag == IsEnabled()) return;
+  Touch();
+  if (flag) m_flags |= e_enabledFlag; else m_flags &= ~e_enabledFlag;
+  m_world->m_newContacts = true;
+}
+bool b2Body::IsEnabled() const { return (m_flags & e_enabledFlag) == e_enabledFlag; }
+void b2Body::SetFixedRotation(bool flag) {
+  bool status = (m_flags & e_fixedRotationFlag) == e_fixedRotationFlag;
+  if (status == flag) return;
+  Touch();
+  if (flag) m_flags |= e_fixedRotationFlag; else m_flags &= ~e_fixedRotationFlag;
+  m_angularVelocity = 0.0f;
+  ResetMassData();
+}
+bool b2Body::IsFixedRotation() const { return (m_flags & e_fixedRotationFlag) == e_fixedRotationFlag; }
+int32 b2Body::GetContactCount() {
+  m_world->m_impl->pullContacts();
+  return (int32)m_contacts.size();
+}
+b2Contact* b2Body::GetContact(int32 idx) {
+  m_world->m_impl->pullContacts();
+  return m_contacts[idx];
+}
+bool b2Body::ShouldCollide(const b2Body* other) const {
+  if (m_type != b2_dynamicBody && other->m_type != b2_dynamicBody) return false;
+  for (b2JointEdge* jn = m_jointList; jn; jn = jn->next)
+    if (jn->other == other && jn->joint->GetCollideConnected() == false) return false;
+  return true;
+}
+
+// ================================================================================================
+// b2Fixture / b2Contact / joints / filter
+// ================================================================================================
+void b2Fixture::SetSensor(bool sensor) {
+  if (sensor == m_isSensor) return;
+  m_body->Touch();
+  m_isSensor = sensor;
+  m_body->m_world->m_impl->touchFixture(m_index);
+}
+void b2Fixture::SetFilterData(const b2Filter& filter) {
+  m_filter = filter;
+  Refilter();
+}
+void b2Fixture::Refilter() {
+  // the device re-evaluates the filter for every pair on every broadphase pass, which is the
+  // effect of the reference's e_filterFlag protocol (b2_fixture.cpp:100-136)
+  m_body->m_world->m_impl->touchFixture(m_index);
+  m_body->m_world->m_newContacts = true;
+}
+bool b2Fixture::TestPoint(const b2Vec2& p) const { return m_shape->TestPoint(m_body->GetTransform(), p); }
+void b2Fixture::SetFriction(float v) { m_friction = v; m_body->m_world->m_impl->touchFixture(m_index); }
+void b2Fixture::SetRestitution(float v) { m_restitution = v; m_body->m_world->m_impl->touchFixture(m_index); }
+void b2Fixture::SetRestitutionThreshold(float v) {
+  m_restitutionThreshold = v;
+  m_body->m_world->m_impl->touchFixture(m_index);
+}
+void b2Fixture::UpdateAABB() { m_shape->ComputeAABB(&m_aabb, m_body->GetTransform()); }
+const b2AABB& b2Fixture::GetAABB() const {
+  // static fixtures keep the AABB of their creation transform
+  if (m_body->m_type != b2_staticBody) m_shape->ComputeAABB(&m_aabb, m_body->GetTransform());
+  return m_aabb;
+}
+
+void b2Contact::GetWorldManifold(b2WorldManifold* wm) const {
+  const b2Body* bodyA = m_fixtureA->GetBody();
+  const b2Body* bodyB = m_fixtureB->GetBody();
+  wm->Initialize(&m_manifold, bodyA->GetTransform(), m_fixtureA->GetShape()->m_radius, bodyB->GetTransform(),
+                 m_fixtureB->GetShape()->m_radius);
+}
+void b2Contact::SetEnabled(bool flag) {
+  if (flag) m_flags |= e_enabledFlag; else m_flags &= ~e_enabledFlag;
+  m_overridden = true;
+}
+void b2Contact::SetFriction(float v) { m_friction = v; m_overridden = true; }
+void b2Contact::ResetFriction() { SetFriction(b2MixFriction(m_fixtureA->m_friction, m_fixtureB->m_friction)); }
+void b2Contact::SetRestitution(float v) { m_restitution = v; m_overridden = true; }
+void b2Contact::ResetRestitution() {
+  SetRestitution(b2MixRestitution(m_fixtureA->m_restitution, m_fixtureB->m_restitution));
+}
+void b2Contact::SetRestitutionThreshold(float v) { m_restitutionThreshold = v; m_overridden = true; }
+void b2Contact::ResetRestitutionThreshold() {
+  SetRestitutionThreshold(
+      b2MixRestitutionThreshold(m_fixtureA->m_restitutionThreshold, m_fixtureB->m_restitutionThreshold));
+}
+void b2Contact::SetTangentSpeed(float v) { m_tangentSpeed = v; m_overridden = true; }
+
+bool b2ContactFilter::ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB) {
+  const b2Filter& filterA = fixtureA->GetFilterData();
+  const b2Filter& filterB = fixtureB->GetFilterData();
+  if (filterA.groupIndex == filterB.groupIndex && filterA.groupIndex != 0) return filterA.groupIndex > 0;
+  return (filterA.maskBits & filterB.categoryBits) != 0 && (filterA.categoryBits & filterB.maskBits) != 0;
+}
+
+b2Joint::b2Joint(const b2JointDef* def) {
+  m_type = def->type;
+  m_prev = m_next = nullptr;
+  m_bodyA = def->bodyA;
+  m_bodyB = def->bodyB;
+  m_index = 0;
+  m_collideConnected = def->collideConnected;
+  m_userData = def->userData;
+  m_edgeA.joint = m_edgeB.joint = nullptr;
+  m_edgeA.other = m_edgeB.other = nullptr;
+  m_edgeA.prev = m_edgeA.next = m_edgeB.prev = m_edgeB.next = nullptr;
+}
+
+void b2RevoluteJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor) {
+  bodyA = bA;
+  bodyB = bB;
+  localAnchorA = bodyA->GetLocalPoint(anchor);
+  localAnchorB = bodyB->GetLocalPoint(anchor);
+  referenceAngle = bodyB->GetAngle() - bodyA->GetAngle();
+}
+
+b2RevoluteJoint::b2RevoluteJoint(const b2RevoluteJointDef* def) : b2Joint(def) {
+  m_localAnchorA = def->localAnchorA;
+  m_localAnchorB = def->localAnchorB;
+  m_referenceAngle = def->referenceAngle;
+  m_lowerAngle = def->lowerAngle;
+  m_upperAngle = def->upperAngle;
+  m_maxMotorTorque = def->maxMotorTorque;
+  m_motorSpeed = def->motorSpeed;
+  m_enableLimit = def->enableLimit;
+  m_enableMotor = def->enableMotor;
+}
+b2Vec2 b2RevoluteJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2RevoluteJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+float b2RevoluteJoint::GetJointAngle() const { return m_bodyB->GetAngle() - m_bodyA->GetAngle() - m_referenceAngle; }
+float b2RevoluteJoint::GetJointSpeed() const { return m_bodyB->GetAngularVelocity() - m_bodyA->GetAngularVelocity(); }

@@ -1,0 +1,573 @@
+// b2g_world.h — b2World / b2Body / b2Fixture / b2Contact / listeners of the drop-in C++ API.
+//
+// API mirror of the reference's include/box2d/b2_world.h:49-253, b2_body.h:45-449,
+// b2_fixture.h:37-227, b2_contact.h:65-143, b2_world_callbacks.h:46-210, b2_joint.h,
+// b2_revolute_joint.h and b2_time_step.h:29-36.  Same class names, method names, argument
+// meaning and error behaviour (silent no-op / nullptr while the world is locked), but the
+// objects are thin host handles: all simulation state lives in a device arena
+// (include/b2cuda.h) and b2World::Step launches the CUDA step.  Host copies of body state
+// are refreshed lazily after a step, on the first getter that needs them.
+#ifndef B2G_WORLD_H
+#define B2G_WORLD_H
+
+#include <vector>
+#include "b2g_shapes.h"
+
+class b2World;
+class b2Body;
+class b2Fixture;
+class b2Contact;
+class b2Joint;
+struct b2WorldImpl;
+
+enum b2BodyType { b2_staticBody = 0, b2_kinematicBody, b2_dynamicBody };
+
+struct b2BodyDef {
+  b2BodyDef() {
+    position.Set(0.0f, 0.0f);
+    angle = 0.0f;
+    linearVelocity.Set(0.0f, 0.0f);
+    angularVelocity = 0.0f;
+    linearDamping = 0.0f;
+    angularDamping = 0.0f;
+    allowSleep = true;
+    awake = true;
+    fixedRotation = false;
+    bullet = false;
+    type = b2_staticBody;
+    enabled = true;
+    gravityScale = 1.0f;
+  }
+  b2BodyType type;
+  b2Vec2 position;
+  float angle;
+  b2Vec2 linearVelocity;
+  float angularVelocity;
+  float linearDamping;
+  float angularDamping;
+  bool allowSleep;
+  bool awake;
+  bool fixedRotation;
+  bool bullet;
+  bool enabled;
+  b2BodyUserData userData;
+  float gravityScale;
+};
+
+struct b2Filter {
+  b2Filter() {
+    categoryBits = 0x0001;
+    maskBits = 0xFFFF;
+    groupIndex = 0;
+  }
+  uint16 categoryBits;
+  uint16 maskBits;
+  int16 groupIndex;
+};
+
+struct b2FixtureDef {
+  b2FixtureDef() {
+    shape = nullptr;
+    friction = 0.2f;
+    restitution = 0.0f;
+    restitutionThreshold = 1.0f * b2_lengthUnitsPerMeter;
+    density = 0.0f;
+    isSensor = false;
+  }
+  const b2Shape* shape;
+  b2FixtureUserData userData;
+  float friction;
+  float restitution;
+  float restitutionThreshold;
+  float density;
+  bool isSensor;
+  b2Filter filter;
+};
+
+class b2Fixture {
+ public:
+  b2Shape::Type GetType() const { return m_shape->GetType(); }
+  b2Shape* GetShape() { return m_shape; }
+  const b2Shape* GetShape() const { return m_shape; }
+  void SetSensor(bool sensor);
+  bool IsSensor() const { return m_isSensor; }
+  void SetFilterData(const b2Filter& filter);
+  const b2Filter& GetFilterData() const { return m_filter; }
+  void Refilter();
+  b2Body* GetBody() { return m_body; }
+  const b2Body* GetBody() const { return m_body; }
+  b2Fixture* GetNext() { return m_next; }
+  const b2Fixture* GetNext() const { return m_next; }
+  b2FixtureUserData& GetUserData() { return m_userData; }
+  uint32 GetId() { return m_id; }
+  bool TestPoint(const b2Vec2& p) const;
+  void GetMassData(b2MassData* massData) const { m_shape->ComputeMass(massData, m_density); }
+  void SetDensity(float density) { m_density = density; }
+  float GetDensity() const { return m_density; }
+  float GetFriction() const { return m_friction; }
+  void SetFriction(float friction);
+  float GetRestitution() const { return m_restitution; }
+  void SetRestitution(float restitution);
+  float GetRestitutionThreshold() const { return m_restitutionThreshold; }
+  void SetRestitutionThreshold(float threshold);
+  void UpdateAABB();
+  const b2AABB& GetAABB() const;
+
+ private:
+  friend class b2Body;
+  friend class b2World;
+  friend class b2Contact;
+  friend struct b2WorldImpl;
+  b2Fixture() {}
+  float m_density;
+  b2Fixture* m_next;
+  b2Body* m_body;
+  b2Shape* m_shape;
+  float m_friction;
+  float m_restitution;
+  float m_restitutionThreshold;
+  b2Filter m_filter;
+  bool m_isSensor;
+  b2FixtureUserData m_userData;
+  mutable b2AABB m_aabb;
+  uint32 m_id;
+  int32 m_index;     // index in the device fixture arrays
+  int32 m_shapeOff;  // offset in the device shape pool
+};
+
+struct b2JointEdge {
+  b2Body* other;
+  b2Joint* joint;
+  b2JointEdge* prev;
+  b2JointEdge* next;
+};
+
+class b2Body {
+ public:
+  b2Fixture* CreateFixture(const b2FixtureDef* def);
+  b2Fixture* CreateFixture(const b2Shape* shape, float density);
+  void DestroyFixture(b2Fixture* fixture);
+  void SetTransform(const b2Vec2& position, float angle);
+  const b2Transform& GetTransform() const;
+  const b2Vec2& GetPosition() const;
+  float GetAngle() const;
+  const b2Vec2& GetWorldCenter() const;
+  const b2Vec2& GetLocalCenter() const;
+  void SetLinearVelocity(const b2Vec2& v);
+  const b2Vec2& GetLinearVelocity() const;
+  void SetAngularVelocity(float omega);
+  float GetAngularVelocity() const;
+  void ApplyForce(const b2Vec2& force, const b2Vec2& point) { ApplyForce(force, point, true); }
+  void ApplyForceToCenter(const b2Vec2& force) { ApplyForceToCenter(force, true); }
+  void ApplyTorque(float torque) { ApplyTorque(torque, true); }
+  void ApplyLinearImpulse(const b2Vec2& impulse, const b2Vec2& point) { ApplyLinearImpulse(impulse, point, true); }
+  void ApplyLinearImpulseToCenter(const b2Vec2& impulse) { ApplyLinearImpulseToCenter(impulse, true); }
+  void ApplyAngularImpulse(float impulse) { ApplyAngularImpulse(impulse, true); }
+  void ApplyForce(const b2Vec2& force, const b2Vec2& point, bool wake);
+  void ApplyForceToCenter(const b2Vec2& force, bool wake);
+  void ApplyTorque(float torque, bool wake);
+  void ApplyLinearImpulse(const b2Vec2& impulse, const b2Vec2& point, bool wake);
+  void ApplyLinearImpulseToCenter(const b2Vec2& impulse, bool wake);
+  void ApplyAngularImpulse(float impulse, bool wake);
+  float GetMass() const { return m_mass; }
+  float GetInertia() const;
+  void GetMassData(b2MassData* data) const;
+  void SetMassData(const b2MassData* data);
+  void ResetMassData();
+  b2Vec2 GetWorldPoint(const b2Vec2& localPoint) const { return b2Mul(GetTransform(), localPoint); }
+  b2Vec2 GetWorldVector(const b2Vec2& localVector) const { return b2Mul(GetTransform().q, localVector); }
+  b2Vec2 GetLocalPoint(const b2Vec2& worldPoint) const { return b2MulT(GetTransform(), worldPoint); }
+  b2Vec2 GetLocalVector(const b2Vec2& worldVector) const { return b2MulT(GetTransform().q, worldVector); }
+  b2Vec2 GetLinearVelocityFromWorldPoint(const b2Vec2& worldPoint) const;
+  b2Vec2 GetLinearVelocityFromLocalPoint(const b2Vec2& localPoint) const {
+    return GetLinearVelocityFromWorldPoint(GetWorldPoint(localPoint));
+  }
+  float GetLinearDamping() const { return m_linearDamping; }
+  void SetLinearDamping(float linearDamping);
+  float GetAngularDamping() const { return m_angularDamping; }
+  void SetAngularDamping(float angularDamping);
+  float GetGravityScale() const { return m_gravityScale; }
+  void SetGravityScale(float scale);
+  void SetType(b2BodyType type);
+  b2BodyType GetType() const { return m_type; }
+  void SetBullet(bool flag);
+  bool IsBullet() const;
+  void SetSleepingAllowed(bool flag);
+  bool IsSleepingAllowed() const;
+  void SetAwake(bool flag);
+  bool IsAwake() const;
+  void SetEnabled(bool flag);
+  bool IsEnabled() const;
+  void SetFixedRotation(bool flag);
+  bool IsFixedRotation() const;
+  b2Fixture* GetFixtureList() { return m_fixtureList; }
+  const b2Fixture* GetFixtureList() const { return m_fixtureList; }
+  b2JointEdge* GetJointList() { return m_jointList; }
+  const b2JointEdge* GetJointList() const { return m_jointList; }
+  int32 GetContactCount();
+  b2Contact* GetContact(int32 idx);
+  b2Body* GetNext() { return m_next; }
+  const b2Body* GetNext() const { return m_next; }
+  b2BodyUserData& GetUserData() { return m_userData; }
+  b2World* GetWorld() { return m_world; }
+  const b2World* GetWorld() const { return m_world; }
+  void UpdateAABBs();
+
+ private:
+  friend class b2World;
+  friend class b2Fixture;
+  friend class b2Contact;
+  friend class b2Joint;
+  friend class b2RevoluteJoint;
+  friend struct b2WorldImpl;
+  b2Body(const b2BodyDef* bd, b2World* world);
+  ~b2Body() {}
+  void SyncIn() const;  // make the host copy current
+  void Touch();         // host copy changed: upload before the next step
+  void SynchronizeTransform() {
+    m_xf.q.Set(m_sweep.a);
+    m_xf.p = m_sweep.c - b2Mul(m_xf.q, m_sweep.localCenter);
+  }
+  bool ShouldCollide(const b2Body* other) const;
+
+  b2BodyType m_type;
+  uint16 m_flags;
+  int32 m_index;  // index in the device body arrays (creation order)
+  mutable b2Transform m_xf;
+  mutable b2Sweep m_sweep;
+  mutable b2Vec2 m_linearVelocity;
+  mutable float m_angularVelocity;
+  mutable b2Vec2 m_force;
+  mutable float m_torque;
+  b2World* m_world;
+  b2Body* m_prev;
+  b2Body* m_next;
+  b2Fixture* m_fixtureList;
+  int32 m_fixtureCount;
+  b2JointEdge* m_jointList;
+  std::vector<b2Contact*> m_contacts;
+  float m_mass, m_invMass;
+  float m_I, m_invI;
+  float m_linearDamping;
+  float m_angularDamping;
+  float m_gravityScale;
+  mutable float m_sleepTime;
+  b2BodyUserData m_userData;
+
+ public:
+  enum {
+    e_islandFlag = 0x0001,
+    e_awakeFlag = 0x0002,
+    e_autoSleepFlag = 0x0004,
+    e_bulletFlag = 0x0008,
+    e_fixedRotationFlag = 0x0010,
+    e_enabledFlag = 0x0020,
+    e_toiFlag = 0x0040
+  };
+};
+
+// ---- contacts -------------------------------------------------------------------------------
+inline float b2MixFriction(float friction1, float friction2) { return b2Sqrt(friction1 * friction2); }
+inline float b2MixRestitution(float restitution1, float restitution2) {
+  return restitution1 > restitution2 ? restitution1 : restitution2;
+}
+inline float b2MixRestitutionThreshold(float threshold1, float threshold2) {
+  return threshold1 < threshold2 ? threshold1 : threshold2;
+}
+
+class b2Contact {
+ public:
+  b2Manifold* GetManifold() { return &m_manifold; }
+  const b2Manifold* GetManifold() const { return &m_manifold; }
+  void GetWorldManifold(b2WorldManifold* worldManifold) const;
+  bool IsTouching() const { return (m_flags & e_touchingFlag) == e_touchingFlag; }
+  void SetEnabled(bool flag);
+  bool IsEnabled() const { return (m_flags & e_enabledFlag) == e_enabledFlag; }
+  b2Contact* GetNext() { return m_next; }
+  const b2Contact* GetNext() const { return m_next; }
+  b2Fixture* GetFixtureA() { return m_fixtureA; }
+  const b2Fixture* GetFixtureA() const { return m_fixtureA; }
+  b2Fixture* GetFixtureB() { return m_fixtureB; }
+  const b2Fixture* GetFixtureB() const { return m_fixtureB; }
+  void SetFriction(float friction);
+  float GetFriction() const { return m_friction; }
+  void ResetFriction();
+  void SetRestitution(float restitution);
+  float GetRestitution() const { return m_restitution; }
+  void ResetRestitution();
+  void SetRestitutionThreshold(float threshold);
+  float GetRestitutionThreshold() const { return m_restitutionThreshold; }
+  void ResetRestitutionThreshold();
+  void SetTangentSpeed(float speed);
+  float GetTangentSpeed() const { return m_tangentSpeed; }
+
+  enum {
+    e_islandFlag = 0x0001,
+    e_persistFlag = 0x0002,
+    e_filterFlag = 0x0004,
+    e_touchingFlag = 0x0008,
+    e_enabledFlag = 0x0010,
+    e_bulletHitFlag = 0x0020,
+  };
+
+ private:
+  friend class b2World;
+  friend class b2Body;
+  friend struct b2WorldImpl;
+  b2Contact() {}
+  uint32 m_flags;
+  b2Contact* m_prev;
+  b2Contact* m_next;
+  b2Fixture* m_fixtureA;
+  b2Fixture* m_fixtureB;
+  b2Manifold m_manifold;
+  float m_friction;
+  float m_restitution;
+  float m_restitutionThreshold;
+  float m_tangentSpeed;
+  int32 m_deviceIndex;  // index in the device contact arrays after the last step
+  bool m_overridden;    // a setter was called: push flags/material back before the solve
+  b2World* m_world;
+};
+
+// ---- joints ---------------------------------------------------------------------------------
+enum b2JointType {
+  e_unknownJoint,
+  e_revoluteJoint,
+  e_prismaticJoint,
+  e_distanceJoint,
+  e_pulleyJoint,
+  e_mouseJoint,
+  e_gearJoint,
+  e_wheelJoint,
+  e_weldJoint,
+  e_frictionJoint,
+  e_ropeJoint,
+  e_motorJoint
+};
+
+struct b2JointDef {
+  b2JointDef() {
+    type = e_unknownJoint;
+    bodyA = nullptr;
+    bodyB = nullptr;
+    collideConnected = false;
+  }
+  b2JointType type;
+  b2JointUserData userData;
+  b2Body* bodyA;
+  b2Body* bodyB;
+  bool collideConnected;
+};
+
+struct b2RevoluteJointDef : public b2JointDef {
+  b2RevoluteJointDef() {
+    type = e_revoluteJoint;
+    localAnchorA.Set(0.0f, 0.0f);
+    localAnchorB.Set(0.0f, 0.0f);
+    referenceAngle = 0.0f;
+    lowerAngle = 0.0f;
+    upperAngle = 0.0f;
+    maxMotorTorque = 0.0f;
+    motorSpeed = 0.0f;
+    enableLimit = false;
+    enableMotor = false;
+  }
+  void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec2& anchor);
+  b2Vec2 localAnchorA;
+  b2Vec2 localAnchorB;
+  float referenceAngle;
+  bool enableLimit;
+  float lowerAngle;
+  float upperAngle;
+  bool enableMotor;
+  float motorSpeed;
+  float maxMotorTorque;
+};
+
+class b2Joint {
+ public:
+  b2JointType GetType() const { return m_type; }
+  b2Body* GetBodyA() { return m_bodyA; }
+  b2Body* GetBodyB() { return m_bodyB; }
+  virtual b2Vec2 GetAnchorA() const = 0;
+  virtual b2Vec2 GetAnchorB() const = 0;
+  b2Joint* GetNext() { return m_next; }
+  const b2Joint* GetNext() const { return m_next; }
+  b2JointUserData& GetUserData() { return m_userData; }
+  bool GetCollideConnected() const { return m_collideConnected; }
+  virtual ~b2Joint() {}
+
+ protected:
+  friend class b2World;
+  friend class b2Body;
+  friend struct b2WorldImpl;
+  b2Joint(const b2JointDef* def);
+  b2JointType m_type;
+  b2Joint* m_prev;
+  b2Joint* m_next;
+  b2JointEdge m_edgeA;
+  b2JointEdge m_edgeB;
+  b2Body* m_bodyA;
+  b2Body* m_bodyB;
+  int32 m_index;
+  bool m_collideConnected;
+  b2JointUserData m_userData;
+};
+
+class b2RevoluteJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  const b2Vec2& GetLocalAnchorA() const { return m_localAnchorA; }
+  const b2Vec2& GetLocalAnchorB() const { return m_localAnchorB; }
+  float GetReferenceAngle() const { return m_referenceAngle; }
+  float GetJointAngle() const;
+  float GetJointSpeed() const;
+  bool IsLimitEnabled() const { return m_enableLimit; }
+  bool IsMotorEnabled() const { return m_enableMotor; }
+  float GetMotorSpeed() const { return m_motorSpeed; }
+  float GetMaxMotorTorque() const { return m_maxMotorTorque; }
+  float GetLowerLimit() const { return m_lowerAngle; }
+  float GetUpperLimit() const { return m_upperAngle; }
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2RevoluteJoint(const b2RevoluteJointDef* def);
+  b2Vec2 m_localAnchorA;
+  b2Vec2 m_localAnchorB;
+  float m_referenceAngle;
+  bool m_enableLimit;
+  float m_lowerAngle;
+  float m_upperAngle;
+  bool m_enableMotor;
+  float m_motorSpeed;
+  float m_maxMotorTorque;
+};
+
+// ---- callbacks (b2_world_callbacks.h) ---------------------------------------------------------
+class b2DestructionListener {
+ public:
+  virtual ~b2DestructionListener() {}
+  virtual void SayGoodbye(b2Joint* joint) = 0;
+  virtual void SayGoodbye(b2Fixture* fixture) = 0;
+};
+
+class b2ContactFilter {
+ public:
+  virtual ~b2ContactFilter() {}
+  virtual bool ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB);
+};
+
+struct b2ContactImpulse {
+  float normalImpulses[b2_maxManifoldPoints];
+  float tangentImpulses[b2_maxManifoldPoints];
+  int32 count;
+};
+
+class b2ContactListener {
+ public:
+  virtual ~b2ContactListener() {}
+  virtual void BeginContact(b2Contact* contact) { B2_NOT_USED(contact); }
+  virtual void EndContact(b2Contact* contact) { B2_NOT_USED(contact); }
+  virtual void PreSolve(b2Contact* contact, const b2Manifold* oldManifold) {
+    B2_NOT_USED(contact);
+    B2_NOT_USED(oldManifold);
+  }
+  virtual void PostSolve(b2Contact* contact, const b2ContactImpulse* impulse) {
+    B2_NOT_USED(contact);
+    B2_NOT_USED(impulse);
+  }
+};
+
+struct b2Profile {
+  float step;
+  float collide;
+  float solve;
+  float broadphase;
+  float solveTOI;
+};
+
+// ---- the world --------------------------------------------------------------------------------
+class b2World {
+ public:
+  b2World(const b2Vec2& gravity);
+  ~b2World();
+  void SetDestructionListener(b2DestructionListener* listener) { m_destructionListener = listener; }
+  void SetContactFilter(b2ContactFilter* filter) { m_contactFilter = filter; }
+  void SetContactListener(b2ContactListener* listener) { m_contactListener = listener; }
+  b2Body* CreateBody(const b2BodyDef* def);
+  void DestroyBody(b2Body* body);
+  b2Joint* CreateJoint(const b2JointDef* def);
+  void DestroyJoint(b2Joint* joint);
+  void Step(float timeStep, int32 velocityIterations, int32 positionIterations, int32 particleIterations);
+  void Step(float timeStep, int32 velocityIterations, int32 positionIterations) {
+    Step(timeStep, velocityIterations, positionIterations, 1);
+  }
+  void ClearForces();
+  b2Body* GetBodyList() { return m_bodyListHead; }
+  const b2Body* GetBodyList() const { return m_bodyListHead; }
+  b2Joint* GetJointList() { return m_jointList; }
+  const b2Joint* GetJointList() const { return m_jointList; }
+  b2Contact* GetContactListStart();
+  b2Contact* GetContactListEnd();
+  void SetAllowSleeping(bool flag);
+  bool GetAllowSleeping() const { return m_allowSleep; }
+  void SetWarmStarting(bool flag) { m_warmStarting = flag; }
+  bool GetWarmStarting() const { return m_warmStarting; }
+  void SetContinuousPhysics(bool flag) { m_continuousPhysics = flag; }
+  bool GetContinuousPhysics() const { return m_continuousPhysics; }
+  void SetSubStepping(bool flag) { m_subStepping = flag; }
+  bool GetSubStepping() const { return m_subStepping; }
+  int32 GetProxyCount() const;
+  int32 GetBodyCount() const { return m_bodyCount; }
+  int32 GetJointCount() const { return m_jointCount; }
+  int32 GetContactCount() const;
+  int32 GetTreeHeight() const { return 0; }
+  void SetGravity(const b2Vec2& gravity) { m_gravity = gravity; }
+  b2Vec2 GetGravity() const { return m_gravity; }
+  bool IsLocked() const { return m_locked; }
+  void SetAutoClearForces(bool flag) { m_clearForces = flag; }
+  bool GetAutoClearForces() const { return m_clearForces; }
+  const b2Profile& GetProfile() const { return m_profile; }
+
+  // ---- extensions of the B200 build (not in the reference API) ----
+  /// device capacities used by worlds constructed afterwards (grown automatically when exceeded)
+  static void SetDefaultCapacity(int32 bodies, int32 fixtures, int32 contacts);
+  /// CUDA device ordinal used by worlds constructed afterwards (default: env B2G_DEVICE or 0)
+  static void SetDefaultDevice(int32 device);
+  /// B2G_SOLVER_COLOURED (0, default) or B2G_SOLVER_SEQUENTIAL (1)
+  void SetSolverMode(int32 mode) { m_solverMode = mode; }
+  int32 GetSolverMode() const { return m_solverMode; }
+  /// fill GetProfile() from CUDA events (adds a synchronisation per step)
+  void SetProfiling(bool flag);
+  b2WorldImpl* GetImpl() { return m_impl; }
+
+ private:
+  friend class b2Body;
+  friend class b2Fixture;
+  friend class b2Contact;
+  friend struct b2WorldImpl;
+  b2WorldImpl* m_impl;
+  b2Body* m_bodyListHead;
+  b2Body* m_bodyListTail;
+  b2Joint* m_jointList;
+  int32 m_bodyCount;
+  int32 m_jointCount;
+  b2Vec2 m_gravity;
+  bool m_allowSleep;
+  b2DestructionListener* m_destructionListener;
+  b2ContactFilter* m_contactFilter;
+  b2ContactListener* m_contactListener;
+  bool m_newContacts;
+  bool m_locked;
+  bool m_clearForces;
+  bool m_warmStarting;
+  bool m_continuousPhysics;
+  bool m_subStepping;
+  int32 m_solverMode;
+  b2Profile m_profile;
+};
+
+#endif

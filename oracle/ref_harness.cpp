@@ -1,0 +1,303 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE ONLY.  Never linked into the product.
+//
+// Compiled by oracle/Makefile together with the UNMODIFIED reference sources where they lie under
+// /root/reference (src/collision, src/common, src/dynamics, src/particle) into
+// oracle/_ref/libb2ref.so.  Nothing from the reference is copied into this repository: this
+// file only *calls* it.  It exposes
+//   (1) the shared scene shim (scenes/b2_scene_shim.h) expanded with the b2ref_ prefix, i.e. the
+//       reference's own b2World::Step on the BASELINE scenes — the parity oracle and the
+//       `cpu_baseline.kind = "reference"` timing arm;
+//   (2) white-box taps (built with -fno-access-control, as SURVEY.md §8c / Appendix C describe):
+//       the five b2Collide* functions on explicit shapes, b2PolygonShape::Set, ComputeAABB,
+//       b2ContactManager::Collide on a live world, and b2ContactSolver driven on explicit arrays
+//       with per-iteration iterates dumped.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load it.
+#include <cstring>
+#include <vector>
+#include "box2d/box2d.h"
+#include "dynamics/b2_contact_solver.h"  // private header, reachable through -I/root/reference/src
+
+#define SHIM(name) b2ref_##name
+#include "b2_scene_shim.h"
+
+namespace {
+
+struct ShapeBox {
+  b2CircleShape circle;
+  b2EdgeShape edge;
+  b2PolygonShape poly;
+  b2Shape* get(int type) {
+    if (type == 0) return &circle;
+    if (type == 1) return &edge;
+    return &poly;
+  }
+};
+
+void shape_from_quads(ShapeBox& s, int type, const float* q) {
+  if (type == 0) {
+    s.circle.m_p.Set(q[0], q[1]);
+    s.circle.m_radius = q[2];
+  } else if (type == 1) {
+    s.edge.m_vertex1.Set(q[0], q[1]);
+    s.edge.m_vertex2.Set(q[2], q[3]);
+    s.edge.m_vertex0.Set(q[4], q[5]);
+    s.edge.m_vertex3.Set(q[6], q[7]);
+    s.edge.m_radius = q[8];
+    s.edge.m_oneSided = q[9] != 0.0f;
+  } else {
+    s.poly.m_centroid.Set(q[0], q[1]);
+    s.poly.m_radius = q[2];
+    s.poly.m_count = (int32)q[3];
+    for (int i = 0; i < s.poly.m_count; ++i) {
+      s.poly.m_vertices[i].Set(q[4 + 4 * i], q[5 + 4 * i]);
+      s.poly.m_normals[i].Set(q[6 + 4 * i], q[7 + 4 * i]);
+    }
+  }
+}
+
+b2Transform xf_from(const float* x) {
+  b2Transform t;
+  t.p.Set(x[0], x[1]);
+  t.q.s = x[2];
+  t.q.c = x[3];
+  return t;
+}
+
+void manifold_to_floats(const b2Manifold& m, float* q) {
+  q[0] = m.localNormal.x; q[1] = m.localNormal.y; q[2] = m.localPoint.x; q[3] = m.localPoint.y;
+  for (int k = 0; k < 2; ++k) {
+    q[4 + 4 * k] = m.points[k].localPoint.x; q[5 + 4 * k] = m.points[k].localPoint.y;
+    q[6 + 4 * k] = m.points[k].normalImpulse; q[7 + 4 * k] = m.points[k].tangentImpulse;
+    uint32_t key = m.points[k].id.key;
+    memcpy(&q[12 + k], &key, 4);
+  }
+  int32_t type = (int32_t)m.type, count = m.pointCount;
+  memcpy(&q[14], &type, 4);
+  memcpy(&q[15], &count, 4);
+}
+
+void manifold_from_floats(b2Manifold& m, const float* q) {
+  m.localNormal.Set(q[0], q[1]);
+  m.localPoint.Set(q[2], q[3]);
+  for (int k = 0; k < 2; ++k) {
+    m.points[k].localPoint.Set(q[4 + 4 * k], q[5 + 4 * k]);
+    m.points[k].normalImpulse = q[6 + 4 * k];
+    m.points[k].tangentImpulse = q[7 + 4 * k];
+    memcpy(&m.points[k].id.key, &q[12 + k], 4);
+  }
+  int32_t type, count;
+  memcpy(&type, &q[14], 4);
+  memcpy(&count, &q[15], 4);
+  m.type = (b2Manifold::Type)type;
+  m.pointCount = count;
+}
+
+}  // namespace
+
+extern "C" {
+
+// b2PolygonShape::Set on `count` points -> shape-pool record (1 + m_count quads). Returns m_count.
+int b2ref_polygon_set(const float* points, int count, float* quads) {
+  b2Vec2 pts[b2_maxPolygonVertices];
+  int n = count < b2_maxPolygonVertices ? count : b2_maxPolygonVertices;
+  for (int i = 0; i < n; ++i) pts[i].Set(points[2 * i], points[2 * i + 1]);
+  b2PolygonShape p;
+  p.Set(pts, n);
+  scene_write_shape_quads(&p, quads);
+  return p.m_count;
+}
+
+// polygon mass data through the reference: out = mass, center.x, center.y, I
+void b2ref_shape_mass(int type, const float* quads, float density, float* out) {
+  ShapeBox s;
+  shape_from_quads(s, type, quads);
+  b2MassData md;
+  s.get(type)->ComputeMass(&md, density);
+  out[0] = md.mass; out[1] = md.center.x; out[2] = md.center.y; out[3] = md.I;
+}
+
+void b2ref_compute_aabbs(int n, const int* type, const int* shapeOff, const float* quads, const float* xf, float* aabb) {
+  for (int i = 0; i < n; ++i) {
+    ShapeBox s;
+    shape_from_quads(s, type[i], quads + 4 * shapeOff[i]);
+    b2AABB bb;
+    s.get(type[i])->ComputeAABB(&bb, xf_from(xf + 4 * i));
+    aabb[4 * i] = bb.lowerBound.x; aabb[4 * i + 1] = bb.lowerBound.y;
+    aabb[4 * i + 2] = bb.upperBound.x; aabb[4 * i + 3] = bb.upperBound.y;
+  }
+}
+
+// the five b2Collide* functions on n ordered pairs; returns -1 if a pair has no function
+int b2ref_collide_pairs(int n, const int* typeA, const int* offA, const float* xfA, const int* typeB, const int* offB,
+                        const float* xfB, const float* quads, float* manifold) {
+  for (int i = 0; i < n; ++i) {
+    ShapeBox a, b;
+    shape_from_quads(a, typeA[i], quads + 4 * offA[i]);
+    shape_from_quads(b, typeB[i], quads + 4 * offB[i]);
+    b2Transform ta = xf_from(xfA + 4 * i), tb = xf_from(xfB + 4 * i);
+    b2Manifold m;
+    memset(&m, 0, sizeof(m));
+    if (typeA[i] == 0 && typeB[i] == 0) b2CollideCircles(&m, &a.circle, ta, &b.circle, tb);
+    else if (typeA[i] == 2 && typeB[i] == 0) b2CollidePolygonAndCircle(&m, &a.poly, ta, &b.circle, tb);
+    else if (typeA[i] == 2 && typeB[i] == 2) b2CollidePolygons(&m, &a.poly, ta, &b.poly, tb);
+    else if (typeA[i] == 1 && typeB[i] == 0) b2CollideEdgeAndCircle(&m, &a.edge, ta, &b.circle, tb);
+    else if (typeA[i] == 1 && typeB[i] == 2) b2CollideEdgeAndPolygon(&m, &a.edge, ta, &b.poly, tb);
+    else return -1;
+    manifold_to_floats(m, manifold + 16 * i);
+  }
+  return 0;
+}
+
+// run the narrowphase of the NEXT step on a live world now (b2ContactManager::Collide)
+void b2ref_world_collide(void* h) { static_cast<Scene*>(h)->world->m_contactManager.Collide(); }
+
+// out[n][2] = m_invMass, m_invI (private members; exact solver inputs)
+void b2ref_get_body_inv(void* h, float* out) {
+  Scene* s = static_cast<Scene*>(h);
+  for (size_t i = 0; i < s->bodies.size(); ++i) {
+    out[2 * i] = s->bodies[i]->m_invMass;
+    out[2 * i + 1] = s->bodies[i]->m_invI;
+  }
+}
+float b2ref_get_inv_dt0(void* h) { return static_cast<Scene*>(h)->world->m_inv_dt0; }
+// out[n] = sleep timers
+void b2ref_get_sleep_times(void* h, float* out) {
+  Scene* s = static_cast<Scene*>(h);
+  for (size_t i = 0; i < s->bodies.size(); ++i) out[i] = s->bodies[i]->m_sleepTime;
+}
+
+// b2ContactSolver on explicit arrays, driven as b2Island::Solve drives it (b2_island.cpp:306-409).
+// Same signature and array layouts as b2g_solve_sequential in include/b2cuda.h (minus `device`).
+int b2ref_solve(int nb, float* pos, float* vel, const float* mass, int nc, const int* index, float* manifold,
+                const float* material, const float* radii, float dt, float dtRatio, int warmStarting, int velIters,
+                int posIters, float* velIterates, float* posIterates, int* posItersDone) {
+  std::vector<b2Position> positions(nb);
+  std::vector<b2Velocity> velocities(nb);
+  for (int i = 0; i < nb; ++i) {
+    positions[i].c.Set(pos[4 * i], pos[4 * i + 1]);
+    positions[i].a = pos[4 * i + 2];
+    velocities[i].v.Set(vel[4 * i], vel[4 * i + 1]);
+    velocities[i].w = vel[4 * i + 2];
+  }
+  // stand-in bodies / fixtures / contacts carrying exactly the fields b2ContactSolver::Initialize reads
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  std::vector<b2Body*> bodies(nb);
+  for (int i = 0; i < nb; ++i) {
+    bodies[i] = new b2Body(&bd, nullptr);
+    bodies[i]->m_islandIndex = i;
+    bodies[i]->m_invMass = mass[4 * i];
+    bodies[i]->m_invI = mass[4 * i + 1];
+    bodies[i]->m_sweep.localCenter.Set(mass[4 * i + 2], mass[4 * i + 3]);
+  }
+  std::vector<b2CircleShape> shapes(2 * (size_t)nc);
+  std::vector<b2Fixture*> fixtures(2 * (size_t)nc);
+  std::vector<b2Contact*> contacts(nc);
+  for (int i = 0; i < nc; ++i) {
+    for (int k = 0; k < 2; ++k) {
+      shapes[2 * i + k].m_radius = radii[2 * i + k];
+      b2Fixture* f = new b2Fixture();
+      f->m_shape = &shapes[2 * i + k];
+      f->m_body = bodies[index[2 * i + k]];
+      f->m_friction = 0.0f;
+      f->m_restitution = 0.0f;
+      f->m_restitutionThreshold = 0.0f;
+      f->m_isSensor = false;
+      fixtures[2 * i + k] = f;
+    }
+    void* mem = malloc(sizeof(b2Contact));
+    b2Contact* c = new (mem) b2Contact(fixtures[2 * i], fixtures[2 * i + 1], nullptr);
+    c->m_friction = material[4 * i];
+    c->m_restitution = material[4 * i + 1];
+    c->m_restitutionThreshold = material[4 * i + 2];
+    c->m_tangentSpeed = material[4 * i + 3];
+    manifold_from_floats(c->m_manifold, manifold + 16 * i);
+    contacts[i] = c;
+  }
+
+  b2StackAllocator allocator;
+  b2TimeStep step;
+  step.dt = dt;
+  step.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+  step.dtRatio = dtRatio;
+  step.velocityIterations = velIters;
+  step.positionIterations = posIters;
+  step.particleIterations = 1;
+  step.warmStarting = warmStarting != 0;
+  int done = 0;
+  {
+    b2ContactSolver solver;
+    if (nc > 0) {
+      b2ContactSolverDef def;
+      def.step = step;
+      def.contacts = contacts.data();
+      def.count = nc;
+      def.positions = positions.data();
+      def.velocities = velocities.data();
+      def.allocator = &allocator;
+      solver.Initialize(&def);
+      solver.InitializeVelocityConstraints();
+      if (step.warmStarting) solver.WarmStart();
+    }
+    for (int it = 0; it < velIters; ++it) {
+      if (nc > 0) solver.SolveVelocityConstraints();
+      if (velIterates)
+        for (int i = 0; i < nb; ++i) {
+          float* o = velIterates + ((size_t)it * nb + i) * 4;
+          o[0] = velocities[i].v.x; o[1] = velocities[i].v.y; o[2] = velocities[i].w; o[3] = 0.0f;
+        }
+    }
+    if (nc > 0) solver.StoreImpulses();
+    // integrate positions exactly as b2_island.cpp:353-385
+    for (int i = 0; i < nb; ++i) {
+      b2Vec2 c = positions[i].c;
+      float a = positions[i].a;
+      b2Vec2 v = velocities[i].v;
+      float w = velocities[i].w;
+      b2Vec2 translation = dt * v;
+      if (b2Dot(translation, translation) > b2_maxTranslationSquared) {
+        float ratio = b2_maxTranslation / translation.Length();
+        v *= ratio;
+      }
+      float rotation = dt * w;
+      if (rotation * rotation > b2_maxRotationSquared) {
+        float ratio = b2_maxRotation / b2Abs(rotation);
+        w *= ratio;
+      }
+      c += dt * v;
+      a += dt * w;
+      positions[i].c = c;
+      positions[i].a = a;
+      velocities[i].v = v;
+      velocities[i].w = w;
+    }
+    for (int it = 0; it < posIters; ++it) {
+      bool ok = nc > 0 ? solver.SolvePositionConstraints() : true;
+      ++done;
+      if (posIterates)
+        for (int i = 0; i < nb; ++i) {
+          float* o = posIterates + ((size_t)it * nb + i) * 4;
+          o[0] = positions[i].c.x; o[1] = positions[i].c.y; o[2] = positions[i].a; o[3] = 0.0f;
+        }
+      if (ok) break;
+    }
+  }
+  for (int i = 0; i < nb; ++i) {
+    pos[4 * i] = positions[i].c.x; pos[4 * i + 1] = positions[i].c.y; pos[4 * i + 2] = positions[i].a;
+    vel[4 * i] = velocities[i].v.x; vel[4 * i + 1] = velocities[i].v.y; vel[4 * i + 2] = velocities[i].w;
+  }
+  for (int i = 0; i < nc; ++i) {
+    manifold_to_floats(contacts[i]->m_manifold, manifold + 16 * i);
+    free(contacts[i]);
+    delete fixtures[2 * i];
+    delete fixtures[2 * i + 1];
+  }
+  for (int i = 0; i < nb; ++i) {
+    b2Free(bodies[i]->m_contactList);
+    delete bodies[i];
+  }
+  if (posItersDone) *posItersDone = done;
+  return 0;
+}
+
+}  // extern "C"

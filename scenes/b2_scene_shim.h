@@ -1,0 +1,136 @@
+// b2_scene_shim.h — extern "C" access to the scenes of b2_scenes.h, for ctypes.
+//
+// Included by exactly two translation units, each defining SHIM(name) first:
+//   oracle/ref_harness.cpp                     SHIM(x) = b2ref_##x  (the compiled reference)
+//   box2d_optimized_b200/host/gpu_scene_shim.cpp  SHIM(x) = b2gpu_##x  (the drop-in API over CUDA)
+// Only public Box2D API is used here, so both expansions are the same program.
+#ifndef B2_SCENE_SHIM_H
+#define B2_SCENE_SHIM_H
+
+#include "b2_scenes.h"
+
+extern "C" {
+
+void* SHIM(scene_create)(const char* name, int size, int seed) { return scene_build(name, size, seed); }
+void SHIM(scene_destroy)(void* h) { delete static_cast<Scene*>(h); }
+void SHIM(scene_step)(void* h, int n) {
+  Scene* s = static_cast<Scene*>(h);
+  for (int i = 0; i < n; ++i) s->step();
+}
+// wall-clock milliseconds for n steps (CPU baseline timing, std::chrono::steady_clock)
+double SHIM(scene_time_steps)(void* h, int n) {
+  Scene* s = static_cast<Scene*>(h);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < n; ++i) s->step();
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double, std::milli>(t1 - t0).count();
+}
+void SHIM(scene_set_iterations)(void* h, int vi, int pi) {
+  Scene* s = static_cast<Scene*>(h);
+  s->velocityIterations = vi;
+  s->positionIterations = pi;
+}
+void SHIM(scene_set_flags)(void* h, int allowSleep, int warmStarting) {
+  Scene* s = static_cast<Scene*>(h);
+  s->world->SetAllowSleeping(allowSleep != 0);
+  s->world->SetWarmStarting(warmStarting != 0);
+}
+int SHIM(scene_body_count)(void* h) { return (int)static_cast<Scene*>(h)->bodies.size(); }
+int SHIM(scene_fixture_count)(void* h) { return (int)static_cast<Scene*>(h)->fixtures.size(); }
+int SHIM(scene_contact_count)(void* h) { return static_cast<Scene*>(h)->world->GetContactCount(); }
+
+// out[n][12] = xf.p.x, xf.p.y, xf.q.s, xf.q.c, c.x, c.y, a, v.x, v.y, w, awake, type
+void SHIM(scene_get_bodies)(void* h, float* out) {
+  Scene* s = static_cast<Scene*>(h);
+  for (size_t i = 0; i < s->bodies.size(); ++i) {
+    b2Body* b = s->bodies[i];
+    float* o = out + i * 12;
+    const b2Transform& xf = b->GetTransform();
+    o[0] = xf.p.x; o[1] = xf.p.y; o[2] = xf.q.s; o[3] = xf.q.c;
+    o[4] = b->GetWorldCenter().x; o[5] = b->GetWorldCenter().y; o[6] = b->GetAngle();
+    o[7] = b->GetLinearVelocity().x; o[8] = b->GetLinearVelocity().y; o[9] = b->GetAngularVelocity();
+    o[10] = b->IsAwake() ? 1.0f : 0.0f;
+    o[11] = (float)b->GetType();
+  }
+}
+// out[n][8] = mass, inertia about the origin, localCenter.x, localCenter.y, linearDamping,
+//             angularDamping, gravityScale, sleepingAllowed
+void SHIM(scene_get_body_params)(void* h, float* out) {
+  Scene* s = static_cast<Scene*>(h);
+  for (size_t i = 0; i < s->bodies.size(); ++i) {
+    b2Body* b = s->bodies[i];
+    float* o = out + i * 8;
+    o[0] = b->GetMass(); o[1] = b->GetInertia(); o[2] = b->GetLocalCenter().x; o[3] = b->GetLocalCenter().y;
+    o[4] = b->GetLinearDamping(); o[5] = b->GetAngularDamping(); o[6] = b->GetGravityScale();
+    o[7] = b->IsSleepingAllowed() ? 1.0f : 0.0f;
+  }
+}
+int SHIM(scene_shape_quad_total)(void* h) {
+  Scene* s = static_cast<Scene*>(h);
+  int total = 0;
+  for (b2Fixture* f : s->fixtures) total += scene_shape_quad_count(f->GetShape());
+  return total;
+}
+// body[n], type[n], shapeOff[n], filter[n][3] = category, mask, group, material[n][4] =
+// friction, restitution, restitutionThreshold, density; sensor[n]; quads = shape pool in fixture order
+void SHIM(scene_get_fixtures)(void* h, int* body, int* type, int* shapeOff, int* filter, float* material, int* sensor,
+                              float* quads) {
+  Scene* s = static_cast<Scene*>(h);
+  int off = 0;
+  for (size_t i = 0; i < s->fixtures.size(); ++i) {
+    b2Fixture* f = s->fixtures[i];
+    body[i] = s->bodyIndex[f->GetBody()];
+    type[i] = (int)f->GetType();
+    shapeOff[i] = off;
+    const b2Filter& fl = f->GetFilterData();
+    filter[3 * i] = fl.categoryBits; filter[3 * i + 1] = fl.maskBits; filter[3 * i + 2] = fl.groupIndex;
+    material[4 * i] = f->GetFriction(); material[4 * i + 1] = f->GetRestitution();
+    material[4 * i + 2] = f->GetRestitutionThreshold(); material[4 * i + 3] = f->GetDensity();
+    sensor[i] = f->IsSensor() ? 1 : 0;
+    scene_write_shape_quads(f->GetShape(), quads + 4 * off);
+    off += scene_shape_quad_count(f->GetShape());
+  }
+}
+// aabb[n][4] of every fixture as the broadphase sees it
+void SHIM(scene_get_aabbs)(void* h, float* aabb) {
+  Scene* s = static_cast<Scene*>(h);
+  for (size_t i = 0; i < s->fixtures.size(); ++i) {
+    const b2AABB& bb = s->fixtures[i]->GetAABB();
+    aabb[4 * i] = bb.lowerBound.x; aabb[4 * i + 1] = bb.lowerBound.y;
+    aabb[4 * i + 2] = bb.upperBound.x; aabb[4 * i + 3] = bb.upperBound.y;
+  }
+}
+// world contact list in list order: fixA[n], fixB[n] (creation-order fixture indices),
+// flags[n] (bit 0 touching, bit 1 enabled), manifold[n][16] in the include/b2cuda.h layout,
+// material[n][4] = friction, restitution, restitutionThreshold, tangentSpeed.  Returns n.
+int SHIM(scene_get_contacts)(void* h, int cap, int* fixA, int* fixB, int* flags, float* manifold, float* material) {
+  Scene* s = static_cast<Scene*>(h);
+  int n = 0;
+  for (b2Contact* c = s->world->GetContactListStart(); c != s->world->GetContactListEnd(); c = c->GetNext()) {
+    if (n >= cap) break;
+    fixA[n] = s->fixtureIndex[c->GetFixtureA()];
+    fixB[n] = s->fixtureIndex[c->GetFixtureB()];
+    flags[n] = (c->IsTouching() ? 1 : 0) | (c->IsEnabled() ? 2 : 0);
+    const b2Manifold* m = c->GetManifold();
+    float* q = manifold + 16 * n;
+    q[0] = m->localNormal.x; q[1] = m->localNormal.y; q[2] = m->localPoint.x; q[3] = m->localPoint.y;
+    for (int k = 0; k < 2; ++k) {
+      q[4 + 4 * k] = m->points[k].localPoint.x; q[5 + 4 * k] = m->points[k].localPoint.y;
+      q[6 + 4 * k] = m->points[k].normalImpulse; q[7 + 4 * k] = m->points[k].tangentImpulse;
+      uint32_t key = m->points[k].id.key;
+      memcpy(&q[12 + k], &key, 4);
+    }
+    int32_t type = (int32_t)m->type, count = m->pointCount;
+    memcpy(&q[14], &type, 4);
+    memcpy(&q[15], &count, 4);
+    if (material) {
+      material[4 * n] = c->GetFriction(); material[4 * n + 1] = c->GetRestitution();
+      material[4 * n + 2] = c->GetRestitutionThreshold(); material[4 * n + 3] = c->GetTangentSpeed();
+    }
+    ++n;
+  }
+  return n;
+}
+
+}  // extern "C"
+#endif

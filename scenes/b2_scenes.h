@@ -1,0 +1,290 @@
+// b2_scenes.h — the BASELINE.json scenes, written ONCE against the public Box2D API.
+//
+// This file includes only "box2d/box2d.h" and uses only b2World / b2Body / b2Fixture / shape
+// calls, so the very same source compiles against
+//   (a) the reference (-I/root/reference/include, linked with its sources) -> oracle/_ref/libb2ref.so
+//   (b) this repo's drop-in API (-Iinclude, linked with libb2cuda)         -> libb2gpu_scenes.so
+// which is the drop-in claim in executable form.  Scene definitions follow SURVEY.md §8(d):
+//   pyramid        testbed/tests/pyramid.cpp:33-72 (config 1)
+//   many_pyramids  `size` copies of it 30 m apart on one ground edge (config 2)
+//   mixed          circles + convex polygons dropped into a 3-box container, LCG seed (config 3)
+//   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
+//   hello          unit-test/hello_world.cpp:33-112
+//   falling_squares / falling_circles   benchmarks.h:57-135 (b1, b2)
+#ifndef B2_SCENES_H
+#define B2_SCENES_H
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "box2d/box2d.h"
+
+struct SceneLCG {
+  uint32_t state;
+  explicit SceneLCG(uint32_t seed) : state(seed) {}
+  float next() {  // U[0,1)
+    state = state * 1664525u + 1013904223u;
+    return (float)(state >> 8) / 16777216.0f;
+  }
+  float range(float lo, float hi) { return lo + (hi - lo) * next(); }
+};
+
+struct Scene {
+  b2World* world = nullptr;
+  std::vector<b2Body*> bodies;        // creation order = device body index
+  std::vector<b2Fixture*> fixtures;   // creation order = device fixture index
+  std::unordered_map<const b2Fixture*, int> fixtureIndex;
+  std::unordered_map<const b2Body*, int> bodyIndex;
+  float dt = 1.0f / 60.0f;
+  int velocityIterations = 8;
+  int positionIterations = 3;
+  std::string kind;
+  int spawnTarget = 0, spawned = 0;  // tumbler: one box per step until spawnTarget
+  int steps = 0;
+
+  ~Scene() { delete world; }
+
+  b2Body* addBody(const b2BodyDef& bd) {
+    b2Body* b = world->CreateBody(&bd);
+    bodyIndex[b] = (int)bodies.size();
+    bodies.push_back(b);
+    return b;
+  }
+  b2Fixture* addFixture(b2Body* b, const b2FixtureDef& fd) {
+    b2Fixture* f = b->CreateFixture(&fd);
+    fixtureIndex[f] = (int)fixtures.size();
+    fixtures.push_back(f);
+    return f;
+  }
+  b2Fixture* addFixture(b2Body* b, const b2Shape& shape, float density) {
+    b2FixtureDef fd;
+    fd.shape = &shape;
+    fd.density = density;
+    return addFixture(b, fd);
+  }
+
+  void step() {
+    world->Step(dt, velocityIterations, positionIterations);
+    if (kind == "tumbler" && spawned < spawnTarget) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(0.0f, 10.0f);
+      b2Body* body = addBody(bd);
+      b2PolygonShape shape;
+      shape.SetAsBox(0.125f, 0.125f);
+      addFixture(body, shape, 1.0f);
+      ++spawned;
+    }
+    ++steps;
+  }
+};
+
+inline void scene_add_pyramid(Scene& s, int rows, float xOffset) {
+  float a = 0.5f;
+  b2PolygonShape shape;
+  shape.SetAsBox(a, a);
+  b2Vec2 x(-7.0f + xOffset, 0.75f);
+  b2Vec2 y;
+  b2Vec2 deltaX(0.5625f, 1.25f);
+  b2Vec2 deltaY(1.125f, 0.0f);
+  for (int i = 0; i < rows; ++i) {
+    y = x;
+    for (int j = i; j < rows; ++j) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position = y;
+      b2Body* body = s.addBody(bd);
+      s.addFixture(body, shape, 5.0f);
+      y += deltaY;
+    }
+    x += deltaX;
+  }
+}
+
+inline Scene* scene_build(const std::string& name, int size, int seed) {
+  Scene* s = new Scene();
+  s->kind = name;
+  s->world = new b2World(b2Vec2(0.0f, -10.0f));
+  s->world->SetContinuousPhysics(false);  // as both reference benchmark mains do (single.cpp:44)
+  if (name == "pyramid" || name == "many_pyramids") {
+    int rows = name == "pyramid" ? (size > 0 ? size : 20) : 20;
+    int copies = name == "pyramid" ? 1 : (size > 0 ? size : 100);
+    {
+      b2BodyDef bd;
+      b2Body* ground = s->addBody(bd);
+      b2EdgeShape shape;
+      shape.SetTwoSided(b2Vec2(-40.0f, 0.0f), b2Vec2(40.0f + 30.0f * (float)(copies - 1), 0.0f));
+      s->addFixture(ground, shape, 0.0f);
+    }
+    for (int k = 0; k < copies; ++k) scene_add_pyramid(*s, rows, 30.0f * (float)k);
+  } else if (name == "mixed") {
+    int n = size > 0 ? size : 1000;
+    SceneLCG rng((uint32_t)(seed > 0 ? seed : 12345));
+    int cols = (int)std::ceil(1.5 * std::sqrt((double)n));
+    float pitch = 1.1f;
+    float width = pitch * (float)cols;
+    int rowsNeeded = (n + cols - 1) / cols;
+    float height = pitch * (float)rowsNeeded + 10.0f;
+    {
+      b2BodyDef bd;
+      b2Body* container = s->addBody(bd);
+      b2PolygonShape floor, wallL, wallR;
+      floor.SetAsBox(0.5f * width + 2.0f, 1.0f, b2Vec2(0.5f * width, -1.0f), 0.0f);
+      wallL.SetAsBox(1.0f, 0.5f * height + 1.0f, b2Vec2(-1.5f, 0.5f * height), 0.0f);
+      wallR.SetAsBox(1.0f, 0.5f * height + 1.0f, b2Vec2(width + 1.5f, 0.5f * height), 0.0f);
+      s->addFixture(container, floor, 0.0f);
+      s->addFixture(container, wallL, 0.0f);
+      s->addFixture(container, wallR, 0.0f);
+    }
+    for (int i = 0; i < n; ++i) {
+      int cx = i % cols, cy = i / cols;
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(0.55f + pitch * (float)cx, 0.6f + pitch * (float)cy);
+      bd.angle = rng.range(0.0f, 2.0f * b2_pi);
+      b2Body* body = s->addBody(bd);
+      b2FixtureDef fd;
+      fd.density = 1.0f;
+      fd.friction = 0.2f;
+      if (i & 1) {
+        b2CircleShape circle;
+        circle.m_radius = rng.range(0.25f, 0.5f);
+        fd.shape = &circle;
+        s->addFixture(body, fd);
+      } else {
+        int nv = 3 + (int)(rng.next() * 6.0f);
+        if (nv > 8) nv = 8;
+        float rx = rng.range(0.3f, 0.5f), ry = rng.range(0.3f, 0.5f);
+        b2Vec2 pts[8];
+        for (int k = 0; k < nv; ++k) {
+          float ang = 2.0f * b2_pi * (float)k / (float)nv;
+          pts[k].Set(rx * cosf(ang), ry * sinf(ang));
+        }
+        b2PolygonShape poly;
+        poly.Set(pts, nv);
+        fd.shape = &poly;
+        s->addFixture(body, fd);
+      }
+    }
+  } else if (name == "tumbler") {
+    s->spawnTarget = size > 0 ? size : 500;
+    b2Body* ground;
+    {
+      b2BodyDef bd;
+      ground = s->addBody(bd);
+    }
+    {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(0.0f, 10.0f);
+      b2Body* body = s->addBody(bd);
+      b2PolygonShape shape;
+      shape.SetAsBox(0.5f, 10.0f, b2Vec2(10.0f, 0.0f), 0.0);
+      s->addFixture(body, shape, 5.0f);
+      shape.SetAsBox(0.5f, 10.0f, b2Vec2(-10.0f, 0.0f), 0.0);
+      s->addFixture(body, shape, 5.0f);
+      shape.SetAsBox(10.0f, 0.5f, b2Vec2(0.0f, 10.0f), 0.0);
+      s->addFixture(body, shape, 5.0f);
+      shape.SetAsBox(10.0f, 0.5f, b2Vec2(0.0f, -10.0f), 0.0);
+      s->addFixture(body, shape, 5.0f);
+      b2RevoluteJointDef jd;
+      jd.bodyA = ground;
+      jd.bodyB = body;
+      jd.localAnchorA.Set(0.0f, 10.0f);
+      jd.localAnchorB.Set(0.0f, 0.0f);
+      jd.referenceAngle = 0.0f;
+      jd.motorSpeed = 0.05f * b2_pi;
+      jd.maxMotorTorque = 1e8f;
+      jd.enableMotor = true;
+      s->world->CreateJoint(&jd);
+    }
+  } else if (name == "hello") {
+    s->velocityIterations = 6;
+    s->positionIterations = 2;
+    b2BodyDef groundBodyDef;
+    groundBodyDef.position.Set(0.0f, -10.0f);
+    b2Body* groundBody = s->addBody(groundBodyDef);
+    b2PolygonShape groundBox;
+    groundBox.SetAsBox(50.0f, 10.0f);
+    s->addFixture(groundBody, groundBox, 0.0f);
+    b2BodyDef bodyDef;
+    bodyDef.type = b2_dynamicBody;
+    bodyDef.position.Set(0.0f, 4.0f);
+    b2Body* body = s->addBody(bodyDef);
+    b2PolygonShape dynamicBox;
+    dynamicBox.SetAsBox(1.0f, 1.0f);
+    b2FixtureDef fixtureDef;
+    fixtureDef.shape = &dynamicBox;
+    fixtureDef.density = 1.0f;
+    fixtureDef.friction = 0.3f;
+    s->addFixture(body, fixtureDef);
+  } else if (name == "falling_squares" || name == "falling_circles") {
+    int n = size > 0 ? size : 300;
+    {
+      b2BodyDef bd;
+      b2Body* ground = s->addBody(bd);
+      b2PolygonShape shape;
+      shape.SetAsBox(200.0f, 10.0f, b2Vec2(0.0f, -10.0f), 0.0f);
+      s->addFixture(ground, shape, 0.0f);
+    }
+    SceneLCG rng((uint32_t)(seed > 0 ? seed : 7));
+    int cols = 30;
+    for (int i = 0; i < n; ++i) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(-18.0f + 1.25f * (float)(i % cols) + rng.range(-0.1f, 0.1f), 1.0f + 1.25f * (float)(i / cols));
+      b2Body* body = s->addBody(bd);
+      if (name == "falling_squares") {
+        b2PolygonShape shape;
+        shape.SetAsBox(0.5f, 0.5f);
+        s->addFixture(body, shape, 1.0f);
+      } else {
+        b2CircleShape shape;
+        shape.m_radius = 0.5f;
+        s->addFixture(body, shape, 1.0f);
+      }
+    }
+  } else {
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
+
+// ---- export helpers (public shape members only) ---------------------------------------------
+inline int scene_shape_quad_count(const b2Shape* sh) {
+  switch (sh->GetType()) {
+    case b2Shape::e_circle: return 1;
+    case b2Shape::e_edge: return 3;
+    case b2Shape::e_polygon: return 1 + static_cast<const b2PolygonShape*>(sh)->m_count;
+    default: return 0;
+  }
+}
+inline void scene_write_shape_quads(const b2Shape* sh, float* q) {
+  switch (sh->GetType()) {
+    case b2Shape::e_circle: {
+      const b2CircleShape* c = static_cast<const b2CircleShape*>(sh);
+      q[0] = c->m_p.x; q[1] = c->m_p.y; q[2] = c->m_radius; q[3] = 0.0f;
+    } break;
+    case b2Shape::e_edge: {
+      const b2EdgeShape* e = static_cast<const b2EdgeShape*>(sh);
+      q[0] = e->m_vertex1.x; q[1] = e->m_vertex1.y; q[2] = e->m_vertex2.x; q[3] = e->m_vertex2.y;
+      q[4] = e->m_vertex0.x; q[5] = e->m_vertex0.y; q[6] = e->m_vertex3.x; q[7] = e->m_vertex3.y;
+      q[8] = e->m_radius; q[9] = e->m_oneSided ? 1.0f : 0.0f; q[10] = 0.0f; q[11] = 0.0f;
+    } break;
+    case b2Shape::e_polygon: {
+      const b2PolygonShape* p = static_cast<const b2PolygonShape*>(sh);
+      q[0] = p->m_centroid.x; q[1] = p->m_centroid.y; q[2] = p->m_radius; q[3] = (float)p->m_count;
+      for (int i = 0; i < p->m_count; ++i) {
+        q[4 + 4 * i] = p->m_vertices[i].x; q[5 + 4 * i] = p->m_vertices[i].y;
+        q[6 + 4 * i] = p->m_normals[i].x;  q[7 + 4 * i] = p->m_normals[i].y;
+      }
+    } break;
+    default: break;
+  }
+}
+
+#endif
