@@ -22,7 +22,7 @@ struct StepCounts {
   int numTouching;
   int numAwake;
   int beginCount, endCount;
-  int pad;
+  int lastUsefulRound;  // 1 + index of the last colouring round that coloured something
   int colourCount[B2G_MAX_COLOURS + 1];
   unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
 };
@@ -61,7 +61,8 @@ struct b2gArena {
   float4 *pos, *vel, *xf, *mass, *center, *force;
   uint32_t* bflags;
   int* bworld;
-  int* island;             // union-find parent, flattened to the island root
+  int* islandParent;       // union-find forest (lock-free unions)
+  int* island;             // flattened: island id = smallest body index of the component
   uint32_t* islandAwake;   // per root: some member is awake
   uint32_t* islandMinSleep;  // per root: float bits of min sleepTime
   uint32_t* islandPen;     // [B2G_MAX_POS_ITERS][capBodies] float bits of max penetration per iteration
@@ -95,7 +96,9 @@ struct b2gArena {
   int *leafFixture, *leafFixtureSorted;
   float4* leafBox;
   int4* leafInfo;
-  int* leafWorldEnd;
+  unsigned long long* leafKey;  // (AABB size bits, sorted position): who reports a pair
+  ulonglong2* nodeMaxKey;       // per internal node: max leafKey under the left / right child
+  int* worldFirst;
   int* worldLast;
   int4* nodeRange;  // first, split, last, parent
   float4 *nodeBoxL, *nodeBoxR;

@@ -11,7 +11,7 @@
 // SET it reports is exactly "all fixture pairs with inclusive tight-AABB overlap" (SURVEY
 // Appendix B.20), independent of tree shape.  The device path therefore builds a linear BVH
 // (Karras 2012) over Morton-sorted fixture AABBs every step and lets every leaf traverse it,
-// reporting each pair once (only partners later in the sorted order), with warp-aggregated
+// reporting each pair once (by its smaller-AABB member), with warp-aggregated
 // compaction into a key list that is then sorted and merged against the previous contacts.
 #pragma once
 #include "b2g_step_kernels.cuh"
@@ -131,7 +131,8 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
                               const unsigned long long* __restrict__ keysSorted, const float4* __restrict__ fAabb,
                               const int* __restrict__ fBody, const uint32_t* __restrict__ fTypeFlags,
                               const uint2* __restrict__ fFilter, const uint32_t* __restrict__ bflags, float4* leafBox,
-                              int4* leafInfo, int* worldLast, int numWorlds) {
+                              int4* leafInfo, unsigned long long* leafKey, int* worldFirst, int* worldLast,
+                              int numWorlds) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nf) return;
   int f = leafFixtureSorted[p];
@@ -144,10 +145,18 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
   unsigned int z = (tf & 3u) | ((tf & B2G_FIX_SENSOR) ? 4u : 0u) | (B2G_BODY_TYPE(bf) == B2G_DYNAMIC ? 8u : 0u) |
                    (dead ? 16u : 0u) | ((fl.y & 0xffffu) << 16);
   leafInfo[p] = make_int4(f, b, (int)z, (int)fl.x);
+  // reporting order: the leaf with the SMALLER (size, position) key reports the pair, so a huge
+  // AABB (ground edge, container wall) never walks the tree for its thousands of partners —
+  // they each find it instead.  size = half perimeter as non-negative float bits (monotone).
+  float4 bx = leafBox[p];
+  float size = dead ? 0.0f : (bx.z - bx.x) + (bx.w - bx.y);
+  leafKey[p] = ((unsigned long long)__float_as_uint(fmaxf(size, 0.0f)) << 32) | (unsigned int)p;
   if (numWorlds > 1) {
     unsigned int w = (unsigned int)(keysSorted[p] >> 32);
     bool lastOfWorld = (p == nf - 1) || ((unsigned int)(keysSorted[p + 1] >> 32) != w);
+    bool firstOfWorld = (p == 0) || ((unsigned int)(keysSorted[p - 1] >> 32) != w);
     if (lastOfWorld && w < (unsigned int)numWorlds) worldLast[w] = p;
+    if (firstOfWorld && w < (unsigned int)numWorlds) worldFirst[w] = p;
   }
 }
 
@@ -190,22 +199,32 @@ __global__ void k_lbvh_build(int n, const unsigned long long* __restrict__ keys,
 
 // bottom-up refit: the second thread to reach a node carries the union upward; child boxes are
 // stored IN the parent so the traversal tests both children with one node fetch
-__global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const int* __restrict__ leafParent,
-                             const int4* __restrict__ nodeRange, float4* nodeBoxL, float4* nodeBoxR, int* nodeVisit) {
+__global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const unsigned long long* __restrict__ leafKey,
+                             const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, float4* nodeBoxL,
+                             float4* nodeBoxR, ulonglong2* nodeMaxKey, int* nodeVisit) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   float4 box = leafBox[p];
+  unsigned long long key = leafKey[p];
   int idx = p;
   int parent = leafParent[p];
   while (parent >= 0) {
     int4 nr = nodeRange[parent];
     bool isLeft = (idx == nr.y);
-    if (isLeft) nodeBoxL[parent] = box; else nodeBoxR[parent] = box;
+    if (isLeft) {
+      nodeBoxL[parent] = box;
+      nodeMaxKey[parent].x = key;
+    } else {
+      nodeBoxR[parent] = box;
+      nodeMaxKey[parent].y = key;
+    }
     __threadfence();
     int old = atomicAdd(&nodeVisit[parent], 1);
     if (old == 0) return;
     float4 sib = isLeft ? __ldcg(&nodeBoxR[parent]) : __ldcg(&nodeBoxL[parent]);
+    unsigned long long sibKey = isLeft ? __ldcg(&nodeMaxKey[parent].y) : __ldcg(&nodeMaxKey[parent].x);
     box = make_float4(fminf(box.x, sib.x), fminf(box.y, sib.y), fmaxf(box.z, sib.z), fmaxf(box.w, sib.w));
+    key = key > sibKey ? key : sibKey;
     idx = parent;
     parent = nr.w;
   }
@@ -258,22 +277,26 @@ __device__ __forceinline__ void emit_pair(int4 a, int4 b, unsigned long long* pa
   }
 }
 
-// one thread per query leaf; reports partners later in sorted order (each pair once) and never
-// leaves the query's own world segment
+// one thread per query leaf.  Leaf i reports partner j iff key(j) > key(i) (each pair once, by
+// its smaller member); subtrees whose largest key is not above key(i) are pruned, and the walk
+// never leaves the query's own world segment [ws, we] of the sorted order.
 __global__ void __launch_bounds__(128)
 k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo,
-              const int4* __restrict__ nodeRange, const float4* __restrict__ nodeBoxL,
-              const float4* __restrict__ nodeBoxR, const int* __restrict__ worldLast,
-              const unsigned long long* __restrict__ keysSorted, int numWorlds, unsigned long long* pairKeys,
-              int capacity, int fixBits, StepCounts* counts) {
+              const unsigned long long* __restrict__ leafKey, const int4* __restrict__ nodeRange,
+              const float4* __restrict__ nodeBoxL, const float4* __restrict__ nodeBoxR,
+              const ulonglong2* __restrict__ nodeMaxKey, const int* __restrict__ worldFirst,
+              const int* __restrict__ worldLast, const unsigned long long* __restrict__ keysSorted, int numWorlds,
+              unsigned long long* pairKeys, int capacity, int fixBits, StepCounts* counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || n < 2) return;
   int4 me = leafInfo[i];
   if ((unsigned int)me.z & 16u) return;
   float4 qbox = leafBox[i];
-  int we = n - 1;
+  const unsigned long long myKey = leafKey[i];
+  int ws = 0, we = n - 1;
   if (numWorlds > 1) {
     unsigned int w = (unsigned int)(keysSorted[i] >> 32);
+    ws = worldFirst[w];
     we = worldLast[w];
   }
   int stack[64];
@@ -282,14 +305,14 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
   while (sp > 0) {
     int node = stack[--sp];
     int4 nr = nodeRange[node];
-    float4 bl = nodeBoxL[node], br = nodeBoxR[node];
+    ulonglong2 mk = nodeMaxKey[node];
     // left child covers [first, split]
-    if (nr.y > i && nr.x <= we && aabb_overlap(qbox, bl)) {
+    if (mk.x > myKey && nr.x <= we && nr.y >= ws && aabb_overlap(qbox, nodeBoxL[node])) {
       if (nr.x == nr.y) emit_pair(me, leafInfo[nr.y], pairKeys, capacity, fixBits, counts);
       else stack[sp++] = nr.y;
     }
     // right child covers [split+1, last]
-    if (nr.z > i && nr.y + 1 <= we && aabb_overlap(qbox, br)) {
+    if (mk.y > myKey && nr.y + 1 <= we && nr.z >= ws && aabb_overlap(qbox, nodeBoxR[node])) {
       if (nr.y + 1 == nr.z) emit_pair(me, leafInfo[nr.z], pairKeys, capacity, fixBits, counts);
       else stack[sp++] = nr.y + 1;
     }

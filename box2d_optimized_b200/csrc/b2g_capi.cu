@@ -121,6 +121,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->bflags, nb));
   CK(dalloc(&A->bworld, nb));
   CK(dalloc(&A->island, nb));
+  CK(dalloc(&A->islandParent, nb));
   CK(dalloc(&A->islandAwake, nb));
   CK(dalloc(&A->islandMinSleep, nb));
   CK(dalloc(&A->islandPen, (size_t)nb * B2G_MAX_POS_ITERS));
@@ -154,7 +155,9 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->leafFixtureSorted, nf));
   CK(dalloc(&A->leafBox, nf));
   CK(dalloc(&A->leafInfo, nf));
-  CK(dalloc(&A->leafWorldEnd, nf));
+  CK(dalloc(&A->leafKey, nf));
+  CK(dalloc(&A->nodeMaxKey, nf));
+  CK(dalloc(&A->worldFirst, A->numWorlds + 1));
   CK(dalloc(&A->worldLast, A->numWorlds + 1));
   CK(dalloc(&A->nodeRange, nf));
   CK(dalloc(&A->nodeBoxL, nf));
@@ -215,12 +218,12 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   if (!A) return B2G_ERR_INVALID;
   cudaSetDevice(A->device);
   cudaStreamSynchronize(A->stream);
-  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island,
+  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent,
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
                   A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->oldPersist, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
-                  A->leafWorldEnd, A->worldLast, A->nodeRange, A->nodeBoxL, A->nodeBoxR, A->leafParent,
+                  A->leafKey, A->nodeMaxKey, A->worldFirst, A->worldLast, A->nodeRange, A->nodeBoxL, A->nodeBoxR, A->leafParent,
                   A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
                   A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
@@ -377,16 +380,17 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
                                        A->leafFixtureSorted, nf, 0, 32 + (A->numWorlds > 1 ? A->worldBits : 0),
                                        A->stream));
     LAUNCH(A, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted, A->fAabb, A->fBody,
-           A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->worldLast, A->numWorlds);
+           A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->leafKey, A->worldFirst, A->worldLast,
+           A->numWorlds);
     CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
     CK(cudaMemsetAsync(A->nodeVisit, 0, sizeof(int) * nf, A->stream));
     if (nf > 1) {
       LAUNCH(A, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange, A->leafParent);
-      LAUNCH(A, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafParent, A->nodeRange, A->nodeBoxL,
-             A->nodeBoxR, A->nodeVisit);
-      LAUNCH(A, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->nodeRange, A->nodeBoxL,
-             A->nodeBoxR, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->pairKeys, A->capContacts, A->fixBits,
-             A->dCounts);
+      LAUNCH(A, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent, A->nodeRange,
+             A->nodeBoxL, A->nodeBoxR, A->nodeMaxKey, A->nodeVisit);
+      LAUNCH(A, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->nodeRange, A->nodeBoxL,
+             A->nodeBoxR, A->nodeMaxKey, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->pairKeys,
+             A->capContacts, A->fixBits, A->dCounts);
     }
     int rc2 = read_counts(A);  // the one mid-pipeline sync: the sort below needs the pair count
     if (rc2) return rc2;
@@ -476,11 +480,11 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
 
   if (h > 0.0f && nb > 0) {
     // ---- islands ---------------------------------------------------------------------
-    LAUNCH(A, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->island, A->islandAwake,
+    LAUNCH(A, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent, A->islandAwake,
            A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest);
-    if (nc > 0) LAUNCH(A, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->island);
-    if (nj > 0) LAUNCH(A, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->island);
-    LAUNCH(A, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake);
+    if (nc > 0) LAUNCH(A, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
+    if (nj > 0) LAUNCH(A, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
+    LAUNCH(A, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island, A->islandAwake);
     LAUNCH(A, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->vel, A->mass,
            A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y), A->dCounts);
 
@@ -516,8 +520,12 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
           batch = 4;
         }
         rounds = round;
-        // adapt the first batch: steady state needs 1-2 rounds, a cold start ~10
-        A->roundsHint = round <= 2 ? 2 : (round < 16 ? round : 16);
+        // adapt the first batch to what was actually needed: a settled scene colours nothing new
+        // (one probing round), a cold start needs ~10
+        {
+          int useful = A->hCounts->lastUsefulRound;
+          A->roundsHint = useful < 1 ? 1 : (useful + 1 < 16 ? useful + 1 : 16);
+        }
         numActive = A->hCounts->numActive;
         int acc = 0;
         for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {

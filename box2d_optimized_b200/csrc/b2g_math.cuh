@@ -103,10 +103,22 @@ B2G_HD Xf xf_from4(float4 v) {
 }
 B2G_HD float4 xf_to4(Xf T) { return make_float4(T.p.x, T.p.y, T.q.s, T.q.c); }
 // b2Rot::Set (b2_math.h:313-318)
+// The reference calls glibc's sinf/cosf, which evaluate in double precision and round once
+// (error < 0.51 ulp, i.e. correctly rounded except in rare near-halfway cases).  CUDA's float
+// sinf/cosf differ from that by 1-2 ulp, enough to flip the solver's branchy thresholds
+// (block-solver condition number, restitution threshold) and break iterate parity, so the device
+// takes the same route: double-precision sincos, rounded once to float.
 B2G_HD Rot rot_set(float angle) {
   Rot q;
+#ifdef __CUDA_ARCH__
+  double sd, cd;
+  sincos((double)angle, &sd, &cd);
+  q.s = (float)sd;
+  q.c = (float)cd;
+#else
   q.s = sinf(angle);
   q.c = cosf(angle);
+#endif
   return q;
 }
 // transform of a body at (c, a) with local centre lc: b2Body::SynchronizeTransform (b2_body.h:957-961)

@@ -123,7 +123,7 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
 // bodies (b2_world.cpp:560-647).  Lock-free union-find, smaller index wins, so the root of an
 // island is its smallest body index — deterministic whatever the thread order.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* island, uint32_t* islandAwake,
+__global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islandParent, uint32_t* islandAwake,
                              uint32_t* islandMinSleep, uint32_t* islandPen, int penStride, int posIters,
                              unsigned long long* colourMask, unsigned long long* bodyBest) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,7 +137,7 @@ __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islan
     fo.w = 0.0f;
     force[b] = fo;
   }
-  island[b] = b;
+  islandParent[b] = b;
   islandAwake[b] = 0;
   islandMinSleep[b] = __float_as_uint(B2G_MAX_FLOAT);
   for (int k = 0; k < posIters; ++k) islandPen[(size_t)k * penStride + b] = 0;
@@ -195,10 +195,15 @@ __global__ void k_island_union_joints(int nj, const int2* __restrict__ jBodies, 
   uf_union(island, bd.x, bd.y);
 }
 
-__global__ void k_island_flatten(int nb, const uint32_t* __restrict__ bflags, int* island, uint32_t* islandAwake) {
+// Flatten into a SEPARATE array with a read-only find: compressing paths in place here would
+// race with other threads' finds (a late path-halving store can overwrite a finished entry with
+// a non-root ancestor), which made island ids — and therefore the whole step — nondeterministic.
+__global__ void k_island_flatten(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ parent,
+                                 int* island, uint32_t* islandAwake) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  int root = uf_find(island, b);
+  int root = b;
+  for (int p = parent[root]; p != root; p = parent[root]) root = p;
   island[b] = root;
   uint32_t f = bflags[b];
   // an island is simulated when any member could seed it (b2_world.cpp:526-545)
@@ -335,6 +340,7 @@ __global__ void k_colour_commit(const int* __restrict__ numActivePtr, const int*
         if (movB) colourMask[bd.y] |= bit;
       }
       atomicAdd(&counts->colourCount[c], 1);
+      if (counts->lastUsefulRound < round + 1) atomicMax(&counts->lastUsefulRound, round + 1);
     } else if (lastOfBatch) {
       atomicAdd(&counts->remaining, 1);
     }
@@ -415,8 +421,10 @@ k_solve_position(int first, int last, SolverPlanes S, float4* pos, const int* __
   int root = croot[s];
   if (island_done(islandPen, penStride, iter, root)) return;
   float minSep = solve_position_constraint(S, s, pos);
-  // -minSep >= 0, so the float bit pattern is monotone as an unsigned integer
-  atomicMax(&islandPen[(size_t)iter * penStride + root], __float_as_uint(-minSep));
+  // penetration >= +0.0 (never -0.0, whose bit pattern would win the max), so the float bit
+  // pattern is monotone as an unsigned integer
+  float pen = minSep < 0.0f ? -minSep : 0.0f;
+  atomicMax(&islandPen[(size_t)iter * penStride + root], __float_as_uint(pen));
 }
 
 // sequential single-thread variants: same device functions, list order (parity vehicle and the
@@ -434,7 +442,7 @@ __global__ void k_solve_position_seq(int first, int last, SolverPlanes S, float4
     if (island_done(islandPen, penStride, iter, root)) continue;
     float minSep = solve_position_constraint(S, s, pos);
     uint32_t* slot = &islandPen[(size_t)iter * penStride + root];
-    uint32_t v = __float_as_uint(-minSep);
+    uint32_t v = __float_as_uint(minSep < 0.0f ? -minSep : 0.0f);
     if (v > *slot) *slot = v;
   }
 }

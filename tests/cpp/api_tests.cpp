@@ -1,0 +1,226 @@
+// api_tests.cpp — acceptance tests of the public C++ API, compiled twice:
+//   against the reference (-I/root/reference/include + its sources): proves the tests are right
+//   against this repo's drop-in API (-Iinclude + libb2gpu_scenes.so): proves the drop-in
+// The cases restate the reference's own unit tests (unit-test/hello_world.cpp:33-112,
+// world_test.cpp:38-73, collision_test.cpp:28-81, math_test.cpp:27-54) without doctest.
+#include <cstdio>
+#include <cmath>
+#include <cfloat>
+#include "box2d/box2d.h"
+
+static int g_failed = 0;
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);       \
+      ++g_failed;                                                          \
+    }                                                                      \
+  } while (0)
+
+static void hello_world() {
+  b2Vec2 gravity(0.0f, -10.0f);
+  b2World world(gravity);
+  b2BodyDef groundBodyDef;
+  groundBodyDef.position.Set(0.0f, -10.0f);
+  b2Body* groundBody = world.CreateBody(&groundBodyDef);
+  b2PolygonShape groundBox;
+  groundBox.SetAsBox(50.0f, 10.0f);
+  groundBody->CreateFixture(&groundBox, 0.0f);
+  b2BodyDef bodyDef;
+  bodyDef.type = b2_dynamicBody;
+  bodyDef.position.Set(0.0f, 4.0f);
+  b2Body* body = world.CreateBody(&bodyDef);
+  b2PolygonShape dynamicBox;
+  dynamicBox.SetAsBox(1.0f, 1.0f);
+  b2FixtureDef fixtureDef;
+  fixtureDef.shape = &dynamicBox;
+  fixtureDef.density = 1.0f;
+  fixtureDef.friction = 0.3f;
+  body->CreateFixture(&fixtureDef);
+  float timeStep = 1.0f / 60.0f;
+  b2Vec2 position = body->GetPosition();
+  float angle = body->GetAngle();
+  for (int32 i = 0; i < 60; ++i) {
+    world.Step(timeStep, 6, 2);
+    position = body->GetPosition();
+    angle = body->GetAngle();
+  }
+  printf("hello world: %4.3f %4.3f %4.3f\n", position.x, position.y, angle);
+  CHECK(b2Abs(position.x) < 0.01f);
+  CHECK(b2Abs(position.y - 1.01f) < 0.01f);
+  CHECK(b2Abs(angle) < 0.01f);
+}
+
+static bool begin_contact = false;
+static int end_contacts = 0, pre_solves = 0, post_solves = 0;
+class MyContactListener : public b2ContactListener {
+ public:
+  void BeginContact(b2Contact* contact) override {
+    begin_contact = true;
+    CHECK(contact->GetFixtureA() != nullptr && contact->GetFixtureB() != nullptr);
+    CHECK(contact->IsTouching());
+  }
+  void EndContact(b2Contact*) override { ++end_contacts; }
+  void PreSolve(b2Contact* c, const b2Manifold* oldManifold) override {
+    ++pre_solves;
+    CHECK(oldManifold != nullptr);
+    CHECK(c->GetManifold()->pointCount > 0);
+  }
+  void PostSolve(b2Contact*, const b2ContactImpulse* impulse) override {
+    ++post_solves;
+    CHECK(impulse->count > 0);
+  }
+};
+
+static void begin_contact_test() {
+  b2World world = b2World(b2Vec2(0.0f, -10.0f));
+  MyContactListener listener;
+  world.SetContactListener(&listener);
+  b2CircleShape circle;
+  circle.m_radius = 5.f;
+  b2BodyDef bodyDef;
+  bodyDef.type = b2_dynamicBody;
+  b2Body* bodyA = world.CreateBody(&bodyDef);
+  b2Body* bodyB = world.CreateBody(&bodyDef);
+  bodyA->CreateFixture(&circle, 0.0f);
+  bodyB->CreateFixture(&circle, 0.0f);
+  bodyA->SetTransform(b2Vec2(0.f, 0.f), 0.f);
+  bodyB->SetTransform(b2Vec2(100.f, 0.f), 0.f);
+  const float timeStep = 1.f / 60.f;
+  world.Step(timeStep, 6, 2);
+  CHECK(world.GetContactListStart() == world.GetContactListEnd());
+  CHECK(begin_contact == false);
+  bodyB->SetTransform(b2Vec2(1.f, 0.f), 0.f);
+  world.Step(timeStep, 6, 2);
+  CHECK(world.GetContactListStart() != world.GetContactListEnd());
+  CHECK(begin_contact == true);
+  CHECK(pre_solves > 0);
+  CHECK(post_solves > 0);
+  CHECK(bodyA->GetContactCount() == 1);
+  CHECK(bodyA->GetContact(0) == world.GetContactListStart());
+  // separate again: the contact ends
+  bodyB->SetTransform(b2Vec2(100.f, 0.f), 0.f);
+  world.Step(timeStep, 6, 2);
+  world.Step(timeStep, 6, 2);
+  CHECK(end_contacts > 0);
+  CHECK(world.GetContactCount() == 0);
+}
+
+static void polygon_mass_data() {
+  const b2Vec2 center(100.0f, -50.0f);
+  const float hx = 0.5f, hy = 1.5f;
+  const float angle1 = 0.25f;
+  b2PolygonShape polygon1;
+  polygon1.SetAsBox(hx, hy, center, angle1);
+  const float absTol = 2.0f * b2_epsilon;
+  const float relTol = 2.0f * b2_epsilon;
+  CHECK(b2Abs(polygon1.m_centroid.x - center.x) < absTol + relTol * b2Abs(center.x));
+  CHECK(b2Abs(polygon1.m_centroid.y - center.y) < absTol + relTol * b2Abs(center.y));
+  b2Vec2 vertices[4];
+  vertices[0].Set(center.x - hx, center.y - hy);
+  vertices[1].Set(center.x + hx, center.y - hy);
+  vertices[2].Set(center.x - hx, center.y + hy);
+  vertices[3].Set(center.x + hx, center.y + hy);
+  b2PolygonShape polygon2;
+  polygon2.Set(vertices, 4);
+  CHECK(b2Abs(polygon2.m_centroid.x - center.x) < absTol + relTol * b2Abs(center.x));
+  CHECK(b2Abs(polygon2.m_centroid.y - center.y) < absTol + relTol * b2Abs(center.y));
+  const float mass = 4.0f * hx * hy;
+  const float inertia = (mass / 3.0f) * (hx * hx + hy * hy) + mass * b2Dot(center, center);
+  b2MassData massData1;
+  polygon1.ComputeMass(&massData1, 1.0f);
+  CHECK(b2Abs(massData1.center.x - center.x) < absTol + relTol * b2Abs(center.x));
+  CHECK(b2Abs(massData1.center.y - center.y) < absTol + relTol * b2Abs(center.y));
+  CHECK(b2Abs(massData1.mass - mass) < 20.0f * (absTol + relTol * mass));
+  CHECK(b2Abs(massData1.I - inertia) < 40.0f * (absTol + relTol * inertia));
+  b2MassData massData2;
+  polygon2.ComputeMass(&massData2, 1.0f);
+  CHECK(b2Abs(massData2.center.x - center.x) < absTol + relTol * b2Abs(center.x));
+  CHECK(b2Abs(massData2.center.y - center.y) < absTol + relTol * b2Abs(center.y));
+  CHECK(b2Abs(massData2.mass - mass) < 20.0f * (absTol + relTol * mass));
+  CHECK(b2Abs(massData2.I - inertia) < 40.0f * (absTol + relTol * inertia));
+}
+
+static void sweep_math() {
+  b2Sweep sweep;
+  sweep.localCenter.SetZero();
+  sweep.c0.Set(-2.0f, 4.0f);
+  sweep.c.Set(3.0f, 8.0f);
+  sweep.a0 = 0.5f;
+  sweep.a = 5.0f;
+  sweep.alpha0 = 0.0f;
+  b2Transform transform;
+  sweep.GetTransform(&transform, 0.0f);
+  CHECK(transform.p.x == sweep.c0.x);
+  CHECK(transform.p.y == sweep.c0.y);
+  CHECK(transform.q.c == cosf(sweep.a0));
+  CHECK(transform.q.s == sinf(sweep.a0));
+  sweep.GetTransform(&transform, 1.0f);
+  CHECK(transform.p.x == sweep.c.x);
+  CHECK(transform.p.y == sweep.c.y);
+  CHECK(transform.q.c == cosf(sweep.a));
+  CHECK(transform.q.s == sinf(sweep.a));
+}
+
+// locked-world error convention: creation calls made from inside a callback are silent no-ops
+static b2World* g_world = nullptr;
+static b2Body* g_created = (b2Body*)1;
+class LockProbe : public b2ContactListener {
+ public:
+  void BeginContact(b2Contact*) override {
+    CHECK(g_world->IsLocked());
+    b2BodyDef bd;
+    g_created = g_world->CreateBody(&bd);
+  }
+};
+static void locked_world_is_silent() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  g_world = &world;
+  LockProbe probe;
+  world.SetContactListener(&probe);
+  b2CircleShape circle;
+  circle.m_radius = 1.0f;
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  b2Body* a = world.CreateBody(&bd);
+  bd.position.Set(0.5f, 0.0f);
+  b2Body* b = world.CreateBody(&bd);
+  a->CreateFixture(&circle, 1.0f);
+  b->CreateFixture(&circle, 1.0f);
+  int32 before = world.GetBodyCount();
+  world.Step(1.0f / 60.0f, 6, 2);
+  world.Step(1.0f / 60.0f, 6, 2);
+  CHECK(g_created == nullptr);
+  CHECK(world.GetBodyCount() == before);
+  CHECK(!world.IsLocked());
+}
+
+// body list order: non-static bodies at the head in reverse creation order, static at the tail
+static void body_list_order() {
+  b2World world(b2Vec2(0.0f, 0.0f));
+  b2BodyDef sd;
+  b2BodyDef dd;
+  dd.type = b2_dynamicBody;
+  b2Body* s1 = world.CreateBody(&sd);
+  b2Body* d1 = world.CreateBody(&dd);
+  b2Body* d2 = world.CreateBody(&dd);
+  b2Body* s2 = world.CreateBody(&sd);
+  b2Body* expect[4] = {d2, d1, s1, s2};
+  int i = 0;
+  for (b2Body* b = world.GetBodyList(); b; b = b->GetNext()) CHECK(i < 4 && b == expect[i++]);
+  CHECK(i == 4);
+  CHECK(world.GetBodyCount() == 4);
+  world.DestroyBody(d1);
+  CHECK(world.GetBodyCount() == 3);
+}
+
+int main() {
+  hello_world();
+  begin_contact_test();
+  polygon_mass_data();
+  sweep_math();
+  locked_world_is_silent();
+  body_list_order();
+  printf(g_failed ? "FAILED %d checks\n" : "all API checks passed\n", g_failed);
+  return g_failed ? 1 : 0;
+}
