@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — ms per b2World::Step and body-steps/s (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload NAME]
+
+A "step" is one b2World::Step of the workload.  At N=1 the workload is BASELINE.json configs[1]
+("many_pyramids": 100 independent 20-row pyramids, 21 001 bodies, one world); for N>1 every rank
+steps its own copy of that world (independent worlds sharded across GPUs, no data-path
+collective: weak scaling) and `value` is the sum over ranks divided by the max-over-ranks time.
+
+  value  : device-resident throughput — bodies x K / sum of per-step CUDA-event times on the
+           arena's stream; L2 is flushed (256 MiB memset) between timed steps.
+  e2e    : the same metric through the C-ABI with HOST buffers: every step uploads the force
+           accumulators from pinned host memory, runs b2g_step and reads body transforms +
+           velocities back to pinned host memory, all inside the timed region.
+  roofline     : the dominant kernel class by CUDA-event time over a profiled pass, algorithmic
+                 bytes from SURVEY.md §8(d) (table in DESIGN.md) / measured launch time, against
+                 MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline : the reference's own CPU Step (oracle/_ref, compiled from /root/reference) on a
+                 bounded sample of the same workload, rank 0 / N=1 only.
+`--impl reference` times that CPU implementation alone (one world per thread, n_gpus worlds).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# algorithmic bytes per unit of work, SURVEY.md §8(d) (restated in DESIGN.md §5)
+ALGO_BYTES = {
+    "narrowphase": 324.0,       # per contact, box-box
+    "islands": 28.0,            # per body / contact visited
+    "integrate": 62.0,          # per body (60 velocity, 64 position pass)
+    "colour": 16.0,             # per constraint per round (not in the survey: key + 2 body masks)
+    "prepare": 292.0,           # per constraint
+    "warm_start": 180.0,        # per constraint
+    "solve_velocity": 196.0,    # per constraint per iteration (2-point manifold)
+    "solve_position": 136.0,    # per constraint per iteration
+    "store_impulses": 32.0,     # per constraint
+    "finalize": 92.0,           # per body (64 write-back + 28 sleep)
+    "bp_build": 144.0,          # per fixture (AABB + key + node build), spread over 5 kernels
+    "bp_traverse": 32.0 * 15,   # per fixture: 32 B x log2(N_f) traversal upper bound
+    "contact_merge": 32.0,      # per pair
+    "sort_scan": 64.0,          # per key (4-pass radix of 8-byte key/value)
+}
+
+WORKLOADS = {
+    # name: (scene, size, seed, description)
+    "many_pyramids": ("many_pyramids", 100, 0, "100 independent 20-row pyramids (21001 bodies) in one world"),
+    "pyramid": ("pyramid", 20, 0, "testbed pyramid, 20 rows (211 bodies)"),
+    "mixed_100k": ("mixed", 100000, 12345, "100k circles + convex polygons settling into a container, sleeping on"),
+    "mixed_10k": ("mixed", 10000, 12345, "10k circles + convex polygons settling into a container"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=60)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="many_pyramids", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=150)
+    ap.add_argument("--profile-steps", type=int, default=20)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clocks and throttle reasons with nvidia-smi while the timed region runs"""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.stop_flag = threading.Event()
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True,
+                                     timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.sm_max = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU b2World::Step, one world per host thread."""
+    if rank != 0:
+        return
+    from box2d_optimized_b200 import RefScene
+    scene, size, seed, desc = WORKLOADS[args.workload]
+    nworlds = max(1, args.gpus)
+    worlds = [RefScene(scene, size, seed) for _ in range(nworlds)]
+    nb = worlds[0].body_count
+    times = [0.0] * nworlds
+
+    def work(i):
+        worlds[i].step(args.warmup)
+        times[i] = worlds[i].time_steps(args.steps)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(nworlds)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    ms = max(times)
+    value = nb * nworlds * args.steps / (ms / 1000.0)
+    line = {
+        "impl": "reference", "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "bodies_per_world": nb, "worlds": nworlds,
+                   "velocity_iterations": 8, "position_iterations": 3, "dt": 1.0 / 60.0, "sleeping": True,
+                   "continuous": False},
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": nworlds, "kind": "reference",
+                         "sample": f"steps {args.warmup}..{args.warmup + args.steps} of {args.workload}, "
+                                   f"{nworlds} world(s), one thread each (the reference is single-threaded)"},
+        "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from box2d_optimized_b200 import capi, Arena, arena_from_scene, GpuScene
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene_name, size, seed, desc = WORKLOADS[args.workload]
+    lib = capi.load_cuda()
+    # host-side scene construction through the drop-in C++ API; never stepped itself
+    scene = GpuScene(scene_name, size, seed)
+    nb = scene.body_count
+    cap_contacts = max(4096, 8 * nb)
+
+    def fresh_arena():
+        A = arena_from_scene(scene, max_contacts=cap_contacts, device=local_rank)
+        A.find_new_contacts()
+        return A
+
+    P = Arena.params()
+    st = capi.StepStats()
+
+    # ------------------------------------------------------------------ device-resident value
+    A = fresh_arena()
+    ext = torch.cuda.ExternalStream(A.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    for _ in range(args.warmup):
+        A.step(P, st)
+    A.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches = 0
+    contacts_seen, constraints_seen, colours_seen = [], [], []
+    for k in range(args.steps):
+        with torch.cuda.stream(ext):
+            flush.zero_()  # evict the step's working set from L2 (outside the timed bracket)
+        starts[k].record(ext)
+        A.step(P, st)
+        ends[k].record(ext)
+        launches += st.num_launches
+        contacts_seen.append(st.num_contacts)
+        constraints_seen.append(st.num_constraints)
+        colours_seen.append(st.num_colours)
+    A.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.result()
+    elapsed_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms_max = float(t.item())
+    value = nb * world * args.steps / (elapsed_ms_max / 1000.0)
+
+    # ------------------------------------------------------------------ per-kernel roofline pass
+    A.set_kernel_timing(True)
+    for _ in range(args.profile_steps):
+        A.step(P, st)
+    kt = A.kernel_timing()
+    A.set_kernel_timing(False)
+    total_kernel_ms = sum(v[0] for v in kt.values()) or 1.0
+    dom = max(kt, key=lambda k: kt[k][0])
+    dom_ms, dom_launches, dom_units = kt[dom]
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = ALGO_BYTES[dom] * dom_units / max(dom_launches, 1)
+    us_per_launch = 1000.0 * dom_ms / max(dom_launches, 1)
+    achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9 if us_per_launch > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": us_per_launch,
+                "launches_per_step": dom_launches / args.profile_steps,
+                "share_of_kernel_time": dom_ms / total_kernel_ms,
+                "kernel_time_shares": {k: round(v[0] / total_kernel_ms, 4) for k, v in kt.items()}}
+    A.close()
+
+    # ------------------------------------------------------------------ end to end, host buffers
+    B = fresh_arena()
+    hforce = C.c_void_p()
+    hstate = C.c_void_p()
+    capi.check(lib.b2g_host_alloc(C.byref(hforce), nb * 16))
+    capi.check(lib.b2g_host_alloc(C.byref(hstate), nb * 32))
+    force_view = np.ctypeslib.as_array(C.cast(hforce, capi.f32p), shape=(nb, 4))
+    state_view = np.ctypeslib.as_array(C.cast(hstate, capi.f32p), shape=(nb, 8))
+    force_view[:] = 0.0
+
+    def e2e_step():
+        B.upload_forces(hforce, 0, nb)                                   # H2D from pinned memory
+        B.step(P, None)
+        capi.check(lib.b2g_download_body_state_async(B.h, 0, nb, hstate))  # D2H into pinned memory
+        B.synchronize()
+
+    for _ in range(args.warmup):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t.item())
+    e2e_value = nb * world * args.steps / (e2e_ms_max / 1000.0)
+    assert np.isfinite(state_view).all()
+    B.close()
+    lib.b2g_host_free(hforce)
+    lib.b2g_host_free(hstate)
+
+    # ------------------------------------------------------------------ CPU baseline (reference)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from box2d_optimized_b200 import RefScene
+            r = RefScene(scene_name, size, seed)
+            r.step(args.warmup)
+            n = min(args.cpu_sample_steps, args.steps)
+            ms = r.time_steps(n)
+            cpu = {"value": nb * n / (ms / 1000.0), "unit": "body-steps/s", "cores": 1, "kind": "reference",
+                   "ms_per_step": ms / n,
+                   "sample": f"steps {args.warmup}..{args.warmup + n} of {args.workload} on 1 host core "
+                             "(the reference is single-threaded), oracle/_ref/libb2ref.so compiled from "
+                             "/root/reference with -O3 -DNDEBUG"}
+        except Exception as exc:  # the oracle is optional for the product, mandatory for the number
+            cpu = {"value": None, "unit": "body-steps/s", "cores": 0, "kind": "reference",
+                   "sample": f"unavailable: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "bodies_per_world": nb, "worlds": world,
+                       "contacts_mean": float(np.mean(contacts_seen)), "constraints_mean": float(np.mean(constraints_seen)),
+                       "colours_max": int(max(colours_seen)), "velocity_iterations": 8, "position_iterations": 3,
+                       "dt": 1.0 / 60.0, "sleeping": True, "continuous": False, "solver": "graph-coloured",
+                       "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",
+                       "timed_window": f"steps {args.warmup}..{args.warmup + args.steps}"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": e2e_ms_max / args.steps,
+                    "h2d_bytes_per_step": nb * 12, "d2h_bytes_per_step": nb * 32},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -129,6 +129,18 @@ class Arena:
     def set_profiling(self, on=True):
         self.lib.b2g_set_profiling(self.h, int(on))
 
+    def set_kernel_timing(self, on=True):
+        self.lib.b2g_set_kernel_timing(self.h, int(on))
+
+    def kernel_timing(self):
+        """{class name: (total ms, launches, summed work items)} since timing was switched on"""
+        out = {}
+        for c in range(self.lib.b2g_kernel_class_count()):
+            ms, n, u = C.c_double(), C.c_int64(), C.c_double()
+            self.lib.b2g_get_kernel_timing(self.h, c, C.byref(ms), C.byref(n), C.byref(u))
+            out[self.lib.b2g_kernel_class_name(c).decode()] = (ms.value, n.value, u.value)
+        return out
+
     def set_inv_dt0(self, v):
         self.lib.b2g_set_inv_dt0(self.h, float(v))
 

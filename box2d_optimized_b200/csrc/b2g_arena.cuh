@@ -13,6 +13,7 @@
 #define B2G_MAX_COLOURS 24          // colours solved by parallel launches
 #define B2G_OVERFLOW_COLOUR B2G_MAX_COLOURS  // serial overflow bucket
 #define B2G_MAX_POS_ITERS 16
+#define B2G_KT_MAX 2048  // timed launches per step when per-kernel timing is on
 
 // device-side counters, zeroed at the start of every step; mirrored to pinned host memory
 struct StepCounts {
@@ -56,6 +57,13 @@ struct b2gArena {
   float invDt0;
   long long launches;
   long long launchesAtStepStart;
+  // per-kernel-class CUDA-event timing (off by default: it serialises launches)
+  int kernelTiming, ktCount;
+  cudaEvent_t ktEv[2 * B2G_KT_MAX];
+  int ktClass[B2G_KT_MAX];
+  double ktUnits[B2G_KT_MAX];
+  double ktMs[16], ktUnitsSum[16];
+  long long ktLaunches[16];
 
   // bodies
   float4 *pos, *vel, *xf, *mass, *center, *force;

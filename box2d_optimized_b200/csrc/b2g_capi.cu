@@ -26,10 +26,53 @@ static int set_err(const char* what, const char* detail) {
   } while (0)
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
-#define LAUNCH(A, kernel, grid, block, ...)                       \
+// kernel classes for the per-kernel timing of bench.py's roofline line (b2g_get_kernel_timing)
+enum KClass {
+  KC_NARROWPHASE, KC_ISLANDS, KC_INTEGRATE, KC_COLOUR, KC_PREPARE, KC_WARM_START, KC_SOLVE_VELOCITY,
+  KC_SOLVE_POSITION, KC_STORE_IMPULSES, KC_FINALIZE, KC_BP_BUILD, KC_BP_TRAVERSE, KC_CONTACT_MERGE, KC_SORT_SCAN,
+  KC_COUNT
+};
+static const char* kClassNames[KC_COUNT] = {
+    "narrowphase", "islands", "integrate", "colour", "prepare", "warm_start", "solve_velocity", "solve_position",
+    "store_impulses", "finalize", "bp_build", "bp_traverse", "contact_merge", "sort_scan"};
+
+static inline void ktime_begin(b2gArena* A, int cls, double units) {
+  if (!A->kernelTiming || A->ktCount >= B2G_KT_MAX) return;
+  cudaEventRecord(A->ktEv[2 * A->ktCount], A->stream);
+  A->ktClass[A->ktCount] = cls;
+  A->ktUnits[A->ktCount] = units;
+}
+static inline void ktime_end(b2gArena* A) {
+  if (!A->kernelTiming || A->ktCount >= B2G_KT_MAX) return;
+  cudaEventRecord(A->ktEv[2 * A->ktCount + 1], A->stream);
+  A->ktCount++;
+}
+// called after a stream sync: fold this step's event pairs into the per-class totals
+static void ktime_collect(b2gArena* A) {
+  for (int i = 0; i < A->ktCount; ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, A->ktEv[2 * i], A->ktEv[2 * i + 1]);
+    int c = A->ktClass[i];
+    A->ktMs[c] += ms;
+    A->ktLaunches[c] += 1;
+    A->ktUnitsSum[c] += A->ktUnits[i];
+  }
+  A->ktCount = 0;
+}
+
+// `units` = the work items of this launch in the unit SURVEY §8(d) quotes bytes for
+#define LAUNCH(A, cls, units, kernel, grid, block, ...)           \
   do {                                                            \
+    ktime_begin((A), (cls), (double)(units));                     \
     kernel<<<(grid), (block), 0, (A)->stream>>>(__VA_ARGS__);     \
+    ktime_end((A));                                               \
     (A)->launches++;                                              \
+  } while (0)
+#define TIMED(A, cls, units, stmt) \
+  do {                             \
+    ktime_begin((A), (cls), (double)(units)); \
+    stmt;                          \
+    ktime_end((A));                \
   } while (0)
 
 extern "C" const char* b2g_last_error(void) { return g_err; }
@@ -110,6 +153,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   A->roundsHint = 8;
   CK(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&A->ev[i]));
+  for (int i = 0; i < 2 * B2G_KT_MAX; ++i) CK(cudaEventCreate(&A->ktEv[i]));
 
   const int nb = A->capBodies, nf = A->capFixtures, nc = A->capContacts, nj = A->capJoints;
   CK(dalloc(&A->pos, nb));
@@ -234,6 +278,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   cudaFreeHost(A->hCounts);
   cudaFreeHost(A->hostStage);
   for (int i = 0; i < 5; ++i) cudaEventDestroy(A->ev[i]);
+  for (int i = 0; i < 2 * B2G_KT_MAX; ++i) cudaEventDestroy(A->ktEv[i]);
   cudaStreamDestroy(A->stream);
   free(A);
   return B2G_OK;
@@ -370,25 +415,26 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
     int rc = reset_bounds(A);
     if (rc) return rc;
     CK(cudaMemsetAsync(&A->dCounts->numPairs, 0, sizeof(int), A->stream));
-    LAUNCH(A, k_update_aabbs, div_up(nf, 256), 256, nf, A->fBody, A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags,
+    LAUNCH(A, KC_BP_BUILD, nf, k_update_aabbs, div_up(nf, 256), 256, nf, A->fBody, A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags,
            A->xf, A->fAabb, A->fRadius, A->aabbAllDirty, A->dCounts);
     A->aabbAllDirty = 0;
-    LAUNCH(A, k_morton_keys, div_up(nf, 256), 256, nf, A->fAabb, A->fTypeFlags, A->fBody, A->bworld, A->dCounts,
+    LAUNCH(A, KC_BP_BUILD, nf, k_morton_keys, div_up(nf, 256), 256, nf, A->fAabb, A->fTypeFlags, A->fBody, A->bworld, A->dCounts,
            A->mortonKeys, A->leafFixture, A->numWorlds);
     size_t tb = A->cubTempBytes;
-    CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb, A->mortonKeys, A->mortonKeysSorted, A->leafFixture,
-                                       A->leafFixtureSorted, nf, 0, 32 + (A->numWorlds > 1 ? A->worldBits : 0),
-                                       A->stream));
-    LAUNCH(A, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted, A->fAabb, A->fBody,
+    TIMED(A, KC_SORT_SCAN, nf,
+          CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb, A->mortonKeys, A->mortonKeysSorted, A->leafFixture,
+                                             A->leafFixtureSorted, nf, 0,
+                                             32 + (A->numWorlds > 1 ? A->worldBits : 0), A->stream)));
+    LAUNCH(A, KC_BP_BUILD, nf, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted, A->fAabb, A->fBody,
            A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->leafKey, A->worldFirst, A->worldLast,
            A->numWorlds);
     CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
     CK(cudaMemsetAsync(A->nodeVisit, 0, sizeof(int) * nf, A->stream));
     if (nf > 1) {
-      LAUNCH(A, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange, A->leafParent);
-      LAUNCH(A, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent, A->nodeRange,
+      LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange, A->leafParent);
+      LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent, A->nodeRange,
              A->nodeBoxL, A->nodeBoxR, A->nodeMaxKey, A->nodeVisit);
-      LAUNCH(A, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->nodeRange, A->nodeBoxL,
+      LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->nodeRange, A->nodeBoxL,
              A->nodeBoxR, A->nodeMaxKey, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->pairKeys,
              A->capContacts, A->fixBits, A->dCounts);
     }
@@ -405,16 +451,17 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
   if (nNew > 0) {
     size_t tb = A->cubTempBytes;
     // sorted straight into the new buffer's key array, then merged in place
-    CK(cub::DeviceRadixSort::SortKeys(A->cubTemp, tb, A->pairKeys, N.key, nNew, 0,
-                                      3 + 2 * A->fixBits, A->stream));
+    TIMED(A, KC_SORT_SCAN, nNew,
+          CK(cub::DeviceRadixSort::SortKeys(A->cubTemp, tb, A->pairKeys, N.key, nNew, 0, 3 + 2 * A->fixBits,
+                                            A->stream)));
     CK(cudaMemsetAsync(A->oldPersist, 0, nOld > 0 ? nOld : 1, A->stream));
-    LAUNCH(A, k_contact_merge, div_up(nNew, 256), 256, nNew, N.key, nOld, O, N, A->oldPersist, A->fixBits, A->fBody,
+    LAUNCH(A, KC_CONTACT_MERGE, nNew, k_contact_merge, div_up(nNew, 256), 256, nNew, N.key, nOld, O, N, A->oldPersist, A->fixBits, A->fBody,
            A->fTypeFlags, A->fMaterial);
   } else if (nOld > 0) {
     CK(cudaMemsetAsync(A->oldPersist, 0, nOld, A->stream));
   }
   if (nOld > 0) {
-    LAUNCH(A, k_contact_dead, div_up(nOld, 256), 256, nOld, O, A->oldPersist, A->fTypeFlags, A->bflags, A->force,
+    LAUNCH(A, KC_CONTACT_MERGE, nOld, k_contact_dead, div_up(nOld, 256), 256, nOld, O, A->oldPersist, A->fTypeFlags, A->bflags, A->force,
            A->dCounts, recordEvents, A->endEvents, A->capContacts);
   }
   A->cur ^= 1;
@@ -455,7 +502,7 @@ extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
   CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
   if (A->profiling) CK(cudaEventRecord(A->ev[0], A->stream));
   if (nc > 0) {
-    LAUNCH(A, k_narrowphase, div_up(nc, 128), 128, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
+    LAUNCH(A, KC_NARROWPHASE, nc, k_narrowphase, div_up(nc, 128), 128, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
            A->bflags, A->dCounts, P->record_events, A->beginEvents, A->endEvents, A->capContacts);
   }
   if (A->profiling) CK(cudaEventRecord(A->ev[1], A->stream));
@@ -480,34 +527,35 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
 
   if (h > 0.0f && nb > 0) {
     // ---- islands ---------------------------------------------------------------------
-    LAUNCH(A, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent, A->islandAwake,
+    LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent, A->islandAwake,
            A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest);
-    if (nc > 0) LAUNCH(A, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
-    if (nj > 0) LAUNCH(A, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
-    LAUNCH(A, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island, A->islandAwake);
-    LAUNCH(A, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->vel, A->mass,
+    if (nc > 0) LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
+    if (nj > 0) LAUNCH(A, KC_ISLANDS, nj, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
+    LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island, A->islandAwake);
+    LAUNCH(A, KC_INTEGRATE, nb, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->vel, A->mass,
            A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y), A->dCounts);
 
     // ---- constraint list + colouring -------------------------------------------------
     if (nc > 0) {
-      LAUNCH(A, k_mark_active, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->island, A->islandAwake, A->activeFlag,
+      LAUNCH(A, KC_COLOUR, nc, k_mark_active, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->island, A->islandAwake, A->activeFlag,
              A->recolour);
       A->recolour = 0;
       size_t tb = A->cubTempBytes;
-      CK(cub::DeviceSelect::Flagged(A->cubTemp, tb, thrust::counting_iterator<int>(0), A->activeFlag, A->activeList,
-                                    &A->dCounts->numActive, nc, A->stream));
+      TIMED(A, KC_SORT_SCAN, nc,
+            CK(cub::DeviceSelect::Flagged(A->cubTemp, tb, thrust::counting_iterator<int>(0), A->activeFlag,
+                                          A->activeList, &A->dCounts->numActive, nc, A->stream)));
       const int* nAct = &A->dCounts->numActive;
       if (P->solver_mode == B2G_SOLVER_COLOURED) {
         int grid = div_up(nc, 256);
         if (grid > 148 * 8) grid = 148 * 8;
-        LAUNCH(A, k_colour_begin, grid, 256, nAct, A->activeList, C, A->mass, A->colourMask, A->dCounts);
+        LAUNCH(A, KC_COLOUR, nc, k_colour_begin, grid, 256, nAct, A->activeList, C, A->mass, A->colourMask, A->dCounts);
         int round = 0;
         int batch = A->roundsHint;
         while (true) {
           CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
           for (int r = 0; r < batch; ++r, ++round) {
-            LAUNCH(A, k_colour_propose, grid, 256, nAct, A->activeList, C, A->mass, A->bodyBest, round);
-            LAUNCH(A, k_colour_commit, grid, 256, nAct, A->activeList, C, A->mass, A->colourMask, A->bodyBest, round,
+            LAUNCH(A, KC_COLOUR, nc, k_colour_propose, grid, 256, nAct, A->activeList, C, A->mass, A->bodyBest, round);
+            LAUNCH(A, KC_COLOUR, nc, k_colour_commit, grid, 256, nAct, A->activeList, C, A->mass, A->colourMask, A->bodyBest, round,
                    A->dCounts, r == batch - 1);
           }
           int rc = read_counts(A);
@@ -536,10 +584,11 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
         colourFirst[B2G_MAX_COLOURS + 1] = acc;
         numOverflow = A->hCounts->colourCount[B2G_MAX_COLOURS];
         if (numActive > 0) {
-          LAUNCH(A, k_colour_keys, grid, 256, nAct, A->activeList, C, A->colourKey);
+          LAUNCH(A, KC_COLOUR, numActive, k_colour_keys, grid, 256, nAct, A->activeList, C, A->colourKey);
           size_t tb2 = A->cubTempBytes;
-          CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb2, A->colourKey, A->colourKeySorted, A->activeList,
-                                             A->sortedList, numActive, 0, 8, A->stream));
+          TIMED(A, KC_SORT_SCAN, numActive,
+                CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb2, A->colourKey, A->colourKeySorted, A->activeList,
+                                                   A->sortedList, numActive, 0, 8, A->stream)));
         }
       } else {
         int rc = read_counts(A);
@@ -555,19 +604,19 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
     SolverPlanes& S = A->planes;
     const bool coloured = P->solver_mode == B2G_SOLVER_COLOURED;
     if (numActive > 0) {
-      LAUNCH(A, k_prepare, div_up(numActive, 128), 128, numActive, A->sortedList, C, A->fRadius, A->bflags, A->island,
+      LAUNCH(A, KC_PREPARE, numActive, k_prepare, div_up(numActive, 128), 128, numActive, A->sortedList, C, A->fRadius, A->bflags, A->island,
              S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
       if (P->warm_starting) {
         if (coloured) {
           for (int c = 0; c < numColours; ++c) {
             int n = colourFirst[c + 1] - colourFirst[c];
-            if (n > 0) LAUNCH(A, k_warm_start, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
+            if (n > 0) LAUNCH(A, KC_WARM_START, n, k_warm_start, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
           }
           if (numOverflow > 0)
-            LAUNCH(A, k_warm_start_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
+            LAUNCH(A, KC_WARM_START, numOverflow, k_warm_start_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
                    A->vel);
         } else {
-          LAUNCH(A, k_warm_start_seq, 1, 1, 0, numActive, S, A->vel);
+          LAUNCH(A, KC_WARM_START, numActive, k_warm_start_seq, 1, 1, 0, numActive, S, A->vel);
         }
       }
       for (int it = 0; it < P->velocity_iterations; ++it) {
@@ -575,18 +624,18 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
           for (int c = 0; c < numColours; ++c) {
             int n = colourFirst[c + 1] - colourFirst[c];
             if (n > 0)
-              LAUNCH(A, k_solve_velocity, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
+              LAUNCH(A, KC_SOLVE_VELOCITY, n, k_solve_velocity, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
           }
           if (numOverflow > 0)
-            LAUNCH(A, k_solve_velocity_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
+            LAUNCH(A, KC_SOLVE_VELOCITY, numOverflow, k_solve_velocity_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
                    A->vel);
         } else {
-          LAUNCH(A, k_solve_velocity_seq, 1, 1, 0, numActive, S, A->vel);
+          LAUNCH(A, KC_SOLVE_VELOCITY, numActive, k_solve_velocity_seq, 1, 1, 0, numActive, S, A->vel);
         }
       }
-      LAUNCH(A, k_store_impulses, div_up(numActive, 256), 256, numActive, S, C);
+      LAUNCH(A, KC_STORE_IMPULSES, numActive, k_store_impulses, div_up(numActive, 256), 256, numActive, S, C);
     }
-    LAUNCH(A, k_integrate_positions, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
+    LAUNCH(A, KC_INTEGRATE, nb, k_integrate_positions, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
            h);
     if (numActive > 0) {
       for (int it = 0; it < P->position_iterations; ++it) {
@@ -594,20 +643,20 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
           for (int c = 0; c < numColours; ++c) {
             int n = colourFirst[c + 1] - colourFirst[c];
             if (n > 0)
-              LAUNCH(A, k_solve_position, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->pos,
+              LAUNCH(A, KC_SOLVE_POSITION, n, k_solve_position, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->pos,
                      A->croot, A->islandPen, A->capBodies, it);
           }
           if (numOverflow > 0)
-            LAUNCH(A, k_solve_position_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
+            LAUNCH(A, KC_SOLVE_POSITION, numOverflow, k_solve_position_seq, 1, 1, colourFirst[B2G_MAX_COLOURS], colourFirst[B2G_MAX_COLOURS + 1], S,
                    A->pos, A->croot, A->islandPen, A->capBodies, it);
         } else {
-          LAUNCH(A, k_solve_position_seq, 1, 1, 0, numActive, S, A->pos, A->croot, A->islandPen, A->capBodies, it);
+          LAUNCH(A, KC_SOLVE_POSITION, numActive, k_solve_position_seq, 1, 1, 0, numActive, S, A->pos, A->croot, A->islandPen, A->capBodies, it);
         }
       }
     }
-    LAUNCH(A, k_finalize_bodies, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
+    LAUNCH(A, KC_FINALIZE, nb, k_finalize_bodies, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
            A->center, A->xf, A->force, A->islandMinSleep, h, P->allow_sleep);
-    LAUNCH(A, k_sleep_and_clear, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->islandMinSleep,
+    LAUNCH(A, KC_FINALIZE, nb, k_sleep_and_clear, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->islandMinSleep,
            A->islandPen, A->capBodies, P->position_iterations, A->vel, A->force, P->allow_sleep, P->clear_forces,
            A->dCounts);
     if (prof) CK(cudaEventRecord(A->ev[2], A->stream));
@@ -626,6 +675,10 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
     if (rc) return rc;
   }
 
+  if (A->kernelTiming) {
+    CK(cudaStreamSynchronize(A->stream));
+    ktime_collect(A);
+  }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     // hCounts was last read inside find_new_contacts, after every counter of this step was final
@@ -793,6 +846,29 @@ extern "C" void* b2g_stream(b2gArena* A) { return A ? (void*)A->stream : nullptr
 extern "C" int b2g_set_profiling(b2gArena* A, int32_t on) {
   if (!A) return B2G_ERR_INVALID;
   A->profiling = on;
+  return B2G_OK;
+}
+extern "C" int b2g_set_kernel_timing(b2gArena* A, int32_t on) {
+  if (!A) return B2G_ERR_INVALID;
+  A->kernelTiming = on;
+  A->ktCount = 0;
+  for (int c = 0; c < KC_COUNT; ++c) {
+    A->ktMs[c] = 0.0;
+    A->ktLaunches[c] = 0;
+    A->ktUnitsSum[c] = 0.0;
+  }
+  return B2G_OK;
+}
+extern "C" int b2g_kernel_class_count(void) { return KC_COUNT; }
+extern "C" const char* b2g_kernel_class_name(int32_t cls) {
+  return (cls >= 0 && cls < KC_COUNT) ? kClassNames[cls] : "";
+}
+extern "C" int b2g_get_kernel_timing(b2gArena* A, int32_t cls, double* total_ms, int64_t* launches,
+                                     double* units) {
+  if (!A || cls < 0 || cls >= KC_COUNT) return B2G_ERR_INVALID;
+  if (total_ms) *total_ms = A->ktMs[cls];
+  if (launches) *launches = A->ktLaunches[cls];
+  if (units) *units = A->ktUnitsSum[cls];
   return B2G_OK;
 }
 extern "C" int b2g_set_inv_dt0(b2gArena* A, float v) {

@@ -242,6 +242,14 @@ int b2g_synchronize(b2gArena* arena);
 /* cudaStream_t the arena launches on (for external CUDA-event timing). */
 void* b2g_stream(b2gArena* arena);
 int b2g_set_profiling(b2gArena* arena, int32_t on);
+/* Per-kernel-class CUDA-event timing on the arena's stream, for the roofline line of bench.py
+ * (the reference's only profile is b2Profile's four wall-clock phases, b2_time_step.h:29-36).
+ * While on, every launch is bracketed by two events; totals accumulate until switched on again.
+ * `units` returns the summed work items (bodies / fixtures / contacts / constraints). */
+int b2g_set_kernel_timing(b2gArena* arena, int32_t on);
+int b2g_kernel_class_count(void);
+const char* b2g_kernel_class_name(int32_t cls);
+int b2g_get_kernel_timing(b2gArena* arena, int32_t cls, double* total_ms, int64_t* launches, double* units);
 /* previous step's 1/dt (m_inv_dt0, b2_world.cpp:69,1162) — exposed for tests. */
 int b2g_set_inv_dt0(b2gArena* arena, float inv_dt0);
 
