@@ -243,7 +243,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": us_per_launch,
-                "launches_per_step": dom_launches / args.profile_steps,
+                "launches_per_step": dom_launches / max(args.profile_steps, 1),
                 "share_of_kernel_time": dom_ms / total_kernel_ms,
                 "kernel_time_shares": {k: round(v[0] / total_kernel_ms, 4) for k, v in kt.items()}}
     A.close()
