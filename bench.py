@@ -59,7 +59,11 @@ WORKLOADS = {
     "pyramid": ("pyramid", 20, 0, "testbed pyramid, 20 rows (211 bodies)"),
     "mixed_100k": ("mixed", 100000, 12345, "100k circles + convex polygons settling into a container, sleeping on"),
     "mixed_10k": ("mixed", 10000, 12345, "10k circles + convex polygons settling into a container"),
+    # batched independent worlds in ONE arena per GPU (world id in the broadphase key), sharded
+    # round-robin over ranks: size = worlds per GPU
+    "pyramid_worlds": ("pyramid", 20, 0, "512 independent 20-row pyramid worlds per GPU (108k bodies), one arena"),
 }
+WORLDS_PER_GPU = {"pyramid_worlds": 512}
 
 
 def parse():
@@ -129,7 +133,13 @@ def run_reference(args, rank, world):
         return
     from box2d_optimized_b200 import RefScene
     scene, size, seed, desc = WORKLOADS[args.workload]
+    # one world per GPU of our arm for the single-world workloads; for the batched workloads a
+    # bounded sample of one world per host thread (the per-world cost is identical)
     nworlds = max(1, args.gpus)
+    ncpu = os.cpu_count() or 1
+    if args.workload in WORLDS_PER_GPU:
+        nworlds = min(ncpu, WORLDS_PER_GPU[args.workload] * max(1, args.gpus))
+    nworlds = min(nworlds, max(1, ncpu))
     worlds = [RefScene(scene, size, seed) for _ in range(nworlds)]
     nb = worlds[0].body_count
     times = [0.0] * nworlds
@@ -182,8 +192,17 @@ def main():
     nb = scene.body_count
     cap_contacts = max(4096, 8 * nb)
 
+    from box2d_optimized_b200.sharding import aggregate, shard_worlds
+    per_gpu = WORLDS_PER_GPU.get(args.workload, 1)
+    my_worlds = shard_worlds(per_gpu * world, rank, world)   # independent worlds, no data-path collective
+    copies = len(my_worlds)
+    nb_world = nb
+    nb = nb_world * copies
+    cap_contacts = max(4096, 8 * nb)
+
     def fresh_arena():
-        A = arena_from_scene(scene, max_contacts=cap_contacts, device=local_rank)
+        A = arena_from_scene(scene, max_contacts=cap_contacts, device=local_rank, copies=copies,
+                             num_worlds=copies)
         A.find_new_contacts()
         return A
 
@@ -220,12 +239,7 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.result()
     elapsed_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms_max = float(t.item())
-    value = nb * world * args.steps / (elapsed_ms_max / 1000.0)
+    _, elapsed_ms_max, value = aggregate(nb * args.steps, elapsed_ms, device=f"cuda:{local_rank}")
 
     # ------------------------------------------------------------------ per-kernel roofline pass
     A.set_kernel_timing(True)
@@ -274,12 +288,7 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1000.0
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t.item())
-    e2e_value = nb * world * args.steps / (e2e_ms_max / 1000.0)
+    _, e2e_ms_max, e2e_value = aggregate(nb * args.steps, e2e_ms, device=f"cuda:{local_rank}")
     assert np.isfinite(state_view).all()
     B.close()
     lib.b2g_host_free(hforce)
@@ -308,8 +317,8 @@ def main():
             "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "bodies_per_world": nb, "worlds": world,
-                       "contacts_mean": float(np.mean(contacts_seen)), "constraints_mean": float(np.mean(constraints_seen)),
+            "config": {"workload": args.workload, "description": desc, "bodies_per_world": nb_world, "worlds": per_gpu * world,
+                       "worlds_per_gpu": per_gpu, "contacts_mean": float(np.mean(contacts_seen)), "constraints_mean": float(np.mean(constraints_seen)),
                        "colours_max": int(max(colours_seen)), "velocity_iterations": 8, "position_iterations": 3,
                        "dt": 1.0 / 60.0, "sleeping": True, "continuous": False, "solver": "graph-coloured",
                        "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",

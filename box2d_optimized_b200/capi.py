@@ -216,6 +216,30 @@ def load_ref():
     return _ref
 
 
+_oracle = None
+
+
+def oracle_path():
+    return os.path.join(ROOT, "oracle", "libb2oracle.so")
+
+
+def load_oracle():
+    """TEST ONLY: the plain-C restatement (oracle/b2_oracle.c).  Never used by the product path."""
+    global _oracle
+    if _oracle is None:
+        p = oracle_path()
+        if not os.path.exists(p):
+            raise B2GError(f"{p} is missing: `make -C oracle port`")
+        lib = C.CDLL(p)
+        lib.b2o_compute_aabbs.argtypes = [C.c_int, i32p, i32p, f32p, f32p, f32p]
+        lib.b2o_collide_pairs.argtypes = [C.c_int, i32p, i32p, f32p, i32p, i32p, f32p, f32p, f32p]
+        lib.b2o_find_pairs.argtypes = [C.c_int, f32p, i32p, i32p, u8p, i32p, C.c_int, i32p]
+        lib.b2o_solve.argtypes = [C.c_int, f32p, f32p, f32p, C.c_int, i32p, f32p, f32p, f32p, C.c_float, C.c_float,
+                                  C.c_int, C.c_int, C.c_int, f32p, f32p, i32p]
+        _oracle = lib
+    return _oracle
+
+
 def fp(a):
     return a.ctypes.data_as(f32p) if a is not None else None
 
