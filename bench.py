@@ -51,6 +51,9 @@ ALGO_BYTES = {
     "bp_traverse": 32.0 * 15,   # per fixture: 32 B x log2(N_f) traversal upper bound
     "contact_merge": 32.0,      # per pair
     "sort_scan": 64.0,          # per key (4-pass radix of 8-byte key/value)
+    # whole island solve per constraint per step at 8/3 iterations: prepare 292 + warm start 180 +
+    # 8 x 196 + 3 x 136 + store 32 (the N_t term of SURVEY §8d's B_step)
+    "fused_solve": 2480.0,
 }
 
 WORKLOADS = {

@@ -24,6 +24,8 @@ struct StepCounts {
   int numAwake;
   int beginCount, endCount;
   int lastUsefulRound;  // 1 + index of the last colouring round that coloured something
+  int numBig;           // constraints of islands too large for a fused tile
+  int numColours, numOverflow, maxIslandBodies;
   int colourCount[B2G_MAX_COLOURS + 1];
   unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
 };
@@ -62,8 +64,8 @@ struct b2gArena {
   cudaEvent_t ktEv[2 * B2G_KT_MAX];
   int ktClass[B2G_KT_MAX];
   double ktUnits[B2G_KT_MAX];
-  double ktMs[16], ktUnitsSum[16];
-  long long ktLaunches[16];
+  double ktMs[20], ktUnitsSum[20];
+  long long ktLaunches[20];
 
   // bodies
   float4 *pos, *vel, *xf, *mass, *center, *force;
@@ -76,6 +78,12 @@ struct b2gArena {
   uint32_t* islandPen;     // [B2G_MAX_POS_ITERS][capBodies] float bits of max penetration per iteration
   unsigned long long* colourMask;  // per body: colours used by its constraints
   unsigned long long* bodyBest;    // per body: best proposal this round
+  // fused solver: island-sorted body slots and bins
+  int *islandCount, *islandStart, *islandCursor, *bodySlot, *slotBody, *binFirst, *binEnd, *cbin;
+  unsigned int *conKeys, *conKeysSorted;
+  int *conVals;
+  int nbinsMax, bigMode, lastMaxIsland;
+  size_t fusedSmemSet;
 
   // fixtures + shapes
   int* fBody;

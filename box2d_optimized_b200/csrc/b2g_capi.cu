@@ -10,6 +10,8 @@
 #include <cstring>
 #include <vector>
 #include "b2g_broadphase.cuh"
+#include "b2g_fused.cuh"
+#include <thrust/iterator/transform_iterator.h>
 
 static thread_local char g_err[512] = "";
 static int set_err(const char* what, const char* detail) {
@@ -30,11 +32,11 @@ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 enum KClass {
   KC_NARROWPHASE, KC_ISLANDS, KC_INTEGRATE, KC_COLOUR, KC_PREPARE, KC_WARM_START, KC_SOLVE_VELOCITY,
   KC_SOLVE_POSITION, KC_STORE_IMPULSES, KC_FINALIZE, KC_BP_BUILD, KC_BP_TRAVERSE, KC_CONTACT_MERGE, KC_SORT_SCAN,
-  KC_COUNT
+  KC_FUSED_SOLVE, KC_COUNT
 };
 static const char* kClassNames[KC_COUNT] = {
     "narrowphase", "islands", "integrate", "colour", "prepare", "warm_start", "solve_velocity", "solve_position",
-    "store_impulses", "finalize", "bp_build", "bp_traverse", "contact_merge", "sort_scan"};
+    "store_impulses", "finalize", "bp_build", "bp_traverse", "contact_merge", "sort_scan", "fused_solve"};
 
 static inline void ktime_begin(b2gArena* A, int cls, double units) {
   if (!A->kernelTiming || A->ktCount >= B2G_KT_MAX) return;
@@ -171,6 +173,14 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->islandPen, (size_t)nb * B2G_MAX_POS_ITERS));
   CK(dalloc(&A->colourMask, nb));
   CK(dalloc(&A->bodyBest, nb));
+  CK(dalloc(&A->islandCount, nb));
+  CK(dalloc(&A->islandStart, nb));
+  CK(dalloc(&A->islandCursor, nb));
+  CK(dalloc(&A->bodySlot, nb));
+  CK(dalloc(&A->slotBody, nb));
+  A->nbinsMax = nb / 32 + 8;
+  CK(dalloc(&A->binFirst, A->nbinsMax));
+  CK(dalloc(&A->binEnd, A->nbinsMax));
 
   CK(dalloc(&A->fBody, nf));
   CK(dalloc(&A->fShapeOff, nf));
@@ -216,6 +226,10 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->colourKey, nc));
   CK(dalloc(&A->colourKeySorted, nc));
   CK(dalloc(&A->croot, nc));
+  CK(dalloc(&A->cbin, nc));
+  CK(dalloc(&A->conKeys, nc));
+  CK(dalloc(&A->conKeysSorted, nc));
+  CK(dalloc(&A->conVals, nc));
   SolverPlanes& S = A->planes;
   CK(dalloc(&S.nf, nc));
   CK(dalloc(&S.r1, nc));
@@ -251,6 +265,14 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   cub::DeviceSelect::Flagged(nullptr, t, thrust::counting_iterator<int>(0), A->activeFlag, A->activeList,
                              &A->dCounts->numActive, nc, A->stream);
   need = t > need ? t : need;
+  cub::DeviceRadixSort::SortPairs(nullptr, t, A->conKeys, A->conKeysSorted, A->conVals, A->sortedList, nc, 0, 32,
+                                  A->stream);
+  need = t > need ? t : need;
+  {
+    auto in = thrust::make_transform_iterator(A->islandCount, FusedCountOp{1024});
+    cub::DeviceScan::ExclusiveSum(nullptr, t, in, A->islandStart, nb, A->stream);
+    need = t > need ? t : need;
+  }
   A->cubTempBytes = need + 256;
   CK(cudaMalloc(&A->cubTemp, A->cubTempBytes));
   CK(cudaStreamSynchronize(A->stream));
@@ -263,7 +285,8 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   cudaSetDevice(A->device);
   cudaStreamSynchronize(A->stream);
   void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent,
-                  A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->fBody,
+                  A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
+                  A->binFirst, A->binEnd, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
                   A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->oldPersist, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
@@ -482,58 +505,32 @@ extern "C" int b2g_find_new_contacts(b2gArena* A) {
 // ---------------------------------------------------------------------------------------------
 // the step
 // ---------------------------------------------------------------------------------------------
-static int step_check(b2gArena* A, const b2gStepParams* P) {
-  if (!A || !P) return B2G_ERR_INVALID;
-  if (P->position_iterations > B2G_MAX_POS_ITERS || P->position_iterations < 0 || P->velocity_iterations < 0) {
-    set_err("b2g_step", "iteration counts out of range");
-    return B2G_ERR_INVALID;
-  }
-  return B2G_OK;
-}
+// ---------------------------------------------------------------------------------------------
+// Solve, list-order / per-colour-launch path: used by B2G_SOLVER_SEQUENTIAL (parity vehicle).  One
+// kernel per reference loop, constraints addressed through global body arrays.
+// ---------------------------------------------------------------------------------------------
+struct SolveOut {
+  int numActive = 0, numColours = 0, numOverflow = 0, rounds = 0;
+};
 
-// first half of Step: b2ContactManager::Collide (b2_world.cpp:1134-1138)
-extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
-  int rc0 = step_check(A, P);
-  if (rc0) return rc0;
-  CK(cudaSetDevice(A->device));
-  A->launchesAtStepStart = A->launches;
-  const int nc = A->nContacts;
-  ContactBuf& C = A->cb[A->cur];
-  CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
-  if (A->profiling) CK(cudaEventRecord(A->ev[0], A->stream));
-  if (nc > 0) {
-    LAUNCH(A, KC_NARROWPHASE, nc, k_narrowphase, div_up(nc, 128), 128, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
-           A->bflags, A->dCounts, P->record_events, A->beginEvents, A->endEvents, A->capContacts);
-  }
-  if (A->profiling) CK(cudaEventRecord(A->ev[1], A->stream));
-  return B2G_OK;
-}
-
-// second half of Step: Solve + FindNewContacts + ClearForces (b2_world.cpp:1140-1167)
-extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats* stats) {
-  int rc0 = step_check(A, P);
-  if (rc0) return rc0;
-  CK(cudaSetDevice(A->device));
-  const long long launches0 = A->launchesAtStepStart;
+static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   const int nb = A->nBodies, nc = A->nContacts, nj = A->nJoints;
   const float h = P->dt;
-  const float inv_dt = h > 0.0f ? 1.0f / h : 0.0f;
   const float dtRatio = A->invDt0 * h;
-  const int prof = A->profiling;
   ContactBuf& C = A->cb[A->cur];
   int numActive = 0, numColours = 0, numOverflow = 0, rounds = 0;
   int colourFirst[B2G_MAX_COLOURS + 2];
   memset(colourFirst, 0, sizeof(colourFirst));
-
-  if (h > 0.0f && nb > 0) {
+  {
     // ---- islands ---------------------------------------------------------------------
     LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent, A->islandAwake,
-           A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest);
+           A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest,
+           A->islandCount, A->islandCursor);
     if (nc > 0) LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
     if (nj > 0) LAUNCH(A, KC_ISLANDS, nj, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
     LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island, A->islandAwake);
     LAUNCH(A, KC_INTEGRATE, nb, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->vel, A->mass,
-           A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y), A->dCounts);
+           A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y), A->dCounts, nullptr, 0);
 
     // ---- constraint list + colouring -------------------------------------------------
     if (nc > 0) {
@@ -545,7 +542,7 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
             CK(cub::DeviceSelect::Flagged(A->cubTemp, tb, thrust::counting_iterator<int>(0), A->activeFlag,
                                           A->activeList, &A->dCounts->numActive, nc, A->stream)));
       const int* nAct = &A->dCounts->numActive;
-      if (P->solver_mode == B2G_SOLVER_COLOURED) {
+      if (P->solver_mode != B2G_SOLVER_SEQUENTIAL) {
         int grid = div_up(nc, 256);
         if (grid > 148 * 8) grid = 148 * 8;
         LAUNCH(A, KC_COLOUR, nc, k_colour_begin, grid, 256, nAct, A->activeList, C, A->mass, A->colourMask, A->dCounts);
@@ -602,9 +599,9 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
 
     // ---- contact solver --------------------------------------------------------------
     SolverPlanes& S = A->planes;
-    const bool coloured = P->solver_mode == B2G_SOLVER_COLOURED;
+    const bool coloured = P->solver_mode != B2G_SOLVER_SEQUENTIAL;
     if (numActive > 0) {
-      LAUNCH(A, KC_PREPARE, numActive, k_prepare, div_up(numActive, 128), 128, numActive, A->sortedList, C, A->fRadius, A->bflags, A->island,
+      LAUNCH(A, KC_PREPARE, numActive, k_prepare, div_up(numActive, 128), 128, 0, numActive, A->sortedList, C, A->fRadius, A->bflags, A->island,
              S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
       if (P->warm_starting) {
         if (coloured) {
@@ -633,10 +630,10 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
           LAUNCH(A, KC_SOLVE_VELOCITY, numActive, k_solve_velocity_seq, 1, 1, 0, numActive, S, A->vel);
         }
       }
-      LAUNCH(A, KC_STORE_IMPULSES, numActive, k_store_impulses, div_up(numActive, 256), 256, numActive, S, C);
+      LAUNCH(A, KC_STORE_IMPULSES, numActive, k_store_impulses, div_up(numActive, 256), 256, 0, numActive, S, C);
     }
     LAUNCH(A, KC_INTEGRATE, nb, k_integrate_positions, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
-           h);
+           h, nullptr, 0);
     if (numActive > 0) {
       for (int it = 0; it < P->position_iterations; ++it) {
         if (coloured) {
@@ -655,10 +652,250 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
       }
     }
     LAUNCH(A, KC_FINALIZE, nb, k_finalize_bodies, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
-           A->center, A->xf, A->force, A->islandMinSleep, h, P->allow_sleep);
+           A->center, A->xf, A->force, A->islandMinSleep, h, P->allow_sleep, nullptr, 0);
     LAUNCH(A, KC_FINALIZE, nb, k_sleep_and_clear, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->islandMinSleep,
            A->islandPen, A->capBodies, P->position_iterations, A->vel, A->force, P->allow_sleep, P->clear_forces,
-           A->dCounts);
+           A->dCounts, nullptr, 0);
+  }
+  out.numActive = numActive;
+  out.numColours = numColours;
+  out.numOverflow = numOverflow;
+  out.rounds = rounds;
+  return B2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solve, production path: islands packed into bins, one thread block per bin solves it start to
+// finish in shared memory (b2g_fused.cuh); islands too large for a tile take the per-colour
+// whole-GPU kernels.  One mid-step readback (colouring convergence + size of the big set).
+// ---------------------------------------------------------------------------------------------
+#define B2G_BIG_ISLAND 1024  // bodies; larger islands do not go through a shared-memory tile
+
+static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
+  const int nb = A->nBodies, nc = A->nContacts, nj = A->nJoints;
+  const float h = P->dt;
+  const float dtRatio = A->invDt0 * h;
+  ContactBuf& C = A->cb[A->cur];
+  SolverPlanes& S = A->planes;
+  const int bigThr = B2G_BIG_ISLAND;
+  // aim at >= 2 bins per SM so the fused kernel fills the chip, within what a tile can hold
+  int binSize = nb / (2 * 148);
+  if (binSize < 32) binSize = 32;
+  if (binSize > 512) binSize = 512;
+  const int nbins = nb / binSize + 1;
+  const int bigBin = nbins;  // sorts after every fused bin
+  if (nbins + 1 > A->nbinsMax) {
+    set_err("b2g_step", "internal: bin table too small");
+    return B2G_ERR_CAPACITY;
+  }
+  const int tileCap = binSize - 1 + bigThr;
+  const size_t smem = FusedTile::bytes(tileCap);
+
+  CK(cudaMemsetAsync(A->binFirst, 0x7f, sizeof(int) * (nbins + 1), A->stream));
+  CK(cudaMemsetAsync(A->binEnd, 0, sizeof(int) * (nbins + 1), A->stream));
+  LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent,
+         A->islandAwake, A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask,
+         A->bodyBest, A->islandCount, A->islandCursor);
+  if (nc > 0)
+    LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
+  if (nj > 0)
+    LAUNCH(A, KC_ISLANDS, nj, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
+  LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island,
+         A->islandAwake);
+  LAUNCH(A, KC_ISLANDS, nb, k_island_count, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
+         A->islandCount, A->dCounts);
+  {
+    size_t tb = A->cubTempBytes;
+    auto in = thrust::make_transform_iterator(A->islandCount, FusedCountOp{bigThr});
+    TIMED(A, KC_SORT_SCAN, nb, CK(cub::DeviceScan::ExclusiveSum(A->cubTemp, tb, in, A->islandStart, nb, A->stream)));
+  }
+  LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
+         A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, A->binFirst, A->binEnd, binSize,
+         bigThr);
+
+  int numActive = 0, numBig = 0, rounds = 0;
+  if (nc > 0) {
+    LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->bflags, A->island,
+           A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->recolour, binSize, bigThr, bigBin, A->dCounts);
+    A->recolour = 0;
+    int grid = div_up(nc, 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    LAUNCH(A, KC_COLOUR, nc, k_colour2_begin, grid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->dCounts, bigBin);
+    int round = 0;
+    int batch = A->roundsHint;
+    while (true) {
+      CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
+      for (int r = 0; r < batch; ++r, ++round) {
+        LAUNCH(A, KC_COLOUR, nc, k_colour2_propose, grid, 256, nc, A->cbin, C, A->mass, A->bodyBest, round);
+        LAUNCH(A, KC_COLOUR, nc, k_colour2_commit, grid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->bodyBest,
+               round, A->dCounts, r == batch - 1, bigBin);
+      }
+      int rc = read_counts(A);  // the mid-step readback
+      if (rc) return rc;
+      if (A->hCounts->remaining == 0) break;
+      if (round > 250) {
+        set_err("b2g_step", "graph colouring did not converge");
+        return B2G_ERR_CUDA;
+      }
+      batch = 4;
+    }
+    rounds = round;
+    {
+      int useful = A->hCounts->lastUsefulRound;
+      A->roundsHint = useful < 1 ? 1 : (useful + 1 < 16 ? useful + 1 : 16);
+    }
+    numActive = A->hCounts->numActive;
+    numBig = A->hCounts->numBig;
+    out.numColours = A->hCounts->numColours;
+    out.numOverflow = A->hCounts->numOverflow;
+    if (numActive > 0) {
+      LAUNCH(A, KC_COLOUR, nc, k_constraint_keys, div_up(nc, 256), 256, nc, A->cbin, C, A->conKeys, A->conVals);
+      size_t tb = A->cubTempBytes;
+      int keyBits = B2G_COLOUR_BITS + bits_for(nbins + 2);
+      if (keyBits > 32) keyBits = 32;
+      TIMED(A, KC_SORT_SCAN, nc,
+            CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb, A->conKeys, A->conKeysSorted, A->conVals,
+                                               A->sortedList, nc, 0, keyBits, A->stream)));
+    }
+  }
+  A->lastMaxIsland = nc > 0 ? A->hCounts->maxIslandBodies : 0;
+
+  // ---- every island that fits a tile: one launch -----------------------------------------------
+  {
+    FusedParams FP;
+    FP.nc = numActive > 0 ? nc : 0;
+    FP.binSize = binSize;
+    FP.h = h;
+    FP.dtRatio = dtRatio;
+    FP.gravity = make_float2(P->gravity_x, P->gravity_y);
+    FP.velIters = P->velocity_iterations;
+    FP.posIters = P->position_iterations;
+    FP.warmStarting = P->warm_starting;
+    FP.allowSleep = P->allow_sleep;
+    FP.clearForces = P->clear_forces;
+    FP.tileCap = tileCap;
+    if (smem > A->fusedSmemSet) {
+      CK(cudaFuncSetAttribute(k_solve_bins_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      A->fusedSmemSet = smem;
+    }
+    ktime_begin(A, KC_FUSED_SOLVE, (double)numActive - numBig);
+    k_solve_bins_fused<<<nbins, B2G_FUSED_THREADS, smem, A->stream>>>(
+        FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->conKeysSorted,
+        A->sortedList, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts);
+    ktime_end(A);
+    A->launches++;
+  }
+
+  // ---- oversize islands: per-colour launches over the whole GPU --------------------------------
+  if (numBig > 0 || (nc == 0 && false)) {
+    const int bigStart = numActive - numBig;
+    int colourFirst[B2G_MAX_COLOURS + 2];
+    int acc = bigStart, numColours = 0;
+    for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {
+      colourFirst[c] = acc;
+      acc += A->hCounts->colourCount[c];
+      if (c < B2G_MAX_COLOURS && A->hCounts->colourCount[c] > 0) numColours = c + 1;
+    }
+    colourFirst[B2G_MAX_COLOURS + 1] = acc;
+    const int numOverflow = A->hCounts->colourCount[B2G_MAX_COLOURS];
+    LAUNCH(A, KC_INTEGRATE, nb, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island,
+           A->islandAwake, A->vel, A->mass, A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y),
+           A->dCounts, A->bodySlot, 1);
+    LAUNCH(A, KC_PREPARE, numBig, k_prepare, div_up(numBig, 128), 128, bigStart, numBig, A->sortedList, C, A->fRadius,
+           A->bflags, A->island, S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
+    if (P->warm_starting) {
+      for (int c = 0; c < numColours; ++c) {
+        int n = colourFirst[c + 1] - colourFirst[c];
+        if (n > 0)
+          LAUNCH(A, KC_WARM_START, n, k_warm_start, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
+      }
+      if (numOverflow > 0)
+        LAUNCH(A, KC_WARM_START, numOverflow, k_warm_start_seq, 1, 1, colourFirst[B2G_MAX_COLOURS],
+               colourFirst[B2G_MAX_COLOURS + 1], S, A->vel);
+    }
+    for (int it = 0; it < P->velocity_iterations; ++it) {
+      for (int c = 0; c < numColours; ++c) {
+        int n = colourFirst[c + 1] - colourFirst[c];
+        if (n > 0)
+          LAUNCH(A, KC_SOLVE_VELOCITY, n, k_solve_velocity, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S,
+                 A->vel);
+      }
+      if (numOverflow > 0)
+        LAUNCH(A, KC_SOLVE_VELOCITY, numOverflow, k_solve_velocity_seq, 1, 1, colourFirst[B2G_MAX_COLOURS],
+               colourFirst[B2G_MAX_COLOURS + 1], S, A->vel);
+    }
+    LAUNCH(A, KC_STORE_IMPULSES, numBig, k_store_impulses, div_up(numBig, 256), 256, bigStart, numBig, S, C);
+    LAUNCH(A, KC_INTEGRATE, nb, k_integrate_positions, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
+           A->pos, A->vel, h, A->bodySlot, 1);
+    for (int it = 0; it < P->position_iterations; ++it) {
+      for (int c = 0; c < numColours; ++c) {
+        int n = colourFirst[c + 1] - colourFirst[c];
+        if (n > 0)
+          LAUNCH(A, KC_SOLVE_POSITION, n, k_solve_position, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S,
+                 A->pos, A->croot, A->islandPen, A->capBodies, it);
+      }
+      if (numOverflow > 0)
+        LAUNCH(A, KC_SOLVE_POSITION, numOverflow, k_solve_position_seq, 1, 1, colourFirst[B2G_MAX_COLOURS],
+               colourFirst[B2G_MAX_COLOURS + 1], S, A->pos, A->croot, A->islandPen, A->capBodies, it);
+    }
+    LAUNCH(A, KC_FINALIZE, nb, k_finalize_bodies, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
+           A->pos, A->vel, A->center, A->xf, A->force, A->islandMinSleep, h, P->allow_sleep, A->bodySlot, 1);
+    LAUNCH(A, KC_FINALIZE, nb, k_sleep_and_clear, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
+           A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->vel, A->force, P->allow_sleep,
+           P->clear_forces, A->dCounts, A->bodySlot, 1);
+  }
+  out.numActive = numActive;
+  out.rounds = rounds;
+  return B2G_OK;
+}
+
+static int step_check(b2gArena* A, const b2gStepParams* P) {
+  if (!A || !P) return B2G_ERR_INVALID;
+  if (P->position_iterations > B2G_MAX_POS_ITERS || P->position_iterations < 0 || P->velocity_iterations < 0) {
+    set_err("b2g_step", "iteration counts out of range");
+    return B2G_ERR_INVALID;
+  }
+  return B2G_OK;
+}
+
+// first half of Step: b2ContactManager::Collide (b2_world.cpp:1134-1138)
+extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
+  int rc0 = step_check(A, P);
+  if (rc0) return rc0;
+  CK(cudaSetDevice(A->device));
+  A->launchesAtStepStart = A->launches;
+  const int nc = A->nContacts;
+  ContactBuf& C = A->cb[A->cur];
+  CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
+  if (A->profiling) CK(cudaEventRecord(A->ev[0], A->stream));
+  if (nc > 0) {
+    LAUNCH(A, KC_NARROWPHASE, nc, k_narrowphase, div_up(nc, 128), 128, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
+           A->bflags, A->dCounts, P->record_events, A->beginEvents, A->endEvents, A->capContacts);
+  }
+  if (A->profiling) CK(cudaEventRecord(A->ev[1], A->stream));
+  return B2G_OK;
+}
+
+// second half of Step: Solve + FindNewContacts + ClearForces (b2_world.cpp:1140-1167)
+extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats* stats) {
+  int rc0 = step_check(A, P);
+  if (rc0) return rc0;
+  CK(cudaSetDevice(A->device));
+  const long long launches0 = A->launchesAtStepStart;
+  const int nb = A->nBodies;
+  const float h = P->dt;
+  const float inv_dt = h > 0.0f ? 1.0f / h : 0.0f;
+  const int prof = A->profiling;
+  int numActive = 0, numColours = 0, numOverflow = 0, rounds = 0;
+
+  if (h > 0.0f && nb > 0) {
+    SolveOut so;
+    int rcs = P->solver_mode == B2G_SOLVER_COLOURED ? solve_fused(A, P, so) : solve_legacy(A, P, so);
+    if (rcs) return rcs;
+    numActive = so.numActive;
+    numColours = so.numColours;
+    numOverflow = so.numOverflow;
+    rounds = so.rounds;
     if (prof) CK(cudaEventRecord(A->ev[2], A->stream));
 
     // ---- FindNewContacts (end of Solve, b2_world.cpp:663-669) ------------------------

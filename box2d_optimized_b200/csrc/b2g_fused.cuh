@@ -1,0 +1,435 @@
+// b2g_fused.cuh — the fused per-island solver of the production (graph-coloured) mode.
+//
+// b2Island::Solve (src/dynamics/b2_island.cpp:253-484) handles one island at a time on one CPU
+// thread.  Here islands are packed into *bins* (consecutive islands, in root order, until a bin
+// holds ~binSize bodies) and ONE thread block solves one bin from start to finish:
+//   velocity integration -> constraint preparation -> warm start -> velocityIterations x colours
+//   -> store impulses -> position integration -> positionIterations x colours with the per-island
+//   early exit -> write-back, SynchronizeTransform, sleep bookkeeping, island sleep, ClearForces,
+// with the bin's body velocities and positions resident in SHARED MEMORY for the whole solve and
+// __syncthreads() between colours instead of kernel relaunches.  Constraints of different islands
+// never share a movable body, so the global colouring stays valid inside a bin.
+//
+// Islands larger than `bigThreshold` bodies do not fit a tile; they are routed to the "big" bin
+// and solved by the per-colour kernels of b2g_step_kernels.cuh over the whole GPU.
+#pragma once
+#include "b2g_step_kernels.cuh"
+
+#define B2G_FUSED_THREADS 256
+#define B2G_COLOUR_BITS 5  // 24 colours + overflow < 32
+#define B2G_SLOT_NONE (-1)
+#define B2G_SLOT_BIG (-2)
+
+// bodies an island of `count` members occupies in fused slot space (big islands: none)
+struct FusedCountOp {
+  int thr;
+  __host__ __device__ int operator()(int count) const { return count > thr ? 0 : count; }
+};
+
+__global__ void k_island_count(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
+                               const uint32_t* __restrict__ islandAwake, int* islandCount, StepCounts* counts) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  if (!body_simulated(bflags[b], island, islandAwake, b)) return;
+  int c = atomicAdd(&islandCount[island[b]], 1) + 1;
+  if (c > counts->maxIslandBodies) atomicMax(&counts->maxIslandBodies, c);
+}
+
+// slot of every simulated body in island-sorted order, and the slot range of every bin
+__global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
+                               const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
+                               const int* __restrict__ islandStart, int* islandCursor, int* bodySlot, int* slotBody,
+                               int* binFirst, int* binEnd, int binSize, int bigThreshold) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  if (!body_simulated(bflags[b], island, islandAwake, b)) {
+    bodySlot[b] = B2G_SLOT_NONE;
+    return;
+  }
+  int root = island[b];
+  int cnt = islandCount[root];
+  if (cnt > bigThreshold) {
+    bodySlot[b] = B2G_SLOT_BIG;
+    return;
+  }
+  int start = islandStart[root];
+  int slot = start + atomicAdd(&islandCursor[root], 1);
+  bodySlot[b] = slot;
+  slotBody[slot] = b;
+  if (b == root) {
+    int bin = start / binSize;
+    atomicMin(&binFirst[bin], start);
+    atomicMax(&binEnd[bin], start + cnt);
+  }
+}
+
+// active constraints and the bin each belongs to (-1 inactive, bigBin for oversize islands)
+__global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restrict__ fTypeFlags,
+                                   const uint32_t* __restrict__ bflags, const int* __restrict__ island,
+                                   const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
+                                   const int* __restrict__ islandStart, int* cbin, int dropColours, int binSize,
+                                   int bigThreshold, int bigBin, StepCounts* counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  uint32_t flags = C.flags[i];
+  bool active = (flags & (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) == (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED);
+  int2 bd = C.body[i];
+  if (active) {
+    int2 fx = C.fix[i];
+    if ((fTypeFlags[fx.x] | fTypeFlags[fx.y]) & B2G_FIX_SENSOR) active = false;
+  }
+  int root = -1;
+  if (active) {
+    root = B2G_BODY_TYPE(bflags[bd.x]) != B2G_STATIC ? island[bd.x] : island[bd.y];
+    active = islandAwake[root] != 0;
+  }
+  int bin = -1;
+  if (active) {
+    bin = islandCount[root] > bigThreshold ? bigBin : islandStart[root] / binSize;
+    auto g = cg::coalesced_threads();
+    if (g.thread_rank() == 0) atomicAdd(&counts->numActive, (int)g.size());
+    if (bin == bigBin) atomicAdd(&counts->numBig, 1);
+  }
+  cbin[i] = bin;
+  if (!active || dropColours) C.colour[i] = -1;
+}
+
+// ---- colouring over the contact array directly (no compacted list) ------------------------------
+__global__ void k_colour2_begin(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
+                                unsigned long long* colourMask, StepCounts* counts, int bigBin) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+    int bin = cbin[i];
+    if (bin < 0) continue;
+    int c = C.colour[i];
+    if (c >= B2G_MAX_COLOURS) {
+      C.colour[i] = -1;  // overflow constraints retry every step
+      c = -1;
+    }
+    if (c >= 0) {
+      int2 bd = C.body[i];
+      unsigned long long bit = 1ull << c;
+      if (body_movable(mass[bd.x])) atomicOr(&colourMask[bd.x], bit);
+      if (body_movable(mass[bd.y])) atomicOr(&colourMask[bd.y], bit);
+      if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
+      if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
+    }
+  }
+}
+
+__global__ void k_colour2_propose(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
+                                  unsigned long long* bodyBest, int round) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+    if (cbin[i] < 0 || C.colour[i] >= 0) continue;
+    int2 bd = C.body[i];
+    unsigned long long pr = colour_priority(round, i, C.key[i]);
+    if (body_movable(mass[bd.x])) atomicMax(&bodyBest[bd.x], pr);
+    if (body_movable(mass[bd.y])) atomicMax(&bodyBest[bd.y], pr);
+  }
+}
+
+__global__ void k_colour2_commit(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
+                                 unsigned long long* colourMask, const unsigned long long* __restrict__ bodyBest,
+                                 int round, StepCounts* counts, int lastOfBatch, int bigBin) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+    int bin = cbin[i];
+    if (bin < 0 || C.colour[i] >= 0) continue;
+    int2 bd = C.body[i];
+    unsigned long long pr = colour_priority(round, i, C.key[i]);
+    bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
+    bool win = (!movA || bodyBest[bd.x] == pr) && (!movB || bodyBest[bd.y] == pr);
+    if (win) {
+      unsigned long long used = (movA ? colourMask[bd.x] : 0ull) | (movB ? colourMask[bd.y] : 0ull);
+      unsigned long long freeBits = ~used & ((1ull << B2G_MAX_COLOURS) - 1ull);
+      int c = freeBits ? (__ffsll((long long)freeBits) - 1) : B2G_OVERFLOW_COLOUR;
+      C.colour[i] = c;
+      if (c < B2G_MAX_COLOURS) {
+        unsigned long long bit = 1ull << c;
+        if (movA) colourMask[bd.x] |= bit;
+        if (movB) colourMask[bd.y] |= bit;
+        if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
+      } else {
+        atomicAdd(&counts->numOverflow, 1);
+      }
+      if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
+      if (counts->lastUsefulRound < round + 1) atomicMax(&counts->lastUsefulRound, round + 1);
+    } else if (lastOfBatch) {
+      atomicAdd(&counts->remaining, 1);
+    }
+  }
+}
+
+// sort key: bin (high) | colour (low); inactive contacts get the all-ones sentinel and sort last
+__global__ void k_constraint_keys(int nc, const int* __restrict__ cbin, ContactBuf C, unsigned int* keys, int* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  int bin = cbin[i];
+  keys[i] = bin < 0 ? 0xffffffffu : ((unsigned int)bin << B2G_COLOUR_BITS) | (unsigned int)C.colour[i];
+  vals[i] = i;
+}
+
+__device__ __forceinline__ int lower_bound_u32(const unsigned int* __restrict__ a, int n, unsigned int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+struct FusedParams {
+  int nc;              // contacts (length of the sorted key / index arrays)
+  int binSize;
+  float h, dtRatio;
+  float2 gravity;
+  int velIters, posIters, warmStarting, allowSleep, clearForces;
+  int tileCap;         // bodies the shared-memory tile can hold
+};
+
+// dynamic shared memory layout for a tile of `cap` bodies
+struct FusedTile {
+  float4* vel;
+  float4* pos;
+  int* body;        // global body index of each slot
+  int* head;        // tile slot of the first body of this slot's island (per-island state lives there)
+  unsigned int* pen;     // per island head: max penetration of the current position iteration
+  unsigned int* sleepMin;  // per island head: float bits of min sleep time
+  int* done;        // per island head: position solver converged
+  __host__ __device__ static size_t bytes(int cap) { return (size_t)cap * (16 + 16 + 4 + 4 + 4 + 4 + 4); }
+};
+
+__global__ void __launch_bounds__(B2G_FUSED_THREADS)
+k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* __restrict__ binEnd,
+                   const int* __restrict__ slotBody, const int* __restrict__ bodySlot,
+                   const int* __restrict__ island, const int* __restrict__ islandStart,
+                   const unsigned int* __restrict__ keysSorted, const int* __restrict__ sortedList, ContactBuf C,
+                   const float* __restrict__ fRadius, SolverPlanes S, uint32_t* bflags, float4* gpos, float4* gvel,
+                   float4* gxf, float4* gforce, const float4* __restrict__ gmass, const float4* __restrict__ gcenter,
+                   StepCounts* counts) {
+  const int bin = blockIdx.x;
+  const int first = binFirst[bin];
+  const int nbod = binEnd[bin] - first;
+  if (nbod <= 0 || first >= 0x7f000000) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  FusedTile T;
+  {
+    unsigned char* p = smemRaw;
+    T.vel = (float4*)p;  p += (size_t)P.tileCap * 16;
+    T.pos = (float4*)p;  p += (size_t)P.tileCap * 16;
+    T.body = (int*)p;    p += (size_t)P.tileCap * 4;
+    T.head = (int*)p;    p += (size_t)P.tileCap * 4;
+    T.pen = (unsigned int*)p;       p += (size_t)P.tileCap * 4;
+    T.sleepMin = (unsigned int*)p;  p += (size_t)P.tileCap * 4;
+    T.done = (int*)p;
+  }
+  __shared__ int cstart[B2G_MAX_COLOURS + 3];
+
+  // constraint ranges of this bin, one per colour (+ overflow), by binary search in the sorted keys
+  if (tid <= B2G_MAX_COLOURS + 1) {
+    unsigned int key = tid <= B2G_MAX_COLOURS ? (((unsigned int)bin << B2G_COLOUR_BITS) | (unsigned int)tid)
+                                              : ((unsigned int)(bin + 1) << B2G_COLOUR_BITS);
+    cstart[tid] = lower_bound_u32(keysSorted, P.nc, key);
+  }
+
+  // ---- phase 0: load the tile, integrate velocities (b2_island.cpp:257-293) --------------------
+  const float h = P.h;
+  for (int l = tid; l < nbod; l += nt) {
+    int b = slotBody[first + l];
+    T.body[l] = b;
+    T.head[l] = islandStart[island[b]] - first;
+    T.pen[l] = 0u;
+    T.sleepMin[l] = __float_as_uint(B2G_MAX_FLOAT);
+    T.done[l] = 0;
+    uint32_t f = bflags[b];
+    if (!(f & B2G_BODY_AWAKE)) bflags[b] = f | B2G_BODY_AWAKE;  // reached bodies are woken, timer kept
+    float4 v4 = gvel[b];
+    if (B2G_BODY_TYPE(f) == B2G_DYNAMIC) {
+      float4 m4 = gmass[b], c4 = gcenter[b], f4 = gforce[b];
+      float t = h * m4.x;
+      float gs = m4.w * m4.z;
+      v4.x += t * (gs * P.gravity.x + f4.x);
+      v4.y += t * (gs * P.gravity.y + f4.y);
+      v4.z += h * m4.y * f4.z;
+      float dl = 1.0f + h * c4.z;
+      float da = 1.0f + h * c4.w;
+      v4.x /= dl;
+      v4.y /= dl;
+      v4.z /= da;
+    }
+    T.vel[l] = v4;
+    T.pos[l] = gpos[b];
+  }
+  __syncthreads();
+  const int cAll0 = cstart[0], cAll1 = cstart[B2G_MAX_COLOURS + 1];
+  const TileBodies velAcc{T.vel, gvel};
+  const TileBodies posAcc{T.pos, gpos};
+
+  // ---- phase 1: prepare every constraint of the bin --------------------------------------------
+  for (int s = cAll0 + tid; s < cAll1; s += nt) {
+    int i = sortedList[s];
+    Manifold m;
+    manifold_unpack(m, C.m0[i], C.m1[i], C.m2[i], C.m3[i]);
+    int2 bd = C.body[i];
+    int2 fx = C.fix[i];
+    int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
+    int ia = sa >= 0 ? sa - first : ~bd.x;
+    int ib = sb >= 0 ? sb - first : ~bd.y;
+    prepare_constraint(S, s, i, m, bd.x, bd.y, ia, ib, C.material[i], fRadius[fx.x], fRadius[fx.y], posAcc, velAcc,
+                       gmass, gcenter, P.dtRatio, P.warmStarting != 0);
+  }
+  __syncthreads();
+
+  // ---- phase 2: warm start, colour by colour ---------------------------------------------------
+  if (P.warmStarting) {
+    for (int c = 0; c < B2G_MAX_COLOURS; ++c) {
+      int s0 = cstart[c], s1 = cstart[c + 1];
+      if (s0 == s1) continue;  // block-uniform
+      for (int s = s0 + tid; s < s1; s += nt) warm_start_constraint(S, s, velAcc);
+      __syncthreads();
+    }
+    if (cstart[B2G_MAX_COLOURS] != cstart[B2G_MAX_COLOURS + 1]) {
+      if (tid == 0)
+        for (int s = cstart[B2G_MAX_COLOURS]; s < cstart[B2G_MAX_COLOURS + 1]; ++s) warm_start_constraint(S, s, velAcc);
+      __syncthreads();
+    }
+  }
+
+  // ---- phase 3: velocity iterations ---------------------------------------------------------------
+  for (int it = 0; it < P.velIters; ++it) {
+    for (int c = 0; c < B2G_MAX_COLOURS; ++c) {
+      int s0 = cstart[c], s1 = cstart[c + 1];
+      if (s0 == s1) continue;
+      for (int s = s0 + tid; s < s1; s += nt) solve_velocity_constraint(S, s, velAcc);
+      __syncthreads();
+    }
+    if (cstart[B2G_MAX_COLOURS] != cstart[B2G_MAX_COLOURS + 1]) {
+      if (tid == 0)
+        for (int s = cstart[B2G_MAX_COLOURS]; s < cstart[B2G_MAX_COLOURS + 1]; ++s)
+          solve_velocity_constraint(S, s, velAcc);
+      __syncthreads();
+    }
+  }
+
+  // ---- phase 4: store impulses (b2_contact_solver.cpp:641-657) -----------------------------------
+  for (int s = cAll0 + tid; s < cAll1; s += nt) {
+    int4 ix = S.idx[s];
+    float4 imp = S.imp[s];
+    int i = ix.w;
+    float4 q1 = C.m1[i];
+    q1.z = imp.x;
+    q1.w = imp.y;
+    C.m1[i] = q1;
+    if (ix.z == 2) {
+      float4 q2 = C.m2[i];
+      q2.z = imp.z;
+      q2.w = imp.w;
+      C.m2[i] = q2;
+    }
+  }
+
+  // ---- phase 5: integrate positions (b2_island.cpp:353-385) --------------------------------------
+  for (int l = tid; l < nbod; l += nt) {
+    float4 p4 = T.pos[l], v4 = T.vel[l];
+    float2 v = make_float2(v4.x, v4.y);
+    float w = v4.z;
+    float2 translation = h * v;
+    if (dot2(translation, translation) > B2G_MAX_TRANSLATION_SQ) {
+      float ratio = B2G_MAX_TRANSLATION / len2(translation);
+      v.x *= ratio;
+      v.y *= ratio;
+    }
+    float rotation = h * w;
+    if (rotation * rotation > B2G_MAX_ROTATION_SQ) {
+      float ratio = B2G_MAX_ROTATION / absf_(rotation);
+      w *= ratio;
+    }
+    p4.x += h * v.x;
+    p4.y += h * v.y;
+    p4.z += h * w;
+    T.pos[l] = p4;
+    T.vel[l] = make_float4(v.x, v.y, w, v4.w);
+  }
+  __syncthreads();
+
+  // ---- phase 6: position iterations with the per-island early exit (b2_island.cpp:391-409) --------
+  for (int it = 0; it < P.posIters; ++it) {
+    for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {
+      int s0 = cstart[c], s1 = cstart[c + 1];
+      if (s0 == s1) continue;
+      int sBegin = s0 + tid, sStep = nt;
+      if (c == B2G_MAX_COLOURS) {  // overflow bucket: one thread, list order
+        sBegin = tid == 0 ? s0 : s1;
+        sStep = 1;
+      }
+      for (int s = sBegin; s < s1; s += sStep) {
+        int4 ix = S.idx[s];
+        int slot = ix.x >= 0 ? ix.x : ix.y;  // a tile member of the island (the other may be static)
+        int hd = T.head[slot];
+        if (T.done[hd]) continue;
+        float minSep = solve_position_constraint(S, s, posAcc);
+        float pen = minSep < 0.0f ? -minSep : 0.0f;
+        atomicMax(&T.pen[hd], __float_as_uint(pen));
+      }
+      __syncthreads();
+    }
+    // island converged? (contactsOkay: minSeparation >= -3 slop)
+    for (int l = tid; l < nbod; l += nt) {
+      if (T.head[l] == l && !T.done[l]) {
+        if (__uint_as_float(T.pen[l]) <= 3.0f * B2G_LINEAR_SLOP) T.done[l] = 1;
+        T.pen[l] = 0u;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 7: write back, SynchronizeTransform, sleep (b2_island.cpp:430-483), ClearForces ------
+  const float linTolSqr = B2G_LINEAR_SLEEP_TOL * B2G_LINEAR_SLEEP_TOL;
+  const float angTolSqr = B2G_ANGULAR_SLEEP_TOL * B2G_ANGULAR_SLEEP_TOL;
+  if (P.allowSleep) {
+    for (int l = tid; l < nbod; l += nt) {
+      int b = T.body[l];
+      uint32_t f = bflags[b];
+      float4 v4 = T.vel[l];
+      float st = gforce[b].w;
+      float minSleep;
+      if (!(f & B2G_BODY_AUTOSLEEP) || v4.z * v4.z > angTolSqr || v4.x * v4.x + v4.y * v4.y > linTolSqr) {
+        st = 0.0f;
+        minSleep = 0.0f;
+      } else {
+        st += h;
+        minSleep = st;
+      }
+      T.vel[l].w = st;  // park the new sleep time in the unused lane
+      atomicMin(&T.sleepMin[T.head[l]], __float_as_uint(minSleep));
+    }
+    __syncthreads();
+  }
+  int awake = 0;
+  for (int l = tid; l < nbod; l += nt) {
+    int b = T.body[l];
+    float4 p4 = T.pos[l], v4 = T.vel[l], c4 = gcenter[b];
+    Xf X = xf_from_sweep(make_float2(p4.x, p4.y), p4.z, make_float2(c4.x, c4.y));
+    gpos[b] = p4;
+    gxf[b] = xf_to4(X);
+    float4 fo = gforce[b];
+    bool sleepNow = false;
+    if (P.allowSleep) {
+      int hd = T.head[l];
+      fo.w = v4.w;
+      sleepNow = __uint_as_float(T.sleepMin[hd]) >= B2G_TIME_TO_SLEEP && T.done[hd] != 0;
+    }
+    if (sleepNow) {
+      // b2Body::SetAwake(false), b2_body.h:731-739
+      bflags[b] &= ~B2G_BODY_AWAKE;
+      gvel[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      gforce[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    } else {
+      gvel[b] = make_float4(v4.x, v4.y, v4.z, 0.0f);
+      if (P.clearForces) fo.x = fo.y = fo.z = 0.0f;
+      gforce[b] = fo;
+      ++awake;
+    }
+  }
+  if (awake) atomicAdd(&counts->numAwake, awake);
+}

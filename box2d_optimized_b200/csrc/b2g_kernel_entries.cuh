@@ -176,8 +176,9 @@ __global__ void k_entry_prepare(int nc, SolverPlanes S, const int2* __restrict__
   manifold_unpack(m, man[4 * s], man[4 * s + 1], man[4 * s + 2], man[4 * s + 3]);
   int2 ix = index[s];
   float2 r = radii[s];
-  prepare_constraint(S, s, s, m, ix.x, ix.y, material[s], r.x, r.y, pos, vel, bodyMass, bodyCenter, dtRatio,
-                     warmStarting != 0);
+  prepare_constraint(S, s, s, m, ix.x, ix.y, ix.x, ix.y, material[s], r.x, r.y,
+                     GlobalBodies{const_cast<float4*>(pos)}, GlobalBodies{const_cast<float4*>(vel)}, bodyMass,
+                     bodyCenter, dtRatio, warmStarting != 0);
 }
 
 __global__ void k_entry_split_mass(int nb, const float4* __restrict__ in, float4* mass, float4* center) {

@@ -38,22 +38,42 @@ struct SolverPlanes {
 };
 
 #ifdef __CUDACC__
+// ---- body state accessors ----------------------------------------------------------------------
+// The solver functions are templated on where body velocities / positions live:
+//   GlobalBodies  plain arrays in HBM, index = global body index (per-colour launches, seq mode)
+//   TileBodies    the fused per-island-bin kernel: index >= 0 is a slot of the CTA's shared-memory
+//                 tile, index < 0 is ~globalIndex of a body outside the tile (static bodies: read
+//                 only, never stored because they are not movable)
+struct GlobalBodies {
+  float4* a;
+  __device__ __forceinline__ float4 load(int i) const { return a[i]; }
+  __device__ __forceinline__ void store(int i, float4 v) const { a[i] = v; }
+};
+struct TileBodies {
+  float4* tile;
+  const float4* __restrict__ global;
+  __device__ __forceinline__ float4 load(int i) const { return i >= 0 ? tile[i] : global[~i]; }
+  __device__ __forceinline__ void store(int i, float4 v) const { tile[i] = v; }
+};
+
 // ---- prepare -------------------------------------------------------------------------------
 // bodyPos = (c.x, c.y, a, _), bodyVel = (v.x, v.y, w, _), bodyMass = (invMass, invI, _, _),
 // bodyCenter = (localCenter.x, localCenter.y, _, _).
+// idxA/idxB are what the iteration kernels will use to address the bodies (global index, or tile
+// slot / ~global in the fused kernel); bodyA/bodyB are always global (mass, centre).
+template <class PosAccess, class VelAccess>
 __device__ __forceinline__ void prepare_constraint(const SolverPlanes& S, int s, int contactIndex, const Manifold& m,
-                                                   int bodyA, int bodyB, float4 material, float radiusA,
-                                                   float radiusB, const float4* __restrict__ bodyPos,
-                                                   const float4* __restrict__ bodyVel,
-                                                   const float4* __restrict__ bodyMass,
+                                                   int bodyA, int bodyB, int idxA, int idxB, float4 material,
+                                                   float radiusA, float radiusB, const PosAccess& bodyPos,
+                                                   const VelAccess& bodyVel, const float4* __restrict__ bodyMass,
                                                    const float4* __restrict__ bodyCenter, float dtRatio,
                                                    bool warmStarting) {
   float4 mAq = bodyMass[bodyA], mBq = bodyMass[bodyB];
   float mA = mAq.x, iA = mAq.y, mB = mBq.x, iB = mBq.y;
   float4 cenA = bodyCenter[bodyA], cenB = bodyCenter[bodyB];
   float2 localCenterA = make_float2(cenA.x, cenA.y), localCenterB = make_float2(cenB.x, cenB.y);
-  float4 pA = bodyPos[bodyA], pB = bodyPos[bodyB];
-  float4 vAq = bodyVel[bodyA], vBq = bodyVel[bodyB];
+  float4 pA = bodyPos.load(idxA), pB = bodyPos.load(idxB);
+  float4 vAq = bodyVel.load(idxA), vBq = bodyVel.load(idxB);
   float2 cA = make_float2(pA.x, pA.y), cB = make_float2(pB.x, pB.y);
   float aA = pA.z, aB = pB.z;
   float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
@@ -142,7 +162,7 @@ __device__ __forceinline__ void prepare_constraint(const SolverPlanes& S, int s,
   S.m1[s] = make_float4(normalMass[0], tangentMass[0], velocityBias[0], normalMass[1]);
   S.m2[s] = make_float4(tangentMass[1], velocityBias[1], k11, k12);
   S.kk[s] = make_float4(k22, n11, n12, n22);
-  S.idx[s] = make_int4(bodyA, bodyB, velPointCount, contactIndex);
+  S.idx[s] = make_int4(idxA, idxB, velPointCount, contactIndex);
 }
 
 // A body whose inverse mass and inertia are both zero (static, kinematic, massless) is never
@@ -150,7 +170,8 @@ __device__ __forceinline__ void prepare_constraint(const SolverPlanes& S, int s,
 // such bodies are shared by many constraints of one colour.
 __device__ __forceinline__ bool movable(float invM, float invI) { return invM != 0.0f || invI != 0.0f; }
 
-__device__ __forceinline__ void warm_start_constraint(const SolverPlanes& S, int s, float4* __restrict__ bodyVel) {
+template <class VelAccess>
+__device__ __forceinline__ void warm_start_constraint(const SolverPlanes& S, int s, const VelAccess& bodyVel) {
   int4 ix = S.idx[s];
   float4 ms = S.mass[s];
   float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
@@ -158,7 +179,7 @@ __device__ __forceinline__ void warm_start_constraint(const SolverPlanes& S, int
   float2 normal = make_float2(nf.x, nf.y);
   float2 tangent = cross_vs(normal, 1.0f);
   float4 r1 = S.r1[s], r2 = S.r2[s], imp = S.imp[s];
-  float4 vAq = bodyVel[ix.x], vBq = bodyVel[ix.y];
+  float4 vAq = bodyVel.load(ix.x), vBq = bodyVel.load(ix.y);
   float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
   float wA = vAq.z, wB = vBq.z;
   {
@@ -177,11 +198,12 @@ __device__ __forceinline__ void warm_start_constraint(const SolverPlanes& S, int
     wB += iB * cross2(rB, P);
     vB += mB * P;
   }
-  if (movable(mA, iA)) bodyVel[ix.x] = make_float4(vA.x, vA.y, wA, vAq.w);
-  if (movable(mB, iB)) bodyVel[ix.y] = make_float4(vB.x, vB.y, wB, vBq.w);
+  if (movable(mA, iA)) bodyVel.store(ix.x, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) bodyVel.store(ix.y, make_float4(vB.x, vB.y, wB, vBq.w));
 }
 
-__device__ __forceinline__ void solve_velocity_constraint(const SolverPlanes& S, int s, float4* __restrict__ bodyVel) {
+template <class VelAccess>
+__device__ __forceinline__ void solve_velocity_constraint(const SolverPlanes& S, int s, const VelAccess& bodyVel) {
   int4 ix = S.idx[s];
   float4 ms = S.mass[s];
   float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
@@ -193,7 +215,7 @@ __device__ __forceinline__ void solve_velocity_constraint(const SolverPlanes& S,
   float2 rA1 = make_float2(r1.x, r1.y), rB1 = make_float2(r1.z, r1.w);
   float2 rA2 = make_float2(r2.x, r2.y), rB2 = make_float2(r2.z, r2.w);
 
-  float4 vAq = bodyVel[ix.x], vBq = bodyVel[ix.y];
+  float4 vAq = bodyVel.load(ix.x), vBq = bodyVel.load(ix.y);
   float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
   float wA = vAq.z, wB = vBq.z;
 
@@ -296,12 +318,13 @@ __device__ __forceinline__ void solve_velocity_constraint(const SolverPlanes& S,
   }
 
   S.imp[s] = imp;
-  if (movable(mA, iA)) bodyVel[ix.x] = make_float4(vA.x, vA.y, wA, vAq.w);
-  if (movable(mB, iB)) bodyVel[ix.y] = make_float4(vB.x, vB.y, wB, vBq.w);
+  if (movable(mA, iA)) bodyVel.store(ix.x, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) bodyVel.store(ix.y, make_float4(vB.x, vB.y, wB, vBq.w));
 }
 
 // returns the smallest separation seen (<= 0 contributes to the island's minSeparation)
-__device__ __forceinline__ float solve_position_constraint(const SolverPlanes& S, int s, float4* __restrict__ bodyPos) {
+template <class PosAccess>
+__device__ __forceinline__ float solve_position_constraint(const SolverPlanes& S, int s, const PosAccess& bodyPos) {
   int4 ix = S.idx[s];
   float4 ms = S.mass[s];
   float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
@@ -312,7 +335,7 @@ __device__ __forceinline__ float solve_position_constraint(const SolverPlanes& S
   const int type = __float_as_int(pr.z);
   const int pointCount = __float_as_int(pr.w);
 
-  float4 pAq = bodyPos[ix.x], pBq = bodyPos[ix.y];
+  float4 pAq = bodyPos.load(ix.x), pBq = bodyPos.load(ix.y);
   float2 cA = make_float2(pAq.x, pAq.y), cB = make_float2(pBq.x, pBq.y);
   float aA = pAq.z, aB = pBq.z;
   float minSeparation = 0.0f;
@@ -358,8 +381,8 @@ __device__ __forceinline__ float solve_position_constraint(const SolverPlanes& S
     cB += mB * P;
     aB += iB * cross2(rB, P);
   }
-  if (movable(mA, iA)) bodyPos[ix.x] = make_float4(cA.x, cA.y, aA, pAq.w);
-  if (movable(mB, iB)) bodyPos[ix.y] = make_float4(cB.x, cB.y, aB, pBq.w);
+  if (movable(mA, iA)) bodyPos.store(ix.x, make_float4(cA.x, cA.y, aA, pAq.w));
+  if (movable(mB, iB)) bodyPos.store(ix.y, make_float4(cB.x, cB.y, aB, pBq.w));
   return minSeparation;
 }
 #endif  // __CUDACC__

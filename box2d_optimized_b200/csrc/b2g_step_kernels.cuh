@@ -125,9 +125,12 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islandParent, uint32_t* islandAwake,
                              uint32_t* islandMinSleep, uint32_t* islandPen, int penStride, int posIters,
-                             unsigned long long* colourMask, unsigned long long* bodyBest) {
+                             unsigned long long* colourMask, unsigned long long* bodyBest, int* islandCount,
+                             int* islandCursor) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  islandCount[b] = 0;
+  islandCursor[b] = 0;
   uint32_t f = bflags[b];
   if (f & B2G_BODY_WAKE_REQUEST) {
     // b2Body::SetAwake(true): b2_body.h:726-730
@@ -218,9 +221,10 @@ __global__ void k_integrate_velocities(int nb, uint32_t* bflags, const int* __re
                                        const uint32_t* __restrict__ islandAwake, float4* vel,
                                        const float4* __restrict__ mass, const float4* __restrict__ center,
                                        const float4* __restrict__ force, float h, float2 gravity,
-                                       StepCounts* counts) {
+                                       StepCounts* counts, const int* __restrict__ bodySlot, int onlyBig) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  if (onlyBig && bodySlot[b] != -2) return;  // bodies of tile-sized islands are integrated by the fused kernel
   uint32_t f = bflags[b];
   uint32_t type = B2G_BODY_TYPE(f);
   if (type == B2G_STATIC || !(f & B2G_BODY_ENABLED)) return;
@@ -378,18 +382,20 @@ __global__ void k_colour_validate(int n, const int* __restrict__ sortedList, Con
 // order in the production mode, contact order in the sequential mode).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_prepare(int n, const int* __restrict__ sortedList, ContactBuf C, const float* __restrict__ fRadius,
+k_prepare(int first, int n, const int* __restrict__ sortedList, ContactBuf C, const float* __restrict__ fRadius,
           const uint32_t* __restrict__ bflags, const int* __restrict__ island, SolverPlanes S, int* croot,
           const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ mass,
           const float4* __restrict__ center, float dtRatio, int warmStarting) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  s += first;
   int i = sortedList[s];
   Manifold m;
   manifold_unpack(m, C.m0[i], C.m1[i], C.m2[i], C.m3[i]);
   int2 bd = C.body[i];
   int2 fx = C.fix[i];
-  prepare_constraint(S, s, i, m, bd.x, bd.y, C.material[i], fRadius[fx.x], fRadius[fx.y], pos, vel, mass, center,
+  prepare_constraint(S, s, i, m, bd.x, bd.y, bd.x, bd.y, C.material[i], fRadius[fx.x], fRadius[fx.y],
+                     GlobalBodies{const_cast<float4*>(pos)}, GlobalBodies{const_cast<float4*>(vel)}, mass, center,
                      dtRatio, warmStarting != 0);
   croot[s] = B2G_BODY_TYPE(bflags[bd.x]) != B2G_STATIC ? island[bd.x] : island[bd.y];
 }
@@ -397,13 +403,13 @@ k_prepare(int n, const int* __restrict__ sortedList, ContactBuf C, const float* 
 __global__ void __launch_bounds__(256) k_warm_start(int first, int last, SolverPlanes S, float4* vel) {
   int s = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= last) return;
-  warm_start_constraint(S, s, vel);
+  warm_start_constraint(S, s, GlobalBodies{vel});
 }
 
 __global__ void __launch_bounds__(256) k_solve_velocity(int first, int last, SolverPlanes S, float4* vel) {
   int s = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= last) return;
-  solve_velocity_constraint(S, s, vel);
+  solve_velocity_constraint(S, s, GlobalBodies{vel});
 }
 
 // island has converged in an earlier position iteration? (b2_island.cpp:391-409 early exit)
@@ -420,7 +426,7 @@ k_solve_position(int first, int last, SolverPlanes S, float4* pos, const int* __
   if (s >= last) return;
   int root = croot[s];
   if (island_done(islandPen, penStride, iter, root)) return;
-  float minSep = solve_position_constraint(S, s, pos);
+  float minSep = solve_position_constraint(S, s, GlobalBodies{pos});
   // penetration >= +0.0 (never -0.0, whose bit pattern would win the max), so the float bit
   // pattern is monotone as an unsigned integer
   float pen = minSep < 0.0f ? -minSep : 0.0f;
@@ -430,26 +436,27 @@ k_solve_position(int first, int last, SolverPlanes S, float4* pos, const int* __
 // sequential single-thread variants: same device functions, list order (parity vehicle and the
 // serial overflow colour)
 __global__ void k_warm_start_seq(int first, int last, SolverPlanes S, float4* vel) {
-  for (int s = first; s < last; ++s) warm_start_constraint(S, s, vel);
+  for (int s = first; s < last; ++s) warm_start_constraint(S, s, GlobalBodies{vel});
 }
 __global__ void k_solve_velocity_seq(int first, int last, SolverPlanes S, float4* vel) {
-  for (int s = first; s < last; ++s) solve_velocity_constraint(S, s, vel);
+  for (int s = first; s < last; ++s) solve_velocity_constraint(S, s, GlobalBodies{vel});
 }
 __global__ void k_solve_position_seq(int first, int last, SolverPlanes S, float4* pos, const int* __restrict__ croot,
                                      uint32_t* islandPen, int penStride, int iter) {
   for (int s = first; s < last; ++s) {
     int root = croot[s];
     if (island_done(islandPen, penStride, iter, root)) continue;
-    float minSep = solve_position_constraint(S, s, pos);
+    float minSep = solve_position_constraint(S, s, GlobalBodies{pos});
     uint32_t* slot = &islandPen[(size_t)iter * penStride + root];
     uint32_t v = __float_as_uint(minSep < 0.0f ? -minSep : 0.0f);
     if (v > *slot) *slot = v;
   }
 }
 
-__global__ void k_store_impulses(int n, SolverPlanes S, ContactBuf C) {
+__global__ void k_store_impulses(int first, int n, SolverPlanes S, ContactBuf C) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  s += first;
   int4 ix = S.idx[s];
   float4 imp = S.imp[s];
   int i = ix.w;
@@ -471,9 +478,11 @@ __device__ __forceinline__ bool body_simulated(uint32_t f, const int* __restrict
 }
 
 __global__ void k_integrate_positions(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
-                                      const uint32_t* __restrict__ islandAwake, float4* pos, float4* vel, float h) {
+                                      const uint32_t* __restrict__ islandAwake, float4* pos, float4* vel, float h,
+                                      const int* __restrict__ bodySlot, int onlyBig) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  if (onlyBig && bodySlot[b] != -2) return;
   if (!body_simulated(bflags[b], island, islandAwake, b)) return;
   float4 p4 = pos[b], v4 = vel[b];
   float2 v = make_float2(v4.x, v4.y);
@@ -501,9 +510,11 @@ __global__ void k_integrate_positions(int nb, const uint32_t* __restrict__ bflag
 __global__ void k_finalize_bodies(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                   const uint32_t* __restrict__ islandAwake, const float4* __restrict__ pos,
                                   const float4* __restrict__ vel, const float4* __restrict__ center, float4* xf,
-                                  float4* force, uint32_t* islandMinSleep, float h, int allowSleep) {
+                                  float4* force, uint32_t* islandMinSleep, float h, int allowSleep,
+                                  const int* __restrict__ bodySlot, int onlyBig) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  if (onlyBig && bodySlot[b] != -2) return;
   uint32_t f = bflags[b];
   if (!body_simulated(f, island, islandAwake, b)) return;
   float4 p4 = pos[b], c4 = center[b];
@@ -533,9 +544,11 @@ __global__ void k_sleep_and_clear(int nb, uint32_t* bflags, const int* __restric
                                   const uint32_t* __restrict__ islandAwake,
                                   const uint32_t* __restrict__ islandMinSleep,
                                   const uint32_t* __restrict__ islandPen, int penStride, int posIters, float4* vel,
-                                  float4* force, int allowSleep, int clearForces, StepCounts* counts) {
+                                  float4* force, int allowSleep, int clearForces, StepCounts* counts,
+                                  const int* __restrict__ bodySlot, int onlyBig) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  if (onlyBig && bodySlot[b] != -2) return;
   uint32_t f = bflags[b];
   float4 fo = force[b];
   bool dirty = false;
