@@ -13,6 +13,7 @@
 #define B2G_MAX_COLOURS 24          // colours solved by parallel launches
 #define B2G_OVERFLOW_COLOUR B2G_MAX_COLOURS  // serial overflow bucket
 #define B2G_MAX_POS_ITERS 16
+#define B2G_BVH_REBUILD_PERIOD 8  // steps between LBVH topology rebuilds (boxes are refit every step)
 #define B2G_KT_MAX 2048  // timed launches per step when per-kernel timing is on
 
 // device-side counters, zeroed at the start of every step; mirrored to pinned host memory
@@ -26,13 +27,23 @@ struct StepCounts {
   int lastUsefulRound;  // 1 + index of the last colouring round that coloured something
   int numBig;           // constraints of islands too large for a fused tile
   int numColours, numOverflow, maxIslandBodies;
+  int slotCursor;       // next free slot of the island-sorted body order
+  int numDead;          // contacts retired by this step's sweep
+  int freeTopRead;      // host copy of the free-stack height (filled by the readback)
   int colourCount[B2G_MAX_COLOURS + 1];
   unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
 };
 
-// contacts are rebuilt in sorted-key order after every broadphase, so they are double buffered
+// (fixLo << 32 | fixHi) -> contact slot, open addressing; see b2g_broadphase.cuh
+struct ContactHash {
+  unsigned long long* keys;
+  int* vals;
+  unsigned int mask;  // capacity - 1 (capacity is a power of two)
+};
+
+// contacts live in stable slots; a slot is live when its flags carry B2G_CONTACT_ALIVE
 struct ContactBuf {
-  unsigned long long* key;  // [bucket | fixLo | fixHi], sorted ascending
+  unsigned long long* key;  // fixLo << 32 | fixHi (the contact's identity)
   int2* fix;                // fixtureA, fixtureB (A/B by the type table, b2_contact.cpp:58-77)
   int2* body;               // bodyA, bodyB
   uint32_t* flags;          // B2G_CONTACT_*
@@ -54,6 +65,7 @@ struct b2gArena {
   int nBodies, nFixtures, nJoints, nContacts;
   int fixBits;        // bits per fixture index in the pair key
   int aabbAllDirty;   // recompute static AABBs too (after fixture / body upload)
+  int bvhLeaves, bvhAge;  // leaves of the current LBVH topology, steps since it was built
   int recolour;       // drop persistent colours (after mass / type edits)
   int roundsHint;     // colouring rounds to launch before the first check
   float invDt0;
@@ -79,7 +91,7 @@ struct b2gArena {
   unsigned long long* colourMask;  // per body: colours used by its constraints
   unsigned long long* bodyBest;    // per body: best proposal this round
   // fused solver: island-sorted body slots and bins
-  int *islandCount, *islandStart, *islandCursor, *bodySlot, *slotBody, *binFirst, *binEnd, *cbin;
+  int *islandCount, *islandStart, *islandCursor, *bodySlot, *slotBody, *binFirst, *binEnd, *cbin, *bucketCount, *bucketStart;
   unsigned int *conKeys, *conKeysSorted;
   int *conVals;
   int nbinsMax, bigMode, lastMaxIsland;
@@ -103,9 +115,15 @@ struct b2gArena {
   float4* jState;    // impulse.x, impulse.y, motorImpulse, lowerImpulse/upperImpulse packed later
 
   // contacts
-  ContactBuf cb[2];
-  int cur;
-  uint8_t* oldPersist;
+  ContactBuf cb[1];           // stable slots; nContacts = slot high-water mark, nAlive = live contacts
+  unsigned long long* seqKeys;  // [2][capContacts] scratch: key sort of the sequential mode's list
+  uint8_t* persist;           // per slot: pair re-reported by this step's broadphase
+  int* freeStack;             // free slots (LIFO)
+  int* dFreeTop;              // device: entries in freeStack
+  int nAlive, tombstones;
+  ContactHash hash;
+  int* downloadSlots;  // host: slot of each contact in the order of the last download
+  int downloadCount;
 
   // broadphase scratch
   unsigned long long *mortonKeys, *mortonKeysSorted;
@@ -120,7 +138,7 @@ struct b2gArena {
   float4 *nodeBoxL, *nodeBoxR;
   int* leafParent;
   int* nodeVisit;
-  unsigned long long *pairKeys;
+  unsigned long long *pairKeys;  // new pairs (no live contact yet) reported by the traversal
 
   // solver scratch
   uint8_t* activeFlag;

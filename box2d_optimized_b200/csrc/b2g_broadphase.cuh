@@ -11,8 +11,8 @@
 // SET it reports is exactly "all fixture pairs with inclusive tight-AABB overlap" (SURVEY
 // Appendix B.20), independent of tree shape.  The device path therefore builds a linear BVH
 // (Karras 2012) over Morton-sorted fixture AABBs every step and lets every leaf traverse it,
-// reporting each pair once (by its smaller-AABB member), with warp-aggregated
-// compaction into a key list that is then sorted and merged against the previous contacts.
+// reporting each pair once (by its smaller-AABB member); a hash probe either flags the pair's
+// existing contact as persisting or queues the pair (warp-aggregated compaction) for creation.
 #pragma once
 #include "b2g_step_kernels.cuh"
 
@@ -160,6 +160,30 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
   }
 }
 
+// Refit-only steps: the tree TOPOLOGY of the last rebuild is kept (any valid BVH reports the same
+// exact pair set); every leaf gets its fresh tight AABB and size key.  Replaces k_update_aabbs +
+// k_morton_keys + sort + k_leaf_gather + k_lbvh_build on the steps between rebuilds.
+__global__ void __launch_bounds__(256)
+k_refresh_leaves(int nf, const int* __restrict__ leafFixtureSorted, const int* __restrict__ fBody,
+                 const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
+                 const float4* __restrict__ shapes, const uint32_t* __restrict__ bflags,
+                 const float4* __restrict__ xf, float4* fAabb, float4* leafBox, unsigned long long* leafKey) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nf) return;
+  int f = leafFixtureSorted[p];
+  uint32_t tf = fTypeFlags[f];
+  if (tf & B2G_FIX_DEAD) return;  // keeps the empty box written at the last rebuild
+  int b = fBody[f];
+  float4 box;
+  if (B2G_BODY_TYPE(bflags[b]) != B2G_STATIC) {
+    box = shape_aabb(shapes, (int)(tf & 3u), fShapeOff[f], xf_from4(xf[b]));
+    fAabb[f] = box;
+    leafBox[p] = box;
+    float size = (box.z - box.x) + (box.w - box.y);
+    leafKey[p] = ((unsigned long long)__float_as_uint(fmaxf(size, 0.0f)) << 32) | (unsigned int)p;
+  }
+}
+
 // ---- Karras 2012: one thread per internal node -------------------------------------------------
 __device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
@@ -261,20 +285,77 @@ __device__ __forceinline__ unsigned int type_bucket(unsigned int ta, unsigned in
   return 4;
 }
 
-__device__ __forceinline__ void emit_pair(int4 a, int4 b, unsigned long long* pairKeys, int capacity, int fixBits,
-                                          StepCounts* counts) {
-  bool ok = pair_passes(a, b);
-  if (!ok) return;
+// ---- contact identity: open-addressing hash table  (fixLo << 32 | fixHi) -> contact slot --------
+// The reference looks an existing contact up by scanning the body's contact array
+// (b2_contact_manager.cpp:145-158); here it is one hash probe.  Empty key = ~0, value -1 = tombstone.
+#define B2G_HASH_EMPTY 0xffffffffffffffffull
+__device__ __forceinline__ unsigned int hash_slot(unsigned long long k, unsigned int mask) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (unsigned int)k & mask;
+}
+// returns the contact slot, or -1 when the pair has no live contact
+__device__ __forceinline__ int hash_find(const ContactHash& H, unsigned long long key) {
+  unsigned int p = hash_slot(key, H.mask);
+  while (true) {
+    unsigned long long k = H.keys[p];
+    if (k == key) return H.vals[p];
+    if (k == B2G_HASH_EMPTY) return -1;
+    p = (p + 1) & H.mask;
+  }
+}
+__device__ __forceinline__ void hash_insert(const ContactHash& H, unsigned long long key, int slot) {
+  unsigned int p = hash_slot(key, H.mask);
+  while (true) {
+    unsigned long long k = H.keys[p];
+    if (k == key) {  // tombstone of the same pair: revive
+      H.vals[p] = slot;
+      return;
+    }
+    if (k == B2G_HASH_EMPTY) {
+      unsigned long long old = atomicCAS(&H.keys[p], B2G_HASH_EMPTY, key);
+      if (old == B2G_HASH_EMPTY || old == key) {
+        H.vals[p] = slot;
+        return;
+      }
+    }
+    p = (p + 1) & H.mask;
+  }
+}
+__device__ __forceinline__ void hash_erase(const ContactHash& H, unsigned long long key) {
+  unsigned int p = hash_slot(key, H.mask);
+  while (true) {
+    unsigned long long k = H.keys[p];
+    if (k == key) {
+      H.vals[p] = -1;
+      return;
+    }
+    if (k == B2G_HASH_EMPTY) return;
+    p = (p + 1) & H.mask;
+  }
+}
+
+// b2ContactManager::QueryCallback (b2_contact_manager.cpp:136-188): an overlapping, filter-passing
+// pair either persists its existing contact or is queued for creation
+__device__ __forceinline__ void emit_pair(int4 a, int4 b, const ContactHash& H, uint8_t* persist,
+                                          unsigned long long* newPairs, int capacity, StepCounts* counts) {
+  if (!pair_passes(a, b)) return;
+  unsigned long long lo = (unsigned long long)min(a.x, b.x), hi = (unsigned long long)max(a.x, b.x);
+  unsigned long long key = (lo << 32) | hi;
+  int slot = hash_find(H, key);
+  if (slot >= 0) {
+    persist[slot] = 1;
+    return;
+  }
   auto g = cg::coalesced_threads();
   int base = 0;
   if (g.thread_rank() == 0) base = atomicAdd(&counts->numPairs, (int)g.size());
   base = g.shfl(base, 0);
   int k = base + (int)g.thread_rank();
-  if (k < capacity) {
-    unsigned long long lo = (unsigned long long)min(a.x, b.x), hi = (unsigned long long)max(a.x, b.x);
-    unsigned long long bucket = type_bucket((unsigned int)a.z & 3u, (unsigned int)b.z & 3u);
-    pairKeys[k] = (bucket << (2 * fixBits)) | (lo << fixBits) | hi;
-  }
+  if (k < capacity) newPairs[k] = key;
 }
 
 // one thread per query leaf.  Leaf i reports partner j iff key(j) > key(i) (each pair once, by
@@ -286,7 +367,7 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
               const float4* __restrict__ nodeBoxL, const float4* __restrict__ nodeBoxR,
               const ulonglong2* __restrict__ nodeMaxKey, const int* __restrict__ worldFirst,
               const int* __restrict__ worldLast, const unsigned long long* __restrict__ keysSorted, int numWorlds,
-              unsigned long long* pairKeys, int capacity, int fixBits, StepCounts* counts) {
+              ContactHash H, uint8_t* persist, unsigned long long* newPairs, int capacity, StepCounts* counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || n < 2) return;
   int4 me = leafInfo[i];
@@ -308,97 +389,48 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
     ulonglong2 mk = nodeMaxKey[node];
     // left child covers [first, split]
     if (mk.x > myKey && nr.x <= we && nr.y >= ws && aabb_overlap(qbox, nodeBoxL[node])) {
-      if (nr.x == nr.y) emit_pair(me, leafInfo[nr.y], pairKeys, capacity, fixBits, counts);
+      if (nr.x == nr.y) emit_pair(me, leafInfo[nr.y], H, persist, newPairs, capacity, counts);
       else stack[sp++] = nr.y;
     }
     // right child covers [split+1, last]
     if (mk.y > myKey && nr.y + 1 <= we && nr.z >= ws && aabb_overlap(qbox, nodeBoxR[node])) {
-      if (nr.y + 1 == nr.z) emit_pair(me, leafInfo[nr.z], pairKeys, capacity, fixBits, counts);
+      if (nr.y + 1 == nr.z) emit_pair(me, leafInfo[nr.z], H, persist, newPairs, capacity, counts);
       else stack[sp++] = nr.y + 1;
     }
   }
 }
 
-// ---- pair list -> contact list ---------------------------------------------------------------
-__device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restrict__ a, int n,
-                                               unsigned long long key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (a[mid] < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// new contact i takes its persistent state from the old contact with the same key (the
-// e_persistFlag protocol) or is created fresh (b2Contact ctor, b2_contact.cpp:96-122)
-__global__ void __launch_bounds__(256)
-k_contact_merge(int nNew, const unsigned long long* __restrict__ newKeys, int nOld, ContactBuf O, ContactBuf N,
-                uint8_t* oldPersist, int fixBits, const int* __restrict__ fBody,
-                const uint32_t* __restrict__ fTypeFlags, const float4* __restrict__ fMaterial) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nNew) return;
-  unsigned long long key = newKeys[i];
-  N.key[i] = key;
-  int j = lower_bound_u64(O.key, nOld, key);
-  if (j < nOld && O.key[j] == key) {
-    oldPersist[j] = 1;
-    N.fix[i] = O.fix[j];
-    N.body[i] = O.body[j];
-    N.flags[i] = O.flags[j];
-    N.material[i] = O.material[j];
-    N.m0[i] = O.m0[j];
-    N.m1[i] = O.m1[j];
-    N.m2[i] = O.m2[j];
-    N.m3[i] = O.m3[j];
-    N.colour[i] = O.colour[j];
-    return;
-  }
-  unsigned long long maskBits = (1ull << fixBits) - 1ull;
-  int lo = (int)((key >> fixBits) & maskBits), hi = (int)(key & maskBits);
-  unsigned int tl = fTypeFlags[lo] & 3u, th = fTypeFlags[hi] & 3u;
-  // A/B order from the function table: [circle][circle] [polygon][circle] [polygon][polygon]
-  // [edge][circle] [edge][polygon]; same-type pairs keep the lower fixture index as A
-  bool loFirst = (tl == th) || (tl == B2G_SHAPE_POLYGON && th == B2G_SHAPE_CIRCLE) ||
-                 (tl == B2G_SHAPE_EDGE && th == B2G_SHAPE_CIRCLE) || (tl == B2G_SHAPE_EDGE && th == B2G_SHAPE_POLYGON);
-  int fa = loFirst ? lo : hi, fb = loFirst ? hi : lo;
-  N.fix[i] = make_int2(fa, fb);
-  N.body[i] = make_int2(fBody[fa], fBody[fb]);
-  N.flags[i] = B2G_CONTACT_ENABLED;
-  float4 ma = fMaterial[fa], mb = fMaterial[fb];
-  // mixing laws, include/box2d/b2_contact.h:42-60
-  float friction = sqrtf(ma.x * mb.x);
-  float restitution = ma.y > mb.y ? ma.y : mb.y;
-  float threshold = ma.z < mb.z ? ma.z : mb.z;
-  N.material[i] = make_float4(friction, restitution, threshold, 0.0f);
-  float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  N.m0[i] = z;
-  N.m1[i] = z;
-  N.m2[i] = z;
-  N.m3[i] = z;
-  N.colour[i] = -1;
-}
+// ---- contact list maintenance -------------------------------------------------------------------
+// Contacts live in STABLE slots (no per-step sort or copy).  After the traversal has flagged every
+// still-overlapping pair, k_contact_sweep retires the rest and k_contact_insert creates the new
+// ones in free slots.  Slot numbers are not deterministic (free-list order), and nothing depends
+// on them: islands, colours and the solver are functions of bodies and pair keys only.
 
 // contacts that were not re-reported die: b2ContactManager::Destroy (b2_contact_manager.cpp:48-61)
 // fires EndContact if touching, b2Contact::Destroy (b2_contact.cpp:79-94) wakes both bodies if the
 // manifold had points
-__global__ void k_contact_dead(int nOld, ContactBuf O, const uint8_t* __restrict__ oldPersist,
-                               const uint32_t* __restrict__ fTypeFlags, uint32_t* bflags, float4* force,
-                               StepCounts* counts, int recordEvents, int2* endEvents, int eventCap) {
+__global__ void k_contact_sweep(int nSlots, ContactBuf C, uint8_t* persist, ContactHash H,
+                                const uint32_t* __restrict__ fTypeFlags, uint32_t* bflags, float4* force,
+                                int* freeStack, int* freeTop, StepCounts* counts, int recordEvents, int2* endEvents,
+                                int eventCap) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nOld) return;
-  if (oldPersist[j]) return;
-  int2 fx = O.fix[j];
-  uint32_t flags = O.flags[j];
+  if (j >= nSlots) return;
+  uint32_t flags = C.flags[j];
+  if (!(flags & B2G_CONTACT_ALIVE)) return;
+  if (persist[j]) {
+    persist[j] = 0;
+    return;
+  }
+  int2 fx = C.fix[j];
   if (recordEvents && (flags & B2G_CONTACT_TOUCHING)) {
     int k = atomicAdd(&counts->endCount, 1);
     if (k < eventCap) endEvents[k] = fx;
   }
-  int pointCount = __float_as_int(O.m3[j].w);
+  int pointCount = __float_as_int(C.m3[j].w);
   if (pointCount > 0 && !((fTypeFlags[fx.x] | fTypeFlags[fx.y]) & B2G_FIX_SENSOR)) {
     // SetAwake(true) takes effect immediately (the next Collide must see the body awake);
     // concurrent writers all store the same values
-    int2 bd = O.body[j];
+    int2 bd = C.body[j];
     if (B2G_BODY_TYPE(bflags[bd.x]) != B2G_STATIC) {
       atomicOr(&bflags[bd.x], B2G_BODY_AWAKE);
       force[bd.x].w = 0.0f;
@@ -408,4 +440,56 @@ __global__ void k_contact_dead(int nOld, ContactBuf O, const uint8_t* __restrict
       force[bd.y].w = 0.0f;
     }
   }
+  C.flags[j] = 0;
+  C.colour[j] = -1;
+  hash_erase(H, C.key[j]);
+  int t = atomicAdd(freeTop, 1);
+  freeStack[t] = j;
+  atomicAdd(&counts->numDead, 1);
+}
+
+// new contacts (b2Contact::Create + ctor, b2_contact.cpp:58-122): slot from the free stack, else
+// appended past the high-water mark
+__global__ void __launch_bounds__(256)
+k_contact_insert(int nNew, const unsigned long long* __restrict__ newPairs, int freeTopBefore, int highWater,
+                 ContactBuf C, uint8_t* persist, ContactHash H, const int* __restrict__ freeStack, int* freeTop,
+                 const int* __restrict__ fBody, const uint32_t* __restrict__ fTypeFlags,
+                 const float4* __restrict__ fMaterial) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *freeTop = freeTopBefore > nNew ? freeTopBefore - nNew : 0;
+  if (i >= nNew) return;
+  unsigned long long key = newPairs[i];
+  int slot = i < freeTopBefore ? freeStack[freeTopBefore - 1 - i] : highWater + (i - freeTopBefore);
+  int lo = (int)(key >> 32), hi = (int)(key & 0xffffffffull);
+  unsigned int tl = fTypeFlags[lo] & 3u, th = fTypeFlags[hi] & 3u;
+  // A/B order from the function table: [circle][circle] [polygon][circle] [polygon][polygon]
+  // [edge][circle] [edge][polygon]; same-type pairs keep the lower fixture index as A
+  bool loFirst = (tl == th) || (tl == B2G_SHAPE_POLYGON && th == B2G_SHAPE_CIRCLE) ||
+                 (tl == B2G_SHAPE_EDGE && th == B2G_SHAPE_CIRCLE) || (tl == B2G_SHAPE_EDGE && th == B2G_SHAPE_POLYGON);
+  int fa = loFirst ? lo : hi, fb = loFirst ? hi : lo;
+  C.key[slot] = key;
+  C.fix[slot] = make_int2(fa, fb);
+  C.body[slot] = make_int2(fBody[fa], fBody[fb]);
+  C.flags[slot] = B2G_CONTACT_ENABLED | B2G_CONTACT_ALIVE;
+  float4 ma = fMaterial[fa], mb = fMaterial[fb];
+  // mixing laws, include/box2d/b2_contact.h:42-60
+  float friction = sqrtf(ma.x * mb.x);
+  float restitution = ma.y > mb.y ? ma.y : mb.y;
+  float threshold = ma.z < mb.z ? ma.z : mb.z;
+  C.material[slot] = make_float4(friction, restitution, threshold, 0.0f);
+  float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  C.m0[slot] = z;
+  C.m1[slot] = z;
+  C.m2[slot] = z;
+  C.m3[slot] = z;
+  C.colour[slot] = -1;
+  persist[slot] = 0;
+  hash_insert(H, key, slot);
+}
+
+// rebuild the table from the live contacts (drops tombstones)
+__global__ void k_hash_rebuild(int nSlots, ContactBuf C, ContactHash H) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nSlots) return;
+  if (C.flags[j] & B2G_CONTACT_ALIVE) hash_insert(H, C.key[j], j);
 }

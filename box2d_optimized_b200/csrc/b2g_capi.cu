@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include "b2g_broadphase.cuh"
 #include "b2g_fused.cuh"
 #include <thrust/iterator/transform_iterator.h>
@@ -28,6 +29,35 @@ static int set_err(const char* what, const char* detail) {
   } while (0)
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  template <typename T>
+  T* as() {
+    return (T*)p;
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  cudaError_t upload(const void* src, size_t bytes) {
+    cudaError_t e = alloc(bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
+  }
+};
+
+static int use_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("b2cuda", "no CUDA device: this library has no CPU fallback");
+    return B2G_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(device));
+  return B2G_OK;
+}
+
 // kernel classes for the per-kernel timing of bench.py's roofline line (b2g_get_kernel_timing)
 enum KClass {
   KC_NARROWPHASE, KC_ISLANDS, KC_INTEGRATE, KC_COLOUR, KC_PREPARE, KC_WARM_START, KC_SOLVE_VELOCITY,
@@ -181,6 +211,8 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   A->nbinsMax = nb / 32 + 8;
   CK(dalloc(&A->binFirst, A->nbinsMax));
   CK(dalloc(&A->binEnd, A->nbinsMax));
+  CK(dalloc(&A->bucketCount, (size_t)(A->nbinsMax + 1) * 32 + 1));
+  CK(dalloc(&A->bucketStart, (size_t)(A->nbinsMax + 1) * 32 + 1));
 
   CK(dalloc(&A->fBody, nf));
   CK(dalloc(&A->fShapeOff, nf));
@@ -199,9 +231,19 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
 
   int rc = alloc_contact_buf(A->cb[0], nc);
   if (rc) return rc;
-  rc = alloc_contact_buf(A->cb[1], nc);
-  if (rc) return rc;
-  CK(dalloc(&A->oldPersist, nc));
+  CK(dalloc(&A->persist, nc));
+  CK(dalloc(&A->seqKeys, (size_t)2 * nc));
+  CK(dalloc(&A->freeStack, nc));
+  CK(dalloc(&A->dFreeTop, 1));
+  {
+    unsigned int cap = 1024;
+    while (cap < 2u * (unsigned int)nc) cap <<= 1;
+    A->hash.mask = cap - 1;
+    CK(cudaMalloc((void**)&A->hash.keys, (size_t)cap * 8));
+    CK(cudaMalloc((void**)&A->hash.vals, (size_t)cap * 4));
+    CK(cudaMemset(A->hash.keys, 0xff, (size_t)cap * 8));
+    CK(cudaMemset(A->hash.vals, 0xff, (size_t)cap * 4));
+  }
 
   CK(dalloc(&A->mortonKeys, nf));
   CK(dalloc(&A->mortonKeysSorted, nf));
@@ -257,22 +299,15 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   cub::DeviceRadixSort::SortPairs(nullptr, t, A->mortonKeys, A->mortonKeysSorted, A->leafFixture,
                                   A->leafFixtureSorted, nf, 0, 64, A->stream);
   need = t > need ? t : need;
-  cub::DeviceRadixSort::SortKeys(nullptr, t, A->pairKeys, A->cb[0].key, nc, 0, 64, A->stream);
-  need = t > need ? t : need;
   cub::DeviceRadixSort::SortPairs(nullptr, t, A->colourKey, A->colourKeySorted, A->activeList, A->sortedList, nc, 0, 8,
                                   A->stream);
   need = t > need ? t : need;
   cub::DeviceSelect::Flagged(nullptr, t, thrust::counting_iterator<int>(0), A->activeFlag, A->activeList,
                              &A->dCounts->numActive, nc, A->stream);
   need = t > need ? t : need;
-  cub::DeviceRadixSort::SortPairs(nullptr, t, A->conKeys, A->conKeysSorted, A->conVals, A->sortedList, nc, 0, 32,
+  cub::DeviceRadixSort::SortPairs(nullptr, t, A->seqKeys, A->seqKeys + nc, A->activeList, A->sortedList, nc, 0, 64,
                                   A->stream);
   need = t > need ? t : need;
-  {
-    auto in = thrust::make_transform_iterator(A->islandCount, FusedCountOp{1024});
-    cub::DeviceScan::ExclusiveSum(nullptr, t, in, A->islandStart, nb, A->stream);
-    need = t > need ? t : need;
-  }
   A->cubTempBytes = need + 256;
   CK(cudaMalloc(&A->cubTemp, A->cubTempBytes));
   CK(cudaStreamSynchronize(A->stream));
@@ -286,9 +321,9 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   cudaStreamSynchronize(A->stream);
   void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent,
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
-                  A->binFirst, A->binEnd, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
+                  A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->oldPersist, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->nodeMaxKey, A->worldFirst, A->worldLast, A->nodeRange, A->nodeBoxL, A->nodeBoxR, A->leafParent,
                   A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -297,7 +332,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->cubTemp};
   for (void* p : ptrs) cudaFree(p);
   free_contact_buf(A->cb[0]);
-  free_contact_buf(A->cb[1]);
+  free(A->downloadSlots);
   cudaFreeHost(A->hCounts);
   cudaFreeHost(A->hostStage);
   for (int i = 0; i < 5; ++i) cudaEventDestroy(A->ev[i]);
@@ -430,65 +465,85 @@ static int reset_bounds(b2gArena* A) {
 
 static int find_new_contacts(b2gArena* A, int recordEvents) {
   const int nf = A->nFixtures;
-  ContactBuf& O = A->cb[A->cur];
-  ContactBuf& N = A->cb[A->cur ^ 1];
-  const int nOld = A->nContacts;
+  ContactBuf& C = A->cb[0];
+  const int nSlots = A->nContacts;  // slot high-water mark
   int nNew = 0;
   if (nf > 0) {
-    int rc = reset_bounds(A);
-    if (rc) return rc;
     CK(cudaMemsetAsync(&A->dCounts->numPairs, 0, sizeof(int), A->stream));
-    LAUNCH(A, KC_BP_BUILD, nf, k_update_aabbs, div_up(nf, 256), 256, nf, A->fBody, A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags,
-           A->xf, A->fAabb, A->fRadius, A->aabbAllDirty, A->dCounts);
-    A->aabbAllDirty = 0;
-    LAUNCH(A, KC_BP_BUILD, nf, k_morton_keys, div_up(nf, 256), 256, nf, A->fAabb, A->fTypeFlags, A->fBody, A->bworld, A->dCounts,
-           A->mortonKeys, A->leafFixture, A->numWorlds);
-    size_t tb = A->cubTempBytes;
-    TIMED(A, KC_SORT_SCAN, nf,
-          CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb, A->mortonKeys, A->mortonKeysSorted, A->leafFixture,
-                                             A->leafFixtureSorted, nf, 0,
-                                             32 + (A->numWorlds > 1 ? A->worldBits : 0), A->stream)));
-    LAUNCH(A, KC_BP_BUILD, nf, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted, A->fAabb, A->fBody,
-           A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->leafKey, A->worldFirst, A->worldLast,
-           A->numWorlds);
-    CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
+    // The LBVH topology is rebuilt (Morton sort + Karras build) when fixtures were added / edited
+    // or every B2G_BVH_REBUILD_PERIOD steps; in between only the boxes are refit.  The reported
+    // pair set is exact either way — only traversal cost depends on tree quality.
+    const bool rebuild = A->aabbAllDirty != 0 || A->bvhLeaves != nf || A->bvhAge >= B2G_BVH_REBUILD_PERIOD;
+    if (rebuild) {
+      int rc = reset_bounds(A);
+      if (rc) return rc;
+      LAUNCH(A, KC_BP_BUILD, nf, k_update_aabbs, div_up(nf, 256), 256, nf, A->fBody, A->fShapeOff, A->fTypeFlags,
+             A->shapes, A->bflags, A->xf, A->fAabb, A->fRadius, A->aabbAllDirty, A->dCounts);
+      A->aabbAllDirty = 0;
+      LAUNCH(A, KC_BP_BUILD, nf, k_morton_keys, div_up(nf, 256), 256, nf, A->fAabb, A->fTypeFlags, A->fBody, A->bworld,
+             A->dCounts, A->mortonKeys, A->leafFixture, A->numWorlds);
+      size_t tb = A->cubTempBytes;
+      TIMED(A, KC_SORT_SCAN, nf,
+            CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb, A->mortonKeys, A->mortonKeysSorted, A->leafFixture,
+                                               A->leafFixtureSorted, nf, 0,
+                                               32 + (A->numWorlds > 1 ? A->worldBits : 0), A->stream)));
+      LAUNCH(A, KC_BP_BUILD, nf, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted,
+             A->fAabb, A->fBody, A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->leafKey,
+             A->worldFirst, A->worldLast, A->numWorlds);
+      CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
+      if (nf > 1)
+        LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange,
+               A->leafParent);
+      A->bvhLeaves = nf;
+      A->bvhAge = 0;
+    } else {
+      LAUNCH(A, KC_BP_BUILD, nf, k_refresh_leaves, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->fBody,
+             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey);
+      A->bvhAge++;
+    }
     CK(cudaMemsetAsync(A->nodeVisit, 0, sizeof(int) * nf, A->stream));
     if (nf > 1) {
-      LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange, A->leafParent);
       LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent, A->nodeRange,
              A->nodeBoxL, A->nodeBoxR, A->nodeMaxKey, A->nodeVisit);
       LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->nodeRange, A->nodeBoxL,
-             A->nodeBoxR, A->nodeMaxKey, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->pairKeys,
-             A->capContacts, A->fixBits, A->dCounts);
+             A->nodeBoxR, A->nodeMaxKey, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash,
+             A->persist, A->pairKeys, A->capContacts, A->dCounts);
     }
-    int rc2 = read_counts(A);  // the one mid-pipeline sync: the sort below needs the pair count
-    if (rc2) return rc2;
-    nNew = A->hCounts->numPairs;
-    if (nNew > A->capContacts) {
-      char msg[128];
-      snprintf(msg, sizeof(msg), "broadphase found %d pairs, max_contacts is %d", nNew, A->capContacts);
-      set_err("b2g_step", msg);
-      return B2G_ERR_CAPACITY;
-    }
+  }
+  // retire contacts whose pair was not re-reported (all of them when there are no fixtures left)
+  if (nSlots > 0) {
+    LAUNCH(A, KC_CONTACT_MERGE, nSlots, k_contact_sweep, div_up(nSlots, 256), 256, nSlots, C, A->persist, A->hash,
+           A->fTypeFlags, A->bflags, A->force, A->freeStack, A->dFreeTop, A->dCounts, recordEvents, A->endEvents,
+           A->capContacts);
+  }
+  // the end-of-broadphase readback: how many pairs are new, how many contacts died
+  CK(cudaMemcpyAsync(A->hCounts, A->dCounts, sizeof(StepCounts), cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(&A->hCounts->freeTopRead, A->dFreeTop, sizeof(int), cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  nNew = A->hCounts->numPairs;
+  const int freeTop = A->hCounts->freeTopRead;
+  A->tombstones += A->hCounts->numDead;
+  const int appended = nNew > freeTop ? nNew - freeTop : 0;
+  if (nNew > A->capContacts || nSlots + appended > A->capContacts) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "broadphase needs %d contact slots (%d new pairs), max_contacts is %d",
+             nSlots + appended, nNew, A->capContacts);
+    set_err("b2g_step", msg);
+    return B2G_ERR_CAPACITY;
   }
   if (nNew > 0) {
-    size_t tb = A->cubTempBytes;
-    // sorted straight into the new buffer's key array, then merged in place
-    TIMED(A, KC_SORT_SCAN, nNew,
-          CK(cub::DeviceRadixSort::SortKeys(A->cubTemp, tb, A->pairKeys, N.key, nNew, 0, 3 + 2 * A->fixBits,
-                                            A->stream)));
-    CK(cudaMemsetAsync(A->oldPersist, 0, nOld > 0 ? nOld : 1, A->stream));
-    LAUNCH(A, KC_CONTACT_MERGE, nNew, k_contact_merge, div_up(nNew, 256), 256, nNew, N.key, nOld, O, N, A->oldPersist, A->fixBits, A->fBody,
-           A->fTypeFlags, A->fMaterial);
-  } else if (nOld > 0) {
-    CK(cudaMemsetAsync(A->oldPersist, 0, nOld, A->stream));
+    LAUNCH(A, KC_CONTACT_MERGE, nNew, k_contact_insert, div_up(nNew, 256), 256, nNew, A->pairKeys, freeTop, nSlots, C,
+           A->persist, A->hash, A->freeStack, A->dFreeTop, A->fBody, A->fTypeFlags, A->fMaterial);
   }
-  if (nOld > 0) {
-    LAUNCH(A, KC_CONTACT_MERGE, nOld, k_contact_dead, div_up(nOld, 256), 256, nOld, O, A->oldPersist, A->fTypeFlags, A->bflags, A->force,
-           A->dCounts, recordEvents, A->endEvents, A->capContacts);
+  A->nContacts = nSlots + appended;
+  A->nAlive += nNew - A->hCounts->numDead;
+  // tombstones slow probes down: rebuild the table once they rival the live entries
+  if (A->tombstones > (int)((A->hash.mask + 1) / 4)) {
+    CK(cudaMemsetAsync(A->hash.keys, 0xff, (size_t)(A->hash.mask + 1) * 8, A->stream));
+    CK(cudaMemsetAsync(A->hash.vals, 0xff, (size_t)(A->hash.mask + 1) * 4, A->stream));
+    LAUNCH(A, KC_CONTACT_MERGE, A->nContacts, k_hash_rebuild, div_up(A->nContacts, 256), 256, A->nContacts, C, A->hash);
+    A->tombstones = 0;
   }
-  A->cur ^= 1;
-  A->nContacts = nNew;
   return B2G_OK;
 }
 
@@ -517,7 +572,7 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   const int nb = A->nBodies, nc = A->nContacts, nj = A->nJoints;
   const float h = P->dt;
   const float dtRatio = A->invDt0 * h;
-  ContactBuf& C = A->cb[A->cur];
+  ContactBuf& C = A->cb[0];
   int numActive = 0, numColours = 0, numOverflow = 0, rounds = 0;
   int colourFirst[B2G_MAX_COLOURS + 2];
   memset(colourFirst, 0, sizeof(colourFirst));
@@ -591,9 +646,14 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         int rc = read_counts(A);
         if (rc) return rc;
         numActive = A->hCounts->numActive;
-        if (numActive > 0)
-          CK(cudaMemcpyAsync(A->sortedList, A->activeList, sizeof(int) * numActive, cudaMemcpyDeviceToDevice,
-                             A->stream));
+        if (numActive > 0) {
+          // contact slots are unordered; the sequential mode's list order is ascending pair key
+          LAUNCH(A, KC_COLOUR, numActive, k_gather_keys, div_up(numActive, 256), 256, numActive, A->activeList, C,
+                 A->seqKeys);
+          size_t tb3 = A->cubTempBytes;
+          CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb3, A->seqKeys, A->seqKeys + A->capContacts, A->activeList,
+                                             A->sortedList, numActive, 0, 64, A->stream));
+        }
       }
     }
 
@@ -675,9 +735,13 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   const int nb = A->nBodies, nc = A->nContacts, nj = A->nJoints;
   const float h = P->dt;
   const float dtRatio = A->invDt0 * h;
-  ContactBuf& C = A->cb[A->cur];
+  ContactBuf& C = A->cb[0];
   SolverPlanes& S = A->planes;
-  const int bigThr = B2G_BIG_ISLAND;
+  // Tile capacity follows the largest island of the previous step (x1.5 + slack): small islands
+  // leave shared memory for the constraint planes and a second resident block per SM.  An island
+  // that outgrows the cap within one step is simply routed to the big path for that step.
+  int bigThr = A->lastMaxIsland + A->lastMaxIsland / 2 + 64;
+  if (bigThr > B2G_BIG_ISLAND) bigThr = B2G_BIG_ISLAND;
   // aim at >= 2 bins per SM so the fused kernel fills the chip, within what a tile can hold
   int binSize = nb / (2 * 148);
   if (binSize < 32) binSize = 32;
@@ -689,7 +753,12 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     return B2G_ERR_CAPACITY;
   }
   const int tileCap = binSize - 1 + bigThr;
-  const size_t smem = FusedTile::bytes(tileCap);
+  const size_t tileBytes = FusedTile::bytes(tileCap);
+  // two blocks per SM when the tile allows it (113 KB each), otherwise one large block
+  size_t budget = tileBytes + 32 * 1024 <= 113 * 1024 ? 113 * 1024 : 225 * 1024;
+  int conCap = (int)((budget - tileBytes) / (B2G_PLANES * 16));
+  if (conCap < 0) conCap = 0;
+  const size_t smem = tileBytes + (size_t)conCap * B2G_PLANES * 16;
 
   CK(cudaMemsetAsync(A->binFirst, 0x7f, sizeof(int) * (nbins + 1), A->stream));
   CK(cudaMemsetAsync(A->binEnd, 0, sizeof(int) * (nbins + 1), A->stream));
@@ -704,14 +773,10 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
          A->islandAwake);
   LAUNCH(A, KC_ISLANDS, nb, k_island_count, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
          A->islandCount, A->dCounts);
-  {
-    size_t tb = A->cubTempBytes;
-    auto in = thrust::make_transform_iterator(A->islandCount, FusedCountOp{bigThr});
-    TIMED(A, KC_SORT_SCAN, nb, CK(cub::DeviceScan::ExclusiveSum(A->cubTemp, tb, in, A->islandStart, nb, A->stream)));
-  }
+  LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandCount, A->islandStart,
+         A->binFirst, A->binEnd, binSize, bigThr, A->dCounts);
   LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
-         A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, A->binFirst, A->binEnd, binSize,
-         bigThr);
+         A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr);
 
   int numActive = 0, numBig = 0, rounds = 0;
   if (nc > 0) {
@@ -749,13 +814,12 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     out.numColours = A->hCounts->numColours;
     out.numOverflow = A->hCounts->numOverflow;
     if (numActive > 0) {
-      LAUNCH(A, KC_COLOUR, nc, k_constraint_keys, div_up(nc, 256), 256, nc, A->cbin, C, A->conKeys, A->conVals);
-      size_t tb = A->cubTempBytes;
-      int keyBits = B2G_COLOUR_BITS + bits_for(nbins + 2);
-      if (keyBits > 32) keyBits = 32;
-      TIMED(A, KC_SORT_SCAN, nc,
-            CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb, A->conKeys, A->conKeysSorted, A->conVals,
-                                               A->sortedList, nc, 0, keyBits, A->stream)));
+      const int nbuckets = (nbins + 1) << B2G_COLOUR_BITS;
+      CK(cudaMemsetAsync(A->bucketCount, 0, sizeof(int) * nbuckets, A->stream));
+      LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
+      LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
+      LAUNCH(A, KC_COLOUR, nc, k_bucket_scatter, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketStart, A->conVals,
+             A->sortedList);
     }
   }
   A->lastMaxIsland = nc > 0 ? A->hCounts->maxIslandBodies : 0;
@@ -774,14 +838,15 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     FP.allowSleep = P->allow_sleep;
     FP.clearForces = P->clear_forces;
     FP.tileCap = tileCap;
+    FP.conCap = conCap;
     if (smem > A->fusedSmemSet) {
       CK(cudaFuncSetAttribute(k_solve_bins_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       A->fusedSmemSet = smem;
     }
     ktime_begin(A, KC_FUSED_SOLVE, (double)numActive - numBig);
     k_solve_bins_fused<<<nbins, B2G_FUSED_THREADS, smem, A->stream>>>(
-        FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->conKeysSorted,
-        A->sortedList, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts);
+        FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->bucketStart,
+        A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts);
     ktime_end(A);
     A->launches++;
   }
@@ -798,6 +863,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     }
     colourFirst[B2G_MAX_COLOURS + 1] = acc;
     const int numOverflow = A->hCounts->colourCount[B2G_MAX_COLOURS];
+    if (numOverflow > 1)
+      LAUNCH(A, KC_COLOUR, numOverflow, k_order_overflow, 1, 256, colourFirst[B2G_MAX_COLOURS],
+             colourFirst[B2G_MAX_COLOURS + 1], A->sortedList, (int*)A->conKeys, C);
     LAUNCH(A, KC_INTEGRATE, nb, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island,
            A->islandAwake, A->vel, A->mass, A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y),
            A->dCounts, A->bodySlot, 1);
@@ -865,7 +933,7 @@ extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
   CK(cudaSetDevice(A->device));
   A->launchesAtStepStart = A->launches;
   const int nc = A->nContacts;
-  ContactBuf& C = A->cb[A->cur];
+  ContactBuf& C = A->cb[0];
   CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
   if (A->profiling) CK(cudaEventRecord(A->ev[0], A->stream));
   if (nc > 0) {
@@ -921,7 +989,7 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
     // hCounts was last read inside find_new_contacts, after every counter of this step was final
     stats->num_bodies = nb;
     stats->num_fixtures = A->nFixtures;
-    stats->num_contacts = A->nContacts;
+    stats->num_contacts = A->nAlive;
     stats->num_touching = A->hCounts->numTouching;
     stats->num_constraints = numActive;
     stats->num_colours = numColours;
@@ -1000,57 +1068,136 @@ extern "C" int b2g_download_fixture_aabbs(b2gArena* A, int32_t first, int32_t co
 
 extern "C" int b2g_contact_count(b2gArena* A, int32_t* out) {
   if (!A || !out) return B2G_ERR_INVALID;
-  *out = A->nContacts;
+  *out = A->nAlive;
   return B2G_OK;
 }
 
-__global__ void k_pack_manifolds(int first, int count, ContactBuf C, float4* out, int* fa, int* fb) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  int j = first + i;
-  out[4 * i] = C.m0[j];
-  out[4 * i + 1] = C.m1[j];
-  out[4 * i + 2] = C.m2[j];
-  out[4 * i + 3] = C.m3[j];
+// gathers the live contacts (slots are sparse and unordered) into dense arrays
+__global__ void k_pack_alive(int nSlots, ContactBuf C, int* counter, int* slots, unsigned long long* keys,
+                             float4* man, int* fa, int* fb, uint32_t* flags, float4* material, int* colour) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nSlots) return;
+  uint32_t f = C.flags[j];
+  if (!(f & B2G_CONTACT_ALIVE)) return;
+  int i = atomicAdd(counter, 1);
+  slots[i] = j;
+  keys[i] = C.key[j];
+  man[4 * i] = C.m0[j];
+  man[4 * i + 1] = C.m1[j];
+  man[4 * i + 2] = C.m2[j];
+  man[4 * i + 3] = C.m3[j];
   int2 fx = C.fix[j];
   fa[i] = fx.x;
   fb[i] = fx.y;
+  flags[i] = f & ~B2G_CONTACT_ALIVE;
+  material[i] = C.material[j];
+  colour[i] = C.colour[j];
 }
 
-extern "C" int b2g_download_contacts(b2gArena* A, int32_t first, int32_t count, const b2gContactArrays* d) {
-  if (!A || !d || first < 0 || count < 0 || first + count > A->nContacts) return B2G_ERR_INVALID;
-  if (count == 0) return B2G_OK;
-  CK(cudaSetDevice(A->device));
-  ContactBuf& C = A->cb[A->cur];
-  float4* tmp = nullptr;
-  int *ta = nullptr, *tb = nullptr;
-  CK(cudaMalloc(&tmp, (size_t)count * 64));
-  CK(cudaMalloc(&ta, (size_t)count * 4));
-  CK(cudaMalloc(&tb, (size_t)count * 4));
-  k_pack_manifolds<<<div_up(count, 256), 256, 0, A->stream>>>(first, count, C, tmp, ta, tb);
-  if (d->manifold) CK(cudaMemcpyAsync(d->manifold, tmp, (size_t)count * 64, cudaMemcpyDeviceToHost, A->stream));
-  if (d->fixture_a) CK(cudaMemcpyAsync(d->fixture_a, ta, (size_t)count * 4, cudaMemcpyDeviceToHost, A->stream));
-  if (d->fixture_b) CK(cudaMemcpyAsync(d->fixture_b, tb, (size_t)count * 4, cudaMemcpyDeviceToHost, A->stream));
-  DOWN(d->flags, C.flags, 1, uint32_t);
-  DOWN(d->material, (float*)C.material, 4, float);
-  DOWN(d->colour, C.colour, 1, int32_t);
+struct PackedContacts {
+  std::vector<int> slots, fa, fb, colour;
+  std::vector<unsigned long long> keys;
+  std::vector<uint32_t> flags;
+  std::vector<float> man, material;
+  std::vector<int> order;  // permutation that sorts by key: the order the C-ABI presents
+};
+
+// live contacts in ascending pair-key order (deterministic for the caller, whatever the slots)
+static int pack_contacts(b2gArena* A, PackedContacts& out) {
+  const int nSlots = A->nContacts, nAlive = A->nAlive;
+  out = PackedContacts();
+  if (nAlive <= 0) return B2G_OK;
+  ContactBuf& C = A->cb[0];
+  DevBuf dCnt, dSlots, dKeys, dMan, dFa, dFb, dFlags, dMat, dCol;
+  CK(dCnt.alloc(4));
+  CK(cudaMemsetAsync(dCnt.p, 0, 4, A->stream));
+  CK(dSlots.alloc((size_t)nAlive * 4));
+  CK(dKeys.alloc((size_t)nAlive * 8));
+  CK(dMan.alloc((size_t)nAlive * 64));
+  CK(dFa.alloc((size_t)nAlive * 4));
+  CK(dFb.alloc((size_t)nAlive * 4));
+  CK(dFlags.alloc((size_t)nAlive * 4));
+  CK(dMat.alloc((size_t)nAlive * 16));
+  CK(dCol.alloc((size_t)nAlive * 4));
+  k_pack_alive<<<div_up(nSlots, 256), 256, 0, A->stream>>>(nSlots, C, dCnt.as<int>(), dSlots.as<int>(),
+                                                           dKeys.as<unsigned long long>(), dMan.as<float4>(),
+                                                           dFa.as<int>(), dFb.as<int>(), dFlags.as<uint32_t>(),
+                                                           dMat.as<float4>(), dCol.as<int>());
+  out.slots.resize(nAlive);
+  out.keys.resize(nAlive);
+  out.man.resize((size_t)nAlive * 16);
+  out.fa.resize(nAlive);
+  out.fb.resize(nAlive);
+  out.flags.resize(nAlive);
+  out.material.resize((size_t)nAlive * 4);
+  out.colour.resize(nAlive);
+  int packed = 0;
+  CK(cudaMemcpyAsync(&packed, dCnt.p, 4, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.slots.data(), dSlots.p, (size_t)nAlive * 4, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.keys.data(), dKeys.p, (size_t)nAlive * 8, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.man.data(), dMan.p, (size_t)nAlive * 64, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.fa.data(), dFa.p, (size_t)nAlive * 4, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.fb.data(), dFb.p, (size_t)nAlive * 4, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.flags.data(), dFlags.p, (size_t)nAlive * 4, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.material.data(), dMat.p, (size_t)nAlive * 16, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(out.colour.data(), dCol.p, (size_t)nAlive * 4, cudaMemcpyDeviceToHost, A->stream));
   CK(cudaStreamSynchronize(A->stream));
-  cudaFree(tmp);
-  cudaFree(ta);
-  cudaFree(tb);
+  if (packed != nAlive) {
+    set_err("b2g_download_contacts", "internal: live-contact count mismatch");
+    return B2G_ERR_CUDA;
+  }
+  out.order.resize(nAlive);
+  for (int i = 0; i < nAlive; ++i) out.order[i] = i;
+  std::sort(out.order.begin(), out.order.end(),
+            [&](int x, int y) { return out.keys[x] < out.keys[y]; });
   return B2G_OK;
 }
 
+extern "C" int b2g_download_contacts(b2gArena* A, int32_t first, int32_t count, const b2gContactArrays* d) {
+  if (!A || !d || first < 0 || count < 0 || first + count > A->nAlive) return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
+  CK(cudaSetDevice(A->device));
+  PackedContacts pc;
+  int rc = pack_contacts(A, pc);
+  if (rc) return rc;
+  // remember which slot each presented index refers to (b2g_upload_contact_overrides)
+  free(A->downloadSlots);
+  A->downloadSlots = (int*)malloc(sizeof(int) * pc.order.size());
+  A->downloadCount = (int)pc.order.size();
+  for (size_t i = 0; i < pc.order.size(); ++i) A->downloadSlots[i] = pc.slots[pc.order[i]];
+  for (int i = 0; i < count; ++i) {
+    int k = pc.order[first + i];
+    if (d->fixture_a) d->fixture_a[i] = pc.fa[k];
+    if (d->fixture_b) d->fixture_b[i] = pc.fb[k];
+    if (d->flags) d->flags[i] = pc.flags[k];
+    if (d->manifold) memcpy(d->manifold + (size_t)i * 16, &pc.man[(size_t)k * 16], 64);
+    if (d->material) memcpy(d->material + (size_t)i * 4, &pc.material[(size_t)k * 4], 16);
+    if (d->colour) d->colour[i] = pc.colour[k];
+  }
+  return B2G_OK;
+}
+
+__global__ void k_scatter_overrides(int n, const int* __restrict__ slots, const uint32_t* __restrict__ flags,
+                                    const float4* __restrict__ material, ContactBuf C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int j = slots[i];
+  if (flags) C.flags[j] = (C.flags[j] & B2G_CONTACT_ALIVE) | (flags[i] & ~B2G_CONTACT_ALIVE);
+  if (material) C.material[j] = material[i];
+}
+
+// indices refer to the order of the LAST b2g_download_contacts
 extern "C" int b2g_upload_contact_overrides(b2gArena* A, int32_t first, int32_t count, const uint32_t* flags,
                                             const float* material) {
-  if (!A || first < 0 || count < 0 || first + count > A->nContacts) return B2G_ERR_INVALID;
+  if (!A || first < 0 || count < 0 || !A->downloadSlots || first + count > A->downloadCount) return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
   CK(cudaSetDevice(A->device));
-  ContactBuf& C = A->cb[A->cur];
-  if (flags)
-    CK(cudaMemcpyAsync(C.flags + first, flags, (size_t)count * 4, cudaMemcpyHostToDevice, A->stream));
-  if (material)
-    CK(cudaMemcpyAsync((float*)C.material + (size_t)first * 4, material, (size_t)count * 16, cudaMemcpyHostToDevice,
-                       A->stream));
+  DevBuf dS, dF, dM;
+  CK(dS.upload(A->downloadSlots + first, (size_t)count * 4));
+  if (flags) CK(dF.upload(flags, (size_t)count * 4));
+  if (material) CK(dM.upload(material, (size_t)count * 16));
+  k_scatter_overrides<<<div_up(count, 256), 256, 0, A->stream>>>(count, dS.as<int>(), flags ? dF.as<uint32_t>() : nullptr,
+                                                                material ? dM.as<float4>() : nullptr, A->cb[0]);
   CK(cudaStreamSynchronize(A->stream));
   return B2G_OK;
 }

@@ -20,12 +20,6 @@
 #define B2G_SLOT_NONE (-1)
 #define B2G_SLOT_BIG (-2)
 
-// bodies an island of `count` members occupies in fused slot space (big islands: none)
-struct FusedCountOp {
-  int thr;
-  __host__ __device__ int operator()(int count) const { return count > thr ? 0 : count; }
-};
-
 __global__ void k_island_count(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                const uint32_t* __restrict__ islandAwake, int* islandCount, StepCounts* counts) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -35,11 +29,29 @@ __global__ void k_island_count(int nb, const uint32_t* __restrict__ bflags, cons
   if (c > counts->maxIslandBodies) atomicMax(&counts->maxIslandBodies, c);
 }
 
-// slot of every simulated body in island-sorted order, and the slot range of every bin
+// Slot range of every tile-sized island: the island's root claims `count` consecutive slots from a
+// global cursor.  The order in which islands claim (hence which islands share a bin) varies from
+// run to run, but islands are independent and every per-island reduction is order-free, so the
+// simulation result does not depend on it.
+__global__ void k_island_alloc(int nb, const int* __restrict__ island, const int* __restrict__ islandCount,
+                               int* islandStart, int* binFirst, int* binEnd, int binSize, int bigThreshold,
+                               StepCounts* counts) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int cnt = islandCount[b];
+  if (cnt <= 0 || cnt > bigThreshold || island[b] != b) return;
+  int start = atomicAdd(&counts->slotCursor, cnt);
+  islandStart[b] = start;
+  int bin = start / binSize;
+  atomicMin(&binFirst[bin], start);
+  atomicMax(&binEnd[bin], start + cnt);
+}
+
+// slot of every simulated body inside its island's range
 __global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
                                const int* __restrict__ islandStart, int* islandCursor, int* bodySlot, int* slotBody,
-                               int* binFirst, int* binEnd, int binSize, int bigThreshold) {
+                               int bigThreshold) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   if (!body_simulated(bflags[b], island, islandAwake, b)) {
@@ -47,20 +59,13 @@ __global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, cons
     return;
   }
   int root = island[b];
-  int cnt = islandCount[root];
-  if (cnt > bigThreshold) {
+  if (islandCount[root] > bigThreshold) {
     bodySlot[b] = B2G_SLOT_BIG;
     return;
   }
-  int start = islandStart[root];
-  int slot = start + atomicAdd(&islandCursor[root], 1);
+  int slot = islandStart[root] + atomicAdd(&islandCursor[root], 1);
   bodySlot[b] = slot;
   slotBody[slot] = b;
-  if (b == root) {
-    int bin = start / binSize;
-    atomicMin(&binFirst[bin], start);
-    atomicMax(&binEnd[bin], start + cnt);
-  }
 }
 
 // active constraints and the bin each belongs to (-1 inactive, bigBin for oversize islands)
@@ -158,22 +163,81 @@ __global__ void k_colour2_commit(int nc, const int* __restrict__ cbin, ContactBu
   }
 }
 
-// sort key: bin (high) | colour (low); inactive contacts get the all-ones sentinel and sort last
-__global__ void k_constraint_keys(int nc, const int* __restrict__ cbin, ContactBuf C, unsigned int* keys, int* vals) {
+// Counting sort of the active constraints by bucket = bin * 32 + colour.  Order INSIDE a bucket is
+// whatever the atomics give: constraints of one colour never share a movable body, so any order
+// produces bit-identical results.
+__global__ void k_bucket_count(int nc, const int* __restrict__ cbin, ContactBuf C, int* bucketCount, int* rank) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   int bin = cbin[i];
-  keys[i] = bin < 0 ? 0xffffffffu : ((unsigned int)bin << B2G_COLOUR_BITS) | (unsigned int)C.colour[i];
-  vals[i] = i;
+  if (bin < 0) return;
+  rank[i] = atomicAdd(&bucketCount[(bin << B2G_COLOUR_BITS) | C.colour[i]], 1);
 }
 
-__device__ __forceinline__ int lower_bound_u32(const unsigned int* __restrict__ a, int n, unsigned int key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (a[mid] < key) lo = mid + 1; else hi = mid;
+// exclusive scan of the bucket counts by one block (buckets = bins x 32, a few thousand entries)
+__global__ void __launch_bounds__(1024) k_bucket_scan(int n, const int* __restrict__ bucketCount, int* bucketStart) {
+  __shared__ int warpSums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < n ? bucketCount[i] : 0;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warpSums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warpSums[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warpSums[lane] = w;
+    }
+    __syncthreads();
+    int prefix = carry + (wid > 0 ? warpSums[wid - 1] : 0) + x - v;
+    if (i < n) bucketStart[i] = prefix;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = prefix + v;
+    __syncthreads();
   }
-  return lo;
+  if (threadIdx.x == 0) bucketStart[n] = carry;
+}
+
+__global__ void k_bucket_scatter(int nc, const int* __restrict__ cbin, ContactBuf C, const int* __restrict__ bucketStart,
+                                 const int* __restrict__ rank, int* sortedList) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  int bin = cbin[i];
+  if (bin < 0) return;
+  sortedList[bucketStart[(bin << B2G_COLOUR_BITS) | C.colour[i]] + rank[i]] = i;
+}
+
+// The overflow bucket is the only place where constraint ORDER matters (one thread, Gauss-Seidel in
+// list order), and the counting sort above leaves bucket contents in arbitrary order: rank-sort it
+// by pair key so runs stay bit-reproducible.  Block-wide, O(n^2) key compares, n = overflow size.
+__device__ __forceinline__ void order_bucket_by_key(int o0, int o1, int* sortedList, int* scratch, const ContactBuf& C) {
+  const int n = o1 - o0;
+  if (n <= 1) return;  // block-uniform
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    int i = sortedList[o0 + t];
+    unsigned long long ki = C.key[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += C.key[sortedList[o0 + j]] < ki ? 1 : 0;
+    scratch[o0 + rank] = i;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n; t += blockDim.x) sortedList[o0 + t] = scratch[o0 + t];
+  __syncthreads();
+}
+
+__global__ void k_order_overflow(int o0, int o1, int* sortedList, int* scratch, ContactBuf C) {
+  order_bucket_by_key(o0, o1, sortedList, scratch, C);
 }
 
 struct FusedParams {
@@ -183,7 +247,9 @@ struct FusedParams {
   float2 gravity;
   int velIters, posIters, warmStarting, allowSleep, clearForces;
   int tileCap;         // bodies the shared-memory tile can hold
+  int conCap;          // constraints whose 13 planes fit in shared memory next to the tile
 };
+#define B2G_PLANES 13
 
 // dynamic shared memory layout for a tile of `cap` bodies
 struct FusedTile {
@@ -194,14 +260,15 @@ struct FusedTile {
   unsigned int* pen;     // per island head: max penetration of the current position iteration
   unsigned int* sleepMin;  // per island head: float bits of min sleep time
   int* done;        // per island head: position solver converged
-  __host__ __device__ static size_t bytes(int cap) { return (size_t)cap * (16 + 16 + 4 + 4 + 4 + 4 + 4); }
+  // rounded up so the constraint planes that follow stay 16-byte aligned
+  __host__ __device__ static size_t bytes(int cap) { return (((size_t)cap * (16 + 16 + 4 + 4 + 4 + 4 + 4)) + 15) & ~(size_t)15; }
 };
 
 __global__ void __launch_bounds__(B2G_FUSED_THREADS)
 k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* __restrict__ binEnd,
                    const int* __restrict__ slotBody, const int* __restrict__ bodySlot,
                    const int* __restrict__ island, const int* __restrict__ islandStart,
-                   const unsigned int* __restrict__ keysSorted, const int* __restrict__ sortedList, ContactBuf C,
+                   const int* __restrict__ bucketStart, int* sortedList, int* orderScratch, ContactBuf C,
                    const float* __restrict__ fRadius, SolverPlanes S, uint32_t* bflags, float4* gpos, float4* gvel,
                    float4* gxf, float4* gforce, const float4* __restrict__ gmass, const float4* __restrict__ gcenter,
                    StepCounts* counts) {
@@ -225,12 +292,8 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
   }
   __shared__ int cstart[B2G_MAX_COLOURS + 3];
 
-  // constraint ranges of this bin, one per colour (+ overflow), by binary search in the sorted keys
-  if (tid <= B2G_MAX_COLOURS + 1) {
-    unsigned int key = tid <= B2G_MAX_COLOURS ? (((unsigned int)bin << B2G_COLOUR_BITS) | (unsigned int)tid)
-                                              : ((unsigned int)(bin + 1) << B2G_COLOUR_BITS);
-    cstart[tid] = lower_bound_u32(keysSorted, P.nc, key);
-  }
+  // constraint ranges of this bin, one per colour (+ overflow), from the bucket table
+  if (tid <= B2G_MAX_COLOURS + 1) cstart[tid] = P.nc > 0 ? bucketStart[(bin << B2G_COLOUR_BITS) + tid] : 0;
 
   // ---- phase 0: load the tile, integrate velocities (b2_island.cpp:257-293) --------------------
   const float h = P.h;
@@ -261,9 +324,30 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     T.pos[l] = gpos[b];
   }
   __syncthreads();
+  order_bucket_by_key(cstart[B2G_MAX_COLOURS], cstart[B2G_MAX_COLOURS + 1], sortedList, orderScratch, C);
   const int cAll0 = cstart[0], cAll1 = cstart[B2G_MAX_COLOURS + 1];
   const TileBodies velAcc{T.vel, gvel};
   const TileBodies posAcc{T.pos, gpos};
+  // Constraint planes: in shared memory when the whole bin fits (they are re-read by every one of
+  // the 1 + velIters + posIters passes, each on the critical path between two barriers), else in
+  // HBM/L2.  Slot s of a plane is addressed as plane[s] either way (shared base is pre-offset).
+  if (cAll1 - cAll0 <= P.conCap) {
+    float4* base = (float4*)(smemRaw + FusedTile::bytes(P.tileCap));
+    const ptrdiff_t cc = P.conCap;
+    S.nf = base + 0 * cc - cAll0;
+    S.r1 = base + 1 * cc - cAll0;
+    S.r2 = base + 2 * cc - cAll0;
+    S.m1 = base + 3 * cc - cAll0;
+    S.m2 = base + 4 * cc - cAll0;
+    S.kk = base + 5 * cc - cAll0;
+    S.mass = base + 6 * cc - cAll0;
+    S.idx = (int4*)(base + 7 * cc) - cAll0;
+    S.imp = base + 8 * cc - cAll0;
+    S.pn = base + 9 * cc - cAll0;
+    S.pp = base + 10 * cc - cAll0;
+    S.pc = base + 11 * cc - cAll0;
+    S.pr = base + 12 * cc - cAll0;
+  }
 
   // ---- phase 1: prepare every constraint of the bin --------------------------------------------
   for (int s = cAll0 + tid; s < cAll1; s += nt) {

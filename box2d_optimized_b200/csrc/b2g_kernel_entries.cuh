@@ -4,34 +4,6 @@
 // the oracle with the oracle's own ordered inputs.
 #pragma once
 
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-  template <typename T>
-  T* as() {
-    return (T*)p;
-  }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-  cudaError_t upload(const void* src, size_t bytes) {
-    cudaError_t e = alloc(bytes);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
-  }
-};
-
-static int use_device(int device) {
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    set_err("b2cuda", "no CUDA device: this library has no CPU fallback");
-    return B2G_ERR_NO_DEVICE;
-  }
-  if (device < 0 || device >= ndev) return B2G_ERR_INVALID;
-  CK(cudaSetDevice(device));
-  return B2G_OK;
-}
-
 __global__ void k_entry_aabbs(int n, const int* __restrict__ type, const int* __restrict__ off,
                               const float4* __restrict__ shapes, const float4* __restrict__ xf, float4* aabb) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,15 +122,12 @@ extern "C" int b2g_find_pairs(int32_t device, int32_t n, const float* aabb, cons
     *num_pairs = A->hCounts->numPairs;
   }
   if (!rc) {
-    cudaStreamSynchronize(A->stream);
-    int np = A->nContacts;
-    std::vector<unsigned long long> keys(np);
-    if (np > 0 && cudaMemcpy(keys.data(), A->cb[A->cur].key, (size_t)np * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
-      rc = B2G_ERR_CUDA;
-    unsigned long long maskBits = (1ull << A->fixBits) - 1ull;
-    for (int k = 0; k < np && !rc; ++k) {
-      pairs[2 * k] = (int)((keys[k] >> A->fixBits) & maskBits);
-      pairs[2 * k + 1] = (int)(keys[k] & maskBits);
+    PackedContacts pc;
+    rc = pack_contacts(A, pc);
+    for (size_t k = 0; k < pc.order.size() && !rc; ++k) {
+      unsigned long long key = pc.keys[pc.order[k]];
+      pairs[2 * k] = (int)(key >> 32);
+      pairs[2 * k + 1] = (int)(key & 0xffffffffull);
     }
   }
   b2g_arena_destroy(A);

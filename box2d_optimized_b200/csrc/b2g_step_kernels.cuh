@@ -49,11 +49,12 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
               int2* beginEvents, int2* endEvents, int eventCap) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
+  uint32_t flags = C.flags[i];
+  if (!(flags & B2G_CONTACT_ALIVE)) return;  // free slot
   int2 bd = C.body[i];
   uint32_t fa = bflags[bd.x], fb = bflags[bd.y];
   bool activeA = (fa & B2G_BODY_AWAKE) && B2G_BODY_TYPE(fa) != B2G_STATIC;
   bool activeB = (fb & B2G_BODY_AWAKE) && B2G_BODY_TYPE(fb) != B2G_STATIC;
-  uint32_t flags = C.flags[i];
   if (!(activeA || activeB)) {
     if (flags & B2G_CONTACT_TOUCHING) {
       auto g = cg::coalesced_threads();
@@ -302,9 +303,17 @@ __global__ void k_colour_begin(const int* __restrict__ numActivePtr, const int* 
   }
 }
 
+// Unique per constraint (a bijection of the 56-bit pair key) so two constraints on one body can
+// never tie, and a function of the pair alone so colours do not depend on contact slot numbers.
 __device__ __forceinline__ unsigned long long colour_priority(int round, int s, unsigned long long key) {
-  unsigned int h = hash32((unsigned int)(key ^ (key >> 29))) & 0xffffffu;
-  return ((unsigned long long)(round + 1) << 56) | ((unsigned long long)h << 32) | (unsigned int)s;
+  (void)s;
+  const unsigned long long M56 = (1ull << 56) - 1ull;
+  unsigned long long k = ((key >> 32) << 28 | (key & 0xfffffffull)) & M56;  // fixture indices < 2^28
+  k = (k * 0x9e3779b97f4a7c15ull) & M56;  // odd multiplier: bijective mod 2^56
+  k ^= k >> 29;                          // xor-shift: bijective
+  k = (k * 0xbf58476d1ce4e5b9ull) & M56;
+  k ^= k >> 31;
+  return ((unsigned long long)(round + 1) << 56) | k;
 }
 
 __global__ void k_colour_propose(const int* __restrict__ numActivePtr, const int* __restrict__ activeList, ContactBuf C,
@@ -356,6 +365,11 @@ __global__ void k_colour_keys(const int* __restrict__ numActivePtr, const int* _
   int n = *numActivePtr;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
     colourKey[s] = (uint8_t)C.colour[activeList[s]];
+}
+
+__global__ void k_gather_keys(int n, const int* __restrict__ list, ContactBuf C, unsigned long long* keys) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) keys[s] = C.key[list[s]];
 }
 
 // self-check used by the tests: counts pairs of same-colour constraints that share a movable body

@@ -50,6 +50,7 @@ extern "C" {
 #define B2G_FIX_DEAD 0x200u /* destroyed fixture: ignored by the broadphase */
 
 /* ---- contact flags (include/box2d/b2_contact.h:155-173) */
+#define B2G_CONTACT_ALIVE 0x0001u /* device-internal: the slot holds a live contact */
 #define B2G_CONTACT_TOUCHING 0x0008u
 #define B2G_CONTACT_ENABLED 0x0010u
 
