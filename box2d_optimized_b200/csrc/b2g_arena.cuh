@@ -131,11 +131,10 @@ struct b2gArena {
   float4* leafBox;
   int4* leafInfo;
   unsigned long long* leafKey;  // (AABB size bits, sorted position): who reports a pair
-  ulonglong2* nodeMaxKey;       // per internal node: max leafKey under the left / right child
   int* worldFirst;
   int* worldLast;
   int4* nodeRange;  // first, split, last, parent
-  float4 *nodeBoxL, *nodeBoxR;
+  struct BvhNode* bvhNodes;     // 64-byte traversal records, one per internal node
   int* leafParent;
   int* nodeVisit;
   unsigned long long *pairKeys;  // new pairs (no live contact yet) reported by the traversal

@@ -132,7 +132,7 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
                               const int* __restrict__ fBody, const uint32_t* __restrict__ fTypeFlags,
                               const uint2* __restrict__ fFilter, const uint32_t* __restrict__ bflags, float4* leafBox,
                               int4* leafInfo, unsigned long long* leafKey, int* worldFirst, int* worldLast,
-                              int numWorlds) {
+                              int numWorlds, int* nodeVisit) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nf) return;
   int f = leafFixtureSorted[p];
@@ -145,6 +145,7 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
   unsigned int z = (tf & 3u) | ((tf & B2G_FIX_SENSOR) ? 4u : 0u) | (B2G_BODY_TYPE(bf) == B2G_DYNAMIC ? 8u : 0u) |
                    (dead ? 16u : 0u) | ((fl.y & 0xffffu) << 16);
   leafInfo[p] = make_int4(f, b, (int)z, (int)fl.x);
+  nodeVisit[p] = 0;
   // reporting order: the leaf with the SMALLER (size, position) key reports the pair, so a huge
   // AABB (ground edge, container wall) never walks the tree for its thousands of partners —
   // they each find it instead.  size = half perimeter as non-negative float bits (monotone).
@@ -167,9 +168,11 @@ __global__ void __launch_bounds__(256)
 k_refresh_leaves(int nf, const int* __restrict__ leafFixtureSorted, const int* __restrict__ fBody,
                  const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
                  const float4* __restrict__ shapes, const uint32_t* __restrict__ bflags,
-                 const float4* __restrict__ xf, float4* fAabb, float4* leafBox, unsigned long long* leafKey) {
+                 const float4* __restrict__ xf, float4* fAabb, float4* leafBox, unsigned long long* leafKey,
+                 int* nodeVisit) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nf) return;
+  nodeVisit[p] = 0;
   int f = leafFixtureSorted[p];
   uint32_t tf = fTypeFlags[f];
   if (tf & B2G_FIX_DEAD) return;  // keeps the empty box written at the last rebuild
@@ -223,9 +226,17 @@ __global__ void k_lbvh_build(int n, const unsigned long long* __restrict__ keys,
 
 // bottom-up refit: the second thread to reach a node carries the union upward; child boxes are
 // stored IN the parent so the traversal tests both children with one node fetch
+// Traversal record of an internal node: both child boxes, both child max-keys and the leaf range
+// in ONE 64-byte line, so a node visit is a single L2 round trip.
+struct __align__(16) BvhNode {
+  float4 boxL, boxR;
+  unsigned long long maxL, maxR;
+  int first, split, last, pad;
+};
+
 __global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const unsigned long long* __restrict__ leafKey,
-                             const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, float4* nodeBoxL,
-                             float4* nodeBoxR, ulonglong2* nodeMaxKey, int* nodeVisit) {
+                             const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
+                             int* nodeVisit) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   float4 box = leafBox[p];
@@ -235,18 +246,25 @@ __global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const un
   while (parent >= 0) {
     int4 nr = nodeRange[parent];
     bool isLeft = (idx == nr.y);
+    BvhNode* nd = &nodes[parent];
     if (isLeft) {
-      nodeBoxL[parent] = box;
-      nodeMaxKey[parent].x = key;
+      nd->boxL = box;
+      nd->maxL = key;
+      nd->first = nr.x;   // range fields are written by whoever passes; both writers store the same values
+      nd->split = nr.y;
+      nd->last = nr.z;
     } else {
-      nodeBoxR[parent] = box;
-      nodeMaxKey[parent].y = key;
+      nd->boxR = box;
+      nd->maxR = key;
+      nd->first = nr.x;
+      nd->split = nr.y;
+      nd->last = nr.z;
     }
     __threadfence();
     int old = atomicAdd(&nodeVisit[parent], 1);
     if (old == 0) return;
-    float4 sib = isLeft ? __ldcg(&nodeBoxR[parent]) : __ldcg(&nodeBoxL[parent]);
-    unsigned long long sibKey = isLeft ? __ldcg(&nodeMaxKey[parent].y) : __ldcg(&nodeMaxKey[parent].x);
+    float4 sib = isLeft ? __ldcg(&nd->boxR) : __ldcg(&nd->boxL);
+    unsigned long long sibKey = isLeft ? __ldcg(&nd->maxR) : __ldcg(&nd->maxL);
     box = make_float4(fminf(box.x, sib.x), fminf(box.y, sib.y), fmaxf(box.z, sib.z), fmaxf(box.w, sib.w));
     key = key > sibKey ? key : sibKey;
     idx = parent;
@@ -363,9 +381,8 @@ __device__ __forceinline__ void emit_pair(int4 a, int4 b, const ContactHash& H, 
 // never leaves the query's own world segment [ws, we] of the sorted order.
 __global__ void __launch_bounds__(128)
 k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo,
-              const unsigned long long* __restrict__ leafKey, const int4* __restrict__ nodeRange,
-              const float4* __restrict__ nodeBoxL, const float4* __restrict__ nodeBoxR,
-              const ulonglong2* __restrict__ nodeMaxKey, const int* __restrict__ worldFirst,
+              const unsigned long long* __restrict__ leafKey, const BvhNode* __restrict__ nodes,
+              const int* __restrict__ worldFirst,
               const int* __restrict__ worldLast, const unsigned long long* __restrict__ keysSorted, int numWorlds,
               ContactHash H, uint8_t* persist, unsigned long long* newPairs, int capacity, StepCounts* counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,15 +402,18 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
   stack[sp++] = 0;
   while (sp > 0) {
     int node = stack[--sp];
-    int4 nr = nodeRange[node];
-    ulonglong2 mk = nodeMaxKey[node];
+    const float4* q = reinterpret_cast<const float4*>(&nodes[node]);
+    float4 bl = __ldg(q), br = __ldg(q + 1), mk4 = __ldg(q + 2);
+    int4 nr = __ldg(reinterpret_cast<const int4*>(q + 3));
+    unsigned long long mkL = ((unsigned long long)__float_as_uint(mk4.y) << 32) | __float_as_uint(mk4.x);
+    unsigned long long mkR = ((unsigned long long)__float_as_uint(mk4.w) << 32) | __float_as_uint(mk4.z);
     // left child covers [first, split]
-    if (mk.x > myKey && nr.x <= we && nr.y >= ws && aabb_overlap(qbox, nodeBoxL[node])) {
+    if (mkL > myKey && nr.x <= we && nr.y >= ws && aabb_overlap(qbox, bl)) {
       if (nr.x == nr.y) emit_pair(me, leafInfo[nr.y], H, persist, newPairs, capacity, counts);
       else stack[sp++] = nr.y;
     }
     // right child covers [split+1, last]
-    if (mk.y > myKey && nr.y + 1 <= we && nr.z >= ws && aabb_overlap(qbox, nodeBoxR[node])) {
+    if (mkR > myKey && nr.y + 1 <= we && nr.z >= ws && aabb_overlap(qbox, br)) {
       if (nr.y + 1 == nr.z) emit_pair(me, leafInfo[nr.z], H, persist, newPairs, capacity, counts);
       else stack[sp++] = nr.y + 1;
     }

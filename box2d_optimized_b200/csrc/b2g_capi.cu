@@ -252,12 +252,10 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->leafBox, nf));
   CK(dalloc(&A->leafInfo, nf));
   CK(dalloc(&A->leafKey, nf));
-  CK(dalloc(&A->nodeMaxKey, nf));
   CK(dalloc(&A->worldFirst, A->numWorlds + 1));
   CK(dalloc(&A->worldLast, A->numWorlds + 1));
   CK(dalloc(&A->nodeRange, nf));
-  CK(dalloc(&A->nodeBoxL, nf));
-  CK(dalloc(&A->nodeBoxR, nf));
+  CK(dalloc(&A->bvhNodes, nf));
   CK(dalloc(&A->leafParent, nf));
   CK(dalloc(&A->nodeVisit, nf));
   CK(dalloc(&A->pairKeys, nc));
@@ -325,7 +323,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
                   A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
-                  A->leafKey, A->nodeMaxKey, A->worldFirst, A->worldLast, A->nodeRange, A->nodeBoxL, A->nodeBoxR, A->leafParent,
+                  A->leafKey, A->worldFirst, A->worldLast, A->nodeRange, A->bvhNodes, A->leafParent,
                   A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
                   A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
@@ -469,7 +467,6 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
   const int nSlots = A->nContacts;  // slot high-water mark
   int nNew = 0;
   if (nf > 0) {
-    CK(cudaMemsetAsync(&A->dCounts->numPairs, 0, sizeof(int), A->stream));
     // The LBVH topology is rebuilt (Morton sort + Karras build) when fixtures were added / edited
     // or every B2G_BVH_REBUILD_PERIOD steps; in between only the boxes are refit.  The reported
     // pair set is exact either way — only traversal cost depends on tree quality.
@@ -489,7 +486,7 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
                                                32 + (A->numWorlds > 1 ? A->worldBits : 0), A->stream)));
       LAUNCH(A, KC_BP_BUILD, nf, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted,
              A->fAabb, A->fBody, A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->leafKey,
-             A->worldFirst, A->worldLast, A->numWorlds);
+             A->worldFirst, A->worldLast, A->numWorlds, A->nodeVisit);
       CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
       if (nf > 1)
         LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange,
@@ -498,15 +495,13 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
       A->bvhAge = 0;
     } else {
       LAUNCH(A, KC_BP_BUILD, nf, k_refresh_leaves, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->fBody,
-             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey);
+             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey, A->nodeVisit);
       A->bvhAge++;
     }
-    CK(cudaMemsetAsync(A->nodeVisit, 0, sizeof(int) * nf, A->stream));
     if (nf > 1) {
       LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent, A->nodeRange,
-             A->nodeBoxL, A->nodeBoxR, A->nodeMaxKey, A->nodeVisit);
-      LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->nodeRange, A->nodeBoxL,
-             A->nodeBoxR, A->nodeMaxKey, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash,
+             A->bvhNodes, A->nodeVisit);
+      LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->bvhNodes, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash,
              A->persist, A->pairKeys, A->capContacts, A->dCounts);
     }
   }
@@ -580,10 +575,11 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     // ---- islands ---------------------------------------------------------------------
     LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent, A->islandAwake,
            A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest,
-           A->islandCount, A->islandCursor);
+           A->islandCount, A->islandCursor, A->binFirst, A->binEnd, 0, A->bucketCount, 0);
     if (nc > 0) LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
     if (nj > 0) LAUNCH(A, KC_ISLANDS, nj, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
-    LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island, A->islandAwake);
+    LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island, A->islandAwake,
+           A->islandCount, A->dCounts);
     LAUNCH(A, KC_INTEGRATE, nb, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->vel, A->mass,
            A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y), A->dCounts, nullptr, 0);
 
@@ -760,20 +756,17 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   if (conCap < 0) conCap = 0;
   const size_t smem = tileBytes + (size_t)conCap * B2G_PLANES * 16;
 
-  CK(cudaMemsetAsync(A->binFirst, 0x7f, sizeof(int) * (nbins + 1), A->stream));
-  CK(cudaMemsetAsync(A->binEnd, 0, sizeof(int) * (nbins + 1), A->stream));
+  const int nbuckets = (nbins + 1) << B2G_COLOUR_BITS;
   LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent,
          A->islandAwake, A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask,
-         A->bodyBest, A->islandCount, A->islandCursor);
+         A->bodyBest, A->islandCount, A->islandCursor, A->binFirst, A->binEnd, nbins + 1, A->bucketCount, nbuckets);
   if (nc > 0)
     LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
   if (nj > 0)
     LAUNCH(A, KC_ISLANDS, nj, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
   LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island,
-         A->islandAwake);
-  LAUNCH(A, KC_ISLANDS, nb, k_island_count, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
-         A->islandCount, A->dCounts);
-  LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandCount, A->islandStart,
+         A->islandAwake, A->islandCount, A->dCounts);
+  LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandAwake, A->islandCount, A->islandStart,
          A->binFirst, A->binEnd, binSize, bigThr, A->dCounts);
   LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
          A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr);
@@ -781,15 +774,15 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   int numActive = 0, numBig = 0, rounds = 0;
   if (nc > 0) {
     LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->bflags, A->island,
-           A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->recolour, binSize, bigThr, bigBin, A->dCounts);
+           A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->recolour, binSize, bigThr, bigBin, A->dCounts,
+           A->mass, A->colourMask);
     A->recolour = 0;
     int grid = div_up(nc, 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    LAUNCH(A, KC_COLOUR, nc, k_colour2_begin, grid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->dCounts, bigBin);
     int round = 0;
     int batch = A->roundsHint;
     while (true) {
-      CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
+      if (round > 0) CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
       for (int r = 0; r < batch; ++r, ++round) {
         LAUNCH(A, KC_COLOUR, nc, k_colour2_propose, grid, 256, nc, A->cbin, C, A->mass, A->bodyBest, round);
         LAUNCH(A, KC_COLOUR, nc, k_colour2_commit, grid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->bodyBest,
@@ -814,8 +807,6 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     out.numColours = A->hCounts->numColours;
     out.numOverflow = A->hCounts->numOverflow;
     if (numActive > 0) {
-      const int nbuckets = (nbins + 1) << B2G_COLOUR_BITS;
-      CK(cudaMemsetAsync(A->bucketCount, 0, sizeof(int) * nbuckets, A->stream));
       LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
       LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
       LAUNCH(A, KC_COLOUR, nc, k_bucket_scatter, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketStart, A->conVals,

@@ -20,26 +20,17 @@
 #define B2G_SLOT_NONE (-1)
 #define B2G_SLOT_BIG (-2)
 
-__global__ void k_island_count(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
-                               const uint32_t* __restrict__ islandAwake, int* islandCount, StepCounts* counts) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  if (!body_simulated(bflags[b], island, islandAwake, b)) return;
-  int c = atomicAdd(&islandCount[island[b]], 1) + 1;
-  if (c > counts->maxIslandBodies) atomicMax(&counts->maxIslandBodies, c);
-}
-
 // Slot range of every tile-sized island: the island's root claims `count` consecutive slots from a
 // global cursor.  The order in which islands claim (hence which islands share a bin) varies from
 // run to run, but islands are independent and every per-island reduction is order-free, so the
 // simulation result does not depend on it.
-__global__ void k_island_alloc(int nb, const int* __restrict__ island, const int* __restrict__ islandCount,
-                               int* islandStart, int* binFirst, int* binEnd, int binSize, int bigThreshold,
-                               StepCounts* counts) {
+__global__ void k_island_alloc(int nb, const int* __restrict__ island, const uint32_t* __restrict__ islandAwake,
+                               const int* __restrict__ islandCount, int* islandStart, int* binFirst, int* binEnd,
+                               int binSize, int bigThreshold, StepCounts* counts) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   int cnt = islandCount[b];
-  if (cnt <= 0 || cnt > bigThreshold || island[b] != b) return;
+  if (cnt <= 0 || cnt > bigThreshold || island[b] != b || !islandAwake[b]) return;
   int start = atomicAdd(&counts->slotCursor, cnt);
   islandStart[b] = start;
   int bin = start / binSize;
@@ -73,7 +64,8 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
                                    const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                    const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
                                    const int* __restrict__ islandStart, int* cbin, int dropColours, int binSize,
-                                   int bigThreshold, int bigBin, StepCounts* counts) {
+                                   int bigThreshold, int bigBin, StepCounts* counts, const float4* __restrict__ mass,
+                                   unsigned long long* colourMask) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   uint32_t flags = C.flags[i];
@@ -96,28 +88,19 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
     if (bin == bigBin) atomicAdd(&counts->numBig, 1);
   }
   cbin[i] = bin;
-  if (!active || dropColours) C.colour[i] = -1;
-}
-
-// ---- colouring over the contact array directly (no compacted list) ------------------------------
-__global__ void k_colour2_begin(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
-                                unsigned long long* colourMask, StepCounts* counts, int bigBin) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
-    int bin = cbin[i];
-    if (bin < 0) continue;
-    int c = C.colour[i];
-    if (c >= B2G_MAX_COLOURS) {
-      C.colour[i] = -1;  // overflow constraints retry every step
-      c = -1;
-    }
-    if (c >= 0) {
-      int2 bd = C.body[i];
-      unsigned long long bit = 1ull << c;
-      if (body_movable(mass[bd.x])) atomicOr(&colourMask[bd.x], bit);
-      if (body_movable(mass[bd.y])) atomicOr(&colourMask[bd.y], bit);
-      if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
-      if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
-    }
+  int c = C.colour[i];
+  if (!active || dropColours || c >= B2G_MAX_COLOURS) {
+    // inactive contacts lose their colour; overflow constraints retry every step
+    if (c != -1) C.colour[i] = -1;
+    c = -1;
+  }
+  // colours persist from step to step: publish the ones still in use (was k_colour_begin)
+  if (c >= 0) {
+    unsigned long long bit = 1ull << c;
+    if (body_movable(mass[bd.x])) atomicOr(&colourMask[bd.x], bit);
+    if (body_movable(mass[bd.y])) atomicOr(&colourMask[bd.y], bit);
+    if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
+    if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
   }
 }
 

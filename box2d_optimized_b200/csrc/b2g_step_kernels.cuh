@@ -127,8 +127,15 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
 __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islandParent, uint32_t* islandAwake,
                              uint32_t* islandMinSleep, uint32_t* islandPen, int penStride, int posIters,
                              unsigned long long* colourMask, unsigned long long* bodyBest, int* islandCount,
-                             int* islandCursor) {
+                             int* islandCursor, int* binFirst, int* binEnd, int nbinsPlus, int* bucketCount,
+                             int nbuckets) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // per-step tables of the fused solver, cleared here instead of by separate memsets
+  for (int k = b; k < nbinsPlus; k += gridDim.x * blockDim.x) {
+    binFirst[k] = 0x7f7f7f7f;
+    binEnd[k] = 0;
+  }
+  for (int k = b; k < nbuckets; k += gridDim.x * blockDim.x) bucketCount[k] = 0;
   if (b >= nb) return;
   islandCount[b] = 0;
   islandCursor[b] = 0;
@@ -203,13 +210,18 @@ __global__ void k_island_union_joints(int nj, const int2* __restrict__ jBodies, 
 // race with other threads' finds (a late path-halving store can overwrite a finished entry with
 // a non-root ancestor), which made island ids — and therefore the whole step — nondeterministic.
 __global__ void k_island_flatten(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ parent,
-                                 int* island, uint32_t* islandAwake) {
+                                 int* island, uint32_t* islandAwake, int* islandCount, StepCounts* counts) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   int root = b;
   for (int p = parent[root]; p != root; p = parent[root]) root = p;
   island[b] = root;
   uint32_t f = bflags[b];
+  if ((f & B2G_BODY_ENABLED) && B2G_BODY_TYPE(f) != B2G_STATIC) {
+    // island size = its non-static members (all of them are simulated once the island is awake)
+    int c = atomicAdd(&islandCount[root], 1) + 1;
+    if (c > counts->maxIslandBodies) atomicMax(&counts->maxIslandBodies, c);
+  }
   // an island is simulated when any member could seed it (b2_world.cpp:526-545)
   if ((f & B2G_BODY_AWAKE) && (f & B2G_BODY_ENABLED) && B2G_BODY_TYPE(f) != B2G_STATIC) islandAwake[root] = 1u;
 }
