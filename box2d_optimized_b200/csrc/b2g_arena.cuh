@@ -94,7 +94,9 @@ struct b2gArena {
   int *islandCount, *islandStart, *islandCursor, *bodySlot, *slotBody, *binFirst, *binEnd, *cbin, *bucketCount, *bucketStart;
   unsigned int *conKeys, *conKeysSorted;
   int *conVals;
-  int nbinsMax, bigMode, lastMaxIsland;
+  int nbinsMax, bigMode, lastMaxIsland, lastNumBig;
+  int islandsValid;   // island[] of the previous step may seed this step's union-find
+  uint8_t* islandDirty;  // per island root: an edge was removed since the labels were computed
   size_t fusedSmemSet;
 
   // fixtures + shapes

@@ -145,7 +145,7 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
   unsigned int z = (tf & 3u) | ((tf & B2G_FIX_SENSOR) ? 4u : 0u) | (B2G_BODY_TYPE(bf) == B2G_DYNAMIC ? 8u : 0u) |
                    (dead ? 16u : 0u) | ((fl.y & 0xffffu) << 16);
   leafInfo[p] = make_int4(f, b, (int)z, (int)fl.x);
-  nodeVisit[p] = 0;
+  nodeVisit[p] = 0;  // new topology: arrival counters restart
   // reporting order: the leaf with the SMALLER (size, position) key reports the pair, so a huge
   // AABB (ground edge, container wall) never walks the tree for its thousands of partners —
   // they each find it instead.  size = half perimeter as non-negative float bits (monotone).
@@ -158,32 +158,6 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
     bool firstOfWorld = (p == 0) || ((unsigned int)(keysSorted[p - 1] >> 32) != w);
     if (lastOfWorld && w < (unsigned int)numWorlds) worldLast[w] = p;
     if (firstOfWorld && w < (unsigned int)numWorlds) worldFirst[w] = p;
-  }
-}
-
-// Refit-only steps: the tree TOPOLOGY of the last rebuild is kept (any valid BVH reports the same
-// exact pair set); every leaf gets its fresh tight AABB and size key.  Replaces k_update_aabbs +
-// k_morton_keys + sort + k_leaf_gather + k_lbvh_build on the steps between rebuilds.
-__global__ void __launch_bounds__(256)
-k_refresh_leaves(int nf, const int* __restrict__ leafFixtureSorted, const int* __restrict__ fBody,
-                 const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
-                 const float4* __restrict__ shapes, const uint32_t* __restrict__ bflags,
-                 const float4* __restrict__ xf, float4* fAabb, float4* leafBox, unsigned long long* leafKey,
-                 int* nodeVisit) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nf) return;
-  nodeVisit[p] = 0;
-  int f = leafFixtureSorted[p];
-  uint32_t tf = fTypeFlags[f];
-  if (tf & B2G_FIX_DEAD) return;  // keeps the empty box written at the last rebuild
-  int b = fBody[f];
-  float4 box;
-  if (B2G_BODY_TYPE(bflags[b]) != B2G_STATIC) {
-    box = shape_aabb(shapes, (int)(tf & 3u), fShapeOff[f], xf_from4(xf[b]));
-    fAabb[f] = box;
-    leafBox[p] = box;
-    float size = (box.z - box.x) + (box.w - box.y);
-    leafKey[p] = ((unsigned long long)__float_as_uint(fmaxf(size, 0.0f)) << 32) | (unsigned int)p;
   }
 }
 
@@ -234,13 +208,11 @@ struct __align__(16) BvhNode {
   int first, split, last, pad;
 };
 
-__global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const unsigned long long* __restrict__ leafKey,
-                             const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
-                             int* nodeVisit) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  float4 box = leafBox[p];
-  unsigned long long key = leafKey[p];
+// Bottom-up refit walk of one leaf.  The second thread to reach a node carries the union upward;
+// arrival is detected by the PARITY of a never-reset counter (every node receives exactly two
+// arrivals per refit), so no per-step clearing pass is needed while the topology is unchanged.
+__device__ __forceinline__ void refit_walk(int p, float4 box, unsigned long long key, const int* __restrict__ leafParent,
+                                           const int4* __restrict__ nodeRange, BvhNode* nodes, int* nodeVisit) {
   int idx = p;
   int parent = leafParent[p];
   while (parent >= 0) {
@@ -250,19 +222,16 @@ __global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const un
     if (isLeft) {
       nd->boxL = box;
       nd->maxL = key;
-      nd->first = nr.x;   // range fields are written by whoever passes; both writers store the same values
-      nd->split = nr.y;
-      nd->last = nr.z;
     } else {
       nd->boxR = box;
       nd->maxR = key;
-      nd->first = nr.x;
-      nd->split = nr.y;
-      nd->last = nr.z;
     }
+    nd->first = nr.x;  // both arrivals store the same range
+    nd->split = nr.y;
+    nd->last = nr.z;
     __threadfence();
     int old = atomicAdd(&nodeVisit[parent], 1);
-    if (old == 0) return;
+    if ((old & 1) == 0) return;
     float4 sib = isLeft ? __ldcg(&nd->boxR) : __ldcg(&nd->boxL);
     unsigned long long sibKey = isLeft ? __ldcg(&nd->maxR) : __ldcg(&nd->maxL);
     box = make_float4(fminf(box.x, sib.x), fminf(box.y, sib.y), fmaxf(box.z, sib.z), fmaxf(box.w, sib.w));
@@ -270,6 +239,44 @@ __global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const un
     idx = parent;
     parent = nr.w;
   }
+}
+
+__global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const unsigned long long* __restrict__ leafKey,
+                             const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
+                             int* nodeVisit) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  refit_walk(p, leafBox[p], leafKey[p], leafParent, nodeRange, nodes, nodeVisit);
+}
+
+// Refit-only steps: the tree TOPOLOGY of the last rebuild is kept (any valid BVH reports the same
+// exact pair set); every leaf gets its fresh tight AABB and size key.  Replaces k_update_aabbs +
+// k_morton_keys + sort + k_leaf_gather + k_lbvh_build + k_lbvh_refit on the steps between rebuilds.
+__global__ void __launch_bounds__(256)
+k_refresh_leaves(int nf, const int* __restrict__ leafFixtureSorted, const int* __restrict__ fBody,
+                 const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
+                 const float4* __restrict__ shapes, const uint32_t* __restrict__ bflags,
+                 const float4* __restrict__ xf, float4* fAabb, float4* leafBox, unsigned long long* leafKey,
+                 const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
+                 int* nodeVisit) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nf) return;
+  int f = leafFixtureSorted[p];
+  uint32_t tf = fTypeFlags[f];
+  float4 box = leafBox[p];              // dead / static leaves keep the box of the last rebuild
+  unsigned long long key = leafKey[p];
+  if (!(tf & B2G_FIX_DEAD)) {
+    int b = fBody[f];
+    if (B2G_BODY_TYPE(bflags[b]) != B2G_STATIC) {
+      box = shape_aabb(shapes, (int)(tf & 3u), fShapeOff[f], xf_from4(xf[b]));
+      fAabb[f] = box;
+      leafBox[p] = box;
+      float size = (box.z - box.x) + (box.w - box.y);
+      key = ((unsigned long long)__float_as_uint(fmaxf(size, 0.0f)) << 32) | (unsigned int)p;
+      leafKey[p] = key;
+    }
+  }
+  refit_walk(p, box, key, leafParent, nodeRange, nodes, nodeVisit);  // refit fused into the refresh
 }
 
 // inclusive AABB overlap, b2TestOverlap (include/box2d/b2_collision.h:270-276)
@@ -432,7 +439,7 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
 __global__ void k_contact_sweep(int nSlots, ContactBuf C, uint8_t* persist, ContactHash H,
                                 const uint32_t* __restrict__ fTypeFlags, uint32_t* bflags, float4* force,
                                 int* freeStack, int* freeTop, StepCounts* counts, int recordEvents, int2* endEvents,
-                                int eventCap) {
+                                int eventCap, const int* __restrict__ island, uint8_t* islandDirty) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nSlots) return;
   uint32_t flags = C.flags[j];
@@ -445,6 +452,11 @@ __global__ void k_contact_sweep(int nSlots, ContactBuf C, uint8_t* persist, Cont
   if (recordEvents && (flags & B2G_CONTACT_TOUCHING)) {
     int k = atomicAdd(&counts->endCount, 1);
     if (k < eventCap) endEvents[k] = fx;
+  }
+  if (flags & B2G_CONTACT_TOUCHING) {
+    // a touching contact dies = an island edge disappears (see k_narrowphase)
+    int2 bd0 = C.body[j];
+    islandDirty[island[B2G_BODY_TYPE(bflags[bd0.x]) != B2G_STATIC ? bd0.x : bd0.y]] = 1;
   }
   int pointCount = __float_as_int(C.m3[j].w);
   if (pointCount > 0 && !((fTypeFlags[fx.x] | fTypeFlags[fx.y]) & B2G_FIX_SENSOR)) {

@@ -198,6 +198,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->bworld, nb));
   CK(dalloc(&A->island, nb));
   CK(dalloc(&A->islandParent, nb));
+  CK(dalloc(&A->islandDirty, nb));
   CK(dalloc(&A->islandAwake, nb));
   CK(dalloc(&A->islandMinSleep, nb));
   CK(dalloc(&A->islandPen, (size_t)nb * B2G_MAX_POS_ITERS));
@@ -317,7 +318,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   if (!A) return B2G_ERR_INVALID;
   cudaSetDevice(A->device);
   cudaStreamSynchronize(A->stream);
-  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent,
+  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent, A->islandDirty,
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
@@ -362,6 +363,7 @@ extern "C" int b2g_upload_bodies(b2gArena* A, int32_t first, int32_t count, cons
   CK(cudaStreamSynchronize(A->stream));
   if (first + count > A->nBodies) A->nBodies = first + count;
   A->aabbAllDirty = 1;
+  A->islandsValid = 0;
   if (s->mass || s->flags) A->recolour = 1;
   return B2G_OK;
 }
@@ -381,6 +383,7 @@ extern "C" int b2g_upload_fixtures(b2gArena* A, int32_t first, int32_t count, co
   CK(cudaStreamSynchronize(A->stream));
   if (first + count > A->nFixtures) A->nFixtures = first + count;
   A->aabbAllDirty = 1;
+  A->islandsValid = 0;
   return B2G_OK;
 }
 
@@ -424,6 +427,7 @@ extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, cons
   }
   CK(cudaStreamSynchronize(A->stream));
   if (first + count > A->nJoints) A->nJoints = first + count;
+  A->islandsValid = 0;
   return B2G_OK;
 }
 
@@ -434,6 +438,7 @@ extern "C" int b2g_set_counts(b2gArena* A, int32_t nb, int32_t nf, int32_t nj) {
   A->nFixtures = nf;
   A->nJoints = nj;
   A->aabbAllDirty = 1;
+  A->islandsValid = 0;
   return B2G_OK;
 }
 
@@ -495,12 +500,14 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
       A->bvhAge = 0;
     } else {
       LAUNCH(A, KC_BP_BUILD, nf, k_refresh_leaves, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->fBody,
-             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey, A->nodeVisit);
+             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey, A->leafParent,
+             A->nodeRange, A->bvhNodes, A->nodeVisit);
       A->bvhAge++;
     }
     if (nf > 1) {
-      LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent, A->nodeRange,
-             A->bvhNodes, A->nodeVisit);
+      if (rebuild)
+        LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent,
+               A->nodeRange, A->bvhNodes, A->nodeVisit);
       LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->bvhNodes, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash,
              A->persist, A->pairKeys, A->capContacts, A->dCounts);
     }
@@ -509,7 +516,7 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
   if (nSlots > 0) {
     LAUNCH(A, KC_CONTACT_MERGE, nSlots, k_contact_sweep, div_up(nSlots, 256), 256, nSlots, C, A->persist, A->hash,
            A->fTypeFlags, A->bflags, A->force, A->freeStack, A->dFreeTop, A->dCounts, recordEvents, A->endEvents,
-           A->capContacts);
+           A->capContacts, A->island, A->islandDirty);
   }
   // the end-of-broadphase readback: how many pairs are new, how many contacts died
   CK(cudaMemcpyAsync(A->hCounts, A->dCounts, sizeof(StepCounts), cudaMemcpyDeviceToHost, A->stream));
@@ -574,12 +581,13 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   {
     // ---- islands ---------------------------------------------------------------------
     LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent, A->islandAwake,
+           A->island, A->islandDirty, A->islandsValid,
            A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest,
            A->islandCount, A->islandCursor, A->binFirst, A->binEnd, 0, A->bucketCount, 0);
     if (nc > 0) LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
     if (nj > 0) LAUNCH(A, KC_ISLANDS, nj, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
     LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island, A->islandAwake,
-           A->islandCount, A->dCounts);
+           A->islandCount, A->dCounts, A->islandDirty);
     LAUNCH(A, KC_INTEGRATE, nb, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->vel, A->mass,
            A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y), A->dCounts, nullptr, 0);
 
@@ -758,14 +766,14 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
 
   const int nbuckets = (nbins + 1) << B2G_COLOUR_BITS;
   LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent,
-         A->islandAwake, A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask,
+         A->islandAwake, A->island, A->islandDirty, A->islandsValid, A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask,
          A->bodyBest, A->islandCount, A->islandCursor, A->binFirst, A->binEnd, nbins + 1, A->bucketCount, nbuckets);
   if (nc > 0)
     LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
   if (nj > 0)
     LAUNCH(A, KC_ISLANDS, nj, k_island_union_joints, div_up(nj, 256), 256, nj, A->jBodies, A->bflags, A->islandParent);
   LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island,
-         A->islandAwake, A->islandCount, A->dCounts);
+         A->islandAwake, A->islandCount, A->dCounts, A->islandDirty);
   LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandAwake, A->islandCount, A->islandStart,
          A->binFirst, A->binEnd, binSize, bigThr, A->dCounts);
   LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
@@ -779,8 +787,13 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     A->recolour = 0;
     int grid = div_up(nc, 256);
     if (grid > 148 * 8) grid = 148 * 8;
+    // Colouring rounds.  Constraints of tile-sized islands that are still uncoloured after the
+    // rounds launched simply go to their bin's serial overflow bucket for this step (a handful per
+    // bin; they keep colour -1 and retry next step, when their neighbours are already coloured),
+    // so no convergence loop is needed for them.  Constraints of big islands must all be coloured
+    // (their overflow bucket is one thread for the whole GPU), so there the loop runs to convergence.
     int round = 0;
-    int batch = A->roundsHint;
+    int batch = A->lastNumBig > 0 ? A->roundsHint : 2;
     while (true) {
       if (round > 0) CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
       for (int r = 0; r < batch; ++r, ++round) {
@@ -790,7 +803,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       }
       int rc = read_counts(A);  // the mid-step readback
       if (rc) return rc;
-      if (A->hCounts->remaining == 0) break;
+      if (A->hCounts->remaining == 0 || A->hCounts->numBig == 0) break;
       if (round > 250) {
         set_err("b2g_step", "graph colouring did not converge");
         return B2G_ERR_CUDA;
@@ -804,8 +817,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     }
     numActive = A->hCounts->numActive;
     numBig = A->hCounts->numBig;
+    A->lastNumBig = numBig;
     out.numColours = A->hCounts->numColours;
-    out.numOverflow = A->hCounts->numOverflow;
+    out.numOverflow = A->hCounts->numOverflow + A->hCounts->remaining;
     if (numActive > 0) {
       LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
       LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
@@ -929,7 +943,8 @@ extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
   if (A->profiling) CK(cudaEventRecord(A->ev[0], A->stream));
   if (nc > 0) {
     LAUNCH(A, KC_NARROWPHASE, nc, k_narrowphase, div_up(nc, 128), 128, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
-           A->bflags, A->dCounts, P->record_events, A->beginEvents, A->endEvents, A->capContacts);
+           A->bflags, A->dCounts, P->record_events, A->beginEvents, A->endEvents, A->capContacts, A->island,
+           A->islandDirty);
   }
   if (A->profiling) CK(cudaEventRecord(A->ev[1], A->stream));
   return B2G_OK;
@@ -951,6 +966,7 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
     SolveOut so;
     int rcs = P->solver_mode == B2G_SOLVER_COLOURED ? solve_fused(A, P, so) : solve_legacy(A, P, so);
     if (rcs) return rcs;
+    A->islandsValid = 1;
     numActive = so.numActive;
     numColours = so.numColours;
     numOverflow = so.numOverflow;
@@ -1187,6 +1203,7 @@ extern "C" int b2g_upload_contact_overrides(b2gArena* A, int32_t first, int32_t 
   CK(dS.upload(A->downloadSlots + first, (size_t)count * 4));
   if (flags) CK(dF.upload(flags, (size_t)count * 4));
   if (material) CK(dM.upload(material, (size_t)count * 16));
+  A->islandsValid = 0;  // a disabled contact removes an island edge
   k_scatter_overrides<<<div_up(count, 256), 256, 0, A->stream>>>(count, dS.as<int>(), flags ? dF.as<uint32_t>() : nullptr,
                                                                 material ? dM.as<float4>() : nullptr, A->cb[0]);
   CK(cudaStreamSynchronize(A->stream));

@@ -154,7 +154,9 @@ __global__ void k_bucket_count(int nc, const int* __restrict__ cbin, ContactBuf 
   if (i >= nc) return;
   int bin = cbin[i];
   if (bin < 0) return;
-  rank[i] = atomicAdd(&bucketCount[(bin << B2G_COLOUR_BITS) | C.colour[i]], 1);
+  int c = C.colour[i];
+  if (c < 0) c = B2G_OVERFLOW_COLOUR;  // not coloured within this step's rounds: serial bucket, retried next step
+  rank[i] = atomicAdd(&bucketCount[(bin << B2G_COLOUR_BITS) | c], 1);
 }
 
 // exclusive scan of the bucket counts by one block (buckets = bins x 32, a few thousand entries)
@@ -198,7 +200,9 @@ __global__ void k_bucket_scatter(int nc, const int* __restrict__ cbin, ContactBu
   if (i >= nc) return;
   int bin = cbin[i];
   if (bin < 0) return;
-  sortedList[bucketStart[(bin << B2G_COLOUR_BITS) | C.colour[i]] + rank[i]] = i;
+  int c = C.colour[i];
+  if (c < 0) c = B2G_OVERFLOW_COLOUR;
+  sortedList[bucketStart[(bin << B2G_COLOUR_BITS) | c] + rank[i]] = i;
 }
 
 // The overflow bucket is the only place where constraint ORDER matters (one thread, Gauss-Seidel in

@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(128)
 k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __restrict__ xf,
               const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
               const float4* __restrict__ shapes, uint32_t* bflagsRW, StepCounts* counts, int recordEvents,
-              int2* beginEvents, int2* endEvents, int eventCap) {
+              int2* beginEvents, int2* endEvents, int eventCap, const int* __restrict__ islandPrev,
+              uint8_t* islandDirty) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   uint32_t flags = C.flags[i];
@@ -94,6 +95,9 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
     if (touching != wasTouching) {
       if (B2G_BODY_TYPE(fa) != B2G_STATIC) atomicOr(&bflagsRW[bd.x], B2G_BODY_WAKE_REQUEST);
       if (B2G_BODY_TYPE(fb) != B2G_STATIC) atomicOr(&bflagsRW[bd.y], B2G_BODY_WAKE_REQUEST);
+      // an island edge disappeared: last step's island labels of this island cannot seed the
+      // union-find any more (it may have split)
+      if (!touching) islandDirty[islandPrev[B2G_BODY_TYPE(fa) != B2G_STATIC ? bd.x : bd.y]] = 1;
     }
   }
   float4 q0, q1, q2, q3;
@@ -125,6 +129,7 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
 // island is its smallest body index — deterministic whatever the thread order.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islandParent, uint32_t* islandAwake,
+                             const int* __restrict__ islandPrev, const uint8_t* __restrict__ islandDirty, int labelsValid,
                              uint32_t* islandMinSleep, uint32_t* islandPen, int penStride, int posIters,
                              unsigned long long* colourMask, unsigned long long* bodyBest, int* islandCount,
                              int* islandCursor, int* binFirst, int* binEnd, int nbinsPlus, int* bucketCount,
@@ -148,7 +153,14 @@ __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islan
     fo.w = 0.0f;
     force[b] = fo;
   }
-  islandParent[b] = b;
+  // Seed the union-find with last step's labels unless that island lost an edge: surviving islands
+  // start flattened (depth 1), so the union pass over their old edges is two loads per edge.
+  int seed = b;
+  if (labelsValid) {
+    int r = islandPrev[b];
+    if (!islandDirty[r]) seed = r;
+  }
+  islandParent[b] = seed;
   islandAwake[b] = 0;
   islandMinSleep[b] = __float_as_uint(B2G_MAX_FLOAT);
   for (int k = 0; k < posIters; ++k) islandPen[(size_t)k * penStride + b] = 0;
@@ -210,9 +222,11 @@ __global__ void k_island_union_joints(int nj, const int2* __restrict__ jBodies, 
 // race with other threads' finds (a late path-halving store can overwrite a finished entry with
 // a non-root ancestor), which made island ids — and therefore the whole step — nondeterministic.
 __global__ void k_island_flatten(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ parent,
-                                 int* island, uint32_t* islandAwake, int* islandCount, StepCounts* counts) {
+                                 int* island, uint32_t* islandAwake, int* islandCount, StepCounts* counts,
+                                 uint8_t* islandDirty) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  islandDirty[b] = 0;  // consumed by k_body_begin of this step
   int root = b;
   for (int p = parent[root]; p != root; p = parent[root]) root = p;
   island[b] = root;
