@@ -13,6 +13,7 @@
 #define B2G_MAX_COLOURS 24          // colours solved by parallel launches
 #define B2G_OVERFLOW_COLOUR B2G_MAX_COLOURS  // serial overflow bucket
 #define B2G_MAX_POS_ITERS 16
+#define B2G_ISLAND_EXACT_PERIOD 8  // steps between exact recomputations of oversize islands' labels
 #define B2G_BVH_REBUILD_PERIOD 8  // steps between LBVH topology rebuilds (boxes are refit every step)
 #define B2G_KT_MAX 2048  // timed launches per step when per-kernel timing is on
 
@@ -97,7 +98,10 @@ struct b2gArena {
   int nbinsMax, bigMode, lastMaxIsland, lastNumBig;
   int islandsValid;   // island[] of the previous step may seed this step's union-find
   uint8_t* islandDirty;  // per island root: an edge was removed since the labels were computed
+  uint8_t* islandWasBig; // per island root: last step it was too large for a tile
+  long long stepCount;
   size_t fusedSmemSet;
+  int bigGrid;  // co-resident grid of the persistent big-island kernel
 
   // fixtures + shapes
   int* fBody;

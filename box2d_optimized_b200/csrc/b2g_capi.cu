@@ -199,6 +199,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->island, nb));
   CK(dalloc(&A->islandParent, nb));
   CK(dalloc(&A->islandDirty, nb));
+  CK(dalloc(&A->islandWasBig, nb));
   CK(dalloc(&A->islandAwake, nb));
   CK(dalloc(&A->islandMinSleep, nb));
   CK(dalloc(&A->islandPen, (size_t)nb * B2G_MAX_POS_ITERS));
@@ -318,7 +319,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   if (!A) return B2G_ERR_INVALID;
   cudaSetDevice(A->device);
   cudaStreamSynchronize(A->stream);
-  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent, A->islandDirty,
+  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent, A->islandDirty, A->islandWasBig,
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
@@ -581,7 +582,7 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   {
     // ---- islands ---------------------------------------------------------------------
     LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent, A->islandAwake,
-           A->island, A->islandDirty, A->islandsValid,
+           A->island, A->islandDirty, A->islandsValid, A->islandWasBig, 1,
            A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask, A->bodyBest,
            A->islandCount, A->islandCursor, A->binFirst, A->binEnd, 0, A->bucketCount, 0);
     if (nc > 0) LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
@@ -766,7 +767,8 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
 
   const int nbuckets = (nbins + 1) << B2G_COLOUR_BITS;
   LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent,
-         A->islandAwake, A->island, A->islandDirty, A->islandsValid, A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask,
+         A->islandAwake, A->island, A->islandDirty, A->islandsValid, A->islandWasBig,
+         (A->stepCount % B2G_ISLAND_EXACT_PERIOD) == 0, A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask,
          A->bodyBest, A->islandCount, A->islandCursor, A->binFirst, A->binEnd, nbins + 1, A->bucketCount, nbuckets);
   if (nc > 0)
     LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
@@ -775,7 +777,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   LAUNCH(A, KC_ISLANDS, nb, k_island_flatten, div_up(nb, 256), 256, nb, A->bflags, A->islandParent, A->island,
          A->islandAwake, A->islandCount, A->dCounts, A->islandDirty);
   LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandAwake, A->islandCount, A->islandStart,
-         A->binFirst, A->binEnd, binSize, bigThr, A->dCounts);
+         A->binFirst, A->binEnd, binSize, bigThr, A->dCounts, A->islandWasBig);
   LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
          A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr);
 
@@ -876,40 +878,27 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
            A->dCounts, A->bodySlot, 1);
     LAUNCH(A, KC_PREPARE, numBig, k_prepare, div_up(numBig, 128), 128, bigStart, numBig, A->sortedList, C, A->fRadius,
            A->bflags, A->island, S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
-    if (P->warm_starting) {
-      for (int c = 0; c < numColours; ++c) {
-        int n = colourFirst[c + 1] - colourFirst[c];
-        if (n > 0)
-          LAUNCH(A, KC_WARM_START, n, k_warm_start, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S, A->vel);
+    {
+      // one persistent cooperative launch: all colours x all iterations, grid barrier in between
+      BigRanges R;
+      for (int c = 0; c <= B2G_MAX_COLOURS + 1; ++c) R.first[c] = colourFirst[c];
+      R.numColours = numColours;
+      if (A->bigGrid == 0) {
+        int perSM = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_big_solve, 256, 0));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
+        if (perSM > 1) perSM = 1;  // one block per SM: the grid barrier costs grow with the block count
+        A->bigGrid = perSM * sms;
       }
-      if (numOverflow > 0)
-        LAUNCH(A, KC_WARM_START, numOverflow, k_warm_start_seq, 1, 1, colourFirst[B2G_MAX_COLOURS],
-               colourFirst[B2G_MAX_COLOURS + 1], S, A->vel);
-    }
-    for (int it = 0; it < P->velocity_iterations; ++it) {
-      for (int c = 0; c < numColours; ++c) {
-        int n = colourFirst[c + 1] - colourFirst[c];
-        if (n > 0)
-          LAUNCH(A, KC_SOLVE_VELOCITY, n, k_solve_velocity, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S,
-                 A->vel);
-      }
-      if (numOverflow > 0)
-        LAUNCH(A, KC_SOLVE_VELOCITY, numOverflow, k_solve_velocity_seq, 1, 1, colourFirst[B2G_MAX_COLOURS],
-               colourFirst[B2G_MAX_COLOURS + 1], S, A->vel);
-    }
-    LAUNCH(A, KC_STORE_IMPULSES, numBig, k_store_impulses, div_up(numBig, 256), 256, bigStart, numBig, S, C);
-    LAUNCH(A, KC_INTEGRATE, nb, k_integrate_positions, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
-           A->pos, A->vel, h, A->bodySlot, 1);
-    for (int it = 0; it < P->position_iterations; ++it) {
-      for (int c = 0; c < numColours; ++c) {
-        int n = colourFirst[c + 1] - colourFirst[c];
-        if (n > 0)
-          LAUNCH(A, KC_SOLVE_POSITION, n, k_solve_position, div_up(n, 256), 256, colourFirst[c], colourFirst[c + 1], S,
-                 A->pos, A->croot, A->islandPen, A->capBodies, it);
-      }
-      if (numOverflow > 0)
-        LAUNCH(A, KC_SOLVE_POSITION, numOverflow, k_solve_position_seq, 1, 1, colourFirst[B2G_MAX_COLOURS],
-               colourFirst[B2G_MAX_COLOURS + 1], S, A->pos, A->croot, A->islandPen, A->capBodies, it);
+      int velIters = P->velocity_iterations, posIters = P->position_iterations, warm = P->warm_starting;
+      int penStride = A->capBodies, nbodies = nb;
+      float hh = h;
+      void* args[] = {&R, &S, &C, &A->vel, &A->pos, &A->croot, &A->islandPen, &penStride, &nbodies, &A->bflags,
+                      &A->island, &A->islandAwake, &A->bodySlot, &hh, &velIters, &posIters, &warm};
+      ktime_begin(A, KC_SOLVE_VELOCITY, (double)numBig * (velIters + posIters + 1));
+      CK(cudaLaunchCooperativeKernel((void*)k_big_solve, dim3(A->bigGrid), dim3(256), args, 0, A->stream));
+      ktime_end(A);
+      A->launches++;
     }
     LAUNCH(A, KC_FINALIZE, nb, k_finalize_bodies, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
            A->pos, A->vel, A->center, A->xf, A->force, A->islandMinSleep, h, P->allow_sleep, A->bodySlot, 1);
@@ -967,6 +956,7 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
     int rcs = P->solver_mode == B2G_SOLVER_COLOURED ? solve_fused(A, P, so) : solve_legacy(A, P, so);
     if (rcs) return rcs;
     A->islandsValid = 1;
+    A->stepCount++;
     numActive = so.numActive;
     numColours = so.numColours;
     numOverflow = so.numOverflow;

@@ -14,6 +14,8 @@
 // and solved by the per-colour kernels of b2g_step_kernels.cuh over the whole GPU.
 #pragma once
 #include "b2g_step_kernels.cuh"
+#include <cooperative_groups/scan.h>
+#include <cooperative_groups/reduce.h>
 
 #define B2G_FUSED_THREADS 256
 #define B2G_COLOUR_BITS 5  // 24 colours + overflow < 32
@@ -26,12 +28,19 @@
 // simulation result does not depend on it.
 __global__ void k_island_alloc(int nb, const int* __restrict__ island, const uint32_t* __restrict__ islandAwake,
                                const int* __restrict__ islandCount, int* islandStart, int* binFirst, int* binEnd,
-                               int binSize, int bigThreshold, StepCounts* counts) {
+                               int binSize, int bigThreshold, StepCounts* counts, uint8_t* islandWasBig) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   int cnt = islandCount[b];
+  islandWasBig[b] = (island[b] == b && cnt > bigThreshold) ? 1 : 0;
   if (cnt <= 0 || cnt > bigThreshold || island[b] != b || !islandAwake[b]) return;
-  int start = atomicAdd(&counts->slotCursor, cnt);
+  // one atomic per warp: a scene of many small islands would otherwise hammer the single cursor
+  auto g = cg::coalesced_threads();
+  int prefix = cg::exclusive_scan(g, cnt, cg::plus<int>());
+  int total = cg::reduce(g, cnt, cg::plus<int>());
+  int base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&counts->slotCursor, total);
+  int start = g.shfl(base, 0) + prefix;
   islandStart[b] = start;
   int bin = start / binSize;
   atomicMin(&binFirst[bin], start);
@@ -503,4 +512,114 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     }
   }
   if (awake) atomicAdd(&counts->numAwake, awake);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Oversize islands (more bodies than a tile holds, e.g. a settled 100k-body pile = ONE island):
+// a persistent cooperative kernel walks warm start, the velocity iterations, position integration
+// and the position iterations colour by colour with a grid-wide barrier between colours, instead
+// of one launch per colour per iteration (14 colours x 12 passes = 170 launches of ~16k
+// constraints each were launch-latency bound).  Body state stays in global memory / L2.
+// ---------------------------------------------------------------------------------------------
+struct BigRanges {
+  int first[B2G_MAX_COLOURS + 2];  // first[c]..first[c+1] = slots of colour c; [MAX] = overflow bucket
+  int numColours;
+};
+
+__global__ void __launch_bounds__(256)
+k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos, const int* __restrict__ croot,
+            uint32_t* islandPen, int penStride, int nb, const uint32_t* __restrict__ bflags,
+            const int* __restrict__ island, const uint32_t* __restrict__ islandAwake,
+            const int* __restrict__ bodySlot, float h, int velIters, int posIters, int warmStarting) {
+  cg::grid_group grid = cg::this_grid();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gsize = gridDim.x * blockDim.x;
+  const GlobalBodies velAcc{vel};
+  const GlobalBodies posAcc{pos};
+  const int ov0 = R.first[B2G_MAX_COLOURS], ov1 = R.first[B2G_MAX_COLOURS + 1];
+
+  if (warmStarting) {
+    for (int c = 0; c < R.numColours; ++c) {
+      for (int s = R.first[c] + gtid; s < R.first[c + 1]; s += gsize) warm_start_constraint(S, s, velAcc);
+      grid.sync();
+    }
+    if (ov1 > ov0) {
+      if (gtid == 0)
+        for (int s = ov0; s < ov1; ++s) warm_start_constraint(S, s, velAcc);
+      grid.sync();
+    }
+  }
+  for (int it = 0; it < velIters; ++it) {
+    for (int c = 0; c < R.numColours; ++c) {
+      for (int s = R.first[c] + gtid; s < R.first[c + 1]; s += gsize) solve_velocity_constraint(S, s, velAcc);
+      grid.sync();
+    }
+    if (ov1 > ov0) {
+      if (gtid == 0)
+        for (int s = ov0; s < ov1; ++s) solve_velocity_constraint(S, s, velAcc);
+      grid.sync();
+    }
+  }
+  // store impulses (b2_contact_solver.cpp:641-657)
+  for (int s = R.first[0] + gtid; s < ov1; s += gsize) {
+    int4 ix = S.idx[s];
+    float4 imp = S.imp[s];
+    int i = ix.w;
+    float4 q1 = C.m1[i];
+    q1.z = imp.x;
+    q1.w = imp.y;
+    C.m1[i] = q1;
+    if (ix.z == 2) {
+      float4 q2 = C.m2[i];
+      q2.z = imp.z;
+      q2.w = imp.w;
+      C.m2[i] = q2;
+    }
+  }
+  // integrate positions of the big islands' bodies (b2_island.cpp:353-385)
+  for (int b = gtid; b < nb; b += gsize) {
+    if (bodySlot[b] != B2G_SLOT_BIG) continue;
+    if (!body_simulated(bflags[b], island, islandAwake, b)) continue;
+    float4 p4 = pos[b], v4 = vel[b];
+    float2 v = make_float2(v4.x, v4.y);
+    float w = v4.z;
+    float2 translation = h * v;
+    if (dot2(translation, translation) > B2G_MAX_TRANSLATION_SQ) {
+      float ratio = B2G_MAX_TRANSLATION / len2(translation);
+      v.x *= ratio;
+      v.y *= ratio;
+    }
+    float rotation = h * w;
+    if (rotation * rotation > B2G_MAX_ROTATION_SQ) {
+      float ratio = B2G_MAX_ROTATION / absf_(rotation);
+      w *= ratio;
+    }
+    p4.x += h * v.x;
+    p4.y += h * v.y;
+    p4.z += h * w;
+    pos[b] = p4;
+    vel[b] = make_float4(v.x, v.y, w, v4.w);
+  }
+  grid.sync();
+  for (int it = 0; it < posIters; ++it) {
+    for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {
+      if (c >= R.numColours && c < B2G_MAX_COLOURS) continue;
+      int s0 = R.first[c], s1 = R.first[c + 1];
+      if (s0 == s1) continue;  // grid-uniform
+      int sBegin = s0 + gtid, sStep = gsize;
+      if (c == B2G_MAX_COLOURS) {
+        sBegin = gtid == 0 ? s0 : s1;
+        sStep = 1;
+      }
+      for (int s = sBegin; s < s1; s += sStep) {
+        int root = croot[s];
+        if (island_done(islandPen, penStride, it, root)) continue;
+        float minSep = solve_position_constraint(S, s, posAcc);
+        float pen = minSep < 0.0f ? -minSep : 0.0f;
+        atomicMax(&islandPen[(size_t)it * penStride + root], __float_as_uint(pen));
+      }
+      grid.sync();
+    }
+  }
 }

@@ -130,6 +130,7 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islandParent, uint32_t* islandAwake,
                              const int* __restrict__ islandPrev, const uint8_t* __restrict__ islandDirty, int labelsValid,
+                             const uint8_t* __restrict__ islandWasBig, int exactStep,
                              uint32_t* islandMinSleep, uint32_t* islandPen, int penStride, int posIters,
                              unsigned long long* colourMask, unsigned long long* bodyBest, int* islandCount,
                              int* islandCursor, int* binFirst, int* binEnd, int nbinsPlus, int* bucketCount,
@@ -158,7 +159,14 @@ __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islan
   int seed = b;
   if (labelsValid) {
     int r = islandPrev[b];
-    if (!islandDirty[r]) seed = r;
+    // Tile-sized islands: exact — rebuilt from their edges whenever one disappeared.  Oversize
+    // islands (a settled pile) lose and gain edges every step while staying connected, and
+    // re-uniting 100k bodies under one root is the most contended thing in the step, so their
+    // labels are kept between exact recomputations every B2G_ISLAND_EXACT_PERIOD steps.  A stale
+    // label can only keep a piece that just broke off attached a few steps longer (it then shares
+    // the pile's sleep timer and position-iteration early exit): conservative, never unsafe.
+    bool reuse = islandWasBig[r] ? !exactStep : !islandDirty[r];
+    if (reuse) seed = r;
   }
   islandParent[b] = seed;
   islandAwake[b] = 0;
