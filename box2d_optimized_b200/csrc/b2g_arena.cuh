@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include "../../include/b2cuda.h"
 #include "b2g_solver.cuh"
+#include "b2g_joint.cuh"
 
 #define B2G_MAX_COLOURS 24          // colours solved by parallel launches
 #define B2G_OVERFLOW_COLOUR B2G_MAX_COLOURS  // serial overflow bucket
@@ -31,6 +32,7 @@ struct StepCounts {
   int slotCursor;       // next free slot of the island-sorted body order
   int numDead;          // contacts retired by this step's sweep
   int freeTopRead;      // host copy of the free-stack height (filled by the readback)
+  int jointOverflow;    // joints that did not fit a tile's joint list (reported as an error)
   int colourCount[B2G_MAX_COLOURS + 1];
   unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
 };
@@ -118,7 +120,9 @@ struct b2gArena {
   float4* jAnchors;
   float4* jParams0;  // referenceAngle, lower, upper, maxMotorTorque
   float4* jParams1;  // motorSpeed, bits(flags), 0, 0
-  float4* jState;    // impulse.x, impulse.y, motorImpulse, lowerImpulse/upperImpulse packed later
+  float4* jState;    // impulse.x, impulse.y, motorImpulse, lowerImpulse
+  float* jUpper;     // upperImpulse
+  JointWork* jWork;  // per-step scratch
 
   // contacts
   ContactBuf cb[1];           // stable slots; nContacts = slot high-water mark, nAlive = live contacts

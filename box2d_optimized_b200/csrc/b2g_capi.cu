@@ -230,6 +230,8 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->jParams0, nj));
   CK(dalloc(&A->jParams1, nj));
   CK(dalloc(&A->jState, nj));
+  CK(dalloc(&A->jUpper, nj));
+  CK(dalloc(&A->jWork, nj));
 
   int rc = alloc_contact_buf(A->cb[0], nc);
   if (rc) return rc;
@@ -323,7 +325,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->worldFirst, A->worldLast, A->nodeRange, A->bvhNodes, A->leafParent,
                   A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -424,6 +426,7 @@ extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, cons
     CK(cudaMemcpyAsync((float*)A->jParams1 + (size_t)first * 4, p1.data(), p1.size() * sizeof(float),
                        cudaMemcpyHostToDevice, A->stream));
     CK(cudaMemsetAsync((float*)A->jState + (size_t)first * 4, 0, (size_t)count * 4 * sizeof(float), A->stream));
+    CK(cudaMemsetAsync(A->jUpper + first, 0, (size_t)count * sizeof(float), A->stream));
     CK(cudaStreamSynchronize(A->stream));
   }
   CK(cudaStreamSynchronize(A->stream));
@@ -567,6 +570,28 @@ extern "C" int b2g_find_new_contacts(b2gArena* A) {
 // Solve, list-order / per-colour-launch path: used by B2G_SOLVER_SEQUENTIAL (parity vehicle).  One
 // kernel per reference loop, constraints addressed through global body arrays.
 // ---------------------------------------------------------------------------------------------
+static JointArraysDev joint_views(b2gArena* A) {
+  JointArraysDev J;
+  J.bodies = A->jBodies;
+  J.anchors = A->jAnchors;
+  J.params0 = A->jParams0;
+  J.params1 = A->jParams1;
+  J.state = A->jState;
+  J.upper = A->jUpper;
+  J.work = A->jWork;
+  return J;
+}
+static JointWalk joint_walk(b2gArena* A, int onlyBig) {
+  JointWalk W;
+  W.nj = A->nJoints;
+  W.onlyBig = onlyBig;
+  W.bflags = A->bflags;
+  W.island = A->island;
+  W.islandAwake = A->islandAwake;
+  W.bodySlot = A->bodySlot;
+  return W;
+}
+
 struct SolveOut {
   int numActive = 0, numColours = 0, numOverflow = 0, rounds = 0;
 };
@@ -665,6 +690,9 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     // ---- contact solver --------------------------------------------------------------
     SolverPlanes& S = A->planes;
     const bool coloured = P->solver_mode != B2G_SOLVER_SEQUENTIAL;
+    const JointWalk JW = joint_walk(A, 0);
+    const JointArraysDev JV = joint_views(A);
+    const float invH = h > 0.0f ? 1.0f / h : 0.0f;
     if (numActive > 0) {
       LAUNCH(A, KC_PREPARE, numActive, k_prepare, div_up(numActive, 128), 128, 0, numActive, A->sortedList, C, A->fRadius, A->bflags, A->island,
              S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
@@ -681,7 +709,15 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
           LAUNCH(A, KC_WARM_START, numActive, k_warm_start_seq, 1, 1, 0, numActive, S, A->vel);
         }
       }
-      for (int it = 0; it < P->velocity_iterations; ++it) {
+    }
+    // joints: InitVelocityConstraints after the contacts' warm start (b2_island.cpp:323-325)
+    if (nj > 0)
+      LAUNCH(A, KC_WARM_START, nj, k_joints_init_seq, 1, 1, JW, JV, A->pos, A->vel, A->mass, A->center, dtRatio,
+             P->warm_starting);
+    for (int it = 0; it < P->velocity_iterations; ++it) {
+      // joints first, then contacts (b2_island.cpp:330-338)
+      if (nj > 0) LAUNCH(A, KC_SOLVE_VELOCITY, nj, k_joints_velocity_seq, 1, 1, JW, JV, A->vel, h, invH);
+      if (numActive > 0) {
         if (coloured) {
           for (int c = 0; c < numColours; ++c) {
             int n = colourFirst[c + 1] - colourFirst[c];
@@ -695,12 +731,14 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
           LAUNCH(A, KC_SOLVE_VELOCITY, numActive, k_solve_velocity_seq, 1, 1, 0, numActive, S, A->vel);
         }
       }
-      LAUNCH(A, KC_STORE_IMPULSES, numActive, k_store_impulses, div_up(numActive, 256), 256, 0, numActive, S, C);
     }
+    if (numActive > 0)
+      LAUNCH(A, KC_STORE_IMPULSES, numActive, k_store_impulses, div_up(numActive, 256), 256, 0, numActive, S, C);
     LAUNCH(A, KC_INTEGRATE, nb, k_integrate_positions, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
            h, nullptr, 0);
-    if (numActive > 0) {
-      for (int it = 0; it < P->position_iterations; ++it) {
+    for (int it = 0; it < P->position_iterations; ++it) {
+      // contacts first, then joints (b2_island.cpp:392-401)
+      if (numActive > 0) {
         if (coloured) {
           for (int c = 0; c < numColours; ++c) {
             int n = colourFirst[c + 1] - colourFirst[c];
@@ -715,6 +753,8 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
           LAUNCH(A, KC_SOLVE_POSITION, numActive, k_solve_position_seq, 1, 1, 0, numActive, S, A->pos, A->croot, A->islandPen, A->capBodies, it);
         }
       }
+      if (nj > 0)
+        LAUNCH(A, KC_SOLVE_POSITION, nj, k_joints_position_seq, 1, 1, JW, JV, A->pos, A->islandPen, A->capBodies, it);
     }
     LAUNCH(A, KC_FINALIZE, nb, k_finalize_bodies, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake, A->pos, A->vel,
            A->center, A->xf, A->force, A->islandMinSleep, h, P->allow_sleep, nullptr, 0);
@@ -846,6 +886,8 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     FP.clearForces = P->clear_forces;
     FP.tileCap = tileCap;
     FP.conCap = conCap;
+    FP.nj = nj;
+    FP.invH = h > 0.0f ? 1.0f / h : 0.0f;
     if (smem > A->fusedSmemSet) {
       CK(cudaFuncSetAttribute(k_solve_bins_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       A->fusedSmemSet = smem;
@@ -853,7 +895,8 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     ktime_begin(A, KC_FUSED_SOLVE, (double)numActive - numBig);
     k_solve_bins_fused<<<nbins, B2G_FUSED_THREADS, smem, A->stream>>>(
         FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->bucketStart,
-        A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts);
+        A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts,
+        joint_views(A));
     ktime_end(A);
     A->launches++;
   }
@@ -892,9 +935,12 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       }
       int velIters = P->velocity_iterations, posIters = P->position_iterations, warm = P->warm_starting;
       int penStride = A->capBodies, nbodies = nb;
-      float hh = h;
+      float hh = h, dtr = dtRatio;
+      JointWalk JW = joint_walk(A, 1);
+      JointArraysDev JV = joint_views(A);
       void* args[] = {&R, &S, &C, &A->vel, &A->pos, &A->croot, &A->islandPen, &penStride, &nbodies, &A->bflags,
-                      &A->island, &A->islandAwake, &A->bodySlot, &hh, &velIters, &posIters, &warm};
+                      &A->island, &A->islandAwake, &A->bodySlot, &hh, &velIters, &posIters, &warm, &JW, &JV,
+                      &A->mass, &A->center, &dtr};
       ktime_begin(A, KC_SOLVE_VELOCITY, (double)numBig * (velIters + posIters + 1));
       CK(cudaLaunchCooperativeKernel((void*)k_big_solve, dim3(A->bigGrid), dim3(256), args, 0, A->stream));
       ktime_end(A);

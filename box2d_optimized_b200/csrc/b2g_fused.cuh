@@ -244,7 +244,10 @@ struct FusedParams {
   int velIters, posIters, warmStarting, allowSleep, clearForces;
   int tileCap;         // bodies the shared-memory tile can hold
   int conCap;          // constraints whose 13 planes fit in shared memory next to the tile
+  int nj;              // joints in the arena
+  float invH;
 };
+#define B2G_TILE_JOINTS 64
 #define B2G_PLANES 13
 
 // dynamic shared memory layout for a tile of `cap` bodies
@@ -267,7 +270,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
                    const int* __restrict__ bucketStart, int* sortedList, int* orderScratch, ContactBuf C,
                    const float* __restrict__ fRadius, SolverPlanes S, uint32_t* bflags, float4* gpos, float4* gvel,
                    float4* gxf, float4* gforce, const float4* __restrict__ gmass, const float4* __restrict__ gcenter,
-                   StepCounts* counts) {
+                   StepCounts* counts, JointArraysDev J) {
   const int bin = blockIdx.x;
   const int first = binFirst[bin];
   const int nbod = binEnd[bin] - first;
@@ -287,6 +290,9 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     T.done = (int*)p;
   }
   __shared__ int cstart[B2G_MAX_COLOURS + 3];
+  __shared__ int sJoint[B2G_TILE_JOINTS];
+  __shared__ int sJointCount;
+  if (tid == 0) sJointCount = 0;
 
   // constraint ranges of this bin, one per colour (+ overflow), from the bucket table
   if (tid <= B2G_MAX_COLOURS + 1) cstart[tid] = P.nc > 0 ? bucketStart[(bin << B2G_COLOUR_BITS) + tid] : 0;
@@ -320,6 +326,34 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     T.pos[l] = gpos[b];
   }
   __syncthreads();
+  // joints whose island lives in this tile (b2_island.cpp:323-325 walks the island's joint list)
+  if (P.nj > 0) {
+    for (int j = tid; j < P.nj; j += nt) {
+      int2 bd = J.bodies[j];
+      int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
+      int sl = sa >= 0 ? sa : sb;
+      if (sl >= first && sl < first + nbod) {
+        int k = atomicAdd(&sJointCount, 1);
+        if (k < B2G_TILE_JOINTS) sJoint[k] = j;
+        else atomicAdd(&counts->jointOverflow, 1);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {  // joint-index order, whatever order the atomics produced
+      int n = min(sJointCount, B2G_TILE_JOINTS);
+      for (int a = 1; a < n; ++a) {
+        int v = sJoint[a], b = a - 1;
+        while (b >= 0 && sJoint[b] > v) {
+          sJoint[b + 1] = sJoint[b];
+          --b;
+        }
+        sJoint[b + 1] = v;
+      }
+      sJointCount = n;
+    }
+    __syncthreads();
+  }
+  const int njTile = P.nj > 0 ? sJointCount : 0;
   order_bucket_by_key(cstart[B2G_MAX_COLOURS], cstart[B2G_MAX_COLOURS + 1], sortedList, orderScratch, C);
   const int cAll0 = cstart[0], cAll1 = cstart[B2G_MAX_COLOURS + 1];
   const TileBodies velAcc{T.vel, gvel};
@@ -375,8 +409,27 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     }
   }
 
+  // joints: InitVelocityConstraints incl. their warm start (b2_island.cpp:323-325), after the contacts'
+  if (njTile > 0) {
+    if (tid == 0) {
+      for (int k = 0; k < njTile; ++k) {
+        int j = sJoint[k];
+        int2 bd = J.bodies[j];
+        int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
+        joint_init(J, j, sa >= 0 ? sa - first : ~bd.x, sb >= 0 ? sb - first : ~bd.y, posAcc, velAcc, gmass, gcenter,
+                   P.dtRatio, P.warmStarting != 0);
+      }
+    }
+    __syncthreads();
+  }
+
   // ---- phase 3: velocity iterations ---------------------------------------------------------------
   for (int it = 0; it < P.velIters; ++it) {
+    if (njTile > 0) {  // joints first, then contacts (b2_island.cpp:330-338)
+      if (tid == 0)
+        for (int k = 0; k < njTile; ++k) joint_solve_velocity(J, sJoint[k], velAcc, P.h, P.invH);
+      __syncthreads();
+    }
     for (int c = 0; c < B2G_MAX_COLOURS; ++c) {
       int s0 = cstart[c], s1 = cstart[c + 1];
       if (s0 == s1) continue;
@@ -453,7 +506,21 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
       }
       __syncthreads();
     }
-    // island converged? (contactsOkay: minSeparation >= -3 slop)
+    if (njTile > 0) {  // contacts first, then joints (b2_island.cpp:392-401); a joint that is not
+                       // okay keeps its island iterating, expressed as a large "penetration"
+      if (tid == 0) {
+        for (int k = 0; k < njTile; ++k) {
+          int j = sJoint[k];
+          JointWork w = J.work[j];
+          int slot = w.ia >= 0 ? w.ia : w.ib;
+          int hd = T.head[slot];
+          if (T.done[hd]) continue;
+          if (!joint_solve_position(J, j, posAcc)) atomicMax(&T.pen[hd], __float_as_uint(1.0f));
+        }
+      }
+      __syncthreads();
+    }
+    // island converged? (contactsOkay && jointsOkay: minSeparation >= -3 slop)
     for (int l = tid; l < nbod; l += nt) {
       if (T.head[l] == l && !T.done[l]) {
         if (__uint_as_float(T.pen[l]) <= 3.0f * B2G_LINEAR_SLOP) T.done[l] = 1;
@@ -522,6 +589,62 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
 // of one launch per colour per iteration (14 colours x 12 passes = 170 launches of ~16k
 // constraints each were launch-latency bound).  Body state stays in global memory / L2.
 // ---------------------------------------------------------------------------------------------
+// ---- joints of islands that are solved through the global arrays (big islands, sequential mode):
+// one thread, joint-index order
+struct JointWalk {
+  int nj, onlyBig;
+  const uint32_t* bflags;
+  const int* island;
+  const uint32_t* islandAwake;
+  const int* bodySlot;
+};
+__device__ __forceinline__ int joint_owner_body(const JointWalk& W, const JointArraysDev& J, int j) {
+  int2 bd = J.bodies[j];
+  uint32_t fa = W.bflags[bd.x], fb = W.bflags[bd.y];
+  if (!(fa & B2G_BODY_ENABLED) || !(fb & B2G_BODY_ENABLED)) return -1;
+  int s = B2G_BODY_TYPE(fa) != B2G_STATIC ? bd.x : bd.y;
+  if (B2G_BODY_TYPE(W.bflags[s]) == B2G_STATIC) return -1;
+  if (!W.islandAwake[W.island[s]]) return -1;
+  if (W.onlyBig && W.bodySlot[s] != B2G_SLOT_BIG) return -1;
+  return s;
+}
+__device__ __forceinline__ void joints_init_global(const JointWalk& W, const JointArraysDev& J, float4* pos, float4* vel,
+                                                   const float4* __restrict__ mass, const float4* __restrict__ center,
+                                                   float dtRatio, int warm) {
+  for (int j = 0; j < W.nj; ++j) {
+    if (joint_owner_body(W, J, j) < 0) continue;
+    int2 bd = J.bodies[j];
+    joint_init(J, j, bd.x, bd.y, GlobalBodies{pos}, GlobalBodies{vel}, mass, center, dtRatio, warm != 0);
+  }
+}
+__device__ __forceinline__ void joints_velocity_global(const JointWalk& W, const JointArraysDev& J, float4* vel, float h,
+                                                       float invH) {
+  for (int j = 0; j < W.nj; ++j)
+    if (joint_owner_body(W, J, j) >= 0) joint_solve_velocity(J, j, GlobalBodies{vel}, h, invH);
+}
+__device__ __forceinline__ void joints_position_global(const JointWalk& W, const JointArraysDev& J, float4* pos,
+                                                       uint32_t* islandPen, int penStride, int iter) {
+  for (int j = 0; j < W.nj; ++j) {
+    int s = joint_owner_body(W, J, j);
+    if (s < 0) continue;
+    int root = W.island[s];
+    if (island_done(islandPen, penStride, iter, root)) continue;
+    if (!joint_solve_position(J, j, GlobalBodies{pos}))
+      atomicMax(&islandPen[(size_t)iter * penStride + root], __float_as_uint(1.0f));
+  }
+}
+__global__ void k_joints_init_seq(JointWalk W, JointArraysDev J, float4* pos, float4* vel, const float4* mass,
+                                  const float4* center, float dtRatio, int warm) {
+  joints_init_global(W, J, pos, vel, mass, center, dtRatio, warm);
+}
+__global__ void k_joints_velocity_seq(JointWalk W, JointArraysDev J, float4* vel, float h, float invH) {
+  joints_velocity_global(W, J, vel, h, invH);
+}
+__global__ void k_joints_position_seq(JointWalk W, JointArraysDev J, float4* pos, uint32_t* islandPen, int penStride,
+                                      int iter) {
+  joints_position_global(W, J, pos, islandPen, penStride, iter);
+}
+
 struct BigRanges {
   int first[B2G_MAX_COLOURS + 2];  // first[c]..first[c+1] = slots of colour c; [MAX] = overflow bucket
   int numColours;
@@ -531,7 +654,8 @@ __global__ void __launch_bounds__(256)
 k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos, const int* __restrict__ croot,
             uint32_t* islandPen, int penStride, int nb, const uint32_t* __restrict__ bflags,
             const int* __restrict__ island, const uint32_t* __restrict__ islandAwake,
-            const int* __restrict__ bodySlot, float h, int velIters, int posIters, int warmStarting) {
+            const int* __restrict__ bodySlot, float h, int velIters, int posIters, int warmStarting, JointWalk W,
+            JointArraysDev J, const float4* __restrict__ mass, const float4* __restrict__ center, float dtRatio) {
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gsize = gridDim.x * blockDim.x;
@@ -550,7 +674,16 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
       grid.sync();
     }
   }
+  const float invH = h > 0.0f ? 1.0f / h : 0.0f;
+  if (W.nj > 0) {
+    if (gtid == 0) joints_init_global(W, J, pos, vel, mass, center, dtRatio, warmStarting);
+    grid.sync();
+  }
   for (int it = 0; it < velIters; ++it) {
+    if (W.nj > 0) {
+      if (gtid == 0) joints_velocity_global(W, J, vel, h, invH);
+      grid.sync();
+    }
     for (int c = 0; c < R.numColours; ++c) {
       for (int s = R.first[c] + gtid; s < R.first[c + 1]; s += gsize) solve_velocity_constraint(S, s, velAcc);
       grid.sync();
@@ -619,6 +752,10 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
         float pen = minSep < 0.0f ? -minSep : 0.0f;
         atomicMax(&islandPen[(size_t)it * penStride + root], __float_as_uint(pen));
       }
+      grid.sync();
+    }
+    if (W.nj > 0) {
+      if (gtid == 0) joints_position_global(W, J, pos, islandPen, penStride, it);
       grid.sync();
     }
   }

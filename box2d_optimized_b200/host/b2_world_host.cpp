@@ -39,6 +39,7 @@ struct b2WorldImpl {
   std::vector<b2Joint*> joints;
   std::vector<float> shapePool;     // float4 records, append-only
   int32 shapesUploaded = 0;         // quads already on the device
+  int32 bodiesOnDevice = 0;         // bodies the arena knows about (created-but-not-flushed ones are host only)
   int32 bodyDirtyLo = INT32_MAX, bodyDirtyHi = 0;
   int32 fixtureDirtyLo = INT32_MAX, fixtureDirtyHi = 0;
   bool jointsDirty = false;
@@ -109,6 +110,7 @@ void b2WorldImpl::ensureArena() {
   b2gCheck(b2g_arena_create(&def, &arena), "b2g_arena_create");
   b2g_set_profiling(arena, profiling ? 1 : 0);
   shapesUploaded = 0;
+  bodiesOnDevice = 0;
   bodyDirtyLo = 0;
   bodyDirtyHi = needBodies;
   fixtureDirtyLo = 0;
@@ -157,6 +159,7 @@ void b2WorldImpl::flush() {
     a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.mass = mass.data(); a.center = center.data();
     a.force = force.data(); a.flags = flags.data(); a.world = wid.data();
     b2gCheck(b2g_upload_bodies(arena, lo, n, &a), "b2g_upload_bodies");
+    bodiesOnDevice = std::max(bodiesOnDevice, lo + n);
     bodyDirtyLo = INT32_MAX;
     bodyDirtyHi = 0;
   }
@@ -212,7 +215,7 @@ void b2WorldImpl::flush() {
 void b2WorldImpl::pullBodies() {
   if (!bodiesStale || !arena) return;
   bodiesStale = false;
-  int32 n = (int32)bodies.size();
+  int32 n = std::min((int32)bodies.size(), bodiesOnDevice);
   if (n == 0) return;
   std::vector<float> pos((size_t)n * 4), vel((size_t)n * 4), xf((size_t)n * 4), force((size_t)n * 4);
   std::vector<uint32_t> flags(n);

@@ -201,6 +201,35 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
       jd.enableMotor = true;
       s->world->CreateJoint(&jd);
     }
+  } else if (name == "pendulum" || name == "pendulum_limit" || name == "pendulum_motor") {
+    // revolute joint checks (cf. unit-test/joint_test.cpp:27-106): `size` boxes, each hinged to the
+    // static ground 2 m to the side of its centre, no contacts between them (they are 10 m apart)
+    int n = size > 0 ? size : 3;
+    b2BodyDef gd;
+    b2Body* ground = s->addBody(gd);
+    for (int i = 0; i < n; ++i) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(10.0f * (float)i + 2.0f, 5.0f);
+      bd.angularDamping = 0.05f * (float)i;
+      b2Body* body = s->addBody(bd);
+      b2PolygonShape box;
+      box.SetAsBox(0.5f + 0.1f * (float)i, 0.25f);
+      s->addFixture(body, box, 1.0f + (float)i);
+      b2RevoluteJointDef jd;
+      jd.Initialize(ground, body, b2Vec2(10.0f * (float)i, 5.0f));
+      if (name == "pendulum_limit") {
+        jd.enableLimit = true;
+        jd.lowerAngle = -0.4f;
+        jd.upperAngle = 0.3f;
+      }
+      if (name == "pendulum_motor") {
+        jd.enableMotor = true;
+        jd.motorSpeed = 1.0f;
+        jd.maxMotorTorque = 40.0f;
+      }
+      s->world->CreateJoint(&jd);
+    }
   } else if (name == "hello") {
     s->velocityIterations = 6;
     s->positionIterations = 2;
