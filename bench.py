@@ -65,8 +65,12 @@ WORKLOADS = {
     # batched independent worlds in ONE arena per GPU (world id in the broadphase key), sharded
     # round-robin over ranks: size = worlds per GPU
     "pyramid_worlds": ("pyramid", 20, 0, "512 independent 20-row pyramid worlds per GPU (108k bodies), one arena"),
+    # BASELINE config 4 shape: motor-driven tumbler (benchmarks.h b3) with 500 boxes per world; the
+    # scene is stepped to the state where every box has been spawned, then replicated per world
+    "tumbler_worlds": ("tumbler", 500, 0, "256 independent 500-box tumbler worlds per GPU (128k bodies), one arena"),
 }
-WORLDS_PER_GPU = {"pyramid_worlds": 512}
+WORLDS_PER_GPU = {"pyramid_worlds": 512, "tumbler_worlds": 256}
+PRESTEP = {"tumbler_worlds": 520}  # steps run through the drop-in API before the state is replicated
 
 
 def parse():
@@ -144,6 +148,8 @@ def run_reference(args, rank, world):
         nworlds = min(ncpu, WORLDS_PER_GPU[args.workload] * max(1, args.gpus))
     nworlds = min(nworlds, max(1, ncpu))
     worlds = [RefScene(scene, size, seed) for _ in range(nworlds)]
+    if args.workload in PRESTEP:
+        [w.step(PRESTEP[args.workload]) for w in worlds]
     nb = worlds[0].body_count
     times = [0.0] * nworlds
 
@@ -192,6 +198,8 @@ def main():
     lib = capi.load_cuda()
     # host-side scene construction through the drop-in C++ API; never stepped itself
     scene = GpuScene(scene_name, size, seed)
+    if args.workload in PRESTEP:
+        scene.step(PRESTEP[args.workload])
     nb = scene.body_count
     cap_contacts = max(4096, 8 * nb)
 

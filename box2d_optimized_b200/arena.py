@@ -196,7 +196,10 @@ def arena_from_scene(scene, max_contacts=None, device=0, num_worlds=1, copies=1)
     nb, nf, nq = len(b), len(fx["body"]), len(fx["quads"])
     if max_contacts is None:
         max_contacts = max(1024, 8 * nb * copies)
-    A = Arena(nb * copies, nf * copies, nq * copies, max_contacts, num_worlds=num_worlds, device=device)
+    jn = scene.joints()
+    nj = len(jn["bodies"])
+    A = Arena(nb * copies, nf * copies, nq * copies, max_contacts, num_worlds=num_worlds, device=device,
+              max_joints=max(nj * copies, 1))
     btype = b[:, 11].astype(np.int32)
     mass = p[:, 0]
     inertia_origin = p[:, 1]
@@ -223,5 +226,7 @@ def arena_from_scene(scene, max_contacts=None, device=0, num_worlds=1, copies=1)
         A.upload_shapes(fx["quads"], first=k * nq)
         A.upload_fixtures(k * nf, body=fx["body"] + k * nb, shape_off=fx["shape_off"] + k * nq, type_flags=tf,
                           filter=filt, material=fx["material"])
+        if nj:
+            A.upload_joints(jn["bodies"] + k * nb, jn["anchors"], jn["params"], first=k * nj)
     A.scene_inv = (inv_mass, inv_i)
     return A

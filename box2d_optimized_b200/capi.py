@@ -169,6 +169,8 @@ def _declare_shim(lib, prefix):
     g("scene_get_fixtures").argtypes = [C.c_void_p, i32p, i32p, i32p, i32p, f32p, i32p, f32p]
     g("scene_get_aabbs").argtypes = [C.c_void_p, f32p]
     g("scene_get_contacts").argtypes = [C.c_void_p, C.c_int, i32p, i32p, i32p, f32p, f32p]
+    g("scene_joint_count").argtypes = [C.c_void_p]
+    g("scene_get_joints").argtypes = [C.c_void_p, C.c_int, i32p, f32p, f32p]
 
 
 def load_gpu_scenes():

@@ -89,6 +89,15 @@ class _Scene:
             self._f("scene_get_aabbs")(self.h, capi.fp(out))
         return out
 
+    def joints(self):
+        """revolute joints: bodies [n,2], anchors [n,4], params [n,8] (include/b2cuda.h b2gJointArrays)"""
+        cap = max(self._f("scene_joint_count")(self.h), 1)
+        bodies = np.zeros((cap, 2), np.int32)
+        anchors = np.zeros((cap, 4), np.float32)
+        params = np.zeros((cap, 8), np.float32)
+        n = self._f("scene_get_joints")(self.h, cap, capi.ip(bodies), capi.fp(anchors), capi.fp(params))
+        return dict(bodies=bodies[:n], anchors=anchors[:n], params=params[:n])
+
     def contacts(self):
         cap = max(self.contact_count, 1)
         fa = np.zeros(cap, np.int32)

@@ -132,5 +132,33 @@ int SHIM(scene_get_contacts)(void* h, int cap, int* fixA, int* fixB, int* flags,
   return n;
 }
 
+int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->GetJointCount(); }
+// revolute joints in creation order: bodies[n][2], anchors[n][4] = localAnchorA.xy, localAnchorB.xy,
+// params[n][8] = referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
+// with flags 1 = enableLimit, 2 = enableMotor, 4 = collideConnected (include/b2cuda.h b2gJointArrays)
+int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float* params) {
+  Scene* s = static_cast<Scene*>(h);
+  std::vector<b2Joint*> js;
+  for (b2Joint* j = s->world->GetJointList(); j; j = j->GetNext()) js.push_back(j);
+  int n = 0;
+  for (auto it = js.rbegin(); it != js.rend() && n < cap; ++it) {  // the list is newest-first
+    b2Joint* j = *it;
+    if (j->GetType() != e_revoluteJoint) continue;
+    b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(j);
+    bodies[2 * n] = s->bodyIndex[r->GetBodyA()];
+    bodies[2 * n + 1] = s->bodyIndex[r->GetBodyB()];
+    anchors[4 * n] = r->GetLocalAnchorA().x; anchors[4 * n + 1] = r->GetLocalAnchorA().y;
+    anchors[4 * n + 2] = r->GetLocalAnchorB().x; anchors[4 * n + 3] = r->GetLocalAnchorB().y;
+    float* p = params + 8 * n;
+    p[0] = r->GetReferenceAngle(); p[1] = r->GetLowerLimit(); p[2] = r->GetUpperLimit();
+    p[3] = r->GetMaxMotorTorque(); p[4] = r->GetMotorSpeed();
+    uint32_t fl = (r->IsLimitEnabled() ? 1u : 0u) | (r->IsMotorEnabled() ? 2u : 0u) | (r->GetCollideConnected() ? 4u : 0u);
+    memcpy(&p[5], &fl, 4);
+    p[6] = p[7] = 0.0f;
+    ++n;
+  }
+  return n;
+}
+
 }  // extern "C"
 #endif
