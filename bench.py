@@ -68,7 +68,12 @@ WORKLOADS = {
     # BASELINE config 4 shape: motor-driven tumbler (benchmarks.h b3) with 500 boxes per world; the
     # scene is stepped to the state where every box has been spawned, then replicated per world
     "tumbler_worlds": ("tumbler", 500, 0, "256 independent 500-box tumbler worlds per GPU (128k bodies), one arena"),
+    # BASELINE config 5 shape: ONE world cut into x-slabs, one per GPU, ghost layer refreshed by a
+    # per-step NCCL halo exchange (strong scaling: the world is fixed, the slab shrinks with N)
+    "mixed_slab_400k": ("mixed", 400000, 12345, "one 400k-body world, x-slab per GPU, per-step NCCL halo exchange"),
+    "mixed_slab_1m": ("mixed", 1000000, 12345, "one 1M-body world, x-slab per GPU, per-step NCCL halo exchange"),
 }
+SLAB = {"mixed_slab_400k", "mixed_slab_1m"}
 WORLDS_PER_GPU = {"pyramid_worlds": 512, "tumbler_worlds": 256}
 PRESTEP = {"tumbler_worlds": 520}  # steps run through the drop-in API before the state is replicated
 
@@ -211,11 +216,31 @@ def main():
     nb = nb_world * copies
     cap_contacts = max(4096, 8 * nb)
 
+    slab_mode = args.workload in SLAB and world > 1
+    halo_bytes = 0
+    if slab_mode:
+        from box2d_optimized_b200.slab import SlabRank, exchange_distributed, make_slabs, scene_arrays
+        glob = scene_arrays(scene)
+        slabs, _, _ = make_slabs(glob, world, halo=3.0)
+        nb_total = nb_world
+        nb = slabs[rank].num_owned  # bodies this rank advances (ghosts are redundant work)
+        copies = 1
+
     def fresh_arena():
+        if slab_mode:
+            sr = SlabRank(glob, slabs[rank], device=local_rank, max_contacts=max(4096, 8 * len(slabs[rank].global_ids)))
+            sr.arena._slab = sr
+            return sr.arena
         A = arena_from_scene(scene, max_contacts=cap_contacts, device=local_rank, copies=copies,
                              num_worlds=copies)
         A.find_new_contacts()
         return A
+
+    def after_step(A):
+        # the once-per-step halo exchange of the slab decomposition (NCCL point-to-point)
+        if slab_mode:
+            A.synchronize()
+            exchange_distributed(A._slab)
 
     P = Arena.params()
     st = capi.StepStats()
@@ -226,7 +251,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
     for _ in range(args.warmup):
         A.step(P, st)
+        after_step(A)
     A.synchronize()
+    if slab_mode:
+        halo_bytes = A._slab.halo_bytes()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -241,7 +269,11 @@ def main():
             flush.zero_()  # evict the step's working set from L2 (outside the timed bracket)
         starts[k].record(ext)
         A.step(P, st)
-        ends[k].record(ext)
+        if slab_mode:
+            after_step(A)
+            ends[k].record()      # the exchange runs on torch's stream, after the arena's stream drained
+        else:
+            ends[k].record(ext)
         launches += st.num_launches
         contacts_seen.append(st.num_contacts)
         constraints_seen.append(st.num_constraints)
@@ -256,6 +288,7 @@ def main():
     A.set_kernel_timing(True)
     for _ in range(args.profile_steps):
         A.step(P, st)
+        after_step(A)
     kt = A.kernel_timing()
     A.set_kernel_timing(False)
     total_kernel_ms = sum(v[0] for v in kt.values()) or 1.0
@@ -286,6 +319,7 @@ def main():
     def e2e_step():
         B.upload_forces(hforce, 0, nb)                                   # H2D from pinned memory
         B.step(P, None)
+        after_step(B)
         capi.check(lib.b2g_download_body_state_async(B.h, 0, nb, hstate))  # D2H into pinned memory
         B.synchronize()
 
@@ -327,8 +361,11 @@ def main():
         line = {
             "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "bodies_per_world": nb_world, "worlds": per_gpu * world,
+            "higher_is_better": True, "scaling": "strong" if args.workload in SLAB else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "bodies_per_world": nb_world,
+                       "worlds": 1 if args.workload in SLAB else per_gpu * world,
+                       "halo_bytes_per_step_per_rank": halo_bytes,
                        "worlds_per_gpu": per_gpu, "contacts_mean": float(np.mean(contacts_seen)), "constraints_mean": float(np.mean(constraints_seen)),
                        "colours_max": int(max(colours_seen)), "velocity_iterations": 8, "position_iterations": 3,
                        "dt": 1.0 / 60.0, "sleeping": True, "continuous": False, "solver": "graph-coloured",

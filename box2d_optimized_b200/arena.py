@@ -129,6 +129,11 @@ class Arena:
     def set_profiling(self, on=True):
         self.lib.b2g_set_profiling(self.h, int(on))
 
+    def device_views(self):
+        v = capi.DeviceViews()
+        capi.check(self.lib.b2g_device_views(self.h, C.byref(v)), "b2g_device_views")
+        return v
+
     def set_kernel_timing(self, on=True):
         self.lib.b2g_set_kernel_timing(self.h, int(on))
 

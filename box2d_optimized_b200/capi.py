@@ -51,6 +51,11 @@ class JointArrays(C.Structure):
     _fields_ = [("bodies", i32p), ("anchors", f32p), ("params", f32p)]
 
 
+class DeviceViews(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("vel", C.c_void_p), ("xf", C.c_void_p), ("force", C.c_void_p),
+                ("flags", C.c_void_p), ("capacity", C.c_int32), ("device", C.c_int32)]
+
+
 class StepParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("velocity_iterations", C.c_int32), ("position_iterations", C.c_int32),
                 ("gravity_x", C.c_float), ("gravity_y", C.c_float), ("warm_starting", C.c_int32),
@@ -78,7 +83,7 @@ CUDA_SYMBOLS = [
     "b2g_download_body_state_async", "b2g_download_fixture_aabbs", "b2g_contact_count", "b2g_download_contacts",
     "b2g_upload_contact_overrides", "b2g_download_events", "b2g_synchronize", "b2g_stream", "b2g_set_profiling",
     "b2g_set_inv_dt0", "b2g_set_kernel_timing", "b2g_kernel_class_count", "b2g_kernel_class_name",
-    "b2g_get_kernel_timing", "b2g_host_alloc", "b2g_host_free", "b2g_compute_aabbs", "b2g_collide_pairs",
+    "b2g_get_kernel_timing", "b2g_device_views", "b2g_host_alloc", "b2g_host_free", "b2g_compute_aabbs", "b2g_collide_pairs",
     "b2g_find_pairs", "b2g_solve_sequential",
 ]
 
@@ -129,6 +134,7 @@ def load_cuda():
         lib.b2g_download_events.argtypes = [C.c_void_p, i32p, i32p, i32p, i32p, C.c_int32]
         lib.b2g_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         lib.b2g_set_inv_dt0.argtypes = [C.c_void_p, C.c_float]
+        lib.b2g_device_views.argtypes = [C.c_void_p, C.POINTER(DeviceViews)]
         lib.b2g_set_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
         lib.b2g_kernel_class_name.restype = C.c_char_p
         lib.b2g_kernel_class_name.argtypes = [C.c_int32]

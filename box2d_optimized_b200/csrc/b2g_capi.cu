@@ -1264,6 +1264,18 @@ extern "C" int b2g_download_events(b2gArena* A, int32_t* beginPairs, int32_t* be
   return B2G_OK;
 }
 
+extern "C" int b2g_device_views(b2gArena* A, b2gDeviceViews* out) {
+  if (!A || !out) return B2G_ERR_INVALID;
+  out->pos = A->pos;
+  out->vel = A->vel;
+  out->xf = A->xf;
+  out->force = A->force;
+  out->flags = A->bflags;
+  out->capacity = A->capBodies;
+  out->device = A->device;
+  return B2G_OK;
+}
+
 extern "C" int b2g_synchronize(b2gArena* A) {
   if (!A) return B2G_ERR_INVALID;
   CK(cudaSetDevice(A->device));

@@ -239,6 +239,22 @@ int b2g_upload_contact_overrides(b2gArena* arena, int32_t first, int32_t count,
 int b2g_download_events(b2gArena* arena, int32_t* begin_pairs, int32_t* begin_count, int32_t* end_pairs,
                         int32_t* end_count, int32_t capacity_each);
 
+/* Raw device addresses of the body state arrays ([capacity][4] float32 each, flags [capacity]
+ * uint32), for zero-copy interop on the same device: the slab decomposition of one large world
+ *  packs boundary bodies straight out of these arrays into its NCCL send buffers and
+ * scatters the received ghost states straight back in.  The caller must order its own accesses
+ * against the arena's stream (b2g_synchronize / b2g_stream). */
+typedef struct b2gDeviceViews {
+  void* pos;
+  void* vel;
+  void* xf;
+  void* force;
+  void* flags;
+  int32_t capacity;
+  int32_t device;
+} b2gDeviceViews;
+int b2g_device_views(b2gArena* arena, b2gDeviceViews* out);
+
 int b2g_synchronize(b2gArena* arena);
 /* cudaStream_t the arena launches on (for external CUDA-event timing). */
 void* b2g_stream(b2gArena* arena);
