@@ -354,6 +354,21 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     __syncthreads();
   }
   const int njTile = P.nj > 0 ? sJointCount : 0;
+  // the (few) non-empty parallel colours of this bin, so the pass loops do not walk all 24
+  __shared__ int usedS0[B2G_MAX_COLOURS], usedS1[B2G_MAX_COLOURS];
+  __shared__ int usedCount;
+  if (tid == 0) {
+    int k = 0;
+    for (int c = 0; c < B2G_MAX_COLOURS; ++c)
+      if (cstart[c] != cstart[c + 1]) {
+        usedS0[k] = cstart[c];
+        usedS1[k] = cstart[c + 1];
+        ++k;
+      }
+    usedCount = k;
+  }
+  __syncthreads();
+  const int nUsed = usedCount;
   order_bucket_by_key(cstart[B2G_MAX_COLOURS], cstart[B2G_MAX_COLOURS + 1], sortedList, orderScratch, C);
   const int cAll0 = cstart[0], cAll1 = cstart[B2G_MAX_COLOURS + 1];
   const TileBodies velAcc{T.vel, gvel};
@@ -396,9 +411,8 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
 
   // ---- phase 2: warm start, colour by colour ---------------------------------------------------
   if (P.warmStarting) {
-    for (int c = 0; c < B2G_MAX_COLOURS; ++c) {
-      int s0 = cstart[c], s1 = cstart[c + 1];
-      if (s0 == s1) continue;  // block-uniform
+    for (int k = 0; k < nUsed; ++k) {
+      int s0 = usedS0[k], s1 = usedS1[k];
       for (int s = s0 + tid; s < s1; s += nt) warm_start_constraint(S, s, velAcc);
       __syncthreads();
     }
@@ -430,9 +444,8 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
         for (int k = 0; k < njTile; ++k) joint_solve_velocity(J, sJoint[k], velAcc, P.h, P.invH);
       __syncthreads();
     }
-    for (int c = 0; c < B2G_MAX_COLOURS; ++c) {
-      int s0 = cstart[c], s1 = cstart[c + 1];
-      if (s0 == s1) continue;
+    for (int k = 0; k < nUsed; ++k) {
+      int s0 = usedS0[k], s1 = usedS1[k];
       for (int s = s0 + tid; s < s1; s += nt) solve_velocity_constraint(S, s, velAcc);
       __syncthreads();
     }
@@ -487,11 +500,16 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
 
   // ---- phase 6: position iterations with the per-island early exit (b2_island.cpp:391-409) --------
   for (int it = 0; it < P.posIters; ++it) {
-    for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {
-      int s0 = cstart[c], s1 = cstart[c + 1];
-      if (s0 == s1) continue;
-      int sBegin = s0 + tid, sStep = nt;
-      if (c == B2G_MAX_COLOURS) {  // overflow bucket: one thread, list order
+    for (int k = 0; k <= nUsed; ++k) {
+      int s0, s1, sBegin, sStep = nt;
+      if (k < nUsed) {
+        s0 = usedS0[k];
+        s1 = usedS1[k];
+        sBegin = s0 + tid;
+      } else {  // overflow bucket: one thread, list order
+        s0 = cstart[B2G_MAX_COLOURS];
+        s1 = cstart[B2G_MAX_COLOURS + 1];
+        if (s0 == s1) continue;
         sBegin = tid == 0 ? s0 : s1;
         sStep = 1;
       }
