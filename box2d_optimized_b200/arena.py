@@ -103,6 +103,17 @@ class Arena:
         a = capi.JointArrays(capi.ip(bodies), capi.fp(anchors), capi.fp(params))
         capi.check(self.lib.b2g_upload_joints(self.h, first, len(bodies), C.byref(a)), "b2g_upload_joints")
 
+    def upload_contacts(self, fix_a, fix_b, flags, manifold, material):
+        fix_a, fix_b, flags = i32(fix_a), i32(fix_b), u32(flags)
+        manifold, material = f32(manifold).reshape(-1, 16), f32(material).reshape(-1, 4)
+        a = capi.ContactArrays(capi.ip(fix_a), capi.ip(fix_b), capi.up(flags), capi.fp(manifold), capi.fp(material), None)
+        capi.check(self.lib.b2g_upload_contacts(self.h, len(fix_a), C.byref(a)), "b2g_upload_contacts")
+
+    def set_sequential_order(self, fix_a, fix_b):
+        fix_a, fix_b = i32(fix_a), i32(fix_b)
+        capi.check(self.lib.b2g_set_sequential_order(self.h, len(fix_a), capi.ip(fix_a), capi.ip(fix_b)),
+                   "b2g_set_sequential_order")
+
     def upload_forces(self, force_ptr, first, count):
         capi.check(self.lib.b2g_upload_forces(self.h, first, count, force_ptr), "b2g_upload_forces")
 

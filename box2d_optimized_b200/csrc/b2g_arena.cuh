@@ -126,6 +126,8 @@ struct b2gArena {
 
   // contacts
   ContactBuf cb[1];           // stable slots; nContacts = slot high-water mark, nAlive = live contacts
+  unsigned long long* orderKey;  // per slot: visiting order imposed for the next sequential step
+  int seqOrderActive;
   unsigned long long* seqKeys;  // [2][capContacts] scratch: key sort of the sequential mode's list
   uint8_t* persist;           // per slot: pair re-reported by this step's broadphase
   int* freeStack;             // free slots (LIFO)

@@ -237,6 +237,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   if (rc) return rc;
   CK(dalloc(&A->persist, nc));
   CK(dalloc(&A->seqKeys, (size_t)2 * nc));
+  CK(dalloc(&A->orderKey, nc));
   CK(dalloc(&A->freeStack, nc));
   CK(dalloc(&A->dFreeTop, 1));
   {
@@ -678,8 +679,14 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         numActive = A->hCounts->numActive;
         if (numActive > 0) {
           // contact slots are unordered; the sequential mode's list order is ascending pair key
-          LAUNCH(A, KC_COLOUR, numActive, k_gather_keys, div_up(numActive, 256), 256, numActive, A->activeList, C,
-                 A->seqKeys);
+          if (A->seqOrderActive) {  // explicit order imposed by b2g_set_sequential_order (this step only)
+            LAUNCH(A, KC_COLOUR, numActive, k_gather_order, div_up(numActive, 256), 256, numActive, A->activeList,
+                   A->orderKey, A->seqKeys);
+            A->seqOrderActive = 0;
+          } else {
+            LAUNCH(A, KC_COLOUR, numActive, k_gather_keys, div_up(numActive, 256), 256, numActive, A->activeList, C,
+                   A->seqKeys);
+          }
           size_t tb3 = A->cubTempBytes;
           CK(cub::DeviceRadixSort::SortPairs(A->cubTemp, tb3, A->seqKeys, A->seqKeys + A->capContacts, A->activeList,
                                              A->sortedList, numActive, 0, 64, A->stream));
@@ -1243,6 +1250,93 @@ extern "C" int b2g_upload_contact_overrides(b2gArena* A, int32_t first, int32_t 
   k_scatter_overrides<<<div_up(count, 256), 256, 0, A->stream>>>(count, dS.as<int>(), flags ? dF.as<uint32_t>() : nullptr,
                                                                 material ? dM.as<float4>() : nullptr, A->cb[0]);
   CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+__global__ void k_contacts_load(int n, const int* __restrict__ fa, const int* __restrict__ fb,
+                                const uint32_t* __restrict__ flags, const float4* __restrict__ man,
+                                const float4* __restrict__ material, const int* __restrict__ fBody, ContactBuf C,
+                                uint8_t* persist, ContactHash H) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = fa[i], b = fb[i];
+  unsigned long long key = ((unsigned long long)min(a, b) << 32) | (unsigned long long)max(a, b);
+  C.key[i] = key;
+  C.fix[i] = make_int2(a, b);
+  C.body[i] = make_int2(fBody[a], fBody[b]);
+  C.flags[i] = (flags[i] & (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) | B2G_CONTACT_ALIVE;
+  C.material[i] = material[i];
+  C.m0[i] = man[4 * i];
+  C.m1[i] = man[4 * i + 1];
+  C.m2[i] = man[4 * i + 2];
+  C.m3[i] = man[4 * i + 3];
+  C.colour[i] = -1;
+  persist[i] = 0;
+  hash_insert(H, key, i);
+}
+
+extern "C" int b2g_upload_contacts(b2gArena* A, int32_t count, const b2gContactArrays* s) {
+  if (!A || count < 0 || (count > 0 && (!s || !s->fixture_a || !s->fixture_b || !s->flags || !s->manifold || !s->material)))
+    return B2G_ERR_INVALID;
+  if (count > A->capContacts) {
+    set_err("b2g_upload_contacts", "max_contacts exceeded");
+    return B2G_ERR_CAPACITY;
+  }
+  CK(cudaSetDevice(A->device));
+  CK(cudaMemsetAsync(A->hash.keys, 0xff, (size_t)(A->hash.mask + 1) * 8, A->stream));
+  CK(cudaMemsetAsync(A->hash.vals, 0xff, (size_t)(A->hash.mask + 1) * 4, A->stream));
+  CK(cudaMemsetAsync(A->cb[0].flags, 0, (size_t)A->capContacts * 4, A->stream));
+  CK(cudaMemsetAsync(A->dFreeTop, 0, 4, A->stream));
+  if (count > 0) {
+    DevBuf dA, dB, dF, dM, dMat;
+    CK(dA.upload(s->fixture_a, (size_t)count * 4));
+    CK(dB.upload(s->fixture_b, (size_t)count * 4));
+    CK(dF.upload(s->flags, (size_t)count * 4));
+    CK(dM.upload(s->manifold, (size_t)count * 64));
+    CK(dMat.upload(s->material, (size_t)count * 16));
+    k_contacts_load<<<div_up(count, 256), 256, 0, A->stream>>>(count, dA.as<int>(), dB.as<int>(), dF.as<uint32_t>(),
+                                                               dM.as<float4>(), dMat.as<float4>(), A->fBody, A->cb[0],
+                                                               A->persist, A->hash);
+    CK(cudaStreamSynchronize(A->stream));
+  }
+  CK(cudaStreamSynchronize(A->stream));
+  A->nContacts = count;
+  A->nAlive = count;
+  A->tombstones = 0;
+  A->islandsValid = 0;
+  A->recolour = 1;
+  return B2G_OK;
+}
+
+__global__ void k_order_default(int nSlots, ContactBuf C, unsigned long long* orderKey) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nSlots) orderKey[j] = (1ull << 62) | (C.key[j] & ((1ull << 62) - 1ull));
+}
+__global__ void k_order_assign(int n, const int* __restrict__ fa, const int* __restrict__ fb, ContactHash H,
+                               unsigned long long* orderKey) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = fa[i], b = fb[i];
+  unsigned long long key = ((unsigned long long)min(a, b) << 32) | (unsigned long long)max(a, b);
+  int slot = hash_find(H, key);
+  if (slot >= 0) orderKey[slot] = (unsigned long long)i;
+}
+
+extern "C" int b2g_set_sequential_order(b2gArena* A, int32_t count, const int32_t* fa, const int32_t* fb) {
+  if (!A || count < 0 || (count > 0 && (!fa || !fb))) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  const int nSlots = A->nContacts;
+  if (nSlots > 0)
+    k_order_default<<<div_up(nSlots, 256), 256, 0, A->stream>>>(nSlots, A->cb[0], A->orderKey);
+  if (count > 0) {
+    DevBuf dA, dB;
+    CK(dA.upload(fa, (size_t)count * 4));
+    CK(dB.upload(fb, (size_t)count * 4));
+    k_order_assign<<<div_up(count, 256), 256, 0, A->stream>>>(count, dA.as<int>(), dB.as<int>(), A->hash, A->orderKey);
+    CK(cudaStreamSynchronize(A->stream));
+  }
+  CK(cudaStreamSynchronize(A->stream));
+  A->seqOrderActive = 1;
   return B2G_OK;
 }
 

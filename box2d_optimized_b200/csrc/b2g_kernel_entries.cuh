@@ -30,6 +30,27 @@ extern "C" int b2g_compute_aabbs(int32_t device, int32_t n, const int32_t* type,
   return B2G_OK;
 }
 
+__global__ void k_entry_rotations(int n, const float* __restrict__ angle, float2* sc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rot q = rot_set(angle[i]);
+  sc[i] = make_float2(q.s, q.c);
+}
+
+extern "C" int b2g_rotations(int32_t device, int32_t n, const float* angle, float* sin_cos) {
+  if (n < 0 || !angle || !sin_cos) return B2G_ERR_INVALID;
+  int rc = use_device(device);
+  if (rc) return rc;
+  if (n == 0) return B2G_OK;
+  DevBuf dA, dR;
+  CK(dA.upload(angle, (size_t)n * 4));
+  CK(dR.alloc((size_t)n * 8));
+  k_entry_rotations<<<div_up(n, 256), 256>>>(n, dA.as<float>(), dR.as<float2>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(sin_cos, dR.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return B2G_OK;
+}
+
 __global__ void __launch_bounds__(128)
 k_entry_collide(int n, const int* __restrict__ typeA, const int* __restrict__ offA, const float4* __restrict__ xfA,
                 const int* __restrict__ typeB, const int* __restrict__ offB, const float4* __restrict__ xfB,

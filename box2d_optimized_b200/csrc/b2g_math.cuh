@@ -103,18 +103,51 @@ B2G_HD Xf xf_from4(float4 v) {
 }
 B2G_HD float4 xf_to4(Xf T) { return make_float4(T.p.x, T.p.y, T.q.s, T.q.c); }
 // b2Rot::Set (b2_math.h:313-318)
-// The reference calls glibc's sinf/cosf, which evaluate in double precision and round once
-// (error < 0.51 ulp, i.e. correctly rounded except in rare near-halfway cases).  CUDA's float
-// sinf/cosf differ from that by 1-2 ulp, enough to flip the solver's branchy thresholds
-// (block-solver condition number, restitution threshold) and break iterate parity, so the device
-// takes the same route: double-precision sincos, rounded once to float.
+// The reference calls the host libm's sinf/cosf.  CUDA's float sinf/cosf differ from those by 1-2
+// ulp, and even a correctly rounded result differs from glibc's in ~1 % of arguments; one ulp in
+// a rotation is amplified by ill-conditioned resting contacts into 1e-4-level velocity differences
+// and can flip the solver's branchy thresholds.  So the device evaluates the SAME function glibc
+// (>= 2.28, x86-64 FMA variant; the published ARM optimized-routines sincosf) evaluates: argument
+// reduction by pi/2 in double with a 2^24-prescaled quadrant, a degree-7 sine / degree-8 cosine
+// minimax polynomial in double with fused multiply-adds, one rounding to float.  Checked here
+// bit-for-bit against glibc 2.39 on 3e8 arguments (tests/test_oracle_port.py runs a sample).
+// |angle| >= 120 (glibc's large-argument path) falls back to double sincos rounded once.
 B2G_HD Rot rot_set(float angle) {
   Rot q;
 #ifdef __CUDA_ARCH__
-  double sd, cd;
-  sincos((double)angle, &sd, &cd);
-  q.s = (float)sd;
-  q.c = (float)cd;
+  float ay = fabsf(angle);
+  if (ay < 0x1p-12f) {
+    q.s = angle;
+    q.c = 1.0f;
+    return q;
+  }
+  if (!(ay < 120.0f)) {
+    double sd, cd;
+    sincos((double)angle, &sd, &cd);
+    q.s = (float)sd;
+    q.c = (float)cd;
+    return q;
+  }
+  double x = (double)angle;
+  int n = 0;
+  if (ay >= 0.75f) {  // glibc compares the top 12 bits with those of pi/4
+    double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+  }
+  double cs = (n & 2) ? -1.0 : 1.0;  // second table: negated cosine polynomial
+  double x2 = __dmul_rn(x, x);
+  if (((n + 1) & 2)) x = -x;         // sign[n & 3] = {1, -1, -1, 1}
+  double x4 = __dmul_rn(x2, x2), x3 = __dmul_rn(x2, x);
+  double c2 = __fma_rn(x2, cs * 0x1.99343027bf8c3p-16, cs * -0x1.6c087e89a359dp-10);
+  double s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+  double c1 = __fma_rn(x2, cs * -0x1.ffffffd0c621cp-2, cs);
+  double x5 = __dmul_rn(x3, x2), x6 = __dmul_rn(x4, x2);
+  double s = __fma_rn(x3, -0x1.555545995a603p-3, x);
+  double c = __fma_rn(x4, cs * 0x1.55553e1068f19p-5, c1);
+  float sv = (float)__fma_rn(x5, s1, s), cv = (float)__fma_rn(x6, c2, c);
+  q.s = (n & 1) ? cv : sv;
+  q.c = (n & 1) ? sv : cv;
 #else
   q.s = sinf(angle);
   q.c = cosf(angle);

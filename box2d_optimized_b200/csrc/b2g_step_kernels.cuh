@@ -406,6 +406,12 @@ __global__ void k_gather_keys(int n, const int* __restrict__ list, ContactBuf C,
   if (s < n) keys[s] = C.key[list[s]];
 }
 
+__global__ void k_gather_order(int n, const int* __restrict__ list, const unsigned long long* __restrict__ orderKey,
+                               unsigned long long* keys) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) keys[s] = orderKey[list[s]];
+}
+
 // self-check used by the tests: counts pairs of same-colour constraints that share a movable body
 __global__ void k_colour_validate(int n, const int* __restrict__ sortedList, ContactBuf C,
                                   const float4* __restrict__ mass, int* bodyStamp, int* violations) {

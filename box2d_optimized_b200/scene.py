@@ -149,6 +149,15 @@ class RefScene(_Scene):
     def inv_dt0(self):
         return float(self.lib.b2ref_get_inv_dt0(self.h))
 
+    def step_recording_order(self):
+        """one Step with a PostSolve tap: returns the ordered (fixA, fixB) pairs in the order the
+        reference's island solver visited them"""
+        cap = max(self.contact_count, 1) + 16
+        fa = np.zeros(cap, np.int32)
+        fb = np.zeros(cap, np.int32)
+        n = self.lib.b2ref_step_recording_order(self.h, cap, capi.ip(fa), capi.ip(fb))
+        return fa[:n], fb[:n]
+
     def sleep_times(self):
         out = np.zeros(self.body_count, np.float32)
         self.lib.b2ref_get_sleep_times(self.h, capi.fp(out))

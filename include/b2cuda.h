@@ -233,6 +233,19 @@ int b2g_download_contacts(b2gArena* arena, int32_t first, int32_t count, const b
 int b2g_upload_contact_overrides(b2gArena* arena, int32_t first, int32_t count,
                                  const uint32_t* flags, const float* material);
 
+/* Replaces the whole contact set with `count` contacts given in the b2gContactArrays layout
+ * (fixture_a/fixture_b as ordered A,B; flags = B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED;
+ * manifold incl. warm-start impulses; material).  Lets a host mirror an existing b2World — its
+ * contact list (b2_contact_manager.h:60-76) — into the arena mid-simulation; the parity tests use
+ * it to start every step from the reference's exact state. */
+int b2g_upload_contacts(b2gArena* arena, int32_t count, const b2gContactArrays* src);
+
+/* B2G_SOLVER_SEQUENTIAL visits constraints in ascending pair-key order by default.  This call
+ * imposes an explicit order for the NEXT step only: the listed ordered pairs first, in the given
+ * order (e.g. the reference's island order as reported by b2ContactListener::PostSolve,
+ * b2_island.cpp:621-647), every other constraint after them by pair key. */
+int b2g_set_sequential_order(b2gArena* arena, int32_t count, const int32_t* fixture_a, const int32_t* fixture_b);
+
 /* b2ContactListener::BeginContact / EndContact (b2_contact.cpp:197-204,
  * b2_contact_manager.cpp:48-51) recorded by the last step when record_events was set:
  * each event = fixtureA, fixtureB.  Returns the number available through *count. */
@@ -279,6 +292,10 @@ int b2g_host_free(void* p);
  * arrays.  They exist so the parity tests can feed the GPU the oracle's exact ordered inputs
  * (SURVEY.md §7 "Hard parts": A/B order and solver order are traversal dependent).
  * ---------------------------------------------------------------------------------------- */
+
+/* b2Rot::Set (b2_math.h:313-318): angle[n] -> sin_cos[n][2].  The device evaluates the host
+ * libm's sinf/cosf algorithm so that body transforms match the reference bit for bit. */
+int b2g_rotations(int32_t device, int32_t n, const float* angle, float* sin_cos);
 
 /* b2Fixture::UpdateAABB -> b2{Polygon,Circle,Edge}Shape::ComputeAABB
  * (b2_fixture.cpp:138-140, b2_polygon_shape.cpp:373-388, b2_circle_shape.cpp:91-96,

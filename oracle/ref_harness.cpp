@@ -166,6 +166,32 @@ void b2ref_get_sleep_times(void* h, float* out) {
   for (size_t i = 0; i < s->bodies.size(); ++i) out[i] = s->bodies[i]->m_sleepTime;
 }
 
+// one b2World::Step with a PostSolve tap: the island solver's visiting order (SURVEY Appendix C:
+// PostSolve order IS the solver order).  Returns the number of solved contacts.
+namespace {
+struct OrderTap : b2ContactListener {
+  Scene* scene;
+  std::vector<std::pair<int, int>> order;
+  void PostSolve(b2Contact* c, const b2ContactImpulse*) override {
+    order.push_back(std::make_pair(scene->fixtureIndex[c->GetFixtureA()], scene->fixtureIndex[c->GetFixtureB()]));
+  }
+};
+}  // namespace
+int b2ref_step_recording_order(void* h, int cap, int* fixA, int* fixB) {
+  Scene* s = static_cast<Scene*>(h);
+  OrderTap tap;
+  tap.scene = s;
+  s->world->SetContactListener(&tap);
+  s->step();
+  s->world->SetContactListener(nullptr);
+  int n = (int)tap.order.size() < cap ? (int)tap.order.size() : cap;
+  for (int i = 0; i < n; ++i) {
+    fixA[i] = tap.order[i].first;
+    fixB[i] = tap.order[i].second;
+  }
+  return (int)tap.order.size();
+}
+
 // b2ContactSolver on explicit arrays, driven as b2Island::Solve drives it (b2_island.cpp:306-409).
 // Same signature and array layouts as b2g_solve_sequential in include/b2cuda.h (minus `device`).
 int b2ref_solve(int nb, float* pos, float* vel, const float* mass, int nc, const int* index, float* manifold,
