@@ -96,12 +96,19 @@ class Arena:
         quads = f32(quads).reshape(-1, 4)
         capi.check(self.lib.b2g_upload_shapes(self.h, first, len(quads), capi.fp(quads)), "b2g_upload_shapes")
 
-    def upload_joints(self, bodies, anchors, params, first=0):
+    def upload_joints(self, bodies, anchors, params, first=0, state=None):
         bodies = i32(bodies).reshape(-1, 2)
         anchors = f32(anchors).reshape(-1, 4)
         params = f32(params).reshape(-1, 8)
-        a = capi.JointArrays(capi.ip(bodies), capi.fp(anchors), capi.fp(params))
+        state = None if state is None else f32(state).reshape(-1, 5)
+        a = capi.JointArrays(capi.ip(bodies), capi.fp(anchors), capi.fp(params), None if state is None else capi.fp(state))
         capi.check(self.lib.b2g_upload_joints(self.h, first, len(bodies), C.byref(a)), "b2g_upload_joints")
+
+    def download_joints(self, count, first=0):
+        """accumulated joint impulses [count, 5] = impulse.xy, motor, lower, upper"""
+        state = np.zeros((count, 5), np.float32)
+        capi.check(self.lib.b2g_download_joints(self.h, first, count, capi.fp(state)), "b2g_download_joints")
+        return state
 
     def upload_contacts(self, fix_a, fix_b, flags, manifold, material):
         fix_a, fix_b, flags = i32(fix_a), i32(fix_b), u32(flags)

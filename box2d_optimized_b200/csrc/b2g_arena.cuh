@@ -68,6 +68,7 @@ struct b2gArena {
   int nBodies, nFixtures, nJoints, nContacts;
   int fixBits;        // bits per fixture index in the pair key
   int aabbAllDirty;   // recompute static AABBs too (after fixture / body upload)
+  int newFixtures;    // b2World::m_newContacts: fixtures were added, the next step starts with FindNewContacts
   int bvhLeaves, bvhAge;  // leaves of the current LBVH topology, steps since it was built
   int recolour;       // drop persistent colours (after mass / type edits)
   int roundsHint;     // colouring rounds to launch before the first check

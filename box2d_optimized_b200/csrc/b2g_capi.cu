@@ -387,6 +387,7 @@ extern "C" int b2g_upload_fixtures(b2gArena* A, int32_t first, int32_t count, co
   CK(cudaStreamSynchronize(A->stream));
   if (first + count > A->nFixtures) A->nFixtures = first + count;
   A->aabbAllDirty = 1;
+  A->newFixtures = 1;
   A->islandsValid = 0;
   return B2G_OK;
 }
@@ -401,6 +402,7 @@ extern "C" int b2g_upload_shapes(b2gArena* A, int32_t first, int32_t count, cons
   UP((float*)A->shapes, quads, 4, float);
   CK(cudaStreamSynchronize(A->stream));
   A->aabbAllDirty = 1;
+  A->newFixtures = 1;
   return B2G_OK;
 }
 
@@ -426,13 +428,41 @@ extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, cons
                        cudaMemcpyHostToDevice, A->stream));
     CK(cudaMemcpyAsync((float*)A->jParams1 + (size_t)first * 4, p1.data(), p1.size() * sizeof(float),
                        cudaMemcpyHostToDevice, A->stream));
-    CK(cudaMemsetAsync((float*)A->jState + (size_t)first * 4, 0, (size_t)count * 4 * sizeof(float), A->stream));
-    CK(cudaMemsetAsync(A->jUpper + first, 0, (size_t)count * sizeof(float), A->stream));
     CK(cudaStreamSynchronize(A->stream));
   }
-  CK(cudaStreamSynchronize(A->stream));
+  {
+    std::vector<float> st((size_t)count * 4, 0.0f), up((size_t)count, 0.0f);
+    if (s->state) {
+      for (int i = 0; i < count; ++i) {
+        for (int k = 0; k < 4; ++k) st[(size_t)i * 4 + k] = s->state[(size_t)i * 5 + k];
+        up[i] = s->state[(size_t)i * 5 + 4];
+      }
+    }
+    if (s->state || s->params) {  // a joint created by this call starts from zero impulses
+      CK(cudaMemcpyAsync((float*)A->jState + (size_t)first * 4, st.data(), st.size() * sizeof(float),
+                         cudaMemcpyHostToDevice, A->stream));
+      CK(cudaMemcpyAsync(A->jUpper + first, up.data(), up.size() * sizeof(float), cudaMemcpyHostToDevice, A->stream));
+    }
+    CK(cudaStreamSynchronize(A->stream));
+  }
   if (first + count > A->nJoints) A->nJoints = first + count;
   A->islandsValid = 0;
+  return B2G_OK;
+}
+
+extern "C" int b2g_download_joints(b2gArena* A, int32_t first, int32_t count, float* state) {
+  if (!A || !state || first < 0 || count < 0 || first + count > A->nJoints) return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
+  CK(cudaSetDevice(A->device));
+  std::vector<float> st((size_t)count * 4), up((size_t)count);
+  CK(cudaMemcpyAsync(st.data(), (float*)A->jState + (size_t)first * 4, st.size() * sizeof(float),
+                     cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemcpyAsync(up.data(), A->jUpper + first, up.size() * sizeof(float), cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  for (int i = 0; i < count; ++i) {
+    for (int k = 0; k < 4; ++k) state[(size_t)i * 5 + k] = st[(size_t)i * 4 + k];
+    state[(size_t)i * 5 + 4] = up[i];
+  }
   return B2G_OK;
 }
 
@@ -476,6 +506,7 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
   ContactBuf& C = A->cb[0];
   const int nSlots = A->nContacts;  // slot high-water mark
   int nNew = 0;
+  A->newFixtures = 0;
   if (nf > 0) {
     // The LBVH topology is rebuilt (Morton sort + Karras build) when fixtures were added / edited
     // or every B2G_BVH_REBUILD_PERIOD steps; in between only the boxes are refit.  The reported
@@ -979,6 +1010,13 @@ extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
   if (rc0) return rc0;
   CK(cudaSetDevice(A->device));
   A->launchesAtStepStart = A->launches;
+  if (A->newFixtures) {
+    // b2World::Step starts with FindNewContacts when fixtures were added (m_newContacts,
+    // b2_world.cpp:1114-1122); this also fills the fixture radii the solver reads
+    CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
+    int rcn = find_new_contacts(A, 0);
+    if (rcn) return rcn;
+  }
   const int nc = A->nContacts;
   ContactBuf& C = A->cb[0];
   CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));

@@ -43,6 +43,8 @@ struct b2WorldImpl {
   int32 bodyDirtyLo = INT32_MAX, bodyDirtyHi = 0;
   int32 fixtureDirtyLo = INT32_MAX, fixtureDirtyHi = 0;
   bool jointsDirty = false;
+  bool jointsStale = false;    // device has newer joint impulses than the host copies
+  int32 jointsOnDevice = 0;    // joints the arena holds, in the order of `joints` at the last flush
   bool bodiesStale = false;    // device has newer body state than the host copies
   bool contactsStale = true;   // host contact list does not reflect the device
   bool profiling = false;
@@ -65,6 +67,7 @@ struct b2WorldImpl {
   void ensureArena();
   void flush();
   void pullBodies();
+  void pullJoints();
   void pullContacts();
   b2Contact* findContact(int32 fa, int32 fb);
   void pushContactOverrides();
@@ -116,6 +119,7 @@ void b2WorldImpl::ensureArena() {
   fixtureDirtyLo = 0;
   fixtureDirtyHi = needFixtures;
   jointsDirty = needJoints > 0;
+  jointsOnDevice = 0;
   world->m_newContacts = true;
 }
 
@@ -192,7 +196,7 @@ void b2WorldImpl::flush() {
   if (jointsDirty) {
     int32 n = (int32)joints.size();
     std::vector<int32_t> jb((size_t)n * 2);
-    std::vector<float> anchors((size_t)n * 4), params((size_t)n * 8, 0.0f);
+    std::vector<float> anchors((size_t)n * 4), params((size_t)n * 8, 0.0f), state((size_t)n * 5);
     for (int32 k = 0; k < n; ++k) {
       b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(joints[k]);
       jb[(size_t)k * 2] = j->m_bodyA->m_index;
@@ -204,11 +208,33 @@ void b2WorldImpl::flush() {
       p[4] = j->m_motorSpeed;
       uint32_t fl = (j->m_enableLimit ? 1u : 0u) | (j->m_enableMotor ? 2u : 0u) | (j->m_collideConnected ? 4u : 0u);
       memcpy(&p[5], &fl, 4);
+      float* st = &state[(size_t)k * 5];
+      st[0] = j->m_impulse.x; st[1] = j->m_impulse.y; st[2] = j->m_motorImpulse;
+      st[3] = j->m_lowerImpulse; st[4] = j->m_upperImpulse;
     }
     b2gJointArrays a;
-    a.bodies = jb.data(); a.anchors = anchors.data(); a.params = params.data();
+    a.bodies = jb.data(); a.anchors = anchors.data(); a.params = params.data(); a.state = state.data();
     if (n > 0) b2gCheck(b2g_upload_joints(arena, 0, n, &a), "b2g_upload_joints");
+    jointsOnDevice = n;
     jointsDirty = false;
+  }
+}
+
+// every site that edits the joint table calls this first, so `joints` and the device agree on order
+void b2WorldImpl::pullJoints() {
+  if (!jointsStale || !arena) return;
+  jointsStale = false;
+  int32 n = std::min((int32)joints.size(), jointsOnDevice);
+  if (n == 0) return;
+  std::vector<float> state((size_t)n * 5);
+  b2gCheck(b2g_download_joints(arena, 0, n, state.data()), "b2g_download_joints");
+  for (int32 k = 0; k < n; ++k) {
+    b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(joints[k]);
+    const float* st = &state[(size_t)k * 5];
+    j->m_impulse.Set(st[0], st[1]);
+    j->m_motorImpulse = st[2];
+    j->m_lowerImpulse = st[3];
+    j->m_upperImpulse = st[4];
   }
 }
 
@@ -477,6 +503,7 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
             (int)def->type);
     return nullptr;
   }
+  m_impl->pullJoints();
   b2RevoluteJoint* j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
   j->m_index = (int32)m_impl->joints.size();
   m_impl->joints.push_back(j);
@@ -504,6 +531,7 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
 
 void b2World::DestroyJoint(b2Joint* j) {
   if (IsLocked() || !j) return;
+  m_impl->pullJoints();
   if (j->m_prev) j->m_prev->m_next = j->m_next;
   if (j->m_next) j->m_next->m_prev = j->m_prev;
   if (j == m_jointList) m_jointList = j->m_next;
@@ -611,6 +639,7 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
   for (b2Contact* c : I->graveyard) delete c;
   I->graveyard.clear();
   I->bodiesStale = true;
+  I->jointsStale = true;
   I->contactsStale = true;
   if (I->profiling) {
     m_profile.step = I->lastStats.ms_step;
@@ -1105,6 +1134,59 @@ b2RevoluteJoint::b2RevoluteJoint(const b2RevoluteJointDef* def) : b2Joint(def) {
   m_motorSpeed = def->motorSpeed;
   m_enableLimit = def->enableLimit;
   m_enableMotor = def->enableMotor;
+  m_impulse.SetZero();
+  m_motorImpulse = 0.0f;
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+}
+void b2RevoluteJoint::Touch() {
+  b2WorldImpl* I = m_bodyA->GetWorld()->GetImpl();
+  I->pullJoints();
+  m_bodyA->SetAwake(true);
+  m_bodyB->SetAwake(true);
+  I->jointsDirty = true;
+}
+b2Vec2 b2RevoluteJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_impulse;
+}
+float b2RevoluteJoint::GetReactionTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * (m_motorImpulse + m_lowerImpulse - m_upperImpulse);
+}
+float b2RevoluteJoint::GetMotorTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_motorImpulse;
+}
+void b2RevoluteJoint::EnableLimit(bool flag) {
+  if (flag == m_enableLimit) return;
+  Touch();
+  m_enableLimit = flag;
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+}
+void b2RevoluteJoint::SetLimits(float lower, float upper) {
+  if (lower == m_lowerAngle && upper == m_upperAngle) return;
+  Touch();
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+  m_lowerAngle = lower;
+  m_upperAngle = upper;
+}
+void b2RevoluteJoint::EnableMotor(bool flag) {
+  if (flag == m_enableMotor) return;
+  Touch();
+  m_enableMotor = flag;
+}
+void b2RevoluteJoint::SetMotorSpeed(float speed) {
+  if (speed == m_motorSpeed) return;
+  Touch();
+  m_motorSpeed = speed;
+}
+void b2RevoluteJoint::SetMaxMotorTorque(float torque) {
+  if (torque == m_maxMotorTorque) return;
+  Touch();
+  m_maxMotorTorque = torque;
 }
 b2Vec2 b2RevoluteJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
 b2Vec2 b2RevoluteJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }

@@ -158,6 +158,13 @@ class RefScene(_Scene):
         n = self.lib.b2ref_step_recording_order(self.h, cap, capi.ip(fa), capi.ip(fb))
         return fa[:n], fb[:n]
 
+    def joint_state(self):
+        """accumulated impulses of the revolute joints [n, 5] (white-box: b2_revolute_joint.h:178-181)"""
+        n = self.lib.b2ref_scene_joint_count(self.h)
+        out = np.zeros((max(n, 1), 5), np.float32)
+        n = self.lib.b2ref_get_joint_state(self.h, n, capi.fp(out))
+        return out[:n]
+
     def sleep_times(self):
         out = np.zeros(self.body_count, np.float32)
         self.lib.b2ref_get_sleep_times(self.h, capi.fp(out))

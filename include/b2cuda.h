@@ -146,11 +146,15 @@ typedef struct b2gContactArrays {
  *   anchors [n][4] = localAnchorA.xy, localAnchorB.xy
  *   params  [n][8] = referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed,
  *                    bits(flags: 1 enableLimit, 2 enableMotor, 4 collideConnected), 0, 0
+ *   state   [n][5] = m_impulse.x, m_impulse.y, m_motorImpulse, m_lowerImpulse, m_upperImpulse
+ *                    (include/box2d/b2_revolute_joint.h:178-181), the warm-start accumulators.
+ *                    NULL on upload = start from zero, as b2RevoluteJoint's constructor does.
  */
 typedef struct b2gJointArrays {
   int32_t* bodies;
   float* anchors;
   float* params;
+  float* state;
 } b2gJointArrays;
 
 /* Per-step parameters = b2TimeStep (include/box2d/b2_time_step.h:39-48) + the world
@@ -196,6 +200,10 @@ int b2g_upload_fixtures(b2gArena* arena, int32_t first, int32_t count, const b2g
 int b2g_upload_shapes(b2gArena* arena, int32_t first_quad, int32_t count_quads, const float* quads);
 /* b2World::CreateJoint for revolute joints (b2_world.cpp:268-323). */
 int b2g_upload_joints(b2gArena* arena, int32_t first, int32_t count, const b2gJointArrays* src);
+/* The joints' accumulated impulses after the last step, state[count][5] as above
+ * (b2RevoluteJoint::GetReactionForce / GetReactionTorque / GetMotorTorque read them,
+ * b2_revolute_joint.cpp:333-342, 374-377). */
+int b2g_download_joints(b2gArena* arena, int32_t first, int32_t count, float* state);
 /* Truncate counts (b2World::DestroyBody of trailing bodies; full compaction is host-side). */
 int b2g_set_counts(b2gArena* arena, int32_t num_bodies, int32_t num_fixtures, int32_t num_joints);
 

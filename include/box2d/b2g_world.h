@@ -392,6 +392,8 @@ class b2Joint {
   b2Body* GetBodyB() { return m_bodyB; }
   virtual b2Vec2 GetAnchorA() const = 0;
   virtual b2Vec2 GetAnchorB() const = 0;
+  virtual b2Vec2 GetReactionForce(float inv_dt) const = 0;
+  virtual float GetReactionTorque(float inv_dt) const = 0;
   b2Joint* GetNext() { return m_next; }
   const b2Joint* GetNext() const { return m_next; }
   b2JointUserData& GetUserData() { return m_userData; }
@@ -430,6 +432,16 @@ class b2RevoluteJoint : public b2Joint {
   float GetMaxMotorTorque() const { return m_maxMotorTorque; }
   float GetLowerLimit() const { return m_lowerAngle; }
   float GetUpperLimit() const { return m_upperAngle; }
+  // b2_revolute_joint.cpp:333-342, 364-447: reactions read the impulses the device accumulated in
+  // the last step; setters wake both bodies and take effect at the next Step
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  float GetMotorTorque(float inv_dt) const;
+  void EnableLimit(bool flag);
+  void SetLimits(float lower, float upper);
+  void EnableMotor(bool flag);
+  void SetMotorSpeed(float speed);
+  void SetMaxMotorTorque(float torque);
 
  protected:
   friend class b2World;
@@ -444,6 +456,12 @@ class b2RevoluteJoint : public b2Joint {
   bool m_enableMotor;
   float m_motorSpeed;
   float m_maxMotorTorque;
+  // host copies of the warm-start accumulators, refreshed lazily from the device
+  mutable b2Vec2 m_impulse;
+  mutable float m_motorImpulse;
+  mutable float m_lowerImpulse;
+  mutable float m_upperImpulse;
+  void Touch();  // pull the accumulators, wake both bodies, mark the joint table dirty
 };
 
 // ---- callbacks (b2_world_callbacks.h) ---------------------------------------------------------

@@ -166,6 +166,22 @@ void b2ref_get_sleep_times(void* h, float* out) {
   for (size_t i = 0; i < s->bodies.size(); ++i) out[i] = s->bodies[i]->m_sleepTime;
 }
 
+// revolute joints in creation order (the order of scene_get_joints): out[n][5] = m_impulse.xy,
+// m_motorImpulse, m_lowerImpulse, m_upperImpulse (b2_revolute_joint.h:178-181).  Returns n.
+int b2ref_get_joint_state(void* h, int cap, float* out) {
+  Scene* s = static_cast<Scene*>(h);
+  std::vector<b2Joint*> js;
+  for (b2Joint* j = s->world->GetJointList(); j; j = j->GetNext()) js.push_back(j);
+  int n = 0;
+  for (auto it = js.rbegin(); it != js.rend() && n < cap; ++it) {
+    if ((*it)->GetType() != e_revoluteJoint) continue;
+    b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(*it);
+    float* o = out + 5 * n++;
+    o[0] = r->m_impulse.x; o[1] = r->m_impulse.y; o[2] = r->m_motorImpulse; o[3] = r->m_lowerImpulse; o[4] = r->m_upperImpulse;
+  }
+  return n;
+}
+
 // one b2World::Step with a PostSolve tap: the island solver's visiting order (SURVEY Appendix C:
 // PostSolve order IS the solver order).  Returns the number of solved contacts.
 namespace {

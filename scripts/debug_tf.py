@@ -4,19 +4,31 @@ import util
 from box2d_optimized_b200 import capi, Arena, arena_from_scene, RefScene
 from test_world_step_parity import mirror_reference_state
 name, size, seed, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-ref = RefScene(name, size, seed); ref.step(1)
+ref = RefScene(name, size, seed); ref.step(size + 2 if name == "tumbler" else 1)
 A = arena_from_scene(ref, max_contacts=max(4096, 16 * ref.body_count))
 params, inv = ref.body_params(), ref.body_inv()
-P = Arena.params(solver_mode=capi.SOLVER_SEQUENTIAL); stats = capi.StepStats()
+import os
+PI = int(os.environ.get("POSITERS", "3"))
+ref.set_iterations(8, PI)
+P = Arena.params(solver_mode=capi.SOLVER_SEQUENTIAL, pos_iters=PI); stats = capi.StepStats()
 fixbody = ref.fixtures()["body"]
+import os
+fresh = int(os.environ.get("FRESH", "-1"))
 for k in range(steps):
+    if k == fresh:
+        A.close(); A = arena_from_scene(ref, max_contacts=max(4096, 16 * ref.body_count)); print("fresh arena at", k)
     before = mirror_reference_state(A, ref, params, inv)
     b0 = ref.bodies()
     fa, fb = ref.step_recording_order(); A.set_sequential_order(fa, fb); A.step(P, stats)
+    if stats.num_constraints != len(fa): print("step", k, "constraints", stats.num_constraints, "ref", len(fa))
+    cg, cr = A.download_contacts(), ref.contacts()
+    sg, sr = util.pair_set(cg["fix_a"], cg["fix_b"]), util.pair_set(cr["fix_a"], cr["fix_b"])
+    if sg != sr: print("step", k, "pairs gpu-only", sorted(sg - sr), "ref-only", sorted(sr - sg))
     rb = ref.bodies(); gb = A.download_bodies(what=("pos", "vel", "flags", "force"))
     ev = np.abs(gb["vel"][:, :3] - rb[:, 7:10]) / np.maximum(1, np.abs(rb[:, 7:10]))
     ep = np.abs(gb["pos"][:, :3] - rb[:, 4:7]) / np.maximum(1, np.abs(rb[:, 4:7]))
     if ev.max() > 2e-5 or ep.max() > 2e-5:
-        i = int(np.argmax(ev.max(1)))
+        print("bodies with error", np.nonzero((ev.max(1) > 2e-5) | (ep.max(1) > 2e-5))[0])
+        i = int(np.argmax(np.maximum(ev.max(1), ep.max(1))))
         nc = [(int(a), int(b)) for a, b in zip(fa, fb) if fixbody[a] == i or fixbody[b] == i]
         print(f"step {k} body {i} type {rb[i,11]} ev {ev[i]} ep {ep[i]} gpu vel {gb['vel'][i,:3]} ref vel {rb[i,7:10]} before vel {b0[i,7:10]} a {b0[i,6]} constraints {nc}")

@@ -214,6 +214,63 @@ static void body_list_order() {
   CHECK(world.GetBodyCount() == 3);
 }
 
+// revolute joint: reactions, motor and limit setters (b2_revolute_joint.cpp:333-447)
+static void revolute_joint_api() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  bd.position.Set(0.0f, -2.0f);  // hangs straight down from the pivot at the origin
+  b2Body* rod = world.CreateBody(&bd);
+  b2PolygonShape box;
+  box.SetAsBox(0.1f, 2.0f);
+  rod->CreateFixture(&box, 1.0f);  // mass 0.8
+  b2RevoluteJointDef jd;
+  jd.Initialize(ground, rod, b2Vec2(0.0f, 0.0f));
+  b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(world.CreateJoint(&jd));
+  CHECK(j != nullptr && world.GetJointCount() == 1);
+  for (int i = 0; i < 60; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  b2Vec2 F = j->GetReactionForce(60.0f);
+  CHECK(fabsf(F.y - 8.0f) < 0.05f);
+  CHECK(fabsf(F.x) < 1e-3f);
+  CHECK(fabsf(j->GetJointAngle()) < 1e-4f);
+  CHECK(j->GetReactionTorque(60.0f) == 0.0f);
+  CHECK(j->GetMotorTorque(60.0f) == 0.0f);
+  // motor: drives the joint speed and reports the torque that holds the rod against gravity
+  j->SetMaxMotorTorque(1000.0f);
+  j->SetMotorSpeed(1.0f);
+  j->EnableMotor(true);
+  CHECK(j->IsMotorEnabled() && j->GetMotorSpeed() == 1.0f && j->GetMaxMotorTorque() == 1000.0f);
+  CHECK(rod->IsAwake());
+  for (int i = 0; i < 30; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(fabsf(j->GetJointSpeed() - 1.0f) < 1e-3f);
+  CHECK(j->GetJointAngle() > 0.45f && j->GetJointAngle() < 0.55f);
+  float torque = j->GetMotorTorque(60.0f);
+  CHECK(torque > 5.0f && torque < 12.0f);  // m g l sin(angle) = 0.8 * 10 * 2 * sin(0.5) = 7.7
+  CHECK(j->GetReactionTorque(60.0f) == torque);
+  // limit: the motor is released and the joint pushed back inside [-0.2, 0.2]
+  j->EnableMotor(false);
+  j->SetLimits(-0.2f, 0.2f);
+  j->EnableLimit(true);
+  CHECK(j->IsLimitEnabled() && j->GetLowerLimit() == -0.2f && j->GetUpperLimit() == 0.2f);
+  float lo = 10.0f, hi = -10.0f;
+  for (int i = 0; i < 240; ++i) {
+    world.Step(1.0f / 60.0f, 8, 3);
+    if (i >= 60) {
+      lo = b2Min(lo, j->GetJointAngle());
+      hi = b2Max(hi, j->GetJointAngle());
+    }
+  }
+  CHECK(hi <= 0.2f + 0.04f && lo >= -0.2f - 0.04f);
+  CHECK(hi - lo > 0.05f);  // still swinging between the stops
+  printf("revolute: F=(%.9g, %.9g) torque=%.9g swing=[%.9g, %.9g] angle=%.9g\n", F.x, F.y, torque, lo, hi, j->GetJointAngle());
+  world.DestroyJoint(j);
+  CHECK(world.GetJointCount() == 0);
+  world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(rod->GetLinearVelocity().y < 0.0f || rod->GetPosition().y < -2.0f);  // free fall now
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -221,6 +278,7 @@ int main() {
   sweep_math();
   locked_world_is_silent();
   body_list_order();
+  revolute_joint_api();
   printf(g_failed ? "FAILED %d checks\n" : "all API checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }

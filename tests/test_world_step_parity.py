@@ -41,6 +41,9 @@ def mirror_reference_state(A, ref, params, inv):
     fl = np.where(c["flags"] & 1, capi.CONTACT_TOUCHING, 0) | np.where(c["flags"] & 2, capi.CONTACT_ENABLED, 0)
     A.upload_contacts(c["fix_a"], c["fix_b"], fl.astype(np.uint32), c["manifold"], c["material"])
     A.set_inv_dt0(ref.inv_dt0())
+    j = ref.joints()
+    if len(j["bodies"]):
+        A.upload_joints(j["bodies"], j["anchors"], j["params"], state=ref.joint_state())
     return c
 
 
@@ -58,17 +61,20 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("name,size,seed,steps", [("pyramid", 12, 0, 150), ("mixed", 700, 12345, 260),
-                                                   ("falling_squares", 200, 7, 160)])
+                                                   ("falling_squares", 200, 7, 160), ("tumbler", 80, 3, 200),
+                                                   ("pendulum_limit", 6, 0, 120), ("pendulum_motor", 6, 0, 120)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
     from box2d_optimized_b200 import RefScene
     ref = RefScene(name, size, seed)
-    ref.step(1)  # the reference creates its first contacts inside the first Step
+    # the reference creates its first contacts inside the first Step; the tumbler spawns one body per step
+    ref.step(size + 2 if name == "tumbler" else 1)
     A = arena_from_scene(ref, max_contacts=max(4096, 16 * ref.body_count))
     params = ref.body_params()
     inv = ref.body_inv()
     P = Arena.params(solver_mode=capi.SOLVER_SEQUENTIAL)
     stats = capi.StepStats()
-    worst = dict(pos=0.0, vel=0.0, imp=0.0, sleep=0.0)
+    worst = dict(pos=0.0, vel=0.0, imp=0.0, sleep=0.0, joint=0.0)
+    nj = len(ref.joints()["bodies"])
     solved_total = 0
     for k in range(steps):
         before = mirror_reference_state(A, ref, params, inv)
@@ -84,6 +90,8 @@ def test_every_step_from_the_reference_state(require_ref, name, size, seed, step
         awake_g = (gb["flags"] & capi.BODY_AWAKE) != 0
         assert np.array_equal(awake_g, rb[:, 10] != 0), f"step {k}: awake flags differ"
         worst["sleep"] = max(worst["sleep"], float(np.abs(gb["force"][:, 3] - ref.sleep_times()).max()))
+        if nj:
+            worst["joint"] = max(worst["joint"], rel(A.download_joints(nj), ref.joint_state()))
         # contacts after the step
         cg, cr = A.download_contacts(), ref.contacts()
         assert util.pair_set(cg["fix_a"], cg["fix_b"]) == util.pair_set(cr["fix_a"], cr["fix_b"]), f"step {k}: pair sets differ"
@@ -108,10 +116,11 @@ def test_every_step_from_the_reference_state(require_ref, name, size, seed, step
             worst["imp"] = max(worst["imp"], rel(mg[one][:, [6, 7]], mr[one][:, [6, 7]]),
                                rel(mg[two][:, [10, 11]], mr[two][:, [10, 11]]))
     print(f"{name}: {steps} teacher-forced steps, {solved_total} constraint solves; worst relative error "
-          f"pos {worst['pos']:.3g} vel {worst['vel']:.3g} impulses {worst['imp']:.3g} sleepTime {worst['sleep']:.3g}")
-    assert solved_total > 1000
-    assert worst["pos"] <= 1e-4 and worst["vel"] <= 1e-4 and worst["imp"] <= 1e-4 and worst["sleep"] <= 1e-6
+          f"pos {worst['pos']:.3g} vel {worst['vel']:.3g} impulses {worst['imp']:.3g} sleepTime {worst['sleep']:.3g} "
+          f"joint impulses {worst['joint']:.3g}")
+    assert solved_total > 1000 or nj
+    assert max(worst["pos"], worst["vel"], worst["imp"], worst["joint"]) <= 1e-4 and worst["sleep"] <= 1e-6
     if device_rotations_match_libm():
         # same libm algorithm on both sides -> every float of the step is reproduced bit for bit
-        assert worst == dict(pos=0.0, vel=0.0, imp=0.0, sleep=0.0), worst
+        assert worst == dict(pos=0.0, vel=0.0, imp=0.0, sleep=0.0, joint=0.0), worst
     A.close()
