@@ -85,6 +85,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=60)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="many_pyramids", choices=sorted(WORKLOADS))
+    ap.add_argument("--worlds-per-gpu", type=int, default=0,
+                    help="batched-world workloads: independent worlds per GPU (config 4 = 8192 worlds / 8 GPUs = 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=150)
     ap.add_argument("--profile-steps", type=int, default=20)
@@ -210,6 +212,8 @@ def main():
 
     from box2d_optimized_b200.sharding import aggregate, shard_worlds
     per_gpu = WORLDS_PER_GPU.get(args.workload, 1)
+    if args.worlds_per_gpu > 0 and args.workload in WORLDS_PER_GPU:
+        per_gpu = args.worlds_per_gpu
     my_worlds = shard_worlds(per_gpu * world, rank, world)   # independent worlds, no data-path collective
     copies = len(my_worlds)
     nb_world = nb
@@ -281,7 +285,8 @@ def main():
     A.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.result()
-    elapsed_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    elapsed_ms = sum(per_step_ms)
     _, elapsed_ms_max, value = aggregate(nb * args.steps, elapsed_ms, device=f"cuda:{local_rank}")
 
     # ------------------------------------------------------------------ per-kernel roofline pass
@@ -361,6 +366,7 @@ def main():
         line = {
             "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms_max / args.steps,
+            "ms_per_step_p50": float(np.percentile(per_step_ms, 50)), "ms_per_step_p99": float(np.percentile(per_step_ms, 99)),
             "higher_is_better": True, "scaling": "strong" if args.workload in SLAB else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "bodies_per_world": nb_world,

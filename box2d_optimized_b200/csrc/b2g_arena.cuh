@@ -123,6 +123,7 @@ struct b2gArena {
   float4* jParams1;  // motorSpeed, bits(flags), 0, 0
   float4* jState;    // impulse.x, impulse.y, motorImpulse, lowerImpulse
   float* jUpper;     // upperImpulse
+  float4* stateStage; // [capBodies][2] packed xf+vel for b2g_download_body_state_async (one linear D2H)
   JointWork* jWork;  // per-step scratch
 
   // contacts

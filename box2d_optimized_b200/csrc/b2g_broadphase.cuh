@@ -24,6 +24,7 @@ k_update_aabbs(int nf, const int* __restrict__ fBody, const int* __restrict__ fS
                const uint32_t* __restrict__ fTypeFlags, const float4* __restrict__ shapes,
                const uint32_t* __restrict__ bflags, const float4* __restrict__ xf, float4* fAabb, float* fRadius,
                int all, StepCounts* counts) {
+  B2G_PDL_ENTER();
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   float cx = 0.0f, cy = 0.0f;
   bool valid = false;
@@ -104,6 +105,7 @@ __global__ void k_morton_keys(int nf, const float4* __restrict__ fAabb, const ui
                               const int* __restrict__ fBody, const int* __restrict__ bworld,
                               const StepCounts* __restrict__ counts, unsigned long long* keys, int* leafFixture,
                               int numWorlds) {
+  B2G_PDL_ENTER();
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nf) return;
   leafFixture[f] = f;
@@ -133,6 +135,7 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
                               const uint2* __restrict__ fFilter, const uint32_t* __restrict__ bflags, float4* leafBox,
                               int4* leafInfo, unsigned long long* leafKey, int* worldFirst, int* worldLast,
                               int numWorlds, int* nodeVisit) {
+  B2G_PDL_ENTER();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nf) return;
   int f = leafFixtureSorted[p];
@@ -170,6 +173,7 @@ __device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__
 }
 
 __global__ void k_lbvh_build(int n, const unsigned long long* __restrict__ keys, int4* nodeRange, int* leafParent) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -244,6 +248,7 @@ __device__ __forceinline__ void refit_walk(int p, float4 box, unsigned long long
 __global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const unsigned long long* __restrict__ leafKey,
                              const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
                              int* nodeVisit) {
+  B2G_PDL_ENTER();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   refit_walk(p, leafBox[p], leafKey[p], leafParent, nodeRange, nodes, nodeVisit);
@@ -259,6 +264,7 @@ k_refresh_leaves(int nf, const int* __restrict__ leafFixtureSorted, const int* _
                  const float4* __restrict__ xf, float4* fAabb, float4* leafBox, unsigned long long* leafKey,
                  const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
                  int* nodeVisit) {
+  B2G_PDL_ENTER();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nf) return;
   int f = leafFixtureSorted[p];
@@ -392,6 +398,7 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
               const int* __restrict__ worldFirst,
               const int* __restrict__ worldLast, const unsigned long long* __restrict__ keysSorted, int numWorlds,
               ContactHash H, uint8_t* persist, unsigned long long* newPairs, int capacity, StepCounts* counts) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || n < 2) return;
   int4 me = leafInfo[i];
@@ -440,6 +447,7 @@ __global__ void k_contact_sweep(int nSlots, ContactBuf C, uint8_t* persist, Cont
                                 const uint32_t* __restrict__ fTypeFlags, uint32_t* bflags, float4* force,
                                 int* freeStack, int* freeTop, StepCounts* counts, int recordEvents, int2* endEvents,
                                 int eventCap, const int* __restrict__ island, uint8_t* islandDirty) {
+  B2G_PDL_ENTER();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nSlots) return;
   uint32_t flags = C.flags[j];
@@ -487,6 +495,7 @@ k_contact_insert(int nNew, const unsigned long long* __restrict__ newPairs, int 
                  ContactBuf C, uint8_t* persist, ContactHash H, const int* __restrict__ freeStack, int* freeTop,
                  const int* __restrict__ fBody, const uint32_t* __restrict__ fTypeFlags,
                  const float4* __restrict__ fMaterial) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *freeTop = freeTopBefore > nNew ? freeTopBefore - nNew : 0;
   if (i >= nNew) return;
@@ -521,6 +530,7 @@ k_contact_insert(int nNew, const unsigned long long* __restrict__ newPairs, int 
 
 // rebuild the table from the live contacts (drops tombstones)
 __global__ void k_hash_rebuild(int nSlots, ContactBuf C, ContactHash H) {
+  B2G_PDL_ENTER();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nSlots) return;
   if (C.flags[j] & B2G_CONTACT_ALIVE) hash_insert(H, C.key[j], j);

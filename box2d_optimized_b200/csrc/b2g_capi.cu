@@ -93,12 +93,38 @@ static void ktime_collect(b2gArena* A) {
 }
 
 // `units` = the work items of this launch in the unit SURVEY §8(d) quotes bytes for
-#define LAUNCH(A, cls, units, kernel, grid, block, ...)           \
-  do {                                                            \
-    ktime_begin((A), (cls), (double)(units));                     \
-    kernel<<<(grid), (block), 0, (A)->stream>>>(__VA_ARGS__);     \
-    ktime_end((A));                                               \
-    (A)->launches++;                                              \
+// every step kernel is launched with programmatic stream serialization (B2G_PDL_ENTER in
+// b2g_math.cuh); B2G_PDL=0 in the environment falls back to plain stream order (A/B measurements)
+static int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2G_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(cudaStream_t st, dim3 grid, dim3 block, size_t smem, void (*kernel)(KArgs...),
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define LAUNCH(A, cls, units, kernel, grid, block, ...)                      \
+  do {                                                                       \
+    ktime_begin((A), (cls), (double)(units));                                \
+    launch_pdl((A)->stream, dim3(grid), dim3(block), 0, kernel, __VA_ARGS__); \
+    ktime_end((A));                                                          \
+    (A)->launches++;                                                         \
   } while (0)
 #define TIMED(A, cls, units, stmt) \
   do {                             \
@@ -232,6 +258,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->jState, nj));
   CK(dalloc(&A->jUpper, nj));
   CK(dalloc(&A->jWork, nj));
+  CK(dalloc(&A->stateStage, (size_t)nb * 2));
 
   int rc = alloc_contact_buf(A->cb[0], nc);
   if (rc) return rc;
@@ -326,7 +353,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->stateStage, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->worldFirst, A->worldLast, A->nodeRange, A->bvhNodes, A->leafParent,
                   A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -931,7 +958,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       A->fusedSmemSet = smem;
     }
     ktime_begin(A, KC_FUSED_SOLVE, (double)numActive - numBig);
-    k_solve_bins_fused<<<nbins, B2G_FUSED_THREADS, smem, A->stream>>>(
+    launch_pdl(A->stream, dim3(nbins), dim3(B2G_FUSED_THREADS), smem, k_solve_bins_fused,
         FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->bucketStart,
         A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts,
         joint_views(A));
@@ -1136,12 +1163,13 @@ __global__ void k_pack_body_state(int first, int count, const float4* __restrict
 extern "C" int b2g_download_body_state_async(b2gArena* A, int32_t first, int32_t count, float* dst) {
   if (!A || !dst || first < 0 || count < 0 || first + count > A->nBodies) return B2G_ERR_INVALID;
   CK(cudaSetDevice(A->device));
-  // pack into the (idle between steps) leafBox/nodeBox scratch is not safe for count > capFixtures/2,
-  // so copy the two planes with strided 2-D copies straight into the interleaved host layout
-  CK(cudaMemcpy2DAsync(dst, 32, (const float*)A->xf + (size_t)first * 4, 16, 16, count, cudaMemcpyDeviceToHost,
-                       A->stream));
-  CK(cudaMemcpy2DAsync(dst + 4, 32, (const float*)A->vel + (size_t)first * 4, 16, 16, count, cudaMemcpyDeviceToHost,
-                       A->stream));
+  if (count == 0) return B2G_OK;
+  // interleave on the device, then ONE linear copy: strided 2-D copies of 16-byte rows cost a DMA
+  // descriptor per row and were slower than the step itself at 100k bodies
+  k_pack_body_state<<<div_up(count, 256), 256, 0, A->stream>>>(first, count, A->xf, A->vel, A->stateStage);
+  CK(cudaGetLastError());
+  A->launches++;
+  CK(cudaMemcpyAsync(dst, A->stateStage, (size_t)count * 32, cudaMemcpyDeviceToHost, A->stream));
   return B2G_OK;
 }
 

@@ -29,6 +29,7 @@
 __global__ void k_island_alloc(int nb, const int* __restrict__ island, const uint32_t* __restrict__ islandAwake,
                                const int* __restrict__ islandCount, int* islandStart, int* binFirst, int* binEnd,
                                int binSize, int bigThreshold, StepCounts* counts, uint8_t* islandWasBig) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   int cnt = islandCount[b];
@@ -52,6 +53,7 @@ __global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, cons
                                const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
                                const int* __restrict__ islandStart, int* islandCursor, int* bodySlot, int* slotBody,
                                int bigThreshold) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   if (!body_simulated(bflags[b], island, islandAwake, b)) {
@@ -75,6 +77,7 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
                                    const int* __restrict__ islandStart, int* cbin, int dropColours, int binSize,
                                    int bigThreshold, int bigBin, StepCounts* counts, const float4* __restrict__ mass,
                                    unsigned long long* colourMask) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   uint32_t flags = C.flags[i];
@@ -115,6 +118,7 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
 
 __global__ void k_colour2_propose(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
                                   unsigned long long* bodyBest, int round) {
+  B2G_PDL_ENTER();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
     if (cbin[i] < 0 || C.colour[i] >= 0) continue;
     int2 bd = C.body[i];
@@ -127,6 +131,7 @@ __global__ void k_colour2_propose(int nc, const int* __restrict__ cbin, ContactB
 __global__ void k_colour2_commit(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
                                  unsigned long long* colourMask, const unsigned long long* __restrict__ bodyBest,
                                  int round, StepCounts* counts, int lastOfBatch, int bigBin) {
+  B2G_PDL_ENTER();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
     int bin = cbin[i];
     if (bin < 0 || C.colour[i] >= 0) continue;
@@ -159,6 +164,7 @@ __global__ void k_colour2_commit(int nc, const int* __restrict__ cbin, ContactBu
 // whatever the atomics give: constraints of one colour never share a movable body, so any order
 // produces bit-identical results.
 __global__ void k_bucket_count(int nc, const int* __restrict__ cbin, ContactBuf C, int* bucketCount, int* rank) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   int bin = cbin[i];
@@ -170,6 +176,7 @@ __global__ void k_bucket_count(int nc, const int* __restrict__ cbin, ContactBuf 
 
 // exclusive scan of the bucket counts by one block (buckets = bins x 32, a few thousand entries)
 __global__ void __launch_bounds__(1024) k_bucket_scan(int n, const int* __restrict__ bucketCount, int* bucketStart) {
+  B2G_PDL_ENTER();
   __shared__ int warpSums[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -205,6 +212,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(int n, const int* __restri
 
 __global__ void k_bucket_scatter(int nc, const int* __restrict__ cbin, ContactBuf C, const int* __restrict__ bucketStart,
                                  const int* __restrict__ rank, int* sortedList) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   int bin = cbin[i];
@@ -233,6 +241,7 @@ __device__ __forceinline__ void order_bucket_by_key(int o0, int o1, int* sortedL
 }
 
 __global__ void k_order_overflow(int o0, int o1, int* sortedList, int* scratch, ContactBuf C) {
+  B2G_PDL_ENTER();
   order_bucket_by_key(o0, o1, sortedList, scratch, C);
 }
 
@@ -271,6 +280,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
                    const float* __restrict__ fRadius, SolverPlanes S, uint32_t* bflags, float4* gpos, float4* gvel,
                    float4* gxf, float4* gforce, const float4* __restrict__ gmass, const float4* __restrict__ gcenter,
                    StepCounts* counts, JointArraysDev J) {
+  B2G_PDL_ENTER();
   const int bin = blockIdx.x;
   const int first = binFirst[bin];
   const int nbod = binEnd[bin] - first;
@@ -653,13 +663,16 @@ __device__ __forceinline__ void joints_position_global(const JointWalk& W, const
 }
 __global__ void k_joints_init_seq(JointWalk W, JointArraysDev J, float4* pos, float4* vel, const float4* mass,
                                   const float4* center, float dtRatio, int warm) {
+  B2G_PDL_ENTER();
   joints_init_global(W, J, pos, vel, mass, center, dtRatio, warm);
 }
 __global__ void k_joints_velocity_seq(JointWalk W, JointArraysDev J, float4* vel, float h, float invH) {
+  B2G_PDL_ENTER();
   joints_velocity_global(W, J, vel, h, invH);
 }
 __global__ void k_joints_position_seq(JointWalk W, JointArraysDev J, float4* pos, uint32_t* islandPen, int penStride,
                                       int iter) {
+  B2G_PDL_ENTER();
   joints_position_global(W, J, pos, islandPen, penStride, iter);
 }
 

@@ -6,6 +6,23 @@
 // intermediate rounds the same way.  The library is compiled with -fmad=false so nvcc does
 // not contract a*b+c into an FMA (the reference is built for baseline x86-64: no FMA).
 #pragma once
+
+// Programmatic dependent launch (sm_90+): every step kernel starts with this pair.  The kernels of
+// a step are small and strictly ordered on one stream, so most of a step is launch latency and
+// grid ramp-up/drain; letting grid N+1 be scheduled while grid N is still running hides that.
+// launch_dependents lets the next grid's CTAs become resident; wait blocks them until every
+// prerequisite grid has COMPLETED and its writes are visible, so nothing is read early.  Without
+// the launch attribute (cudaLaunchAttributeProgrammaticStreamSerialization) both are no-ops.
+#ifdef __CUDA_ARCH__
+#define B2G_PDL_ENTER()                                     \
+  do {                                                      \
+    asm volatile("griddepcontrol.launch_dependents;");      \
+    asm volatile("griddepcontrol.wait;" ::: "memory");      \
+  } while (0)
+#else
+#define B2G_PDL_ENTER() do {} while (0)
+#endif
+
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
@@ -110,7 +127,7 @@ B2G_HD float4 xf_to4(Xf T) { return make_float4(T.p.x, T.p.y, T.q.s, T.q.c); }
 // (>= 2.28, x86-64 FMA variant; the published ARM optimized-routines sincosf) evaluates: argument
 // reduction by pi/2 in double with a 2^24-prescaled quadrant, a degree-7 sine / degree-8 cosine
 // minimax polynomial in double with fused multiply-adds, one rounding to float.  Checked here
-// bit-for-bit against glibc 2.39 on 3e8 arguments (tests/test_oracle_port.py runs a sample).
+// bit-for-bit against glibc 2.39 on 3e8 arguments (CPU restatement) and by tests/test_rotation_parity.py.
 // |angle| >= 120 (glibc's large-argument path) falls back to double sincos rounded once.
 B2G_HD Rot rot_set(float angle) {
   Rot q;

@@ -48,6 +48,7 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
               const float4* __restrict__ shapes, uint32_t* bflagsRW, StepCounts* counts, int recordEvents,
               int2* beginEvents, int2* endEvents, int eventCap, const int* __restrict__ islandPrev,
               uint8_t* islandDirty) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   uint32_t flags = C.flags[i];
@@ -135,6 +136,7 @@ __global__ void k_body_begin(int nb, uint32_t* bflags, float4* force, int* islan
                              unsigned long long* colourMask, unsigned long long* bodyBest, int* islandCount,
                              int* islandCursor, int* binFirst, int* binEnd, int nbinsPlus, int* bucketCount,
                              int nbuckets) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   // per-step tables of the fused solver, cleared here instead of by separate memsets
   for (int k = b; k < nbinsPlus; k += gridDim.x * blockDim.x) {
@@ -204,6 +206,7 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 
 __global__ void k_island_union(int nc, ContactBuf C, const uint32_t* __restrict__ bflags,
                                const uint32_t* __restrict__ fTypeFlags, int* island) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   uint32_t flags = C.flags[i];
@@ -217,6 +220,7 @@ __global__ void k_island_union(int nc, ContactBuf C, const uint32_t* __restrict_
 
 __global__ void k_island_union_joints(int nj, const int2* __restrict__ jBodies, const uint32_t* __restrict__ bflags,
                                       int* island) {
+  B2G_PDL_ENTER();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nj) return;
   int2 bd = jBodies[j];
@@ -232,6 +236,7 @@ __global__ void k_island_union_joints(int nj, const int2* __restrict__ jBodies, 
 __global__ void k_island_flatten(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ parent,
                                  int* island, uint32_t* islandAwake, int* islandCount, StepCounts* counts,
                                  uint8_t* islandDirty) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   islandDirty[b] = 0;  // consumed by k_body_begin of this step
@@ -257,6 +262,7 @@ __global__ void k_integrate_velocities(int nb, uint32_t* bflags, const int* __re
                                        const float4* __restrict__ mass, const float4* __restrict__ center,
                                        const float4* __restrict__ force, float h, float2 gravity,
                                        StepCounts* counts, const int* __restrict__ bodySlot, int onlyBig) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   if (onlyBig && bodySlot[b] != -2) return;  // bodies of tile-sized islands are integrated by the fused kernel
@@ -292,6 +298,7 @@ __global__ void k_integrate_velocities(int nb, uint32_t* bflags, const int* __re
 __global__ void k_mark_active(int nc, ContactBuf C, const uint32_t* __restrict__ fTypeFlags,
                               const int* __restrict__ island, const uint32_t* __restrict__ islandAwake,
                               uint8_t* activeFlag, int dropColours) {
+  B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   uint32_t flags = C.flags[i];
@@ -319,6 +326,7 @@ __device__ __forceinline__ bool body_movable(float4 m) { return m.x != 0.0f || m
 
 __global__ void k_colour_begin(const int* __restrict__ numActivePtr, const int* __restrict__ activeList, ContactBuf C,
                                const float4* __restrict__ mass, unsigned long long* colourMask, StepCounts* counts) {
+  B2G_PDL_ENTER();
   int n = *numActivePtr;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     int i = activeList[s];
@@ -352,6 +360,7 @@ __device__ __forceinline__ unsigned long long colour_priority(int round, int s, 
 
 __global__ void k_colour_propose(const int* __restrict__ numActivePtr, const int* __restrict__ activeList, ContactBuf C,
                                  const float4* __restrict__ mass, unsigned long long* bodyBest, int round) {
+  B2G_PDL_ENTER();
   int n = *numActivePtr;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     int i = activeList[s];
@@ -367,6 +376,7 @@ __global__ void k_colour_commit(const int* __restrict__ numActivePtr, const int*
                                 const float4* __restrict__ mass, unsigned long long* colourMask,
                                 const unsigned long long* __restrict__ bodyBest, int round, StepCounts* counts,
                                 int lastOfBatch) {
+  B2G_PDL_ENTER();
   int n = *numActivePtr;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     int i = activeList[s];
@@ -396,18 +406,21 @@ __global__ void k_colour_commit(const int* __restrict__ numActivePtr, const int*
 
 __global__ void k_colour_keys(const int* __restrict__ numActivePtr, const int* __restrict__ activeList, ContactBuf C,
                               uint8_t* colourKey) {
+  B2G_PDL_ENTER();
   int n = *numActivePtr;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
     colourKey[s] = (uint8_t)C.colour[activeList[s]];
 }
 
 __global__ void k_gather_keys(int n, const int* __restrict__ list, ContactBuf C, unsigned long long* keys) {
+  B2G_PDL_ENTER();
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n) keys[s] = C.key[list[s]];
 }
 
 __global__ void k_gather_order(int n, const int* __restrict__ list, const unsigned long long* __restrict__ orderKey,
                                unsigned long long* keys) {
+  B2G_PDL_ENTER();
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n) keys[s] = orderKey[list[s]];
 }
@@ -415,6 +428,7 @@ __global__ void k_gather_order(int n, const int* __restrict__ list, const unsign
 // self-check used by the tests: counts pairs of same-colour constraints that share a movable body
 __global__ void k_colour_validate(int n, const int* __restrict__ sortedList, ContactBuf C,
                                   const float4* __restrict__ mass, int* bodyStamp, int* violations) {
+  B2G_PDL_ENTER();
   // bodyStamp[b * stride + colour] would be exact; instead each constraint claims (body, colour)
   // with atomicExch on a per-body slot tagged by colour, one colour range per launch (host loops)
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,6 +454,7 @@ k_prepare(int first, int n, const int* __restrict__ sortedList, ContactBuf C, co
           const uint32_t* __restrict__ bflags, const int* __restrict__ island, SolverPlanes S, int* croot,
           const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ mass,
           const float4* __restrict__ center, float dtRatio, int warmStarting) {
+  B2G_PDL_ENTER();
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   s += first;
@@ -455,12 +470,14 @@ k_prepare(int first, int n, const int* __restrict__ sortedList, ContactBuf C, co
 }
 
 __global__ void __launch_bounds__(256) k_warm_start(int first, int last, SolverPlanes S, float4* vel) {
+  B2G_PDL_ENTER();
   int s = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= last) return;
   warm_start_constraint(S, s, GlobalBodies{vel});
 }
 
 __global__ void __launch_bounds__(256) k_solve_velocity(int first, int last, SolverPlanes S, float4* vel) {
+  B2G_PDL_ENTER();
   int s = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= last) return;
   solve_velocity_constraint(S, s, GlobalBodies{vel});
@@ -476,6 +493,7 @@ __device__ __forceinline__ bool island_done(const uint32_t* __restrict__ islandP
 __global__ void __launch_bounds__(256)
 k_solve_position(int first, int last, SolverPlanes S, float4* pos, const int* __restrict__ croot, uint32_t* islandPen,
                  int penStride, int iter) {
+  B2G_PDL_ENTER();
   int s = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= last) return;
   int root = croot[s];
@@ -490,13 +508,16 @@ k_solve_position(int first, int last, SolverPlanes S, float4* pos, const int* __
 // sequential single-thread variants: same device functions, list order (parity vehicle and the
 // serial overflow colour)
 __global__ void k_warm_start_seq(int first, int last, SolverPlanes S, float4* vel) {
+  B2G_PDL_ENTER();
   for (int s = first; s < last; ++s) warm_start_constraint(S, s, GlobalBodies{vel});
 }
 __global__ void k_solve_velocity_seq(int first, int last, SolverPlanes S, float4* vel) {
+  B2G_PDL_ENTER();
   for (int s = first; s < last; ++s) solve_velocity_constraint(S, s, GlobalBodies{vel});
 }
 __global__ void k_solve_position_seq(int first, int last, SolverPlanes S, float4* pos, const int* __restrict__ croot,
                                      uint32_t* islandPen, int penStride, int iter) {
+  B2G_PDL_ENTER();
   for (int s = first; s < last; ++s) {
     int root = croot[s];
     if (island_done(islandPen, penStride, iter, root)) continue;
@@ -508,6 +529,7 @@ __global__ void k_solve_position_seq(int first, int last, SolverPlanes S, float4
 }
 
 __global__ void k_store_impulses(int first, int n, SolverPlanes S, ContactBuf C) {
+  B2G_PDL_ENTER();
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   s += first;
@@ -534,6 +556,7 @@ __device__ __forceinline__ bool body_simulated(uint32_t f, const int* __restrict
 __global__ void k_integrate_positions(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                       const uint32_t* __restrict__ islandAwake, float4* pos, float4* vel, float h,
                                       const int* __restrict__ bodySlot, int onlyBig) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   if (onlyBig && bodySlot[b] != -2) return;
@@ -566,6 +589,7 @@ __global__ void k_finalize_bodies(int nb, const uint32_t* __restrict__ bflags, c
                                   const float4* __restrict__ vel, const float4* __restrict__ center, float4* xf,
                                   float4* force, uint32_t* islandMinSleep, float h, int allowSleep,
                                   const int* __restrict__ bodySlot, int onlyBig) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   if (onlyBig && bodySlot[b] != -2) return;
@@ -600,6 +624,7 @@ __global__ void k_sleep_and_clear(int nb, uint32_t* bflags, const int* __restric
                                   const uint32_t* __restrict__ islandPen, int penStride, int posIters, float4* vel,
                                   float4* force, int allowSleep, int clearForces, StepCounts* counts,
                                   const int* __restrict__ bodySlot, int onlyBig) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   if (onlyBig && bodySlot[b] != -2) return;
