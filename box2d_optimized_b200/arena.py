@@ -104,6 +104,64 @@ class Arena:
         a = capi.JointArrays(capi.ip(bodies), capi.fp(anchors), capi.fp(params), None if state is None else capi.fp(state))
         capi.check(self.lib.b2g_upload_joints(self.h, first, len(bodies), C.byref(a)), "b2g_upload_joints")
 
+    # ---- spatial queries on the broadphase tree (include/b2cuda.h "Spatial queries") ----
+    @staticmethod
+    def _ptr(a):
+        return None if a is None else C.c_void_p(a.ctypes.data)
+
+    def query_aabb(self, aabbs, cap, world=None):
+        """aabbs [n,4] -> (counts [n], fixtures [n,cap] sorted ascending, -1 padded)"""
+        aabbs = f32(aabbs).reshape(-1, 4)
+        n = len(aabbs)
+        world = None if world is None else i32(world)
+        counts = np.zeros(n, np.int32)
+        fixtures = np.full((n, max(cap, 1)), -1, np.int32)
+        capi.check(self.lib.b2g_query_aabb(self.h, n, self._ptr(aabbs), self._ptr(world), cap, self._ptr(counts),
+                                           self._ptr(fixtures), 0), "b2g_query_aabb")
+        big = np.iinfo(np.int32).max
+        k = np.arange(fixtures.shape[1])[None, :] < np.minimum(counts, cap)[:, None]
+        fixtures = np.where(k, fixtures, big)
+        fixtures.sort(axis=1)
+        fixtures[fixtures == big] = -1
+        return counts, fixtures
+
+    def ray_cast_closest(self, rays, max_fraction=None, world=None, category_mask=0xFFFF):
+        """rays [n,4] = p1, p2 -> (fixture [n] or -1, fraction [n], normal [n,2])"""
+        rays = f32(rays).reshape(-1, 4)
+        n = len(rays)
+        mf = None if max_fraction is None else f32(max_fraction)
+        world = None if world is None else i32(world)
+        fixture = np.full(n, -1, np.int32)
+        fraction = np.zeros(n, np.float32)
+        normal = np.zeros((n, 2), np.float32)
+        capi.check(self.lib.b2g_ray_cast_closest(self.h, n, self._ptr(rays), self._ptr(mf), self._ptr(world),
+                                                 category_mask, self._ptr(fixture), self._ptr(fraction),
+                                                 self._ptr(normal), 0), "b2g_ray_cast_closest")
+        return fixture, fraction, normal
+
+    def ray_cast_all(self, rays, cap, max_fraction=None, world=None, category_mask=0xFFFF):
+        """every hit per ray, sorted by (fraction, fixture): (counts [n], fixture [n,cap], fraction [n,cap], normal [n,cap,2])"""
+        rays = f32(rays).reshape(-1, 4)
+        n = len(rays)
+        mf = None if max_fraction is None else f32(max_fraction)
+        world = None if world is None else i32(world)
+        counts = np.zeros(n, np.int32)
+        fixture = np.full((n, max(cap, 1)), -1, np.int32)
+        fraction = np.full((n, max(cap, 1)), np.inf, np.float32)
+        normal = np.zeros((n, max(cap, 1), 2), np.float32)
+        capi.check(self.lib.b2g_ray_cast_all(self.h, n, self._ptr(rays), self._ptr(mf), self._ptr(world), category_mask,
+                                             cap, self._ptr(counts), self._ptr(fixture), self._ptr(fraction),
+                                             self._ptr(normal), 0), "b2g_ray_cast_all")
+        valid = np.arange(fixture.shape[1])[None, :] < np.minimum(counts, cap)[:, None]
+        fraction = np.where(valid, fraction, np.inf)
+        fixture = np.where(valid, fixture, np.iinfo(np.int32).max)
+        order = np.lexsort((fixture, fraction), axis=1)
+        fixture = np.take_along_axis(fixture, order, 1)
+        fraction = np.take_along_axis(fraction, order, 1)
+        normal = np.take_along_axis(normal, order[:, :, None], 1)
+        fixture[~np.take_along_axis(valid, order, 1)] = -1
+        return counts, fixture, fraction, normal
+
     def download_joints(self, count, first=0):
         """accumulated joint impulses [count, 5] = impulse.xy, motor, lower, upper"""
         state = np.zeros((count, 5), np.float32)

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include "b2g_broadphase.cuh"
 #include "b2g_fused.cuh"
+#include "b2g_query.cuh"
 #include <thrust/iterator/transform_iterator.h>
 
 static thread_local char g_err[512] = "";
@@ -62,11 +63,11 @@ static int use_device(int device) {
 enum KClass {
   KC_NARROWPHASE, KC_ISLANDS, KC_INTEGRATE, KC_COLOUR, KC_PREPARE, KC_WARM_START, KC_SOLVE_VELOCITY,
   KC_SOLVE_POSITION, KC_STORE_IMPULSES, KC_FINALIZE, KC_BP_BUILD, KC_BP_TRAVERSE, KC_CONTACT_MERGE, KC_SORT_SCAN,
-  KC_FUSED_SOLVE, KC_COUNT
+  KC_FUSED_SOLVE, KC_QUERY, KC_COUNT
 };
 static const char* kClassNames[KC_COUNT] = {
     "narrowphase", "islands", "integrate", "colour", "prepare", "warm_start", "solve_velocity", "solve_position",
-    "store_impulses", "finalize", "bp_build", "bp_traverse", "contact_merge", "sort_scan", "fused_solve"};
+    "store_impulses", "finalize", "bp_build", "bp_traverse", "contact_merge", "sort_scan", "fused_solve", "query"};
 
 static inline void ktime_begin(b2gArena* A, int cls, double units) {
   if (!A->kernelTiming || A->ktCount >= B2G_KT_MAX) return;
@@ -1404,6 +1405,114 @@ extern "C" int b2g_set_sequential_order(b2gArena* A, int32_t count, const int32_
   CK(cudaStreamSynchronize(A->stream));
   A->seqOrderActive = 1;
   return B2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spatial queries on the broadphase BVH (b2g_query.cuh)
+// ---------------------------------------------------------------------------------------------
+// the tree must reflect every upload made since the last step (b2BroadPhase::EnsureBuiltTree)
+static int query_prepare(b2gArena* A) {
+  CK(cudaSetDevice(A->device));
+  if (A->newFixtures || A->aabbAllDirty || A->bvhLeaves != A->nFixtures) {
+    CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
+    int rc = find_new_contacts(A, 0);
+    if (rc) return rc;
+  }
+  return B2G_OK;
+}
+// host or device pointer -> device pointer on the arena's stream (staging through `buf` for host memory)
+static cudaError_t q_in(b2gArena* A, DevBuf& buf, const void* src, size_t bytes, int onDevice, const void** out) {
+  if (!src || onDevice) {
+    *out = src;
+    return cudaSuccess;
+  }
+  cudaError_t e = buf.alloc(bytes);
+  if (e != cudaSuccess) return e;
+  *out = buf.p;
+  return cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, A->stream);
+}
+static cudaError_t q_out(DevBuf& buf, void* dst, size_t bytes, int onDevice, void** out) {
+  if (onDevice) {
+    *out = dst;
+    return cudaSuccess;
+  }
+  cudaError_t e = buf.alloc(bytes);
+  *out = buf.p;
+  return e;
+}
+#define Q_BACK(buf, dst, bytes)                                                                        \
+  if (!on_device && (dst)) CK(cudaMemcpyAsync((dst), (buf).p, (bytes), cudaMemcpyDeviceToHost, A->stream))
+
+extern "C" int b2g_query_aabb(b2gArena* A, int32_t n, const float* aabbs, const int32_t* world, int32_t cap,
+                              int32_t* counts, int32_t* fixtures, int32_t on_device) {
+  if (!A || n < 0 || cap < 0 || (n > 0 && (!aabbs || !counts || (cap > 0 && !fixtures)))) return B2G_ERR_INVALID;
+  int rc = query_prepare(A);
+  if (rc) return rc;
+  if (n == 0) return B2G_OK;
+  DevBuf bQ, bW, bC, bF;
+  const void *dQ, *dW;
+  void *dC, *dF;
+  CK(q_in(A, bQ, aabbs, (size_t)n * 16, on_device, &dQ));
+  CK(q_in(A, bW, world, (size_t)n * 4, on_device, &dW));
+  CK(q_out(bC, counts, (size_t)n * 4, on_device, &dC));
+  CK(q_out(bF, fixtures, (size_t)n * (cap ? cap : 1) * 4, on_device, &dF));
+  if (A->nFixtures == 0) {
+    CK(cudaMemsetAsync(dC, 0, (size_t)n * 4, A->stream));
+  } else {
+    LAUNCH(A, KC_QUERY, n, k_query_aabb, div_up(n, 128), 128, n, (const float4*)dQ, (const int*)dW, A->nFixtures,
+           A->leafBox, A->leafInfo, A->bvhNodes, A->worldFirst, A->worldLast, A->numWorlds, cap, (int*)dC, (int*)dF);
+    CK(cudaGetLastError());
+  }
+  Q_BACK(bC, counts, (size_t)n * 4);
+  Q_BACK(bF, fixtures, (size_t)n * cap * 4);
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+static int ray_cast_common(b2gArena* A, int mode, int32_t n, const float* rays, const float* max_fraction,
+                           const int32_t* world, uint32_t category_mask, int32_t cap, int32_t* counts,
+                           int32_t* fixture, float* fraction, float* normal, int32_t on_device) {
+  int rc = query_prepare(A);
+  if (rc) return rc;
+  if (n == 0) return B2G_OK;
+  const size_t per = mode == 0 ? 1 : (size_t)(cap ? cap : 1);
+  DevBuf bR, bM, bW, bC, bF, bT, bN;
+  const void *dR, *dM, *dW;
+  void *dC = nullptr, *dF, *dT, *dN;
+  CK(q_in(A, bR, rays, (size_t)n * 16, on_device, &dR));
+  CK(q_in(A, bM, max_fraction, (size_t)n * 4, on_device, &dM));
+  CK(q_in(A, bW, world, (size_t)n * 4, on_device, &dW));
+  if (mode == 1) CK(q_out(bC, counts, (size_t)n * 4, on_device, &dC));
+  CK(q_out(bF, fixture, (size_t)n * per * 4, on_device, &dF));
+  CK(q_out(bT, fraction, (size_t)n * per * 4, on_device, &dT));
+  CK(q_out(bN, normal, (size_t)n * per * 8, on_device, &dN));
+  LAUNCH(A, KC_QUERY, n, k_ray_cast, div_up(n, 128), 128, n, (const float4*)dR, (const float*)dM, (const int*)dW, mode,
+         category_mask, A->nFixtures, A->leafBox, A->leafInfo, A->bvhNodes, A->worldFirst, A->worldLast, A->numWorlds,
+         A->fShapeOff, A->shapes, A->xf, cap, (int*)dC, (int*)dF, (float*)dT, (float2*)dN);
+  CK(cudaGetLastError());
+  if (mode == 1) Q_BACK(bC, counts, (size_t)n * 4);
+  Q_BACK(bF, fixture, (size_t)n * per * 4);
+  Q_BACK(bT, fraction, (size_t)n * per * 4);
+  Q_BACK(bN, normal, (size_t)n * per * 8);
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+extern "C" int b2g_ray_cast_closest(b2gArena* A, int32_t n, const float* rays, const float* max_fraction,
+                                    const int32_t* world, uint32_t category_mask, int32_t* fixture, float* fraction,
+                                    float* normal, int32_t on_device) {
+  if (!A || n < 0 || (n > 0 && (!rays || !fixture || !fraction || !normal))) return B2G_ERR_INVALID;
+  return ray_cast_common(A, 0, n, rays, max_fraction, world, category_mask, 1, nullptr, fixture, fraction, normal,
+                         on_device);
+}
+
+extern "C" int b2g_ray_cast_all(b2gArena* A, int32_t n, const float* rays, const float* max_fraction,
+                                const int32_t* world, uint32_t category_mask, int32_t cap, int32_t* counts,
+                                int32_t* fixture, float* fraction, float* normal, int32_t on_device) {
+  if (!A || n < 0 || cap < 0 || (n > 0 && (!rays || !counts || (cap > 0 && (!fixture || !fraction || !normal)))))
+    return B2G_ERR_INVALID;
+  return ray_cast_common(A, 1, n, rays, max_fraction, world, category_mask, cap, counts, fixture, fraction, normal,
+                         on_device);
 }
 
 extern "C" int b2g_download_events(b2gArena* A, int32_t* beginPairs, int32_t* beginCount, int32_t* endPairs,

@@ -326,3 +326,74 @@ void b2GetPointStates(b2PointState state1[b2_maxManifoldPoints], b2PointState st
       }
   }
 }
+
+// ---- single-shape ray casts (host).  Same equations as the device versions in
+// csrc/b2g_query.cuh; restated from b2_circle_shape.cpp:56-89, b2_edge_shape.cpp:89-154,
+// b2_polygon_shape.cpp:303-371. ---------------------------------------------------------------
+bool b2CircleShape::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf) const {
+  const b2Vec2 centre = xf.p + b2Mul(xf.q, m_p);
+  const b2Vec2 s = input.p1 - centre;
+  const b2Vec2 r = input.p2 - input.p1;
+  const float b = b2Dot(s, s) - m_radius * m_radius;
+  const float c = b2Dot(s, r);
+  const float rr = b2Dot(r, r);
+  const float sigma = c * c - rr * b;
+  if (sigma < 0.0f || rr < b2_epsilon) return false;  // line misses the circle, or degenerate segment
+  float a = -(c + b2Sqrt(sigma));
+  if (a < 0.0f || a > input.maxFraction * rr) return false;
+  a /= rr;
+  output->fraction = a;
+  output->normal = s + a * r;
+  output->normal.Normalize();
+  return true;
+}
+
+bool b2EdgeShape::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf) const {
+  // ray in the edge's frame
+  const b2Vec2 p1 = b2MulT(xf.q, input.p1 - xf.p);
+  const b2Vec2 p2 = b2MulT(xf.q, input.p2 - xf.p);
+  const b2Vec2 d = p2 - p1;
+  const b2Vec2 e = m_vertex2 - m_vertex1;
+  b2Vec2 normal(e.y, -e.x);  // to the right of v1 -> v2
+  normal.Normalize();
+  const float numerator = b2Dot(normal, m_vertex1 - p1);
+  if (m_oneSided && numerator > 0.0f) return false;
+  const float denominator = b2Dot(normal, d);
+  if (denominator == 0.0f) return false;
+  const float t = numerator / denominator;
+  if (t < 0.0f || input.maxFraction < t) return false;
+  const b2Vec2 q = p1 + t * d;
+  const float rr = b2Dot(e, e);
+  if (rr == 0.0f) return false;
+  const float along = b2Dot(q - m_vertex1, e) / rr;
+  if (along < 0.0f || 1.0f < along) return false;
+  output->fraction = t;
+  output->normal = numerator > 0.0f ? -b2Mul(xf.q, normal) : b2Mul(xf.q, normal);
+  return true;
+}
+
+bool b2PolygonShape::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf) const {
+  const b2Vec2 p1 = b2MulT(xf.q, input.p1 - xf.p);
+  const b2Vec2 p2 = b2MulT(xf.q, input.p2 - xf.p);
+  const b2Vec2 d = p2 - p1;
+  float enter = 0.0f, leave = input.maxFraction;
+  int32 face = -1;
+  for (int32 i = 0; i < m_count; ++i) {
+    // clip the segment against the half-plane of face i: dot(n, p1 + a d - v) <= 0
+    const float numerator = b2Dot(m_normals[i], m_vertices[i] - p1);
+    const float denominator = b2Dot(m_normals[i], d);
+    if (denominator == 0.0f) {
+      if (numerator < 0.0f) return false;  // parallel and outside
+    } else if (denominator < 0.0f && numerator < enter * denominator) {
+      enter = numerator / denominator;
+      face = i;
+    } else if (denominator > 0.0f && numerator < leave * denominator) {
+      leave = numerator / denominator;
+    }
+    if (leave < enter) return false;
+  }
+  if (face < 0) return false;
+  output->fraction = enter;
+  output->normal = b2Mul(xf.q, m_normals[face]);
+  return true;
+}

@@ -529,6 +529,57 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   return j;
 }
 
+// ---- spatial queries (b2_world.cpp:1193-1246) on the device tree -------------------------------
+void b2World::QueryAABB(b2QueryCallback* callback, const b2AABB& aabb) {
+  b2WorldImpl* I = m_impl;
+  if (!callback) return;
+  I->flush();
+  if (I->arena == nullptr || I->fixtures.empty()) return;
+  const int32 nf = (int32)I->fixtures.size();
+  std::vector<int32_t> found((size_t)nf);
+  int32_t count = 0;
+  const float box[4] = {aabb.lowerBound.x, aabb.lowerBound.y, aabb.upperBound.x, aabb.upperBound.y};
+  b2gCheck(b2g_query_aabb(I->arena, 1, box, nullptr, nf, &count, found.data(), 0), "b2g_query_aabb");
+  count = std::min(count, nf);
+  std::sort(found.begin(), found.begin() + count);
+  for (int32 k = 0; k < count; ++k) {
+    b2Fixture* f = I->fixtures[found[k]];
+    if (f && !callback->ReportFixture(f)) return;
+  }
+}
+
+void b2World::RayCast(b2RayCastCallback* callback, const b2Vec2& point1, const b2Vec2& point2) {
+  b2WorldImpl* I = m_impl;
+  if (!callback) return;
+  I->flush();
+  if (I->arena == nullptr || I->fixtures.empty()) return;
+  const int32 nf = (int32)I->fixtures.size();
+  std::vector<int32_t> fix((size_t)nf);
+  std::vector<float> frac((size_t)nf), nrm((size_t)nf * 2);
+  int32_t count = 0;
+  const float ray[4] = {point1.x, point1.y, point2.x, point2.y};
+  b2gCheck(b2g_ray_cast_all(I->arena, 1, ray, nullptr, nullptr, 0xFFFFu, nf, &count, fix.data(), frac.data(), nrm.data(), 0),
+           "b2g_ray_cast_all");
+  count = std::min(count, nf);
+  std::vector<int32> order((size_t)count);
+  for (int32 k = 0; k < count; ++k) order[k] = k;
+  std::sort(order.begin(), order.end(), [&](int32 a, int32 b) {
+    return frac[a] < frac[b] || (frac[a] == frac[b] && fix[a] < fix[b]);
+  });
+  // replay into the user's callback, nearest first, honouring its clip value (b2_broad_phase.h:690-707)
+  float maxFraction = 1.0f;
+  for (int32 k : order) {
+    if (frac[k] > maxFraction) break;
+    b2Fixture* f = I->fixtures[fix[k]];
+    if (!f) continue;
+    const float fraction = frac[k];
+    const b2Vec2 point = (1.0f - fraction) * point1 + fraction * point2;
+    const float value = callback->ReportFixture(f, point, b2Vec2(nrm[2 * k], nrm[2 * k + 1]), fraction);
+    if (value == 0.0f) return;
+    if (value > 0.0f) maxFraction = value;
+  }
+}
+
 void b2World::DestroyJoint(b2Joint* j) {
   if (IsLocked() || !j) return;
   m_impl->pullJoints();
@@ -1060,6 +1111,9 @@ void b2Fixture::Refilter() {
   m_body->m_world->m_newContacts = true;
 }
 bool b2Fixture::TestPoint(const b2Vec2& p) const { return m_shape->TestPoint(m_body->GetTransform(), p); }
+bool b2Fixture::RayCast(b2RayCastOutput* output, const b2RayCastInput& input) const {
+  return m_shape->RayCast(output, input, m_body->GetTransform());
+}
 void b2Fixture::SetFriction(float v) { m_friction = v; m_body->m_world->m_impl->touchFixture(m_index); }
 void b2Fixture::SetRestitution(float v) { m_restitution = v; m_body->m_world->m_impl->touchFixture(m_index); }
 void b2Fixture::SetRestitutionThreshold(float v) {

@@ -89,6 +89,37 @@ class _Scene:
             self._f("scene_get_aabbs")(self.h, capi.fp(out))
         return out
 
+    # ---- spatial queries through the public C++ API (b2World::QueryAABB / RayCast) ----
+    def query_aabb(self, aabbs, cap):
+        aabbs = np.ascontiguousarray(aabbs, np.float32).reshape(-1, 4)
+        counts = np.zeros(len(aabbs), np.int32)
+        fixtures = np.full((len(aabbs), max(cap, 1)), -1, np.int32)
+        self._f("scene_query_aabb")(self.h, len(aabbs), capi.fp(aabbs), cap, capi.ip(counts), capi.ip(fixtures))
+        return counts, fixtures
+
+    def ray_cast_closest(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 4)
+        n = len(rays)
+        fixture = np.zeros(n, np.int32)
+        fraction = np.zeros(n, np.float32)
+        normal = np.zeros((n, 2), np.float32)
+        point = np.zeros((n, 2), np.float32)
+        self._f("scene_ray_cast_closest")(self.h, n, capi.fp(rays), capi.ip(fixture), capi.fp(fraction), capi.fp(normal),
+                                          capi.fp(point))
+        return fixture, fraction, normal, point
+
+    def ray_cast_all(self, ray, cap):
+        ray = np.ascontiguousarray(ray, np.float32).reshape(4)
+        fixture = np.full(max(cap, 1), -1, np.int32)
+        fraction = np.zeros(max(cap, 1), np.float32)
+        normal = np.zeros((max(cap, 1), 2), np.float32)
+        n = self._f("scene_ray_cast_all")(self.h, capi.fp(ray), cap, capi.ip(fixture), capi.fp(fraction), capi.fp(normal))
+        return n, fixture[:min(n, cap)], fraction[:min(n, cap)], normal[:min(n, cap)]
+
+    def time_ray_casts(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 4)
+        return self._f("scene_time_ray_casts")(self.h, len(rays), capi.fp(rays))
+
     def joints(self):
         """revolute joints: bodies [n,2], anchors [n,4], params [n,8] (include/b2cuda.h b2gJointArrays)"""
         cap = max(self._f("scene_joint_count")(self.h), 1)

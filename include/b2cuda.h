@@ -296,6 +296,37 @@ int b2g_host_alloc(void** out, uint64_t bytes);
 int b2g_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------
+ * Spatial queries on the broadphase tree, batched.  All pointers are host
+ * pointers, or device pointers on the arena's device when on_device != 0 (results then stay in
+ * HBM; the call still returns after the kernel has finished).  world[i] >= 0 restricts query i to
+ * one world of a multi-world arena; NULL or -1 = every world.  The tree reflects the last step or
+ * pair refresh; pending uploads are applied first (b2BroadPhase::EnsureBuiltTree).
+ * ---------------------------------------------------------------------------------------- */
+
+/* b2World::QueryAABB (b2_world.cpp:1193-1207; b2BroadPhase::Query, b2_broad_phase.h:622-643):
+ * aabbs[n][4] = lower.xy, upper.xy.  counts[n] = fixtures whose AABB overlaps (inclusive test,
+ * b2TestOverlap); fixtures[n][cap] = the first cap of them per query, in no particular order. */
+int b2g_query_aabb(b2gArena* arena, int32_t n, const float* aabbs, const int32_t* world, int32_t cap,
+                   int32_t* counts, int32_t* fixtures, int32_t on_device);
+
+/* b2World::RayCast (b2_world.cpp:1226-1246; b2BroadPhase::RayCast, b2_broad_phase.h:645-716;
+ * shape tests b2_circle_shape.cpp:56-89, b2_edge_shape.cpp:89-154, b2_polygon_shape.cpp:303-371)
+ * with the callback every "closest hit" user writes (return fraction): rays[n][4] = p1.xy, p2.xy;
+ * max_fraction[n] or NULL (= 1).  fixture[n] = hit fixture or -1, fraction[n], normal[n][2].
+ * Only fixtures with (categoryBits & category_mask) != 0 are considered.  Equal fractions: the
+ * lower fixture index wins (the reference keeps whichever its tree visits last). */
+int b2g_ray_cast_closest(b2gArena* arena, int32_t n, const float* rays, const float* max_fraction,
+                         const int32_t* world, uint32_t category_mask, int32_t* fixture, float* fraction,
+                         float* normal, int32_t on_device);
+
+/* The same cast with the callback that returns 1 (report everything): counts[n] hits per ray and
+ * the first cap of them in fixture/fraction/normal[n][cap](,[2]), unordered.  The host-side
+ * b2World::RayCast replays these, sorted by fraction, into the user's b2RayCastCallback. */
+int b2g_ray_cast_all(b2gArena* arena, int32_t n, const float* rays, const float* max_fraction,
+                     const int32_t* world, uint32_t category_mask, int32_t cap, int32_t* counts, int32_t* fixture,
+                     float* fraction, float* normal, int32_t on_device);
+
+/* ------------------------------------------------------------------------------------------
  * Kernel-level entry points: each runs ONE production device function over explicit host
  * arrays.  They exist so the parity tests can feed the GPU the oracle's exact ordered inputs
  * (SURVEY.md §7 "Hard parts": A/B order and solver order are traversal dependent).

@@ -49,6 +49,16 @@ inline bool b2TestOverlap(const b2AABB& a, const b2AABB& b) {
          (a.upperBound.y >= b.lowerBound.y) & (a.lowerBound.y <= b.upperBound.y);
 }
 
+/// b2_collision.h:147-160
+struct b2RayCastInput {
+  b2Vec2 p1, p2;
+  float maxFraction;
+};
+struct b2RayCastOutput {
+  b2Vec2 normal;
+  float fraction;
+};
+
 class b2Shape {
  public:
   enum Type { e_circle = 0, e_edge = 1, e_polygon = 2, e_chain = 3, e_typeCount = 4 };
@@ -56,6 +66,8 @@ class b2Shape {
   virtual b2Shape* Clone() const = 0;
   Type GetType() const { return m_type; }
   virtual bool TestPoint(const b2Transform& xf, const b2Vec2& p) const = 0;
+  /// single-shape ray cast on the host (b2_shape.h:90-93); b2World::RayCast runs batched on the device
+  virtual bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf) const = 0;
   virtual void ComputeAABB(b2AABB* aabb, const b2Transform& xf) const = 0;
   virtual void ComputeMass(b2MassData* massData, float density) const = 0;
   /// number of float4 records this shape occupies in the device shape pool
@@ -75,6 +87,7 @@ class b2CircleShape : public b2Shape {
   }
   b2Shape* Clone() const override { return new b2CircleShape(*this); }
   bool TestPoint(const b2Transform& xf, const b2Vec2& p) const override;
+  bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf) const override;
   void ComputeAABB(b2AABB* aabb, const b2Transform& xf) const override;
   void ComputeMass(b2MassData* massData, float density) const override;
   int32 DeviceQuadCount() const override { return 1; }
@@ -97,6 +110,7 @@ class b2EdgeShape : public b2Shape {
   void SetTwoSided(const b2Vec2& v1, const b2Vec2& v2);
   b2Shape* Clone() const override { return new b2EdgeShape(*this); }
   bool TestPoint(const b2Transform& xf, const b2Vec2& p) const override;
+  bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf) const override;
   void ComputeAABB(b2AABB* aabb, const b2Transform& xf) const override;
   void ComputeMass(b2MassData* massData, float density) const override;
   int32 DeviceQuadCount() const override { return 3; }
@@ -119,6 +133,7 @@ class b2PolygonShape : public b2Shape {
   void SetAsBox(float hx, float hy);
   void SetAsBox(float hx, float hy, const b2Vec2& center, float angle);
   bool TestPoint(const b2Transform& xf, const b2Vec2& p) const override;
+  bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf) const override;
   void ComputeAABB(b2AABB* aabb, const b2Transform& xf) const override;
   void ComputeMass(b2MassData* massData, float density) const override;
   bool Validate() const;

@@ -101,6 +101,7 @@ class b2Fixture {
   b2FixtureUserData& GetUserData() { return m_userData; }
   uint32 GetId() { return m_id; }
   bool TestPoint(const b2Vec2& p) const;
+  bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input) const;
   void GetMassData(b2MassData* massData) const { m_shape->ComputeMass(massData, m_density); }
   void SetDensity(float density) { m_density = density; }
   float GetDensity() const { return m_density; }
@@ -484,6 +485,20 @@ struct b2ContactImpulse {
   int32 count;
 };
 
+/// b2_world_callbacks.h:133-161
+class b2QueryCallback {
+ public:
+  virtual ~b2QueryCallback() {}
+  /// return false to terminate the query
+  virtual bool ReportFixture(b2Fixture* fixture) = 0;
+};
+class b2RayCastCallback {
+ public:
+  virtual ~b2RayCastCallback() {}
+  /// return -1 to ignore the fixture, 0 to terminate, a fraction to clip the ray, 1 to continue
+  virtual float ReportFixture(b2Fixture* fixture, const b2Vec2& point, const b2Vec2& normal, float fraction) = 0;
+};
+
 class b2ContactListener {
  public:
   virtual ~b2ContactListener() {}
@@ -519,6 +534,10 @@ class b2World {
   void DestroyBody(b2Body* body);
   b2Joint* CreateJoint(const b2JointDef* def);
   void DestroyJoint(b2Joint* joint);
+  /// b2_world.cpp:1193-1246, on the device's broadphase tree.  Fixtures are reported in ascending
+  /// creation order (QueryAABB) / ascending fraction (RayCast), not in the reference's tree order.
+  void QueryAABB(b2QueryCallback* callback, const b2AABB& aabb);
+  void RayCast(b2RayCastCallback* callback, const b2Vec2& point1, const b2Vec2& point2);
   void Step(float timeStep, int32 velocityIterations, int32 positionIterations, int32 particleIterations);
   void Step(float timeStep, int32 velocityIterations, int32 positionIterations) {
     Step(timeStep, velocityIterations, positionIterations, 1);

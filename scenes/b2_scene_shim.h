@@ -132,6 +132,120 @@ int SHIM(scene_get_contacts)(void* h, int cap, int* fixA, int* fixB, int* flags,
   return n;
 }
 
+// ---- spatial queries through the public API (b2World::QueryAABB / RayCast) ----------------------
+namespace {
+struct ShimQueryAll : b2QueryCallback {
+  Scene* s;
+  std::vector<int> found;
+  bool ReportFixture(b2Fixture* f) override {
+    found.push_back(s->fixtureIndex[f]);
+    return true;
+  }
+};
+struct ShimRayClosest : b2RayCastCallback {
+  Scene* s;
+  int fixture = -1;
+  float fraction = 0.0f;
+  b2Vec2 normal, point;
+  float ReportFixture(b2Fixture* f, const b2Vec2& p, const b2Vec2& n, float fr) override {
+    fixture = s->fixtureIndex[f];
+    fraction = fr;
+    normal = n;
+    point = p;
+    return fr;
+  }
+};
+struct ShimRayClosestLean : b2RayCastCallback {  // what a user's closest-hit callback costs: no index lookup
+  b2Fixture* fixture = nullptr;
+  float fraction = 0.0f;
+  float ReportFixture(b2Fixture* f, const b2Vec2&, const b2Vec2&, float fr) override {
+    fixture = f;
+    fraction = fr;
+    return fr;
+  }
+};
+struct ShimRayAll : b2RayCastCallback {
+  Scene* s;
+  std::vector<int> fixtures;
+  std::vector<float> fractions, normals;
+  float ReportFixture(b2Fixture* f, const b2Vec2&, const b2Vec2& n, float fr) override {
+    fixtures.push_back(s->fixtureIndex[f]);
+    fractions.push_back(fr);
+    normals.push_back(n.x);
+    normals.push_back(n.y);
+    return 1.0f;
+  }
+};
+}  // namespace
+// aabbs[n][4]; counts[n]; fixtures[n][cap] ascending.  Returns the largest count.
+int SHIM(scene_query_aabb)(void* h, int n, const float* aabbs, int cap, int* counts, int* fixtures) {
+  Scene* s = static_cast<Scene*>(h);
+  int most = 0;
+  for (int i = 0; i < n; ++i) {
+    ShimQueryAll cb;
+    cb.s = s;
+    b2AABB box;
+    box.lowerBound.Set(aabbs[4 * i], aabbs[4 * i + 1]);
+    box.upperBound.Set(aabbs[4 * i + 2], aabbs[4 * i + 3]);
+    s->world->QueryAABB(&cb, box);
+    std::sort(cb.found.begin(), cb.found.end());
+    counts[i] = (int)cb.found.size();
+    if (counts[i] > most) most = counts[i];
+    for (int k = 0; k < counts[i] && k < cap; ++k) fixtures[(size_t)i * cap + k] = cb.found[k];
+  }
+  return most;
+}
+// rays[n][4]; fixture[n] (-1 = no hit), fraction[n], normal[n][2], point[n][2]
+void SHIM(scene_ray_cast_closest)(void* h, int n, const float* rays, int* fixture, float* fraction, float* normal,
+                                  float* point) {
+  Scene* s = static_cast<Scene*>(h);
+  for (int i = 0; i < n; ++i) {
+    ShimRayClosest cb;
+    cb.s = s;
+    cb.normal.SetZero();
+    cb.point.SetZero();
+    s->world->RayCast(&cb, b2Vec2(rays[4 * i], rays[4 * i + 1]), b2Vec2(rays[4 * i + 2], rays[4 * i + 3]));
+    fixture[i] = cb.fixture;
+    fraction[i] = cb.fraction;
+    normal[2 * i] = cb.normal.x; normal[2 * i + 1] = cb.normal.y;
+    point[2 * i] = cb.point.x; point[2 * i + 1] = cb.point.y;
+  }
+}
+// every hit of ONE ray (callback returns 1), sorted by (fraction, fixture).  Returns the count.
+int SHIM(scene_ray_cast_all)(void* h, const float* ray, int cap, int* fixtures, float* fractions, float* normals) {
+  Scene* s = static_cast<Scene*>(h);
+  ShimRayAll cb;
+  cb.s = s;
+  s->world->RayCast(&cb, b2Vec2(ray[0], ray[1]), b2Vec2(ray[2], ray[3]));
+  int n = (int)cb.fixtures.size();
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    return cb.fractions[a] < cb.fractions[b] || (cb.fractions[a] == cb.fractions[b] && cb.fixtures[a] < cb.fixtures[b]);
+  });
+  for (int k = 0; k < n && k < cap; ++k) {
+    int i = order[k];
+    fixtures[k] = cb.fixtures[i];
+    fractions[k] = cb.fractions[i];
+    normals[2 * k] = cb.normals[2 * i];
+    normals[2 * k + 1] = cb.normals[2 * i + 1];
+  }
+  return n;
+}
+// wall-clock milliseconds for n closest-hit ray casts (CPU baseline of the query path)
+double SHIM(scene_time_ray_casts)(void* h, int n, const float* rays) {
+  Scene* s = static_cast<Scene*>(h);
+  auto t0 = std::chrono::steady_clock::now();
+  int hits = 0;
+  for (int i = 0; i < n; ++i) {
+    ShimRayClosestLean cb;
+    s->world->RayCast(&cb, b2Vec2(rays[4 * i], rays[4 * i + 1]), b2Vec2(rays[4 * i + 2], rays[4 * i + 3]));
+    hits += cb.fixture != nullptr;
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double, std::milli>(t1 - t0).count() + 0.0 * hits;
+}
+
 int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->GetJointCount(); }
 // revolute joints in creation order: bodies[n][2], anchors[n][4] = localAnchorA.xy, localAnchorB.xy,
 // params[n][8] = referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0

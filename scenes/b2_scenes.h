@@ -14,6 +14,7 @@
 #ifndef B2_SCENES_H
 #define B2_SCENES_H
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
