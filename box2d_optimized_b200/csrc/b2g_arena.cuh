@@ -42,6 +42,10 @@ struct ContactHash {
   unsigned long long* keys;
   int* vals;
   unsigned int mask;  // capacity - 1 (capacity is a power of two)
+  // b2Body::ShouldCollide (b2_body.cpp:396-419): body pairs joined by a joint with
+  // collideConnected == false, as sorted keys bodyLo << 32 | bodyHi (binary search; usually empty)
+  const unsigned long long* ncKeys;
+  int ncCount;
 };
 
 // contacts live in stable slots; a slot is live when its flags carry B2G_CONTACT_ALIVE
@@ -123,6 +127,10 @@ struct b2gArena {
   float4* jParams1;  // motorSpeed, bits(flags), 0, 0
   float4* jState;    // impulse.x, impulse.y, motorImpulse, lowerImpulse
   float* jUpper;     // upperImpulse
+  unsigned long long* ncKeys;     // [capJoints] unsorted, then sorted into ncKeysSorted
+  unsigned long long* ncKeysSorted;
+  uint8_t* bodyNoCollide;         // [capBodies] body has at least one collideConnected == false joint
+  int jointFilterDirty;
   float4* stateStage; // [capBodies][2] packed xf+vel for b2g_download_body_state_async (one linear D2H)
   JointWork* jWork;  // per-step scratch
 

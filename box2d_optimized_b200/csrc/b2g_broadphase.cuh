@@ -127,12 +127,33 @@ __global__ void k_morton_keys(int nf, const float4* __restrict__ fAabb, const ui
   keys[f] = (w << 32) | morton;
 }
 
+// joints with collideConnected == false -> body-pair keys + per-body marks (rebuilt when the joint
+// table changes; b2World::CreateJoint / DestroyJoint flag the pair's contacts for filtering,
+// b2_world.cpp:307-323, 389-405)
+__global__ void k_joint_filter_build(int nj, const int2* __restrict__ jBodies, const float4* __restrict__ jParams1,
+                                     unsigned long long* keys, uint8_t* bodyNoCollide) {
+  B2G_PDL_ENTER();
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nj) return;
+  int2 bd = jBodies[j];
+  uint32_t flags = __float_as_uint(jParams1[j].y);
+  if (flags & 4u) {  // collideConnected
+    keys[j] = 0xffffffffffffffffull;
+    return;
+  }
+  keys[j] = ((unsigned long long)min(bd.x, bd.y) << 32) | (unsigned long long)max(bd.x, bd.y);
+  bodyNoCollide[bd.x] = 1;
+  bodyNoCollide[bd.y] = 1;
+}
+
 // leaves in sorted order: box + everything the pair filter needs in one int4
-//   x = fixture, y = body, z = type | sensor<<2 | dynamic<<3 | dead<<4 | group<<16, w = category | mask<<16
+//   x = fixture, y = body, z = type | sensor<<2 | dynamic<<3 | dead<<4 | noCollideJoint<<5 | group<<16,
+//   w = category | mask<<16
 __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
                               const unsigned long long* __restrict__ keysSorted, const float4* __restrict__ fAabb,
                               const int* __restrict__ fBody, const uint32_t* __restrict__ fTypeFlags,
-                              const uint2* __restrict__ fFilter, const uint32_t* __restrict__ bflags, float4* leafBox,
+                              const uint2* __restrict__ fFilter, const uint32_t* __restrict__ bflags,
+                              const uint8_t* __restrict__ bodyNoCollide, float4* leafBox,
                               int4* leafInfo, unsigned long long* leafKey, int* worldFirst, int* worldLast,
                               int numWorlds, int* nodeVisit) {
   B2G_PDL_ENTER();
@@ -146,7 +167,7 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
   bool dead = (tf & B2G_FIX_DEAD) != 0;
   leafBox[p] = dead ? make_float4(B2G_MAX_FLOAT, B2G_MAX_FLOAT, -B2G_MAX_FLOAT, -B2G_MAX_FLOAT) : fAabb[f];
   unsigned int z = (tf & 3u) | ((tf & B2G_FIX_SENSOR) ? 4u : 0u) | (B2G_BODY_TYPE(bf) == B2G_DYNAMIC ? 8u : 0u) |
-                   (dead ? 16u : 0u) | ((fl.y & 0xffffu) << 16);
+                   (dead ? 16u : 0u) | (bodyNoCollide[b] ? 32u : 0u) | ((fl.y & 0xffffu) << 16);
   leafInfo[p] = make_int4(f, b, (int)z, (int)fl.x);
   nodeVisit[p] = 0;  // new topology: arrival counters restart
   // reporting order: the leaf with the SMALLER (size, position) key reports the pair, so a huge
@@ -374,6 +395,17 @@ __device__ __forceinline__ void hash_erase(const ContactHash& H, unsigned long l
 __device__ __forceinline__ void emit_pair(int4 a, int4 b, const ContactHash& H, uint8_t* persist,
                                           unsigned long long* newPairs, int capacity, StepCounts* counts) {
   if (!pair_passes(a, b)) return;
+  if (((unsigned int)a.z & (unsigned int)b.z & 32u) && H.ncCount > 0) {
+    // both bodies carry a collideConnected == false joint: is it the same joint?
+    unsigned long long bk = ((unsigned long long)min(a.y, b.y) << 32) | (unsigned long long)max(a.y, b.y);
+    int l = 0, r = H.ncCount - 1;
+    while (l <= r) {
+      int m = (l + r) >> 1;
+      unsigned long long v = H.ncKeys[m];
+      if (v == bk) return;
+      if (v < bk) l = m + 1; else r = m - 1;
+    }
+  }
   unsigned long long lo = (unsigned long long)min(a.x, b.x), hi = (unsigned long long)max(a.x, b.x);
   unsigned long long key = (lo << 32) | hi;
   int slot = hash_find(H, key);

@@ -260,6 +260,9 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->jUpper, nj));
   CK(dalloc(&A->jWork, nj));
   CK(dalloc(&A->stateStage, (size_t)nb * 2));
+  CK(dalloc(&A->ncKeys, nj));
+  CK(dalloc(&A->ncKeysSorted, nj));
+  CK(dalloc(&A->bodyNoCollide, nb));
 
   int rc = alloc_contact_buf(A->cb[0], nc);
   if (rc) return rc;
@@ -354,7 +357,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->stateStage, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->stateStage, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->worldFirst, A->worldLast, A->nodeRange, A->bvhNodes, A->leafParent,
                   A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -475,6 +478,13 @@ extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, cons
   }
   if (first + count > A->nJoints) A->nJoints = first + count;
   A->islandsValid = 0;
+  if (s->params || s->bodies) {
+    // the joint table changed: contacts between the joined bodies are re-filtered before the next
+    // Collide (b2World::CreateJoint flags them, b2_world.cpp:307-323)
+    A->jointFilterDirty = 1;
+    A->aabbAllDirty = 1;
+    A->newFixtures = 1;
+  }
   return B2G_OK;
 }
 
@@ -499,6 +509,10 @@ extern "C" int b2g_set_counts(b2gArena* A, int32_t nb, int32_t nf, int32_t nj) {
     return B2G_ERR_INVALID;
   A->nBodies = nb;
   A->nFixtures = nf;
+  if (nj != A->nJoints) {
+    A->jointFilterDirty = 1;
+    A->newFixtures = 1;
+  }
   A->nJoints = nj;
   A->aabbAllDirty = 1;
   A->islandsValid = 0;
@@ -539,6 +553,20 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
     // The LBVH topology is rebuilt (Morton sort + Karras build) when fixtures were added / edited
     // or every B2G_BVH_REBUILD_PERIOD steps; in between only the boxes are refit.  The reported
     // pair set is exact either way — only traversal cost depends on tree quality.
+    if (A->jointFilterDirty) {
+      const int nj = A->nJoints;
+      CK(cudaMemsetAsync(A->bodyNoCollide, 0, (size_t)A->capBodies, A->stream));
+      if (nj > 0) {
+        LAUNCH(A, KC_BP_BUILD, nj, k_joint_filter_build, div_up(nj, 256), 256, nj, A->jBodies, A->jParams1, A->ncKeys,
+               A->bodyNoCollide);
+        size_t tbj = A->cubTempBytes;
+        CK(cub::DeviceRadixSort::SortKeys(A->cubTemp, tbj, A->ncKeys, A->ncKeysSorted, nj, 0, 64, A->stream));
+      }
+      A->hash.ncKeys = A->ncKeysSorted;
+      A->hash.ncCount = nj;  // collideConnected joints sort last as ~0 keys, which match no body pair
+      A->jointFilterDirty = 0;
+      A->aabbAllDirty = A->aabbAllDirty ? A->aabbAllDirty : 1;  // leaf records carry the per-body mark
+    }
     const bool rebuild = A->aabbAllDirty != 0 || A->bvhLeaves != nf || A->bvhAge >= B2G_BVH_REBUILD_PERIOD;
     if (rebuild) {
       int rc = reset_bounds(A);
@@ -554,7 +582,7 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
                                                A->leafFixtureSorted, nf, 0,
                                                32 + (A->numWorlds > 1 ? A->worldBits : 0), A->stream)));
       LAUNCH(A, KC_BP_BUILD, nf, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted,
-             A->fAabb, A->fBody, A->fTypeFlags, A->fFilter, A->bflags, A->leafBox, A->leafInfo, A->leafKey,
+             A->fAabb, A->fBody, A->fTypeFlags, A->fFilter, A->bflags, A->bodyNoCollide, A->leafBox, A->leafInfo, A->leafKey,
              A->worldFirst, A->worldLast, A->numWorlds, A->nodeVisit);
       CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
       if (nf > 1)

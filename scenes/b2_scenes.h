@@ -9,6 +9,7 @@
 //   many_pyramids  `size` copies of it 30 m apart on one ground edge (config 2)
 //   mixed          circles + convex polygons dropped into a 3-box container, LCG seed (config 3)
 //   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
+//   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
 //   hello          unit-test/hello_world.cpp:33-112
 //   falling_squares / falling_circles   benchmarks.h:57-135 (b1, b2)
 #ifndef B2_SCENES_H
@@ -230,6 +231,35 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
         jd.maxMotorTorque = 40.0f;
       }
       s->world->CreateJoint(&jd);
+    }
+  } else if (name == "chain" || name == "chain_collide") {
+    // a chain of overlapping links hinged end to end (cf. testbed/tests/chain.cpp:31-66), swinging
+    // down onto a ground edge: joined neighbours overlap but must not collide unless
+    // collideConnected is set (b2Body::ShouldCollide, b2_body.cpp:396-419); non-neighbours do
+    int n = size > 0 ? size : 12;
+    b2BodyDef gd;
+    b2Body* ground = s->addBody(gd);
+    b2EdgeShape edge;
+    edge.SetTwoSided(b2Vec2(-40.0f, 0.0f), b2Vec2(40.0f, 0.0f));
+    s->addFixture(ground, edge, 0.0f);
+    b2PolygonShape link;
+    link.SetAsBox(0.6f, 0.125f);
+    b2FixtureDef fd;
+    fd.shape = &link;
+    fd.density = 20.0f;
+    fd.friction = 0.2f;
+    b2Body* prev = ground;
+    for (int i = 0; i < n; ++i) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(0.5f + (float)i, 6.0f);
+      b2Body* body = s->addBody(bd);
+      s->addFixture(body, fd);
+      b2RevoluteJointDef jd;
+      jd.Initialize(prev, body, b2Vec2((float)i, 6.0f));
+      jd.collideConnected = (name == "chain_collide");
+      s->world->CreateJoint(&jd);
+      prev = body;
     }
   } else if (name == "hello") {
     s->velocityIterations = 6;

@@ -121,7 +121,11 @@ def test_capacity_overflow_is_reported_not_truncated():
 
 @pytest.mark.parametrize("name,size,steps", [("pyramid", 20, 1), ("pyramid", 20, 90), ("many_pyramids", 12, 60),
                                               ("mixed", 3000, 120), ("tumbler", 150, 200),
-                                              ("falling_squares", 300, 100)])
+                                              ("falling_squares", 300, 100),
+                                              # joined neighbours overlap: b2Body::ShouldCollide filters them
+                                              # unless collideConnected is set; folded non-neighbours collide
+                                              ("chain", 14, 0), ("chain", 14, 90), ("chain", 14, 200),
+                                              ("chain_collide", 14, 1), ("chain_collide", 14, 120)])
 def test_live_reference_pair_set_and_order(require_ref, name, size, steps):
     """pair set == the reference's contact set on the reference's own transforms; A/B order of
     mixed-type pairs follows the reference's function table"""
