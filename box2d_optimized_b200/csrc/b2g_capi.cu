@@ -623,6 +623,9 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
     snprintf(msg, sizeof(msg), "broadphase needs %d contact slots (%d new pairs), max_contacts is %d",
              nSlots + appended, nNew, A->capContacts);
     set_err("b2g_step", msg);
+    // the sweep above already ran: keep the live count right so the caller can download the
+    // surviving contacts, grow, and let the next pair refresh find the pairs dropped here
+    A->nAlive -= A->hCounts->numDead;
     return B2G_ERR_CAPACITY;
   }
   if (nNew > 0) {
@@ -1112,9 +1115,9 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
 
     // ---- FindNewContacts (end of Solve, b2_world.cpp:663-669) ------------------------
     int rc = find_new_contacts(A, P->record_events);
+    A->invDt0 = inv_dt;  // the solve is complete even if the pair list could not grow
     if (rc) return rc;
     if (prof) CK(cudaEventRecord(A->ev[3], A->stream));
-    A->invDt0 = inv_dt;
   } else {
     if (prof) {
       CK(cudaEventRecord(A->ev[2], A->stream));

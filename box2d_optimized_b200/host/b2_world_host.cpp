@@ -64,6 +64,14 @@ struct b2WorldImpl {
   }
   static uint64_t key(int32 a, int32 b) { return ((uint64_t)(uint32)a << 32) | (uint32)b; }
 
+  // device-only state carried across an arena re-creation (contacts keep manifolds + impulses)
+  struct SavedContacts {
+    std::vector<int32_t> fa, fb;
+    std::vector<uint32_t> flags;
+    std::vector<float> man, mat;
+  } saved;
+  void saveDeviceState();
+  void growContacts();
   void ensureArena();
   void flush();
   void pullBodies();
@@ -80,8 +88,9 @@ void b2WorldImpl::ensureArena() {
       needJoints <= capJoints)
     return;
   if (arena) {
-    // grow: pull everything the host does not own (body state, contacts are rebuilt), recreate
-    pullBodies();
+    // grow: pull everything the host does not own (body state, joint impulses, contacts with their
+    // manifolds and warm-start impulses), recreate, re-upload at the end of flush()
+    saveDeviceState();
     b2gCheck(b2g_arena_destroy(arena), "b2g_arena_destroy");
     arena = nullptr;
     contactsStale = true;
@@ -95,6 +104,7 @@ void b2WorldImpl::ensureArena() {
   capFixtures = grow(capFixtures, needFixtures, g_defaultFixtures);
   capQuads = grow(capQuads, needQuads, std::max(g_defaultFixtures * 5, 1024));
   capContacts = std::max(capContacts, g_defaultContacts);
+  while (capContacts < (int32)saved.fa.size() * 2) capContacts *= 2;
   capJoints = grow(capJoints, needJoints, 64);
   b2gArenaDef def;
   memset(&def, 0, sizeof(def));
@@ -121,6 +131,40 @@ void b2WorldImpl::ensureArena() {
   jointsDirty = needJoints > 0;
   jointsOnDevice = 0;
   world->m_newContacts = true;
+}
+
+void b2WorldImpl::saveDeviceState() {
+  pullBodies();
+  pullJoints();
+  int32 n = 0;
+  b2gCheck(b2g_contact_count(arena, &n), "b2g_contact_count");
+  saved.fa.assign(n, 0);
+  saved.fb.assign(n, 0);
+  saved.flags.assign(n, 0);
+  saved.man.assign((size_t)n * 16, 0.0f);
+  saved.mat.assign((size_t)n * 4, 0.0f);
+  if (n > 0) {
+    b2gContactArrays a;
+    memset(&a, 0, sizeof(a));
+    a.fixture_a = saved.fa.data(); a.fixture_b = saved.fb.data(); a.flags = saved.flags.data();
+    a.manifold = saved.man.data(); a.material = saved.mat.data();
+    b2gCheck(b2g_download_contacts(arena, 0, n, &a), "b2g_download_contacts");
+  }
+}
+
+// max_contacts was too small for the pairs found at the end of the step that just ran (the step
+// itself is complete): double it, keeping every contact; the next Step's pair refresh inserts the
+// pairs that did not fit (include/b2cuda.h, "B2G_ERR_CAPACITY from a step")
+void b2WorldImpl::growContacts() {
+  bodiesStale = true;
+  jointsStale = true;
+  saveDeviceState();
+  b2gCheck(b2g_arena_destroy(arena), "b2g_arena_destroy");
+  arena = nullptr;
+  capContacts *= 2;
+  fprintf(stderr, "[b2cuda] contact capacity grown to %d\n", capContacts);
+  flush();
+  contactsStale = true;
 }
 
 // upload everything the host changed since the last step
@@ -217,6 +261,17 @@ void b2WorldImpl::flush() {
     if (n > 0) b2gCheck(b2g_upload_joints(arena, 0, n, &a), "b2g_upload_joints");
     jointsOnDevice = n;
     jointsDirty = false;
+  }
+  if (!saved.fa.empty()) {
+    // contacts carried over from the previous arena; pairs whose fixture died meanwhile are retired
+    // by the pair refresh that starts the next step
+    b2gContactArrays a;
+    memset(&a, 0, sizeof(a));
+    a.fixture_a = saved.fa.data(); a.fixture_b = saved.fb.data(); a.flags = saved.flags.data();
+    a.manifold = saved.man.data(); a.material = saved.mat.data();
+    b2gCheck(b2g_upload_contacts(arena, (int32_t)saved.fa.size(), &a), "b2g_upload_contacts");
+    saved = SavedContacts();
+    world->m_newContacts = true;
   }
 }
 
@@ -617,7 +672,12 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
   }
   // new fixtures / moved bodies: refresh the pair list first (b2_world.cpp:1114-1122)
   if (m_newContacts) {
-    b2gCheck(b2g_find_new_contacts(I->arena), "b2g_find_new_contacts");
+    int rc = b2g_find_new_contacts(I->arena);
+    for (int attempt = 0; rc == B2G_ERR_CAPACITY && attempt < 8; ++attempt) {
+      I->growContacts();  // keeps every contact, doubles max_contacts
+      rc = b2g_find_new_contacts(I->arena);
+    }
+    b2gCheck(rc, "b2g_find_new_contacts");
     m_newContacts = false;
     I->contactsStale = true;
   }
@@ -634,7 +694,12 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
   P.record_events = m_contactListener ? 1 : 0;
 
   if (m_contactListener == nullptr) {
-    b2gCheck(b2g_step(I->arena, &P, &I->lastStats), "b2g_step");
+    int rc = b2g_step(I->arena, &P, &I->lastStats);
+    if (rc == B2G_ERR_CAPACITY) {
+      I->growContacts();
+      rc = B2G_OK;
+    }
+    b2gCheck(rc, "b2g_step");
   } else {
     // callbacks need the contact list between Collide and Solve (b2_contact.cpp:197-209)
     I->pullContacts();  // previous manifolds, for PreSolve's oldManifold
@@ -666,7 +731,12 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
       }
     }
     I->pushContactOverrides();
-    b2gCheck(b2g_step_solve(I->arena, &P, &I->lastStats), "b2g_step_solve");
+    int rc = b2g_step_solve(I->arena, &P, &I->lastStats);
+    if (rc == B2G_ERR_CAPACITY) {
+      I->growContacts();
+      rc = B2G_OK;
+    }
+    b2gCheck(rc, "b2g_step_solve");
     // the broadphase at the end of the step rebuilt the list; handles of contacts that died are
     // parked in the graveyard (still valid) until the callbacks below have run
     I->contactsStale = true;

@@ -214,6 +214,12 @@ int b2g_upload_forces(b2gArena* arena, int32_t first, int32_t count, const float
 /* b2World::Step (src/dynamics/b2_world.cpp:1108-1171): Collide -> Solve (islands, contact
  * solver, integration, sleep) -> FindNewContacts -> ClearForces, all on the device. */
 int b2g_step(b2gArena* arena, const b2gStepParams* params, b2gStepStats* stats);
+/* B2G_ERR_CAPACITY from a step means max_contacts was too small for the pairs found at the END of
+ * the step: bodies, joints and the surviving contacts are final and consistent, only the new
+ * pairs were not inserted.  Nothing is dropped silently: download the state, create a larger
+ * arena, upload (b2g_upload_contacts keeps manifolds and impulses) and carry on — the next step's
+ * pair refresh creates the missing contacts exactly when the reference would first use them.
+ * host/b2_world_host.cpp does this automatically. */
 
 /* The same step in two halves, for hosts that must run b2ContactListener::PreSolve between
  * the narrowphase and the solver (b2_contact.cpp:197-209 fires inside Collide):

@@ -271,6 +271,45 @@ static void revolute_joint_api() {
   CHECK(rod->GetLinearVelocity().y < 0.0f || rod->GetPosition().y < -2.0f);  // free fall now
 }
 
+// a pyramid settles to the same place whether or not the contact buffers had to grow on the way
+// (reference: b2BlockAllocator / b2GrowableStack grow transparently; §8(b) "grow-and-retry, never drop")
+static float pyramid_top_height(int rows) {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2EdgeShape edge;
+  edge.SetTwoSided(b2Vec2(-40.0f, 0.0f), b2Vec2(40.0f, 0.0f));
+  ground->CreateFixture(&edge, 0.0f);
+  b2PolygonShape box;
+  box.SetAsBox(0.5f, 0.5f);
+  b2Body* top = nullptr;
+  for (int i = 0; i < rows; ++i)
+    for (int j = i; j < rows; ++j) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(-7.0f + 0.5625f * (float)i + 1.125f * (float)(j - i), 0.75f + 1.25f * (float)i);
+      top = world.CreateBody(&bd);
+      top->CreateFixture(&box, 5.0f);
+    }
+  for (int i = 0; i < 200; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(world.GetContactCount() > rows * rows / 2);
+  return top->GetPosition().y;
+}
+static void contact_buffers_grow() {
+  const int rows = 12;
+#ifdef B2G_WORLD_H
+  b2World::SetDefaultCapacity(1 << 10, 1 << 10, 64);  // 78 boxes need ~220 contacts: grows twice
+#endif
+  float small = pyramid_top_height(rows);
+#ifdef B2G_WORLD_H
+  b2World::SetDefaultCapacity(1 << 16, 1 << 16, 1 << 18);
+#endif
+  float large = pyramid_top_height(rows);
+  CHECK(small > 11.5f && small < 11.8f);  // 12 rows of unit boxes plus their skins (reference: 11.6345)
+  CHECK(fabsf(small - large) < 0.01f);
+  printf("pyramid top: %.6f (grown buffers) %.6f (large buffers)\n", small, large);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -279,6 +318,7 @@ int main() {
   locked_world_is_silent();
   body_list_order();
   revolute_joint_api();
+  contact_buffers_grow();
   printf(g_failed ? "FAILED %d checks\n" : "all API checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }
