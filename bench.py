@@ -67,14 +67,14 @@ WORKLOADS = {
     "pyramid_worlds": ("pyramid", 20, 0, "512 independent 20-row pyramid worlds per GPU (108k bodies), one arena"),
     # BASELINE config 4 shape: motor-driven tumbler (benchmarks.h b3) with 500 boxes per world; the
     # scene is stepped to the state where every box has been spawned, then replicated per world
-    "tumbler_worlds": ("tumbler", 500, 0, "256 independent 500-box tumbler worlds per GPU (128k bodies), one arena"),
+    "tumbler_worlds": ("tumbler", 500, 0, "config 4: 1024 independent 500-box tumbler worlds per GPU (8192 on 8 GPUs; 514k bodies per arena)"),
     # BASELINE config 5 shape: ONE world cut into x-slabs, one per GPU, ghost layer refreshed by a
     # per-step NCCL halo exchange (strong scaling: the world is fixed, the slab shrinks with N)
     "mixed_slab_400k": ("mixed", 400000, 12345, "one 400k-body world, x-slab per GPU, per-step NCCL halo exchange"),
     "mixed_slab_1m": ("mixed", 1000000, 12345, "one 1M-body world, x-slab per GPU, per-step NCCL halo exchange"),
 }
 SLAB = {"mixed_slab_400k", "mixed_slab_1m"}
-WORLDS_PER_GPU = {"pyramid_worlds": 512, "tumbler_worlds": 256}
+WORLDS_PER_GPU = {"pyramid_worlds": 512, "tumbler_worlds": 1024}
 PRESTEP = {"tumbler_worlds": 520}  # steps run through the drop-in API before the state is replicated
 
 

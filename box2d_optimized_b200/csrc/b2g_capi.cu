@@ -888,6 +888,37 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   int binSize = nb / (2 * 148);
   if (binSize < 32) binSize = 32;
   if (binSize > 512) binSize = 512;
+  // Resident blocks per SM.  An island's colour passes and its serial bucket are latency chains
+  // (one barrier / one constraint deep), so with many mid-size islands (batched tumbler worlds:
+  // one 500-body island with a 100-constraint serial chain per world) throughput comes from
+  // overlapping MANY islands per SM, not from keeping one island's planes in shared memory:
+  // smaller blocks (128 threads, 4 per SM) with just the body tile in shared memory and the planes
+  // in L2: 1024 tumbler worlds 6.3 -> 3.5 ms/step.  Pyramid-like islands (6 colours, no serial
+  // bucket) are faster with their planes in shared memory: two or one fat blocks per SM as before.
+  // B2G_FUSED_CTAS=n overrides the choice (measurements).
+  static int ctasOverride = -1;
+  if (ctasOverride < 0) {
+    const char* e = getenv("B2G_FUSED_CTAS");
+    ctasOverride = e ? atoi(e) : 0;
+  }
+  int fusedThreads = B2G_FUSED_THREADS;
+  size_t budget = 0;
+  {
+    int want = ctasOverride;
+    // chain-heavy = at least 4 % of last step's solver rows sat in serial buckets (hub bodies)
+    if (want == 0)
+      want = (nb / binSize + 1 >= 4 * 148 && bigThr >= 128 && A->lastActive > 0 &&
+              (long long)A->lastOverflow * 25 >= A->lastActive) ? 4 : 2;
+    if (want > 2) {
+      size_t per = (size_t)(227 * 1024) / want - 2048;
+      int fit = (int)(per / (FusedTile::bytes(1024) / 1024)) - bigThr;  // bodies of small islands that still fit next to one big one
+      if (fit >= 32) {
+        if (binSize > fit) binSize = fit;
+        budget = per;
+        fusedThreads = 128;
+      }
+    }
+  }
   const int nbins = nb / binSize + 1;
   const int bigBin = nbins;  // sorts after every fused bin
   if (nbins + 1 > A->nbinsMax) {
@@ -896,9 +927,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   }
   const int tileCap = binSize - 1 + bigThr;
   const size_t tileBytes = FusedTile::bytes(tileCap);
-  // two blocks per SM when the tile allows it (113 KB each), otherwise one large block
-  size_t budget = tileBytes + 32 * 1024 <= 113 * 1024 ? 113 * 1024 : 225 * 1024;
-  int conCap = (int)((budget - tileBytes) / (B2G_PLANES * 16));
+  // otherwise: two blocks per SM when the tile allows it (113 KB each), or one large block
+  if (budget == 0) budget = tileBytes + 32 * 1024 <= 113 * 1024 ? 113 * 1024 : 225 * 1024;
+  int conCap = budget > tileBytes ? (int)((budget - tileBytes) / (B2G_PLANES * 16)) : 0;
   if (conCap < 0) conCap = 0;
   const size_t smem = tileBytes + (size_t)conCap * B2G_PLANES * 16;
 
@@ -959,6 +990,8 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     A->lastNumBig = numBig;
     out.numColours = A->hCounts->numColours;
     out.numOverflow = A->hCounts->numOverflow + A->hCounts->remaining;
+    A->lastOverflow = out.numOverflow;
+    A->lastActive = numActive;
     if (numActive > 0) {
       LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
       LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
@@ -990,7 +1023,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       A->fusedSmemSet = smem;
     }
     ktime_begin(A, KC_FUSED_SOLVE, (double)numActive - numBig);
-    launch_pdl(A->stream, dim3(nbins), dim3(B2G_FUSED_THREADS), smem, k_solve_bins_fused,
+    launch_pdl(A->stream, dim3(nbins), dim3(fusedThreads), smem, k_solve_bins_fused,
         FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->bucketStart,
         A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts,
         joint_views(A));
