@@ -950,61 +950,68 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
          A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr);
 
   int numActive = 0, numBig = 0, rounds = 0;
+  // Colouring rounds.  Constraints of tile-sized islands that are still uncoloured after the rounds
+  // launched simply go to their bin's serial overflow bucket for this step (a handful per bin; they
+  // keep colour -1 and retry next step, when their neighbours are already coloured), so no
+  // convergence loop is needed for them.  Constraints of big islands must all be coloured (their
+  // overflow bucket is one thread for the whole GPU), so there the loop runs to convergence.
+  int round = 0;
+  int cgrid = div_up(nc > 0 ? nc : 1, 256);
+  if (cgrid > 148 * 8) cgrid = 148 * 8;
+  auto colour_rounds = [&](int n) {
+    for (int r = 0; r < n; ++r, ++round) {
+      LAUNCH(A, KC_COLOUR, nc, k_colour2_propose, cgrid, 256, nc, A->cbin, C, A->mass, A->bodyBest, round);
+      LAUNCH(A, KC_COLOUR, nc, k_colour2_commit, cgrid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->bodyBest,
+             round, A->dCounts, r == n - 1, bigBin);
+    }
+  };
+  auto bucket_sort = [&]() {
+    LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
+    LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
+    LAUNCH(A, KC_COLOUR, nc, k_bucket_scatter, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketStart, A->conVals,
+           A->sortedList);
+  };
+  auto converge = [&]() -> int {  // hCounts holds the state after the rounds launched so far
+    while (A->hCounts->remaining != 0 && A->hCounts->numBig != 0) {
+      if (round > 250) {
+        set_err("b2g_step", "graph colouring did not converge");
+        return B2G_ERR_CUDA;
+      }
+      CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
+      colour_rounds(4);
+      int rc = read_counts(A);
+      if (rc) return rc;
+    }
+    return B2G_OK;
+  };
+  // The mid-step readback (colouring state, size of the big set).  When the previous step had no
+  // oversize island the answer is almost always "none" again, so the copy is only ENQUEUED and is
+  // waited for after the bucket sort and the fused kernel have been queued behind it: the host
+  // wait then overlaps the GPU's work instead of draining the stream.
+  const bool speculative = nc > 0 && A->lastNumBig == 0 && !A->kernelTiming;
   if (nc > 0) {
     LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->bflags, A->island,
            A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->recolour, binSize, bigThr, bigBin, A->dCounts,
            A->mass, A->colourMask);
     A->recolour = 0;
-    int grid = div_up(nc, 256);
-    if (grid > 148 * 8) grid = 148 * 8;
-    // Colouring rounds.  Constraints of tile-sized islands that are still uncoloured after the
-    // rounds launched simply go to their bin's serial overflow bucket for this step (a handful per
-    // bin; they keep colour -1 and retry next step, when their neighbours are already coloured),
-    // so no convergence loop is needed for them.  Constraints of big islands must all be coloured
-    // (their overflow bucket is one thread for the whole GPU), so there the loop runs to convergence.
-    int round = 0;
-    int batch = A->lastNumBig > 0 ? A->roundsHint : 2;
-    while (true) {
-      if (round > 0) CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
-      for (int r = 0; r < batch; ++r, ++round) {
-        LAUNCH(A, KC_COLOUR, nc, k_colour2_propose, grid, 256, nc, A->cbin, C, A->mass, A->bodyBest, round);
-        LAUNCH(A, KC_COLOUR, nc, k_colour2_commit, grid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->bodyBest,
-               round, A->dCounts, r == batch - 1, bigBin);
-      }
-      int rc = read_counts(A);  // the mid-step readback
+    colour_rounds(A->lastNumBig > 0 ? A->roundsHint : 2);
+    if (speculative) {
+      CK(cudaMemcpyAsync(A->hCounts, A->dCounts, sizeof(StepCounts), cudaMemcpyDeviceToHost, A->stream));
+      CK(cudaEventRecord(A->ev[4], A->stream));
+      bucket_sort();
+    } else {
+      int rc = read_counts(A);
       if (rc) return rc;
-      if (A->hCounts->remaining == 0 || A->hCounts->numBig == 0) break;
-      if (round > 250) {
-        set_err("b2g_step", "graph colouring did not converge");
-        return B2G_ERR_CUDA;
-      }
-      batch = 4;
-    }
-    rounds = round;
-    {
-      int useful = A->hCounts->lastUsefulRound;
-      A->roundsHint = useful < 1 ? 1 : (useful + 1 < 16 ? useful + 1 : 16);
-    }
-    numActive = A->hCounts->numActive;
-    numBig = A->hCounts->numBig;
-    A->lastNumBig = numBig;
-    out.numColours = A->hCounts->numColours;
-    out.numOverflow = A->hCounts->numOverflow + A->hCounts->remaining;
-    A->lastOverflow = out.numOverflow;
-    A->lastActive = numActive;
-    if (numActive > 0) {
-      LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
-      LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
-      LAUNCH(A, KC_COLOUR, nc, k_bucket_scatter, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketStart, A->conVals,
-             A->sortedList);
+      rc = converge();
+      if (rc) return rc;
+      if (A->hCounts->numActive > 0) bucket_sort();
     }
   }
-  A->lastMaxIsland = nc > 0 ? A->hCounts->maxIslandBodies : 0;
 
   // ---- every island that fits a tile: one launch -----------------------------------------------
   {
     FusedParams FP;
-    FP.nc = numActive > 0 ? nc : 0;
+    FP.nc = (speculative || (nc > 0 && A->hCounts->numActive > 0)) ? nc : 0;
     FP.binSize = binSize;
     FP.h = h;
     FP.dtRatio = dtRatio;
@@ -1022,7 +1029,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       CK(cudaFuncSetAttribute(k_solve_bins_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       A->fusedSmemSet = smem;
     }
-    ktime_begin(A, KC_FUSED_SOLVE, (double)numActive - numBig);
+    ktime_begin(A, KC_FUSED_SOLVE, nc > 0 && !speculative ? (double)A->hCounts->numActive - A->hCounts->numBig : 0.0);
     launch_pdl(A->stream, dim3(nbins), dim3(fusedThreads), smem, k_solve_bins_fused,
         FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->bucketStart,
         A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts,
@@ -1030,6 +1037,31 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     ktime_end(A);
     A->launches++;
   }
+
+  if (nc > 0) {
+    if (speculative) {
+      CK(cudaEventSynchronize(A->ev[4]));  // the copy finished long ago; the fused kernel is still running
+      if (A->hCounts->numBig > 0) {
+        // an oversize island appeared this step: finish its colouring and sort again (the fused
+        // kernel has consumed its own buckets; the big bin is all the big path reads)
+        int rc = converge();
+        if (rc) return rc;
+        CK(cudaMemsetAsync(A->bucketCount, 0, sizeof(int) * (size_t)nbuckets, A->stream));
+        bucket_sort();
+      }
+    }
+    rounds = round;
+    int useful = A->hCounts->lastUsefulRound;
+    A->roundsHint = useful < 1 ? 1 : (useful + 1 < 16 ? useful + 1 : 16);
+    numActive = A->hCounts->numActive;
+    numBig = A->hCounts->numBig;
+    A->lastNumBig = numBig;
+    out.numColours = A->hCounts->numColours;
+    out.numOverflow = A->hCounts->numOverflow + A->hCounts->remaining;
+    A->lastOverflow = out.numOverflow;
+    A->lastActive = numActive;
+  }
+  A->lastMaxIsland = nc > 0 ? A->hCounts->maxIslandBodies : 0;
 
   // ---- oversize islands: per-colour launches over the whole GPU --------------------------------
   if (numBig > 0 || (nc == 0 && false)) {
