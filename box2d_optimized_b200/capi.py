@@ -67,12 +67,12 @@ class StepStats(C.Structure):
     _fields_ = [("num_bodies", C.c_int32), ("num_fixtures", C.c_int32), ("num_contacts", C.c_int32),
                 ("num_touching", C.c_int32), ("num_constraints", C.c_int32), ("num_colours", C.c_int32),
                 ("num_overflow", C.c_int32), ("num_awake", C.c_int32), ("num_pairs", C.c_int32),
-                ("colour_rounds", C.c_int32), ("num_launches", C.c_int32), ("reserved", C.c_int32),
+                ("colour_rounds", C.c_int32), ("num_launches", C.c_int32), ("bp_max_visits", C.c_int32),
                 ("ms_collide", C.c_float), ("ms_solve", C.c_float), ("ms_broadphase", C.c_float),
-                ("ms_step", C.c_float)]
+                ("ms_step", C.c_float), ("bp_mean_visits", C.c_float), ("bp_rebuilt", C.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
 # every symbol include/b2cuda.h declares (checked by tests/test_capi_symbols.py)

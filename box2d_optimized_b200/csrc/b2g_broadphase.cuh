@@ -14,6 +14,7 @@
 // reporting each pair once (by its smaller-AABB member); a hash probe either flags the pair's
 // existing contact as persisting or queues the pair (warp-aggregated compaction) for creation.
 #pragma once
+#include <cooperative_groups/reduce.h>
 #include "b2g_step_kernels.cuh"
 
 // tight AABBs for fixtures of non-static bodies (b2_broad_phase.h:265-276); static AABBs are
@@ -445,9 +446,11 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
   }
   int stack[64];
   int sp = 0;
+  int visits = 0;
   stack[sp++] = 0;
   while (sp > 0) {
     int node = stack[--sp];
+    ++visits;
     const float4* q = reinterpret_cast<const float4*>(&nodes[node]);
     float4 bl = __ldg(q), br = __ldg(q + 1), mk4 = __ldg(q + 2);
     int4 nr = __ldg(reinterpret_cast<const int4*>(q + 3));
@@ -462,6 +465,16 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
     if (mkR > myKey && nr.y + 1 <= we && nr.z >= ws && aabb_overlap(qbox, br)) {
       if (nr.y + 1 == nr.z) emit_pair(me, leafInfo[nr.z], H, persist, newPairs, capacity, counts);
       else stack[sp++] = nr.y + 1;
+    }
+  }
+  // tree-quality counters for the adaptive rebuild (one atomic per warp)
+  {
+    auto g = cg::coalesced_threads();
+    int total = cg::reduce(g, visits, cg::plus<int>());
+    int most = cg::reduce(g, visits, cg::greater<int>());
+    if (g.thread_rank() == 0) {
+      atomicAdd(&counts->bpVisits, (unsigned long long)total);
+      atomicMax(&counts->bpMaxVisits, most);
     }
   }
 }

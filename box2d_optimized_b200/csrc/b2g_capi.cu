@@ -1208,6 +1208,9 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
     stats->num_overflow = numOverflow;
     stats->num_awake = A->hCounts->numAwake;
     stats->num_pairs = A->hCounts->numPairs;
+    stats->bp_max_visits = A->hCounts->bpMaxVisits;
+    stats->bp_mean_visits = A->nFixtures > 0 ? (float)((double)A->hCounts->bpVisits / A->nFixtures) : 0.0f;
+    stats->bp_rebuilt = A->bvhAge == 0 ? 1 : 0;
     stats->colour_rounds = rounds;
     stats->num_launches = (int)(A->launches - launches0);
     if (prof) {

@@ -181,8 +181,10 @@ typedef struct b2gStepStats {
   int32_t num_pairs;       /* candidate pairs reported by the broadphase */
   int32_t colour_rounds;   /* colouring rounds launched */
   int32_t num_launches;    /* kernels launched by this step (ours; excludes CUB's) */
-  int32_t reserved;
+  int32_t bp_max_visits;   /* tree nodes visited by the longest pair-finder walk (b2World::GetTreeHeight's role: tree quality) */
   float ms_collide, ms_solve, ms_broadphase, ms_step; /* CUDA-event times, 0 unless profiling on */
+  float bp_mean_visits;    /* tree nodes visited per fixture by the pair finder */
+  int32_t bp_rebuilt;      /* 1 when this step re-sorted and rebuilt the tree instead of refitting it */
 } b2gStepStats;
 
 const char* b2g_last_error(void);
