@@ -158,10 +158,9 @@ struct b2gArena {
   unsigned long long* leafKey;  // (AABB size bits, sorted position): who reports a pair
   int* worldFirst;
   int* worldLast;
-  int4* nodeRange;  // first, split, last, parent
-  struct BvhNode* bvhNodes;     // 64-byte traversal records, one per internal node
-  int* leafParent;
-  int* nodeVisit;
+  float4* bvhBox;               // implicit 8-wide tree: boxes of the internal levels (b2g_broadphase.cuh)
+  unsigned long long* bvhKey;   // and the largest leaf key below each node
+  int* bvhDone;                 // last-block-done counter of the refit
   unsigned long long *pairKeys;  // new pairs (no live contact yet) reported by the traversal
 
   // solver scratch

@@ -117,8 +117,13 @@ __global__ void k_morton_keys(int nf, const float4* __restrict__ fAabb, const ui
   float lox = float_unflip(counts->boundsLo[0]), loy = float_unflip(counts->boundsLo[1]);
   float hix = float_unflip(counts->boundsHi[0]), hiy = float_unflip(counts->boundsHi[1]);
   float ex = hix - lox, ey = hiy - loy;
-  float sx = ex > 0.0f ? 65535.0f / ex : 0.0f;
-  float sy = ey > 0.0f ? 65535.0f / ey : 0.0f;
+  // ONE scale for both axes: square cells.  Per-axis scaling made the cells of a wide, flat world
+  // (100 pyramids side by side: 3 km x 20 m) 150 times wider than tall, so the y bits below a
+  // box height were noise that scrambled the order along x — runs of consecutive leaves spanned
+  // ~90 m and every query walked three to four nodes per tree level.
+  float em = fmaxf(ex, ey);
+  float sx = em > 0.0f ? 65535.0f / em : 0.0f;
+  float sy = sx;
   float4 box = fAabb[f];
   float cx = box.x + box.z, cy = box.y + box.w;
   unsigned int qx = (unsigned int)fminf(fmaxf((cx - lox) * sx, 0.0f), 65535.0f);
@@ -156,7 +161,7 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
                               const uint2* __restrict__ fFilter, const uint32_t* __restrict__ bflags,
                               const uint8_t* __restrict__ bodyNoCollide, float4* leafBox,
                               int4* leafInfo, unsigned long long* leafKey, int* worldFirst, int* worldLast,
-                              int numWorlds, int* nodeVisit) {
+                              int numWorlds) {
   B2G_PDL_ENTER();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nf) return;
@@ -170,7 +175,6 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
   unsigned int z = (tf & 3u) | ((tf & B2G_FIX_SENSOR) ? 4u : 0u) | (B2G_BODY_TYPE(bf) == B2G_DYNAMIC ? 8u : 0u) |
                    (dead ? 16u : 0u) | (bodyNoCollide[b] ? 32u : 0u) | ((fl.y & 0xffffu) << 16);
   leafInfo[p] = make_int4(f, b, (int)z, (int)fl.x);
-  nodeVisit[p] = 0;  // new topology: arrival counters restart
   // reporting order: the leaf with the SMALLER (size, position) key reports the pair, so a huge
   // AABB (ground edge, container wall) never walks the tree for its thousands of partners —
   // they each find it instead.  size = half perimeter as non-negative float bits (monotone).
@@ -186,125 +190,164 @@ __global__ void k_leaf_gather(int nf, const int* __restrict__ leafFixtureSorted,
   }
 }
 
-// ---- Karras 2012: one thread per internal node -------------------------------------------------
-__device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
-  if (j < 0 || j >= n) return -1;
-  unsigned long long a = keys[i], b = keys[j];
-  if (a == b) return 64 + __clz(i ^ j);
-  return __clzll((long long)(a ^ b));
-}
-
-__global__ void k_lbvh_build(int n, const unsigned long long* __restrict__ keys, int4* nodeRange, int* leafParent) {
-  B2G_PDL_ENTER();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1) return;
-  int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-  int dmin = lbvh_delta(keys, n, i, i - d);
-  int lmax = 2;
-  while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-  int l = 0;
-  for (int t = lmax >> 1; t >= 1; t >>= 1)
-    if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-  int j = i + l * d;
-  int dnode = lbvh_delta(keys, n, i, j);
-  int s = 0;
-  int t = l;
-  do {
-    t = (t + 1) >> 1;
-    if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
-  } while (t > 1);
-  int split = i + s * d + min(d, 0);
-  int first = min(i, j), last = max(i, j);
-  // children: [first, split] and [split+1, last]; a one-element range is a leaf
-  nodeRange[i].x = first;
-  nodeRange[i].y = split;
-  nodeRange[i].z = last;
-  if (first == split) leafParent[split] = i; else nodeRange[split].w = i;
-  if (split + 1 == last) leafParent[last] = i; else nodeRange[split + 1].w = i;
-  if (i == 0) nodeRange[0].w = -1;
-}
-
-// bottom-up refit: the second thread to reach a node carries the union upward; child boxes are
-// stored IN the parent so the traversal tests both children with one node fetch
-// Traversal record of an internal node: both child boxes, both child max-keys and the leaf range
-// in ONE 64-byte line, so a node visit is a single L2 round trip.
-struct __align__(16) BvhNode {
-  float4 boxL, boxR;
-  unsigned long long maxL, maxR;
-  int first, split, last, pad;
+// ---- implicit 8-wide BVH over the Morton-sorted leaves ------------------------------------------
+// Level 0 = the leaves in sorted order; node j of level l covers children [8j, 8j+8) of level l-1,
+// i.e. leaves [j * 8^l, (j+1) * 8^l).  No topology is stored: a node IS the 8 consecutive
+// (box, max-key) entries of the level below — 128 + 64 contiguous bytes — so a visit is one round
+// trip to L2 with eight independent loads, and a 21 k-leaf tree is 5 visits deep instead of the
+// ~30 dependent visits of a binary LBVH (the walks are pure latency: ~4 warps per SM).  Any valid
+// bounding hierarchy reports the same exact pair set; splitting by count instead of by the highest
+// differing Morton bit costs a little overlap and buys an index-free layout, a refit that is a
+// plain reduction (no atomics per level) and children that can be fetched before their parent is
+// tested.  The leaf order is refreshed by re-sorting every few steps; in between only boxes move.
+#define B2G_BVH_W 8
+#define B2G_BVH_MAX_LEVELS 12
+struct WideBvh {
+  int levels;                        // internal levels; the root level has one node (0 when n == 0)
+  int count[B2G_BVH_MAX_LEVELS];     // entries per level, count[0] = leaves
+  int offset[B2G_BVH_MAX_LEVELS];    // where level l >= 1 starts inside box[] / key[]
+  float4* box;
+  unsigned long long* key;           // largest leaf key below the node (reporting-order pruning)
+  int* done;                         // blocks finished (last-block-done hand-over in the refit)
 };
-
-// Bottom-up refit walk of one leaf.  The second thread to reach a node carries the union upward;
-// arrival is detected by the PARITY of a never-reset counter (every node receives exactly two
-// arrivals per refit), so no per-step clearing pass is needed while the topology is unchanged.
-__device__ __forceinline__ void refit_walk(int p, float4 box, unsigned long long key, const int* __restrict__ leafParent,
-                                           const int4* __restrict__ nodeRange, BvhNode* nodes, int* nodeVisit) {
-  int idx = p;
-  int parent = leafParent[p];
-  while (parent >= 0) {
-    int4 nr = nodeRange[parent];
-    bool isLeft = (idx == nr.y);
-    BvhNode* nd = &nodes[parent];
-    if (isLeft) {
-      nd->boxL = box;
-      nd->maxL = key;
-    } else {
-      nd->boxR = box;
-      nd->maxR = key;
-    }
-    nd->first = nr.x;  // both arrivals store the same range
-    nd->split = nr.y;
-    nd->last = nr.z;
-    __threadfence();
-    int old = atomicAdd(&nodeVisit[parent], 1);
-    if ((old & 1) == 0) return;
-    float4 sib = isLeft ? __ldcg(&nd->boxR) : __ldcg(&nd->boxL);
-    unsigned long long sibKey = isLeft ? __ldcg(&nd->maxR) : __ldcg(&nd->maxL);
-    box = make_float4(fminf(box.x, sib.x), fminf(box.y, sib.y), fmaxf(box.z, sib.z), fmaxf(box.w, sib.w));
-    key = key > sibKey ? key : sibKey;
-    idx = parent;
-    parent = nr.w;
+__host__ __device__ inline void wide_bvh_layout(WideBvh& T, int n) {
+  T.levels = 0;
+  T.count[0] = n;
+  T.offset[0] = 0;
+  int off = 0, c = n;
+  while (c > 1 && T.levels + 1 < B2G_BVH_MAX_LEVELS) {
+    c = (c + B2G_BVH_W - 1) / B2G_BVH_W;
+    ++T.levels;
+    T.count[T.levels] = c;
+    T.offset[T.levels] = off;
+    off += (c + 7) & ~7;  // keep every level 128-byte aligned
+  }
+  if (n == 1) {  // a lone leaf still gets a root so that queries have something to visit
+    T.levels = 1;
+    T.count[1] = 1;
+    T.offset[1] = 0;
   }
 }
-
-__global__ void k_lbvh_refit(int n, const float4* __restrict__ leafBox, const unsigned long long* __restrict__ leafKey,
-                             const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
-                             int* nodeVisit) {
-  B2G_PDL_ENTER();
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  refit_walk(p, leafBox[p], leafKey[p], leafParent, nodeRange, nodes, nodeVisit);
+__host__ __device__ inline int wide_bvh_nodes(int n) {
+  WideBvh T;
+  wide_bvh_layout(T, n);
+  return T.levels > 0 ? T.offset[T.levels] + 8 : 8;
 }
 
-// Refit-only steps: the tree TOPOLOGY of the last rebuild is kept (any valid BVH reports the same
-// exact pair set); every leaf gets its fresh tight AABB and size key.  Replaces k_update_aabbs +
-// k_morton_keys + sort + k_leaf_gather + k_lbvh_build + k_lbvh_refit on the steps between rebuilds.
+__device__ __forceinline__ float4 box_union(float4 a, float4 b) {
+  return make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+#define B2G_EMPTY_BOX make_float4(B2G_MAX_FLOAT, B2G_MAX_FLOAT, -B2G_MAX_FLOAT, -B2G_MAX_FLOAT)
+
+// One block = 256 consecutive leaves = 32 level-1 nodes = 4 level-2 nodes, all reduced in shared
+// memory; the last block to finish reduces the few remaining upper levels.  With REFRESH the leaf
+// boxes are first recomputed from the body transforms (the refit-only steps between re-sorts:
+// replaces k_update_aabbs + k_morton_keys + sort + k_leaf_gather on those steps).
+template <bool REFRESH>
 __global__ void __launch_bounds__(256)
-k_refresh_leaves(int nf, const int* __restrict__ leafFixtureSorted, const int* __restrict__ fBody,
-                 const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
-                 const float4* __restrict__ shapes, const uint32_t* __restrict__ bflags,
-                 const float4* __restrict__ xf, float4* fAabb, float4* leafBox, unsigned long long* leafKey,
-                 const int* __restrict__ leafParent, const int4* __restrict__ nodeRange, BvhNode* nodes,
-                 int* nodeVisit) {
+k_wide_refit(WideBvh T, const int* __restrict__ leafFixtureSorted, const int* __restrict__ fBody,
+             const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
+             const float4* __restrict__ shapes, const uint32_t* __restrict__ bflags, const float4* __restrict__ xf,
+             float4* fAabb, float4* leafBox, unsigned long long* leafKey) {
   B2G_PDL_ENTER();
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nf) return;
-  int f = leafFixtureSorted[p];
-  uint32_t tf = fTypeFlags[f];
-  float4 box = leafBox[p];              // dead / static leaves keep the box of the last rebuild
-  unsigned long long key = leafKey[p];
-  if (!(tf & B2G_FIX_DEAD)) {
-    int b = fBody[f];
-    if (B2G_BODY_TYPE(bflags[b]) != B2G_STATIC) {
-      box = shape_aabb(shapes, (int)(tf & 3u), fShapeOff[f], xf_from4(xf[b]));
-      fAabb[f] = box;
-      leafBox[p] = box;
-      float size = (box.z - box.x) + (box.w - box.y);
-      key = ((unsigned long long)__float_as_uint(fmaxf(size, 0.0f)) << 32) | (unsigned int)p;
-      leafKey[p] = key;
+  __shared__ float4 sBox[256];
+  __shared__ unsigned long long sKey[256];
+  __shared__ float4 s1Box[32];
+  __shared__ unsigned long long s1Key[32];
+  __shared__ int sLast;
+  const int n = T.count[0];
+  const int tid = threadIdx.x;
+  const int p = blockIdx.x * 256 + tid;
+  float4 box = B2G_EMPTY_BOX;
+  unsigned long long key = 0ull;
+  if (p < n) {
+    box = leafBox[p];  // dead / static leaves keep the box of the last re-sort
+    key = leafKey[p];
+    if (REFRESH) {
+      int f = leafFixtureSorted[p];
+      uint32_t tf = fTypeFlags[f];
+      if (!(tf & B2G_FIX_DEAD)) {
+        int b = fBody[f];
+        if (B2G_BODY_TYPE(bflags[b]) != B2G_STATIC) {
+          box = shape_aabb(shapes, (int)(tf & 3u), fShapeOff[f], xf_from4(xf[b]));
+          fAabb[f] = box;
+          leafBox[p] = box;
+          float size = (box.z - box.x) + (box.w - box.y);
+          key = ((unsigned long long)__float_as_uint(fmaxf(size, 0.0f)) << 32) | (unsigned int)p;
+          leafKey[p] = key;
+        }
+      }
     }
   }
-  refit_walk(p, box, key, leafParent, nodeRange, nodes, nodeVisit);  // refit fused into the refresh
+  sBox[tid] = box;
+  sKey[tid] = key;
+  __syncthreads();
+  if (tid < 32 && T.levels >= 1) {
+    float4 u = B2G_EMPTY_BOX;
+    unsigned long long k = 0ull;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      u = box_union(u, sBox[tid * 8 + c]);
+      unsigned long long kc = sKey[tid * 8 + c];
+      k = kc > k ? kc : k;
+    }
+    s1Box[tid] = u;
+    s1Key[tid] = k;
+    int j = blockIdx.x * 32 + tid;
+    if (j < T.count[1]) {
+      T.box[T.offset[1] + j] = u;
+      T.key[T.offset[1] + j] = k;
+    }
+  }
+  __syncthreads();
+  if (tid < 4 && T.levels >= 2) {
+    float4 u = B2G_EMPTY_BOX;
+    unsigned long long k = 0ull;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      u = box_union(u, s1Box[tid * 8 + c]);
+      unsigned long long kc = s1Key[tid * 8 + c];
+      k = kc > k ? kc : k;
+    }
+    int j = blockIdx.x * 4 + tid;
+    if (j < T.count[2]) {
+      T.box[T.offset[2] + j] = u;
+      T.key[T.offset[2] + j] = k;
+    }
+  }
+  if (T.levels < 3) return;
+  // upper levels: whoever finishes last has every level-2 entry visible
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    int old = atomicAdd(T.done, 1);
+    sLast = (old == (int)gridDim.x - 1);
+    if (sLast) *T.done = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  for (int l = 3; l <= T.levels; ++l) {
+    const float4* cb = T.box + T.offset[l - 1];
+    const unsigned long long* ck = T.key + T.offset[l - 1];
+    const int nc = T.count[l - 1];
+    for (int j = tid; j < T.count[l]; j += 256) {
+      float4 u = B2G_EMPTY_BOX;
+      unsigned long long k = 0ull;
+      for (int c = 0; c < 8; ++c) {
+        int ci = j * 8 + c;
+        if (ci < nc) {
+          u = box_union(u, __ldcg(cb + ci));
+          unsigned long long kc = __ldcg(ck + ci);
+          k = kc > k ? kc : k;
+        }
+      }
+      T.box[T.offset[l] + j] = u;
+      T.key[T.offset[l] + j] = k;
+    }
+    __threadfence();
+    __syncthreads();
+  }
 }
 
 // inclusive AABB overlap, b2TestOverlap (include/box2d/b2_collision.h:270-276)
@@ -422,16 +465,43 @@ __device__ __forceinline__ void emit_pair(int4 a, int4 b, const ContactHash& H, 
   if (k < capacity) newPairs[k] = key;
 }
 
+// Children of node (level l, index j) = entries [8j, 8j+8) of level l-1; all eight (box, key) pairs
+// are fetched before any is tested (independent loads, one latency).
+struct WideChildren {
+  float4 box[B2G_BVH_W];
+  unsigned long long key[B2G_BVH_W];
+  int base, count;
+};
+__device__ __forceinline__ void wide_load(const WideBvh& T, const float4* __restrict__ leafBox,
+                                          const unsigned long long* __restrict__ leafKey, int l, int j,
+                                          WideChildren& ch) {
+  const float4* cb = l == 1 ? leafBox : T.box + T.offset[l - 1];
+  const unsigned long long* ck = l == 1 ? leafKey : T.key + T.offset[l - 1];
+  ch.base = j * B2G_BVH_W;
+  ch.count = min(B2G_BVH_W, T.count[l - 1] - ch.base);
+#pragma unroll
+  for (int c = 0; c < B2G_BVH_W; ++c) {
+    bool ok = c < ch.count;
+    ch.box[c] = ok ? __ldg(cb + ch.base + c) : B2G_EMPTY_BOX;
+    ch.key[c] = ok ? __ldg(ck + ch.base + c) : 0ull;
+  }
+}
+// leaves covered by entry c of level l: [c << 3l, ((c + 1) << 3l) - 1]
+__device__ __forceinline__ bool wide_in_range(int l, int c, int ws, int we) {
+  long long lo = (long long)c << (3 * l), hi = (((long long)c + 1) << (3 * l)) - 1;
+  return lo <= we && hi >= ws;
+}
+
 // one thread per query leaf.  Leaf i reports partner j iff key(j) > key(i) (each pair once, by
 // its smaller member); subtrees whose largest key is not above key(i) are pruned, and the walk
 // never leaves the query's own world segment [ws, we] of the sorted order.
 __global__ void __launch_bounds__(128)
-k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo,
-              const unsigned long long* __restrict__ leafKey, const BvhNode* __restrict__ nodes,
-              const int* __restrict__ worldFirst,
+k_bp_traverse(WideBvh T, const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo,
+              const unsigned long long* __restrict__ leafKey, const int* __restrict__ worldFirst,
               const int* __restrict__ worldLast, const unsigned long long* __restrict__ keysSorted, int numWorlds,
               ContactHash H, uint8_t* persist, unsigned long long* newPairs, int capacity, StepCounts* counts) {
   B2G_PDL_ENTER();
+  const int n = T.count[0];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || n < 2) return;
   int4 me = leafInfo[i];
@@ -444,30 +514,33 @@ k_bp_traverse(int n, const float4* __restrict__ leafBox, const int4* __restrict_
     ws = worldFirst[w];
     we = worldLast[w];
   }
-  int stack[64];
+  int stack[72];  // (level << 27) | index; at most 7 pending siblings per level
   int sp = 0;
   int visits = 0;
-  stack[sp++] = 0;
+  stack[sp++] = (T.levels << 27);
+  WideChildren ch;
   while (sp > 0) {
-    int node = stack[--sp];
+    int e = stack[--sp];
+    const int l = e >> 27, j = e & 0x7ffffff;
     ++visits;
-    const float4* q = reinterpret_cast<const float4*>(&nodes[node]);
-    float4 bl = __ldg(q), br = __ldg(q + 1), mk4 = __ldg(q + 2);
-    int4 nr = __ldg(reinterpret_cast<const int4*>(q + 3));
-    unsigned long long mkL = ((unsigned long long)__float_as_uint(mk4.y) << 32) | __float_as_uint(mk4.x);
-    unsigned long long mkR = ((unsigned long long)__float_as_uint(mk4.w) << 32) | __float_as_uint(mk4.z);
-    // left child covers [first, split]
-    if (mkL > myKey && nr.x <= we && nr.y >= ws && aabb_overlap(qbox, bl)) {
-      if (nr.x == nr.y) emit_pair(me, leafInfo[nr.y], H, persist, newPairs, capacity, counts);
-      else stack[sp++] = nr.y;
-    }
-    // right child covers [split+1, last]
-    if (mkR > myKey && nr.y + 1 <= we && nr.z >= ws && aabb_overlap(qbox, br)) {
-      if (nr.y + 1 == nr.z) emit_pair(me, leafInfo[nr.z], H, persist, newPairs, capacity, counts);
-      else stack[sp++] = nr.y + 1;
+    wide_load(T, leafBox, leafKey, l, j, ch);
+    // test all eight children first (straight-line code), then handle the survivors in a compact
+    // loop: emit_pair is large, eight inlined copies of it thrash the instruction cache
+    unsigned int hits = 0;
+#pragma unroll
+    for (int c = 0; c < B2G_BVH_W; ++c)
+      if (ch.key[c] > myKey && aabb_overlap(qbox, ch.box[c])) hits |= 1u << c;
+    while (hits) {
+      const int ci = ch.base + __ffs(hits) - 1;
+      hits &= hits - 1;
+      if (l == 1) {
+        if (ci >= ws && ci <= we) emit_pair(me, leafInfo[ci], H, persist, newPairs, capacity, counts);
+      } else if (wide_in_range(l - 1, ci, ws, we)) {
+        stack[sp++] = ((l - 1) << 27) | ci;
+      }
     }
   }
-  // tree-quality counters for the adaptive rebuild (one atomic per warp)
+  // tree-quality counters (one atomic per warp)
   {
     auto g = cg::coalesced_threads();
     int total = cg::reduce(g, visits, cg::plus<int>());

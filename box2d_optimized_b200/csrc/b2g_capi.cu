@@ -290,10 +290,9 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->leafKey, nf));
   CK(dalloc(&A->worldFirst, A->numWorlds + 1));
   CK(dalloc(&A->worldLast, A->numWorlds + 1));
-  CK(dalloc(&A->nodeRange, nf));
-  CK(dalloc(&A->bvhNodes, nf));
-  CK(dalloc(&A->leafParent, nf));
-  CK(dalloc(&A->nodeVisit, nf));
+  CK(dalloc(&A->bvhBox, (size_t)wide_bvh_nodes(nf)));
+  CK(dalloc(&A->bvhKey, (size_t)wide_bvh_nodes(nf)));
+  CK(dalloc(&A->bvhDone, 1));
   CK(dalloc(&A->pairKeys, nc));
 
   CK(dalloc(&A->activeFlag, nc));
@@ -359,8 +358,8 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
                   A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->stateStage, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
-                  A->leafKey, A->worldFirst, A->worldLast, A->nodeRange, A->bvhNodes, A->leafParent,
-                  A->nodeVisit, A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
+                  A->leafKey, A->worldFirst, A->worldLast, A->bvhBox, A->bvhKey, A->bvhDone,
+                  A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
                   A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
                   A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->cubTemp};
@@ -543,6 +542,15 @@ static int reset_bounds(b2gArena* A) {
   return B2G_OK;
 }
 
+static WideBvh wide_tree(b2gArena* A) {
+  WideBvh T;
+  wide_bvh_layout(T, A->bvhLeaves);
+  T.box = A->bvhBox;
+  T.key = A->bvhKey;
+  T.done = A->bvhDone;
+  return T;
+}
+
 static int find_new_contacts(b2gArena* A, int recordEvents) {
   const int nf = A->nFixtures;
   ContactBuf& C = A->cb[0];
@@ -583,25 +591,23 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
                                                32 + (A->numWorlds > 1 ? A->worldBits : 0), A->stream)));
       LAUNCH(A, KC_BP_BUILD, nf, k_leaf_gather, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->mortonKeysSorted,
              A->fAabb, A->fBody, A->fTypeFlags, A->fFilter, A->bflags, A->bodyNoCollide, A->leafBox, A->leafInfo, A->leafKey,
-             A->worldFirst, A->worldLast, A->numWorlds, A->nodeVisit);
-      CK(cudaMemsetAsync(A->leafParent, 0xff, sizeof(int) * nf, A->stream));
-      if (nf > 1)
-        LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_build, div_up(nf - 1, 256), 256, nf, A->mortonKeysSorted, A->nodeRange,
-               A->leafParent);
+             A->worldFirst, A->worldLast, A->numWorlds);
       A->bvhLeaves = nf;
       A->bvhAge = 0;
+    }
+    const WideBvh T = wide_tree(A);
+    if (rebuild) {
+      LAUNCH(A, KC_BP_BUILD, nf, k_wide_refit<false>, div_up(nf, 256), 256, T, A->leafFixtureSorted, A->fBody,
+             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey);
     } else {
-      LAUNCH(A, KC_BP_BUILD, nf, k_refresh_leaves, div_up(nf, 256), 256, nf, A->leafFixtureSorted, A->fBody,
-             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey, A->leafParent,
-             A->nodeRange, A->bvhNodes, A->nodeVisit);
+      LAUNCH(A, KC_BP_BUILD, nf, k_wide_refit<true>, div_up(nf, 256), 256, T, A->leafFixtureSorted, A->fBody,
+             A->fShapeOff, A->fTypeFlags, A->shapes, A->bflags, A->xf, A->fAabb, A->leafBox, A->leafKey);
       A->bvhAge++;
     }
     if (nf > 1) {
-      if (rebuild)
-        LAUNCH(A, KC_BP_BUILD, nf, k_lbvh_refit, div_up(nf, 256), 256, nf, A->leafBox, A->leafKey, A->leafParent,
-               A->nodeRange, A->bvhNodes, A->nodeVisit);
-      LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, nf, A->leafBox, A->leafInfo, A->leafKey, A->bvhNodes, A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash,
-             A->persist, A->pairKeys, A->capContacts, A->dCounts);
+      LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, T, A->leafBox, A->leafInfo, A->leafKey,
+             A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash, A->persist, A->pairKeys,
+             A->capContacts, A->dCounts);
     }
   }
   // retire contacts whose pair was not re-reported (all of them when there are no fixtures left)
@@ -1558,8 +1564,8 @@ extern "C" int b2g_query_aabb(b2gArena* A, int32_t n, const float* aabbs, const 
   if (A->nFixtures == 0) {
     CK(cudaMemsetAsync(dC, 0, (size_t)n * 4, A->stream));
   } else {
-    LAUNCH(A, KC_QUERY, n, k_query_aabb, div_up(n, 128), 128, n, (const float4*)dQ, (const int*)dW, A->nFixtures,
-           A->leafBox, A->leafInfo, A->bvhNodes, A->worldFirst, A->worldLast, A->numWorlds, cap, (int*)dC, (int*)dF);
+    LAUNCH(A, KC_QUERY, n, k_query_aabb, div_up(n, 128), 128, n, (const float4*)dQ, (const int*)dW, wide_tree(A),
+           A->leafBox, A->leafInfo, A->leafKey, A->worldFirst, A->worldLast, A->numWorlds, cap, (int*)dC, (int*)dF);
     CK(cudaGetLastError());
   }
   Q_BACK(bC, counts, (size_t)n * 4);
@@ -1586,7 +1592,7 @@ static int ray_cast_common(b2gArena* A, int mode, int32_t n, const float* rays, 
   CK(q_out(bT, fraction, (size_t)n * per * 4, on_device, &dT));
   CK(q_out(bN, normal, (size_t)n * per * 8, on_device, &dN));
   LAUNCH(A, KC_QUERY, n, k_ray_cast, div_up(n, 128), 128, n, (const float4*)dR, (const float*)dM, (const int*)dW, mode,
-         category_mask, A->nFixtures, A->leafBox, A->leafInfo, A->bvhNodes, A->worldFirst, A->worldLast, A->numWorlds,
+         category_mask, wide_tree(A), A->leafBox, A->leafInfo, A->leafKey, A->worldFirst, A->worldLast, A->numWorlds,
          A->fShapeOff, A->shapes, A->xf, cap, (int*)dC, (int*)dF, (float*)dT, (float2*)dN);
   CK(cudaGetLastError());
   if (mode == 1) Q_BACK(bC, counts, (size_t)n * 4);

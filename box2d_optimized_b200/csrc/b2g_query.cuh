@@ -2,7 +2,7 @@
 //   b2World::QueryAABB  (src/dynamics/b2_world.cpp:1193-1207 -> b2BroadPhase::Query, b2_broad_phase.h:622-643)
 //   b2World::RayCast    (src/dynamics/b2_world.cpp:1226-1246 -> b2BroadPhase::RayCast, b2_broad_phase.h:645-716,
 //                        b2Fixture::RayCast -> b2{Circle,Edge,Polygon}Shape::RayCast)
-// One thread per query walks the same 64-byte BvhNode records the pair finder walks.  Batches of
+// One thread per query walks the same implicit 8-wide tree the pair finder walks.  Batches of
 // queries are what an RL observation (a fan of rays per agent, thousands of agents) looks like.
 //
 // Results are sets / minima, so they do not depend on the traversal order; where the reference's
@@ -110,13 +110,14 @@ __device__ __forceinline__ bool ray_cast_fixture(const float4* __restrict__ pool
 // `cap` of them (arbitrary order; the host sorts) go to fixtures[q*cap ..].  world[q] >= 0
 // restricts the query to one world of a multi-world arena.
 __global__ void __launch_bounds__(128)
-k_query_aabb(int nq, const float4* __restrict__ qbox, const int* __restrict__ qworld, int n,
-             const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo, const BvhNode* __restrict__ nodes,
-             const int* __restrict__ worldFirst, const int* __restrict__ worldLast, int numWorlds, int cap, int* counts,
-             int* fixtures) {
+k_query_aabb(int nq, const float4* __restrict__ qbox, const int* __restrict__ qworld, WideBvh T,
+             const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo,
+             const unsigned long long* __restrict__ leafKey, const int* __restrict__ worldFirst,
+             const int* __restrict__ worldLast, int numWorlds, int cap, int* counts, int* fixtures) {
   B2G_PDL_ENTER();
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
+  const int n = T.count[0];
   float4 box = qbox[q];
   int ws = 0, we = n - 1;
   if (qworld && numWorlds > 1 && qworld[q] >= 0) {
@@ -135,34 +136,33 @@ k_query_aabb(int nq, const float4* __restrict__ qbox, const int* __restrict__ qw
     counts[q] = found;
     return;
   }
-  int stack[64];
+  int stack[72];
   int sp = 0;
-  if (n > 1) stack[sp++] = 0;
+  if (n > 1) stack[sp++] = (T.levels << 27);
+  WideChildren ch;
   while (sp > 0) {
-    int node = stack[--sp];
-    const float4* p = reinterpret_cast<const float4*>(&nodes[node]);
-    float4 bl = __ldg(p), br = __ldg(p + 1);
-    int4 nr = __ldg(reinterpret_cast<const int4*>(p + 3));
-    if (nr.x <= we && nr.y >= ws && aabb_overlap(box, bl)) {
-      if (nr.x == nr.y) {
-        int4 li = leafInfo[nr.y];
-        if (!((unsigned int)li.z & 16u)) {
-          if (found < cap) out[found] = li.x;
-          ++found;
+    int e = stack[--sp];
+    const int l = e >> 27, j = e & 0x7ffffff;
+    wide_load(T, leafBox, leafKey, l, j, ch);
+    unsigned int hits = 0;
+#pragma unroll
+    for (int c = 0; c < B2G_BVH_W; ++c)
+      if (c < ch.count && aabb_overlap(box, ch.box[c])) hits |= 1u << c;
+    while (hits) {
+      {
+        const int ci = ch.base + __ffs(hits) - 1;
+        hits &= hits - 1;
+        if (l == 1) {
+          if (ci >= ws && ci <= we) {
+            int4 li = leafInfo[ci];
+            if (!((unsigned int)li.z & 16u)) {
+              if (found < cap) out[found] = li.x;
+              ++found;
+            }
+          }
+        } else if (wide_in_range(l - 1, ci, ws, we)) {
+          stack[sp++] = ((l - 1) << 27) | ci;
         }
-      } else {
-        stack[sp++] = nr.y;
-      }
-    }
-    if (nr.y + 1 <= we && nr.z >= ws && aabb_overlap(box, br)) {
-      if (nr.y + 1 == nr.z) {
-        int4 li = leafInfo[nr.z];
-        if (!((unsigned int)li.z & 16u)) {
-          if (found < cap) out[found] = li.x;
-          ++found;
-        }
-      } else {
-        stack[sp++] = nr.y + 1;
       }
     }
   }
@@ -192,14 +192,16 @@ __device__ __forceinline__ float4 segment_box(float2 p1, float2 p2, float maxFra
 // usual filter a callback applies by returning -1; 0xFFFF takes everything.
 __global__ void __launch_bounds__(128)
 k_ray_cast(int nr_, const float4* __restrict__ rays, const float* __restrict__ maxFractionIn,
-           const int* __restrict__ rworld, int mode, uint32_t categoryMask, int n, const float4* __restrict__ leafBox,
-           const int4* __restrict__ leafInfo, const BvhNode* __restrict__ nodes, const int* __restrict__ worldFirst,
+           const int* __restrict__ rworld, int mode, uint32_t categoryMask, WideBvh T,
+           const float4* __restrict__ leafBox, const int4* __restrict__ leafInfo,
+           const unsigned long long* __restrict__ leafKey, const int* __restrict__ worldFirst,
            const int* __restrict__ worldLast, int numWorlds, const int* __restrict__ fShapeOff,
            const float4* __restrict__ shapes, const float4* __restrict__ xf, int cap, int* counts, int* hitFixture,
            float* hitFraction, float2* hitNormal) {
   B2G_PDL_ENTER();
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nr_) return;
+  const int n = T.count[0];
   float4 ray = rays[r];
   float2 p1 = make_float2(ray.x, ray.y), p2 = make_float2(ray.z, ray.w);
   float maxFraction = maxFractionIn ? maxFractionIn[r] : 1.0f;
@@ -247,27 +249,30 @@ k_ray_cast(int nr_, const float4* __restrict__ rays, const float* __restrict__ m
     }
   };
 
-  if (n == 1) {
-    if (ray_hits_box(leafBox[0], segBox, p1, v, absV)) visit_leaf(0);
-  } else if (n > 1) {
-    int stack[64];
+  if (n >= 1) {
+    int stack[72];
     int sp = 0;
-    stack[sp++] = 0;
+    stack[sp++] = (T.levels << 27);
+    WideChildren ch;
     while (sp > 0) {
-      int node = stack[--sp];
-      const float4* p = reinterpret_cast<const float4*>(&nodes[node]);
-      float4 bl = __ldg(p), br = __ldg(p + 1);
-      int4 nr = __ldg(reinterpret_cast<const int4*>(p + 3));
-      bool goL = nr.x <= we && nr.y >= ws && ray_hits_box(bl, segBox, p1, v, absV);
-      bool goR = nr.y + 1 <= we && nr.z >= ws && ray_hits_box(br, segBox, p1, v, absV);
-      if (goL) {
-        if (nr.x == nr.y) visit_leaf(nr.y);
-        else stack[sp++] = nr.y;
-      }
-      if (goR) {
-        // the left leaf may have clipped the segment meanwhile: a stale "go" only costs a visit
-        if (nr.y + 1 == nr.z) visit_leaf(nr.z);
-        else stack[sp++] = nr.y + 1;
+      int e = stack[--sp];
+      const int l = e >> 27, j = e & 0x7ffffff;
+      wide_load(T, leafBox, leafKey, l, j, ch);
+      unsigned int hits = 0;
+#pragma unroll
+      for (int c = 0; c < B2G_BVH_W; ++c)
+        if (c < ch.count && ray_hits_box(ch.box[c], segBox, p1, v, absV)) hits |= 1u << c;
+      while (hits) {
+        // (a leaf visited earlier in this loop may have clipped the segment: a stale hit only costs a visit)
+        {
+          const int ci = ch.base + __ffs(hits) - 1;
+          hits &= hits - 1;
+          if (l == 1) {
+            if (ci >= ws && ci <= we) visit_leaf(ci);
+          } else if (wide_in_range(l - 1, ci, ws, we)) {
+            stack[sp++] = ((l - 1) << 27) | ci;
+          }
+        }
       }
     }
   }
