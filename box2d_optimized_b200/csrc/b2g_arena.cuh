@@ -15,7 +15,7 @@
 #define B2G_OVERFLOW_COLOUR B2G_MAX_COLOURS  // serial overflow bucket
 #define B2G_MAX_POS_ITERS 16
 #define B2G_ISLAND_EXACT_PERIOD 8  // steps between exact recomputations of oversize islands' labels
-#define B2G_BVH_REBUILD_PERIOD 8  // steps between LBVH topology rebuilds (boxes are refit every step)
+#define B2G_BVH_REBUILD_PERIOD 64  // longest run of refit-only steps; the leaf order is re-sorted earlier when walks get longer
 #define B2G_KT_MAX 2048  // timed launches per step when per-kernel timing is on
 
 // device-side counters, zeroed at the start of every step; mirrored to pinned host memory
@@ -75,7 +75,8 @@ struct b2gArena {
   int fixBits;        // bits per fixture index in the pair key
   int aabbAllDirty;   // recompute static AABBs too (after fixture / body upload)
   int newFixtures;    // b2World::m_newContacts: fixtures were added, the next step starts with FindNewContacts
-  int bvhLeaves, bvhAge;  // leaves of the current LBVH topology, steps since it was built
+  int bvhLeaves, bvhAge;  // leaves of the current leaf order, steps since it was sorted
+  float bvhVisitsFresh, bvhVisitsLast;  // mean nodes visited per pair-finder walk: right after the last sort / last step
   int recolour;       // drop persistent colours (after mass / type edits)
   int roundsHint;     // colouring rounds to launch before the first check
   float invDt0;

@@ -558,8 +558,8 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
   int nNew = 0;
   A->newFixtures = 0;
   if (nf > 0) {
-    // The LBVH topology is rebuilt (Morton sort + Karras build) when fixtures were added / edited
-    // or every B2G_BVH_REBUILD_PERIOD steps; in between only the boxes are refit.  The reported
+    // The leaf order is re-sorted (Morton keys + radix sort) when fixtures were added / edited, when
+    // it has degraded, or every B2G_BVH_REBUILD_PERIOD steps; in between only the boxes are refit.  The reported
     // pair set is exact either way — only traversal cost depends on tree quality.
     if (A->jointFilterDirty) {
       const int nj = A->nJoints;
@@ -575,7 +575,10 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
       A->jointFilterDirty = 0;
       A->aabbAllDirty = A->aabbAllDirty ? A->aabbAllDirty : 1;  // leaf records carry the per-body mark
     }
-    const bool rebuild = A->aabbAllDirty != 0 || A->bvhLeaves != nf || A->bvhAge >= B2G_BVH_REBUILD_PERIOD;
+    // re-sort when fixtures changed, when the order has aged, or as soon as the walks have become
+    // 15 % longer than they were on the freshly sorted order (bodies have moved past each other)
+    const bool degraded = A->bvhAge >= 2 && A->bvhVisitsLast > 1.15f * A->bvhVisitsFresh + 0.5f;
+    const bool rebuild = A->aabbAllDirty != 0 || A->bvhLeaves != nf || A->bvhAge >= B2G_BVH_REBUILD_PERIOD || degraded;
     if (rebuild) {
       int rc = reset_bounds(A);
       if (rc) return rc;
@@ -621,6 +624,10 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
   CK(cudaMemcpyAsync(&A->hCounts->freeTopRead, A->dFreeTop, sizeof(int), cudaMemcpyDeviceToHost, A->stream));
   CK(cudaStreamSynchronize(A->stream));
   nNew = A->hCounts->numPairs;
+  if (nf > 1) {
+    A->bvhVisitsLast = (float)((double)A->hCounts->bpVisits / nf);
+    if (A->bvhAge == 0) A->bvhVisitsFresh = A->bvhVisitsLast;
+  }
   const int freeTop = A->hCounts->freeTopRead;
   A->tombstones += A->hCounts->numDead;
   const int appended = nNew > freeTop ? nNew - freeTop : 0;
