@@ -608,9 +608,14 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
       A->bvhAge++;
     }
     if (nf > 1) {
-      LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse, div_up(nf, 128), 128, T, A->leafBox, A->leafInfo, A->leafKey,
-             A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash, A->persist, A->pairKeys,
-             A->capContacts, A->dCounts);
+      if (nf < 65536)
+        LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse<4>, div_up(nf * 4, 128), 128, T, A->leafBox, A->leafInfo, A->leafKey,
+               A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash, A->persist, A->pairKeys,
+               A->capContacts, A->dCounts);
+      else
+        LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse<1>, div_up(nf, 128), 128, T, A->leafBox, A->leafInfo, A->leafKey,
+               A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash, A->persist, A->pairKeys,
+               A->capContacts, A->dCounts);
     }
   }
   // retire contacts whose pair was not re-reported (all of them when there are no fixtures left)
