@@ -80,27 +80,30 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
   B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
+  // loads first, tests afterwards: three rounds of independent loads instead of a six-deep chain
+  // (dead slots keep in-range indices)
   uint32_t flags = C.flags[i];
-  bool active = (flags & (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) == (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED);
   int2 bd = C.body[i];
-  if (active) {
-    int2 fx = C.fix[i];
-    if ((fTypeFlags[fx.x] | fTypeFlags[fx.y]) & B2G_FIX_SENSOR) active = false;
-  }
-  int root = -1;
-  if (active) {
-    root = B2G_BODY_TYPE(bflags[bd.x]) != B2G_STATIC ? island[bd.x] : island[bd.y];
-    active = islandAwake[root] != 0;
-  }
+  int2 fx = C.fix[i];
+  int c = C.colour[i];
+  uint32_t tfa = fTypeFlags[fx.x], tfb = fTypeFlags[fx.y];
+  uint32_t bfa = bflags[bd.x];
+  int ia = island[bd.x], ib = island[bd.y];
+  float4 massA = mass[bd.x], massB = mass[bd.y];
+  int root = B2G_BODY_TYPE(bfa) != B2G_STATIC ? ia : ib;
+  uint32_t awake = islandAwake[root];
+  int icount = islandCount[root], istart = islandStart[root];
+  bool active = (flags & (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) == (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED);
+  if ((tfa | tfb) & B2G_FIX_SENSOR) active = false;
+  if (active) active = awake != 0;
   int bin = -1;
   if (active) {
-    bin = islandCount[root] > bigThreshold ? bigBin : islandStart[root] / binSize;
+    bin = icount > bigThreshold ? bigBin : istart / binSize;
     auto g = cg::coalesced_threads();
     if (g.thread_rank() == 0) atomicAdd(&counts->numActive, (int)g.size());
     if (bin == bigBin) atomicAdd(&counts->numBig, 1);
   }
   cbin[i] = bin;
-  int c = C.colour[i];
   if (!active || dropColours || c >= B2G_MAX_COLOURS) {
     // inactive contacts lose their colour; overflow constraints retry every step
     if (c != -1) C.colour[i] = -1;
@@ -109,8 +112,8 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
   // colours persist from step to step: publish the ones still in use (was k_colour_begin)
   if (c >= 0) {
     unsigned long long bit = 1ull << c;
-    if (body_movable(mass[bd.x])) atomicOr(&colourMask[bd.x], bit);
-    if (body_movable(mass[bd.y])) atomicOr(&colourMask[bd.y], bit);
+    if (body_movable(massA)) atomicOr(&colourMask[bd.x], bit);
+    if (body_movable(massB)) atomicOr(&colourMask[bd.y], bit);
     if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
     if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
   }

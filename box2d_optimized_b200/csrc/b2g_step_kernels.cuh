@@ -209,13 +209,19 @@ __global__ void k_island_union(int nc, ContactBuf C, const uint32_t* __restrict_
   B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
+  // Every load is issued before the first test: the kernel is a chain of dependent round trips
+  // (flags -> fixtures -> bodies -> parents), so the three contact words go out together, then the
+  // six words they index, instead of one round trip per early-out.  Dead slots keep in-range indices.
   uint32_t flags = C.flags[i];
-  if ((flags & (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) != (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) return;
   int2 fx = C.fix[i];
-  if ((fTypeFlags[fx.x] | fTypeFlags[fx.y]) & B2G_FIX_SENSOR) return;
   int2 bd = C.body[i];
-  if (B2G_BODY_TYPE(bflags[bd.x]) == B2G_STATIC || B2G_BODY_TYPE(bflags[bd.y]) == B2G_STATIC) return;
-  uf_union(island, bd.x, bd.y);
+  uint32_t tfa = fTypeFlags[fx.x], tfb = fTypeFlags[fx.y];
+  uint32_t bfa = bflags[bd.x], bfb = bflags[bd.y];
+  int pa = island[bd.x], pb = island[bd.y];  // first hop of both finds (a body's parent is itself or an ancestor)
+  if ((flags & (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) != (B2G_CONTACT_TOUCHING | B2G_CONTACT_ENABLED)) return;
+  if ((tfa | tfb) & B2G_FIX_SENSOR) return;
+  if (B2G_BODY_TYPE(bfa) == B2G_STATIC || B2G_BODY_TYPE(bfb) == B2G_STATIC) return;
+  uf_union(island, pa, pb);
 }
 
 __global__ void k_island_union_joints(int nj, const int2* __restrict__ jBodies, const uint32_t* __restrict__ bflags,
