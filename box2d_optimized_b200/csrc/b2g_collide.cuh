@@ -603,8 +603,7 @@ __device__ __forceinline__ void collide_edge_polygon(Manifold& m, const Edge& E,
 
 // ---- dispatch: b2Contact::functions[typeA][typeB] (b2_contact.cpp:46-56) ----------------
 // Returns false when the reference has no function for the ordered pair (e.g. edge-edge).
-__device__ __forceinline__ bool collide_dispatch(Manifold& m, const float4* __restrict__ pool, int typeA, int offA,
-                                                 Xf xfA, int typeB, int offB, Xf xfB) {
+__device__ __forceinline__ void manifold_clear(Manifold& m) {
   m.pointCount = 0;
   m.type = 0;
   m.localNormal = make_float2(0.0f, 0.0f);
@@ -613,6 +612,10 @@ __device__ __forceinline__ bool collide_dispatch(Manifold& m, const float4* __re
   m.normalImp[0] = m.normalImp[1] = 0.0f;
   m.tangentImp[0] = m.tangentImp[1] = 0.0f;
   m.id[0] = m.id[1] = 0;
+}
+__device__ __forceinline__ bool collide_dispatch(Manifold& m, const float4* __restrict__ pool, int typeA, int offA,
+                                                 Xf xfA, int typeB, int offB, Xf xfB) {
+  manifold_clear(m);
   if (typeA == 0 && typeB == 0) {
     collide_circles(m, load_circle(pool, offA), xfA, load_circle(pool, offB), xfB);
   } else if (typeA == 2 && typeB == 0) {

@@ -12,6 +12,7 @@
 //   broadphase kernels live in b2g_broadphase.cuh
 #pragma once
 #include "b2g_arena.cuh"
+#include "b2g_gjk.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -72,13 +73,15 @@ k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __rest
 
   Xf xfA = xf_from4(xf[bd.x]), xfB = xf_from4(xf[bd.y]);
   Manifold m;
-  collide_dispatch(m, shapes, (int)(tfA & 3u), fShapeOff[fx.x], xfA, (int)(tfB & 3u), fShapeOff[fx.y], xfB);
-  bool touching = m.pointCount > 0;
+  bool touching;
   if (sensor) {
-    // sensors report overlap but carry no manifold (b2_contact.cpp:145-151); overlap is taken
-    // from the manifold test instead of GJK (documented deviation)
-    m.pointCount = 0;
+    // sensors report overlap but carry no manifold (b2_contact.cpp:145-151): b2TestOverlap = GJK
+    // distance with radii (b2g_gjk.cuh)
+    manifold_clear(m);
+    touching = gjk_test_overlap(shapes, (int)(tfA & 3u), fShapeOff[fx.x], xfA, (int)(tfB & 3u), fShapeOff[fx.y], xfB);
   } else {
+    collide_dispatch(m, shapes, (int)(tfA & 3u), fShapeOff[fx.x], xfA, (int)(tfB & 3u), fShapeOff[fx.y], xfB);
+    touching = m.pointCount > 0;
     // carry warm-start impulses across by feature id (b2_contact.cpp:158-181)
     float4 o1 = C.m1[i], o2 = C.m2[i], o3 = C.m3[i];
     int oldCount = __float_as_int(o3.w);

@@ -10,6 +10,7 @@
 //   mixed          circles + convex polygons dropped into a 3-box container, LCG seed (config 3)
 //   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
+//   sensors        sensor zones / paddle / probes in a rain of shapes (b2TestOverlap path)
 //   hello          unit-test/hello_world.cpp:33-112
 //   falling_squares / falling_circles   benchmarks.h:57-135 (b1, b2)
 #ifndef B2_SCENES_H
@@ -260,6 +261,92 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
       jd.collideConnected = (name == "chain_collide");
       s->world->CreateJoint(&jd);
       prev = body;
+    }
+  } else if (name == "sensors") {
+    // sensor fixtures (static regions, a rotating paddle and probes riding on bodies) crossed by a
+    // rain of circles and polygons: b2Contact::Update takes `touching` of a sensor contact from
+    // b2TestOverlap = GJK distance (b2_contact.cpp:145-151, b2_collision.cpp:239-258)
+    int n = size > 0 ? size : 300;
+    SceneLCG rng((uint32_t)(seed > 0 ? seed : 4242));
+    b2BodyDef gd;
+    b2Body* ground = s->addBody(gd);
+    b2EdgeShape edge;
+    edge.SetTwoSided(b2Vec2(-40.0f, 0.0f), b2Vec2(40.0f, 0.0f));
+    s->addFixture(ground, edge, 0.0f);
+    {
+      b2FixtureDef sd;
+      sd.isSensor = true;
+      b2PolygonShape zone;
+      zone.SetAsBox(4.0f, 0.75f, b2Vec2(0.0f, 6.0f), 0.3f);
+      sd.shape = &zone;
+      s->addFixture(ground, sd);
+      b2CircleShape disc;
+      disc.m_p.Set(-7.0f, 4.0f);
+      disc.m_radius = 1.5f;
+      sd.shape = &disc;
+      s->addFixture(ground, sd);
+      b2EdgeShape wire;
+      wire.SetTwoSided(b2Vec2(4.0f, 2.0f), b2Vec2(10.0f, 5.0f));
+      sd.shape = &wire;
+      s->addFixture(ground, sd);
+      b2PolygonShape tri;
+      b2Vec2 pts[3] = {b2Vec2(-3.0f, 1.0f), b2Vec2(-1.0f, 1.2f), b2Vec2(-2.2f, 2.6f)};
+      tri.Set(pts, 3);
+      sd.shape = &tri;
+      s->addFixture(ground, sd);
+    }
+    {
+      // a kinematic paddle that is one long thin sensor, sweeping through the rain
+      b2BodyDef pd;
+      pd.type = b2_kinematicBody;
+      pd.position.Set(6.0f, 8.0f);
+      pd.angularVelocity = 1.3f;
+      b2Body* paddle = s->addBody(pd);
+      b2PolygonShape blade;
+      blade.SetAsBox(3.0f, 0.1f);
+      b2FixtureDef sd;
+      sd.isSensor = true;
+      sd.shape = &blade;
+      s->addFixture(paddle, sd);
+    }
+    int cols = 24;
+    for (int i = 0; i < n; ++i) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(-12.0f + 1.05f * (float)(i % cols) + rng.range(-0.2f, 0.2f), 9.0f + 1.1f * (float)(i / cols));
+      bd.angle = rng.range(0.0f, 2.0f * b2_pi);
+      bd.angularVelocity = rng.range(-3.0f, 3.0f);
+      b2Body* body = s->addBody(bd);
+      b2FixtureDef fd;
+      fd.density = 1.0f;
+      fd.friction = 0.3f;
+      if (i % 3 == 0) {
+        b2CircleShape c;
+        c.m_radius = rng.range(0.15f, 0.4f);
+        fd.shape = &c;
+        s->addFixture(body, fd);
+      } else {
+        int nv = 3 + (int)(rng.next() * 5.0f);
+        float rx = rng.range(0.2f, 0.45f), ry = rng.range(0.2f, 0.45f);
+        b2Vec2 pts[8];
+        for (int k = 0; k < nv; ++k) {
+          float ang = 2.0f * b2_pi * (float)k / (float)nv;
+          pts[k].Set(rx * cosf(ang), ry * sinf(ang));
+        }
+        b2PolygonShape poly;
+        poly.Set(pts, nv);
+        fd.shape = &poly;
+        s->addFixture(body, fd);
+      }
+      if (i % 7 == 0) {
+        // a probe: a sensor disc riding on the body, overlapping its neighbours' solid shapes
+        b2CircleShape probe;
+        probe.m_radius = 0.8f;
+        b2FixtureDef sd;
+        sd.isSensor = true;
+        sd.shape = &probe;
+        s->addFixture(body, sd);
+      }
     }
   } else if (name == "hello") {
     s->velocityIterations = 6;

@@ -62,7 +62,10 @@ def rel(a, b):
 
 @pytest.mark.parametrize("name,size,seed,steps", [("pyramid", 12, 0, 150), ("mixed", 700, 12345, 260),
                                                    ("falling_squares", 200, 7, 160), ("tumbler", 80, 3, 200),
-                                                   ("pendulum_limit", 6, 0, 120), ("pendulum_motor", 6, 0, 120)])
+                                                   ("pendulum_limit", 6, 0, 120), ("pendulum_motor", 6, 0, 120),
+                                                   # sensor zones, a kinematic sensor paddle and probes: touching of sensor
+                                                   # contacts = b2TestOverlap (GJK), compared contact by contact every step
+                                                   ("sensors", 300, 0, 240)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
     from box2d_optimized_b200 import RefScene
     ref = RefScene(name, size, seed)
