@@ -34,7 +34,8 @@ struct StepCounts {
   int freeTopRead;      // host copy of the free-stack height (filled by the readback)
   int jointOverflow;    // joints that did not fit a tile's joint list (reported as an error)
   unsigned long long bpVisits;  // internal nodes visited by this step's pair traversal (tree quality)
-  int bpMaxVisits, bpPad;       // longest single walk
+  int bpMaxVisits;              // longest single walk
+  int numBigBodies;             // bodies of oversize islands (an island can be oversize through joints alone)
   int colourCount[B2G_MAX_COLOURS + 1];
   unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
 };

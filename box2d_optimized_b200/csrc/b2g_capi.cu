@@ -965,7 +965,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandAwake, A->islandCount, A->islandStart,
          A->binFirst, A->binEnd, binSize, bigThr, A->dCounts, A->islandWasBig);
   LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
-         A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr);
+         A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr, A->dCounts);
 
   int numActive = 0, numBig = 0, rounds = 0;
   // Colouring rounds.  Constraints of tile-sized islands that are still uncoloured after the rounds
@@ -1073,16 +1073,23 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     A->roundsHint = useful < 1 ? 1 : (useful + 1 < 16 ? useful + 1 : 16);
     numActive = A->hCounts->numActive;
     numBig = A->hCounts->numBig;
-    A->lastNumBig = numBig;
     out.numColours = A->hCounts->numColours;
     out.numOverflow = A->hCounts->numOverflow + A->hCounts->remaining;
     A->lastOverflow = out.numOverflow;
     A->lastActive = numActive;
+  } else if (nj > 0) {
+    // no contacts at all, but joints can still form an oversize island (a chain in free fall)
+    int rc = read_counts(A);
+    if (rc) return rc;
   }
-  A->lastMaxIsland = nc > 0 ? A->hCounts->maxIslandBodies : 0;
+  // bodies of oversize islands are advanced by the big path even when those islands hold no
+  // contact constraint (joints only)
+  const int bigBodies = (nc > 0 || nj > 0) ? A->hCounts->numBigBodies : 0;
+  A->lastNumBig = numBig > 0 ? numBig : bigBodies;
+  A->lastMaxIsland = (nc > 0 || nj > 0) ? A->hCounts->maxIslandBodies : 0;
 
   // ---- oversize islands: per-colour launches over the whole GPU --------------------------------
-  if (numBig > 0 || (nc == 0 && false)) {
+  if (numBig > 0 || bigBodies > 0) {
     const int bigStart = numActive - numBig;
     int colourFirst[B2G_MAX_COLOURS + 2];
     int acc = bigStart, numColours = 0;
@@ -1099,8 +1106,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     LAUNCH(A, KC_INTEGRATE, nb, k_integrate_velocities, div_up(nb, 256), 256, nb, A->bflags, A->island,
            A->islandAwake, A->vel, A->mass, A->center, A->force, h, make_float2(P->gravity_x, P->gravity_y),
            A->dCounts, A->bodySlot, 1);
-    LAUNCH(A, KC_PREPARE, numBig, k_prepare, div_up(numBig, 128), 128, bigStart, numBig, A->sortedList, C, A->fRadius,
-           A->bflags, A->island, S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
+    if (numBig > 0)
+      LAUNCH(A, KC_PREPARE, numBig, k_prepare, div_up(numBig, 128), 128, bigStart, numBig, A->sortedList, C, A->fRadius,
+             A->bflags, A->island, S, A->croot, A->pos, A->vel, A->mass, A->center, dtRatio, P->warm_starting);
     {
       // one persistent cooperative launch: all colours x all iterations, grid barrier in between
       BigRanges R;

@@ -52,7 +52,7 @@ __global__ void k_island_alloc(int nb, const int* __restrict__ island, const uin
 __global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
                                const int* __restrict__ islandStart, int* islandCursor, int* bodySlot, int* slotBody,
-                               int bigThreshold) {
+                               int bigThreshold, StepCounts* counts) {
   B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
@@ -63,6 +63,8 @@ __global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, cons
   int root = island[b];
   if (islandCount[root] > bigThreshold) {
     bodySlot[b] = B2G_SLOT_BIG;
+    auto g = cg::coalesced_threads();
+    if (g.thread_rank() == 0) atomicAdd(&counts->numBigBodies, (int)g.size());
     return;
   }
   int slot = islandStart[root] + atomicAdd(&islandCursor[root], 1);
@@ -372,8 +374,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
       int sl = sa >= 0 ? sa : sb;
       if (sl >= first && sl < first + nbod) {
         int k = atomicAdd(&sJointCount, 1);
-        if (k < B2G_TILE_JOINTS) sJoint[k] = j;
-        else atomicAdd(&counts->jointOverflow, 1);
+        if (k < B2G_TILE_JOINTS) sJoint[k] = j;  // more than that: the walks below rescan the joint table
       }
     }
     __syncthreads();
@@ -387,11 +388,25 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
         }
         sJoint[b + 1] = v;
       }
-      sJointCount = n;
     }
     __syncthreads();
   }
   const int njTile = P.nj > 0 ? sJointCount : 0;
+  // The tile's joints in joint-index order (the serial walk of b2Island::Solve).  Up to
+  // B2G_TILE_JOINTS of them come from the shared list; a joint-heavy tile (a long chain, a crowd of
+  // ragdolls) falls back to rescanning the joint table, slower but without a capacity.
+  auto for_tile_joints = [&](auto&& f) {
+    if (njTile <= B2G_TILE_JOINTS) {
+      for (int k = njTile - 1; k >= 0; --k) f(sJoint[k]);
+    } else {
+      for (int j = P.nj - 1; j >= 0; --j) {
+        int2 bd = J.bodies[j];
+        int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
+        int sl = sa >= 0 ? sa : sb;
+        if (sl >= first && sl < first + nbod) f(j);
+      }
+    }
+  };
   // the (few) non-empty parallel colours of this bin, so the pass loops do not walk all 24
   __shared__ int usedS0[B2G_MAX_COLOURS], usedS1[B2G_MAX_COLOURS];
   __shared__ int usedCount;
@@ -464,13 +479,12 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
   // joints: InitVelocityConstraints incl. their warm start (b2_island.cpp:323-325), after the contacts'
   if (njTile > 0) {
     if (tid == 0) {
-      for (int k = 0; k < njTile; ++k) {
-        int j = sJoint[k];
+      for_tile_joints([&](int j) {
         int2 bd = J.bodies[j];
         int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
         joint_init(J, j, sa >= 0 ? sa - first : ~bd.x, sb >= 0 ? sb - first : ~bd.y, posAcc, velAcc, gmass, gcenter,
                    P.dtRatio, P.warmStarting != 0);
-      }
+      });
     }
     __syncthreads();
   }
@@ -478,8 +492,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
   // ---- phase 3: velocity iterations ---------------------------------------------------------------
   for (int it = 0; it < P.velIters; ++it) {
     if (njTile > 0) {  // joints first, then contacts (b2_island.cpp:330-338)
-      if (tid == 0)
-        for (int k = 0; k < njTile; ++k) joint_solve_velocity(J, sJoint[k], velAcc, P.h, P.invH);
+      if (tid == 0) for_tile_joints([&](int j) { joint_solve_velocity(J, j, velAcc, P.h, P.invH); });
       __syncthreads();
     }
     for (int k = 0; k < nUsed; ++k) {
@@ -565,14 +578,13 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     if (njTile > 0) {  // contacts first, then joints (b2_island.cpp:392-401); a joint that is not
                        // okay keeps its island iterating, expressed as a large "penetration"
       if (tid == 0) {
-        for (int k = 0; k < njTile; ++k) {
-          int j = sJoint[k];
+        for_tile_joints([&](int j) {
           JointWork w = J.work[j];
           int slot = w.ia >= 0 ? w.ia : w.ib;
           int hd = T.head[slot];
-          if (T.done[hd]) continue;
+          if (T.done[hd]) return;
           if (!joint_solve_position(J, j, posAcc)) atomicMax(&T.pen[hd], __float_as_uint(1.0f));
-        }
+        });
       }
       __syncthreads();
     }
@@ -667,7 +679,7 @@ __device__ __forceinline__ int joint_owner_body(const JointWalk& W, const JointA
 __device__ __forceinline__ void joints_init_global(const JointWalk& W, const JointArraysDev& J, float4* pos, float4* vel,
                                                    const float4* __restrict__ mass, const float4* __restrict__ center,
                                                    float dtRatio, int warm) {
-  for (int j = 0; j < W.nj; ++j) {
+  for (int j = W.nj - 1; j >= 0; --j) {
     if (joint_owner_body(W, J, j) < 0) continue;
     int2 bd = J.bodies[j];
     joint_init(J, j, bd.x, bd.y, GlobalBodies{pos}, GlobalBodies{vel}, mass, center, dtRatio, warm != 0);
@@ -675,12 +687,12 @@ __device__ __forceinline__ void joints_init_global(const JointWalk& W, const Joi
 }
 __device__ __forceinline__ void joints_velocity_global(const JointWalk& W, const JointArraysDev& J, float4* vel, float h,
                                                        float invH) {
-  for (int j = 0; j < W.nj; ++j)
+  for (int j = W.nj - 1; j >= 0; --j)
     if (joint_owner_body(W, J, j) >= 0) joint_solve_velocity(J, j, GlobalBodies{vel}, h, invH);
 }
 __device__ __forceinline__ void joints_position_global(const JointWalk& W, const JointArraysDev& J, float4* pos,
                                                        uint32_t* islandPen, int penStride, int iter) {
-  for (int j = 0; j < W.nj; ++j) {
+  for (int j = W.nj - 1; j >= 0; --j) {
     int s = joint_owner_body(W, J, j);
     if (s < 0) continue;
     int root = W.island[s];

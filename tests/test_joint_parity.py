@@ -55,7 +55,7 @@ def test_chain_of_joined_links_follows_the_reference(require_ref, name):
     overlapping).  Free running, coloured mode: the pair filter (collideConnected) must keep the
     contact counts equal while the chain falls, and the links stay where the reference's are while
     the chain swings and drags over the ground for 6 s.
-    Joints of one island are visited in joint-index order here, in DFS order in the reference, so
+    Once links touch the ground the contact order (colours vs DFS) differs from the reference, so
     this is a tolerance gate, not an iterate gate."""
     from box2d_optimized_b200 import RefScene, GpuScene
     ref, gpu = RefScene(name, 12, 0), GpuScene(name, 12, 0)
@@ -70,3 +70,29 @@ def test_chain_of_joined_links_follows_the_reference(require_ref, name):
     print(f"{name}: link positions after 360 steps differ by {err:.4f} m; contacts {ref.contact_count} / {gpu.contact_count}")
     # links fighting their own hinge contacts (chain_collide) is the stiffer, more order-sensitive case
     assert err < (0.25 if name == "chain" else 0.5)
+
+
+def test_long_chain_has_no_joint_capacity(require_ref):
+    """150 hinges in ONE island: more joints than the fused kernel's shared joint list holds, so the
+    serial joint walk rescans the joint table, and on the first steps an island that is oversize
+    through joints alone (no contact yet).  Joints are visited in descending index order, which is
+    the order the reference's island DFS discovers a chain built root to tip, so while the chain
+    swings freely the production mode reproduces the reference exactly."""
+    from box2d_optimized_b200 import RefScene, GpuScene
+    ref, gpu = RefScene("chain", 150, 0), GpuScene("chain", 150, 0)
+    ref.step(60)
+    gpu.step(60)
+    rb, gb = ref.bodies(), gpu.bodies()
+    err = np.abs(rb[:, 4:6] - gb[:, 4:6]).max()
+    print(f"150-link chain after 60 steps: max position difference {err:.4f} m")
+    assert np.isfinite(gb).all()
+    assert err < 1e-4
+    # hinge gaps: the world anchors of consecutive links coincide
+    gpu.step(120)
+    gb = gpu.bodies()
+    c, a = gb[1:, 4:6], gb[1:, 6]
+    left = c - 0.5 * np.stack([np.cos(a), np.sin(a)], 1)     # anchor at x - 0.5 in the link frame
+    right = c + 0.5 * np.stack([np.cos(a), np.sin(a)], 1)
+    gap = np.linalg.norm(left[1:] - right[:-1], axis=1).max()
+    print(f"largest hinge gap after 180 steps: {gap:.4f} m")
+    assert gap < 0.05
