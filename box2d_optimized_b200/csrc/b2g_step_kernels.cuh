@@ -253,7 +253,7 @@ __global__ void k_island_flatten(int nb, const uint32_t* __restrict__ bflags, co
   for (int p = parent[root]; p != root; p = parent[root]) root = p;
   island[b] = root;
   uint32_t f = bflags[b];
-  if ((f & B2G_BODY_ENABLED) && B2G_BODY_TYPE(f) != B2G_STATIC) {
+  if (B2G_BODY_TYPE(f) != B2G_STATIC) {
     // island size = its non-static members (all of them are simulated once the island is awake)
     int c = atomicAdd(&islandCount[root], 1) + 1;
     if (c > counts->maxIslandBodies) atomicMax(&counts->maxIslandBodies, c);
@@ -277,7 +277,7 @@ __global__ void k_integrate_velocities(int nb, uint32_t* bflags, const int* __re
   if (onlyBig && bodySlot[b] != -2) return;  // bodies of tile-sized islands are integrated by the fused kernel
   uint32_t f = bflags[b];
   uint32_t type = B2G_BODY_TYPE(f);
-  if (type == B2G_STATIC || !(f & B2G_BODY_ENABLED)) return;
+  if (type == B2G_STATIC) return;
   if (!islandAwake[island[b]]) return;
   if (!(f & B2G_BODY_AWAKE)) bflags[b] = f | B2G_BODY_AWAKE;
   if (type != B2G_DYNAMIC) return;
@@ -559,7 +559,10 @@ __global__ void k_store_impulses(int first, int n, SolverPlanes S, ContactBuf C)
 
 __device__ __forceinline__ bool body_simulated(uint32_t f, const int* __restrict__ island,
                                                const uint32_t* __restrict__ islandAwake, int b) {
-  return B2G_BODY_TYPE(f) != B2G_STATIC && (f & B2G_BODY_ENABLED) && islandAwake[island[b]];
+  // A DISABLED body cannot seed an island (b2_world.cpp:531) but in this fork it keeps its fixtures
+  // and contacts (b2Body::SetEnabled only flips the flag, b2_body.cpp:512-559), so it is pulled into
+  // — and simulated with — any island that reaches it through a contact.
+  return B2G_BODY_TYPE(f) != B2G_STATIC && islandAwake[island[b]];
 }
 
 __global__ void k_integrate_positions(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,

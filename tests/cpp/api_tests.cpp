@@ -310,6 +310,102 @@ static void contact_buffers_grow() {
   printf("pyramid top: %.6f (grown buffers) %.6f (large buffers)\n", small, large);
 }
 
+// A scripted session of world edits between steps.  Every TRACE line is compared numerically
+// between the build against the reference and the build against the drop-in (tests/test_host_api.py).
+static void trace(const char* tag, b2World& world, b2Body** b, int n) {
+  printf("TRACE %s contacts=%d", tag, world.GetContactCount());
+  for (int i = 0; i < n; ++i) {
+    if (!b[i]) continue;
+    printf(" | %.5f %.5f %.5f %d", b[i]->GetPosition().x, b[i]->GetPosition().y, b[i]->GetAngle(), b[i]->IsAwake() ? 1 : 0);
+  }
+  printf("\n");
+}
+static void world_editing_session() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2EdgeShape edge;
+  edge.SetTwoSided(b2Vec2(-30.0f, 0.0f), b2Vec2(30.0f, 0.0f));
+  ground->CreateFixture(&edge, 0.0f);
+  b2PolygonShape box;
+  box.SetAsBox(0.5f, 0.5f);
+  b2Body* b[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 5; ++i) {  // a stack of five boxes
+    b2BodyDef bd;
+    bd.type = b2_dynamicBody;
+    bd.position.Set(0.0f, 0.55f + 1.05f * (float)i);
+    b[i] = world.CreateBody(&bd);
+    b[i]->CreateFixture(&box, 2.0f);
+  }
+  {  // a ball to the side and a two-fixture dumbbell
+    b2BodyDef bd;
+    bd.type = b2_dynamicBody;
+    bd.position.Set(4.0f, 3.0f);
+    b[5] = world.CreateBody(&bd);
+    b2CircleShape ball;
+    ball.m_radius = 0.4f;
+    b[5]->CreateFixture(&ball, 1.0f);
+    bd.position.Set(-5.0f, 2.0f);
+    b[6] = world.CreateBody(&bd);
+    b2CircleShape end;
+    end.m_radius = 0.3f;
+    end.m_p.Set(-0.8f, 0.0f);
+    b[6]->CreateFixture(&end, 1.0f);
+    end.m_p.Set(0.8f, 0.0f);
+    b[6]->CreateFixture(&end, 1.0f);
+  }
+  const float dt = 1.0f / 60.0f;
+  for (int i = 0; i < 60; ++i) world.Step(dt, 8, 3);
+  trace("settled", world, b, 7);
+  b[4]->ApplyLinearImpulseToCenter(b2Vec2(0.4f, 0.0f), true);   // nudge the top box: it slides a little
+  b[5]->ApplyAngularImpulse(0.05f, true);                        // and roll the ball
+  for (int i = 0; i < 30; ++i) world.Step(dt, 8, 3);
+  trace("impulse", world, b, 7);
+  world.DestroyBody(b[4]);                                       // take the top box away
+  b[4] = nullptr;
+  CHECK(world.GetBodyCount() == 7);
+  for (int i = 0; i < 60; ++i) world.Step(dt, 8, 3);
+  trace("destroyed", world, b, 7);
+  b[5]->SetTransform(b2Vec2(8.0f, 2.0f), 0.4f);                  // drop the ball somewhere else
+  b[5]->SetLinearVelocity(b2Vec2(0.5f, -2.0f));
+  b[5]->SetAngularVelocity(0.0f);
+  for (int i = 0; i < 45; ++i) world.Step(dt, 8, 3);
+  trace("teleported", world, b, 7);
+  b[6]->DestroyFixture(b[6]->GetFixtureList());                  // the dumbbell loses one end and tips over
+  for (int i = 0; i < 30; ++i) world.Step(dt, 8, 3);
+  trace("fixture_destroyed", world, b, 7);
+  b[3]->SetTransform(b2Vec2(-10.0f, 3.0f), 0.0f);                // lift a box aside, freeze it in the air, thaw it
+  b[3]->SetType(b2_staticBody);
+  for (int i = 0; i < 10; ++i) world.Step(dt, 8, 3);
+  CHECK(b[3]->GetLinearVelocity().Length() == 0.0f && b[3]->GetPosition().y == 3.0f);
+  trace("frozen", world, b, 7);
+  b[3]->SetType(b2_dynamicBody);
+  for (int i = 0; i < 60; ++i) world.Step(dt, 8, 3);
+  trace("retyped", world, b, 7);
+  b[3]->SetTransform(b2Vec2(-12.0f, 3.0f), 0.0f);                // a disabled body is never the seed of an island:
+  b[3]->SetEnabled(false);                                       // alone in the air it just hangs there
+  for (int i = 0; i < 30; ++i) world.Step(dt, 8, 3);
+  CHECK(b[3]->GetPosition().y == 3.0f);
+  trace("disabled", world, b, 7);
+  b[3]->SetEnabled(true);
+  for (int i = 0; i < 60; ++i) world.Step(dt, 8, 3);
+  CHECK(b[3]->GetPosition().y < 0.6f);
+  trace("enabled", world, b, 7);
+  b[2]->SetGravityScale(-0.5f);                                  // the (now) top box floats up against a steady wind
+  for (int i = 0; i < 40; ++i) {
+    b[2]->ApplyForceToCenter(b2Vec2(1.5f, 0.0f), true);
+    world.Step(dt, 8, 3);
+  }
+  trace("forces", world, b, 7);
+  b[2]->SetGravityScale(1.0f);
+  b[2]->SetFixedRotation(true);
+  b[2]->SetAngularVelocity(3.0f);
+  world.Step(dt, 8, 3);
+  CHECK(b[2]->GetAngularVelocity() == 0.0f || b[2]->GetInertia() == 0.0f);
+  for (int i = 0; i < 240; ++i) world.Step(dt, 8, 3);            // everything comes to rest and falls asleep
+  trace("resting", world, b, 7);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -319,6 +415,7 @@ int main() {
   body_list_order();
   revolute_joint_api();
   contact_buffers_grow();
+  world_editing_session();
   printf(g_failed ? "FAILED %d checks\n" : "all API checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }

@@ -43,9 +43,38 @@ def test_api_program_compiles_against_the_drop_in_headers():
     assert r.returncode == 0, r.stdout
 
 
+def _traces(text):
+    out = {}
+    for line in text.splitlines():
+        if line.startswith("TRACE "):
+            head, *bodies = line[6:].split(" | ")
+            tag, contacts = head.split(" contacts=")
+            out[tag] = (int(contacts), [[float(x) for x in b.split()] for b in bodies])
+    return out
+
+
 @pytest.mark.gpu
 def test_api_program_passes_on_the_gpu():
     test_api_program_compiles_against_the_drop_in_headers()
     r = _run([os.path.join(OUT, "api_gpu")])
     assert r.returncode == 0, r.stdout
     assert "all API checks passed" in r.stdout
+    # the scripted editing session (DestroyBody, SetTransform, DestroyFixture, SetType, SetEnabled,
+    # forces, impulses, ...) against the same program linked with the reference: tests/cpp/build/api_ref
+    # is built by the CPU test in the container that holds /root/reference and travels with the tree
+    ref_exe = os.path.join(OUT, "api_ref")
+    if not os.path.exists(ref_exe):
+        pytest.skip("tests/cpp/build/api_ref has not been built (needs /root/reference)")
+    ref, gpu = _traces(_run([ref_exe]).stdout), _traces(r.stdout)
+    assert set(ref) == set(gpu) and len(ref) >= 10
+    worst = 0.0
+    for tag in ref:
+        (rc, rb), (gc, gb) = ref[tag], gpu[tag]
+        assert abs(rc - gc) <= 1, f"{tag}: contact count {gc} vs {rc}"
+        assert len(rb) == len(gb)
+        for x, y in zip(rb, gb):
+            if tag != "resting":   # positions and angles; the awake flag only once everything is asleep or not
+                d = max(abs(a - b) for a, b in zip(x[:3], y[:3]))
+                worst = max(worst, d)
+                assert d < 0.02, f"{tag}: {y} vs {x}"
+    print(f"editing session: worst position/angle difference to the reference {worst:.5f}")
