@@ -184,6 +184,32 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+KERNEL_OF_CLASS = {"fused_solve": "k_solve_bins_fused", "bp_traverse": "k_bp_traverse", "narrowphase": "k_narrowphase",
+                   "solve_velocity": "k_big_solve"}
+
+
+def ncu_traffic(cls, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest
+    committed `ncu --set full` summary (profiles/*_ncu_full_summary.csv, written by
+    scripts/summarize_ncu.py from a capture of the default workload); None when there is none."""
+    import csv
+    import glob
+    if workload != "many_pyramids" or cls not in KERNEL_OF_CLASS:
+        return None, None
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_ncu_full_summary.csv")))
+    if not files:
+        return None, None
+    rows = list(csv.reader(open(files[-1])))
+    hdr, units = rows[0], rows[1]
+    ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+            for r in rows[2:] if len(r) > wi and KERNEL_OF_CLASS[cls] in r[0]]
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals), os.path.basename(files[-1])
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -297,14 +323,17 @@ def main():
     kt = A.kernel_timing()
     A.set_kernel_timing(False)
     total_kernel_ms = sum(v[0] for v in kt.values()) or 1.0
-    dom = max(kt, key=lambda k: kt[k][0])
+    # the dominant KERNEL: classes such as "colour" or "islands" are 6-8 different few-microsecond
+    # kernels per step, so the comparison is per launch, not per class
+    dom = max(kt, key=lambda k: kt[k][0] / max(kt[k][1], 1))
     dom_ms, dom_launches, dom_units = kt[dom]
     peak, peak_src = measured_peaks()
     bytes_per_launch = ALGO_BYTES[dom] * dom_units / max(dom_launches, 1)
     us_per_launch = 1000.0 * dom_ms / max(dom_launches, 1)
     achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9 if us_per_launch > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(dom, args.workload)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": us_per_launch,
                 "launches_per_step": dom_launches / max(args.profile_steps, 1),
                 "share_of_kernel_time": dom_ms / total_kernel_ms,

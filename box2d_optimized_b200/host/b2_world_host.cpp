@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
+#include <typeinfo>
 #include <vector>
 #include "b2cuda.h"
 #include "box2d/box2d.h"
@@ -1220,6 +1221,15 @@ void b2Contact::ResetRestitutionThreshold() {
 }
 void b2Contact::SetTangentSpeed(float v) { m_tangentSpeed = v; m_overridden = true; }
 
+void b2World::SetContactFilter(b2ContactFilter* filter) {
+  m_contactFilter = filter;
+  static bool warned = false;
+  if (filter && typeid(*filter) != typeid(b2ContactFilter) && !warned) {
+    warned = true;
+    fprintf(stderr, "[b2cuda] a custom b2ContactFilter::ShouldCollide is not consulted: pair filtering (category, mask, "
+                    "group, collideConnected) runs on the device\n");
+  }
+}
 bool b2ContactFilter::ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB) {
   const b2Filter& filterA = fixtureA->GetFilterData();
   const b2Filter& filterB = fixtureB->GetFilterData();

@@ -528,7 +528,9 @@ class b2World {
   b2World(const b2Vec2& gravity);
   ~b2World();
   void SetDestructionListener(b2DestructionListener* listener) { m_destructionListener = listener; }
-  void SetContactFilter(b2ContactFilter* filter) { m_contactFilter = filter; }
+  /// Category / mask / group filtering (the default b2ContactFilter) and joint collideConnected run on
+  /// the device.  A user subclass overriding ShouldCollide is NOT consulted (logged once).
+  void SetContactFilter(b2ContactFilter* filter);
   void SetContactListener(b2ContactListener* listener) { m_contactListener = listener; }
   b2Body* CreateBody(const b2BodyDef* def);
   void DestroyBody(b2Body* body);

@@ -6,7 +6,7 @@ WL=${1:-many_pyramids}
 SKIP=${2:-2600}
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --workload $WL --steps 8 --warmup 70 --profile-steps 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_solve_bins_fused|k_bp_traverse|k_narrowphase|k_island_union$|k_solve_velocity$" -s ${3:-300} -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:"k_solve_bins_fused|k_bp_traverse|k_narrowphase|k_wide_refit|k_island_union$" -s ${3:-400} -c 10 \
     -o gpurun_out/prof python bench.py --workload $WL --steps 4 --warmup 70 --profile-steps 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_bench.log | cut -c1-200
 ls -la gpurun_out/
