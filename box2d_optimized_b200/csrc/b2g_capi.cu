@@ -964,8 +964,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
          A->islandAwake, A->islandCount, A->dCounts, A->islandDirty);
   LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandAwake, A->islandCount, A->islandStart,
          A->binFirst, A->binEnd, binSize, bigThr, A->dCounts, A->islandWasBig);
-  LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
-         A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr, A->dCounts);
+  if (nc == 0)  // otherwise the scatter rides in k_mark_active_bins
+    LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
+           A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr, A->dCounts);
 
   int numActive = 0, numBig = 0, rounds = 0;
   // Colouring rounds.  Constraints of tile-sized islands that are still uncoloured after the rounds
@@ -976,15 +977,20 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   int round = 0;
   int cgrid = div_up(nc > 0 ? nc : 1, 256);
   if (cgrid > 148 * 8) cgrid = 148 * 8;
-  auto colour_rounds = [&](int n) {
+  // round 0's proposals were made by k_mark_active_bins; `count` folds the counting pass of the
+  // bucket sort into the last commit (only valid when no further round can follow)
+  auto colour_rounds = [&](int n, bool count) {
     for (int r = 0; r < n; ++r, ++round) {
-      LAUNCH(A, KC_COLOUR, nc, k_colour2_propose, cgrid, 256, nc, A->cbin, C, A->mass, A->bodyBest, round);
+      if (round > 0)
+        LAUNCH(A, KC_COLOUR, nc, k_colour2_propose, cgrid, 256, nc, A->cbin, C, A->mass, A->bodyBest, round);
+      const bool last = r == n - 1;
       LAUNCH(A, KC_COLOUR, nc, k_colour2_commit, cgrid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->bodyBest,
-             round, A->dCounts, r == n - 1, bigBin);
+             round, A->dCounts, last, bigBin, (last && count) ? A->bucketCount : (int*)nullptr, A->conVals);
     }
   };
-  auto bucket_sort = [&]() {
-    LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
+  auto bucket_sort = [&](bool counted) {
+    if (!counted)
+      LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
     LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
     LAUNCH(A, KC_COLOUR, nc, k_bucket_scatter, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketStart, A->conVals,
            A->sortedList);
@@ -996,7 +1002,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         return B2G_ERR_CUDA;
       }
       CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
-      colour_rounds(4);
+      colour_rounds(4, false);
       int rc = read_counts(A);
       if (rc) return rc;
     }
@@ -1008,21 +1014,22 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   // wait then overlaps the GPU's work instead of draining the stream.
   const bool speculative = nc > 0 && A->lastNumBig == 0 && !A->kernelTiming;
   if (nc > 0) {
-    LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->bflags, A->island,
+    const int nmax = nb > nc ? nb : nc;
+    LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nmax, 256), 256, nc, C, A->fTypeFlags, A->bflags, A->island,
            A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->recolour, binSize, bigThr, bigBin, A->dCounts,
-           A->mass, A->colourMask);
+           A->mass, A->colourMask, nb, A->islandCursor, A->bodySlot, A->slotBody, A->bodyBest);
     A->recolour = 0;
-    colour_rounds(A->lastNumBig > 0 ? A->roundsHint : 2);
+    colour_rounds(A->lastNumBig > 0 ? A->roundsHint : 2, speculative);
     if (speculative) {
       CK(cudaMemcpyAsync(A->hCounts, A->dCounts, sizeof(StepCounts), cudaMemcpyDeviceToHost, A->stream));
       CK(cudaEventRecord(A->ev[4], A->stream));
-      bucket_sort();
+      bucket_sort(true);
     } else {
       int rc = read_counts(A);
       if (rc) return rc;
       rc = converge();
       if (rc) return rc;
-      if (A->hCounts->numActive > 0) bucket_sort();
+      if (A->hCounts->numActive > 0) bucket_sort(false);
     }
   }
 
@@ -1065,7 +1072,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         int rc = converge();
         if (rc) return rc;
         CK(cudaMemsetAsync(A->bucketCount, 0, sizeof(int) * (size_t)nbuckets, A->stream));
-        bucket_sort();
+        bucket_sort(false);
       }
     }
     rounds = round;

@@ -49,13 +49,11 @@ __global__ void k_island_alloc(int nb, const int* __restrict__ island, const uin
 }
 
 // slot of every simulated body inside its island's range
-__global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
-                               const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
-                               const int* __restrict__ islandStart, int* islandCursor, int* bodySlot, int* slotBody,
-                               int bigThreshold, StepCounts* counts) {
-  B2G_PDL_ENTER();
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
+__device__ __forceinline__ void body_scatter_one(int b, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
+                                                 const uint32_t* __restrict__ islandAwake,
+                                                 const int* __restrict__ islandCount, const int* __restrict__ islandStart,
+                                                 int* islandCursor, int* bodySlot, int* slotBody, int bigThreshold,
+                                                 StepCounts* counts) {
   if (!body_simulated(bflags[b], island, islandAwake, b)) {
     bodySlot[b] = B2G_SLOT_NONE;
     return;
@@ -71,16 +69,30 @@ __global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, cons
   bodySlot[b] = slot;
   slotBody[slot] = b;
 }
+__global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, const int* __restrict__ island,
+                               const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
+                               const int* __restrict__ islandStart, int* islandCursor, int* bodySlot, int* slotBody,
+                               int bigThreshold, StepCounts* counts) {
+  B2G_PDL_ENTER();
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  body_scatter_one(b, bflags, island, islandAwake, islandCount, islandStart, islandCursor, bodySlot, slotBody, bigThreshold,
+                   counts);
+}
 
-// active constraints and the bin each belongs to (-1 inactive, bigBin for oversize islands)
+// Also carries two neighbours that depend on the same inputs and on nothing else, to save their
+// launches: the body scatter (thread i handles body i) and round 0 of the colouring proposals.
 __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restrict__ fTypeFlags,
                                    const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                    const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
                                    const int* __restrict__ islandStart, int* cbin, int dropColours, int binSize,
                                    int bigThreshold, int bigBin, StepCounts* counts, const float4* __restrict__ mass,
-                                   unsigned long long* colourMask) {
+                                   unsigned long long* colourMask, int nb, int* islandCursor, int* bodySlot,
+                                   int* slotBody, unsigned long long* bodyBest) {
   B2G_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) body_scatter_one(i, bflags, island, islandAwake, islandCount, islandStart, islandCursor, bodySlot, slotBody,
+                               bigThreshold, counts);
   if (i >= nc) return;
   // loads first, tests afterwards: three rounds of independent loads instead of a six-deep chain
   // (dead slots keep in-range indices)
@@ -118,6 +130,11 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
     if (body_movable(massB)) atomicOr(&colourMask[bd.y], bit);
     if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
     if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
+  } else if (active) {
+    // round 0 of the colouring (k_colour2_propose with round = 0)
+    unsigned long long pr = colour_priority(0, i, C.key[i]);
+    if (body_movable(massA)) atomicMax(&bodyBest[bd.x], pr);
+    if (body_movable(massB)) atomicMax(&bodyBest[bd.y], pr);
   }
 }
 
@@ -133,34 +150,44 @@ __global__ void k_colour2_propose(int nc, const int* __restrict__ cbin, ContactB
   }
 }
 
+// bucketCount != nullptr (only on the final round of a step without oversize islands): also the
+// counting pass of the (bin, colour) sort — every active constraint knows its final colour here.
 __global__ void k_colour2_commit(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
                                  unsigned long long* colourMask, const unsigned long long* __restrict__ bodyBest,
-                                 int round, StepCounts* counts, int lastOfBatch, int bigBin) {
+                                 int round, StepCounts* counts, int lastOfBatch, int bigBin, int* bucketCount,
+                                 int* rank) {
   B2G_PDL_ENTER();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
     int bin = cbin[i];
-    if (bin < 0 || C.colour[i] >= 0) continue;
-    int2 bd = C.body[i];
-    unsigned long long pr = colour_priority(round, i, C.key[i]);
-    bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
-    bool win = (!movA || bodyBest[bd.x] == pr) && (!movB || bodyBest[bd.y] == pr);
-    if (win) {
-      unsigned long long used = (movA ? colourMask[bd.x] : 0ull) | (movB ? colourMask[bd.y] : 0ull);
-      unsigned long long freeBits = ~used & ((1ull << B2G_MAX_COLOURS) - 1ull);
-      int c = freeBits ? (__ffsll((long long)freeBits) - 1) : B2G_OVERFLOW_COLOUR;
-      C.colour[i] = c;
-      if (c < B2G_MAX_COLOURS) {
-        unsigned long long bit = 1ull << c;
-        if (movA) colourMask[bd.x] |= bit;
-        if (movB) colourMask[bd.y] |= bit;
-        if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
-      } else {
-        atomicAdd(&counts->numOverflow, 1);
+    if (bin < 0) continue;
+    int c = C.colour[i];
+    if (c < 0) {
+      int2 bd = C.body[i];
+      unsigned long long pr = colour_priority(round, i, C.key[i]);
+      bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
+      bool win = (!movA || bodyBest[bd.x] == pr) && (!movB || bodyBest[bd.y] == pr);
+      if (win) {
+        unsigned long long used = (movA ? colourMask[bd.x] : 0ull) | (movB ? colourMask[bd.y] : 0ull);
+        unsigned long long freeBits = ~used & ((1ull << B2G_MAX_COLOURS) - 1ull);
+        c = freeBits ? (__ffsll((long long)freeBits) - 1) : B2G_OVERFLOW_COLOUR;
+        C.colour[i] = c;
+        if (c < B2G_MAX_COLOURS) {
+          unsigned long long bit = 1ull << c;
+          if (movA) colourMask[bd.x] |= bit;
+          if (movB) colourMask[bd.y] |= bit;
+          if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
+        } else {
+          atomicAdd(&counts->numOverflow, 1);
+        }
+        if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
+        if (counts->lastUsefulRound < round + 1) atomicMax(&counts->lastUsefulRound, round + 1);
+      } else if (lastOfBatch) {
+        atomicAdd(&counts->remaining, 1);
       }
-      if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
-      if (counts->lastUsefulRound < round + 1) atomicMax(&counts->lastUsefulRound, round + 1);
-    } else if (lastOfBatch) {
-      atomicAdd(&counts->remaining, 1);
+    }
+    if (bucketCount) {
+      if (c < 0) c = B2G_OVERFLOW_COLOUR;  // not coloured within this step's rounds: serial bucket, retried next step
+      rank[i] = atomicAdd(&bucketCount[(bin << B2G_COLOUR_BITS) | c], 1);
     }
   }
 }
