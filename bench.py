@@ -352,10 +352,14 @@ def main():
 
     def e2e_step():
         B.upload_forces(hforce, 0, nb)                                   # H2D from pinned memory
-        B.step(P, None)
-        after_step(B)
-        capi.check(lib.b2g_download_body_state_async(B.h, 0, nb, hstate))  # D2H into pinned memory
-        B.synchronize()
+        if slab_mode:
+            B.step(P, None)
+            after_step(B)
+            capi.check(lib.b2g_download_body_state_async(B.h, 0, nb, hstate))  # D2H into pinned memory
+            B.synchronize()
+        else:
+            # step + D2H of the result into pinned memory; returns when both are complete
+            capi.check(lib.b2g_step_download(B.h, C.byref(P), None, 0, nb, hstate))
 
     for _ in range(args.warmup):
         e2e_step()

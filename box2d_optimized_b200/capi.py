@@ -79,7 +79,7 @@ class StepStats(C.Structure):
 CUDA_SYMBOLS = [
     "b2g_last_error", "b2g_device_count", "b2g_arena_create", "b2g_arena_destroy", "b2g_upload_bodies",
     "b2g_upload_fixtures", "b2g_upload_shapes", "b2g_upload_joints", "b2g_set_counts", "b2g_upload_forces",
-    "b2g_step", "b2g_step_collide", "b2g_step_solve", "b2g_find_new_contacts", "b2g_download_bodies",
+    "b2g_step", "b2g_step_download", "b2g_step_collide", "b2g_step_solve", "b2g_find_new_contacts", "b2g_download_bodies",
     "b2g_download_body_state_async", "b2g_download_fixture_aabbs", "b2g_contact_count", "b2g_download_contacts",
     "b2g_upload_contact_overrides", "b2g_download_events", "b2g_synchronize", "b2g_stream", "b2g_set_profiling",
     "b2g_set_inv_dt0", "b2g_set_kernel_timing", "b2g_kernel_class_count", "b2g_kernel_class_name",
@@ -123,6 +123,8 @@ def load_cuda():
         lib.b2g_set_counts.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         lib.b2g_upload_forces.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         lib.b2g_step.argtypes = [C.c_void_p, C.POINTER(StepParams), C.POINTER(StepStats)]
+        lib.b2g_step_download.argtypes = [C.c_void_p, C.POINTER(StepParams), C.POINTER(StepStats), C.c_int32, C.c_int32,
+                                          C.c_void_p]
         lib.b2g_step_collide.argtypes = [C.c_void_p, C.POINTER(StepParams)]
         lib.b2g_step_solve.argtypes = [C.c_void_p, C.POINTER(StepParams), C.POINTER(StepStats)]
         lib.b2g_find_new_contacts.argtypes = [C.c_void_p]

@@ -68,6 +68,10 @@ struct ContactBuf {
 struct b2gArena {
   int device;
   cudaStream_t stream;
+  cudaStream_t copyStream;      // body-state readback of b2g_step_download, overlapped with the pair refresh
+  cudaEvent_t evPacked;
+  float* pendingStateDst;       // host destination of the step in flight (b2g_step_download)
+  int pendingStateFirst, pendingStateCount;
   cudaEvent_t ev[5];
   int profiling;
   int numWorlds, worldBits;

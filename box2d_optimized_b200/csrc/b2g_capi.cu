@@ -211,6 +211,8 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   A->recolour = 1;
   A->roundsHint = 8;
   CK(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&A->copyStream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&A->evPacked, cudaEventDisableTiming));
   for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&A->ev[i]));
   for (int i = 0; i < 2 * B2G_KT_MAX; ++i) CK(cudaEventCreate(&A->ktEv[i]));
 
@@ -371,6 +373,8 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   for (int i = 0; i < 5; ++i) cudaEventDestroy(A->ev[i]);
   for (int i = 0; i < 2 * B2G_KT_MAX; ++i) cudaEventDestroy(A->ktEv[i]);
   cudaStreamDestroy(A->stream);
+  cudaStreamDestroy(A->copyStream);
+  cudaEventDestroy(A->evPacked);
   free(A);
   return B2G_OK;
 }
@@ -1152,6 +1156,14 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   return B2G_OK;
 }
 
+__global__ void k_pack_body_state(int first, int count, const float4* __restrict__ xf, const float4* __restrict__ vel,
+                                  float4* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[2 * i] = xf[first + i];
+  out[2 * i + 1] = vel[first + i];
+}
+
 static int step_check(b2gArena* A, const b2gStepParams* P) {
   if (!A || !P) return B2G_ERR_INVALID;
   if (P->position_iterations > B2G_MAX_POS_ITERS || P->position_iterations < 0 || P->velocity_iterations < 0) {
@@ -1211,6 +1223,19 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
     rounds = so.rounds;
     if (prof) CK(cudaEventRecord(A->ev[2], A->stream));
 
+    // body state is final here (the pair refresh only reads transforms): a requested readback is
+    // packed now and copied on a second stream while the broadphase runs
+    if (A->pendingStateDst && A->pendingStateCount > 0) {
+      k_pack_body_state<<<div_up(A->pendingStateCount, 256), 256, 0, A->stream>>>(
+          A->pendingStateFirst, A->pendingStateCount, A->xf, A->vel, A->stateStage);
+      CK(cudaGetLastError());
+      A->launches++;
+      CK(cudaEventRecord(A->evPacked, A->stream));
+      CK(cudaStreamWaitEvent(A->copyStream, A->evPacked, 0));
+      CK(cudaMemcpyAsync(A->pendingStateDst, A->stateStage, (size_t)A->pendingStateCount * 32, cudaMemcpyDeviceToHost,
+                         A->copyStream));
+    }
+
     // ---- FindNewContacts (end of Solve, b2_world.cpp:663-669) ------------------------
     int rc = find_new_contacts(A, P->record_events);
     A->invDt0 = inv_dt;  // the solve is complete even if the pair list could not grow
@@ -1263,6 +1288,22 @@ extern "C" int b2g_step(b2gArena* A, const b2gStepParams* P, b2gStepStats* stats
   return b2g_step_solve(A, P, stats);
 }
 
+extern "C" int b2g_step_download(b2gArena* A, const b2gStepParams* P, b2gStepStats* stats, int32_t first, int32_t count,
+                                 float* dst) {
+  if (!A || !dst || first < 0 || count < 0 || first + count > A->nBodies) return B2G_ERR_INVALID;
+  int rc = b2g_step_collide(A, P);
+  if (rc) return rc;
+  A->pendingStateDst = dst;
+  A->pendingStateFirst = first;
+  A->pendingStateCount = count;
+  rc = b2g_step_solve(A, P, stats);
+  A->pendingStateDst = nullptr;
+  cudaError_t e = cudaStreamSynchronize(A->copyStream);
+  if (rc) return rc;
+  CK(e);
+  return B2G_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // readback
 // ---------------------------------------------------------------------------------------------
@@ -1285,13 +1326,6 @@ extern "C" int b2g_download_bodies(b2gArena* A, int32_t first, int32_t count, co
   return B2G_OK;
 }
 
-__global__ void k_pack_body_state(int first, int count, const float4* __restrict__ xf, const float4* __restrict__ vel,
-                                  float4* out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  out[2 * i] = xf[first + i];
-  out[2 * i + 1] = vel[first + i];
-}
 
 extern "C" int b2g_download_body_state_async(b2gArena* A, int32_t first, int32_t count, float* dst) {
   if (!A || !dst || first < 0 || count < 0 || first + count > A->nBodies) return B2G_ERR_INVALID;

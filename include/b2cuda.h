@@ -223,6 +223,13 @@ int b2g_step(b2gArena* arena, const b2gStepParams* params, b2gStepStats* stats);
  * pair refresh creates the missing contacts exactly when the reference would first use them.
  * host/b2_world_host.cpp does this automatically. */
 
+/* b2g_step followed by b2g_download_body_state_async + b2g_synchronize for bodies [first,
+ * first+count), except that the readback ([count][8] = xf(4), vel(4), pinned dst recommended)
+ * starts as soon as Solve has written the final body state and overlaps the pair refresh at the
+ * end of the step.  When the call returns, dst is complete. */
+int b2g_step_download(b2gArena* arena, const b2gStepParams* params, b2gStepStats* stats, int32_t first,
+                      int32_t count, float* dst);
+
 /* The same step in two halves, for hosts that must run b2ContactListener::PreSolve between
  * the narrowphase and the solver (b2_contact.cpp:197-209 fires inside Collide):
  *   b2g_step_collide = b2ContactManager::Collide (b2_world.cpp:1134-1138)

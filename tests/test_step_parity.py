@@ -178,3 +178,25 @@ def test_colouring_is_valid(require_ref, name, size, steps):
     print(f"{name}: {st.num_constraints} constraints, {st.num_colours} colours, {st.num_overflow} overflow, "
           f"{st.colour_rounds} rounds")
     A.close()
+
+
+def test_step_download_returns_the_state_of_that_step():
+    """b2g_step_download (readback overlapped with the end-of-step pair refresh) == b2g_step followed by
+    a download, bit for bit, on two arenas stepped side by side."""
+    import ctypes as C
+    from box2d_optimized_b200 import GpuScene
+    sc = GpuScene("pyramid", 12, 0)
+    A, B = arena_from_scene(sc), arena_from_scene(sc)
+    A.find_new_contacts()
+    B.find_new_contacts()
+    P = Arena.params()
+    n = sc.body_count
+    out = np.zeros((n, 8), np.float32)
+    for k in range(40):
+        A.step(P)
+        capi.check(A.lib.b2g_step_download(B.h, C.byref(P), None, 0, n, C.c_void_p(out.ctypes.data)))
+        a = A.download_bodies(what=("xf", "vel"))
+        assert np.array_equal(out[:, :4].view(np.uint32), a["xf"].view(np.uint32)), f"step {k}"
+        assert np.array_equal(out[:, 4:].view(np.uint32), a["vel"].view(np.uint32)), f"step {k}"
+    A.close()
+    B.close()
