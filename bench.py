@@ -412,7 +412,7 @@ def main():
                        "timed_window": f"steps {args.warmup}..{args.warmup + args.steps}"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": e2e_ms_max / args.steps,
-                    "h2d_bytes_per_step": nb * 12, "d2h_bytes_per_step": nb * 32},
+                    "h2d_bytes_per_step": nb * 16, "d2h_bytes_per_step": nb * 32},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -140,6 +140,7 @@ struct b2gArena {
   unsigned long long* ncKeysSorted;
   uint8_t* bodyNoCollide;         // [capBodies] body has at least one collideConnected == false joint
   int jointFilterDirty;
+  float4* forceStage; // [capBodies] host forces land here in one linear copy, then merge into force.xyz
   float4* stateStage; // [capBodies][2] packed xf+vel for b2g_download_body_state_async (one linear D2H)
   JointWork* jWork;  // per-step scratch
 

@@ -200,3 +200,25 @@ def test_step_download_returns_the_state_of_that_step():
         assert np.array_equal(out[:, 4:].view(np.uint32), a["vel"].view(np.uint32)), f"step {k}"
     A.close()
     B.close()
+
+
+def test_upload_forces_sets_force_and_torque_only():
+    """b2g_upload_forces: columns 0-2 (force, torque) come from the host, column 3 (the sleep timer the
+    device owns) is left alone; one step later v = F / m * dt (b2_island.cpp:270-279)."""
+    import ctypes as C
+    sc = GpuScene("hello", 0, 0)   # a static ground box and one dynamic 2x2 box (density 1: mass 4, I = 8/3)
+    A = arena_from_scene(sc)
+    A.find_new_contacts()
+    n = sc.body_count
+    before = A.download_bodies(what=("force", "mass", "vel"))
+    f = np.zeros((n, 4), np.float32)
+    f[1] = [8.0, 0.0, 2.0, 123.0]   # the fourth column must be ignored
+    capi.check(A.lib.b2g_upload_forces(A.h, 0, n, C.c_void_p(f.ctypes.data)))
+    mid = A.download_bodies(what=("force",))["force"]
+    assert np.array_equal(mid[:, :3], f[:, :3]) and np.array_equal(mid[:, 3], before["force"][:, 3])
+    dt = 1.0 / 60.0
+    A.step(Arena.params(dt=dt, gravity=(0.0, 0.0)))
+    v = A.download_bodies(what=("vel",))["vel"][1]
+    inv_m, inv_i = before["mass"][1, 0], before["mass"][1, 1]
+    assert abs(v[0] - 8.0 * inv_m * dt) < 1e-6 and abs(v[2] - 2.0 * inv_i * dt) < 1e-6 and v[1] == 0.0
+    A.close()
