@@ -65,7 +65,10 @@ def rel(a, b):
                                                    ("pendulum_limit", 6, 0, 120), ("pendulum_motor", 6, 0, 120),
                                                    # sensor zones, a kinematic sensor paddle and probes: touching of sensor
                                                    # contacts = b2TestOverlap (GJK), compared contact by contact every step
-                                                   ("sensors", 300, 0, 240)])
+                                                   ("sensors", 300, 0, 240),
+                                                   # several joints in one island: the device walks them in descending
+                                                   # index order, which is the reference's DFS order for these chains
+                                                   ("chain", 14, 0, 300), ("chain_collide", 14, 0, 200)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
     from box2d_optimized_b200 import RefScene
     ref = RefScene(name, size, seed)
