@@ -83,7 +83,7 @@ CUDA_SYMBOLS = [
     "b2g_download_body_state_async", "b2g_download_fixture_aabbs", "b2g_contact_count", "b2g_download_contacts",
     "b2g_upload_contact_overrides", "b2g_download_events", "b2g_synchronize", "b2g_stream", "b2g_set_profiling",
     "b2g_set_inv_dt0", "b2g_set_kernel_timing", "b2g_kernel_class_count", "b2g_kernel_class_name",
-    "b2g_get_kernel_timing", "b2g_device_views", "b2g_upload_contacts", "b2g_set_sequential_order", "b2g_host_alloc", "b2g_host_free", "b2g_query_aabb", "b2g_ray_cast_closest", "b2g_ray_cast_all", "b2g_download_joints", "b2g_rotations", "b2g_compute_aabbs", "b2g_collide_pairs",
+    "b2g_get_kernel_timing", "b2g_device_views", "b2g_upload_contacts", "b2g_set_sequential_order", "b2g_host_alloc", "b2g_host_free", "b2g_download_new_pairs", "b2g_set_pair_vetoes", "b2g_download_veto_seen", "b2g_query_aabb", "b2g_ray_cast_closest", "b2g_ray_cast_all", "b2g_download_joints", "b2g_rotations", "b2g_compute_aabbs", "b2g_collide_pairs",
     "b2g_find_pairs", "b2g_solve_sequential",
 ]
 
@@ -146,6 +146,9 @@ def load_cuda():
                                               C.POINTER(C.c_double)]
         lib.b2g_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
         lib.b2g_host_free.argtypes = [C.c_void_p]
+        lib.b2g_download_new_pairs.argtypes = [C.c_void_p, C.c_int32, i32p, i32p, i32p]
+        lib.b2g_set_pair_vetoes.argtypes = [C.c_void_p, C.c_int32, i32p, i32p]
+        lib.b2g_download_veto_seen.argtypes = [C.c_void_p, C.c_int32, u8p]
         lib.b2g_query_aabb.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         lib.b2g_ray_cast_closest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]

@@ -49,6 +49,12 @@ struct ContactHash {
   // collideConnected == false, as sorted keys bodyLo << 32 | bodyHi (binary search; usually empty)
   const unsigned long long* ncKeys;
   int ncCount;
+  // pairs a user b2ContactFilter::ShouldCollide rejected (b2_contact_manager.cpp:163-170), sorted
+  // fixLo << 32 | fixHi; a rejected pair that is still overlapping marks vetoSeen so that the host
+  // can ask the filter again, as the reference does on every step the pair is found without a contact
+  const unsigned long long* vetoKeys;
+  uint8_t* vetoSeen;
+  int vetoCount;
 };
 
 // contacts live in stable slots; a slot is live when its flags carry B2G_CONTACT_ALIVE
@@ -169,6 +175,10 @@ struct b2gArena {
   unsigned long long* bvhKey;   // and the largest leaf key below each node
   int* bvhDone;                 // last-block-done counter of the refit
   unsigned long long *pairKeys;  // new pairs (no live contact yet) reported by the traversal
+  int lastNewPairs;              // how many of them the last pair refresh inserted
+  unsigned long long* vetoKeys;  // see ContactHash
+  uint8_t* vetoSeen;
+  int vetoCap;
 
   // solver scratch
   uint8_t* activeFlag;

@@ -452,6 +452,18 @@ __device__ __forceinline__ void emit_pair(int4 a, int4 b, const ContactHash& H, 
   }
   unsigned long long lo = (unsigned long long)min(a.x, b.x), hi = (unsigned long long)max(a.x, b.x);
   unsigned long long key = (lo << 32) | hi;
+  if (H.vetoCount > 0) {  // rejected by the user's contact filter: no contact, but remember it still overlaps
+    int l = 0, r = H.vetoCount - 1;
+    while (l <= r) {
+      int m = (l + r) >> 1;
+      unsigned long long v = H.vetoKeys[m];
+      if (v == key) {
+        H.vetoSeen[m] = 1;
+        return;
+      }
+      if (v < key) l = m + 1; else r = m - 1;
+    }
+  }
   int slot = hash_find(H, key);
   if (slot >= 0) {
     persist[slot] = 1;
@@ -593,6 +605,25 @@ k_bp_traverse(WideBvh T, const float4* __restrict__ leafBox, const int4* __restr
 // still-overlapping pair, k_contact_sweep retires the rest and k_contact_insert creates the new
 // ones in free slots.  Slot numbers are not deterministic (free-list order), and nothing depends
 // on them: islands, colours and the solver are functions of bodies and pair keys only.
+
+// contacts of pairs the user's filter has just rejected: they were inserted by the refresh that
+// found the pair and are taken out again before any narrowphase saw them (no wake-up, no event —
+// in the reference such a contact is never created)
+__global__ void k_contacts_remove(int n, const unsigned long long* __restrict__ keys, ContactBuf C, ContactHash H,
+                                  int* freeStack, int* freeTop, int* removed) {
+  B2G_PDL_ENTER();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long key = keys[i];
+  int slot = hash_find(H, key);
+  if (slot < 0) return;
+  C.flags[slot] = 0;
+  C.colour[slot] = -1;
+  hash_erase(H, key);
+  int t = atomicAdd(freeTop, 1);
+  freeStack[t] = slot;
+  atomicAdd(removed, 1);
+}
 
 // contacts that were not re-reported die: b2ContactManager::Destroy (b2_contact_manager.cpp:48-61)
 // fires EndContact if touching, b2Contact::Destroy (b2_contact.cpp:79-94) wakes both bodies if the

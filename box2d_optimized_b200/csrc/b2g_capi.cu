@@ -374,6 +374,8 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   for (int i = 0; i < 5; ++i) cudaEventDestroy(A->ev[i]);
   for (int i = 0; i < 2 * B2G_KT_MAX; ++i) cudaEventDestroy(A->ktEv[i]);
   cudaStreamDestroy(A->stream);
+  if (A->vetoKeys) cudaFree(A->vetoKeys);
+  if (A->vetoSeen) cudaFree(A->vetoSeen);
   cudaStreamDestroy(A->copyStream);
   cudaEventDestroy(A->evPacked);
   free(A);
@@ -645,6 +647,7 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
   CK(cudaMemcpyAsync(&A->hCounts->freeTopRead, A->dFreeTop, sizeof(int), cudaMemcpyDeviceToHost, A->stream));
   CK(cudaStreamSynchronize(A->stream));
   nNew = A->hCounts->numPairs;
+  A->lastNewPairs = nNew <= A->capContacts ? nNew : 0;
   if (nf > 1) {
     A->bvhVisitsLast = (float)((double)A->hCounts->bpVisits / nf);
     if (A->bvhAge == 0) A->bvhVisitsFresh = A->bvhVisitsLast;
@@ -1691,6 +1694,83 @@ extern "C" int b2g_ray_cast_all(b2gArena* A, int32_t n, const float* rays, const
     return B2G_ERR_INVALID;
   return ray_cast_common(A, 1, n, rays, max_fraction, world, category_mask, cap, counts, fixture, fraction, normal,
                          on_device);
+}
+
+// ---------------------------------------------------------------------------------------------
+// user contact filter (b2ContactFilter::ShouldCollide): the callback lives on the host, so the host
+// inspects the pairs each refresh inserted and hands the rejected ones back as a veto list
+// ---------------------------------------------------------------------------------------------
+extern "C" int b2g_download_new_pairs(b2gArena* A, int32_t capacity, int32_t* fixture_a, int32_t* fixture_b,
+                                      int32_t* count) {
+  if (!A || !count || capacity < 0) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  int n = A->lastNewPairs;
+  *count = n;
+  if (n > capacity) n = capacity;
+  if (n == 0 || !fixture_a || !fixture_b) return B2G_OK;
+  std::vector<unsigned long long> keys((size_t)n);
+  CK(cudaMemcpyAsync(keys.data(), A->pairKeys, (size_t)n * 8, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  for (int i = 0; i < n; ++i) {
+    fixture_a[i] = (int32_t)(keys[i] >> 32);
+    fixture_b[i] = (int32_t)(keys[i] & 0xffffffffull);
+  }
+  return B2G_OK;
+}
+
+extern "C" int b2g_set_pair_vetoes(b2gArena* A, int32_t count, const int32_t* fixture_a, const int32_t* fixture_b) {
+  if (!A || count < 0 || (count > 0 && (!fixture_a || !fixture_b))) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  std::vector<unsigned long long> keys((size_t)count);
+  for (int i = 0; i < count; ++i) {
+    unsigned long long lo = (unsigned long long)std::min(fixture_a[i], fixture_b[i]);
+    unsigned long long hi = (unsigned long long)std::max(fixture_a[i], fixture_b[i]);
+    keys[i] = (lo << 32) | hi;
+  }
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  count = (int32_t)keys.size();
+  if (count > A->vetoCap) {
+    int cap = A->vetoCap > 0 ? A->vetoCap : 256;
+    while (cap < count) cap *= 2;
+    CK(cudaStreamSynchronize(A->stream));
+    if (A->vetoKeys) cudaFree(A->vetoKeys);
+    if (A->vetoSeen) cudaFree(A->vetoSeen);
+    CK(dalloc(&A->vetoKeys, (size_t)cap));
+    CK(dalloc(&A->vetoSeen, (size_t)cap));
+    A->vetoCap = cap;
+  }
+  if (count > 0) {
+    CK(cudaMemcpyAsync(A->vetoKeys, keys.data(), (size_t)count * 8, cudaMemcpyHostToDevice, A->stream));
+    CK(cudaMemsetAsync(A->vetoSeen, 0, (size_t)count, A->stream));
+    // contacts of vetoed pairs leave before any narrowphase sees them
+    DevBuf dRemoved;
+    CK(dRemoved.alloc(4));
+    CK(cudaMemsetAsync(dRemoved.p, 0, 4, A->stream));
+    k_contacts_remove<<<div_up(count, 256), 256, 0, A->stream>>>(count, A->vetoKeys, A->cb[0], A->hash, A->freeStack,
+                                                                 A->dFreeTop, dRemoved.as<int>());
+    CK(cudaGetLastError());
+    int removed = 0;
+    CK(cudaMemcpyAsync(&removed, dRemoved.p, 4, cudaMemcpyDeviceToHost, A->stream));
+    CK(cudaStreamSynchronize(A->stream));
+    A->nAlive -= removed;
+    A->tombstones += removed;
+  }
+  CK(cudaStreamSynchronize(A->stream));
+  A->hash.vetoKeys = A->vetoKeys;
+  A->hash.vetoSeen = A->vetoSeen;
+  A->hash.vetoCount = count;
+  return B2G_OK;
+}
+
+extern "C" int b2g_download_veto_seen(b2gArena* A, int32_t count, uint8_t* seen) {
+  if (!A || count < 0 || count > A->hash.vetoCount || (count > 0 && !seen)) return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
+  CK(cudaSetDevice(A->device));
+  CK(cudaMemcpyAsync(seen, A->vetoSeen, (size_t)count, cudaMemcpyDeviceToHost, A->stream));
+  CK(cudaMemsetAsync(A->vetoSeen, 0, (size_t)count, A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
 }
 
 extern "C" int b2g_download_events(b2gArena* A, int32_t* beginPairs, int32_t* beginCount, int32_t* endPairs,

@@ -73,6 +73,12 @@ struct b2WorldImpl {
   } saved;
   void saveDeviceState();
   void growContacts();
+  // user b2ContactFilter: pairs it rejected (fixture index pairs, sorted) and fixtures whose
+  // contacts must be offered to it again (b2Fixture::Refilter)
+  std::vector<std::pair<int32_t, int32_t>> vetoes;
+  std::vector<int32_t> refilter;
+  bool customFilter() const;
+  void applyContactFilter();
   void ensureArena();
   void flush();
   void pullBodies();
@@ -132,6 +138,87 @@ void b2WorldImpl::ensureArena() {
   jointsDirty = needJoints > 0;
   jointsOnDevice = 0;
   world->m_newContacts = true;
+}
+
+bool b2WorldImpl::customFilter() const {
+  b2ContactFilter* F = world->m_contactFilter;
+  return F != nullptr && typeid(*F) != typeid(b2ContactFilter);
+}
+
+// b2ContactFilter::ShouldCollide for a user subclass (b2_contact_manager.cpp:163-170, 84-96).  The
+// device applies the default rule and inserts every pair that passes it; after each pair refresh
+// the host offers the newly inserted pairs (and, as the reference does every step, the rejected
+// pairs that still overlap, and the contacts of re-filtered fixtures) to the user's callback and
+// hands the rejected ones back as a veto list.  Their contacts are removed before any narrowphase.
+void b2WorldImpl::applyContactFilter() {
+  if (!arena) return;
+  if (!customFilter()) {
+    if (!vetoes.empty()) {
+      vetoes.clear();
+      b2gCheck(b2g_set_pair_vetoes(arena, 0, nullptr, nullptr), "b2g_set_pair_vetoes");
+      world->m_newContacts = true;
+    }
+    refilter.clear();
+    return;
+  }
+  b2ContactFilter* F = world->m_contactFilter;
+  auto alive = [&](int32_t f) { return f >= 0 && f < (int32_t)fixtures.size() && fixtures[f] != nullptr; };
+  bool changed = false, released = false;
+  std::vector<std::pair<int32_t, int32_t>> next;
+  if (!vetoes.empty()) {
+    std::vector<uint8_t> seen(vetoes.size());
+    b2gCheck(b2g_download_veto_seen(arena, (int32_t)vetoes.size(), seen.data()), "b2g_download_veto_seen");
+    for (size_t i = 0; i < vetoes.size(); ++i) {
+      auto v = vetoes[i];
+      if (seen[i] && alive(v.first) && alive(v.second) && !F->ShouldCollide(fixtures[v.first], fixtures[v.second])) {
+        next.push_back(v);  // still overlapping, still rejected
+      } else {
+        changed = true;     // separated, destroyed, or accepted now: the pair finder may report it again
+        released = released || seen[i];
+      }
+    }
+  }
+  int32_t nNew = 0;
+  b2gCheck(b2g_download_new_pairs(arena, 0, nullptr, nullptr, &nNew), "b2g_download_new_pairs");
+  if (nNew > 0) {
+    std::vector<int32_t> fa(nNew), fb(nNew);
+    b2gCheck(b2g_download_new_pairs(arena, nNew, fa.data(), fb.data(), &nNew), "b2g_download_new_pairs");
+    for (int32_t i = 0; i < nNew; ++i) {
+      if (!alive(fa[i]) || !alive(fb[i])) continue;
+      if (!F->ShouldCollide(fixtures[fa[i]], fixtures[fb[i]])) {
+        next.emplace_back(std::min(fa[i], fb[i]), std::max(fa[i], fb[i]));
+        changed = true;
+      }
+    }
+  }
+  if (!refilter.empty()) {
+    // b2Fixture::Refilter: every contact of the fixture is offered to the filter again
+    contactsStale = true;
+    pullContacts();
+    std::sort(refilter.begin(), refilter.end());
+    for (b2Contact* c : contacts) {
+      int32_t a = c->m_fixtureA->m_index, b = c->m_fixtureB->m_index;
+      if (!std::binary_search(refilter.begin(), refilter.end(), a) && !std::binary_search(refilter.begin(), refilter.end(), b))
+        continue;
+      if (!F->ShouldCollide(c->m_fixtureA, c->m_fixtureB)) {
+        next.emplace_back(std::min(a, b), std::max(a, b));
+        changed = true;
+      }
+    }
+    refilter.clear();
+  }
+  if (!changed) return;
+  std::sort(next.begin(), next.end());
+  next.erase(std::unique(next.begin(), next.end()), next.end());
+  vetoes.swap(next);
+  std::vector<int32_t> fa(vetoes.size()), fb(vetoes.size());
+  for (size_t i = 0; i < vetoes.size(); ++i) {
+    fa[i] = vetoes[i].first;
+    fb[i] = vetoes[i].second;
+  }
+  b2gCheck(b2g_set_pair_vetoes(arena, (int32_t)vetoes.size(), fa.data(), fb.data()), "b2g_set_pair_vetoes");
+  contactsStale = true;
+  if (released) world->m_newContacts = true;  // a released pair gets its contact at the next step's pair refresh
 }
 
 void b2WorldImpl::saveDeviceState() {
@@ -681,6 +768,7 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
     b2gCheck(rc, "b2g_find_new_contacts");
     m_newContacts = false;
     I->contactsStale = true;
+    I->applyContactFilter();
   }
   b2gStepParams P;
   P.dt = dt;
@@ -701,6 +789,7 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
       rc = B2G_OK;
     }
     b2gCheck(rc, "b2g_step");
+    I->applyContactFilter();  // the pairs this step's closing refresh inserted
   } else {
     // callbacks need the contact list between Collide and Solve (b2_contact.cpp:197-209)
     I->pullContacts();  // previous manifolds, for PreSolve's oldManifold
@@ -738,6 +827,7 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
       rc = B2G_OK;
     }
     b2gCheck(rc, "b2g_step_solve");
+    I->applyContactFilter();  // the pairs this step's closing refresh inserted
     // the broadphase at the end of the step rebuilt the list; handles of contacts that died are
     // parked in the graveyard (still valid) until the callbacks below have run
     I->contactsStale = true;
@@ -1179,6 +1269,7 @@ void b2Fixture::Refilter() {
   // the device re-evaluates the filter for every pair on every broadphase pass, which is the
   // effect of the reference's e_filterFlag protocol (b2_fixture.cpp:100-136)
   m_body->m_world->m_impl->touchFixture(m_index);
+  m_body->m_world->m_impl->refilter.push_back(m_index);
   m_body->m_world->m_newContacts = true;
 }
 bool b2Fixture::TestPoint(const b2Vec2& p) const { return m_shape->TestPoint(m_body->GetTransform(), p); }
@@ -1223,12 +1314,7 @@ void b2Contact::SetTangentSpeed(float v) { m_tangentSpeed = v; m_overridden = tr
 
 void b2World::SetContactFilter(b2ContactFilter* filter) {
   m_contactFilter = filter;
-  static bool warned = false;
-  if (filter && typeid(*filter) != typeid(b2ContactFilter) && !warned) {
-    warned = true;
-    fprintf(stderr, "[b2cuda] a custom b2ContactFilter::ShouldCollide is not consulted: pair filtering (category, mask, "
-                    "group, collideConnected) runs on the device\n");
-  }
+  m_newContacts = true;  // the next step starts with a pair refresh, after which the filter is consulted
 }
 bool b2ContactFilter::ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB) {
   const b2Filter& filterA = fixtureA->GetFilterData();

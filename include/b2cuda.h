@@ -311,6 +311,22 @@ int b2g_host_alloc(void** out, uint64_t bytes);
 int b2g_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------
+ * User contact filter, b2ContactFilter::ShouldCollide (b2_world_callbacks.h:60-69; consulted by
+ * b2ContactManager::QueryCallback, b2_contact_manager.cpp:163-170, whenever an overlapping pair has
+ * no contact).  The default category / mask / group rule and the joints' collideConnected run on
+ * the device; a user callback cannot, so the host mediates:
+ *   b2g_download_new_pairs   the pairs the last pair refresh inserted as contacts
+ *   b2g_set_pair_vetoes      the complete list of rejected pairs; their contacts are removed at
+ *                            once and the pair finder skips them from now on
+ *   b2g_download_veto_seen   seen[i] = 1 when vetoed pair i (sorted by lower fixture, then upper)
+ *                            still overlapped in the last refresh — ask the filter again, as the
+ *                            reference does every step; pairs not seen have separated: drop them
+ * ---------------------------------------------------------------------------------------- */
+int b2g_download_new_pairs(b2gArena* arena, int32_t capacity, int32_t* fixture_a, int32_t* fixture_b, int32_t* count);
+int b2g_set_pair_vetoes(b2gArena* arena, int32_t count, const int32_t* fixture_a, const int32_t* fixture_b);
+int b2g_download_veto_seen(b2gArena* arena, int32_t count, uint8_t* seen);
+
+/* ------------------------------------------------------------------------------------------
  * Spatial queries on the broadphase tree, batched.  All pointers are host
  * pointers, or device pointers on the arena's device when on_device != 0 (results then stay in
  * HBM; the call still returns after the kernel has finished).  world[i] >= 0 restricts query i to

@@ -529,7 +529,8 @@ class b2World {
   ~b2World();
   void SetDestructionListener(b2DestructionListener* listener) { m_destructionListener = listener; }
   /// Category / mask / group filtering (the default b2ContactFilter) and joint collideConnected run on
-  /// the device.  A user subclass overriding ShouldCollide is NOT consulted (logged once).
+  /// the device.  A user subclass is consulted on the host after every pair refresh for the pairs that
+  /// passed the device rule (and again every step for rejected pairs that still overlap).
   void SetContactFilter(b2ContactFilter* filter);
   void SetContactListener(b2ContactListener* listener) { m_contactListener = listener; }
   b2Body* CreateBody(const b2BodyDef* def);

@@ -406,6 +406,61 @@ static void world_editing_session() {
   trace("resting", world, b, 7);
 }
 
+// a user b2ContactFilter: boxes whose user data carry the same non-zero team pass through each other
+struct TeamFilter : b2ContactFilter {
+  int calls = 0;
+  bool ShouldCollide(b2Fixture* a, b2Fixture* b) override {
+    ++calls;
+    uintptr_t ta = a->GetBody()->GetUserData().pointer, tb = b->GetBody()->GetUserData().pointer;
+    if (ta != 0 && ta == tb) return false;
+    return b2ContactFilter::ShouldCollide(a, b);
+  }
+};
+static void user_contact_filter() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  TeamFilter filter;
+  world.SetContactFilter(&filter);
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2EdgeShape edge;
+  edge.SetTwoSided(b2Vec2(-20.0f, 0.0f), b2Vec2(20.0f, 0.0f));
+  ground->CreateFixture(&edge, 0.0f);
+  b2PolygonShape box;
+  box.SetAsBox(0.5f, 0.5f);
+  b2Body* b[3];
+  for (int i = 0; i < 3; ++i) {  // two overlapping boxes of team 7 side by side on the ground, a neutral one on top
+    b2BodyDef bd;
+    bd.type = b2_dynamicBody;
+    bd.position.Set(i == 0 ? 0.0f : (i == 1 ? 0.4f : 0.2f), i < 2 ? 0.6f : 1.8f);
+    bd.userData.pointer = i < 2 ? 7 : 0;
+    b[i] = world.CreateBody(&bd);
+    b[i]->CreateFixture(&box, 1.0f);
+  }
+  for (int i = 0; i < 180; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(filter.calls > 0);
+  // team mates interpenetrate: both rest on the ground; the neutral box rests on them
+  CHECK(fabsf(b[0]->GetPosition().y - 0.51f) < 0.02f);
+  CHECK(fabsf(b[1]->GetPosition().y - 0.51f) < 0.02f);
+  CHECK(fabsf(b[1]->GetPosition().x - b[0]->GetPosition().x - 0.4f) < 0.02f);  // still overlapping by 0.6
+  CHECK(fabsf(b[2]->GetPosition().y - 1.52f) < 0.03f);
+  for (b2Contact* c = world.GetContactListStart(); c != world.GetContactListEnd(); c = c->GetNext()) {
+    uintptr_t ta = c->GetFixtureA()->GetBody()->GetUserData().pointer, tb = c->GetFixtureB()->GetBody()->GetUserData().pointer;
+    CHECK(!(ta != 0 && ta == tb));
+  }
+  int contactsWith = world.GetContactCount();
+  // change sides: box 1 leaves the team, Refilter offers its contacts to the filter again and the
+  // (still overlapping) rejected pair is accepted at the next step
+  b[1]->GetUserData().pointer = 0;
+  b[1]->GetFixtureList()->Refilter();
+  b[1]->SetAwake(true);  // Refilter does not wake anybody, and a contact between sleepers is never evaluated
+  for (int i = 0; i < 120; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(world.GetContactCount() == contactsWith + 1);  // the former team mates now have a contact
+  float gap = b[1]->GetPosition().x - b[0]->GetPosition().x;
+  CHECK(gap > 0.95f);                                   // and have been pushed apart
+  printf("contact filter: %d calls, contacts %d -> %d, former team mates %.3f apart\n", filter.calls, contactsWith,
+         world.GetContactCount(), gap);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -416,6 +471,7 @@ int main() {
   revolute_joint_api();
   contact_buffers_grow();
   world_editing_session();
+  user_contact_filter();
   printf(g_failed ? "FAILED %d checks\n" : "all API checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }
