@@ -673,6 +673,20 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
 }
 
 // ---- spatial queries (b2_world.cpp:1193-1246) on the device tree -------------------------------
+void b2World::ShiftOrigin(const b2Vec2& newOrigin) {
+  if (IsLocked()) return;
+  m_impl->pullBodies();
+  for (b2Body* b = m_bodyListHead; b; b = b->m_next) {
+    b->m_xf.p -= newOrigin;
+    b->m_sweep.c0 -= newOrigin;
+    b->m_sweep.c -= newOrigin;
+    b->UpdateAABBs();
+    m_impl->touchBody(b->m_index);
+  }
+  // revolute joints hold local anchors only (b2_revolute_joint.cpp has no ShiftOrigin state)
+  m_newContacts = true;
+}
+
 void b2World::QueryAABB(b2QueryCallback* callback, const b2AABB& aabb) {
   b2WorldImpl* I = m_impl;
   if (!callback) return;
@@ -1264,6 +1278,11 @@ void b2Fixture::SetSensor(bool sensor) {
 void b2Fixture::SetFilterData(const b2Filter& filter) {
   m_filter = filter;
   Refilter();
+}
+void b2Contact::FlagForFiltering() {
+  b2WorldImpl* I = m_fixtureA->m_body->m_world->m_impl;
+  I->refilter.push_back(m_fixtureA->m_index);
+  m_fixtureA->m_body->m_world->m_newContacts = true;
 }
 void b2Fixture::Refilter() {
   // the device re-evaluates the filter for every pair on every broadphase pass, which is the

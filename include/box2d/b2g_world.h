@@ -293,6 +293,8 @@ class b2Contact {
   void SetFriction(float friction);
   float GetFriction() const { return m_friction; }
   void ResetFriction();
+  /// b2_contact.h:246-249: offer this contact to the contact filter again at the next step
+  void FlagForFiltering();
   void SetRestitution(float restitution);
   float GetRestitution() const { return m_restitution; }
   void ResetRestitution();
@@ -566,6 +568,8 @@ class b2World {
   int32 GetContactCount() const;
   int32 GetTreeHeight() const { return 0; }
   void SetGravity(const b2Vec2& gravity) { m_gravity = gravity; }
+  /// b2_world.cpp:1287-1306: subtract newOrigin from every position (large worlds, floating origin)
+  void ShiftOrigin(const b2Vec2& newOrigin);
   b2Vec2 GetGravity() const { return m_gravity; }
   bool IsLocked() const { return m_locked; }
   void SetAutoClearForces(bool flag) { m_clearForces = flag; }

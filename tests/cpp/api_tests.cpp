@@ -357,6 +357,12 @@ static void world_editing_session() {
   const float dt = 1.0f / 60.0f;
   for (int i = 0; i < 60; ++i) world.Step(dt, 8, 3);
   trace("settled", world, b, 7);
+  world.ShiftOrigin(b2Vec2(100.0f, -50.0f));                     // floating origin: there and back again
+  CHECK(fabsf(b[5]->GetPosition().x - (4.0f - 100.0f)) < 1e-4f && fabsf(ground->GetPosition().y - 50.0f) < 1e-4f);
+  world.Step(dt, 8, 3);
+  world.ShiftOrigin(b2Vec2(-100.0f, 50.0f));
+  for (int i = 0; i < 29; ++i) world.Step(dt, 8, 3);
+  trace("shifted", world, b, 7);
   b[4]->ApplyLinearImpulseToCenter(b2Vec2(0.4f, 0.0f), true);   // nudge the top box: it slides a little
   b[5]->ApplyAngularImpulse(0.05f, true);                        // and roll the ball
   for (int i = 0; i < 30; ++i) world.Step(dt, 8, 3);
