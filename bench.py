@@ -11,11 +11,14 @@ collective: weak scaling) and `value` is the sum over ranks divided by the max-o
   value  : device-resident throughput — bodies x K / sum of per-step CUDA-event times on the
            arena's stream; L2 is flushed (256 MiB memset) between timed steps.
   e2e    : the same metric through the C-ABI with HOST buffers: every step uploads the force
-           accumulators from pinned host memory, runs b2g_step and reads body transforms +
-           velocities back to pinned host memory, all inside the timed region.
-  roofline     : the dominant kernel class by CUDA-event time over a profiled pass, algorithmic
-                 bytes from SURVEY.md §8(d) (table in DESIGN.md) / measured launch time, against
-                 MEASURED_PEAKS.json's HBM copy bandwidth.
+           accumulators from pinned host memory (b2g_upload_forces), steps and reads every body's
+           transform + velocity back to pinned host memory (b2g_step_download), all inside the
+           timed region, one step at a time (no pipelining across steps).
+  roofline     : the dominant KERNEL (largest CUDA-event time per launch over a profiled pass; the
+                 library times every launch by kernel class), algorithmic bytes from SURVEY.md
+                 §8(d) (table in DESIGN.md) / measured launch time, against MEASURED_PEAKS.json's
+                 HBM copy bandwidth; `traffic` = DRAM bytes per launch of that kernel from the newest
+                 committed ncu --set full summary under profiles/.
   cpu_baseline : the reference's own CPU Step (oracle/_ref, compiled from /root/reference) on a
                  bounded sample of the same workload, rank 0 / N=1 only.
 `--impl reference` times that CPU implementation alone (one world per thread, n_gpus worlds).
