@@ -141,3 +141,30 @@ def test_queries_through_the_drop_in_api(require_ref):
     n_r, fx_r, fr_r, _ = ref.ray_cast_all(np.array([-20, 0.75, 20, 0.75], np.float32), 64)
     n_g, fx_g, fr_g, _ = gpu.ray_cast_all(np.array([-20, 0.75, 20, 0.75], np.float32), 64)
     assert n_r == n_g and n_r >= 12 and np.array_equal(fx_r, fx_g) and np.array_equal(fr_r, fr_g)
+
+
+def test_queries_respect_worlds_in_a_batched_arena(require_ref):
+    """Three copies of one scene in one arena: a query tagged with a world sees only that world's
+    fixtures (offset indices), an untagged query sees the three copies."""
+    from box2d_optimized_b200 import RefScene
+    ref = RefScene("pyramid", 10, 0)
+    ref.step(30)
+    nf = ref.fixture_count
+    A = arena_from_scene(ref, max_contacts=4096 * 3, num_worlds=3, copies=3)
+    A.find_new_contacts()
+    boxes = np.array([[-3, 0, 3, 4], [-100, -100, 100, 100]], np.float32)
+    rc, rf = ref.query_aabb(boxes, nf)
+    for w in range(3):
+        gc, gf = A.query_aabb(boxes, 3 * nf, world=np.full(len(boxes), w, np.int32))
+        assert np.array_equal(gc, rc)
+        for q in range(len(boxes)):
+            assert np.array_equal(gf[q, :gc[q]], rf[q, :rc[q]] + w * nf)
+    gc, gf = A.query_aabb(boxes, 3 * nf)
+    assert np.array_equal(gc, 3 * rc)
+    rays = random_rays(np.random.default_rng(3), scene_bounds(ref), 500)
+    rfix, rfrac, _, _ = ref.ray_cast_closest(rays)
+    gfix, gfrac, _ = A.ray_cast_closest(rays, world=np.full(len(rays), 2, np.int32))
+    hit = rfix >= 0
+    assert np.array_equal(hit, gfix >= 0) and np.array_equal(rfrac[hit], gfrac[hit])
+    assert np.array_equal(gfix[hit], rfix[hit] + 2 * nf) or (gfix[hit] >= 2 * nf).all()
+    A.close()
