@@ -117,6 +117,7 @@ struct b2gArena {
   unsigned int *conKeys, *conKeysSorted;
   int *conVals;
   int nbinsMax, bigMode, lastMaxIsland, lastNumBig;
+  float stepDt;  // dt of the step in flight (soft joint constraints)
   int lastOverflow, lastActive;  // serial-bucket constraints / solver rows of the previous step
   int islandsValid;   // island[] of the previous step may seed this step's union-find
   uint8_t* islandDirty;  // per island root: an edge was removed since the labels were computed

@@ -707,6 +707,7 @@ static JointArraysDev joint_views(b2gArena* A) {
   J.state = A->jState;
   J.upper = A->jUpper;
   J.work = A->jWork;
+  J.h = A->stepDt;
   return J;
 }
 static JointWalk joint_walk(b2gArena* A, int onlyBig) {
@@ -1222,6 +1223,7 @@ extern "C" int b2g_step_solve(b2gArena* A, const b2gStepParams* P, b2gStepStats*
   const long long launches0 = A->launchesAtStepStart;
   const int nb = A->nBodies;
   const float h = P->dt;
+  A->stepDt = h;
   const float inv_dt = h > 0.0f ? 1.0f / h : 0.0f;
   const int prof = A->profiling;
   int numActive = 0, numColours = 0, numOverflow = 0, rounds = 0;

@@ -13,6 +13,10 @@
 #define B2G_JOINT_LIMIT 1u
 #define B2G_JOINT_MOTOR 2u
 #define B2G_JOINT_COLLIDE_CONNECTED 4u
+// joint type in bits 8-11 of the flags word (include/b2cuda.h b2gJointArrays)
+#define B2G_JOINT_TYPE(flags) (((flags) >> 8) & 0xFu)
+#define B2G_JOINT_REVOLUTE 0u
+#define B2G_JOINT_DISTANCE 1u
 
 // per-step work area of one joint (plain struct in global memory; one thread touches it)
 struct JointWork {
@@ -22,6 +26,9 @@ struct JointWork {
   float mA, mB, iA, iB;
   float2 lcA, lcB;
   int ia, ib;  // body addresses for the accessors (tile slot, ~global, or global index)
+  // distance joint (b2_distance_joint.h:152-169): axis, its effective masses, soft-constraint terms
+  float2 u;
+  float dMass, softMass, gamma, bias, currentLength;
 };
 
 struct JointArraysDev {
@@ -32,7 +39,10 @@ struct JointArraysDev {
   float4* state;           // impulse.x, impulse.y, motorImpulse, lowerImpulse
   float* upper;            // upperImpulse
   JointWork* work;
+  float h;                 // this step's dt (soft constraints)
 };
+// distance joints reuse the arrays: params0 = length, minLength, maxLength, stiffness;
+// params1 = damping, bits(flags | type << 8), 0, 0; state = impulse, -, -, lowerImpulse; upper = upperImpulse
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float2 mat22_solve(float a11, float a12, float a21, float a22, float2 b) {
@@ -42,7 +52,7 @@ __device__ __forceinline__ float2 mat22_solve(float a11, float a12, float a21, f
 }
 
 template <class PosAccess, class VelAccess>
-__device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+__device__ __forceinline__ void revolute_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
                                            const VelAccess& vel, const float4* __restrict__ bodyMass,
                                            const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
   JointWork w;
@@ -108,7 +118,7 @@ __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int i
 }
 
 template <class VelAccess>
-__device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float dt,
+__device__ __forceinline__ void revolute_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float dt,
                                                      float inv_dt) {
   JointWork w = J.work[j];
   float4 p0 = J.params0[j], p1 = J.params1[j];
@@ -170,7 +180,7 @@ __device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, in
 
 // returns true when the joint's position error is within tolerance (jointOkay)
 template <class PosAccess>
-__device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
+__device__ __forceinline__ bool revolute_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
   JointWork w = J.work[j];
   float4 an = J.anchors[j], p0 = J.params0[j], p1 = J.params1[j];
   uint32_t flags = __float_as_uint(p1.y);
@@ -213,5 +223,199 @@ __device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, in
   if (movable(w.mA, w.iA)) pos.store(w.ia, make_float4(cA.x, cA.y, aA, pAq.w));
   if (movable(w.mB, w.iB)) pos.store(w.ib, make_float4(cB.x, cB.y, aB, pBq.w));
   return positionError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
+}
+
+// ---- distance joint: b2DistanceJoint::{InitVelocityConstraints, SolveVelocityConstraints,
+// SolvePositionConstraints} (src/dynamics/b2_distance_joint.cpp:76-303), rigid, soft (stiffness /
+// damping) and with min / max length limits ------------------------------------------------------
+template <class PosAccess, class VelAccess>
+__device__ __forceinline__ void distance_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+                                              const VelAccess& vel, const float4* __restrict__ bodyMass,
+                                              const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
+  JointWork w;
+  int2 bd = J.bodies[j];
+  float4 mAq = bodyMass[bd.x], mBq = bodyMass[bd.y];
+  float4 cAq = bodyCenter[bd.x], cBq = bodyCenter[bd.y];
+  w.ia = ia;
+  w.ib = ib;
+  w.mA = mAq.x; w.iA = mAq.y; w.mB = mBq.x; w.iB = mBq.y;
+  w.lcA = make_float2(cAq.x, cAq.y);
+  w.lcB = make_float2(cBq.x, cBq.y);
+  w.k11 = w.k12 = w.k22 = w.axialMass = w.angle = 0.0f;
+  float4 an = J.anchors[j], p0 = J.params0[j], p1 = J.params1[j];
+  const float length = p0.x, minLength = p0.y, maxLength = p0.z, stiffness = p0.w, damping = p1.x;
+  float4 pA = pos.load(ia), pB = pos.load(ib);
+  float4 vAq = vel.load(ia), vBq = vel.load(ib);
+  float2 cA = make_float2(pA.x, pA.y), cB = make_float2(pB.x, pB.y);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  Rot qA = rot_set(pA.z), qB = rot_set(pB.z);
+  w.rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+  w.rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  w.u = cB + w.rB - cA - w.rA;
+  float4 st = J.state[j];
+  float upper = J.upper[j];
+  w.currentLength = len2(w.u);
+  if (w.currentLength > B2G_LINEAR_SLOP) {
+    w.u = (1.0f / w.currentLength) * w.u;
+  } else {  // singular: the anchors coincide
+    w.u = make_float2(0.0f, 0.0f);
+    st.x = 0.0f;
+    st.w = 0.0f;
+    upper = 0.0f;
+  }
+  float crAu = cross2(w.rA, w.u), crBu = cross2(w.rB, w.u);
+  float invMass = w.mA + w.iA * crAu * crAu + w.mB + w.iB * crBu * crBu;
+  w.dMass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
+  if (stiffness > 0.0f && minLength < maxLength) {  // soft
+    float C = w.currentLength - length;
+    float h = J.h;
+    w.gamma = h * (damping + h * stiffness);
+    w.gamma = w.gamma != 0.0f ? 1.0f / w.gamma : 0.0f;
+    w.bias = C * h * stiffness * w.gamma;
+    invMass += w.gamma;
+    w.softMass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
+  } else {  // rigid
+    w.gamma = 0.0f;
+    w.bias = 0.0f;
+    w.softMass = w.dMass;
+  }
+  if (warmStarting) {
+    st.x *= dtRatio;
+    st.w *= dtRatio;
+    upper *= dtRatio;
+    float2 P = (st.x + st.w - upper) * w.u;
+    vA -= w.mA * P;
+    wA -= w.iA * cross2(w.rA, P);
+    vB += w.mB * P;
+    wB += w.iB * cross2(w.rB, P);
+  } else {
+    st.x = 0.0f;
+  }
+  J.state[j] = st;
+  J.upper[j] = upper;
+  J.work[j] = w;
+  if (movable(w.mA, w.iA)) vel.store(ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(w.mB, w.iB)) vel.store(ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class VelAccess>
+__device__ __forceinline__ void distance_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float inv_dt) {
+  JointWork w = J.work[j];
+  float4 p0 = J.params0[j];
+  const float minLength = p0.y, maxLength = p0.z, stiffness = p0.w;
+  float4 st = J.state[j];
+  float upper = J.upper[j];
+  float4 vAq = vel.load(w.ia), vBq = vel.load(w.ib);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  if (minLength < maxLength) {
+    if (stiffness > 0.0f) {
+      float2 vpA = vA + cross_sv(wA, w.rA), vpB = vB + cross_sv(wB, w.rB);
+      float Cdot = dot2(w.u, vpB - vpA);
+      float impulse = -w.softMass * (Cdot + w.bias + w.gamma * st.x);
+      st.x += impulse;
+      float2 P = impulse * w.u;
+      vA -= w.mA * P;
+      wA -= w.iA * cross2(w.rA, P);
+      vB += w.mB * P;
+      wB += w.iB * cross2(w.rB, P);
+    }
+    {  // lower limit
+      float C = w.currentLength - minLength;
+      float bias = maxf_(0.0f, C) * inv_dt;
+      float2 vpA = vA + cross_sv(wA, w.rA), vpB = vB + cross_sv(wB, w.rB);
+      float Cdot = dot2(w.u, vpB - vpA);
+      float impulse = -w.dMass * (Cdot + bias);
+      float oldImpulse = st.w;
+      st.w = maxf_(0.0f, st.w + impulse);
+      impulse = st.w - oldImpulse;
+      float2 P = impulse * w.u;
+      vA -= w.mA * P;
+      wA -= w.iA * cross2(w.rA, P);
+      vB += w.mB * P;
+      wB += w.iB * cross2(w.rB, P);
+    }
+    {  // upper limit
+      float C = maxLength - w.currentLength;
+      float bias = maxf_(0.0f, C) * inv_dt;
+      float2 vpA = vA + cross_sv(wA, w.rA), vpB = vB + cross_sv(wB, w.rB);
+      float Cdot = dot2(w.u, vpA - vpB);
+      float impulse = -w.dMass * (Cdot + bias);
+      float oldImpulse = upper;
+      upper = maxf_(0.0f, upper + impulse);
+      impulse = upper - oldImpulse;
+      float2 P = -impulse * w.u;
+      vA -= w.mA * P;
+      wA -= w.iA * cross2(w.rA, P);
+      vB += w.mB * P;
+      wB += w.iB * cross2(w.rB, P);
+    }
+  } else {  // equal limits: a rigid rod
+    float2 vpA = vA + cross_sv(wA, w.rA), vpB = vB + cross_sv(wB, w.rB);
+    float Cdot = dot2(w.u, vpB - vpA);
+    float impulse = -w.dMass * Cdot;
+    st.x += impulse;
+    float2 P = impulse * w.u;
+    vA -= w.mA * P;
+    wA -= w.iA * cross2(w.rA, P);
+    vB += w.mB * P;
+    wB += w.iB * cross2(w.rB, P);
+  }
+  J.state[j] = st;
+  J.upper[j] = upper;
+  if (movable(w.mA, w.iA)) vel.store(w.ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(w.mB, w.iB)) vel.store(w.ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class PosAccess>
+__device__ __forceinline__ bool distance_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
+  JointWork w = J.work[j];
+  float4 an = J.anchors[j], p0 = J.params0[j];
+  const float minLength = p0.y, maxLength = p0.z;
+  float4 pAq = pos.load(w.ia), pBq = pos.load(w.ib);
+  float2 cA = make_float2(pAq.x, pAq.y), cB = make_float2(pBq.x, pBq.y);
+  float aA = pAq.z, aB = pBq.z;
+  Rot qA = rot_set(aA), qB = rot_set(aB);
+  float2 rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+  float2 rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  float2 u = cB + rB - cA - rA;
+  float length = normalize2(u);
+  float C;
+  if (minLength == maxLength) C = length - minLength;
+  else if (length < minLength) C = length - minLength;
+  else if (maxLength < length) C = length - maxLength;
+  else return true;
+  float impulse = -w.dMass * C;
+  float2 P = impulse * u;
+  cA -= w.mA * P;
+  aA -= w.iA * cross2(rA, P);
+  cB += w.mB * P;
+  aB += w.iB * cross2(rB, P);
+  if (movable(w.mA, w.iA)) pos.store(w.ia, make_float4(cA.x, cA.y, aA, pAq.w));
+  if (movable(w.mB, w.iB)) pos.store(w.ib, make_float4(cB.x, cB.y, aB, pBq.w));
+  return absf_(C) < B2G_LINEAR_SLOP;
+}
+
+// ---- dispatch on the joint type -------------------------------------------------------------------
+template <class PosAccess, class VelAccess>
+__device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+                                           const VelAccess& vel, const float4* __restrict__ bodyMass,
+                                           const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
+  if (B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y)) == B2G_JOINT_DISTANCE)
+    distance_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else
+    revolute_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+}
+template <class VelAccess>
+__device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float dt,
+                                                     float inv_dt) {
+  if (B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y)) == B2G_JOINT_DISTANCE) distance_solve_velocity(J, j, vel, inv_dt);
+  else revolute_solve_velocity(J, j, vel, dt, inv_dt);
+}
+template <class PosAccess>
+__device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
+  if (B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y)) == B2G_JOINT_DISTANCE) return distance_solve_position(J, j, pos);
+  return revolute_solve_position(J, j, pos);
 }
 #endif

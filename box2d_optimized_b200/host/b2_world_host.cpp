@@ -330,19 +330,10 @@ void b2WorldImpl::flush() {
     std::vector<int32_t> jb((size_t)n * 2);
     std::vector<float> anchors((size_t)n * 4), params((size_t)n * 8, 0.0f), state((size_t)n * 5);
     for (int32 k = 0; k < n; ++k) {
-      b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(joints[k]);
+      b2Joint* j = joints[k];
       jb[(size_t)k * 2] = j->m_bodyA->m_index;
       jb[(size_t)k * 2 + 1] = j->m_bodyB->m_index;
-      anchors[(size_t)k * 4] = j->m_localAnchorA.x; anchors[(size_t)k * 4 + 1] = j->m_localAnchorA.y;
-      anchors[(size_t)k * 4 + 2] = j->m_localAnchorB.x; anchors[(size_t)k * 4 + 3] = j->m_localAnchorB.y;
-      float* p = &params[(size_t)k * 8];
-      p[0] = j->m_referenceAngle; p[1] = j->m_lowerAngle; p[2] = j->m_upperAngle; p[3] = j->m_maxMotorTorque;
-      p[4] = j->m_motorSpeed;
-      uint32_t fl = (j->m_enableLimit ? 1u : 0u) | (j->m_enableMotor ? 2u : 0u) | (j->m_collideConnected ? 4u : 0u);
-      memcpy(&p[5], &fl, 4);
-      float* st = &state[(size_t)k * 5];
-      st[0] = j->m_impulse.x; st[1] = j->m_impulse.y; st[2] = j->m_motorImpulse;
-      st[3] = j->m_lowerImpulse; st[4] = j->m_upperImpulse;
+      j->WriteDevice(&anchors[(size_t)k * 4], &params[(size_t)k * 8], &state[(size_t)k * 5]);
     }
     b2gJointArrays a;
     a.bodies = jb.data(); a.anchors = anchors.data(); a.params = params.data(); a.state = state.data();
@@ -371,14 +362,7 @@ void b2WorldImpl::pullJoints() {
   if (n == 0) return;
   std::vector<float> state((size_t)n * 5);
   b2gCheck(b2g_download_joints(arena, 0, n, state.data()), "b2g_download_joints");
-  for (int32 k = 0; k < n; ++k) {
-    b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(joints[k]);
-    const float* st = &state[(size_t)k * 5];
-    j->m_impulse.Set(st[0], st[1]);
-    j->m_motorImpulse = st[2];
-    j->m_lowerImpulse = st[3];
-    j->m_upperImpulse = st[4];
-  }
+  for (int32 k = 0; k < n; ++k) joints[k]->ReadDeviceState(&state[(size_t)k * 5]);
 }
 
 void b2WorldImpl::pullBodies() {
@@ -641,13 +625,15 @@ void b2World::DestroyBody(b2Body* b) {
 
 b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   if (IsLocked()) return nullptr;
-  if (def->type != e_revoluteJoint) {
-    fprintf(stderr, "[b2cuda] only revolute joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
+  if (def->type != e_revoluteJoint && def->type != e_distanceJoint) {
+    fprintf(stderr, "[b2cuda] only revolute and distance joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
             (int)def->type);
     return nullptr;
   }
   m_impl->pullJoints();
-  b2RevoluteJoint* j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
+  b2Joint* j = def->type == e_revoluteJoint
+                   ? static_cast<b2Joint*>(new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def)))
+                   : static_cast<b2Joint*>(new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def)));
   j->m_index = (int32)m_impl->joints.size();
   m_impl->joints.push_back(j);
   m_impl->jointsDirty = true;
@@ -1378,12 +1364,120 @@ b2RevoluteJoint::b2RevoluteJoint(const b2RevoluteJointDef* def) : b2Joint(def) {
   m_lowerImpulse = 0.0f;
   m_upperImpulse = 0.0f;
 }
-void b2RevoluteJoint::Touch() {
+void b2Joint::Touch(bool wake) {
   b2WorldImpl* I = m_bodyA->GetWorld()->GetImpl();
   I->pullJoints();
-  m_bodyA->SetAwake(true);
-  m_bodyB->SetAwake(true);
+  if (wake) {
+    m_bodyA->SetAwake(true);
+    m_bodyB->SetAwake(true);
+  }
   I->jointsDirty = true;
+}
+void b2RevoluteJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_localAnchorA.x; anchors[1] = m_localAnchorA.y; anchors[2] = m_localAnchorB.x; anchors[3] = m_localAnchorB.y;
+  p[0] = m_referenceAngle; p[1] = m_lowerAngle; p[2] = m_upperAngle; p[3] = m_maxMotorTorque;
+  p[4] = m_motorSpeed;
+  uint32_t fl = (m_enableLimit ? 1u : 0u) | (m_enableMotor ? 2u : 0u) | (m_collideConnected ? 4u : 0u);  // type 0
+  memcpy(&p[5], &fl, 4);
+  p[6] = p[7] = 0.0f;
+  st[0] = m_impulse.x; st[1] = m_impulse.y; st[2] = m_motorImpulse; st[3] = m_lowerImpulse; st[4] = m_upperImpulse;
+}
+void b2RevoluteJoint::ReadDeviceState(const float* st) {
+  m_impulse.Set(st[0], st[1]);
+  m_motorImpulse = st[2];
+  m_lowerImpulse = st[3];
+  m_upperImpulse = st[4];
+}
+
+// ---- b2DistanceJoint (b2_distance_joint.cpp:44-74, 305-366) -----------------------------------------
+void b2LinearStiffness(float& stiffness, float& damping, float frequencyHertz, float dampingRatio, const b2Body* bodyA,
+                       const b2Body* bodyB) {
+  const float massA = bodyA->GetMass(), massB = bodyB->GetMass();
+  float mass = massB;  // reduced mass of the pair, or the only finite one
+  if (massA > 0.0f && massB > 0.0f) mass = massA * massB / (massA + massB);
+  else if (massA > 0.0f) mass = massA;
+  const float omega = 2.0f * b2_pi * frequencyHertz;
+  stiffness = mass * omega * omega;
+  damping = 2.0f * mass * dampingRatio * omega;
+}
+void b2AngularStiffness(float& stiffness, float& damping, float frequencyHertz, float dampingRatio, const b2Body* bodyA,
+                        const b2Body* bodyB) {
+  const float IA = bodyA->GetInertia(), IB = bodyB->GetInertia();
+  float I = IB;
+  if (IA > 0.0f && IB > 0.0f) I = IA * IB / (IA + IB);
+  else if (IA > 0.0f) I = IA;
+  const float omega = 2.0f * b2_pi * frequencyHertz;
+  stiffness = I * omega * omega;
+  damping = 2.0f * I * dampingRatio * omega;
+}
+void b2DistanceJointDef::Initialize(b2Body* b1, b2Body* b2, const b2Vec2& anchor1, const b2Vec2& anchor2) {
+  bodyA = b1;
+  bodyB = b2;
+  localAnchorA = bodyA->GetLocalPoint(anchor1);
+  localAnchorB = bodyB->GetLocalPoint(anchor2);
+  length = b2Max((anchor2 - anchor1).Length(), b2_linearSlop);
+  minLength = length;
+  maxLength = length;
+}
+b2DistanceJoint::b2DistanceJoint(const b2DistanceJointDef* def) : b2Joint(def) {
+  m_localAnchorA = def->localAnchorA;
+  m_localAnchorB = def->localAnchorB;
+  m_length = b2Max(def->length, b2_linearSlop);
+  m_minLength = b2Max(def->minLength, b2_linearSlop);
+  m_maxLength = b2Max(def->maxLength, m_minLength);
+  m_stiffness = def->stiffness;
+  m_damping = def->damping;
+  m_impulse = m_lowerImpulse = m_upperImpulse = 0.0f;
+}
+void b2DistanceJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_localAnchorA.x; anchors[1] = m_localAnchorA.y; anchors[2] = m_localAnchorB.x; anchors[3] = m_localAnchorB.y;
+  p[0] = m_length; p[1] = m_minLength; p[2] = m_maxLength; p[3] = m_stiffness;
+  p[4] = m_damping;
+  uint32_t fl = (m_collideConnected ? 4u : 0u) | (1u << 8);  // type 1 = distance
+  memcpy(&p[5], &fl, 4);
+  p[6] = p[7] = 0.0f;
+  st[0] = m_impulse; st[1] = 0.0f; st[2] = 0.0f; st[3] = m_lowerImpulse; st[4] = m_upperImpulse;
+}
+void b2DistanceJoint::ReadDeviceState(const float* st) {
+  m_impulse = st[0];
+  m_lowerImpulse = st[3];
+  m_upperImpulse = st[4];
+}
+b2Vec2 b2DistanceJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2DistanceJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+b2Vec2 b2DistanceJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  b2Vec2 u = GetAnchorB() - GetAnchorA();
+  u.Normalize();
+  return inv_dt * (m_impulse + m_lowerImpulse - m_upperImpulse) * u;
+}
+float b2DistanceJoint::GetReactionTorque(float) const { return 0.0f; }
+float b2DistanceJoint::GetCurrentLength() const { return (GetAnchorB() - GetAnchorA()).Length(); }
+float b2DistanceJoint::SetLength(float length) {
+  Touch(false);  // the reference's setters do not wake the bodies
+  m_impulse = 0.0f;
+  m_length = b2Max(b2_linearSlop, length);
+  return m_length;
+}
+float b2DistanceJoint::SetMinLength(float minLength) {
+  Touch(false);  // the reference's setters do not wake the bodies
+  m_lowerImpulse = 0.0f;
+  m_minLength = b2Clamp(minLength, b2_linearSlop, m_maxLength);
+  return m_minLength;
+}
+float b2DistanceJoint::SetMaxLength(float maxLength) {
+  Touch(false);  // the reference's setters do not wake the bodies
+  m_upperImpulse = 0.0f;
+  m_maxLength = b2Max(maxLength, m_minLength);
+  return m_maxLength;
+}
+void b2DistanceJoint::SetStiffness(float stiffness) {
+  Touch(false);  // the reference's setters do not wake the bodies
+  m_stiffness = stiffness;
+}
+void b2DistanceJoint::SetDamping(float damping) {
+  Touch(false);  // the reference's setters do not wake the bodies
+  m_damping = damping;
 }
 b2Vec2 b2RevoluteJoint::GetReactionForce(float inv_dt) const {
   m_bodyA->GetWorld()->GetImpl()->pullJoints();

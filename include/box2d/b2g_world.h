@@ -408,6 +408,11 @@ class b2Joint {
   friend class b2Body;
   friend struct b2WorldImpl;
   b2Joint(const b2JointDef* def);
+  /// device record of this joint (include/b2cuda.h b2gJointArrays): anchors[4], params[8], state[5]
+  virtual void WriteDevice(float* anchors, float* params, float* state) const = 0;
+  /// accumulated impulses read back from the device
+  virtual void ReadDeviceState(const float* state) = 0;
+  void Touch(bool wake = true);  // pull the accumulators, (wake both bodies,) mark the joint table dirty
   b2JointType m_type;
   b2Joint* m_prev;
   b2Joint* m_next;
@@ -464,7 +469,69 @@ class b2RevoluteJoint : public b2Joint {
   mutable float m_motorImpulse;
   mutable float m_lowerImpulse;
   mutable float m_upperImpulse;
-  void Touch();  // pull the accumulators, wake both bodies, mark the joint table dirty
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+};
+
+/// b2_joint.h:76-84
+void b2LinearStiffness(float& stiffness, float& damping, float frequencyHertz, float dampingRatio, const b2Body* bodyA,
+                       const b2Body* bodyB);
+void b2AngularStiffness(float& stiffness, float& damping, float frequencyHertz, float dampingRatio, const b2Body* bodyA,
+                        const b2Body* bodyB);
+
+/// b2_distance_joint.h:30-170: rigid rod, spring (stiffness / damping) and min / max length limits
+struct b2DistanceJointDef : public b2JointDef {
+  b2DistanceJointDef() {
+    type = e_distanceJoint;
+    localAnchorA.Set(0.0f, 0.0f);
+    localAnchorB.Set(0.0f, 0.0f);
+    length = 1.0f;
+    minLength = 0.0f;
+    maxLength = FLT_MAX;
+    stiffness = 0.0f;
+    damping = 0.0f;
+  }
+  void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec2& anchorA, const b2Vec2& anchorB);
+  b2Vec2 localAnchorA;
+  b2Vec2 localAnchorB;
+  float length;
+  float minLength;
+  float maxLength;
+  float stiffness;
+  float damping;
+};
+
+class b2DistanceJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  /// along the current anchor-to-anchor direction (the reference uses the direction at the start of the last step)
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  const b2Vec2& GetLocalAnchorA() const { return m_localAnchorA; }
+  const b2Vec2& GetLocalAnchorB() const { return m_localAnchorB; }
+  float GetLength() const { return m_length; }
+  float SetLength(float length);
+  float GetMinLength() const { return m_minLength; }
+  float SetMinLength(float minLength);
+  float GetMaxLength() const { return m_maxLength; }
+  float SetMaxLength(float maxLength);
+  float GetCurrentLength() const;
+  void SetStiffness(float stiffness);
+  float GetStiffness() const { return m_stiffness; }
+  void SetDamping(float damping);
+  float GetDamping() const { return m_damping; }
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2DistanceJoint(const b2DistanceJointDef* def);
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+  b2Vec2 m_localAnchorA;
+  b2Vec2 m_localAnchorB;
+  float m_length, m_minLength, m_maxLength, m_stiffness, m_damping;
+  mutable float m_impulse, m_lowerImpulse, m_upperImpulse;
 };
 
 // ---- callbacks (b2_world_callbacks.h) ---------------------------------------------------------

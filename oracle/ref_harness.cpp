@@ -174,10 +174,17 @@ int b2ref_get_joint_state(void* h, int cap, float* out) {
   for (b2Joint* j = s->world->GetJointList(); j; j = j->GetNext()) js.push_back(j);
   int n = 0;
   for (auto it = js.rbegin(); it != js.rend() && n < cap; ++it) {
-    if ((*it)->GetType() != e_revoluteJoint) continue;
-    b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(*it);
-    float* o = out + 5 * n++;
-    o[0] = r->m_impulse.x; o[1] = r->m_impulse.y; o[2] = r->m_motorImpulse; o[3] = r->m_lowerImpulse; o[4] = r->m_upperImpulse;
+    float* o = out + 5 * n;
+    if ((*it)->GetType() == e_revoluteJoint) {
+      b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(*it);
+      o[0] = r->m_impulse.x; o[1] = r->m_impulse.y; o[2] = r->m_motorImpulse; o[3] = r->m_lowerImpulse; o[4] = r->m_upperImpulse;
+    } else if ((*it)->GetType() == e_distanceJoint) {  // b2_distance_joint.h:157-159
+      b2DistanceJoint* d = static_cast<b2DistanceJoint*>(*it);
+      o[0] = d->m_impulse; o[1] = 0.0f; o[2] = 0.0f; o[3] = d->m_lowerImpulse; o[4] = d->m_upperImpulse;
+    } else {
+      continue;
+    }
+    ++n;
   }
   return n;
 }

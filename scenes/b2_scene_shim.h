@@ -247,9 +247,11 @@ double SHIM(scene_time_ray_casts)(void* h, int n, const float* rays) {
 }
 
 int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->GetJointCount(); }
-// revolute joints in creation order: bodies[n][2], anchors[n][4] = localAnchorA.xy, localAnchorB.xy,
-// params[n][8] = referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
-// with flags 1 = enableLimit, 2 = enableMotor, 4 = collideConnected (include/b2cuda.h b2gJointArrays)
+// joints in creation order: bodies[n][2], anchors[n][4] = localAnchorA.xy, localAnchorB.xy, params[n][8]
+// in the include/b2cuda.h b2gJointArrays layout:
+//   revolute: referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
+//   distance: length, minLength, maxLength, stiffness, damping, bits(flags | 1 << 8), 0, 0
+// flags: 1 = enableLimit, 2 = enableMotor, 4 = collideConnected.  Other joint types are skipped.
 int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float* params) {
   Scene* s = static_cast<Scene*>(h);
   std::vector<b2Joint*> js;
@@ -257,16 +259,27 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
   int n = 0;
   for (auto it = js.rbegin(); it != js.rend() && n < cap; ++it) {  // the list is newest-first
     b2Joint* j = *it;
-    if (j->GetType() != e_revoluteJoint) continue;
-    b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(j);
-    bodies[2 * n] = s->bodyIndex[r->GetBodyA()];
-    bodies[2 * n + 1] = s->bodyIndex[r->GetBodyB()];
-    anchors[4 * n] = r->GetLocalAnchorA().x; anchors[4 * n + 1] = r->GetLocalAnchorA().y;
-    anchors[4 * n + 2] = r->GetLocalAnchorB().x; anchors[4 * n + 3] = r->GetLocalAnchorB().y;
     float* p = params + 8 * n;
-    p[0] = r->GetReferenceAngle(); p[1] = r->GetLowerLimit(); p[2] = r->GetUpperLimit();
-    p[3] = r->GetMaxMotorTorque(); p[4] = r->GetMotorSpeed();
-    uint32_t fl = (r->IsLimitEnabled() ? 1u : 0u) | (r->IsMotorEnabled() ? 2u : 0u) | (r->GetCollideConnected() ? 4u : 0u);
+    uint32_t fl = j->GetCollideConnected() ? 4u : 0u;
+    if (j->GetType() == e_revoluteJoint) {
+      b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(j);
+      anchors[4 * n] = r->GetLocalAnchorA().x; anchors[4 * n + 1] = r->GetLocalAnchorA().y;
+      anchors[4 * n + 2] = r->GetLocalAnchorB().x; anchors[4 * n + 3] = r->GetLocalAnchorB().y;
+      p[0] = r->GetReferenceAngle(); p[1] = r->GetLowerLimit(); p[2] = r->GetUpperLimit();
+      p[3] = r->GetMaxMotorTorque(); p[4] = r->GetMotorSpeed();
+      fl |= (r->IsLimitEnabled() ? 1u : 0u) | (r->IsMotorEnabled() ? 2u : 0u);
+    } else if (j->GetType() == e_distanceJoint) {
+      b2DistanceJoint* d = static_cast<b2DistanceJoint*>(j);
+      anchors[4 * n] = d->GetLocalAnchorA().x; anchors[4 * n + 1] = d->GetLocalAnchorA().y;
+      anchors[4 * n + 2] = d->GetLocalAnchorB().x; anchors[4 * n + 3] = d->GetLocalAnchorB().y;
+      p[0] = d->GetLength(); p[1] = d->GetMinLength(); p[2] = d->GetMaxLength();
+      p[3] = d->GetStiffness(); p[4] = d->GetDamping();
+      fl |= 1u << 8;
+    } else {
+      continue;
+    }
+    bodies[2 * n] = s->bodyIndex[j->GetBodyA()];
+    bodies[2 * n + 1] = s->bodyIndex[j->GetBodyB()];
     memcpy(&p[5], &fl, 4);
     p[6] = p[7] = 0.0f;
     ++n;

@@ -10,6 +10,7 @@
 //   mixed          circles + convex polygons dropped into a 3-box container, LCG seed (config 3)
 //   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
+//   springs        distance joints: rods, springs, limited ropes (b2_distance_joint.cpp)
 //   sensors        sensor zones / paddle / probes in a rain of shapes (b2TestOverlap path)
 //   hello          unit-test/hello_world.cpp:33-112
 //   falling_squares / falling_circles   benchmarks.h:57-135 (b1, b2)
@@ -261,6 +262,59 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
       jd.collideConnected = (name == "chain_collide");
       s->world->CreateJoint(&jd);
       prev = body;
+    }
+  } else if (name == "springs") {
+    // distance joints in their three regimes (b2_distance_joint.cpp:76-303): rigid rods (a hanging
+    // net of boxes), soft springs (stiffness / damping from b2LinearStiffness) and slack ropes with
+    // min / max length limits, all bumping into each other and a ground edge
+    int n = size > 0 ? size : 8;
+    b2BodyDef gd;
+    b2Body* ground = s->addBody(gd);
+    b2EdgeShape edge;
+    edge.SetTwoSided(b2Vec2(-40.0f, 0.0f), b2Vec2(40.0f, 0.0f));
+    s->addFixture(ground, edge, 0.0f);
+    b2PolygonShape box;
+    box.SetAsBox(0.3f, 0.3f);
+    b2CircleShape ball;
+    ball.m_radius = 0.35f;
+    b2Body* prevRow[64];
+    for (int i = 0; i < n && i < 64; ++i) {
+      // column i: ceiling anchor -> rigid rod -> box -> spring -> ball -> limited rope -> box
+      float x = -0.9f * (float)n + 1.8f * (float)i;
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(x, 4.3f);
+      b2Body* a = s->addBody(bd);
+      s->addFixture(a, box, 1.0f);
+      bd.position.Set(x + 0.4f, 2.3f);
+      b2Body* b = s->addBody(bd);
+      s->addFixture(b, ball, 0.8f);
+      bd.position.Set(x - 0.3f, 0.5f);
+      bd.angle = 0.3f * (float)i;
+      b2Body* c = s->addBody(bd);
+      s->addFixture(c, box, 1.5f);
+      bd.angle = 0.0f;
+      b2DistanceJointDef rod;
+      rod.Initialize(ground, a, b2Vec2(x, 6.3f), b2Vec2(x, 4.6f));
+      s->world->CreateJoint(&rod);
+      b2DistanceJointDef spring;
+      spring.Initialize(a, b, b2Vec2(x, 4.0f), b2Vec2(x + 0.4f, 2.3f));
+      b2LinearStiffness(spring.stiffness, spring.damping, 2.0f + 0.25f * (float)i, 0.1f + 0.05f * (float)i, a, b);
+      spring.minLength = 0.5f * spring.length;
+      spring.maxLength = 1.6f * spring.length;
+      s->world->CreateJoint(&spring);
+      b2DistanceJointDef rope;
+      rope.Initialize(b, c, b2Vec2(x + 0.4f, 2.3f), b2Vec2(x - 0.3f, 0.5f));
+      rope.minLength = 0.25f * rope.length;
+      rope.maxLength = 1.1f * rope.length;   // slack: only the limits act
+      s->world->CreateJoint(&rope);
+      if (i > 0) {  // rigid cross-links between neighbouring columns: one big jointed island
+        b2DistanceJointDef link;
+        link.Initialize(prevRow[i - 1], a, prevRow[i - 1]->GetPosition(), a->GetPosition());
+        link.collideConnected = true;
+        s->world->CreateJoint(&link);
+      }
+      prevRow[i] = a;
     }
   } else if (name == "sensors") {
     // sensor fixtures (static regions, a rotating paddle and probes riding on bodies) crossed by a

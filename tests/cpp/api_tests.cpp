@@ -467,6 +467,65 @@ static void user_contact_filter() {
          world.GetContactCount(), gap);
 }
 
+// distance joint: a rigid rod keeps its length, a spring oscillates at the frequency it was tuned to,
+// a rope with limits stops at its maximum length (b2_distance_joint.cpp)
+static void distance_joint_api() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2CircleShape ball;
+  ball.m_radius = 0.25f;
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  bd.position.Set(2.0f, 0.0f);   // rod: starts horizontal, swings like a pendulum
+  b2Body* bob = world.CreateBody(&bd);
+  bob->CreateFixture(&ball, 1.0f);
+  b2DistanceJointDef rod;
+  rod.Initialize(ground, bob, b2Vec2(0.0f, 0.0f), bob->GetPosition());
+  b2DistanceJoint* jr = static_cast<b2DistanceJoint*>(world.CreateJoint(&rod));
+  CHECK(jr != nullptr && fabsf(jr->GetLength() - 2.0f) < 1e-6f && jr->GetMinLength() == jr->GetMaxLength());
+  bd.position.Set(10.0f, -1.0f);  // spring: 2 Hz, lightly damped, released from rest at its rest length
+  b2Body* mass = world.CreateBody(&bd);
+  mass->CreateFixture(&ball, 1.0f);
+  b2DistanceJointDef sp;
+  sp.Initialize(ground, mass, b2Vec2(10.0f, 0.0f), mass->GetPosition());
+  b2LinearStiffness(sp.stiffness, sp.damping, 2.0f, 0.05f, ground, mass);
+  sp.minLength = 0.1f;
+  sp.maxLength = 5.0f;
+  b2DistanceJoint* js = static_cast<b2DistanceJoint*>(world.CreateJoint(&sp));
+  CHECK(js->GetStiffness() > 0.0f && js->GetDamping() > 0.0f);
+  bd.position.Set(20.0f, -1.0f);  // rope: slack between 0.5 and 1.5, the ball falls until it is taut
+  b2Body* hung = world.CreateBody(&bd);
+  hung->CreateFixture(&ball, 1.0f);
+  b2DistanceJointDef rp;
+  rp.Initialize(ground, hung, b2Vec2(20.0f, 0.0f), hung->GetPosition());
+  rp.minLength = 0.5f;
+  rp.maxLength = 1.5f;
+  b2DistanceJoint* jp = static_cast<b2DistanceJoint*>(world.CreateJoint(&rp));
+  int crossings = 0;
+  float prev = 0.0f, lowest = 0.0f, rodErr = 0.0f;
+  for (int i = 0; i < 240; ++i) {
+    world.Step(1.0f / 60.0f, 8, 3);
+    rodErr = b2Max(rodErr, fabsf(jr->GetCurrentLength() - 2.0f));
+    float v = mass->GetLinearVelocity().y;
+    if (i > 0 && ((prev < 0.0f && v >= 0.0f) || (prev > 0.0f && v <= 0.0f))) ++crossings;
+    prev = v;
+    lowest = b2Min(lowest, hung->GetPosition().y);
+  }
+  CHECK(rodErr < 0.02f);
+  CHECK(crossings >= 8 && crossings <= 17);         // 2 Hz: at most 16 velocity zero crossings in 4 s, fewer once damped out
+  CHECK(lowest < -1.45f && lowest > -1.56f);        // stopped by the upper limit
+  CHECK(fabsf(jp->GetCurrentLength() - 1.5f) < 0.02f);
+  b2Vec2 F = jp->GetReactionForce(60.0f);           // the taut rope carries the ball's weight
+  float m = hung->GetMass();
+  CHECK(fabsf(F.y - 10.0f * m) < 0.05f * 10.0f * m);
+  CHECK(jp->SetMaxLength(1.0f) == 1.0f && jp->SetLength(0.7f) == 0.7f && jp->SetMinLength(2.0f) == 1.0f);
+  hung->SetAwake(true);  // the setters do not wake anybody
+  for (int i = 0; i < 120; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(fabsf(jp->GetCurrentLength() - 1.0f) < 0.02f);
+  printf("distance: rod error %.5f, %d zero crossings, rope bottom %.4f, rope force %.4f\n", rodErr, crossings, lowest, F.y);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -475,6 +534,7 @@ int main() {
   locked_world_is_silent();
   body_list_order();
   revolute_joint_api();
+  distance_joint_api();
   contact_buffers_grow();
   world_editing_session();
   user_contact_filter();
