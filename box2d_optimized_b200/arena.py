@@ -162,6 +162,11 @@ class Arena:
         fixture[~np.take_along_axis(valid, order, 1)] = -1
         return counts, fixture, fraction, normal
 
+    def set_sequential_joint_order(self, joints):
+        joints = i32(joints)
+        capi.check(self.lib.b2g_set_sequential_joint_order(self.h, len(joints), capi.ip(joints)),
+                   "b2g_set_sequential_joint_order")
+
     def download_joints(self, count, first=0):
         """accumulated joint impulses [count, 5] = impulse.xy, motor, lower, upper"""
         state = np.zeros((count, 5), np.float32)

@@ -83,7 +83,7 @@ CUDA_SYMBOLS = [
     "b2g_download_body_state_async", "b2g_download_fixture_aabbs", "b2g_contact_count", "b2g_download_contacts",
     "b2g_upload_contact_overrides", "b2g_download_events", "b2g_synchronize", "b2g_stream", "b2g_set_profiling",
     "b2g_set_inv_dt0", "b2g_set_kernel_timing", "b2g_kernel_class_count", "b2g_kernel_class_name",
-    "b2g_get_kernel_timing", "b2g_device_views", "b2g_upload_contacts", "b2g_set_sequential_order", "b2g_host_alloc", "b2g_host_free", "b2g_download_new_pairs", "b2g_set_pair_vetoes", "b2g_download_veto_seen", "b2g_query_aabb", "b2g_ray_cast_closest", "b2g_ray_cast_all", "b2g_download_joints", "b2g_rotations", "b2g_compute_aabbs", "b2g_collide_pairs",
+    "b2g_get_kernel_timing", "b2g_device_views", "b2g_upload_contacts", "b2g_set_sequential_order", "b2g_set_sequential_joint_order", "b2g_host_alloc", "b2g_host_free", "b2g_download_new_pairs", "b2g_set_pair_vetoes", "b2g_download_veto_seen", "b2g_query_aabb", "b2g_ray_cast_closest", "b2g_ray_cast_all", "b2g_download_joints", "b2g_rotations", "b2g_compute_aabbs", "b2g_collide_pairs",
     "b2g_find_pairs", "b2g_solve_sequential",
 ]
 
@@ -139,6 +139,7 @@ def load_cuda():
         lib.b2g_device_views.argtypes = [C.c_void_p, C.POINTER(DeviceViews)]
         lib.b2g_upload_contacts.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ContactArrays)]
         lib.b2g_set_sequential_order.argtypes = [C.c_void_p, C.c_int32, i32p, i32p]
+        lib.b2g_set_sequential_joint_order.argtypes = [C.c_void_p, C.c_int32, i32p]
         lib.b2g_set_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
         lib.b2g_kernel_class_name.restype = C.c_char_p
         lib.b2g_kernel_class_name.argtypes = [C.c_int32]
@@ -238,6 +239,7 @@ def load_ref():
         lib.b2ref_get_inv_dt0.argtypes = [C.c_void_p]
         lib.b2ref_get_sleep_times.argtypes = [C.c_void_p, f32p]
         lib.b2ref_get_joint_state.argtypes = [C.c_void_p, C.c_int, f32p]
+        lib.b2ref_last_step_joint_order.argtypes = [C.c_void_p, u8p, C.c_int, i32p]
         lib.b2ref_step_recording_order.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
         lib.b2ref_solve.argtypes = [C.c_int, f32p, f32p, f32p, C.c_int, i32p, f32p, f32p, f32p, C.c_float, C.c_float,
                                     C.c_int, C.c_int, C.c_int, f32p, f32p, i32p]

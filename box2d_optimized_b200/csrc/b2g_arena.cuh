@@ -118,6 +118,8 @@ struct b2gArena {
   int *conVals;
   int nbinsMax, bigMode, lastMaxIsland, lastNumBig;
   float stepDt;  // dt of the step in flight (soft joint constraints)
+  int* jointOrder;   // [capJoints] explicit joint order of the sequential mode (one step)
+  int jointOrderCount, jointOrderActive;
   int lastOverflow, lastActive;  // serial-bucket constraints / solver rows of the previous step
   int islandsValid;   // island[] of the previous step may seed this step's union-find
   uint8_t* islandDirty;  // per island root: an edge was removed since the labels were computed

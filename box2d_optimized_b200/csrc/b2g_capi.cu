@@ -263,6 +263,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->jWork, nj));
   CK(dalloc(&A->stateStage, (size_t)nb * 2));
   CK(dalloc(&A->forceStage, (size_t)nb));
+  CK(dalloc(&A->jointOrder, nj));
   CK(dalloc(&A->ncKeys, nj));
   CK(dalloc(&A->ncKeysSorted, nj));
   CK(dalloc(&A->bodyNoCollide, nb));
@@ -359,7 +360,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->stateStage, A->forceStage, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->stateStage, A->forceStage, A->jointOrder, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->worldFirst, A->worldLast, A->bvhBox, A->bvhKey, A->bvhDone,
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -718,6 +719,8 @@ static JointWalk joint_walk(b2gArena* A, int onlyBig) {
   W.island = A->island;
   W.islandAwake = A->islandAwake;
   W.bodySlot = A->bodySlot;
+  W.order = nullptr;
+  W.norder = 0;
   return W;
 }
 
@@ -825,7 +828,12 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     // ---- contact solver --------------------------------------------------------------
     SolverPlanes& S = A->planes;
     const bool coloured = P->solver_mode != B2G_SOLVER_SEQUENTIAL;
-    const JointWalk JW = joint_walk(A, 0);
+    JointWalk JW = joint_walk(A, 0);
+    if (A->jointOrderActive && P->solver_mode == B2G_SOLVER_SEQUENTIAL) {  // b2g_set_sequential_joint_order, this step only
+      JW.order = A->jointOrder;
+      JW.norder = A->jointOrderCount;
+      A->jointOrderActive = 0;
+    }
     const JointArraysDev JV = joint_views(A);
     const float invH = h > 0.0f ? 1.0f / h : 0.0f;
     if (numActive > 0) {
@@ -1772,6 +1780,18 @@ extern "C" int b2g_download_veto_seen(b2gArena* A, int32_t count, uint8_t* seen)
   CK(cudaMemcpyAsync(seen, A->vetoSeen, (size_t)count, cudaMemcpyDeviceToHost, A->stream));
   CK(cudaMemsetAsync(A->vetoSeen, 0, (size_t)count, A->stream));
   CK(cudaStreamSynchronize(A->stream));
+  return B2G_OK;
+}
+
+extern "C" int b2g_set_sequential_joint_order(b2gArena* A, int32_t count, const int32_t* joints) {
+  if (!A || count < 0 || count > A->capJoints || (count > 0 && !joints)) return B2G_ERR_INVALID;
+  for (int i = 0; i < count; ++i)
+    if (joints[i] < 0 || joints[i] >= A->nJoints) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  if (count > 0) CK(cudaMemcpyAsync(A->jointOrder, joints, (size_t)count * 4, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaStreamSynchronize(A->stream));
+  A->jointOrderCount = count;
+  A->jointOrderActive = 1;
   return B2G_OK;
 }
 

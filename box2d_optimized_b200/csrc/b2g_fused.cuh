@@ -692,7 +692,12 @@ struct JointWalk {
   const int* island;
   const uint32_t* islandAwake;
   const int* bodySlot;
+  const int* order;  // explicit visiting order (b2g_set_sequential_joint_order), nullptr = descending index
+  int norder;
 };
+// k-th joint of the walk
+__device__ __forceinline__ int joint_walk_count(const JointWalk& W) { return W.order ? W.norder : W.nj; }
+__device__ __forceinline__ int joint_walk_at(const JointWalk& W, int k) { return W.order ? W.order[k] : W.nj - 1 - k; }
 __device__ __forceinline__ int joint_owner_body(const JointWalk& W, const JointArraysDev& J, int j) {
   int2 bd = J.bodies[j];
   uint32_t fa = W.bflags[bd.x], fb = W.bflags[bd.y];
@@ -706,7 +711,8 @@ __device__ __forceinline__ int joint_owner_body(const JointWalk& W, const JointA
 __device__ __forceinline__ void joints_init_global(const JointWalk& W, const JointArraysDev& J, float4* pos, float4* vel,
                                                    const float4* __restrict__ mass, const float4* __restrict__ center,
                                                    float dtRatio, int warm) {
-  for (int j = W.nj - 1; j >= 0; --j) {
+  for (int k = 0; k < joint_walk_count(W); ++k) {
+    const int j = joint_walk_at(W, k);
     if (joint_owner_body(W, J, j) < 0) continue;
     int2 bd = J.bodies[j];
     joint_init(J, j, bd.x, bd.y, GlobalBodies{pos}, GlobalBodies{vel}, mass, center, dtRatio, warm != 0);
@@ -714,12 +720,15 @@ __device__ __forceinline__ void joints_init_global(const JointWalk& W, const Joi
 }
 __device__ __forceinline__ void joints_velocity_global(const JointWalk& W, const JointArraysDev& J, float4* vel, float h,
                                                        float invH) {
-  for (int j = W.nj - 1; j >= 0; --j)
+  for (int k = 0; k < joint_walk_count(W); ++k) {
+    const int j = joint_walk_at(W, k);
     if (joint_owner_body(W, J, j) >= 0) joint_solve_velocity(J, j, GlobalBodies{vel}, h, invH);
+  }
 }
 __device__ __forceinline__ void joints_position_global(const JointWalk& W, const JointArraysDev& J, float4* pos,
                                                        uint32_t* islandPen, int penStride, int iter) {
-  for (int j = W.nj - 1; j >= 0; --j) {
+  for (int k = 0; k < joint_walk_count(W); ++k) {
+    const int j = joint_walk_at(W, k);
     int s = joint_owner_body(W, J, j);
     if (s < 0) continue;
     int root = W.island[s];

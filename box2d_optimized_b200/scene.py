@@ -196,6 +196,14 @@ class RefScene(_Scene):
         n = self.lib.b2ref_get_joint_state(self.h, n, capi.fp(out))
         return out[:n]
 
+    def last_step_joint_order(self, awake_before):
+        """joint indices in the order the last Step's island DFS added them (oracle/ref_harness.cpp)"""
+        n = self.lib.b2ref_scene_joint_count(self.h)
+        out = np.zeros(max(n, 1), np.int32)
+        flags = np.ascontiguousarray(awake_before, np.uint8)
+        k = self.lib.b2ref_last_step_joint_order(self.h, flags.ctypes.data_as(capi.u8p), n, capi.ip(out))
+        return out[:k]
+
     def sleep_times(self):
         out = np.zeros(self.body_count, np.float32)
         self.lib.b2ref_get_sleep_times(self.h, capi.fp(out))

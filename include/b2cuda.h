@@ -275,6 +275,10 @@ int b2g_upload_contacts(b2gArena* arena, int32_t count, const b2gContactArrays* 
  * order (e.g. the reference's island order as reported by b2ContactListener::PostSolve,
  * b2_island.cpp:621-647), every other constraint after them by pair key. */
 int b2g_set_sequential_order(b2gArena* arena, int32_t count, const int32_t* fixture_a, const int32_t* fixture_b);
+/* The same for joints: the order in which B2G_SOLVER_SEQUENTIAL visits the joints in the NEXT step
+ * only (the reference's island DFS order, b2_world.cpp:622-647); joints not listed are skipped.
+ * Without it joints are visited in descending index order. */
+int b2g_set_sequential_joint_order(b2gArena* arena, int32_t count, const int32_t* joints);
 
 /* b2ContactListener::BeginContact / EndContact (b2_contact.cpp:197-204,
  * b2_contact_manager.cpp:48-51) recorded by the last step when record_events was set:

@@ -189,6 +189,79 @@ int b2ref_get_joint_state(void* h, int cap, float* out) {
   return n;
 }
 
+// The order in which the LAST b2World::Step added joints to its islands (island.Add(joint),
+// b2_world.cpp:622-647): joints have no PostSolve, so the traversal of b2World::Solve (:522-659) is
+// walked again here on the reference's own body list, per-body contact arrays and joint edge lists.
+// Touching / enabled flags are those of that step's Collide (nothing after it changes them); the
+// awake state the step STARTED from is passed in, OR-ed with the present one (bodies woken by that
+// Collide).  Contacts destroyed at the end of the step are gone, new ones are not touching yet.
+// out = creation-order joint indices (the order of scene_get_joints).  Returns the count.
+int b2ref_last_step_joint_order(void* h, const unsigned char* awakeBefore, int cap, int* out) {
+  Scene* s = static_cast<Scene*>(h);
+  b2World* w = s->world;
+  std::vector<b2Joint*> js;
+  for (b2Joint* j = w->GetJointList(); j; j = j->GetNext()) js.push_back(j);
+  std::unordered_map<const b2Joint*, int> jointIndex;
+  {
+    int n = 0;
+    for (auto it = js.rbegin(); it != js.rend(); ++it)
+      if ((*it)->GetType() == e_revoluteJoint || (*it)->GetType() == e_distanceJoint) jointIndex[*it] = n++;
+  }
+  std::unordered_map<const b2Body*, bool> bodySeen;
+  std::unordered_map<const b2Contact*, bool> contactSeen;
+  std::unordered_map<const b2Joint*, bool> jointSeen;
+  std::vector<b2Body*> stack;
+  int n = 0;
+  for (b2Body* seed = w->m_bodyListHead; seed; seed = seed->m_next) {
+    if (bodySeen[seed]) continue;
+    if (!seed->IsEnabled()) continue;
+    bool awake = seed->IsAwake() || (awakeBefore && awakeBefore[s->bodyIndex[seed]]);
+    if (!awake) continue;
+    if (seed->GetType() == b2_staticBody) break;
+    if (seed->GetContactCount() == 0 && seed->GetJointList() == nullptr) {
+      bodySeen[seed] = true;
+      continue;
+    }
+    std::vector<b2Body*> islandBodies;
+    stack.clear();
+    stack.push_back(seed);
+    bodySeen[seed] = true;
+    while (!stack.empty()) {
+      b2Body* b = stack.back();
+      stack.pop_back();
+      islandBodies.push_back(b);
+      if (b->GetType() == b2_staticBody) continue;
+      for (int32 i = 0; i < b->GetContactCount(); ++i) {
+        b2Contact* c = b->GetContact(i);
+        if (contactSeen[c]) continue;
+        if (!c->IsEnabled() || !c->IsTouching()) continue;
+        if (c->GetFixtureA()->IsSensor() || c->GetFixtureB()->IsSensor()) continue;
+        contactSeen[c] = true;
+        b2Body* bA = c->GetFixtureA()->GetBody();
+        b2Body* bB = c->GetFixtureB()->GetBody();
+        b2Body* other = bA == b ? bB : bA;
+        if (bodySeen[other]) continue;
+        stack.push_back(other);
+        bodySeen[other] = true;
+      }
+      for (b2JointEdge* je = b->GetJointList(); je; je = je->next) {
+        if (jointSeen[je->joint]) continue;
+        b2Body* other = je->other;
+        if (!other->IsEnabled()) continue;
+        jointSeen[je->joint] = true;
+        auto it = jointIndex.find(je->joint);
+        if (it != jointIndex.end() && n < cap) out[n++] = it->second;
+        if (bodySeen[other]) continue;
+        stack.push_back(other);
+        bodySeen[other] = true;
+      }
+    }
+    for (b2Body* b : islandBodies)
+      if (b->GetType() == b2_staticBody) bodySeen[b] = false;  // static bodies take part in other islands too
+  }
+  return n;
+}
+
 // one b2World::Step with a PostSolve tap: the island solver's visiting order (SURVEY Appendix C:
 // PostSolve order IS the solver order).  Returns the number of solved contacts.
 namespace {
