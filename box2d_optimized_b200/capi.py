@@ -239,7 +239,7 @@ def load_ref():
         lib.b2ref_get_inv_dt0.argtypes = [C.c_void_p]
         lib.b2ref_get_sleep_times.argtypes = [C.c_void_p, f32p]
         lib.b2ref_get_joint_state.argtypes = [C.c_void_p, C.c_int, f32p]
-        lib.b2ref_last_step_joint_order.argtypes = [C.c_void_p, u8p, C.c_int, i32p]
+        lib.b2ref_next_step_joint_order.argtypes = [C.c_void_p, C.c_int, i32p]
         lib.b2ref_step_recording_order.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
         lib.b2ref_solve.argtypes = [C.c_int, f32p, f32p, f32p, C.c_int, i32p, f32p, f32p, f32p, C.c_float, C.c_float,
                                     C.c_int, C.c_int, C.c_int, f32p, f32p, i32p]

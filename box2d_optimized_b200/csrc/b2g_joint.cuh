@@ -17,6 +17,7 @@
 #define B2G_JOINT_TYPE(flags) (((flags) >> 8) & 0xFu)
 #define B2G_JOINT_REVOLUTE 0u
 #define B2G_JOINT_DISTANCE 1u
+#define B2G_JOINT_WELD 2u
 
 // per-step work area of one joint (plain struct in global memory; one thread touches it)
 struct JointWork {
@@ -29,6 +30,8 @@ struct JointWork {
   // distance joint (b2_distance_joint.h:152-169): axis, its effective masses, soft-constraint terms
   float2 u;
   float dMass, softMass, gamma, bias, currentLength;
+  // weld joint (b2_weld_joint.h:112-126): 3x3 effective mass, columns ex, ey, ez
+  float3 wex, wey, wez;
 };
 
 struct JointArraysDev {
@@ -41,6 +44,8 @@ struct JointArraysDev {
   JointWork* work;
   float h;                 // this step's dt (soft constraints)
 };
+// weld joints: params0 = referenceAngle, stiffness, damping, 0; params1 = 0, bits(flags | 2 << 8), 0, 0;
+// state = impulse.x, impulse.y, impulse.z, -
 // distance joints reuse the arrays: params0 = length, minLength, maxLength, stiffness;
 // params1 = damping, bits(flags | type << 8), 0, 0; state = impulse, -, -, lowerImpulse; upper = upperImpulse
 
@@ -397,25 +402,250 @@ __device__ __forceinline__ bool distance_solve_position(const JointArraysDev& J,
   return absf_(C) < B2G_LINEAR_SLOP;
 }
 
+// ---- weld joint: b2WeldJoint::{InitVelocityConstraints, SolveVelocityConstraints,
+// SolvePositionConstraints} (src/dynamics/b2_weld_joint.cpp:62-305) with the b2Mat33 helpers it uses
+// (src/common/b2_math.cpp:29-98) ------------------------------------------------------------------
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+  return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+struct Mat33 {
+  float3 ex, ey, ez;
+};
+__device__ __forceinline__ Mat33 weld_K(float mA, float mB, float iA, float iB, float2 rA, float2 rB) {
+  Mat33 K;
+  K.ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+  K.ey.x = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+  K.ez.x = -rA.y * iA - rB.y * iB;
+  K.ex.y = K.ey.x;
+  K.ey.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+  K.ez.y = rA.x * iA + rB.x * iB;
+  K.ex.z = K.ez.x;
+  K.ey.z = K.ez.y;
+  K.ez.z = iA + iB;
+  return K;
+}
+__device__ __forceinline__ Mat33 mat33_inverse22(const Mat33& K) {
+  float a = K.ex.x, b = K.ey.x, c = K.ex.y, d = K.ey.y;
+  float det = a * d - b * c;
+  if (det != 0.0f) det = 1.0f / det;
+  Mat33 M;
+  M.ex = make_float3(det * d, -det * c, 0.0f);
+  M.ey = make_float3(-det * b, det * a, 0.0f);
+  M.ez = make_float3(0.0f, 0.0f, 0.0f);
+  return M;
+}
+__device__ __forceinline__ Mat33 mat33_sym_inverse33(const Mat33& K) {
+  float det = dot3(K.ex, cross3(K.ey, K.ez));
+  if (det != 0.0f) det = 1.0f / det;
+  float a11 = K.ex.x, a12 = K.ey.x, a13 = K.ez.x, a22 = K.ey.y, a23 = K.ez.y, a33 = K.ez.z;
+  Mat33 M;
+  M.ex.x = det * (a22 * a33 - a23 * a23);
+  M.ex.y = det * (a13 * a23 - a12 * a33);
+  M.ex.z = det * (a12 * a23 - a13 * a22);
+  M.ey.x = M.ex.y;
+  M.ey.y = det * (a11 * a33 - a13 * a13);
+  M.ey.z = det * (a13 * a12 - a11 * a23);
+  M.ez.x = M.ex.z;
+  M.ez.y = M.ey.z;
+  M.ez.z = det * (a11 * a22 - a12 * a12);
+  return M;
+}
+__device__ __forceinline__ float3 mat33_solve33(const Mat33& K, float3 b) {
+  float det = dot3(K.ex, cross3(K.ey, K.ez));
+  if (det != 0.0f) det = 1.0f / det;
+  return make_float3(det * dot3(b, cross3(K.ey, K.ez)), det * dot3(K.ex, cross3(b, K.ez)), det * dot3(K.ex, cross3(K.ey, b)));
+}
+__device__ __forceinline__ float2 mat33_solve22(const Mat33& K, float2 b) {
+  return mat22_solve(K.ex.x, K.ey.x, K.ex.y, K.ey.y, b);
+}
+
+template <class PosAccess, class VelAccess>
+__device__ __forceinline__ void weld_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+                                          const VelAccess& vel, const float4* __restrict__ bodyMass,
+                                          const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
+  JointWork w;
+  int2 bd = J.bodies[j];
+  float4 mAq = bodyMass[bd.x], mBq = bodyMass[bd.y];
+  float4 cAq = bodyCenter[bd.x], cBq = bodyCenter[bd.y];
+  w.ia = ia;
+  w.ib = ib;
+  w.mA = mAq.x; w.iA = mAq.y; w.mB = mBq.x; w.iB = mBq.y;
+  w.lcA = make_float2(cAq.x, cAq.y);
+  w.lcB = make_float2(cBq.x, cBq.y);
+  w.k11 = w.k12 = w.k22 = w.axialMass = w.angle = 0.0f;
+  w.u = make_float2(0.0f, 0.0f);
+  w.dMass = w.softMass = w.currentLength = 0.0f;
+  float4 an = J.anchors[j], p0 = J.params0[j];
+  const float referenceAngle = p0.x, stiffness = p0.y, damping = p0.z;
+  float4 pA = pos.load(ia), pB = pos.load(ib);
+  float4 vAq = vel.load(ia), vBq = vel.load(ib);
+  float aA = pA.z, aB = pB.z;
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  Rot qA = rot_set(aA), qB = rot_set(aB);
+  w.rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+  w.rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  Mat33 K = weld_K(mA, mB, iA, iB, w.rA, w.rB);
+  Mat33 M;
+  if (stiffness > 0.0f) {
+    M = mat33_inverse22(K);
+    float invM = iA + iB;
+    float C = aB - aA - referenceAngle;
+    float h = J.h;
+    w.gamma = h * (damping + h * stiffness);
+    w.gamma = w.gamma != 0.0f ? 1.0f / w.gamma : 0.0f;
+    w.bias = C * h * stiffness * w.gamma;
+    invM += w.gamma;
+    M.ez.z = invM != 0.0f ? 1.0f / invM : 0.0f;
+  } else if (K.ez.z == 0.0f) {
+    M = mat33_inverse22(K);
+    w.gamma = 0.0f;
+    w.bias = 0.0f;
+  } else {
+    M = mat33_sym_inverse33(K);
+    w.gamma = 0.0f;
+    w.bias = 0.0f;
+  }
+  w.wex = M.ex;
+  w.wey = M.ey;
+  w.wez = M.ez;
+  float4 st = J.state[j];
+  if (warmStarting) {
+    st.x *= dtRatio;
+    st.y *= dtRatio;
+    st.z *= dtRatio;
+    float2 P = make_float2(st.x, st.y);
+    vA -= mA * P;
+    wA -= iA * (cross2(w.rA, P) + st.z);
+    vB += mB * P;
+    wB += iB * (cross2(w.rB, P) + st.z);
+  } else {
+    st.x = st.y = st.z = 0.0f;
+  }
+  J.state[j] = st;
+  J.work[j] = w;
+  if (movable(mA, iA)) vel.store(ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class VelAccess>
+__device__ __forceinline__ void weld_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel) {
+  JointWork w = J.work[j];
+  const float stiffness = J.params0[j].y;
+  float4 st = J.state[j];
+  float4 vAq = vel.load(w.ia), vBq = vel.load(w.ib);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  if (stiffness > 0.0f) {
+    float Cdot2 = wB - wA;
+    float impulse2 = -w.wez.z * (Cdot2 + w.bias + w.gamma * st.z);
+    st.z += impulse2;
+    wA -= iA * impulse2;
+    wB += iB * impulse2;
+    float2 Cdot1 = vB + cross_sv(wB, w.rB) - vA - cross_sv(wA, w.rA);
+    // b2Mul22(m_mass, Cdot1), negated
+    float2 impulse1 = -make_float2(w.wex.x * Cdot1.x + w.wey.x * Cdot1.y, w.wex.y * Cdot1.x + w.wey.y * Cdot1.y);
+    st.x += impulse1.x;
+    st.y += impulse1.y;
+    float2 P = impulse1;
+    vA -= mA * P;
+    wA -= iA * cross2(w.rA, P);
+    vB += mB * P;
+    wB += iB * cross2(w.rB, P);
+  } else {
+    float2 Cdot1 = vB + cross_sv(wB, w.rB) - vA - cross_sv(wA, w.rA);
+    float Cdot2 = wB - wA;
+    // b2Mul(m_mass, Cdot) = Cdot.x * ex + Cdot.y * ey + Cdot.z * ez, negated
+    float3 impulse = make_float3(-((Cdot1.x * w.wex.x + Cdot1.y * w.wey.x) + Cdot2 * w.wez.x),
+                                 -((Cdot1.x * w.wex.y + Cdot1.y * w.wey.y) + Cdot2 * w.wez.y),
+                                 -((Cdot1.x * w.wex.z + Cdot1.y * w.wey.z) + Cdot2 * w.wez.z));
+    st.x += impulse.x;
+    st.y += impulse.y;
+    st.z += impulse.z;
+    float2 P = make_float2(impulse.x, impulse.y);
+    vA -= mA * P;
+    wA -= iA * (cross2(w.rA, P) + impulse.z);
+    vB += mB * P;
+    wB += iB * (cross2(w.rB, P) + impulse.z);
+  }
+  J.state[j] = st;
+  if (movable(mA, iA)) vel.store(w.ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(w.ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class PosAccess>
+__device__ __forceinline__ bool weld_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
+  JointWork w = J.work[j];
+  float4 an = J.anchors[j], p0 = J.params0[j];
+  const float referenceAngle = p0.x, stiffness = p0.y;
+  float4 pAq = pos.load(w.ia), pBq = pos.load(w.ib);
+  float2 cA = make_float2(pAq.x, pAq.y), cB = make_float2(pBq.x, pBq.y);
+  float aA = pAq.z, aB = pBq.z;
+  Rot qA = rot_set(aA), qB = rot_set(aB);
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  float2 rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+  float2 rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  float positionError, angularError;
+  Mat33 K = weld_K(mA, mB, iA, iB, rA, rB);
+  if (stiffness > 0.0f) {
+    float2 C1 = cB + rB - cA - rA;
+    positionError = len2(C1);
+    angularError = 0.0f;
+    float2 P = -mat33_solve22(K, C1);
+    cA -= mA * P;
+    aA -= iA * cross2(rA, P);
+    cB += mB * P;
+    aB += iB * cross2(rB, P);
+  } else {
+    float2 C1 = cB + rB - cA - rA;
+    float C2 = aB - aA - referenceAngle;
+    positionError = len2(C1);
+    angularError = absf_(C2);
+    float3 impulse;
+    if (K.ez.z > 0.0f) {
+      float3 x = mat33_solve33(K, make_float3(C1.x, C1.y, C2));
+      impulse = make_float3(-x.x, -x.y, -x.z);
+    } else {
+      float2 i2 = -mat33_solve22(K, C1);
+      impulse = make_float3(i2.x, i2.y, 0.0f);
+    }
+    float2 P = make_float2(impulse.x, impulse.y);
+    cA -= mA * P;
+    aA -= iA * (cross2(rA, P) + impulse.z);
+    cB += mB * P;
+    aB += iB * (cross2(rB, P) + impulse.z);
+  }
+  if (movable(mA, iA)) pos.store(w.ia, make_float4(cA.x, cA.y, aA, pAq.w));
+  if (movable(mB, iB)) pos.store(w.ib, make_float4(cB.x, cB.y, aB, pBq.w));
+  return positionError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
+}
+
 // ---- dispatch on the joint type -------------------------------------------------------------------
 template <class PosAccess, class VelAccess>
 __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
                                            const VelAccess& vel, const float4* __restrict__ bodyMass,
                                            const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
-  if (B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y)) == B2G_JOINT_DISTANCE)
-    distance_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
-  else
-    revolute_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y));
+  if (type == B2G_JOINT_DISTANCE) distance_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else if (type == B2G_JOINT_WELD) weld_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else revolute_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
 }
 template <class VelAccess>
 __device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float dt,
                                                      float inv_dt) {
-  if (B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y)) == B2G_JOINT_DISTANCE) distance_solve_velocity(J, j, vel, inv_dt);
+  const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y));
+  if (type == B2G_JOINT_DISTANCE) distance_solve_velocity(J, j, vel, inv_dt);
+  else if (type == B2G_JOINT_WELD) weld_solve_velocity(J, j, vel);
   else revolute_solve_velocity(J, j, vel, dt, inv_dt);
 }
 template <class PosAccess>
 __device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
-  if (B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y)) == B2G_JOINT_DISTANCE) return distance_solve_position(J, j, pos);
+  const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y));
+  if (type == B2G_JOINT_DISTANCE) return distance_solve_position(J, j, pos);
+  if (type == B2G_JOINT_WELD) return weld_solve_position(J, j, pos);
   return revolute_solve_position(J, j, pos);
 }
 #endif

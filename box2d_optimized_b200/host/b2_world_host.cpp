@@ -625,15 +625,16 @@ void b2World::DestroyBody(b2Body* b) {
 
 b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   if (IsLocked()) return nullptr;
-  if (def->type != e_revoluteJoint && def->type != e_distanceJoint) {
-    fprintf(stderr, "[b2cuda] only revolute and distance joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
+  if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint) {
+    fprintf(stderr, "[b2cuda] only revolute, distance and weld joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
             (int)def->type);
     return nullptr;
   }
   m_impl->pullJoints();
-  b2Joint* j = def->type == e_revoluteJoint
-                   ? static_cast<b2Joint*>(new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def)))
-                   : static_cast<b2Joint*>(new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def)));
+  b2Joint* j;
+  if (def->type == e_revoluteJoint) j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
+  else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
+  else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
   j->m_index = (int32)m_impl->joints.size();
   m_impl->joints.push_back(j);
   m_impl->jointsDirty = true;
@@ -1387,6 +1388,55 @@ void b2RevoluteJoint::ReadDeviceState(const float* st) {
   m_motorImpulse = st[2];
   m_lowerImpulse = st[3];
   m_upperImpulse = st[4];
+}
+
+// ---- b2WeldJoint (b2_weld_joint.cpp:38-60, 307-330) ---------------------------------------------------
+void b2WeldJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor) {
+  bodyA = bA;
+  bodyB = bB;
+  localAnchorA = bodyA->GetLocalPoint(anchor);
+  localAnchorB = bodyB->GetLocalPoint(anchor);
+  referenceAngle = bodyB->GetAngle() - bodyA->GetAngle();
+}
+b2WeldJoint::b2WeldJoint(const b2WeldJointDef* def) : b2Joint(def) {
+  m_localAnchorA = def->localAnchorA;
+  m_localAnchorB = def->localAnchorB;
+  m_referenceAngle = def->referenceAngle;
+  m_stiffness = def->stiffness;
+  m_damping = def->damping;
+  m_impulse[0] = m_impulse[1] = m_impulse[2] = 0.0f;
+}
+void b2WeldJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_localAnchorA.x; anchors[1] = m_localAnchorA.y; anchors[2] = m_localAnchorB.x; anchors[3] = m_localAnchorB.y;
+  p[0] = m_referenceAngle; p[1] = m_stiffness; p[2] = m_damping; p[3] = 0.0f;
+  p[4] = 0.0f;
+  uint32_t fl = (m_collideConnected ? 4u : 0u) | (2u << 8);  // type 2 = weld
+  memcpy(&p[5], &fl, 4);
+  p[6] = p[7] = 0.0f;
+  st[0] = m_impulse[0]; st[1] = m_impulse[1]; st[2] = m_impulse[2]; st[3] = 0.0f; st[4] = 0.0f;
+}
+void b2WeldJoint::ReadDeviceState(const float* st) {
+  m_impulse[0] = st[0];
+  m_impulse[1] = st[1];
+  m_impulse[2] = st[2];
+}
+b2Vec2 b2WeldJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2WeldJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+b2Vec2 b2WeldJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * b2Vec2(m_impulse[0], m_impulse[1]);
+}
+float b2WeldJoint::GetReactionTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_impulse[2];
+}
+void b2WeldJoint::SetStiffness(float stiffness) {
+  Touch(false);
+  m_stiffness = stiffness;
+}
+void b2WeldJoint::SetDamping(float damping) {
+  Touch(false);
+  m_damping = damping;
 }
 
 // ---- b2DistanceJoint (b2_distance_joint.cpp:44-74, 305-366) -----------------------------------------

@@ -196,12 +196,12 @@ class RefScene(_Scene):
         n = self.lib.b2ref_get_joint_state(self.h, n, capi.fp(out))
         return out[:n]
 
-    def last_step_joint_order(self, awake_before):
-        """joint indices in the order the last Step's island DFS added them (oracle/ref_harness.cpp)"""
+    def next_step_joint_order(self):
+        """joint indices in the order the NEXT Step's island DFS will add them (oracle/ref_harness.cpp);
+        runs the head of that Step (pair refresh + Collide), which the Step then repeats unchanged"""
         n = self.lib.b2ref_scene_joint_count(self.h)
         out = np.zeros(max(n, 1), np.int32)
-        flags = np.ascontiguousarray(awake_before, np.uint8)
-        k = self.lib.b2ref_last_step_joint_order(self.h, flags.ctypes.data_as(capi.u8p), n, capi.ip(out))
+        k = self.lib.b2ref_next_step_joint_order(self.h, n, capi.ip(out))
         return out[:k]
 
     def sleep_times(self):

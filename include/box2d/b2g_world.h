@@ -479,6 +479,50 @@ void b2LinearStiffness(float& stiffness, float& damping, float frequencyHertz, f
 void b2AngularStiffness(float& stiffness, float& damping, float frequencyHertz, float dampingRatio, const b2Body* bodyA,
                         const b2Body* bodyB);
 
+/// b2_weld_joint.h:30-128: glues two bodies together (optionally with a rotational spring)
+struct b2WeldJointDef : public b2JointDef {
+  b2WeldJointDef() {
+    type = e_weldJoint;
+    localAnchorA.Set(0.0f, 0.0f);
+    localAnchorB.Set(0.0f, 0.0f);
+    referenceAngle = 0.0f;
+    stiffness = 0.0f;
+    damping = 0.0f;
+  }
+  void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec2& anchor);
+  b2Vec2 localAnchorA;
+  b2Vec2 localAnchorB;
+  float referenceAngle;
+  float stiffness;
+  float damping;
+};
+
+class b2WeldJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  const b2Vec2& GetLocalAnchorA() const { return m_localAnchorA; }
+  const b2Vec2& GetLocalAnchorB() const { return m_localAnchorB; }
+  float GetReferenceAngle() const { return m_referenceAngle; }
+  void SetStiffness(float stiffness);
+  float GetStiffness() const { return m_stiffness; }
+  void SetDamping(float damping);
+  float GetDamping() const { return m_damping; }
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2WeldJoint(const b2WeldJointDef* def);
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+  b2Vec2 m_localAnchorA;
+  b2Vec2 m_localAnchorB;
+  float m_referenceAngle, m_stiffness, m_damping;
+  mutable float m_impulse[3];
+};
+
 /// b2_distance_joint.h:30-170: rigid rod, spring (stiffness / damping) and min / max length limits
 struct b2DistanceJointDef : public b2JointDef {
   b2DistanceJointDef() {

@@ -181,6 +181,9 @@ int b2ref_get_joint_state(void* h, int cap, float* out) {
     } else if ((*it)->GetType() == e_distanceJoint) {  // b2_distance_joint.h:157-159
       b2DistanceJoint* d = static_cast<b2DistanceJoint*>(*it);
       o[0] = d->m_impulse; o[1] = 0.0f; o[2] = 0.0f; o[3] = d->m_lowerImpulse; o[4] = d->m_upperImpulse;
+    } else if ((*it)->GetType() == e_weldJoint) {  // b2_weld_joint.h:112
+      b2WeldJoint* wj = static_cast<b2WeldJoint*>(*it);
+      o[0] = wj->m_impulse.x; o[1] = wj->m_impulse.y; o[2] = wj->m_impulse.z; o[3] = 0.0f; o[4] = 0.0f;
     } else {
       continue;
     }
@@ -189,23 +192,28 @@ int b2ref_get_joint_state(void* h, int cap, float* out) {
   return n;
 }
 
-// The order in which the LAST b2World::Step added joints to its islands (island.Add(joint),
-// b2_world.cpp:622-647): joints have no PostSolve, so the traversal of b2World::Solve (:522-659) is
-// walked again here on the reference's own body list, per-body contact arrays and joint edge lists.
-// Touching / enabled flags are those of that step's Collide (nothing after it changes them); the
-// awake state the step STARTED from is passed in, OR-ed with the present one (bodies woken by that
-// Collide).  Contacts destroyed at the end of the step are gone, new ones are not touching yet.
+// The order in which the NEXT b2World::Step will add joints to its islands (island.Add(joint),
+// b2_world.cpp:622-647).  Joints have no PostSolve, so the head of Step is run here — the pending pair
+// refresh and b2ContactManager::Collide (b2_world.cpp:1114-1138), which Step will simply repeat with the
+// same outcome — and then the traversal of b2World::Solve (:522-659) is walked on the reference's own
+// body list, per-body contact arrays and joint edge lists, with exactly the flags Solve will see.
 // out = creation-order joint indices (the order of scene_get_joints).  Returns the count.
-int b2ref_last_step_joint_order(void* h, const unsigned char* awakeBefore, int cap, int* out) {
+int b2ref_next_step_joint_order(void* h, int cap, int* out) {
   Scene* s = static_cast<Scene*>(h);
   b2World* w = s->world;
+  if (w->m_newContacts) {
+    w->m_contactManager.FindNewContacts();
+    w->m_newContacts = false;
+  }
+  w->m_contactManager.Collide();
   std::vector<b2Joint*> js;
   for (b2Joint* j = w->GetJointList(); j; j = j->GetNext()) js.push_back(j);
   std::unordered_map<const b2Joint*, int> jointIndex;
   {
     int n = 0;
     for (auto it = js.rbegin(); it != js.rend(); ++it)
-      if ((*it)->GetType() == e_revoluteJoint || (*it)->GetType() == e_distanceJoint) jointIndex[*it] = n++;
+      if ((*it)->GetType() == e_revoluteJoint || (*it)->GetType() == e_distanceJoint || (*it)->GetType() == e_weldJoint)
+        jointIndex[*it] = n++;
   }
   std::unordered_map<const b2Body*, bool> bodySeen;
   std::unordered_map<const b2Contact*, bool> contactSeen;
@@ -215,8 +223,7 @@ int b2ref_last_step_joint_order(void* h, const unsigned char* awakeBefore, int c
   for (b2Body* seed = w->m_bodyListHead; seed; seed = seed->m_next) {
     if (bodySeen[seed]) continue;
     if (!seed->IsEnabled()) continue;
-    bool awake = seed->IsAwake() || (awakeBefore && awakeBefore[s->bodyIndex[seed]]);
-    if (!awake) continue;
+    if (!seed->IsAwake()) continue;
     if (seed->GetType() == b2_staticBody) break;
     if (seed->GetContactCount() == 0 && seed->GetJointList() == nullptr) {
       bodySeen[seed] = true;

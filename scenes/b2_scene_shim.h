@@ -251,6 +251,7 @@ int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->Get
 // in the include/b2cuda.h b2gJointArrays layout:
 //   revolute: referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
 //   distance: length, minLength, maxLength, stiffness, damping, bits(flags | 1 << 8), 0, 0
+//   weld:     referenceAngle, stiffness, damping, 0, 0, bits(flags | 2 << 8), 0, 0
 // flags: 1 = enableLimit, 2 = enableMotor, 4 = collideConnected.  Other joint types are skipped.
 int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float* params) {
   Scene* s = static_cast<Scene*>(h);
@@ -275,6 +276,12 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
       p[0] = d->GetLength(); p[1] = d->GetMinLength(); p[2] = d->GetMaxLength();
       p[3] = d->GetStiffness(); p[4] = d->GetDamping();
       fl |= 1u << 8;
+    } else if (j->GetType() == e_weldJoint) {
+      b2WeldJoint* wj = static_cast<b2WeldJoint*>(j);
+      anchors[4 * n] = wj->GetLocalAnchorA().x; anchors[4 * n + 1] = wj->GetLocalAnchorA().y;
+      anchors[4 * n + 2] = wj->GetLocalAnchorB().x; anchors[4 * n + 3] = wj->GetLocalAnchorB().y;
+      p[0] = wj->GetReferenceAngle(); p[1] = wj->GetStiffness(); p[2] = wj->GetDamping(); p[3] = 0.0f; p[4] = 0.0f;
+      fl |= 2u << 8;
     } else {
       continue;
     }

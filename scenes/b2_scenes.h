@@ -10,6 +10,7 @@
 //   mixed          circles + convex polygons dropped into a 3-box container, LCG seed (config 3)
 //   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
+//   welds          weld joints: cantilever beams, a welded compound (b2_weld_joint.cpp)
 //   springs        distance joints: rods, springs, limited ropes (b2_distance_joint.cpp)
 //   sensors        sensor zones / paddle / probes in a rain of shapes (b2TestOverlap path)
 //   hello          unit-test/hello_world.cpp:33-112
@@ -262,6 +263,51 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
       jd.collideConnected = (name == "chain_collide");
       s->world->CreateJoint(&jd);
       prev = body;
+    }
+  } else if (name == "welds") {
+    // weld joints (b2_weld_joint.cpp:62-305): cantilever beams of welded boxes sticking out of a wall
+    // (rigid and with a rotational spring), a welded compound tumbling onto them
+    int n = size > 0 ? size : 6;
+    b2BodyDef gd;
+    b2Body* ground = s->addBody(gd);
+    b2EdgeShape edge;
+    edge.SetTwoSided(b2Vec2(-40.0f, 0.0f), b2Vec2(40.0f, 0.0f));
+    s->addFixture(ground, edge, 0.0f);
+    b2PolygonShape plank;
+    plank.SetAsBox(0.5f, 0.125f);
+    for (int beam = 0; beam < 2; ++beam) {
+      b2Body* prev = ground;
+      float y = 3.0f + 3.0f * (float)beam;
+      for (int i = 0; i < n; ++i) {
+        b2BodyDef bd;
+        bd.type = b2_dynamicBody;
+        bd.position.Set(-10.0f + 0.5f + 1.0f * (float)i, y);
+        b2Body* body = s->addBody(bd);
+        s->addFixture(body, plank, 20.0f);
+        b2WeldJointDef jd;
+        jd.Initialize(prev, body, b2Vec2(-10.0f + 1.0f * (float)i, y));
+        if (beam == 1) b2AngularStiffness(jd.stiffness, jd.damping, 5.0f, 0.7f, prev, body);
+        s->world->CreateJoint(&jd);
+        prev = body;
+      }
+    }
+    {  // an L-shaped compound of three welded boxes dropped onto the lower beam
+      b2PolygonShape box;
+      box.SetAsBox(0.4f, 0.4f);
+      b2Body* parts[3];
+      const float px[3] = {-7.0f, -6.2f, -6.2f}, py[3] = {9.0f, 9.0f, 9.8f};
+      for (int k = 0; k < 3; ++k) {
+        b2BodyDef bd;
+        bd.type = b2_dynamicBody;
+        bd.position.Set(px[k], py[k]);
+        parts[k] = s->addBody(bd);
+        s->addFixture(parts[k], box, 2.0f);
+      }
+      b2WeldJointDef jd;
+      jd.Initialize(parts[0], parts[1], b2Vec2(-6.6f, 9.0f));
+      s->world->CreateJoint(&jd);
+      jd.Initialize(parts[1], parts[2], b2Vec2(-6.2f, 9.4f));
+      s->world->CreateJoint(&jd);
     }
   } else if (name == "springs") {
     // distance joints in their three regimes (b2_distance_joint.cpp:76-303): rigid rods (a hanging

@@ -19,7 +19,9 @@ for k in range(steps):
         A.close(); A = arena_from_scene(ref, max_contacts=max(4096, 16 * ref.body_count)); print("fresh arena at", k)
     before = mirror_reference_state(A, ref, params, inv)
     b0 = ref.bodies()
+    jo = ref.next_step_joint_order(); A.set_sequential_joint_order(jo)
     fa, fb = ref.step_recording_order(); A.set_sequential_order(fa, fb); A.step(P, stats)
+    if k < 3: print('joint order', jo.tolist())
     if stats.num_constraints != len(fa): print("step", k, "constraints", stats.num_constraints, "ref", len(fa))
     cg, cr = A.download_contacts(), ref.contacts()
     sg, sr = util.pair_set(cg["fix_a"], cg["fix_b"]), util.pair_set(cr["fix_a"], cr["fix_b"])

@@ -526,6 +526,42 @@ static void distance_joint_api() {
   printf("distance: rod error %.5f, %d zero crossings, rope bottom %.4f, rope force %.4f\n", rodErr, crossings, lowest, F.y);
 }
 
+// weld joint: a welded cantilever carries its own weight (reaction force and torque at the root)
+static void weld_joint_api() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2PolygonShape plank;
+  plank.SetAsBox(1.0f, 0.1f);
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  bd.position.Set(1.0f, 5.0f);
+  b2Body* beam = world.CreateBody(&bd);
+  beam->CreateFixture(&plank, 5.0f);   // mass 2 x 0.2 x 5 = 2
+  b2WeldJointDef jd;
+  jd.Initialize(ground, beam, b2Vec2(0.0f, 5.0f));
+  b2WeldJoint* j = static_cast<b2WeldJoint*>(world.CreateJoint(&jd));
+  CHECK(j != nullptr && j->GetReferenceAngle() == 0.0f && j->GetStiffness() == 0.0f);
+  for (int i = 0; i < 120; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(fabsf(beam->GetPosition().y - 5.0f) < 0.02f && fabsf(beam->GetAngle()) < 0.02f);
+  b2Vec2 F = j->GetReactionForce(60.0f);
+  float T = j->GetReactionTorque(60.0f);
+  CHECK(fabsf(F.y - 20.0f) < 0.5f);          // the weight of the beam
+  CHECK(fabsf(T - 20.0f) < 1.0f);            // weight x lever arm of 1 m
+  // a soft weld sags and swings
+  b2AngularStiffness(jd.stiffness, jd.damping, 1.0f, 0.2f, ground, beam);
+  j->SetStiffness(jd.stiffness);
+  j->SetDamping(jd.damping);
+  beam->SetAwake(true);
+  float lowest = 0.0f;
+  for (int i = 0; i < 120; ++i) {
+    world.Step(1.0f / 60.0f, 8, 3);
+    lowest = b2Min(lowest, beam->GetAngle());
+  }
+  CHECK(lowest < -0.1f);
+  printf("weld: F=(%.4f, %.4f) T=%.4f soft sag %.4f\n", F.x, F.y, T, lowest);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -535,6 +571,7 @@ int main() {
   body_list_order();
   revolute_joint_api();
   distance_joint_api();
+  weld_joint_api();
   contact_buffers_grow();
   world_editing_session();
   user_contact_filter();

@@ -70,7 +70,9 @@ def rel(a, b):
                                                    # index order, which is the reference's DFS order for these chains
                                                    ("chain", 14, 0, 300), ("chain_collide", 14, 0, 200),
                                                    # distance joints: rods, springs, limited ropes, cross-linked
-                                                   ("springs", 8, 0, 240)])
+                                                   ("springs", 8, 0, 240),
+                                                   # weld joints: rigid and soft cantilevers, a welded compound falling on them
+                                                   ("welds", 6, 0, 240)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
     from box2d_optimized_b200 import RefScene
     ref = RefScene(name, size, seed)
@@ -86,11 +88,10 @@ def test_every_step_from_the_reference_state(require_ref, name, size, seed, step
     solved_total = 0
     for k in range(steps):
         before = mirror_reference_state(A, ref, params, inv)
-        awake_before = ref.bodies()[:, 10] != 0
+        if nj:
+            A.set_sequential_joint_order(ref.next_step_joint_order())
         fa, fb = ref.step_recording_order()      # the reference advances one Step
         A.set_sequential_order(fa, fb)
-        if nj:
-            A.set_sequential_joint_order(ref.last_step_joint_order(awake_before))
         A.step(P, stats)
         solved_total += len(fa)
         assert stats.num_constraints == len(fa), f"step {k}: {stats.num_constraints} constraints vs {len(fa)} solved by the reference"
