@@ -18,6 +18,7 @@
 #define B2G_JOINT_REVOLUTE 0u
 #define B2G_JOINT_DISTANCE 1u
 #define B2G_JOINT_WELD 2u
+#define B2G_JOINT_PRISMATIC 3u
 
 // per-step work area of one joint (plain struct in global memory; one thread touches it)
 struct JointWork {
@@ -32,6 +33,10 @@ struct JointWork {
   float dMass, softMass, gamma, bias, currentLength;
   // weld joint (b2_weld_joint.h:112-126): 3x3 effective mass, columns ex, ey, ez
   float3 wex, wey, wez;
+  // prismatic joint (b2_prismatic_joint.h:182-190): world axis and its perpendicular, their lever arms
+  // (k11/k12/k22, axialMass and `angle` = translation are shared with the revolute fields)
+  float2 axis, perp;
+  float a1, a2, s1, s2;
 };
 
 struct JointArraysDev {
@@ -44,6 +49,9 @@ struct JointArraysDev {
   JointWork* work;
   float h;                 // this step's dt (soft constraints)
 };
+// prismatic joints: params0 = referenceAngle, lowerTranslation, upperTranslation, maxMotorForce;
+// params1 = motorSpeed, bits(flags | 3 << 8), localXAxisA.x, localXAxisA.y (unit length);
+// state = impulse.x, impulse.y, motorImpulse, lowerImpulse; upper = upperImpulse
 // weld joints: params0 = referenceAngle, stiffness, damping, 0; params1 = 0, bits(flags | 2 << 8), 0, 0;
 // state = impulse.x, impulse.y, impulse.z, -
 // distance joints reuse the arrays: params0 = length, minLength, maxLength, stiffness;
@@ -623,6 +631,245 @@ __device__ __forceinline__ bool weld_solve_position(const JointArraysDev& J, int
   return positionError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
 }
 
+// ---- prismatic joint: b2PrismaticJoint::{InitVelocityConstraints, SolveVelocityConstraints,
+// SolvePositionConstraints} (src/dynamics/b2_prismatic_joint.cpp:114-451): motor, translation limits,
+// the 2-row perpendicular + angular block ----------------------------------------------------------
+template <class PosAccess, class VelAccess>
+__device__ __forceinline__ void prismatic_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+                                               const VelAccess& vel, const float4* __restrict__ bodyMass,
+                                               const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
+  JointWork w;
+  int2 bd = J.bodies[j];
+  float4 mAq = bodyMass[bd.x], mBq = bodyMass[bd.y];
+  float4 cAq = bodyCenter[bd.x], cBq = bodyCenter[bd.y];
+  w.ia = ia;
+  w.ib = ib;
+  w.mA = mAq.x; w.iA = mAq.y; w.mB = mBq.x; w.iB = mBq.y;
+  w.lcA = make_float2(cAq.x, cAq.y);
+  w.lcB = make_float2(cBq.x, cBq.y);
+  w.u = make_float2(0.0f, 0.0f);
+  w.dMass = w.softMass = w.gamma = w.bias = w.currentLength = 0.0f;
+  w.wex = w.wey = w.wez = make_float3(0.0f, 0.0f, 0.0f);
+  float4 an = J.anchors[j], p1 = J.params1[j];
+  const uint32_t flags = __float_as_uint(p1.y);
+  const float2 localX = make_float2(p1.z, p1.w);
+  const float2 localY = cross_sv(1.0f, localX);
+  float4 pA = pos.load(ia), pB = pos.load(ib);
+  float4 vAq = vel.load(ia), vBq = vel.load(ib);
+  float2 cA = make_float2(pA.x, pA.y), cB = make_float2(pB.x, pB.y);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  Rot qA = rot_set(pA.z), qB = rot_set(pB.z);
+  w.rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+  w.rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  float2 d = (cB - cA) + w.rB - w.rA;
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  {
+    w.axis = rot_mul(qA, localX);
+    w.a1 = cross2(d + w.rA, w.axis);
+    w.a2 = cross2(w.rB, w.axis);
+    w.axialMass = mA + mB + iA * w.a1 * w.a1 + iB * w.a2 * w.a2;
+    if (w.axialMass > 0.0f) w.axialMass = 1.0f / w.axialMass;
+  }
+  {
+    w.perp = rot_mul(qA, localY);
+    w.s1 = cross2(d + w.rA, w.perp);
+    w.s2 = cross2(w.rB, w.perp);
+    w.k11 = mA + mB + iA * w.s1 * w.s1 + iB * w.s2 * w.s2;
+    w.k12 = iA * w.s1 + iB * w.s2;
+    w.k22 = iA + iB;
+    if (w.k22 == 0.0f) w.k22 = 1.0f;  // bodies with fixed rotation
+  }
+  float4 st = J.state[j];
+  float upper = J.upper[j];
+  w.angle = 0.0f;  // translation
+  if (flags & B2G_JOINT_LIMIT) {
+    w.angle = dot2(w.axis, d);
+  } else {
+    st.w = 0.0f;
+    upper = 0.0f;
+  }
+  if (!(flags & B2G_JOINT_MOTOR)) st.z = 0.0f;
+  if (warmStarting) {
+    st.x *= dtRatio;
+    st.y *= dtRatio;
+    st.z *= dtRatio;
+    st.w *= dtRatio;
+    upper *= dtRatio;
+    float axialImpulse = st.z + st.w - upper;
+    float2 P = st.x * w.perp + axialImpulse * w.axis;
+    float LA = st.x * w.s1 + st.y + axialImpulse * w.a1;
+    float LB = st.x * w.s2 + st.y + axialImpulse * w.a2;
+    vA -= mA * P;
+    wA -= iA * LA;
+    vB += mB * P;
+    wB += iB * LB;
+  } else {
+    st = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    upper = 0.0f;
+  }
+  J.state[j] = st;
+  J.upper[j] = upper;
+  J.work[j] = w;
+  if (movable(mA, iA)) vel.store(ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class VelAccess>
+__device__ __forceinline__ void prismatic_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float dt,
+                                                         float inv_dt) {
+  JointWork w = J.work[j];
+  float4 p0 = J.params0[j], p1 = J.params1[j];
+  const uint32_t flags = __float_as_uint(p1.y);
+  const float lowerTranslation = p0.y, upperTranslation = p0.z, maxMotorForce = p0.w, motorSpeed = p1.x;
+  float4 st = J.state[j];
+  float upper = J.upper[j];
+  float4 vAq = vel.load(w.ia), vBq = vel.load(w.ib);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  if (flags & B2G_JOINT_MOTOR) {
+    float Cdot = dot2(w.axis, vB - vA) + w.a2 * wB - w.a1 * wA;
+    float impulse = w.axialMass * (motorSpeed - Cdot);
+    float oldImpulse = st.z;
+    float maxImpulse = dt * maxMotorForce;
+    st.z = clampf(st.z + impulse, -maxImpulse, maxImpulse);
+    impulse = st.z - oldImpulse;
+    float2 P = impulse * w.axis;
+    float LA = impulse * w.a1, LB = impulse * w.a2;
+    vA -= mA * P;
+    wA -= iA * LA;
+    vB += mB * P;
+    wB += iB * LB;
+  }
+  if (flags & B2G_JOINT_LIMIT) {
+    {  // lower
+      float C = w.angle - lowerTranslation;
+      float Cdot = dot2(w.axis, vB - vA) + w.a2 * wB - w.a1 * wA;
+      float impulse = -w.axialMass * (Cdot + maxf_(C, 0.0f) * inv_dt);
+      float oldImpulse = st.w;
+      st.w = maxf_(st.w + impulse, 0.0f);
+      impulse = st.w - oldImpulse;
+      float2 P = impulse * w.axis;
+      float LA = impulse * w.a1, LB = impulse * w.a2;
+      vA -= mA * P;
+      wA -= iA * LA;
+      vB += mB * P;
+      wB += iB * LB;
+    }
+    {  // upper (signs flipped so that C and the impulse stay positive)
+      float C = upperTranslation - w.angle;
+      float Cdot = dot2(w.axis, vA - vB) + w.a1 * wA - w.a2 * wB;
+      float impulse = -w.axialMass * (Cdot + maxf_(C, 0.0f) * inv_dt);
+      float oldImpulse = upper;
+      upper = maxf_(upper + impulse, 0.0f);
+      impulse = upper - oldImpulse;
+      float2 P = impulse * w.axis;
+      float LA = impulse * w.a1, LB = impulse * w.a2;
+      vA += mA * P;
+      wA += iA * LA;
+      vB -= mB * P;
+      wB -= iB * LB;
+    }
+  }
+  {  // the prismatic constraint in block form
+    float2 Cdot;
+    Cdot.x = dot2(w.perp, vB - vA) + w.s2 * wB - w.s1 * wA;
+    Cdot.y = wB - wA;
+    float2 df = mat22_solve(w.k11, w.k12, w.k12, w.k22, -Cdot);
+    st.x += df.x;
+    st.y += df.y;
+    float2 P = df.x * w.perp;
+    float LA = df.x * w.s1 + df.y;
+    float LB = df.x * w.s2 + df.y;
+    vA -= mA * P;
+    wA -= iA * LA;
+    vB += mB * P;
+    wB += iB * LB;
+  }
+  J.state[j] = st;
+  J.upper[j] = upper;
+  if (movable(mA, iA)) vel.store(w.ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(w.ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class PosAccess>
+__device__ __forceinline__ bool prismatic_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
+  JointWork w = J.work[j];
+  float4 an = J.anchors[j], p0 = J.params0[j], p1 = J.params1[j];
+  const uint32_t flags = __float_as_uint(p1.y);
+  const float referenceAngle = p0.x, lowerTranslation = p0.y, upperTranslation = p0.z;
+  const float2 localX = make_float2(p1.z, p1.w);
+  const float2 localY = cross_sv(1.0f, localX);
+  float4 pAq = pos.load(w.ia), pBq = pos.load(w.ib);
+  float2 cA = make_float2(pAq.x, pAq.y), cB = make_float2(pBq.x, pBq.y);
+  float aA = pAq.z, aB = pBq.z;
+  Rot qA = rot_set(aA), qB = rot_set(aB);
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  float2 rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+  float2 rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  float2 d = cB + rB - cA - rA;
+  float2 axis = rot_mul(qA, localX);
+  float a1 = cross2(d + rA, axis);
+  float a2 = cross2(rB, axis);
+  float2 perp = rot_mul(qA, localY);
+  float s1 = cross2(d + rA, perp);
+  float s2 = cross2(rB, perp);
+  float3 impulse;
+  float2 C1 = make_float2(dot2(perp, d), aB - aA - referenceAngle);
+  float linearError = absf_(C1.x);
+  float angularError = absf_(C1.y);
+  bool active = false;
+  float C2 = 0.0f;
+  if (flags & B2G_JOINT_LIMIT) {
+    float translation = dot2(axis, d);
+    if (absf_(upperTranslation - lowerTranslation) < 2.0f * B2G_LINEAR_SLOP) {
+      C2 = translation;
+      linearError = maxf_(linearError, absf_(translation));
+      active = true;
+    } else if (translation <= lowerTranslation) {
+      C2 = minf_(translation - lowerTranslation, 0.0f);
+      linearError = maxf_(linearError, lowerTranslation - translation);
+      active = true;
+    } else if (translation >= upperTranslation) {
+      C2 = maxf_(translation - upperTranslation, 0.0f);
+      linearError = maxf_(linearError, translation - upperTranslation);
+      active = true;
+    }
+  }
+  if (active) {
+    float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+    float k12 = iA * s1 + iB * s2;
+    float k13 = iA * s1 * a1 + iB * s2 * a2;
+    float k22 = iA + iB;
+    if (k22 == 0.0f) k22 = 1.0f;
+    float k23 = iA * a1 + iB * a2;
+    float k33 = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+    Mat33 K;
+    K.ex = make_float3(k11, k12, k13);
+    K.ey = make_float3(k12, k22, k23);
+    K.ez = make_float3(k13, k23, k33);
+    impulse = mat33_solve33(K, make_float3(-C1.x, -C1.y, -C2));
+  } else {
+    float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+    float k12 = iA * s1 + iB * s2;
+    float k22 = iA + iB;
+    if (k22 == 0.0f) k22 = 1.0f;
+    float2 impulse1 = mat22_solve(k11, k12, k12, k22, -C1);
+    impulse = make_float3(impulse1.x, impulse1.y, 0.0f);
+  }
+  float2 P = impulse.x * perp + impulse.z * axis;
+  float LA = impulse.x * s1 + impulse.y + impulse.z * a1;
+  float LB = impulse.x * s2 + impulse.y + impulse.z * a2;
+  cA -= mA * P;
+  aA -= iA * LA;
+  cB += mB * P;
+  aB += iB * LB;
+  if (movable(mA, iA)) pos.store(w.ia, make_float4(cA.x, cA.y, aA, pAq.w));
+  if (movable(mB, iB)) pos.store(w.ib, make_float4(cB.x, cB.y, aB, pBq.w));
+  return linearError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
+}
+
 // ---- dispatch on the joint type -------------------------------------------------------------------
 template <class PosAccess, class VelAccess>
 __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
@@ -631,6 +878,7 @@ __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int i
   const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y));
   if (type == B2G_JOINT_DISTANCE) distance_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_WELD) weld_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else if (type == B2G_JOINT_PRISMATIC) prismatic_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else revolute_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
 }
 template <class VelAccess>
@@ -639,6 +887,7 @@ __device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, in
   const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y));
   if (type == B2G_JOINT_DISTANCE) distance_solve_velocity(J, j, vel, inv_dt);
   else if (type == B2G_JOINT_WELD) weld_solve_velocity(J, j, vel);
+  else if (type == B2G_JOINT_PRISMATIC) prismatic_solve_velocity(J, j, vel, dt, inv_dt);
   else revolute_solve_velocity(J, j, vel, dt, inv_dt);
 }
 template <class PosAccess>
@@ -646,6 +895,7 @@ __device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, in
   const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(J.params1[j].y));
   if (type == B2G_JOINT_DISTANCE) return distance_solve_position(J, j, pos);
   if (type == B2G_JOINT_WELD) return weld_solve_position(J, j, pos);
+  if (type == B2G_JOINT_PRISMATIC) return prismatic_solve_position(J, j, pos);
   return revolute_solve_position(J, j, pos);
 }
 #endif

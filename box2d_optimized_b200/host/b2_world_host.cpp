@@ -625,8 +625,9 @@ void b2World::DestroyBody(b2Body* b) {
 
 b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   if (IsLocked()) return nullptr;
-  if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint) {
-    fprintf(stderr, "[b2cuda] only revolute, distance and weld joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
+  if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint &&
+      def->type != e_prismaticJoint) {
+    fprintf(stderr, "[b2cuda] only revolute, distance, weld and prismatic joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
             (int)def->type);
     return nullptr;
   }
@@ -634,6 +635,7 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   b2Joint* j;
   if (def->type == e_revoluteJoint) j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
   else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
+  else if (def->type == e_prismaticJoint) j = new b2PrismaticJoint(static_cast<const b2PrismaticJointDef*>(def));
   else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
   j->m_index = (int32)m_impl->joints.size();
   m_impl->joints.push_back(j);
@@ -1388,6 +1390,107 @@ void b2RevoluteJoint::ReadDeviceState(const float* st) {
   m_motorImpulse = st[2];
   m_lowerImpulse = st[3];
   m_upperImpulse = st[4];
+}
+
+// ---- b2PrismaticJoint (b2_prismatic_joint.cpp:77-112, 453-601) ----------------------------------------
+void b2PrismaticJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor, const b2Vec2& axis) {
+  bodyA = bA;
+  bodyB = bB;
+  localAnchorA = bodyA->GetLocalPoint(anchor);
+  localAnchorB = bodyB->GetLocalPoint(anchor);
+  localAxisA = bodyA->GetLocalVector(axis);
+  referenceAngle = bodyB->GetAngle() - bodyA->GetAngle();
+}
+b2PrismaticJoint::b2PrismaticJoint(const b2PrismaticJointDef* def) : b2Joint(def) {
+  m_localAnchorA = def->localAnchorA;
+  m_localAnchorB = def->localAnchorB;
+  m_localXAxisA = def->localAxisA;
+  m_localXAxisA.Normalize();
+  m_localYAxisA = b2Cross(1.0f, m_localXAxisA);
+  m_referenceAngle = def->referenceAngle;
+  m_impulse.SetZero();
+  m_motorImpulse = 0.0f;
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+  m_lowerTranslation = def->lowerTranslation;
+  m_upperTranslation = def->upperTranslation;
+  m_maxMotorForce = def->maxMotorForce;
+  m_motorSpeed = def->motorSpeed;
+  m_enableLimit = def->enableLimit;
+  m_enableMotor = def->enableMotor;
+}
+void b2PrismaticJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_localAnchorA.x; anchors[1] = m_localAnchorA.y; anchors[2] = m_localAnchorB.x; anchors[3] = m_localAnchorB.y;
+  p[0] = m_referenceAngle; p[1] = m_lowerTranslation; p[2] = m_upperTranslation; p[3] = m_maxMotorForce;
+  p[4] = m_motorSpeed;
+  uint32_t fl = (m_enableLimit ? 1u : 0u) | (m_enableMotor ? 2u : 0u) | (m_collideConnected ? 4u : 0u) | (3u << 8);  // type 3
+  memcpy(&p[5], &fl, 4);
+  p[6] = m_localXAxisA.x; p[7] = m_localXAxisA.y;
+  st[0] = m_impulse.x; st[1] = m_impulse.y; st[2] = m_motorImpulse; st[3] = m_lowerImpulse; st[4] = m_upperImpulse;
+}
+void b2PrismaticJoint::ReadDeviceState(const float* st) {
+  m_impulse.Set(st[0], st[1]);
+  m_motorImpulse = st[2];
+  m_lowerImpulse = st[3];
+  m_upperImpulse = st[4];
+}
+b2Vec2 b2PrismaticJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2PrismaticJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+b2Vec2 b2PrismaticJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  b2Vec2 axis = m_bodyA->GetWorldVector(m_localXAxisA), perp = m_bodyA->GetWorldVector(m_localYAxisA);
+  return inv_dt * (m_impulse.x * perp + (m_motorImpulse + m_lowerImpulse - m_upperImpulse) * axis);
+}
+float b2PrismaticJoint::GetReactionTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_impulse.y;
+}
+float b2PrismaticJoint::GetMotorForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_motorImpulse;
+}
+float b2PrismaticJoint::GetJointTranslation() const {
+  b2Vec2 d = m_bodyB->GetWorldPoint(m_localAnchorB) - m_bodyA->GetWorldPoint(m_localAnchorA);
+  return b2Dot(d, m_bodyA->GetWorldVector(m_localXAxisA));
+}
+float b2PrismaticJoint::GetJointSpeed() const {
+  b2Vec2 rA = b2Mul(m_bodyA->GetTransform().q, m_localAnchorA - m_bodyA->GetLocalCenter());
+  b2Vec2 rB = b2Mul(m_bodyB->GetTransform().q, m_localAnchorB - m_bodyB->GetLocalCenter());
+  b2Vec2 d = (m_bodyB->GetWorldCenter() + rB) - (m_bodyA->GetWorldCenter() + rA);
+  b2Vec2 axis = b2Mul(m_bodyA->GetTransform().q, m_localXAxisA);
+  b2Vec2 vA = m_bodyA->GetLinearVelocity(), vB = m_bodyB->GetLinearVelocity();
+  float wA = m_bodyA->GetAngularVelocity(), wB = m_bodyB->GetAngularVelocity();
+  return b2Dot(d, b2Cross(wA, axis)) + b2Dot(axis, vB + b2Cross(wB, rB) - vA - b2Cross(wA, rA));
+}
+void b2PrismaticJoint::EnableLimit(bool flag) {
+  if (flag == m_enableLimit) return;
+  Touch();
+  m_enableLimit = flag;
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+}
+void b2PrismaticJoint::SetLimits(float lower, float upper) {
+  if (lower == m_lowerTranslation && upper == m_upperTranslation) return;
+  Touch();
+  m_lowerTranslation = lower;
+  m_upperTranslation = upper;
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+}
+void b2PrismaticJoint::EnableMotor(bool flag) {
+  if (flag == m_enableMotor) return;
+  Touch();
+  m_enableMotor = flag;
+}
+void b2PrismaticJoint::SetMotorSpeed(float speed) {
+  if (speed == m_motorSpeed) return;
+  Touch();
+  m_motorSpeed = speed;
+}
+void b2PrismaticJoint::SetMaxMotorForce(float force) {
+  if (force == m_maxMotorForce) return;
+  Touch();
+  m_maxMotorForce = force;
 }
 
 // ---- b2WeldJoint (b2_weld_joint.cpp:38-60, 307-330) ---------------------------------------------------

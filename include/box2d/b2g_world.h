@@ -479,6 +479,85 @@ void b2LinearStiffness(float& stiffness, float& damping, float frequencyHertz, f
 void b2AngularStiffness(float& stiffness, float& damping, float frequencyHertz, float dampingRatio, const b2Body* bodyA,
                         const b2Body* bodyB);
 
+/// b2_prismatic_joint.h:30-190: one translational degree of freedom along an axis fixed in bodyA, with an
+/// optional translation limit and linear motor
+struct b2PrismaticJointDef : public b2JointDef {
+  b2PrismaticJointDef() {
+    type = e_prismaticJoint;
+    localAnchorA.Set(0.0f, 0.0f);
+    localAnchorB.Set(0.0f, 0.0f);
+    localAxisA.Set(1.0f, 0.0f);
+    referenceAngle = 0.0f;
+    enableLimit = false;
+    lowerTranslation = 0.0f;
+    upperTranslation = 0.0f;
+    enableMotor = false;
+    maxMotorForce = 0.0f;
+    motorSpeed = 0.0f;
+  }
+  void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec2& anchor, const b2Vec2& axis);
+  b2Vec2 localAnchorA;
+  b2Vec2 localAnchorB;
+  b2Vec2 localAxisA;
+  float referenceAngle;
+  bool enableLimit;
+  float lowerTranslation;
+  float upperTranslation;
+  bool enableMotor;
+  float maxMotorForce;
+  float motorSpeed;
+};
+
+class b2PrismaticJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  // b2_prismatic_joint.cpp:463-471: the reference uses the axis / perpendicular of the last
+  // InitVelocityConstraints; here they are taken from bodyA's present transform
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  const b2Vec2& GetLocalAnchorA() const { return m_localAnchorA; }
+  const b2Vec2& GetLocalAnchorB() const { return m_localAnchorB; }
+  const b2Vec2& GetLocalAxisA() const { return m_localXAxisA; }
+  float GetReferenceAngle() const { return m_referenceAngle; }
+  float GetJointTranslation() const;
+  float GetJointSpeed() const;
+  bool IsLimitEnabled() const { return m_enableLimit; }
+  void EnableLimit(bool flag);
+  float GetLowerLimit() const { return m_lowerTranslation; }
+  float GetUpperLimit() const { return m_upperTranslation; }
+  void SetLimits(float lower, float upper);
+  bool IsMotorEnabled() const { return m_enableMotor; }
+  void EnableMotor(bool flag);
+  void SetMotorSpeed(float speed);
+  float GetMotorSpeed() const { return m_motorSpeed; }
+  void SetMaxMotorForce(float force);
+  float GetMaxMotorForce() const { return m_maxMotorForce; }
+  float GetMotorForce(float inv_dt) const;
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2PrismaticJoint(const b2PrismaticJointDef* def);
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+  b2Vec2 m_localAnchorA;
+  b2Vec2 m_localAnchorB;
+  b2Vec2 m_localXAxisA;
+  b2Vec2 m_localYAxisA;
+  float m_referenceAngle;
+  float m_lowerTranslation;
+  float m_upperTranslation;
+  float m_maxMotorForce;
+  float m_motorSpeed;
+  bool m_enableLimit;
+  bool m_enableMotor;
+  mutable b2Vec2 m_impulse;
+  mutable float m_motorImpulse;
+  mutable float m_lowerImpulse;
+  mutable float m_upperImpulse;
+};
+
 /// b2_weld_joint.h:30-128: glues two bodies together (optionally with a rotational spring)
 struct b2WeldJointDef : public b2JointDef {
   b2WeldJointDef() {

@@ -252,6 +252,8 @@ int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->Get
 //   revolute: referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
 //   distance: length, minLength, maxLength, stiffness, damping, bits(flags | 1 << 8), 0, 0
 //   weld:     referenceAngle, stiffness, damping, 0, 0, bits(flags | 2 << 8), 0, 0
+//   prismatic: referenceAngle, lowerTranslation, upperTranslation, maxMotorForce, motorSpeed,
+//             bits(flags | 3 << 8), localAxisA.x, localAxisA.y
 // flags: 1 = enableLimit, 2 = enableMotor, 4 = collideConnected.  Other joint types are skipped.
 int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float* params) {
   Scene* s = static_cast<Scene*>(h);
@@ -261,6 +263,7 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
   for (auto it = js.rbegin(); it != js.rend() && n < cap; ++it) {  // the list is newest-first
     b2Joint* j = *it;
     float* p = params + 8 * n;
+    float p6 = 0.0f, p7 = 0.0f;
     uint32_t fl = j->GetCollideConnected() ? 4u : 0u;
     if (j->GetType() == e_revoluteJoint) {
       b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(j);
@@ -282,13 +285,22 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
       anchors[4 * n + 2] = wj->GetLocalAnchorB().x; anchors[4 * n + 3] = wj->GetLocalAnchorB().y;
       p[0] = wj->GetReferenceAngle(); p[1] = wj->GetStiffness(); p[2] = wj->GetDamping(); p[3] = 0.0f; p[4] = 0.0f;
       fl |= 2u << 8;
+    } else if (j->GetType() == e_prismaticJoint) {
+      b2PrismaticJoint* pj = static_cast<b2PrismaticJoint*>(j);
+      anchors[4 * n] = pj->GetLocalAnchorA().x; anchors[4 * n + 1] = pj->GetLocalAnchorA().y;
+      anchors[4 * n + 2] = pj->GetLocalAnchorB().x; anchors[4 * n + 3] = pj->GetLocalAnchorB().y;
+      p[0] = pj->GetReferenceAngle(); p[1] = pj->GetLowerLimit(); p[2] = pj->GetUpperLimit();
+      p[3] = pj->GetMaxMotorForce(); p[4] = pj->GetMotorSpeed();
+      p6 = pj->GetLocalAxisA().x; p7 = pj->GetLocalAxisA().y;
+      fl |= (pj->IsLimitEnabled() ? 1u : 0u) | (pj->IsMotorEnabled() ? 2u : 0u) | (3u << 8);
     } else {
       continue;
     }
     bodies[2 * n] = s->bodyIndex[j->GetBodyA()];
     bodies[2 * n + 1] = s->bodyIndex[j->GetBodyB()];
     memcpy(&p[5], &fl, 4);
-    p[6] = p[7] = 0.0f;
+    p[6] = p6;
+    p[7] = p7;
     ++n;
   }
   return n;

@@ -11,6 +11,7 @@
 //   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
 //   welds          weld joints: cantilever beams, a welded compound (b2_weld_joint.cpp)
+//   sliders        prismatic joints: motorised pistons, limited rails, a free slider (b2_prismatic_joint.cpp)
 //   springs        distance joints: rods, springs, limited ropes (b2_distance_joint.cpp)
 //   sensors        sensor zones / paddle / probes in a rain of shapes (b2TestOverlap path)
 //   hello          unit-test/hello_world.cpp:33-112
@@ -307,6 +308,98 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
       jd.Initialize(parts[0], parts[1], b2Vec2(-6.6f, 9.0f));
       s->world->CreateJoint(&jd);
       jd.Initialize(parts[1], parts[2], b2Vec2(-6.2f, 9.4f));
+      s->world->CreateJoint(&jd);
+    }
+  } else if (name == "sliders") {
+    // prismatic joints (b2_prismatic_joint.cpp:114-451) in their regimes: a motorised piston pushing a
+    // pile of boxes along the ground against a limit, vertical lifts between a lower and an upper
+    // limit carrying loose boxes, tilted free rails (no motor, no limit) and a carriage chained to a
+    // carriage (dynamic-dynamic), all colliding with each other and a ground edge
+    int n = size > 0 ? size : 6;
+    b2BodyDef gd;
+    b2Body* ground = s->addBody(gd);
+    b2EdgeShape edge;
+    edge.SetTwoSided(b2Vec2(-60.0f, 0.0f), b2Vec2(60.0f, 0.0f));
+    s->addFixture(ground, edge, 0.0f);
+    b2PolygonShape box;
+    box.SetAsBox(0.4f, 0.4f);
+    b2PolygonShape plate;
+    plate.SetAsBox(1.0f, 0.2f);
+    b2CircleShape ball;
+    ball.m_radius = 0.3f;
+    {  // the piston: a tall block driven along +x by a motor, limit [0, 6]
+      b2PolygonShape ram;
+      ram.SetAsBox(0.3f, 1.0f);
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(-20.0f, 1.05f);
+      b2Body* body = s->addBody(bd);
+      s->addFixture(body, ram, 5.0f);
+      b2PrismaticJointDef jd;
+      jd.Initialize(ground, body, b2Vec2(-20.0f, 1.05f), b2Vec2(1.0f, 0.0f));
+      jd.enableMotor = true;
+      jd.motorSpeed = 2.0f;
+      jd.maxMotorForce = 400.0f;
+      jd.enableLimit = true;
+      jd.lowerTranslation = 0.0f;
+      jd.upperTranslation = 6.0f;
+      s->world->CreateJoint(&jd);
+      for (int i = 0; i < n; ++i) {
+        b2BodyDef cd;
+        cd.type = b2_dynamicBody;
+        cd.position.Set(-18.5f + 0.9f * (float)(i % 3), 0.45f + 0.85f * (float)(i / 3));
+        s->addFixture(s->addBody(cd), box, 1.0f);
+      }
+    }
+    for (int i = 0; i < n; ++i) {  // lifts: plate on a vertical rail, motor pushing up against gravity, limits
+      float x = -10.0f + 3.0f * (float)i;
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(x, 2.0f);
+      b2Body* lift = s->addBody(bd);
+      s->addFixture(lift, plate, 2.0f);
+      b2PrismaticJointDef jd;
+      jd.Initialize(ground, lift, b2Vec2(x, 2.0f), b2Vec2(0.0f, 1.0f));
+      jd.enableLimit = true;
+      jd.lowerTranslation = -1.0f;
+      jd.upperTranslation = 0.5f + 0.25f * (float)i;
+      jd.enableMotor = (i % 2) == 0;
+      jd.motorSpeed = 1.0f;
+      jd.maxMotorForce = 60.0f + 30.0f * (float)i;
+      s->world->CreateJoint(&jd);
+      b2BodyDef cd;
+      cd.type = b2_dynamicBody;
+      cd.position.Set(x - 0.3f, 2.65f);
+      s->addFixture(s->addBody(cd), box, 1.0f);
+      cd.position.Set(x + 0.45f, 2.6f);
+      s->addFixture(s->addBody(cd), ball, 1.0f);
+    }
+    for (int i = 0; i < n; ++i) {  // tilted free rails with a second carriage hanging off the first
+      float x = -10.0f + 3.0f * (float)i, y = 8.0f;
+      b2Vec2 axis(0.8f, i % 2 ? -0.6f : 0.6f);
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(x, y);
+      bd.angle = 0.1f * (float)i;
+      b2Body* first = s->addBody(bd);
+      s->addFixture(first, box, 1.0f);
+      b2PrismaticJointDef jd;
+      jd.Initialize(ground, first, b2Vec2(x, y), axis);
+      if (i % 3 == 0) {  // lower == upper: the locked-slider branch of the position solver
+        jd.enableLimit = true;
+        jd.lowerTranslation = jd.upperTranslation = 0.0f;
+      }
+      s->world->CreateJoint(&jd);
+      bd.position.Set(x + 0.2f, y - 1.2f);
+      bd.angle = 0.0f;
+      b2Body* second = s->addBody(bd);
+      s->addFixture(second, ball, 3.0f);
+      jd = b2PrismaticJointDef();
+      jd.Initialize(first, second, b2Vec2(x, y - 0.6f), b2Vec2(0.0f, 1.0f));
+      jd.enableLimit = true;
+      jd.lowerTranslation = -0.5f;
+      jd.upperTranslation = 0.3f;
+      jd.collideConnected = (i % 2) == 0;
       s->world->CreateJoint(&jd);
     }
   } else if (name == "springs") {

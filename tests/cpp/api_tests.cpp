@@ -562,6 +562,51 @@ static void weld_joint_api() {
   printf("weld: F=(%.4f, %.4f) T=%.4f soft sag %.4f\n", F.x, F.y, T, lowest);
 }
 
+// prismatic joint: a motorised lift stops at its upper limit carrying its own weight, then falls to the
+// lower limit when the motor is switched off; relative rotation stays locked
+static void prismatic_joint_api() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2PolygonShape plate;
+  plate.SetAsBox(1.0f, 0.25f);
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  bd.position.Set(0.5f, 3.0f);   // anchor off-centre: the rail must also carry a torque
+  b2Body* lift = world.CreateBody(&bd);
+  lift->CreateFixture(&plate, 2.0f);   // mass 2 x 0.5 x 2 = 2
+  b2PrismaticJointDef jd;
+  jd.Initialize(ground, lift, b2Vec2(0.0f, 3.0f), b2Vec2(0.0f, 2.0f));
+  jd.enableLimit = true;
+  jd.lowerTranslation = -1.0f;
+  jd.upperTranslation = 1.5f;
+  jd.enableMotor = true;
+  jd.motorSpeed = 1.0f;
+  jd.maxMotorForce = 100.0f;
+  b2PrismaticJoint* j = static_cast<b2PrismaticJoint*>(world.CreateJoint(&jd));
+  CHECK(j != nullptr && j->IsLimitEnabled() && j->IsMotorEnabled() && j->GetUpperLimit() == 1.5f);
+  CHECK(fabsf(j->GetLocalAxisA().y - 1.0f) < 1e-6f);   // the constructor normalises the axis
+  for (int i = 0; i < 60; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  float speed = j->GetJointSpeed();
+  CHECK(fabsf(j->GetJointTranslation() - 1.0f) < 0.05f && fabsf(speed - 1.0f) < 0.02f);
+  float motorForce = j->GetMotorForce(60.0f);
+  CHECK(fabsf(motorForce - 20.0f) < 0.5f);   // the motor carries the weight
+  for (int i = 0; i < 120; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(fabsf(j->GetJointTranslation() - 1.5f) < 0.02f);
+  CHECK(fabsf(lift->GetAngle()) < 0.01f && fabsf(lift->GetPosition().x - 0.5f) < 0.01f);
+  float T = j->GetReactionTorque(60.0f);
+  CHECK(fabsf(fabsf(T) - 10.0f) < 0.5f);     // weight x 0.5 m lever arm
+  j->EnableMotor(false);
+  for (int i = 0; i < 180; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(fabsf(j->GetJointTranslation() + 1.0f) < 0.02f);
+  b2Vec2 F = j->GetReactionForce(60.0f);
+  CHECK(fabsf(F.y - 20.0f) < 0.5f && fabsf(F.x) < 0.5f);   // the lower limit carries the weight
+  j->SetLimits(-2.0f, 1.5f);
+  for (int i = 0; i < 120; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(fabsf(j->GetJointTranslation() + 2.0f) < 0.02f);
+  printf("prismatic: speed %.4f motor force %.4f torque %.4f F=(%.4f, %.4f)\n", speed, motorForce, T, F.x, F.y);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -572,6 +617,7 @@ int main() {
   revolute_joint_api();
   distance_joint_api();
   weld_joint_api();
+  prismatic_joint_api();
   contact_buffers_grow();
   world_editing_session();
   user_contact_filter();

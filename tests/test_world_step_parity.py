@@ -72,7 +72,10 @@ def rel(a, b):
                                                    # distance joints: rods, springs, limited ropes, cross-linked
                                                    ("springs", 8, 0, 240),
                                                    # weld joints: rigid and soft cantilevers, a welded compound falling on them
-                                                   ("welds", 6, 0, 240)])
+                                                   ("welds", 6, 0, 240),
+                                                   # prismatic joints: motorised piston, lifts between limits,
+                                                   # free and locked rails, carriage on carriage
+                                                   ("sliders", 6, 0, 240)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
     from box2d_optimized_b200 import RefScene
     ref = RefScene(name, size, seed)
