@@ -127,6 +127,7 @@ struct b2gArena {
   long long stepCount;
   size_t fusedSmemSet;
   int bigGrid;  // co-resident grid of the persistent big-island kernel
+  unsigned int* bigBarrier;  // its grid-barrier counter (zeroed before every launch)
 
   // fixtures + shapes
   int* fBody;

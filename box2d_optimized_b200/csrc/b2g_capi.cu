@@ -327,6 +327,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->beginEvents, nc));
   CK(dalloc(&A->endEvents, nc));
   CK(dalloc(&A->dCounts, 1));
+  CK(dalloc(&A->bigBarrier, 1));
   CK(cudaMallocHost((void**)&A->hCounts, sizeof(StepCounts)));
   memset(A->hCounts, 0, sizeof(StepCounts));
   CK(cudaMallocHost((void**)&A->hostStage, 4096));
@@ -366,7 +367,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
                   A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
-                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->cubTemp};
+                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->cubTemp};
   for (void* p : ptrs) cudaFree(p);
   free_contact_buf(A->cb[0]);
   free(A->downloadSlots);
@@ -1149,12 +1150,14 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       BigRanges R;
       for (int c = 0; c <= B2G_MAX_COLOURS + 1; ++c) R.first[c] = colourFirst[c];
       R.numColours = numColours;
+      const size_t stageBytes = (size_t)B2G_BIG_STAGE_PLANES * B2G_BIG_THREADS * sizeof(float4);
       if (A->bigGrid == 0) {
         int perSM = 0, sms = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_big_solve, 256, 0));
+        CK(cudaFuncSetAttribute(k_big_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stageBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_big_solve, B2G_BIG_THREADS, stageBytes));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
-        if (perSM > 1) perSM = 1;  // one block per SM: the grid barrier costs grow with the block count
-        A->bigGrid = perSM * sms;
+        if (perSM < 1) return B2G_ERR_CUDA;
+        A->bigGrid = sms;  // one block per SM: the grid barrier costs grow with the block count
       }
       int velIters = P->velocity_iterations, posIters = P->position_iterations, warm = P->warm_starting;
       int penStride = A->capBodies, nbodies = nb;
@@ -1163,9 +1166,12 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       JointArraysDev JV = joint_views(A);
       void* args[] = {&R, &S, &C, &A->vel, &A->pos, &A->croot, &A->islandPen, &penStride, &nbodies, &A->bflags,
                       &A->island, &A->islandAwake, &A->bodySlot, &hh, &velIters, &posIters, &warm, &JW, &JV,
-                      &A->mass, &A->center, &dtr};
+                      &A->mass, &A->center, &dtr, &A->bigBarrier};
+      CK(cudaMemsetAsync(A->bigBarrier, 0, sizeof(unsigned int), A->stream));
       ktime_begin(A, KC_SOLVE_VELOCITY, (double)numBig * (velIters + posIters + 1));
-      CK(cudaLaunchCooperativeKernel((void*)k_big_solve, dim3(A->bigGrid), dim3(256), args, 0, A->stream));
+      // cooperative launch for the co-residency guarantee; the barrier itself is grid_arrive / grid_wait
+      CK(cudaLaunchCooperativeKernel((void*)k_big_solve, dim3(A->bigGrid), dim3(B2G_BIG_THREADS), args, stageBytes,
+                                     A->stream));
       ktime_end(A);
       A->launches++;
     }
@@ -1860,6 +1866,13 @@ extern "C" int b2g_get_kernel_timing(b2gArena* A, int32_t cls, double* total_ms,
   if (units) *units = A->ktUnitsSum[cls];
   return B2G_OK;
 }
+#ifdef B2G_BIG_TRACE
+extern "C" int b2g_debug_big_trace(unsigned long long* out, int32_t blocks) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out, g_bigTrace, sizeof(unsigned long long) * 2 * B2G_TRACE_CAP * (size_t)blocks));
+  return B2G_OK;
+}
+#endif
 extern "C" int b2g_set_inv_dt0(b2gArena* A, float v) {
   if (!A) return B2G_ERR_INVALID;
   A->invDt0 = v;

@@ -752,53 +752,206 @@ __global__ void k_joints_position_seq(JointWalk W, JointArraysDev J, float4* pos
   joints_position_global(W, J, pos, islandPen, penStride, iter);
 }
 
+// ---- the persistent big-island kernel ----------------------------------------------------------------
+// Body state of an oversize island lives in L2/HBM and is exchanged between SMs every colour pass.
+struct CoherentBodies {  // L2 loads / stores: the other SMs' writes of the previous pass, never a stale L1 line
+  float4* a;
+  __device__ __forceinline__ float4 load(int i) const { return __ldcg(a + i); }
+  __device__ __forceinline__ void store(int i, float4 v) const { __stcg(a + i, v); }
+};
+// Split grid barrier on a monotonic counter (scripts/micro/grid_barrier.cu: 1.28 us vs 1.49 us for
+// cooperative groups at 148 blocks).  arrive: the block's stores are ordered before thread 0's release
+// increment by the CTA barrier (cumulativity); wait: thread 0 spins with acquire loads, the CTA barrier
+// hands the observation to the rest of the block.  Work placed between the two halves (the prefetch of
+// the next pass's constraint constants) overlaps the wait.
+#ifdef B2G_BIG_TRACE  // debug build: per-block timestamps of every barrier (scripts/gpu_big_trace.py)
+#define B2G_TRACE_CAP 1024
+__device__ unsigned long long g_bigTrace[160 * B2G_TRACE_CAP * 2];
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+__device__ __forceinline__ void grid_arrive(unsigned int* counter, unsigned int& target) {
+  __syncthreads();
+  target += gridDim.x;
+#ifdef B2G_BIG_TRACE
+  if (threadIdx.x == 0 && target / gridDim.x <= B2G_TRACE_CAP)
+    g_bigTrace[((size_t)blockIdx.x * B2G_TRACE_CAP + target / gridDim.x - 1) * 2] = trace_now();
+#endif
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int target) {
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);
+#ifdef B2G_BIG_TRACE
+    if (target / gridDim.x <= B2G_TRACE_CAP)
+      g_bigTrace[((size_t)blockIdx.x * B2G_TRACE_CAP + target / gridDim.x - 1) * 2 + 1] = trace_now();
+#endif
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void stage_copy16(void* smemDst, const void* globalSrc) {
+  unsigned int d = (unsigned int)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(globalSrc) : "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#define B2G_BIG_THREADS 512
+#define B2G_BIG_STAGE_PLANES 9
+#define B2G_STAGE_VELOCITY 0  // idx, mass, nf, r1, r2, m1, m2, kk, imp  (warm start + velocity rows)
+#define B2G_STAGE_POSITION 1  // idx, mass, pn, pp, pc, pr
+// Each thread owns one 16-byte slot per plane in shared memory and keeps there the constants of the ONE
+// constraint it will visit in the next colour pass, fetched with cp.async while the grid barrier of the
+// current pass is still collecting arrivals.  After the barrier only the two body records (L2, written
+// by other SMs a moment ago) stand between the thread and the arithmetic.  `staged` = solver slot whose
+// planes are in the thread's slots (-1 none), so a wrong guess only costs a synchronous refill.
+struct BigStage {
+  SolverPlanes T;  // views of the shared-memory slots, indexed by threadIdx.x
+  int staged, kind;
+};
+__device__ __forceinline__ void stage_issue(BigStage& G, const SolverPlanes& S, int s, int kind) {
+  const int t = threadIdx.x;
+  stage_copy16(G.T.idx + t, S.idx + s);
+  stage_copy16(G.T.mass + t, S.mass + s);
+  if (kind == B2G_STAGE_VELOCITY) {
+    stage_copy16(G.T.nf + t, S.nf + s);
+    stage_copy16(G.T.r1 + t, S.r1 + s);
+    stage_copy16(G.T.r2 + t, S.r2 + s);
+    stage_copy16(G.T.m1 + t, S.m1 + s);
+    stage_copy16(G.T.m2 + t, S.m2 + s);
+    stage_copy16(G.T.kk + t, S.kk + s);
+    stage_copy16(G.T.imp + t, S.imp + s);
+  } else {
+    stage_copy16(G.T.pn + t, S.pn + s);
+    stage_copy16(G.T.pp + t, S.pp + s);
+    stage_copy16(G.T.pc + t, S.pc + s);
+    stage_copy16(G.T.pr + t, S.pr + s);
+  }
+  G.staged = s;
+  G.kind = kind;
+}
+__device__ __forceinline__ void stage_prefetch(BigStage& G, const SolverPlanes& S, int s, int kind) {
+  if (G.staged != s || G.kind != kind) stage_issue(G, S, s, kind);  // same slot again: the staged copy is current
+}
+// make slot s of `kind` available in the thread's shared-memory slots (no copy when the prefetch guessed right)
+__device__ __forceinline__ void stage_acquire(BigStage& G, const SolverPlanes& S, int s, int kind) {
+  stage_prefetch(G, S, s, kind);
+  stage_wait();
+}
+// island_done (b2g_step_kernels.cuh) on the penetrations other SMs published during this launch
+__device__ __forceinline__ bool island_done_l2(const uint32_t* islandPen, int penStride, int iter, int root) {
+  if (iter == 0) return false;
+  float pen = __uint_as_float(__ldcg(islandPen + (size_t)(iter - 1) * penStride + root));
+  return pen <= 3.0f * B2G_LINEAR_SLOP;
+}
+
 struct BigRanges {
   int first[B2G_MAX_COLOURS + 2];  // first[c]..first[c+1] = slots of colour c; [MAX] = overflow bucket
   int numColours;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(B2G_BIG_THREADS, 1)
 k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos, const int* __restrict__ croot,
             uint32_t* islandPen, int penStride, int nb, const uint32_t* __restrict__ bflags,
             const int* __restrict__ island, const uint32_t* __restrict__ islandAwake,
             const int* __restrict__ bodySlot, float h, int velIters, int posIters, int warmStarting, JointWalk W,
-            JointArraysDev J, const float4* __restrict__ mass, const float4* __restrict__ center, float dtRatio) {
-  cg::grid_group grid = cg::this_grid();
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+            JointArraysDev J, const float4* __restrict__ mass, const float4* __restrict__ center, float dtRatio,
+            unsigned int* barrier) {
+  extern __shared__ float4 stageMem[];
+  // consecutive groups of 32 constraints go to DIFFERENT blocks (warp w of block b is global warp
+  // w * gridDim + b), so a colour of a few thousand constraints keeps one or two warps busy on every SM
+  // instead of sixteen warps on a handful of SMs
+  const int gtid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
   const int gsize = gridDim.x * blockDim.x;
-  const GlobalBodies velAcc{vel};
-  const GlobalBodies posAcc{pos};
+  const CoherentBodies velAcc{vel};
+  const CoherentBodies posAcc{pos};
   const int ov0 = R.first[B2G_MAX_COLOURS], ov1 = R.first[B2G_MAX_COLOURS + 1];
+  unsigned int target = 0;
+  BigStage G;
+  {
+    float4* m = stageMem;
+    const int B = B2G_BIG_THREADS;
+    G.T.idx = (int4*)m;
+    G.T.mass = m + B;
+    G.T.nf = m + 2 * B;
+    G.T.r1 = m + 3 * B;
+    G.T.r2 = m + 4 * B;
+    G.T.m1 = m + 5 * B;
+    G.T.m2 = m + 6 * B;
+    G.T.kk = m + 7 * B;
+    G.T.imp = m + 8 * B;
+    G.T.pn = m + 2 * B;  // the position planes reuse the velocity slots
+    G.T.pp = m + 3 * B;
+    G.T.pc = m + 4 * B;
+    G.T.pr = m + 5 * B;
+    G.staged = -1;
+    G.kind = B2G_STAGE_VELOCITY;
+  }
+  const int t = threadIdx.x;
+  const int nc = R.numColours;
+#define B2G_BIG_BARRIER(nextSlot, nextLimit, nextKind)                                   \
+  do {                                                                                   \
+    grid_arrive(barrier, target);                                                        \
+    if ((nextSlot) < (nextLimit)) stage_prefetch(G, S, (nextSlot), (nextKind));          \
+    grid_wait(barrier, target);                                                          \
+  } while (0)
+#define B2G_BIG_BARRIER_PLAIN()      \
+  do {                               \
+    grid_arrive(barrier, target);    \
+    grid_wait(barrier, target);      \
+  } while (0)
 
   if (warmStarting) {
-    for (int c = 0; c < R.numColours; ++c) {
-      for (int s = R.first[c] + gtid; s < R.first[c + 1]; s += gsize) warm_start_constraint(S, s, velAcc);
-      grid.sync();
+    for (int c = 0; c < nc; ++c) {
+      const int s0 = R.first[c] + gtid, s1 = R.first[c + 1];
+      if (s0 < s1) {
+        stage_acquire(G, S, s0, B2G_STAGE_VELOCITY);
+        warm_start_constraint(G.T, t, velAcc);
+        for (int s = s0 + gsize; s < s1; s += gsize) warm_start_constraint(S, s, velAcc);
+      }
+      const int cn = c + 1 < nc ? c + 1 : 0;  // after the last colour: colour 0 of the first velocity iteration
+      B2G_BIG_BARRIER(R.first[cn] + gtid, R.first[cn + 1], B2G_STAGE_VELOCITY);
     }
     if (ov1 > ov0) {
       if (gtid == 0)
         for (int s = ov0; s < ov1; ++s) warm_start_constraint(S, s, velAcc);
-      grid.sync();
+      B2G_BIG_BARRIER_PLAIN();
     }
   }
   const float invH = h > 0.0f ? 1.0f / h : 0.0f;
   if (W.nj > 0) {
     if (gtid == 0) joints_init_global(W, J, pos, vel, mass, center, dtRatio, warmStarting);
-    grid.sync();
+    B2G_BIG_BARRIER_PLAIN();
   }
   for (int it = 0; it < velIters; ++it) {
     if (W.nj > 0) {
       if (gtid == 0) joints_velocity_global(W, J, vel, h, invH);
-      grid.sync();
+      B2G_BIG_BARRIER_PLAIN();
     }
-    for (int c = 0; c < R.numColours; ++c) {
-      for (int s = R.first[c] + gtid; s < R.first[c + 1]; s += gsize) solve_velocity_constraint(S, s, velAcc);
-      grid.sync();
+    for (int c = 0; c < nc; ++c) {
+      const int s0 = R.first[c] + gtid, s1 = R.first[c + 1];
+      if (s0 < s1) {
+        stage_acquire(G, S, s0, B2G_STAGE_VELOCITY);
+        solve_velocity_constraint(G.T, t, velAcc);
+        S.imp[s0] = G.T.imp[t];  // the staged copy stays current for a thread that revisits the same slot
+        for (int s = s0 + gsize; s < s1; s += gsize) solve_velocity_constraint(S, s, velAcc);
+      }
+      if (c + 1 < nc || it + 1 < velIters) {
+        const int cn = c + 1 < nc ? c + 1 : 0;
+        B2G_BIG_BARRIER(R.first[cn] + gtid, R.first[cn + 1], B2G_STAGE_VELOCITY);
+      } else {
+        B2G_BIG_BARRIER_PLAIN();
+      }
     }
     if (ov1 > ov0) {
       if (gtid == 0)
         for (int s = ov0; s < ov1; ++s) solve_velocity_constraint(S, s, velAcc);
-      grid.sync();
+      B2G_BIG_BARRIER_PLAIN();
     }
   }
   // store impulses (b2_contact_solver.cpp:641-657)
@@ -821,7 +974,7 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
   for (int b = gtid; b < nb; b += gsize) {
     if (bodySlot[b] != B2G_SLOT_BIG) continue;
     if (!body_simulated(bflags[b], island, islandAwake, b)) continue;
-    float4 p4 = pos[b], v4 = vel[b];
+    float4 p4 = posAcc.load(b), v4 = velAcc.load(b);
     float2 v = make_float2(v4.x, v4.y);
     float w = v4.z;
     float2 translation = h * v;
@@ -838,32 +991,81 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
     p4.x += h * v.x;
     p4.y += h * v.y;
     p4.z += h * w;
-    pos[b] = p4;
-    vel[b] = make_float4(v.x, v.y, w, v4.w);
+    posAcc.store(b, p4);
+    velAcc.store(b, make_float4(v.x, v.y, w, v4.w));
   }
-  grid.sync();
+  {
+    // first non-empty colour of the position passes (grid-uniform)
+    int cf = 0;
+    while (cf < nc && R.first[cf] == R.first[cf + 1]) ++cf;
+    if (cf < nc && posIters > 0) B2G_BIG_BARRIER(R.first[cf] + gtid, R.first[cf + 1], B2G_STAGE_POSITION);
+    else B2G_BIG_BARRIER_PLAIN();
+  }
   for (int it = 0; it < posIters; ++it) {
     for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {
-      if (c >= R.numColours && c < B2G_MAX_COLOURS) continue;
+      if (c >= nc && c < B2G_MAX_COLOURS) continue;
       int s0 = R.first[c], s1 = R.first[c + 1];
       if (s0 == s1) continue;  // grid-uniform
-      int sBegin = s0 + gtid, sStep = gsize;
       if (c == B2G_MAX_COLOURS) {
-        sBegin = gtid == 0 ? s0 : s1;
-        sStep = 1;
+        if (gtid == 0) {
+          for (int s = s0; s < s1; ++s) {
+            int root = croot[s];
+            if (island_done_l2(islandPen, penStride, it, root)) continue;
+            float minSep = solve_position_constraint(S, s, posAcc);
+            float pen = minSep < 0.0f ? -minSep : 0.0f;
+            atomicMax(&islandPen[(size_t)it * penStride + root], __float_as_uint(pen));
+          }
+        }
+        B2G_BIG_BARRIER_PLAIN();
+        continue;
       }
-      for (int s = sBegin; s < s1; s += sStep) {
-        int root = croot[s];
-        if (island_done(islandPen, penStride, it, root)) continue;
-        float minSep = solve_position_constraint(S, s, posAcc);
-        float pen = minSep < 0.0f ? -minSep : 0.0f;
-        atomicMax(&islandPen[(size_t)it * penStride + root], __float_as_uint(pen));
+      {
+        // the thread's staged constraint; the whole warp then publishes one penetration per island root
+        // (every constraint of a 100 k-body island would otherwise hit the same islandPen word)
+        const int sk = s0 + gtid;
+        int root = -1;
+        float pen = 0.0f;
+        if (sk < s1) {
+          root = croot[sk];
+          if (island_done_l2(islandPen, penStride, it, root)) {
+            root = -1;
+          } else {
+            stage_acquire(G, S, sk, B2G_STAGE_POSITION);
+            float minSep = solve_position_constraint(G.T, t, posAcc);
+            pen = minSep < 0.0f ? -minSep : 0.0f;
+          }
+        }
+        const unsigned int peers = __match_any_sync(0xffffffffu, root);
+        const unsigned int worst = __reduce_max_sync(peers, __float_as_uint(pen));
+        if (root >= 0 && worst != 0u && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+          uint32_t* slot = &islandPen[(size_t)it * penStride + root];
+          if (__ldcg(slot) < worst) atomicMax(slot, worst);
+        }
+        for (int s = sk + gsize; s < s1; s += gsize) {
+          int r2 = croot[s];
+          if (island_done_l2(islandPen, penStride, it, r2)) continue;
+          float minSep = solve_position_constraint(S, s, posAcc);
+          float p2 = minSep < 0.0f ? -minSep : 0.0f;
+          if (p2 > 0.0f) atomicMax(&islandPen[(size_t)it * penStride + r2], __float_as_uint(p2));
+        }
       }
-      grid.sync();
+      // next non-empty regular colour (this iteration, else the next one's first)
+      int cn = c + 1;
+      while (cn < nc && R.first[cn] == R.first[cn + 1]) ++cn;
+      bool more = cn < nc;
+      if (!more && it + 1 < posIters) {
+        cn = 0;
+        while (cn < nc && R.first[cn] == R.first[cn + 1]) ++cn;
+        more = cn < nc;
+      }
+      if (more) B2G_BIG_BARRIER(R.first[cn] + gtid, R.first[cn + 1], B2G_STAGE_POSITION);
+      else B2G_BIG_BARRIER_PLAIN();
     }
     if (W.nj > 0) {
       if (gtid == 0) joints_position_global(W, J, pos, islandPen, penStride, it);
-      grid.sync();
+      B2G_BIG_BARRIER_PLAIN();
     }
   }
+#undef B2G_BIG_BARRIER
+#undef B2G_BIG_BARRIER_PLAIN
 }
