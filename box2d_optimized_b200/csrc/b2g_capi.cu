@@ -1136,6 +1136,13 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     }
     colourFirst[B2G_MAX_COLOURS + 1] = acc;
     const int numOverflow = A->hCounts->colourCount[B2G_MAX_COLOURS];
+#ifdef B2G_BIG_TRACE
+    if (A->stepCount % 50 == 0) {
+      fprintf(stderr, "[big] step %lld colours:", A->stepCount);
+      for (int c = 0; c <= B2G_MAX_COLOURS; ++c) fprintf(stderr, " %d", A->hCounts->colourCount[c]);
+      fprintf(stderr, "\n");
+    }
+#endif
     if (numOverflow > 1)
       LAUNCH(A, KC_COLOUR, numOverflow, k_order_overflow, 1, 256, colourFirst[B2G_MAX_COLOURS],
              colourFirst[B2G_MAX_COLOURS + 1], A->sortedList, (int*)A->conKeys, C);
