@@ -854,6 +854,131 @@ struct BigRanges {
   int first[B2G_MAX_COLOURS + 2];  // first[c]..first[c+1] = slots of colour c; [MAX] = overflow bucket
   int numColours;
 };
+// first colour >= from with constraints, or limit
+__device__ __forceinline__ int big_next_colour(const BigRanges& R, int from, int limit) {
+  while (from < limit && R.first[from] == R.first[from + 1]) ++from;
+  return from;
+}
+
+#define B2G_BIG_WARM 0
+#define B2G_BIG_VELOCITY 1
+#define B2G_BIG_POSITION 2
+struct BigPassArgs {
+  const int* croot;
+  uint32_t* islandPen;
+  int penStride, it;
+};
+// one constraint of a pass: from the thread's staged copy, or straight from the planes.  Returns the
+// penetration (position passes).
+template <int PHASE, bool STAGED>
+__device__ __forceinline__ float big_visit(BigStage& G, const SolverPlanes& S, int s, const CoherentBodies& velAcc,
+                                           const CoherentBodies& posAcc) {
+  const int t = threadIdx.x;
+  if (STAGED) stage_acquire(G, S, s, PHASE == B2G_BIG_POSITION ? B2G_STAGE_POSITION : B2G_STAGE_VELOCITY);
+  if (PHASE == B2G_BIG_WARM) {
+    if (STAGED) warm_start_constraint(G.T, t, velAcc);
+    else warm_start_constraint(S, s, velAcc);
+  } else if (PHASE == B2G_BIG_VELOCITY) {
+    if (STAGED) {
+      solve_velocity_constraint(G.T, t, velAcc);
+      S.imp[s] = G.T.imp[t];  // the staged copy stays current for a thread that revisits the same slot
+    } else {
+      solve_velocity_constraint(S, s, velAcc);
+    }
+  } else {
+    float minSep = STAGED ? solve_position_constraint(G.T, t, posAcc) : solve_position_constraint(S, s, posAcc);
+    return minSep < 0.0f ? -minSep : 0.0f;
+  }
+  return 0.0f;
+}
+// this thread's share of one colour: slot sFirst (staged), then sFirst + stride, ... (direct).  Must be
+// called by whole warps (the position passes publish one penetration per warp and island root: every
+// constraint of a 100 k-body island would otherwise hit the same islandPen word).
+template <int PHASE>
+__device__ __forceinline__ void big_colour(BigStage& G, const SolverPlanes& S, int sFirst, int s1, int stride,
+                                           const CoherentBodies& velAcc, const CoherentBodies& posAcc,
+                                           const BigPassArgs& Q) {
+  int root = -1;
+  float pen = 0.0f;
+  if (sFirst < s1) {
+    if (PHASE == B2G_BIG_POSITION) {
+      root = Q.croot[sFirst];
+      if (island_done_l2(Q.islandPen, Q.penStride, Q.it, root)) root = -1;
+    }
+    if (PHASE != B2G_BIG_POSITION || root >= 0) pen = big_visit<PHASE, true>(G, S, sFirst, velAcc, posAcc);
+  }
+  if (PHASE == B2G_BIG_POSITION) {
+    const unsigned int peers = __match_any_sync(0xffffffffu, root);
+    const unsigned int worst = __reduce_max_sync(peers, __float_as_uint(pen));
+    if (root >= 0 && worst != 0u && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      uint32_t* slot = &Q.islandPen[(size_t)Q.it * Q.penStride + root];
+      if (__ldcg(slot) < worst) atomicMax(slot, worst);
+    }
+  }
+  if (stride > 0 && sFirst < s1) {
+    for (int s = sFirst + stride; s < s1; s += stride) {
+      if (PHASE == B2G_BIG_POSITION) {
+        int r2 = Q.croot[s];
+        if (island_done_l2(Q.islandPen, Q.penStride, Q.it, r2)) continue;
+        float p2 = big_visit<PHASE, false>(G, S, s, velAcc, posAcc);
+        if (p2 > 0.0f) atomicMax(&Q.islandPen[(size_t)Q.it * Q.penStride + r2], __float_as_uint(p2));
+      } else {
+        big_visit<PHASE, false>(G, S, s, velAcc, posAcc);
+      }
+    }
+  }
+}
+
+struct BigGrid {
+  unsigned int* barrier;
+  unsigned int target;
+  int gtid, gsize;
+};
+// One sweep over all colours (one solver iteration of PHASE).  `again` = another sweep over the same
+// kind of planes follows (warm start -> velocity iterations, velocity -> velocity, position -> position):
+// its first pass is prefetched behind this sweep's last barrier.
+template <int PHASE>
+__device__ __forceinline__ void big_sweep(BigGrid& Z, BigStage& G, const SolverPlanes& S, const BigRanges& R,
+                                          const CoherentBodies& velAcc, const CoherentBodies& posAcc,
+                                          const BigPassArgs& Q, bool again) {
+  const int kind = PHASE == B2G_BIG_POSITION ? B2G_STAGE_POSITION : B2G_STAGE_VELOCITY;
+  const int ct = R.numColours;
+  const int cFirst = big_next_colour(R, 0, ct);  // first pass of a sweep (ct when there is none)
+  for (int c = cFirst; c < ct;) {
+    big_colour<PHASE>(G, S, R.first[c] + Z.gtid, R.first[c + 1], Z.gsize, velAcc, posAcc, Q);
+    const int cn = big_next_colour(R, c + 1, ct);
+    // what this thread visits next: the next pass, else the first pass of the following sweep
+    int sn = 0, sl = 0;
+    if (cn < ct) {
+      sn = R.first[cn] + Z.gtid;
+      sl = R.first[cn + 1];
+    } else if (again) {
+      sn = R.first[cFirst] + Z.gtid;
+      sl = R.first[cFirst + 1];
+    }
+    grid_arrive(Z.barrier, Z.target);
+    if (sn < sl) stage_prefetch(G, S, sn, kind);
+    grid_wait(Z.barrier, Z.target);
+    c = cn;
+  }
+  const int ov0 = R.first[B2G_MAX_COLOURS], ov1 = R.first[B2G_MAX_COLOURS + 1];
+  if (ov1 > ov0) {  // serial overflow bucket
+    if (Z.gtid == 0) {
+      for (int s = ov0; s < ov1; ++s) {
+        if (PHASE == B2G_BIG_POSITION) {
+          int root = Q.croot[s];
+          if (island_done_l2(Q.islandPen, Q.penStride, Q.it, root)) continue;
+          float pen = big_visit<PHASE, false>(G, S, s, velAcc, posAcc);
+          atomicMax(&Q.islandPen[(size_t)Q.it * Q.penStride + root], __float_as_uint(pen));
+        } else {
+          big_visit<PHASE, false>(G, S, s, velAcc, posAcc);
+        }
+      }
+    }
+    grid_arrive(Z.barrier, Z.target);
+    grid_wait(Z.barrier, Z.target);
+  }
+}
 
 __global__ void __launch_bounds__(B2G_BIG_THREADS, 1)
 k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos, const int* __restrict__ croot,
@@ -863,15 +988,18 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
             JointArraysDev J, const float4* __restrict__ mass, const float4* __restrict__ center, float dtRatio,
             unsigned int* barrier) {
   extern __shared__ float4 stageMem[];
+  BigGrid Z;
+  Z.barrier = barrier;
+  Z.target = 0;
   // consecutive groups of 32 constraints go to DIFFERENT blocks (warp w of block b is global warp
   // w * gridDim + b), so a colour of a few thousand constraints keeps one or two warps busy on every SM
   // instead of sixteen warps on a handful of SMs
-  const int gtid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
-  const int gsize = gridDim.x * blockDim.x;
+  Z.gtid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+  Z.gsize = gridDim.x * blockDim.x;
+  const int gtid = Z.gtid, gsize = Z.gsize;
   const CoherentBodies velAcc{vel};
   const CoherentBodies posAcc{pos};
-  const int ov0 = R.first[B2G_MAX_COLOURS], ov1 = R.first[B2G_MAX_COLOURS + 1];
-  unsigned int target = 0;
+  const int ov1 = R.first[B2G_MAX_COLOURS + 1];
   BigStage G;
   {
     float4* m = stageMem;
@@ -892,67 +1020,26 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
     G.staged = -1;
     G.kind = B2G_STAGE_VELOCITY;
   }
-  const int t = threadIdx.x;
-  const int nc = R.numColours;
-#define B2G_BIG_BARRIER(nextSlot, nextLimit, nextKind)                                   \
-  do {                                                                                   \
-    grid_arrive(barrier, target);                                                        \
-    if ((nextSlot) < (nextLimit)) stage_prefetch(G, S, (nextSlot), (nextKind));          \
-    grid_wait(barrier, target);                                                          \
-  } while (0)
-#define B2G_BIG_BARRIER_PLAIN()      \
-  do {                               \
-    grid_arrive(barrier, target);    \
-    grid_wait(barrier, target);      \
-  } while (0)
+  BigPassArgs Q;
+  Q.croot = croot;
+  Q.islandPen = islandPen;
+  Q.penStride = penStride;
+  Q.it = 0;
 
-  if (warmStarting) {
-    for (int c = 0; c < nc; ++c) {
-      const int s0 = R.first[c] + gtid, s1 = R.first[c + 1];
-      if (s0 < s1) {
-        stage_acquire(G, S, s0, B2G_STAGE_VELOCITY);
-        warm_start_constraint(G.T, t, velAcc);
-        for (int s = s0 + gsize; s < s1; s += gsize) warm_start_constraint(S, s, velAcc);
-      }
-      const int cn = c + 1 < nc ? c + 1 : 0;  // after the last colour: colour 0 of the first velocity iteration
-      B2G_BIG_BARRIER(R.first[cn] + gtid, R.first[cn + 1], B2G_STAGE_VELOCITY);
-    }
-    if (ov1 > ov0) {
-      if (gtid == 0)
-        for (int s = ov0; s < ov1; ++s) warm_start_constraint(S, s, velAcc);
-      B2G_BIG_BARRIER_PLAIN();
-    }
-  }
+  if (warmStarting) big_sweep<B2G_BIG_WARM>(Z, G, S, R, velAcc, posAcc, Q, velIters > 0);
   const float invH = h > 0.0f ? 1.0f / h : 0.0f;
   if (W.nj > 0) {
     if (gtid == 0) joints_init_global(W, J, pos, vel, mass, center, dtRatio, warmStarting);
-    B2G_BIG_BARRIER_PLAIN();
+    grid_arrive(Z.barrier, Z.target);
+    grid_wait(Z.barrier, Z.target);
   }
   for (int it = 0; it < velIters; ++it) {
     if (W.nj > 0) {
       if (gtid == 0) joints_velocity_global(W, J, vel, h, invH);
-      B2G_BIG_BARRIER_PLAIN();
+      grid_arrive(Z.barrier, Z.target);
+      grid_wait(Z.barrier, Z.target);
     }
-    for (int c = 0; c < nc; ++c) {
-      const int s0 = R.first[c] + gtid, s1 = R.first[c + 1];
-      if (s0 < s1) {
-        stage_acquire(G, S, s0, B2G_STAGE_VELOCITY);
-        solve_velocity_constraint(G.T, t, velAcc);
-        S.imp[s0] = G.T.imp[t];  // the staged copy stays current for a thread that revisits the same slot
-        for (int s = s0 + gsize; s < s1; s += gsize) solve_velocity_constraint(S, s, velAcc);
-      }
-      if (c + 1 < nc || it + 1 < velIters) {
-        const int cn = c + 1 < nc ? c + 1 : 0;
-        B2G_BIG_BARRIER(R.first[cn] + gtid, R.first[cn + 1], B2G_STAGE_VELOCITY);
-      } else {
-        B2G_BIG_BARRIER_PLAIN();
-      }
-    }
-    if (ov1 > ov0) {
-      if (gtid == 0)
-        for (int s = ov0; s < ov1; ++s) solve_velocity_constraint(S, s, velAcc);
-      B2G_BIG_BARRIER_PLAIN();
-    }
+    big_sweep<B2G_BIG_VELOCITY>(Z, G, S, R, velAcc, posAcc, Q, it + 1 < velIters);
   }
   // store impulses (b2_contact_solver.cpp:641-657)
   for (int s = R.first[0] + gtid; s < ov1; s += gsize) {
@@ -995,77 +1082,26 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
     velAcc.store(b, make_float4(v.x, v.y, w, v4.w));
   }
   {
-    // first non-empty colour of the position passes (grid-uniform)
-    int cf = 0;
-    while (cf < nc && R.first[cf] == R.first[cf + 1]) ++cf;
-    if (cf < nc && posIters > 0) B2G_BIG_BARRIER(R.first[cf] + gtid, R.first[cf + 1], B2G_STAGE_POSITION);
-    else B2G_BIG_BARRIER_PLAIN();
+    // behind this barrier: the position planes of the thread's first position pass
+    int sn = 0, sl = 0;
+    if (posIters > 0) {
+      const int cf = big_next_colour(R, 0, R.numColours);
+      if (cf < R.numColours) {
+        sn = R.first[cf] + gtid;
+        sl = R.first[cf + 1];
+      }
+    }
+    grid_arrive(Z.barrier, Z.target);
+    if (sn < sl) stage_prefetch(G, S, sn, B2G_STAGE_POSITION);
+    grid_wait(Z.barrier, Z.target);
   }
   for (int it = 0; it < posIters; ++it) {
-    for (int c = 0; c <= B2G_MAX_COLOURS; ++c) {
-      if (c >= nc && c < B2G_MAX_COLOURS) continue;
-      int s0 = R.first[c], s1 = R.first[c + 1];
-      if (s0 == s1) continue;  // grid-uniform
-      if (c == B2G_MAX_COLOURS) {
-        if (gtid == 0) {
-          for (int s = s0; s < s1; ++s) {
-            int root = croot[s];
-            if (island_done_l2(islandPen, penStride, it, root)) continue;
-            float minSep = solve_position_constraint(S, s, posAcc);
-            float pen = minSep < 0.0f ? -minSep : 0.0f;
-            atomicMax(&islandPen[(size_t)it * penStride + root], __float_as_uint(pen));
-          }
-        }
-        B2G_BIG_BARRIER_PLAIN();
-        continue;
-      }
-      {
-        // the thread's staged constraint; the whole warp then publishes one penetration per island root
-        // (every constraint of a 100 k-body island would otherwise hit the same islandPen word)
-        const int sk = s0 + gtid;
-        int root = -1;
-        float pen = 0.0f;
-        if (sk < s1) {
-          root = croot[sk];
-          if (island_done_l2(islandPen, penStride, it, root)) {
-            root = -1;
-          } else {
-            stage_acquire(G, S, sk, B2G_STAGE_POSITION);
-            float minSep = solve_position_constraint(G.T, t, posAcc);
-            pen = minSep < 0.0f ? -minSep : 0.0f;
-          }
-        }
-        const unsigned int peers = __match_any_sync(0xffffffffu, root);
-        const unsigned int worst = __reduce_max_sync(peers, __float_as_uint(pen));
-        if (root >= 0 && worst != 0u && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-          uint32_t* slot = &islandPen[(size_t)it * penStride + root];
-          if (__ldcg(slot) < worst) atomicMax(slot, worst);
-        }
-        for (int s = sk + gsize; s < s1; s += gsize) {
-          int r2 = croot[s];
-          if (island_done_l2(islandPen, penStride, it, r2)) continue;
-          float minSep = solve_position_constraint(S, s, posAcc);
-          float p2 = minSep < 0.0f ? -minSep : 0.0f;
-          if (p2 > 0.0f) atomicMax(&islandPen[(size_t)it * penStride + r2], __float_as_uint(p2));
-        }
-      }
-      // next non-empty regular colour (this iteration, else the next one's first)
-      int cn = c + 1;
-      while (cn < nc && R.first[cn] == R.first[cn + 1]) ++cn;
-      bool more = cn < nc;
-      if (!more && it + 1 < posIters) {
-        cn = 0;
-        while (cn < nc && R.first[cn] == R.first[cn + 1]) ++cn;
-        more = cn < nc;
-      }
-      if (more) B2G_BIG_BARRIER(R.first[cn] + gtid, R.first[cn + 1], B2G_STAGE_POSITION);
-      else B2G_BIG_BARRIER_PLAIN();
-    }
+    Q.it = it;
+    big_sweep<B2G_BIG_POSITION>(Z, G, S, R, velAcc, posAcc, Q, it + 1 < posIters);
     if (W.nj > 0) {
       if (gtid == 0) joints_position_global(W, J, pos, islandPen, penStride, it);
-      B2G_BIG_BARRIER_PLAIN();
+      grid_arrive(Z.barrier, Z.target);
+      grid_wait(Z.barrier, Z.target);
     }
   }
-#undef B2G_BIG_BARRIER
-#undef B2G_BIG_BARRIER_PLAIN
 }
