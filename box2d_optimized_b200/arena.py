@@ -99,7 +99,7 @@ class Arena:
     def upload_joints(self, bodies, anchors, params, first=0, state=None):
         bodies = i32(bodies).reshape(-1, 2)
         anchors = f32(anchors).reshape(-1, 4)
-        params = f32(params).reshape(-1, 8)
+        params = f32(params).reshape(-1, 12)
         state = None if state is None else f32(state).reshape(-1, 5)
         a = capi.JointArrays(capi.ip(bodies), capi.fp(anchors), capi.fp(params), None if state is None else capi.fp(state))
         capi.check(self.lib.b2g_upload_joints(self.h, first, len(bodies), C.byref(a)), "b2g_upload_joints")

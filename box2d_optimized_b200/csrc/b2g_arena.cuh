@@ -144,6 +144,7 @@ struct b2gArena {
   float4* jAnchors;
   float4* jParams0;  // referenceAngle, lower, upper, maxMotorTorque
   float4* jParams1;  // motorSpeed, bits(flags), 0, 0
+  float4* jParams2;  // wheel: damping, 0, 0, 0
   float4* jState;    // impulse.x, impulse.y, motorImpulse, lowerImpulse
   float* jUpper;     // upperImpulse
   unsigned long long* ncKeys;     // [capJoints] unsorted, then sorted into ncKeysSorted

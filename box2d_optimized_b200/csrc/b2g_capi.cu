@@ -258,6 +258,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->jAnchors, nj));
   CK(dalloc(&A->jParams0, nj));
   CK(dalloc(&A->jParams1, nj));
+  CK(dalloc(&A->jParams2, nj));
   CK(dalloc(&A->jState, nj));
   CK(dalloc(&A->jUpper, nj));
   CK(dalloc(&A->jWork, nj));
@@ -361,7 +362,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jState, A->jUpper, A->jWork, A->stateStage, A->forceStage, A->jointOrder, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jParams2, A->jState, A->jUpper, A->jWork, A->stateStage, A->forceStage, A->jointOrder, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->worldFirst, A->worldLast, A->bvhBox, A->bvhKey, A->bvhDone,
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -455,14 +456,17 @@ extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, cons
   UP((int32_t*)A->jBodies, s->bodies, 2, int32_t);
   UP((float*)A->jAnchors, s->anchors, 4, float);
   if (s->params) {
-    // split [n][8] into two float4 planes
-    std::vector<float> p0((size_t)count * 4), p1((size_t)count * 4);
+    // split [n][12] into three float4 planes
+    std::vector<float> p0((size_t)count * 4), p1((size_t)count * 4), p2((size_t)count * 4);
     for (int i = 0; i < count; ++i) {
       for (int k = 0; k < 4; ++k) {
-        p0[(size_t)i * 4 + k] = s->params[(size_t)i * 8 + k];
-        p1[(size_t)i * 4 + k] = s->params[(size_t)i * 8 + 4 + k];
+        p0[(size_t)i * 4 + k] = s->params[(size_t)i * 12 + k];
+        p1[(size_t)i * 4 + k] = s->params[(size_t)i * 12 + 4 + k];
+        p2[(size_t)i * 4 + k] = s->params[(size_t)i * 12 + 8 + k];
       }
     }
+    CK(cudaMemcpyAsync((float*)A->jParams2 + (size_t)first * 4, p2.data(), p2.size() * sizeof(float),
+                       cudaMemcpyHostToDevice, A->stream));
     CK(cudaMemcpyAsync((float*)A->jParams0 + (size_t)first * 4, p0.data(), p0.size() * sizeof(float),
                        cudaMemcpyHostToDevice, A->stream));
     CK(cudaMemcpyAsync((float*)A->jParams1 + (size_t)first * 4, p1.data(), p1.size() * sizeof(float),
@@ -706,6 +710,7 @@ static JointArraysDev joint_views(b2gArena* A) {
   J.anchors = A->jAnchors;
   J.params0 = A->jParams0;
   J.params1 = A->jParams1;
+  J.params2 = A->jParams2;
   J.state = A->jState;
   J.upper = A->jUpper;
   J.work = A->jWork;

@@ -19,6 +19,7 @@
 #define B2G_JOINT_DISTANCE 1u
 #define B2G_JOINT_WELD 2u
 #define B2G_JOINT_PRISMATIC 3u
+#define B2G_JOINT_WHEEL 4u
 
 // per-step work area of one joint (plain struct in global memory; one thread touches it)
 struct JointWork {
@@ -35,6 +36,8 @@ struct JointWork {
   float3 wex, wey, wez;
   // prismatic joint (b2_prismatic_joint.h:182-190): world axis and its perpendicular, their lever arms
   // (k11/k12/k22, axialMass and `angle` = translation are shared with the revolute fields)
+  // wheel joint (b2_wheel_joint.h:219-229): axis = m_ax, perp = m_ay, a1/a2 = m_sAx/m_sBx, s1/s2 = m_sAy/m_sBy,
+  // k11 = m_mass, dMass = m_motorMass, softMass = m_springMass, bias, gamma, angle = m_translation
   float2 axis, perp;
   float a1, a2, s1, s2;
 };
@@ -44,11 +47,16 @@ struct JointArraysDev {
   const float4* anchors;   // localAnchorA.xy, localAnchorB.xy
   const float4* params0;   // referenceAngle, lowerAngle, upperAngle, maxMotorTorque
   const float4* params1;   // motorSpeed, bits(flags), 0, 0
+  const float4* params2;   // third parameter quad (wheel joints)
   float4* state;           // impulse.x, impulse.y, motorImpulse, lowerImpulse
   float* upper;            // upperImpulse
   JointWork* work;
   float h;                 // this step's dt (soft constraints)
 };
+// wheel joints: params0 = stiffness, lowerTranslation, upperTranslation, maxMotorTorque;
+// params1 = motorSpeed, bits(flags | 4 << 8), localXAxisA.x, localXAxisA.y (as given: the reference does not
+// normalise it); params2 = damping, 0, 0, 0;
+// state = impulse, springImpulse, motorImpulse, lowerImpulse; upper = upperImpulse
 // prismatic joints: params0 = referenceAngle, lowerTranslation, upperTranslation, maxMotorForce;
 // params1 = motorSpeed, bits(flags | 3 << 8), localXAxisA.x, localXAxisA.y (unit length);
 // state = impulse.x, impulse.y, motorImpulse, lowerImpulse; upper = upperImpulse
@@ -870,6 +878,255 @@ __device__ __forceinline__ bool prismatic_solve_position(const JointArraysDev& J
   return linearError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
 }
 
+// ---- wheel joint: b2WheelJoint::{InitVelocityConstraints, SolveVelocityConstraints,
+// SolvePositionConstraints} (src/dynamics/b2_wheel_joint.cpp:87-446): point-to-line row, suspension
+// spring along the axis, rotational motor, translation limits -------------------------------------------
+template <class PosAccess, class VelAccess>
+__device__ __forceinline__ void wheel_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+                                           const VelAccess& vel, const float4* __restrict__ bodyMass,
+                                           const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
+  JointWork w;
+  int2 bd = J.bodies[j];
+  float4 mAq = bodyMass[bd.x], mBq = bodyMass[bd.y];
+  float4 cAq = bodyCenter[bd.x], cBq = bodyCenter[bd.y];
+  w.ia = ia;
+  w.ib = ib;
+  w.mA = mAq.x; w.iA = mAq.y; w.mB = mBq.x; w.iB = mBq.y;
+  w.lcA = make_float2(cAq.x, cAq.y);
+  w.lcB = make_float2(cBq.x, cBq.y);
+  w.u = make_float2(0.0f, 0.0f);
+  w.k12 = w.k22 = w.currentLength = 0.0f;
+  w.wex = w.wey = w.wez = make_float3(0.0f, 0.0f, 0.0f);
+  float4 an = J.anchors[j], p0 = J.params0[j], p1 = J.params1[j], p2 = J.params2[j];
+  const uint32_t flags = __float_as_uint(p1.y);
+  const float stiffness = p0.x, damping = p2.x;
+  const float2 localX = make_float2(p1.z, p1.w);
+  const float2 localY = cross_sv(1.0f, localX);
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  float4 pA = pos.load(ia), pB = pos.load(ib);
+  float4 vAq = vel.load(ia), vBq = vel.load(ib);
+  float2 cA = make_float2(pA.x, pA.y), cB = make_float2(pB.x, pB.y);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  Rot qA = rot_set(pA.z), qB = rot_set(pB.z);
+  w.rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+  w.rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  float2 d = cB + w.rB - cA - w.rA;
+  {  // point to line constraint
+    w.perp = rot_mul(qA, localY);
+    w.s1 = cross2(d + w.rA, w.perp);
+    w.s2 = cross2(w.rB, w.perp);
+    w.k11 = mA + mB + iA * w.s1 * w.s1 + iB * w.s2 * w.s2;
+    if (w.k11 > 0.0f) w.k11 = 1.0f / w.k11;
+  }
+  // spring constraint
+  w.axis = rot_mul(qA, localX);
+  w.a1 = cross2(d + w.rA, w.axis);
+  w.a2 = cross2(w.rB, w.axis);
+  const float invMass = mA + mB + iA * w.a1 * w.a1 + iB * w.a2 * w.a2;
+  w.axialMass = invMass > 0.0f ? 1.0f / invMass : 0.0f;
+  w.softMass = 0.0f;
+  w.bias = 0.0f;
+  w.gamma = 0.0f;
+  float4 st = J.state[j];  // impulse, springImpulse, motorImpulse, lowerImpulse
+  float upper = J.upper[j];
+  if (stiffness > 0.0f && invMass > 0.0f) {
+    w.softMass = 1.0f / invMass;
+    float C = dot2(d, w.axis);
+    float h = J.h;
+    w.gamma = h * (damping + h * stiffness);
+    if (w.gamma > 0.0f) w.gamma = 1.0f / w.gamma;
+    w.bias = C * h * stiffness * w.gamma;
+    w.softMass = invMass + w.gamma;
+    if (w.softMass > 0.0f) w.softMass = 1.0f / w.softMass;
+  } else {
+    st.y = 0.0f;
+  }
+  w.angle = 0.0f;  // translation
+  if (flags & B2G_JOINT_LIMIT) {
+    w.angle = dot2(w.axis, d);
+  } else {
+    st.w = 0.0f;
+    upper = 0.0f;
+  }
+  if (flags & B2G_JOINT_MOTOR) {
+    w.dMass = iA + iB;
+    if (w.dMass > 0.0f) w.dMass = 1.0f / w.dMass;
+  } else {
+    w.dMass = 0.0f;
+    st.z = 0.0f;
+  }
+  if (warmStarting) {
+    // the limit impulses are not scaled by dtRatio (b2_wheel_joint.cpp:202-205)
+    st.x *= dtRatio;
+    st.y *= dtRatio;
+    st.z *= dtRatio;
+    float axialImpulse = st.y + st.w - upper;
+    float2 P = st.x * w.perp + axialImpulse * w.axis;
+    float LA = st.x * w.s1 + axialImpulse * w.a1 + st.z;
+    float LB = st.x * w.s2 + axialImpulse * w.a2 + st.z;
+    vA -= mA * P;
+    wA -= iA * LA;
+    vB += mB * P;
+    wB += iB * LB;
+  } else {
+    st = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    upper = 0.0f;
+  }
+  J.state[j] = st;
+  J.upper[j] = upper;
+  J.work[j] = w;
+  if (movable(mA, iA)) vel.store(ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class VelAccess>
+__device__ __forceinline__ void wheel_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float dt,
+                                                     float inv_dt) {
+  JointWork w = J.work[j];
+  float4 p0 = J.params0[j], p1 = J.params1[j];
+  const uint32_t flags = __float_as_uint(p1.y);
+  const float lowerTranslation = p0.y, upperTranslation = p0.z, maxMotorTorque = p0.w, motorSpeed = p1.x;
+  float4 st = J.state[j];
+  float upper = J.upper[j];
+  float4 vAq = vel.load(w.ia), vBq = vel.load(w.ib);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  {  // spring
+    float Cdot = dot2(w.axis, vB - vA) + w.a2 * wB - w.a1 * wA;
+    float impulse = -w.softMass * (Cdot + w.bias + w.gamma * st.y);
+    st.y += impulse;
+    float2 P = impulse * w.axis;
+    float LA = impulse * w.a1, LB = impulse * w.a2;
+    vA -= mA * P;
+    wA -= iA * LA;
+    vB += mB * P;
+    wB += iB * LB;
+  }
+  {  // rotational motor (runs with motorMass = 0 when the motor is off)
+    float Cdot = wB - wA - motorSpeed;
+    float impulse = -w.dMass * Cdot;
+    float oldImpulse = st.z;
+    float maxImpulse = dt * maxMotorTorque;
+    st.z = clampf(st.z + impulse, -maxImpulse, maxImpulse);
+    impulse = st.z - oldImpulse;
+    wA -= iA * impulse;
+    wB += iB * impulse;
+  }
+  if (flags & B2G_JOINT_LIMIT) {
+    {  // lower
+      float C = w.angle - lowerTranslation;
+      float Cdot = dot2(w.axis, vB - vA) + w.a2 * wB - w.a1 * wA;
+      float impulse = -w.axialMass * (Cdot + maxf_(C, 0.0f) * inv_dt);
+      float oldImpulse = st.w;
+      st.w = maxf_(st.w + impulse, 0.0f);
+      impulse = st.w - oldImpulse;
+      float2 P = impulse * w.axis;
+      float LA = impulse * w.a1, LB = impulse * w.a2;
+      vA -= mA * P;
+      wA -= iA * LA;
+      vB += mB * P;
+      wB += iB * LB;
+    }
+    {  // upper (signs flipped)
+      float C = upperTranslation - w.angle;
+      float Cdot = dot2(w.axis, vA - vB) + w.a1 * wA - w.a2 * wB;
+      float impulse = -w.axialMass * (Cdot + maxf_(C, 0.0f) * inv_dt);
+      float oldImpulse = upper;
+      upper = maxf_(upper + impulse, 0.0f);
+      impulse = upper - oldImpulse;
+      float2 P = impulse * w.axis;
+      float LA = impulse * w.a1, LB = impulse * w.a2;
+      vA += mA * P;
+      wA += iA * LA;
+      vB -= mB * P;
+      wB -= iB * LB;
+    }
+  }
+  {  // point to line
+    float Cdot = dot2(w.perp, vB - vA) + w.s2 * wB - w.s1 * wA;
+    float impulse = -w.k11 * Cdot;
+    st.x += impulse;
+    float2 P = impulse * w.perp;
+    float LA = impulse * w.s1, LB = impulse * w.s2;
+    vA -= mA * P;
+    wA -= iA * LA;
+    vB += mB * P;
+    wB += iB * LB;
+  }
+  J.state[j] = st;
+  J.upper[j] = upper;
+  if (movable(mA, iA)) vel.store(w.ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(w.ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class PosAccess>
+__device__ __forceinline__ bool wheel_solve_position(const JointArraysDev& J, int j, const PosAccess& pos) {
+  JointWork w = J.work[j];
+  float4 an = J.anchors[j], p0 = J.params0[j], p1 = J.params1[j];
+  const uint32_t flags = __float_as_uint(p1.y);
+  const float lowerTranslation = p0.y, upperTranslation = p0.z;
+  const float2 localX = make_float2(p1.z, p1.w);
+  const float2 localY = cross_sv(1.0f, localX);
+  float4 pAq = pos.load(w.ia), pBq = pos.load(w.ib);
+  float2 cA = make_float2(pAq.x, pAq.y), cB = make_float2(pBq.x, pBq.y);
+  float aA = pAq.z, aB = pBq.z;
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  float linearError = 0.0f;
+  if (flags & B2G_JOINT_LIMIT) {
+    Rot qA = rot_set(aA), qB = rot_set(aB);
+    float2 rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+    float2 rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+    float2 d = (cB - cA) + rB - rA;
+    float2 ax = rot_mul(qA, localX);
+    // the reference takes the lever arms about the axis of InitVelocityConstraints here (m_ax), :363-364
+    float sAx = cross2(d + rA, w.axis);
+    float sBx = cross2(rB, w.axis);
+    float C = 0.0f;
+    float translation = dot2(ax, d);
+    if (absf_(upperTranslation - lowerTranslation) < 2.0f * B2G_LINEAR_SLOP) C = translation;
+    else if (translation <= lowerTranslation) C = minf_(translation - lowerTranslation, 0.0f);
+    else if (translation >= upperTranslation) C = maxf_(translation - upperTranslation, 0.0f);
+    if (C != 0.0f) {
+      float invMass = mA + mB + iA * sAx * sAx + iB * sBx * sBx;
+      float impulse = 0.0f;
+      if (invMass != 0.0f) impulse = -C / invMass;
+      float2 P = impulse * ax;
+      float LA = impulse * sAx, LB = impulse * sBx;
+      cA -= mA * P;
+      aA -= iA * LA;
+      cB += mB * P;
+      aB += iB * LB;
+      linearError = absf_(C);
+    }
+  }
+  {  // perpendicular constraint
+    Rot qA = rot_set(aA), qB = rot_set(aB);
+    float2 rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+    float2 rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+    float2 d = (cB - cA) + rB - rA;
+    float2 ay = rot_mul(qA, localY);
+    float sAy = cross2(d + rA, ay);
+    float sBy = cross2(rB, ay);
+    float C = dot2(d, ay);
+    // the effective mass uses the lever arms of InitVelocityConstraints (m_sAy, m_sBy), :416
+    float invMass = mA + mB + iA * w.s1 * w.s1 + iB * w.s2 * w.s2;
+    float impulse = 0.0f;
+    if (invMass != 0.0f) impulse = -C / invMass;
+    float2 P = impulse * ay;
+    float LA = impulse * sAy, LB = impulse * sBy;
+    cA -= mA * P;
+    aA -= iA * LA;
+    cB += mB * P;
+    aB += iB * LB;
+    linearError = maxf_(linearError, absf_(C));
+  }
+  if (movable(mA, iA)) pos.store(w.ia, make_float4(cA.x, cA.y, aA, pAq.w));
+  if (movable(mB, iB)) pos.store(w.ib, make_float4(cB.x, cB.y, aB, pBq.w));
+  return linearError <= B2G_LINEAR_SLOP;
+}
+
 // ---- dispatch on the joint type -------------------------------------------------------------------
 template <class PosAccess, class VelAccess>
 __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
@@ -879,6 +1136,7 @@ __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int i
   if (type == B2G_JOINT_DISTANCE) distance_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_WELD) weld_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_PRISMATIC) prismatic_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else if (type == B2G_JOINT_WHEEL) wheel_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else revolute_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
 }
 template <class VelAccess>
@@ -888,6 +1146,7 @@ __device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, in
   if (type == B2G_JOINT_DISTANCE) distance_solve_velocity(J, j, vel, inv_dt);
   else if (type == B2G_JOINT_WELD) weld_solve_velocity(J, j, vel);
   else if (type == B2G_JOINT_PRISMATIC) prismatic_solve_velocity(J, j, vel, dt, inv_dt);
+  else if (type == B2G_JOINT_WHEEL) wheel_solve_velocity(J, j, vel, dt, inv_dt);
   else revolute_solve_velocity(J, j, vel, dt, inv_dt);
 }
 template <class PosAccess>
@@ -896,6 +1155,7 @@ __device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, in
   if (type == B2G_JOINT_DISTANCE) return distance_solve_position(J, j, pos);
   if (type == B2G_JOINT_WELD) return weld_solve_position(J, j, pos);
   if (type == B2G_JOINT_PRISMATIC) return prismatic_solve_position(J, j, pos);
+  if (type == B2G_JOINT_WHEEL) return wheel_solve_position(J, j, pos);
   return revolute_solve_position(J, j, pos);
 }
 #endif

@@ -328,12 +328,12 @@ void b2WorldImpl::flush() {
   if (jointsDirty) {
     int32 n = (int32)joints.size();
     std::vector<int32_t> jb((size_t)n * 2);
-    std::vector<float> anchors((size_t)n * 4), params((size_t)n * 8, 0.0f), state((size_t)n * 5);
+    std::vector<float> anchors((size_t)n * 4), params((size_t)n * 12, 0.0f), state((size_t)n * 5);
     for (int32 k = 0; k < n; ++k) {
       b2Joint* j = joints[k];
       jb[(size_t)k * 2] = j->m_bodyA->m_index;
       jb[(size_t)k * 2 + 1] = j->m_bodyB->m_index;
-      j->WriteDevice(&anchors[(size_t)k * 4], &params[(size_t)k * 8], &state[(size_t)k * 5]);
+      j->WriteDevice(&anchors[(size_t)k * 4], &params[(size_t)k * 12], &state[(size_t)k * 5]);
     }
     b2gJointArrays a;
     a.bodies = jb.data(); a.anchors = anchors.data(); a.params = params.data(); a.state = state.data();
@@ -626,8 +626,8 @@ void b2World::DestroyBody(b2Body* b) {
 b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   if (IsLocked()) return nullptr;
   if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint &&
-      def->type != e_prismaticJoint) {
-    fprintf(stderr, "[b2cuda] only revolute, distance, weld and prismatic joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
+      def->type != e_prismaticJoint && def->type != e_wheelJoint) {
+    fprintf(stderr, "[b2cuda] only revolute, distance, weld, prismatic and wheel joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
             (int)def->type);
     return nullptr;
   }
@@ -636,6 +636,7 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   if (def->type == e_revoluteJoint) j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
   else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
   else if (def->type == e_prismaticJoint) j = new b2PrismaticJoint(static_cast<const b2PrismaticJointDef*>(def));
+  else if (def->type == e_wheelJoint) j = new b2WheelJoint(static_cast<const b2WheelJointDef*>(def));
   else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
   j->m_index = (int32)m_impl->joints.size();
   m_impl->joints.push_back(j);
@@ -1491,6 +1492,115 @@ void b2PrismaticJoint::SetMaxMotorForce(float force) {
   if (force == m_maxMotorForce) return;
   Touch();
   m_maxMotorForce = force;
+}
+
+// ---- b2WheelJoint (b2_wheel_joint.cpp:40-85, 448-628) -------------------------------------------------
+void b2WheelJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor, const b2Vec2& axis) {
+  bodyA = bA;
+  bodyB = bB;
+  localAnchorA = bodyA->GetLocalPoint(anchor);
+  localAnchorB = bodyB->GetLocalPoint(anchor);
+  localAxisA = bodyA->GetLocalVector(axis);
+}
+b2WheelJoint::b2WheelJoint(const b2WheelJointDef* def) : b2Joint(def) {
+  m_localAnchorA = def->localAnchorA;
+  m_localAnchorB = def->localAnchorB;
+  m_localXAxisA = def->localAxisA;  // not normalised, as in the reference
+  m_localYAxisA = b2Cross(1.0f, m_localXAxisA);
+  m_impulse = m_springImpulse = m_motorImpulse = m_lowerImpulse = m_upperImpulse = 0.0f;
+  m_lowerTranslation = def->lowerTranslation;
+  m_upperTranslation = def->upperTranslation;
+  m_enableLimit = def->enableLimit;
+  m_maxMotorTorque = def->maxMotorTorque;
+  m_motorSpeed = def->motorSpeed;
+  m_enableMotor = def->enableMotor;
+  m_stiffness = def->stiffness;
+  m_damping = def->damping;
+}
+void b2WheelJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_localAnchorA.x; anchors[1] = m_localAnchorA.y; anchors[2] = m_localAnchorB.x; anchors[3] = m_localAnchorB.y;
+  p[0] = m_stiffness; p[1] = m_lowerTranslation; p[2] = m_upperTranslation; p[3] = m_maxMotorTorque;
+  p[4] = m_motorSpeed;
+  uint32_t fl = (m_enableLimit ? 1u : 0u) | (m_enableMotor ? 2u : 0u) | (m_collideConnected ? 4u : 0u) | (4u << 8);  // type 4
+  memcpy(&p[5], &fl, 4);
+  p[6] = m_localXAxisA.x; p[7] = m_localXAxisA.y;
+  p[8] = m_damping; p[9] = p[10] = p[11] = 0.0f;
+  st[0] = m_impulse; st[1] = m_springImpulse; st[2] = m_motorImpulse; st[3] = m_lowerImpulse; st[4] = m_upperImpulse;
+}
+void b2WheelJoint::ReadDeviceState(const float* st) {
+  m_impulse = st[0];
+  m_springImpulse = st[1];
+  m_motorImpulse = st[2];
+  m_lowerImpulse = st[3];
+  m_upperImpulse = st[4];
+}
+b2Vec2 b2WheelJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2WheelJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+b2Vec2 b2WheelJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  b2Vec2 ax = m_bodyA->GetWorldVector(m_localXAxisA), ay = m_bodyA->GetWorldVector(m_localYAxisA);
+  return inv_dt * (m_impulse * ay + (m_springImpulse + m_lowerImpulse - m_upperImpulse) * ax);
+}
+float b2WheelJoint::GetReactionTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_motorImpulse;
+}
+float b2WheelJoint::GetMotorTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_motorImpulse;
+}
+float b2WheelJoint::GetJointTranslation() const {
+  b2Vec2 d = m_bodyB->GetWorldPoint(m_localAnchorB) - m_bodyA->GetWorldPoint(m_localAnchorA);
+  return b2Dot(d, m_bodyA->GetWorldVector(m_localXAxisA));
+}
+float b2WheelJoint::GetJointLinearSpeed() const {
+  b2Vec2 rA = b2Mul(m_bodyA->GetTransform().q, m_localAnchorA - m_bodyA->GetLocalCenter());
+  b2Vec2 rB = b2Mul(m_bodyB->GetTransform().q, m_localAnchorB - m_bodyB->GetLocalCenter());
+  b2Vec2 d = (m_bodyB->GetWorldCenter() + rB) - (m_bodyA->GetWorldCenter() + rA);
+  b2Vec2 axis = b2Mul(m_bodyA->GetTransform().q, m_localXAxisA);
+  b2Vec2 vA = m_bodyA->GetLinearVelocity(), vB = m_bodyB->GetLinearVelocity();
+  float wA = m_bodyA->GetAngularVelocity(), wB = m_bodyB->GetAngularVelocity();
+  return b2Dot(d, b2Cross(wA, axis)) + b2Dot(axis, vB + b2Cross(wB, rB) - vA - b2Cross(wA, rA));
+}
+float b2WheelJoint::GetJointAngle() const { return m_bodyB->GetAngle() - m_bodyA->GetAngle(); }
+float b2WheelJoint::GetJointAngularSpeed() const { return m_bodyB->GetAngularVelocity() - m_bodyA->GetAngularVelocity(); }
+void b2WheelJoint::EnableLimit(bool flag) {
+  if (flag == m_enableLimit) return;
+  Touch();
+  m_enableLimit = flag;
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+}
+void b2WheelJoint::SetLimits(float lower, float upper) {
+  if (lower == m_lowerTranslation && upper == m_upperTranslation) return;
+  Touch();
+  m_lowerTranslation = lower;
+  m_upperTranslation = upper;
+  m_lowerImpulse = 0.0f;
+  m_upperImpulse = 0.0f;
+}
+void b2WheelJoint::EnableMotor(bool flag) {
+  if (flag == m_enableMotor) return;
+  Touch();
+  m_enableMotor = flag;
+}
+void b2WheelJoint::SetMotorSpeed(float speed) {
+  if (speed == m_motorSpeed) return;
+  Touch();
+  m_motorSpeed = speed;
+}
+void b2WheelJoint::SetMaxMotorTorque(float torque) {
+  if (torque == m_maxMotorTorque) return;
+  Touch();
+  m_maxMotorTorque = torque;
+}
+void b2WheelJoint::SetStiffness(float stiffness) {
+  Touch(false);  // the reference's spring setters do not wake the bodies
+  m_stiffness = stiffness;
+}
+void b2WheelJoint::SetDamping(float damping) {
+  Touch(false);
+  m_damping = damping;
 }
 
 // ---- b2WeldJoint (b2_weld_joint.cpp:38-60, 307-330) ---------------------------------------------------

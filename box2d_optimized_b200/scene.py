@@ -125,7 +125,7 @@ class _Scene:
         cap = max(self._f("scene_joint_count")(self.h), 1)
         bodies = np.zeros((cap, 2), np.int32)
         anchors = np.zeros((cap, 4), np.float32)
-        params = np.zeros((cap, 8), np.float32)
+        params = np.zeros((cap, 12), np.float32)
         n = self._f("scene_get_joints")(self.h, cap, capi.ip(bodies), capi.fp(anchors), capi.fp(params))
         return dict(bodies=bodies[:n], anchors=anchors[:n], params=params[:n])
 

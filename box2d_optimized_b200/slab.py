@@ -112,7 +112,7 @@ class _SceneView:
 
     def joints(self):
         return dict(bodies=np.zeros((0, 2), np.int32), anchors=np.zeros((0, 4), np.float32),
-                    params=np.zeros((0, 8), np.float32))
+                    params=np.zeros((0, 12), np.float32))
 
 
 # --------------------------------------------------------------------------------- device side

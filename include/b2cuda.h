@@ -142,23 +142,27 @@ typedef struct b2gContactArrays {
 } b2gContactArrays;
 
 /* Joints, SURVEY §8(f) rank 1: revolute (src/dynamics/b2_revolute_joint.cpp:73-321), distance
- * (src/dynamics/b2_distance_joint.cpp:76-303), weld (src/dynamics/b2_weld_joint.cpp:62-305) and
- * prismatic (src/dynamics/b2_prismatic_joint.cpp:114-451).  The type sits in bits 8-11 of the flags word.
+ * (src/dynamics/b2_distance_joint.cpp:76-303), weld (src/dynamics/b2_weld_joint.cpp:62-305),
+ * prismatic (src/dynamics/b2_prismatic_joint.cpp:114-451) and wheel (src/dynamics/b2_wheel_joint.cpp:87-446).  The type sits in bits 8-11 of the flags word.
  *   bodies  [n][2] = bodyA, bodyB
  *   anchors [n][4] = localAnchorA.xy, localAnchorB.xy
- *   params  [n][8], revolute (type 0): referenceAngle, lowerAngle, upperAngle, maxMotorTorque,
+ *   params  [n][12] (unused trailing entries 0), revolute (type 0): referenceAngle, lowerAngle, upperAngle, maxMotorTorque,
  *                    motorSpeed, bits(flags), 0, 0
  *                  distance (type 1): length, minLength, maxLength, stiffness, damping,
  *                    bits(flags | 1 << 8), 0, 0
  *                  weld (type 2): referenceAngle, stiffness, damping, 0, 0, bits(flags | 2 << 8), 0, 0
  *                  prismatic (type 3): referenceAngle, lowerTranslation, upperTranslation, maxMotorForce,
  *                    motorSpeed, bits(flags | 3 << 8), localXAxisA.x, localXAxisA.y (unit length)
+ *                  wheel (type 4): stiffness, lowerTranslation, upperTranslation, maxMotorTorque, motorSpeed,
+ *                    bits(flags | 4 << 8), localXAxisA.x, localXAxisA.y, damping, 0, 0, 0
  *                  flags: 1 enableLimit, 2 enableMotor, 4 collideConnected
  *   state   [n][5], revolute: m_impulse.x, m_impulse.y, m_motorImpulse, m_lowerImpulse, m_upperImpulse
  *                    (include/box2d/b2_revolute_joint.h:178-181)
  *                  distance: m_impulse, 0, 0, m_lowerImpulse, m_upperImpulse
  *                    (include/box2d/b2_distance_joint.h:157-159)
  *                  weld: m_impulse.x, .y, .z, 0, 0 (include/box2d/b2_weld_joint.h:112)
+ *                  wheel: m_impulse, m_springImpulse, m_motorImpulse, m_lowerImpulse, m_upperImpulse
+ *                    (include/box2d/b2_wheel_joint.h:196-200)
  *                  prismatic: m_impulse.x, m_impulse.y, m_motorImpulse, m_lowerImpulse, m_upperImpulse
  *                    (include/box2d/b2_prismatic_joint.h:164-167)
  *                  the warm-start accumulators.  NULL on upload = start from zero, as the joints'

@@ -408,7 +408,7 @@ class b2Joint {
   friend class b2Body;
   friend struct b2WorldImpl;
   b2Joint(const b2JointDef* def);
-  /// device record of this joint (include/b2cuda.h b2gJointArrays): anchors[4], params[8], state[5]
+  /// device record of this joint (include/b2cuda.h b2gJointArrays): anchors[4], params[12], state[5]
   virtual void WriteDevice(float* anchors, float* params, float* state) const = 0;
   /// accumulated impulses read back from the device
   virtual void ReadDeviceState(const float* state) = 0;
@@ -553,6 +553,94 @@ class b2PrismaticJoint : public b2Joint {
   bool m_enableLimit;
   bool m_enableMotor;
   mutable b2Vec2 m_impulse;
+  mutable float m_motorImpulse;
+  mutable float m_lowerImpulse;
+  mutable float m_upperImpulse;
+};
+
+/// b2_wheel_joint.h:30-231: a point of bodyB rides on a line fixed in bodyA (suspension spring along the
+/// line, optional translation limits) and rotates freely, optionally driven by a motor
+struct b2WheelJointDef : public b2JointDef {
+  b2WheelJointDef() {
+    type = e_wheelJoint;
+    localAnchorA.Set(0.0f, 0.0f);
+    localAnchorB.Set(0.0f, 0.0f);
+    localAxisA.Set(1.0f, 0.0f);
+    enableLimit = false;
+    lowerTranslation = 0.0f;
+    upperTranslation = 0.0f;
+    enableMotor = false;
+    maxMotorTorque = 0.0f;
+    motorSpeed = 0.0f;
+    stiffness = 0.0f;
+    damping = 0.0f;
+  }
+  void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec2& anchor, const b2Vec2& axis);
+  b2Vec2 localAnchorA;
+  b2Vec2 localAnchorB;
+  b2Vec2 localAxisA;
+  bool enableLimit;
+  float lowerTranslation;
+  float upperTranslation;
+  bool enableMotor;
+  float maxMotorTorque;
+  float motorSpeed;
+  float stiffness;
+  float damping;
+};
+
+class b2WheelJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  // b2_wheel_joint.cpp:459-467: the reference uses the axes of the last InitVelocityConstraints; here
+  // they are taken from bodyA's present transform
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  const b2Vec2& GetLocalAnchorA() const { return m_localAnchorA; }
+  const b2Vec2& GetLocalAnchorB() const { return m_localAnchorB; }
+  const b2Vec2& GetLocalAxisA() const { return m_localXAxisA; }
+  float GetJointTranslation() const;
+  float GetJointLinearSpeed() const;
+  float GetJointAngle() const;
+  float GetJointAngularSpeed() const;
+  bool IsLimitEnabled() const { return m_enableLimit; }
+  void EnableLimit(bool flag);
+  float GetLowerLimit() const { return m_lowerTranslation; }
+  float GetUpperLimit() const { return m_upperTranslation; }
+  void SetLimits(float lower, float upper);
+  bool IsMotorEnabled() const { return m_enableMotor; }
+  void EnableMotor(bool flag);
+  void SetMotorSpeed(float speed);
+  float GetMotorSpeed() const { return m_motorSpeed; }
+  void SetMaxMotorTorque(float torque);
+  float GetMaxMotorTorque() const { return m_maxMotorTorque; }
+  float GetMotorTorque(float inv_dt) const;
+  void SetStiffness(float stiffness);
+  float GetStiffness() const { return m_stiffness; }
+  void SetDamping(float damping);
+  float GetDamping() const { return m_damping; }
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2WheelJoint(const b2WheelJointDef* def);
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+  b2Vec2 m_localAnchorA;
+  b2Vec2 m_localAnchorB;
+  b2Vec2 m_localXAxisA;
+  b2Vec2 m_localYAxisA;
+  float m_lowerTranslation;
+  float m_upperTranslation;
+  float m_maxMotorTorque;
+  float m_motorSpeed;
+  bool m_enableLimit;
+  bool m_enableMotor;
+  float m_stiffness;
+  float m_damping;
+  mutable float m_impulse;
+  mutable float m_springImpulse;
   mutable float m_motorImpulse;
   mutable float m_lowerImpulse;
   mutable float m_upperImpulse;

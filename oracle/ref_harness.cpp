@@ -184,6 +184,9 @@ int b2ref_get_joint_state(void* h, int cap, float* out) {
     } else if ((*it)->GetType() == e_weldJoint) {  // b2_weld_joint.h:112
       b2WeldJoint* wj = static_cast<b2WeldJoint*>(*it);
       o[0] = wj->m_impulse.x; o[1] = wj->m_impulse.y; o[2] = wj->m_impulse.z; o[3] = 0.0f; o[4] = 0.0f;
+    } else if ((*it)->GetType() == e_wheelJoint) {  // b2_wheel_joint.h:196-200
+      b2WheelJoint* wh = static_cast<b2WheelJoint*>(*it);
+      o[0] = wh->m_impulse; o[1] = wh->m_springImpulse; o[2] = wh->m_motorImpulse; o[3] = wh->m_lowerImpulse; o[4] = wh->m_upperImpulse;
     } else if ((*it)->GetType() == e_prismaticJoint) {  // b2_prismatic_joint.h:164-167
       b2PrismaticJoint* pj = static_cast<b2PrismaticJoint*>(*it);
       o[0] = pj->m_impulse.x; o[1] = pj->m_impulse.y; o[2] = pj->m_motorImpulse; o[3] = pj->m_lowerImpulse; o[4] = pj->m_upperImpulse;
@@ -216,7 +219,7 @@ int b2ref_next_step_joint_order(void* h, int cap, int* out) {
     int n = 0;
     for (auto it = js.rbegin(); it != js.rend(); ++it)
       if ((*it)->GetType() == e_revoluteJoint || (*it)->GetType() == e_distanceJoint || (*it)->GetType() == e_weldJoint ||
-          (*it)->GetType() == e_prismaticJoint)
+          (*it)->GetType() == e_prismaticJoint || (*it)->GetType() == e_wheelJoint)
         jointIndex[*it] = n++;
   }
   std::unordered_map<const b2Body*, bool> bodySeen;

@@ -247,11 +247,13 @@ double SHIM(scene_time_ray_casts)(void* h, int n, const float* rays) {
 }
 
 int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->GetJointCount(); }
-// joints in creation order: bodies[n][2], anchors[n][4] = localAnchorA.xy, localAnchorB.xy, params[n][8]
+// joints in creation order: bodies[n][2], anchors[n][4] = localAnchorA.xy, localAnchorB.xy, params[n][12]
 // in the include/b2cuda.h b2gJointArrays layout:
 //   revolute: referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
 //   distance: length, minLength, maxLength, stiffness, damping, bits(flags | 1 << 8), 0, 0
 //   weld:     referenceAngle, stiffness, damping, 0, 0, bits(flags | 2 << 8), 0, 0
+//   wheel:    stiffness, lowerTranslation, upperTranslation, maxMotorTorque, motorSpeed, bits(flags | 4 << 8),
+//             localAxisA.x, localAxisA.y, damping, 0, 0, 0
 //   prismatic: referenceAngle, lowerTranslation, upperTranslation, maxMotorForce, motorSpeed,
 //             bits(flags | 3 << 8), localAxisA.x, localAxisA.y
 // flags: 1 = enableLimit, 2 = enableMotor, 4 = collideConnected.  Other joint types are skipped.
@@ -262,8 +264,9 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
   int n = 0;
   for (auto it = js.rbegin(); it != js.rend() && n < cap; ++it) {  // the list is newest-first
     b2Joint* j = *it;
-    float* p = params + 8 * n;
+    float* p = params + 12 * n;
     float p6 = 0.0f, p7 = 0.0f;
+    p[8] = p[9] = p[10] = p[11] = 0.0f;
     uint32_t fl = j->GetCollideConnected() ? 4u : 0u;
     if (j->GetType() == e_revoluteJoint) {
       b2RevoluteJoint* r = static_cast<b2RevoluteJoint*>(j);
@@ -285,6 +288,15 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
       anchors[4 * n + 2] = wj->GetLocalAnchorB().x; anchors[4 * n + 3] = wj->GetLocalAnchorB().y;
       p[0] = wj->GetReferenceAngle(); p[1] = wj->GetStiffness(); p[2] = wj->GetDamping(); p[3] = 0.0f; p[4] = 0.0f;
       fl |= 2u << 8;
+    } else if (j->GetType() == e_wheelJoint) {
+      b2WheelJoint* wh = static_cast<b2WheelJoint*>(j);
+      anchors[4 * n] = wh->GetLocalAnchorA().x; anchors[4 * n + 1] = wh->GetLocalAnchorA().y;
+      anchors[4 * n + 2] = wh->GetLocalAnchorB().x; anchors[4 * n + 3] = wh->GetLocalAnchorB().y;
+      p[0] = wh->GetStiffness(); p[1] = wh->GetLowerLimit(); p[2] = wh->GetUpperLimit();
+      p[3] = wh->GetMaxMotorTorque(); p[4] = wh->GetMotorSpeed();
+      p6 = wh->GetLocalAxisA().x; p7 = wh->GetLocalAxisA().y;
+      p[8] = wh->GetDamping();
+      fl |= (wh->IsLimitEnabled() ? 1u : 0u) | (wh->IsMotorEnabled() ? 2u : 0u) | (4u << 8);
     } else if (j->GetType() == e_prismaticJoint) {
       b2PrismaticJoint* pj = static_cast<b2PrismaticJoint*>(j);
       anchors[4 * n] = pj->GetLocalAnchorA().x; anchors[4 * n + 1] = pj->GetLocalAnchorA().y;

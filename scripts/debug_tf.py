@@ -14,6 +14,7 @@ P = Arena.params(solver_mode=capi.SOLVER_SEQUENTIAL, pos_iters=PI); stats = capi
 fixbody = ref.fixtures()["body"]
 import os
 fresh = int(os.environ.get("FRESH", "-1"))
+EPS = float(os.environ.get("EPS", "2e-5"))
 for k in range(steps):
     if k == fresh:
         A.close(); A = arena_from_scene(ref, max_contacts=max(4096, 16 * ref.body_count)); print("fresh arena at", k)
@@ -29,8 +30,20 @@ for k in range(steps):
     rb = ref.bodies(); gb = A.download_bodies(what=("pos", "vel", "flags", "force"))
     ev = np.abs(gb["vel"][:, :3] - rb[:, 7:10]) / np.maximum(1, np.abs(rb[:, 7:10]))
     ep = np.abs(gb["pos"][:, :3] - rb[:, 4:7]) / np.maximum(1, np.abs(rb[:, 4:7]))
-    if ev.max() > 2e-5 or ep.max() > 2e-5:
-        print("bodies with error", np.nonzero((ev.max(1) > 2e-5) | (ep.max(1) > 2e-5))[0])
+    if ev.max() > EPS or ep.max() > EPS:
+        print("bodies with error", np.nonzero((ev.max(1) > EPS) | (ep.max(1) > EPS))[0])
+        js = A.download_joints(len(ref.joint_state()))
+        if js is not None: print('joint state diff', np.abs(js - ref.joint_state()).max(axis=1))
         i = int(np.argmax(np.maximum(ev.max(1), ep.max(1))))
         nc = [(int(a), int(b)) for a, b in zip(fa, fb) if fixbody[a] == i or fixbody[b] == i]
         print(f"step {k} body {i} type {rb[i,11]} ev {ev[i]} ep {ep[i]} gpu vel {gb['vel'][i,:3]} ref vel {rb[i,7:10]} before vel {b0[i,7:10]} a {b0[i,6]} constraints {nc}")
+        if EPS == 0:
+            for q in range(len(cr["fix_a"])):
+                if fixbody[cr["fix_a"][q]] == i or fixbody[cr["fix_b"][q]] == i:
+                    for q2 in range(len(cg["fix_a"])):
+                        if cg["fix_a"][q2] == cr["fix_a"][q] and cg["fix_b"][q2] == cr["fix_b"][q]:
+                            d = cg["manifold"][q2].view(np.uint32) != cr["manifold"][q].view(np.uint32)
+                            print("gpu manifold differs at", np.nonzero(d)[0].tolist(), cg["manifold"][q2][d].tolist(), cr["manifold"][q][d].tolist())
+                    print("ref contact", int(cr["fix_a"][q]), int(cr["fix_b"][q]), "flags", hex(int(cr["flags"][q])), "manifold", cr["manifold"][q].tolist())
+            print("gpu pos", gb["pos"][i, :3].tolist(), "ref pos", rb[i, 4:7].tolist(), "before", b0[i, 4:7].tolist())
+            break

@@ -607,6 +607,48 @@ static void prismatic_joint_api() {
   printf("prismatic: speed %.4f motor force %.4f torque %.4f F=(%.4f, %.4f)\n", speed, motorForce, T, F.x, F.y);
 }
 
+// wheel joint: a wheel hanging on its suspension spring settles where the spring carries its weight,
+// the motor spins it up, the limits stop the travel
+static void wheel_joint_api() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2CircleShape tyre;
+  tyre.m_radius = 0.5f;
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  bd.position.Set(0.0f, 5.0f);
+  b2Body* wheel = world.CreateBody(&bd);
+  wheel->CreateFixture(&tyre, 2.0f);   // mass 2 x pi x 0.25 = 1.5708
+  b2WheelJointDef jd;
+  jd.Initialize(ground, wheel, wheel->GetPosition(), b2Vec2(0.0f, 1.0f));
+  b2LinearStiffness(jd.stiffness, jd.damping, 2.0f, 0.7f, ground, wheel);
+  jd.enableMotor = true;
+  jd.motorSpeed = 3.0f;
+  jd.maxMotorTorque = 50.0f;
+  b2WheelJoint* j = static_cast<b2WheelJoint*>(world.CreateJoint(&jd));
+  CHECK(j != nullptr && j->IsMotorEnabled() && !j->IsLimitEnabled() && j->GetStiffness() == jd.stiffness);
+  for (int i = 0; i < 240; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  // static sag = m g / k
+  float sag = j->GetJointTranslation(), expect = -wheel->GetMass() * 10.0f / jd.stiffness;
+  CHECK(fabsf(sag - expect) < 0.01f);
+  CHECK(fabsf(j->GetJointAngularSpeed() - 3.0f) < 0.01f && fabsf(wheel->GetPosition().x) < 1e-3f);
+  b2Vec2 F = j->GetReactionForce(60.0f);
+  CHECK(fabsf(F.y - wheel->GetMass() * 10.0f) < 0.2f);   // the spring carries the weight
+  // a rigid wheel joint with limits: drops to the lower stop
+  j->SetStiffness(0.0f);
+  j->SetDamping(0.0f);
+  j->EnableMotor(false);
+  j->SetLimits(-1.0f, 0.5f);
+  j->EnableLimit(true);
+  wheel->SetAwake(true);
+  for (int i = 0; i < 180; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(fabsf(j->GetJointTranslation() + 1.0f) < 0.02f);
+  CHECK(fabsf(j->GetJointLinearSpeed()) < 0.01f);
+  printf("wheel: sag %.4f (m g / k = %.4f) spin %.4f F=(%.4f, %.4f) stop %.4f\n", sag, expect, j->GetJointAngularSpeed(), F.x, F.y,
+         j->GetJointTranslation());
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -618,6 +660,7 @@ int main() {
   distance_joint_api();
   weld_joint_api();
   prismatic_joint_api();
+  wheel_joint_api();
   contact_buffers_grow();
   world_editing_session();
   user_contact_filter();

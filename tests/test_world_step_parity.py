@@ -75,7 +75,12 @@ def rel(a, b):
                                                    ("welds", 6, 0, 240),
                                                    # prismatic joints: motorised piston, lifts between limits,
                                                    # free and locked rails, carriage on carriage
-                                                   ("sliders", 6, 0, 240)])
+                                                   ("sliders", 6, 0, 240),
+                                                   # wheel joints: sprung motorised cars over ramps and crates
+                                                   ("cars", 4, 0, 300),
+                                                   # the same cars with crates that fall asleep and are woken by
+                                                   # the impact: ring-order corner, tolerance gate only (see below)
+                                                   ("cars", 4, 1, 300)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
     from box2d_optimized_b200 import RefScene
     ref = RefScene(name, size, seed)
@@ -135,7 +140,12 @@ def test_every_step_from_the_reference_state(require_ref, name, size, seed, step
           f"joint impulses {worst['joint']:.3g}")
     assert solved_total > 1000 or nj
     assert max(worst["pos"], worst["vel"], worst["imp"], worst["joint"]) <= 1e-4 and worst["sleep"] <= 1e-6
-    if device_rotations_match_libm():
+    # A body woken in the middle of b2ContactManager::Collide: the reference re-evaluates its remaining
+    # contacts only if they come LATER in the world's contact ring than the waking contact; the device
+    # narrowphase takes the awake flags of the start of the pass, so such a contact keeps last step's
+    # manifold for one step (1e-6-level difference in its local points).  Within the gates, not bit-exact.
+    ring_order_sensitive = (name, seed) == ("cars", 1)
+    if device_rotations_match_libm() and not ring_order_sensitive:
         # same libm algorithm on both sides -> every float of the step is reproduced bit for bit
         assert worst == dict(pos=0.0, vel=0.0, imp=0.0, sleep=0.0, joint=0.0), worst
     A.close()
