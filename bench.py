@@ -202,15 +202,21 @@ def ncu_traffic(cls, workload):
     files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_ncu_full_summary.csv")))
     if not files:
         return None, None
-    rows = list(csv.reader(open(files[-1])))
-    hdr, units = rows[0], rows[1]
-    ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    # newest summary that actually holds the dominant kernel (a truncated or foreign file must not
+    # take the bench line down)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    vals = [float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
-            for r in rows[2:] if len(r) > wi and KERNEL_OF_CLASS[cls] in r[0]]
-    if not vals:
-        return None, None
-    return sum(vals) / len(vals), os.path.basename(files[-1])
+    for f in reversed(files):
+        try:
+            rows = list(csv.reader(open(f)))
+            hdr, units = rows[0], rows[1]
+            ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            vals = [float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+                    for r in rows[2:] if len(r) > wi and KERNEL_OF_CLASS[cls] in r[0]]
+        except (IndexError, ValueError, KeyError):
+            continue
+        if vals:
+            return sum(vals) / len(vals), os.path.basename(f)
+    return None, None
 
 
 def main():
@@ -386,12 +392,17 @@ def main():
         try:
             from box2d_optimized_b200 import RefScene
             r = RefScene(scene_name, size, seed)
-            r.step(args.warmup)
+            r.step(PRESTEP.get(args.workload, 0) + args.warmup)  # same spawn phase as the replicated GPU state
             n = min(args.cpu_sample_steps, args.steps)
             ms = r.time_steps(n)
-            cpu = {"value": nb * n / (ms / 1000.0), "unit": "body-steps/s", "cores": 1, "kind": "reference",
+            # one world on one core: for the batched workloads that is ONE of the arena's worlds, so the
+            # unit count is that world's bodies, not the arena's
+            cpu_bodies = r.body_count
+            cpu = {"value": cpu_bodies * n / (ms / 1000.0), "unit": "body-steps/s", "cores": 1, "kind": "reference",
                    "ms_per_step": ms / n,
-                   "sample": f"steps {args.warmup}..{args.warmup + n} of {args.workload} on 1 host core "
+                   "sample": f"steps {args.warmup}..{args.warmup + n} of "
+                             f"{'one world (' + str(cpu_bodies) + ' bodies) of ' if args.workload in WORLDS_PER_GPU else ''}"
+                             f"{args.workload} on 1 host core "
                              "(the reference is single-threaded), oracle/_ref/libb2ref.so compiled from "
                              "/root/reference with -O3 -DNDEBUG"}
         except Exception as exc:  # the oracle is optional for the product, mandatory for the number

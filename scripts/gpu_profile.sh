@@ -3,7 +3,7 @@
 # the dominant kernels.  Numbers printed under ncu are not bench values.
 mkdir -p gpurun_out
 WL=${1:-many_pyramids}
-SKIP=${2:-2600}
+SKIP=${2:-900}
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --workload $WL --steps 8 --warmup 70 --profile-steps 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_solve_bins_fused|k_bp_traverse|k_narrowphase|k_wide_refit|k_island_union$" -s ${3:-400} -c 10 \
