@@ -10,9 +10,16 @@ state ("the owner's result wins"), which is the once-per-step halo exchange:
 
 sent with NCCL point-to-point (`torch.distributed.batch_isend_irecv`) straight from views of the
 arena's device arrays (`b2g_device_views`), or — for the single-process emulation used by the
-1-GPU test — copied tensor to tensor.  Membership of the ghost layer is fixed at set-up from the
-initial positions (round-1 limitation: valid while bodies drift less than `halo` across a cut, as
-in a pile settling under gravity); there is no migration yet.
+1-GPU test — copied tensor to tensor.  Ownership and ghost membership are fixed between two
+REBALANCES: every K steps (caller's choice) each rank publishes the state of the bodies it owns,
+every rank rebuilds the same global picture, the cut planes are moved to equal body counts again and
+each rank re-creates its arena from the bodies it now owns plus their ghosts (`rebalance_in_process`,
+`rebalance_distributed`).  That is the ownership migration of SURVEY §8e done wholesale instead of
+body by body: valid while no body drifts more than `halo` across a cut within K steps (at most 2 m per
+step, b2_maxTranslation).  Contacts travel too: every contact is published once (by the owner of its
+lowest-numbered movable body) with its manifold and accumulated impulses, and a rebuilt arena starts
+from the published contacts whose fixtures it holds, so warm starting survives a rebalance; only the
+bodies' sleep timers and the persistent solver colours start over.
 
 This is an approximation, validated by tolerance against the single-arena result (pile height,
 deepest penetration, no lost bodies) — never bit-parity (SURVEY §7 "Hard parts").
@@ -92,7 +99,8 @@ def local_scene(glob, slab):
                 fixtures=dict(body=remap[fx["body"][fsel]].astype(np.int32), type=fx["type"][fsel],
                               shape_off=np.array(offs, np.int32), filter=fx["filter"][fsel],
                               material=fx["material"][fsel], sensor=fx["sensor"][fsel],
-                              quads=np.concatenate(quads) if quads else np.zeros((1, 4), np.float32)))
+                              quads=np.concatenate(quads) if quads else np.zeros((1, 4), np.float32),
+                              gid=fsel.astype(np.int64)))
 
 
 class _SceneView:
@@ -129,7 +137,12 @@ class SlabRank:
         from .arena import arena_from_scene
         self.slab = slab
         self.torch = torch
-        self.arena = arena_from_scene(_SceneView(local_scene(glob, slab)), max_contacts=max_contacts, device=device)
+        local = local_scene(glob, slab)
+        self.fix_gid = local["fixtures"]["gid"]          # local fixture -> global fixture
+        self.fix_body_gid = glob["fixtures"]["body"]     # global fixture -> global body
+        self.num_global_fixtures = len(glob["fixtures"]["body"])
+        self.body_type = glob["bodies"][:, 11].astype(np.int32)
+        self.arena = arena_from_scene(_SceneView(local), max_contacts=max_contacts, device=device)
         self.arena.find_new_contacts()
         v = self.arena.device_views()
         dev = torch.device("cuda", device)
@@ -165,6 +178,55 @@ class SlabRank:
         sl = self.slab.owned_local
         return bd["pos"][sl], bd["vel"][sl], bd["flags"][sl]
 
+    def owned_record(self):
+        """[n, 13] float64 rows (global id, pos c.x c.y a, vel v.x v.y w, xf p.x p.y s c, awake, 0) of the
+        bodies this rank owns: what a rebalance publishes"""
+        bd = self.arena.download_bodies(what=("pos", "vel", "xf", "flags"))
+        sl = self.slab.owned_local
+        gid = self.slab.global_ids[sl].astype(np.float64)
+        awake = ((bd["flags"][sl] & capi.BODY_AWAKE) != 0).astype(np.float64)
+        return np.concatenate([gid[:, None], bd["pos"][sl][:, 0:3], bd["vel"][sl][:, 0:3], bd["xf"][sl][:, 0:4],
+                               awake[:, None], np.zeros((len(sl), 1))], axis=1)
+
+    def contact_record(self):
+        """contacts this rank answers for in a rebalance, by GLOBAL fixture ids, with manifolds and warm-start
+        impulses.  A boundary contact lives on both sides of a cut: it is published by the rank that owns the
+        contact's non-static body with the smallest global id."""
+        c = self.arena.download_contacts()
+        ga, gb = self.fix_gid[c["fix_a"]], self.fix_gid[c["fix_b"]]
+        ba, bb = self.fix_body_gid[ga].astype(np.int64), self.fix_body_gid[gb].astype(np.int64)
+        big = np.int64(1) << 40
+        lead = np.minimum(np.where(self.body_type[ba] != capi.STATIC, ba, big),
+                          np.where(self.body_type[bb] != capi.STATIC, bb, big))
+        mine = np.zeros(len(self.body_type) + 1, bool)
+        mine[self.slab.global_ids[self.slab.owned_local]] = True
+        keep = mine[np.minimum(lead, len(self.body_type))]
+        return dict(fix_a=ga[keep], fix_b=gb[keep], flags=c["flags"][keep], manifold=c["manifold"][keep],
+                    material=c["material"][keep])
+
+    def seed_contacts(self, records, inv_dt0):
+        """start this (freshly built) arena from published contacts: those whose two fixtures it holds"""
+        inv = np.full(self.num_global_fixtures, -1, np.int64)
+        inv[self.fix_gid] = np.arange(len(self.fix_gid))
+        fa, fb, fl, mf, mt = [], [], [], [], []
+        for r in records:
+            if len(r["fix_a"]) == 0:
+                continue
+            la, lb = inv[r["fix_a"]], inv[r["fix_b"]]
+            sel = (la >= 0) & (lb >= 0)
+            fa.append(la[sel]); fb.append(lb[sel]); fl.append(r["flags"][sel])
+            mf.append(r["manifold"][sel]); mt.append(r["material"][sel])
+        if not fa:
+            return 0
+        fa, fb = np.concatenate(fa).astype(np.int32), np.concatenate(fb).astype(np.int32)
+        fl = np.concatenate(fl).astype(np.uint32) & np.uint32(capi.CONTACT_TOUCHING | capi.CONTACT_ENABLED)
+        self.arena.upload_contacts(fa, fb, fl, np.concatenate(mf), np.concatenate(mt))
+        self.arena.set_inv_dt0(inv_dt0)
+        return len(fa)
+
+    def close(self):
+        self.arena.close()
+
 
 def exchange_distributed(sr):
     """once-per-step halo exchange over NCCL point-to-point (one message per neighbour)"""
@@ -187,6 +249,66 @@ def exchange_in_process(ranks):
     for sr in ranks:
         for nb in sr.slab.neighbours:
             sr.unpack(nb, msgs[(nb, sr.slab.rank)])
+
+
+# ------------------------------------------------------------------------------- rebalance
+def merge_records(glob, records):
+    """writes published owner records (SlabRank.owned_record, any order, any number of ranks) into the
+    global scene arrays: rows of scene.bodies() = xf(4), c(2), a, v(2), w, awake, type"""
+    b = glob["bodies"]
+    for rec in records:
+        if len(rec) == 0:
+            continue
+        g = rec[:, 0].astype(np.int64)
+        b[g, 4:7] = rec[:, 1:4].astype(np.float32)
+        b[g, 7:10] = rec[:, 4:7].astype(np.float32)
+        b[g, 0:4] = rec[:, 7:11].astype(np.float32)
+        b[g, 10] = rec[:, 11].astype(np.float32)
+    return glob
+
+
+def rebalance_in_process(glob, ranks, halo=3.0, device=0, max_contacts=None, inv_dt0=60.0):
+    """single-process emulation: all slabs publish, the world is cut again, every slab is rebuilt.
+    Returns (ranks, owner, cuts, migrated) with migrated = bodies that changed owner."""
+    nranks = len(ranks)
+    old_owner = np.full(len(glob["bodies"]), -1, np.int32)
+    for sr in ranks:
+        old_owner[sr.slab.global_ids[sr.slab.owned_local]] = sr.slab.rank
+    merge_records(glob, [sr.owned_record() for sr in ranks])
+    contacts = [sr.contact_record() for sr in ranks]
+    for sr in ranks:
+        sr.close()
+    slabs, owner, cuts = make_slabs(glob, nranks, halo)
+    new = [SlabRank(glob, s, device=device, max_contacts=max_contacts) for s in slabs]
+    for sr in new:
+        sr.seed_contacts(contacts, inv_dt0)
+    return new, owner, cuts, int(np.sum(owner != old_owner))
+
+
+def gather_records(record):
+    """all ranks' owner records on every rank (torch.distributed, any backend)"""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, record)
+    return out
+
+
+def rebalance_distributed(glob, sr, halo=3.0, device=0, max_contacts=None, inv_dt0=60.0):
+    """one process per GPU: all-gather of the owner records (the only collective of a rebalance; every
+    K steps, a few MB), then every rank cuts the same global picture and rebuilds its own slab"""
+    import torch.distributed as dist
+    nranks = dist.get_world_size()
+    records = gather_records(sr.owned_record())
+    contacts = gather_records(sr.contact_record())
+    old_mine = set(sr.slab.global_ids[sr.slab.owned_local].tolist())
+    merge_records(glob, records)
+    rank = sr.slab.rank
+    sr.close()
+    slabs, owner, cuts = make_slabs(glob, nranks, halo)
+    new = SlabRank(glob, slabs[rank], device=device, max_contacts=max_contacts)
+    new.seed_contacts(contacts, inv_dt0)
+    arrived = int(np.sum([g not in old_mine for g in new.slab.global_ids[new.slab.owned_local].tolist()]))
+    return new, owner, cuts, arrived
 
 
 def scene_arrays(scene):
