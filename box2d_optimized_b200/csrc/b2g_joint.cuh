@@ -20,6 +20,8 @@
 #define B2G_JOINT_WELD 2u
 #define B2G_JOINT_PRISMATIC 3u
 #define B2G_JOINT_WHEEL 4u
+#define B2G_JOINT_FRICTION 5u
+#define B2G_JOINT_MOTOR_JOINT 6u
 
 // per-step work area of one joint (plain struct in global memory; one thread touches it)
 struct JointWork {
@@ -36,6 +38,8 @@ struct JointWork {
   float3 wex, wey, wez;
   // prismatic joint (b2_prismatic_joint.h:182-190): world axis and its perpendicular, their lever arms
   // (k11/k12/k22, axialMass and `angle` = translation are shared with the revolute fields)
+  // friction / motor joint (b2_friction_joint.h:103-104, b2_motor_joint.h:120-128): k11/k12/k22 = m_linearMass
+  // (symmetric), axialMass = m_angularMass, u = m_linearError, angle = m_angularError
   // wheel joint (b2_wheel_joint.h:219-229): axis = m_ax, perp = m_ay, a1/a2 = m_sAx/m_sBx, s1/s2 = m_sAy/m_sBy,
   // k11 = m_mass, dMass = m_motorMass, softMass = m_springMass, bias, gamma, angle = m_translation
   float2 axis, perp;
@@ -53,6 +57,10 @@ struct JointArraysDev {
   JointWork* work;
   float h;                 // this step's dt (soft constraints)
 };
+// friction joints: params0 = maxForce, maxTorque, 0, 0; params1 = 0, bits(flags | 5 << 8), 0, 0;
+// state = linearImpulse.x, linearImpulse.y, angularImpulse, -
+// motor joints: anchors = linearOffset.x, linearOffset.y, 0, 0; params0 = maxForce, maxTorque, correctionFactor,
+// angularOffset; params1 = 0, bits(flags | 6 << 8), 0, 0; state as the friction joint
 // wheel joints: params0 = stiffness, lowerTranslation, upperTranslation, maxMotorTorque;
 // params1 = motorSpeed, bits(flags | 4 << 8), localXAxisA.x, localXAxisA.y (as given: the reference does not
 // normalise it); params2 = damping, 0, 0, 0;
@@ -1127,6 +1135,125 @@ __device__ __forceinline__ bool wheel_solve_position(const JointArraysDev& J, in
   return linearError <= B2G_LINEAR_SLOP;
 }
 
+// ---- friction joint and motor joint: b2FrictionJoint / b2MotorJoint::{InitVelocityConstraints,
+// SolveVelocityConstraints} (src/dynamics/b2_friction_joint.cpp:65-181, b2_motor_joint.cpp:70-208): a clamped
+// angular row and a clamped 2-D linear row; the motor joint adds a position-error feed (correctionFactor) and
+// takes its lever arms from the linear offset.  Neither has a position solve (both return true). ------------
+template <bool MOTOR, class PosAccess, class VelAccess>
+__device__ __forceinline__ void drag_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+                                          const VelAccess& vel, const float4* __restrict__ bodyMass,
+                                          const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
+  JointWork w;
+  int2 bd = J.bodies[j];
+  float4 mAq = bodyMass[bd.x], mBq = bodyMass[bd.y];
+  float4 cAq = bodyCenter[bd.x], cBq = bodyCenter[bd.y];
+  w.ia = ia;
+  w.ib = ib;
+  w.mA = mAq.x; w.iA = mAq.y; w.mB = mBq.x; w.iB = mBq.y;
+  w.lcA = make_float2(cAq.x, cAq.y);
+  w.lcB = make_float2(cBq.x, cBq.y);
+  w.dMass = w.softMass = w.gamma = w.bias = w.currentLength = 0.0f;
+  w.wex = w.wey = w.wez = make_float3(0.0f, 0.0f, 0.0f);
+  w.axis = w.perp = make_float2(0.0f, 0.0f);
+  w.a1 = w.a2 = w.s1 = w.s2 = 0.0f;
+  float4 an = J.anchors[j], p0 = J.params0[j];
+  float4 pA = pos.load(ia), pB = pos.load(ib);
+  float4 vAq = vel.load(ia), vBq = vel.load(ib);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  Rot qA = rot_set(pA.z), qB = rot_set(pB.z);
+  if (MOTOR) {
+    w.rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+    w.rB = rot_mul(qB, -w.lcB);
+  } else {
+    w.rA = rot_mul(qA, make_float2(an.x, an.y) - w.lcA);
+    w.rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  }
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  {  // m_linearMass = K.GetInverse() (b2_math.h:204-216)
+    float a = mA + mB + iA * w.rA.y * w.rA.y + iB * w.rB.y * w.rB.y;
+    float b = -iA * w.rA.x * w.rA.y - iB * w.rB.x * w.rB.y;
+    float d = mA + mB + iA * w.rA.x * w.rA.x + iB * w.rB.x * w.rB.x;
+    float det = a * d - b * b;
+    if (det != 0.0f) det = 1.0f / det;
+    w.k11 = det * d;
+    w.k12 = -det * b;
+    w.k22 = det * a;
+  }
+  w.axialMass = iA + iB;
+  if (w.axialMass > 0.0f) w.axialMass = 1.0f / w.axialMass;
+  w.u = make_float2(0.0f, 0.0f);
+  w.angle = 0.0f;
+  if (MOTOR) {
+    float2 cA = make_float2(pA.x, pA.y), cB = make_float2(pB.x, pB.y);
+    w.u = cB + w.rB - cA - w.rA;
+    w.angle = pB.z - pA.z - p0.w;
+  }
+  float4 st = J.state[j];
+  if (warmStarting) {
+    st.x *= dtRatio;
+    st.y *= dtRatio;
+    st.z *= dtRatio;
+    float2 P = make_float2(st.x, st.y);
+    vA -= mA * P;
+    wA -= iA * (cross2(w.rA, P) + st.z);
+    vB += mB * P;
+    wB += iB * (cross2(w.rB, P) + st.z);
+  } else {
+    st = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  J.state[j] = st;
+  J.work[j] = w;
+  if (movable(mA, iA)) vel.store(ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <bool MOTOR, class VelAccess>
+__device__ __forceinline__ void drag_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float h,
+                                                    float inv_h) {
+  JointWork w = J.work[j];
+  float4 p0 = J.params0[j];
+  const float maxForce = p0.x, maxTorque = p0.y, correctionFactor = p0.z;
+  float4 st = J.state[j];
+  float4 vAq = vel.load(w.ia), vBq = vel.load(w.ib);
+  float2 vA = make_float2(vAq.x, vAq.y), vB = make_float2(vBq.x, vBq.y);
+  float wA = vAq.z, wB = vBq.z;
+  float mA = w.mA, mB = w.mB, iA = w.iA, iB = w.iB;
+  {  // angular row
+    float Cdot = wB - wA;
+    if (MOTOR) Cdot = Cdot + inv_h * correctionFactor * w.angle;
+    float impulse = -w.axialMass * Cdot;
+    float oldImpulse = st.z;
+    float maxImpulse = h * maxTorque;
+    st.z = clampf(st.z + impulse, -maxImpulse, maxImpulse);
+    impulse = st.z - oldImpulse;
+    wA -= iA * impulse;
+    wB += iB * impulse;
+  }
+  {  // linear rows
+    float2 Cdot = vB + cross_sv(wB, w.rB) - vA - cross_sv(wA, w.rA);
+    if (MOTOR) Cdot = Cdot + (inv_h * correctionFactor) * w.u;
+    float2 impulse = -make_float2(w.k11 * Cdot.x + w.k12 * Cdot.y, w.k12 * Cdot.x + w.k22 * Cdot.y);
+    float2 oldImpulse = make_float2(st.x, st.y);
+    float2 acc = oldImpulse + impulse;
+    float maxImpulse = h * maxForce;
+    if (dot2(acc, acc) > maxImpulse * maxImpulse) {
+      normalize2(acc);
+      acc = maxImpulse * acc;   // b2Vec2::operator*=(float): component * scalar
+    }
+    st.x = acc.x;
+    st.y = acc.y;
+    impulse = acc - oldImpulse;
+    vA -= mA * impulse;
+    wA -= iA * cross2(w.rA, impulse);
+    vB += mB * impulse;
+    wB += iB * cross2(w.rB, impulse);
+  }
+  J.state[j] = st;
+  if (movable(mA, iA)) vel.store(w.ia, make_float4(vA.x, vA.y, wA, vAq.w));
+  if (movable(mB, iB)) vel.store(w.ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
 // ---- dispatch on the joint type -------------------------------------------------------------------
 template <class PosAccess, class VelAccess>
 __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
@@ -1137,6 +1264,8 @@ __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int i
   else if (type == B2G_JOINT_WELD) weld_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_PRISMATIC) prismatic_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_WHEEL) wheel_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else if (type == B2G_JOINT_FRICTION) drag_init<false>(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else if (type == B2G_JOINT_MOTOR_JOINT) drag_init<true>(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else revolute_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
 }
 template <class VelAccess>
@@ -1147,6 +1276,8 @@ __device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, in
   else if (type == B2G_JOINT_WELD) weld_solve_velocity(J, j, vel);
   else if (type == B2G_JOINT_PRISMATIC) prismatic_solve_velocity(J, j, vel, dt, inv_dt);
   else if (type == B2G_JOINT_WHEEL) wheel_solve_velocity(J, j, vel, dt, inv_dt);
+  else if (type == B2G_JOINT_FRICTION) drag_solve_velocity<false>(J, j, vel, dt, inv_dt);
+  else if (type == B2G_JOINT_MOTOR_JOINT) drag_solve_velocity<true>(J, j, vel, dt, inv_dt);
   else revolute_solve_velocity(J, j, vel, dt, inv_dt);
 }
 template <class PosAccess>
@@ -1156,6 +1287,7 @@ __device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, in
   if (type == B2G_JOINT_WELD) return weld_solve_position(J, j, pos);
   if (type == B2G_JOINT_PRISMATIC) return prismatic_solve_position(J, j, pos);
   if (type == B2G_JOINT_WHEEL) return wheel_solve_position(J, j, pos);
+  if (type == B2G_JOINT_FRICTION || type == B2G_JOINT_MOTOR_JOINT) return true;
   return revolute_solve_position(J, j, pos);
 }
 #endif

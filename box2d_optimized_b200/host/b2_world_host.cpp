@@ -626,8 +626,9 @@ void b2World::DestroyBody(b2Body* b) {
 b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   if (IsLocked()) return nullptr;
   if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint &&
-      def->type != e_prismaticJoint && def->type != e_wheelJoint) {
-    fprintf(stderr, "[b2cuda] only revolute, distance, weld, prismatic and wheel joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
+      def->type != e_prismaticJoint && def->type != e_wheelJoint && def->type != e_frictionJoint &&
+      def->type != e_motorJoint) {
+    fprintf(stderr, "[b2cuda] only revolute, distance, weld, prismatic, wheel, friction and motor joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
             (int)def->type);
     return nullptr;
   }
@@ -637,6 +638,8 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
   else if (def->type == e_prismaticJoint) j = new b2PrismaticJoint(static_cast<const b2PrismaticJointDef*>(def));
   else if (def->type == e_wheelJoint) j = new b2WheelJoint(static_cast<const b2WheelJointDef*>(def));
+  else if (def->type == e_frictionJoint) j = new b2FrictionJoint(static_cast<const b2FrictionJointDef*>(def));
+  else if (def->type == e_motorJoint) j = new b2MotorJoint(static_cast<const b2MotorJointDef*>(def));
   else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
   j->m_index = (int32)m_impl->joints.size();
   m_impl->joints.push_back(j);
@@ -1492,6 +1495,114 @@ void b2PrismaticJoint::SetMaxMotorForce(float force) {
   if (force == m_maxMotorForce) return;
   Touch();
   m_maxMotorForce = force;
+}
+
+// ---- b2FrictionJoint (b2_friction_joint.cpp:39-63, 183-226) -------------------------------------------
+void b2FrictionJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor) {
+  bodyA = bA;
+  bodyB = bB;
+  localAnchorA = bodyA->GetLocalPoint(anchor);
+  localAnchorB = bodyB->GetLocalPoint(anchor);
+}
+b2FrictionJoint::b2FrictionJoint(const b2FrictionJointDef* def) : b2Joint(def) {
+  m_localAnchorA = def->localAnchorA;
+  m_localAnchorB = def->localAnchorB;
+  m_linearImpulse.SetZero();
+  m_angularImpulse = 0.0f;
+  m_maxForce = def->maxForce;
+  m_maxTorque = def->maxTorque;
+}
+void b2FrictionJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_localAnchorA.x; anchors[1] = m_localAnchorA.y; anchors[2] = m_localAnchorB.x; anchors[3] = m_localAnchorB.y;
+  p[0] = m_maxForce; p[1] = m_maxTorque; p[2] = p[3] = p[4] = 0.0f;
+  uint32_t fl = (m_collideConnected ? 4u : 0u) | (5u << 8);  // type 5
+  memcpy(&p[5], &fl, 4);
+  for (int k = 6; k < 12; ++k) p[k] = 0.0f;
+  st[0] = m_linearImpulse.x; st[1] = m_linearImpulse.y; st[2] = m_angularImpulse; st[3] = st[4] = 0.0f;
+}
+void b2FrictionJoint::ReadDeviceState(const float* st) {
+  m_linearImpulse.Set(st[0], st[1]);
+  m_angularImpulse = st[2];
+}
+b2Vec2 b2FrictionJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2FrictionJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+b2Vec2 b2FrictionJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_linearImpulse;
+}
+float b2FrictionJoint::GetReactionTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_angularImpulse;
+}
+void b2FrictionJoint::SetMaxForce(float force) {
+  Touch(false);  // the reference's setters do not wake the bodies
+  m_maxForce = force;
+}
+void b2FrictionJoint::SetMaxTorque(float torque) {
+  Touch(false);
+  m_maxTorque = torque;
+}
+
+// ---- b2MotorJoint (b2_motor_joint.cpp:40-68, 210-297) -------------------------------------------------
+void b2MotorJointDef::Initialize(b2Body* bA, b2Body* bB) {
+  bodyA = bA;
+  bodyB = bB;
+  b2Vec2 xB = bodyB->GetPosition();
+  linearOffset = bodyA->GetLocalPoint(xB);
+  angularOffset = bodyB->GetAngle() - bodyA->GetAngle();
+}
+b2MotorJoint::b2MotorJoint(const b2MotorJointDef* def) : b2Joint(def) {
+  m_linearOffset = def->linearOffset;
+  m_angularOffset = def->angularOffset;
+  m_linearImpulse.SetZero();
+  m_angularImpulse = 0.0f;
+  m_maxForce = def->maxForce;
+  m_maxTorque = def->maxTorque;
+  m_correctionFactor = def->correctionFactor;
+}
+void b2MotorJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_linearOffset.x; anchors[1] = m_linearOffset.y; anchors[2] = anchors[3] = 0.0f;
+  p[0] = m_maxForce; p[1] = m_maxTorque; p[2] = m_correctionFactor; p[3] = m_angularOffset; p[4] = 0.0f;
+  uint32_t fl = (m_collideConnected ? 4u : 0u) | (6u << 8);  // type 6
+  memcpy(&p[5], &fl, 4);
+  for (int k = 6; k < 12; ++k) p[k] = 0.0f;
+  st[0] = m_linearImpulse.x; st[1] = m_linearImpulse.y; st[2] = m_angularImpulse; st[3] = st[4] = 0.0f;
+}
+void b2MotorJoint::ReadDeviceState(const float* st) {
+  m_linearImpulse.Set(st[0], st[1]);
+  m_angularImpulse = st[2];
+}
+b2Vec2 b2MotorJoint::GetAnchorA() const { return m_bodyA->GetPosition(); }
+b2Vec2 b2MotorJoint::GetAnchorB() const { return m_bodyB->GetPosition(); }
+b2Vec2 b2MotorJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_linearImpulse;
+}
+float b2MotorJoint::GetReactionTorque(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_angularImpulse;
+}
+void b2MotorJoint::SetLinearOffset(const b2Vec2& linearOffset) {
+  if (linearOffset.x == m_linearOffset.x && linearOffset.y == m_linearOffset.y) return;
+  Touch();
+  m_linearOffset = linearOffset;
+}
+void b2MotorJoint::SetAngularOffset(float angularOffset) {
+  if (angularOffset == m_angularOffset) return;
+  Touch();
+  m_angularOffset = angularOffset;
+}
+void b2MotorJoint::SetMaxForce(float force) {
+  Touch(false);
+  m_maxForce = force;
+}
+void b2MotorJoint::SetMaxTorque(float torque) {
+  Touch(false);
+  m_maxTorque = torque;
+}
+void b2MotorJoint::SetCorrectionFactor(float factor) {
+  Touch(false);
+  m_correctionFactor = factor;
 }
 
 // ---- b2WheelJoint (b2_wheel_joint.cpp:40-85, 448-628) -------------------------------------------------

@@ -558,6 +558,99 @@ class b2PrismaticJoint : public b2Joint {
   mutable float m_upperImpulse;
 };
 
+/// b2_friction_joint.h:30-118: top-down friction between two bodies (clamped linear and angular drag)
+struct b2FrictionJointDef : public b2JointDef {
+  b2FrictionJointDef() {
+    type = e_frictionJoint;
+    localAnchorA.Set(0.0f, 0.0f);
+    localAnchorB.Set(0.0f, 0.0f);
+    maxForce = 0.0f;
+    maxTorque = 0.0f;
+  }
+  void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec2& anchor);
+  b2Vec2 localAnchorA;
+  b2Vec2 localAnchorB;
+  float maxForce;
+  float maxTorque;
+};
+
+class b2FrictionJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  const b2Vec2& GetLocalAnchorA() const { return m_localAnchorA; }
+  const b2Vec2& GetLocalAnchorB() const { return m_localAnchorB; }
+  void SetMaxForce(float force);
+  float GetMaxForce() const { return m_maxForce; }
+  void SetMaxTorque(float torque);
+  float GetMaxTorque() const { return m_maxTorque; }
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2FrictionJoint(const b2FrictionJointDef* def);
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+  b2Vec2 m_localAnchorA;
+  b2Vec2 m_localAnchorB;
+  float m_maxForce;
+  float m_maxTorque;
+  mutable b2Vec2 m_linearImpulse;
+  mutable float m_angularImpulse;
+};
+
+/// b2_motor_joint.h:30-133: drives bodyB to a linear / angular offset from bodyA with bounded force
+struct b2MotorJointDef : public b2JointDef {
+  b2MotorJointDef() {
+    type = e_motorJoint;
+    linearOffset.Set(0.0f, 0.0f);
+    angularOffset = 0.0f;
+    maxForce = 1.0f;
+    maxTorque = 1.0f;
+    correctionFactor = 0.3f;
+  }
+  void Initialize(b2Body* bodyA, b2Body* bodyB);
+  b2Vec2 linearOffset;
+  float angularOffset;
+  float maxForce;
+  float maxTorque;
+  float correctionFactor;
+};
+
+class b2MotorJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  void SetLinearOffset(const b2Vec2& linearOffset);
+  const b2Vec2& GetLinearOffset() const { return m_linearOffset; }
+  void SetAngularOffset(float angularOffset);
+  float GetAngularOffset() const { return m_angularOffset; }
+  void SetMaxForce(float force);
+  float GetMaxForce() const { return m_maxForce; }
+  void SetMaxTorque(float torque);
+  float GetMaxTorque() const { return m_maxTorque; }
+  void SetCorrectionFactor(float factor);
+  float GetCorrectionFactor() const { return m_correctionFactor; }
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2MotorJoint(const b2MotorJointDef* def);
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+  b2Vec2 m_linearOffset;
+  float m_angularOffset;
+  float m_maxForce;
+  float m_maxTorque;
+  float m_correctionFactor;
+  mutable b2Vec2 m_linearImpulse;
+  mutable float m_angularImpulse;
+};
+
 /// b2_wheel_joint.h:30-231: a point of bodyB rides on a line fixed in bodyA (suspension spring along the
 /// line, optional translation limits) and rotates freely, optionally driven by a motor
 struct b2WheelJointDef : public b2JointDef {

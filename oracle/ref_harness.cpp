@@ -184,6 +184,12 @@ int b2ref_get_joint_state(void* h, int cap, float* out) {
     } else if ((*it)->GetType() == e_weldJoint) {  // b2_weld_joint.h:112
       b2WeldJoint* wj = static_cast<b2WeldJoint*>(*it);
       o[0] = wj->m_impulse.x; o[1] = wj->m_impulse.y; o[2] = wj->m_impulse.z; o[3] = 0.0f; o[4] = 0.0f;
+    } else if ((*it)->GetType() == e_frictionJoint) {  // b2_friction_joint.h:86-87
+      b2FrictionJoint* fj = static_cast<b2FrictionJoint*>(*it);
+      o[0] = fj->m_linearImpulse.x; o[1] = fj->m_linearImpulse.y; o[2] = fj->m_angularImpulse; o[3] = 0.0f; o[4] = 0.0f;
+    } else if ((*it)->GetType() == e_motorJoint) {  // b2_motor_joint.h:104-105
+      b2MotorJoint* mj = static_cast<b2MotorJoint*>(*it);
+      o[0] = mj->m_linearImpulse.x; o[1] = mj->m_linearImpulse.y; o[2] = mj->m_angularImpulse; o[3] = 0.0f; o[4] = 0.0f;
     } else if ((*it)->GetType() == e_wheelJoint) {  // b2_wheel_joint.h:196-200
       b2WheelJoint* wh = static_cast<b2WheelJoint*>(*it);
       o[0] = wh->m_impulse; o[1] = wh->m_springImpulse; o[2] = wh->m_motorImpulse; o[3] = wh->m_lowerImpulse; o[4] = wh->m_upperImpulse;
@@ -219,7 +225,8 @@ int b2ref_next_step_joint_order(void* h, int cap, int* out) {
     int n = 0;
     for (auto it = js.rbegin(); it != js.rend(); ++it)
       if ((*it)->GetType() == e_revoluteJoint || (*it)->GetType() == e_distanceJoint || (*it)->GetType() == e_weldJoint ||
-          (*it)->GetType() == e_prismaticJoint || (*it)->GetType() == e_wheelJoint)
+          (*it)->GetType() == e_prismaticJoint || (*it)->GetType() == e_wheelJoint ||
+          (*it)->GetType() == e_frictionJoint || (*it)->GetType() == e_motorJoint)
         jointIndex[*it] = n++;
   }
   std::unordered_map<const b2Body*, bool> bodySeen;

@@ -252,6 +252,9 @@ int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->Get
 //   revolute: referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
 //   distance: length, minLength, maxLength, stiffness, damping, bits(flags | 1 << 8), 0, 0
 //   weld:     referenceAngle, stiffness, damping, 0, 0, bits(flags | 2 << 8), 0, 0
+//   friction: maxForce, maxTorque, 0, 0, 0, bits(flags | 5 << 8), 0...
+//   motor:    maxForce, maxTorque, correctionFactor, angularOffset, 0, bits(flags | 6 << 8), 0...;
+//             anchors = linearOffset.xy, 0, 0
 //   wheel:    stiffness, lowerTranslation, upperTranslation, maxMotorTorque, motorSpeed, bits(flags | 4 << 8),
 //             localAxisA.x, localAxisA.y, damping, 0, 0, 0
 //   prismatic: referenceAngle, lowerTranslation, upperTranslation, maxMotorForce, motorSpeed,
@@ -288,6 +291,19 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
       anchors[4 * n + 2] = wj->GetLocalAnchorB().x; anchors[4 * n + 3] = wj->GetLocalAnchorB().y;
       p[0] = wj->GetReferenceAngle(); p[1] = wj->GetStiffness(); p[2] = wj->GetDamping(); p[3] = 0.0f; p[4] = 0.0f;
       fl |= 2u << 8;
+    } else if (j->GetType() == e_frictionJoint) {
+      b2FrictionJoint* fj = static_cast<b2FrictionJoint*>(j);
+      anchors[4 * n] = fj->GetLocalAnchorA().x; anchors[4 * n + 1] = fj->GetLocalAnchorA().y;
+      anchors[4 * n + 2] = fj->GetLocalAnchorB().x; anchors[4 * n + 3] = fj->GetLocalAnchorB().y;
+      p[0] = fj->GetMaxForce(); p[1] = fj->GetMaxTorque(); p[2] = p[3] = p[4] = 0.0f;
+      fl |= 5u << 8;
+    } else if (j->GetType() == e_motorJoint) {
+      b2MotorJoint* mj = static_cast<b2MotorJoint*>(j);
+      anchors[4 * n] = mj->GetLinearOffset().x; anchors[4 * n + 1] = mj->GetLinearOffset().y;
+      anchors[4 * n + 2] = anchors[4 * n + 3] = 0.0f;
+      p[0] = mj->GetMaxForce(); p[1] = mj->GetMaxTorque(); p[2] = mj->GetCorrectionFactor(); p[3] = mj->GetAngularOffset();
+      p[4] = 0.0f;
+      fl |= 6u << 8;
     } else if (j->GetType() == e_wheelJoint) {
       b2WheelJoint* wh = static_cast<b2WheelJoint*>(j);
       anchors[4 * n] = wh->GetLocalAnchorA().x; anchors[4 * n + 1] = wh->GetLocalAnchorA().y;

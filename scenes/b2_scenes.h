@@ -12,6 +12,8 @@
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
 //   welds          weld joints: cantilever beams, a welded compound (b2_weld_joint.cpp)
 //   cars           wheel joints: sprung, motorised cars driving over ramps and loose boxes (b2_wheel_joint.cpp)
+//   drags          friction joints (braked falling / spinning boxes) and motor joints (platforms driven to an
+//                  offset, carrying boxes) (b2_friction_joint.cpp, b2_motor_joint.cpp)
 //   sliders        prismatic joints: motorised pistons, limited rails, a free slider (b2_prismatic_joint.cpp)
 //   springs        distance joints: rods, springs, limited ropes (b2_distance_joint.cpp)
 //   sensors        sensor zones / paddle / probes in a rain of shapes (b2TestOverlap path)
@@ -381,6 +383,65 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
         cd.allowSleep = seed == 0 ? false : true;
         s->addFixture(s->addBody(cd), crate, 0.5f);
       }
+    }
+  } else if (name == "drags") {
+    // friction joints (b2_friction_joint.cpp:65-181): boxes tied to the ground by a force / torque budget —
+    // below their weight (they sink slowly, spinning down), above it (they hang), off-centre anchors; motor
+    // joints (b2_motor_joint.cpp:70-208): platforms pulled to a linear + angular offset with bounded force,
+    // soft and stiff correction factors, loose boxes dropped onto them, one platform riding on another
+    int n = size > 0 ? size : 6;
+    b2BodyDef gd;
+    b2Body* ground = s->addBody(gd);
+    b2EdgeShape edge;
+    edge.SetTwoSided(b2Vec2(-60.0f, 0.0f), b2Vec2(60.0f, 0.0f));
+    s->addFixture(ground, edge, 0.0f);
+    b2PolygonShape box;
+    box.SetAsBox(0.5f, 0.5f);
+    b2PolygonShape plate;
+    plate.SetAsBox(1.2f, 0.15f);
+    b2CircleShape ball;
+    ball.m_radius = 0.3f;
+    for (int i = 0; i < n; ++i) {  // braked boxes, mass 1
+      float x = -20.0f + 2.5f * (float)i;
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(x, 6.0f + 0.5f * (float)(i % 3));
+      bd.angularVelocity = 4.0f - 1.5f * (float)i;
+      bd.linearVelocity.Set(1.0f - 0.5f * (float)(i % 4), 0.0f);
+      b2Body* body = s->addBody(bd);
+      s->addFixture(body, box, 1.0f);
+      b2FrictionJointDef jd;
+      jd.Initialize(ground, body, b2Vec2(x + 0.2f * (float)(i % 2), bd.position.y));
+      jd.maxForce = 4.0f + 2.5f * (float)i;      // weight is 10: the first ones sink, the last ones hang
+      jd.maxTorque = 0.5f * (float)(i + 1);
+      jd.collideConnected = true;
+      s->world->CreateJoint(&jd);
+    }
+    b2Body* prevPlatform = nullptr;
+    for (int i = 0; i < n; ++i) {  // driven platforms
+      float x = 0.0f + 4.0f * (float)i;
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(x, 2.0f);
+      b2Body* platform = s->addBody(bd);
+      s->addFixture(platform, plate, 2.0f);
+      b2MotorJointDef jd;
+      b2Body* base = (i % 3 == 2 && prevPlatform) ? prevPlatform : ground;
+      jd.Initialize(base, platform);
+      jd.linearOffset += b2Vec2(0.5f, 1.5f);            // target: up and to the right of where it starts
+      jd.angularOffset = 0.15f * (float)(i % 3) - 0.15f;
+      jd.maxForce = 150.0f + 50.0f * (float)i;
+      jd.maxTorque = 100.0f;
+      jd.correctionFactor = (i % 2) ? 0.9f : 0.3f;
+      jd.collideConnected = true;
+      s->world->CreateJoint(&jd);
+      b2BodyDef cd;
+      cd.type = b2_dynamicBody;
+      cd.position.Set(x - 0.4f, 3.2f);
+      s->addFixture(s->addBody(cd), box, 1.0f);
+      cd.position.Set(x + 0.6f, 3.0f);
+      s->addFixture(s->addBody(cd), ball, 1.0f);
+      prevPlatform = platform;
     }
   } else if (name == "sliders") {
     // prismatic joints (b2_prismatic_joint.cpp:114-451) in their regimes: a motorised piston pushing a

@@ -649,6 +649,76 @@ static void wheel_joint_api() {
          j->GetJointTranslation());
 }
 
+// friction joint: a puck sliding in a world without gravity is braked by exactly maxForce and stops;
+// motor joint: a body is pulled to a linear and angular offset and held there against gravity
+static void friction_and_motor_joint_api() {
+  {
+    b2World world(b2Vec2(0.0f, 0.0f));
+    b2BodyDef gd;
+    b2Body* ground = world.CreateBody(&gd);
+    b2PolygonShape box;
+    box.SetAsBox(0.5f, 0.5f);
+    b2BodyDef bd;
+    bd.type = b2_dynamicBody;
+    bd.position.Set(0.0f, 0.0f);
+    bd.linearVelocity.Set(5.0f, 0.0f);
+    bd.angularVelocity = 2.0f;
+    b2Body* puck = world.CreateBody(&bd);
+    puck->CreateFixture(&box, 1.0f);   // mass 1, inertia 1/6
+    b2FrictionJointDef jd;
+    jd.Initialize(ground, puck, puck->GetPosition());
+    jd.maxForce = 10.0f;
+    jd.maxTorque = 1.0f;
+    b2FrictionJoint* j = static_cast<b2FrictionJoint*>(world.CreateJoint(&jd));
+    CHECK(j != nullptr && j->GetMaxForce() == 10.0f && j->GetMaxTorque() == 1.0f);
+    world.Step(1.0f / 60.0f, 8, 3);
+    b2Vec2 F = j->GetReactionForce(60.0f);
+    CHECK(fabsf(F.x + 10.0f) < 1e-3f && fabsf(F.y) < 1e-3f);                 // braking with the whole budget
+    CHECK(fabsf(puck->GetLinearVelocity().x - (5.0f - 10.0f / 60.0f)) < 1e-4f);
+    for (int i = 0; i < 59; ++i) world.Step(1.0f / 60.0f, 8, 3);
+    CHECK(fabsf(puck->GetLinearVelocity().x) < 1e-4f && fabsf(puck->GetAngularVelocity()) < 1e-4f);
+    CHECK(fabsf(puck->GetPosition().x - 1.2083f) < 0.01f);                   // v0^2 / (2 a), semi-implicit
+    j->SetMaxForce(0.0f);
+    j->SetMaxTorque(0.0f);
+    puck->SetLinearVelocity(b2Vec2(1.0f, 0.0f));
+    for (int i = 0; i < 60; ++i) world.Step(1.0f / 60.0f, 8, 3);
+    CHECK(fabsf(puck->GetLinearVelocity().x - 1.0f) < 1e-5f);                // no budget, no braking
+    printf("friction: F=(%.4f, %.4f) stop at x=%.4f\n", F.x, F.y, puck->GetPosition().x - 1.0f);
+  }
+  {
+    b2World world(b2Vec2(0.0f, -10.0f));
+    b2BodyDef gd;
+    b2Body* ground = world.CreateBody(&gd);
+    b2PolygonShape box;
+    box.SetAsBox(0.5f, 0.5f);
+    b2BodyDef bd;
+    bd.type = b2_dynamicBody;
+    bd.position.Set(0.0f, 4.0f);
+    b2Body* body = world.CreateBody(&bd);
+    body->CreateFixture(&box, 2.0f);   // mass 2
+    b2MotorJointDef jd;
+    jd.Initialize(ground, body);
+    CHECK(jd.linearOffset.x == 0.0f && jd.linearOffset.y == 4.0f && jd.angularOffset == 0.0f);
+    jd.maxForce = 1000.0f;
+    jd.maxTorque = 1000.0f;
+    b2MotorJoint* j = static_cast<b2MotorJoint*>(world.CreateJoint(&jd));
+    CHECK(j != nullptr && j->GetCorrectionFactor() == 0.3f);
+    j->SetLinearOffset(b2Vec2(2.0f, 5.0f));
+    j->SetAngularOffset(1.0f);
+    for (int i = 0; i < 180; ++i) world.Step(1.0f / 60.0f, 8, 3);
+    b2Vec2 p = body->GetPosition();
+    CHECK(fabsf(p.x - 2.0f) < 0.01f && fabsf(p.y - 5.0f) < 0.02f && fabsf(body->GetAngle() - 1.0f) < 0.01f);
+    b2Vec2 F = j->GetReactionForce(60.0f);
+    CHECK(fabsf(F.y - 20.0f) < 0.2f && fabsf(F.x) < 0.2f);                   // holds the weight
+    j->SetMaxForce(5.0f);                                                     // a quarter of the weight: it falls
+    body->SetAwake(true);                                                     // (the setter does not wake it)
+    for (int i = 0; i < 60; ++i) world.Step(1.0f / 60.0f, 8, 3);
+    CHECK(body->GetPosition().y < 2.0f);
+    printf("motor: at (%.4f, %.4f) angle %.4f F=(%.4f, %.4f) then y=%.4f\n", p.x, p.y, body->GetAngle(), F.x, F.y,
+           body->GetPosition().y);
+  }
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -661,6 +731,7 @@ int main() {
   weld_joint_api();
   prismatic_joint_api();
   wheel_joint_api();
+  friction_and_motor_joint_api();
   contact_buffers_grow();
   world_editing_session();
   user_contact_filter();

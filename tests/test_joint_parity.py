@@ -102,9 +102,10 @@ def test_long_chain_has_no_joint_capacity(require_ref):
                                                        # the welded beams (bodies 1-12); the loose compound that
                                                        # tumbles off them lands somewhere else in every solver order
                                                        ("welds", 6, 240, 0.3, 13),
-                                                       ("sliders", 6, 240, 0.05, None), ("cars", 4, 240, 0.6, None)])
+                                                       ("sliders", 6, 240, 0.05, None), ("cars", 4, 240, 0.6, None),
+                                                       ("drags", 6, 240, 0.3, None)])
 def test_jointed_scenes_run_free_in_the_production_mode(require_ref, name, size, steps, tol, gated):
-    """Distance, weld, prismatic and wheel joints through the FUSED per-island kernel (shared-memory tile
+    """Distance, weld, prismatic, wheel, friction and motor joints through the FUSED per-island kernel (shared-memory tile
     accessors, coloured contacts, joints walked by the tile's serial thread) — the sequential parity test
     runs the same device functions through the global-memory accessors only.  Free running against the
     reference's CPU Step: contact order differs (colours vs DFS), so an outcome gate: every body stays
