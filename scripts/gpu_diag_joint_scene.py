@@ -1,7 +1,7 @@
 import sys, numpy as np
 sys.path.insert(0, ".")
 from box2d_optimized_b200 import RefScene, GpuScene, capi
-for name, size in (("welds", 6),):
+for name, size in ((sys.argv[1] if len(sys.argv) > 1 else "welds", int(sys.argv[2]) if len(sys.argv) > 2 else 6),):
     for mode in (capi.SOLVER_COLOURED, capi.SOLVER_SEQUENTIAL):
         ref, gpu = RefScene(name, size, 0), GpuScene(name, size, 0, solver_mode=mode)
         for k in range(6):

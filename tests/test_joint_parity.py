@@ -103,7 +103,11 @@ def test_long_chain_has_no_joint_capacity(require_ref):
                                                        # tumbles off them lands somewhere else in every solver order
                                                        ("welds", 6, 240, 0.3, 13),
                                                        ("sliders", 6, 240, 0.05, None), ("cars", 4, 240, 0.6, None),
-                                                       ("drags", 6, 240, 0.3, None)])
+                                                       # the six braked boxes and the first platform; the boxes and
+                                                       # balls dropped on the platforms roll off differently in every
+                                                       # solver order (the sequential mode, bit-exact when teacher
+                                                       # forced, drifts from the reference by the same 0.5-0.8 m)
+                                                       ("drags", 6, 240, 0.05, 8)])
 def test_jointed_scenes_run_free_in_the_production_mode(require_ref, name, size, steps, tol, gated):
     """Distance, weld, prismatic, wheel, friction and motor joints through the FUSED per-island kernel (shared-memory tile
     accessors, coloured contacts, joints walked by the tile's serial thread) — the sequential parity test
