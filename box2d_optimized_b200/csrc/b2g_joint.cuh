@@ -22,6 +22,7 @@
 #define B2G_JOINT_WHEEL 4u
 #define B2G_JOINT_FRICTION 5u
 #define B2G_JOINT_MOTOR_JOINT 6u
+#define B2G_JOINT_MOUSE 7u
 
 // per-step work area of one joint (plain struct in global memory; one thread touches it)
 struct JointWork {
@@ -57,6 +58,8 @@ struct JointArraysDev {
   JointWork* work;
   float h;                 // this step's dt (soft constraints)
 };
+// mouse joints: anchors = targetA.x, targetA.y, localAnchorB.x, localAnchorB.y; params0 = maxForce, stiffness,
+// damping, 0; params1 = 0, bits(flags | 7 << 8), 0, 0; state = impulse.x, impulse.y, -, -.  Only bodyB is moved.
 // friction joints: params0 = maxForce, maxTorque, 0, 0; params1 = 0, bits(flags | 5 << 8), 0, 0;
 // state = linearImpulse.x, linearImpulse.y, angularImpulse, -
 // motor joints: anchors = linearOffset.x, linearOffset.y, 0, 0; params0 = maxForce, maxTorque, correctionFactor,
@@ -1254,6 +1257,99 @@ __device__ __forceinline__ void drag_solve_velocity(const JointArraysDev& J, int
   if (movable(mB, iB)) vel.store(w.ib, make_float4(vB.x, vB.y, wB, vBq.w));
 }
 
+// ---- mouse joint: b2MouseJoint::{InitVelocityConstraints, SolveVelocityConstraints}
+// (src/dynamics/b2_mouse_joint.cpp:77-160): a soft point constraint dragging bodyB's anchor to a world
+// target with bounded force; bodyA takes no part in the arithmetic -------------------------------------------
+template <class PosAccess, class VelAccess>
+__device__ __forceinline__ void mouse_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
+                                           const VelAccess& vel, const float4* __restrict__ bodyMass,
+                                           const float4* __restrict__ bodyCenter, float dtRatio, bool warmStarting) {
+  JointWork w;
+  int2 bd = J.bodies[j];
+  float4 mBq = bodyMass[bd.y];
+  float4 cBq = bodyCenter[bd.y];
+  w.ia = ia;
+  w.ib = ib;
+  w.mA = 0.0f; w.iA = 0.0f; w.mB = mBq.x; w.iB = mBq.y;
+  w.lcA = make_float2(0.0f, 0.0f);
+  w.lcB = make_float2(cBq.x, cBq.y);
+  w.rA = make_float2(0.0f, 0.0f);
+  w.axialMass = w.angle = 0.0f;
+  w.dMass = w.softMass = w.currentLength = 0.0f;
+  w.wex = w.wey = w.wez = make_float3(0.0f, 0.0f, 0.0f);
+  w.axis = w.perp = make_float2(0.0f, 0.0f);
+  w.a1 = w.a2 = w.s1 = w.s2 = 0.0f;
+  float4 an = J.anchors[j], p0 = J.params0[j];
+  const float k = p0.y, d = p0.z;
+  float4 pB = pos.load(ib);
+  float4 vBq = vel.load(ib);
+  float2 cB = make_float2(pB.x, pB.y);
+  float2 vB = make_float2(vBq.x, vBq.y);
+  float wB = vBq.z;
+  Rot qB = rot_set(pB.z);
+  float h = J.h;
+  w.gamma = h * (d + h * k);
+  if (w.gamma != 0.0f) w.gamma = 1.0f / w.gamma;
+  w.bias = h * k * w.gamma;  // m_beta
+  w.rB = rot_mul(qB, make_float2(an.z, an.w) - w.lcB);
+  {  // m_mass = K.GetInverse()
+    float a = w.mB + w.iB * w.rB.y * w.rB.y + w.gamma;
+    float b = -w.iB * w.rB.x * w.rB.y;
+    float dd = w.mB + w.iB * w.rB.x * w.rB.x + w.gamma;
+    float det = a * dd - b * b;
+    if (det != 0.0f) det = 1.0f / det;
+    w.k11 = det * dd;
+    w.k12 = -det * b;
+    w.k22 = det * a;
+  }
+  w.u = cB + w.rB - make_float2(an.x, an.y);  // m_C
+  w.u.x *= w.bias;
+  w.u.y *= w.bias;
+  wB *= 0.98f;  // cheat with some damping
+  float4 st = J.state[j];
+  if (warmStarting) {
+    st.x *= dtRatio;
+    st.y *= dtRatio;
+    float2 P = make_float2(st.x, st.y);
+    vB += w.mB * P;
+    wB += w.iB * cross2(w.rB, P);
+  } else {
+    st = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  J.state[j] = st;
+  J.work[j] = w;
+  // the reference writes bodyB's velocity back unconditionally; a body without mass keeps it too
+  vel.store(ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
+template <class VelAccess>
+__device__ __forceinline__ void mouse_solve_velocity(const JointArraysDev& J, int j, const VelAccess& vel, float h) {
+  JointWork w = J.work[j];
+  const float maxForce = J.params0[j].x;
+  float4 st = J.state[j];
+  float4 vBq = vel.load(w.ib);
+  float2 vB = make_float2(vBq.x, vBq.y);
+  float wB = vBq.z;
+  float2 Cdot = vB + cross_sv(wB, w.rB);
+  float2 imp0 = make_float2(st.x, st.y);
+  float2 t = -(Cdot + w.u + w.gamma * imp0);
+  float2 impulse = make_float2(w.k11 * t.x + w.k12 * t.y, w.k12 * t.x + w.k22 * t.y);
+  float2 acc = imp0 + impulse;
+  float maxImpulse = h * maxForce;
+  if (dot2(acc, acc) > maxImpulse * maxImpulse) {
+    float s = maxImpulse / len2(acc);
+    acc.x *= s;
+    acc.y *= s;
+  }
+  st.x = acc.x;
+  st.y = acc.y;
+  impulse = acc - imp0;
+  vB += w.mB * impulse;
+  wB += w.iB * cross2(w.rB, impulse);
+  J.state[j] = st;
+  vel.store(w.ib, make_float4(vB.x, vB.y, wB, vBq.w));
+}
+
 // ---- dispatch on the joint type -------------------------------------------------------------------
 template <class PosAccess, class VelAccess>
 __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int ia, int ib, const PosAccess& pos,
@@ -1264,6 +1360,7 @@ __device__ __forceinline__ void joint_init(const JointArraysDev& J, int j, int i
   else if (type == B2G_JOINT_WELD) weld_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_PRISMATIC) prismatic_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_WHEEL) wheel_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
+  else if (type == B2G_JOINT_MOUSE) mouse_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_FRICTION) drag_init<false>(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else if (type == B2G_JOINT_MOTOR_JOINT) drag_init<true>(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
   else revolute_init(J, j, ia, ib, pos, vel, bodyMass, bodyCenter, dtRatio, warmStarting);
@@ -1276,6 +1373,7 @@ __device__ __forceinline__ void joint_solve_velocity(const JointArraysDev& J, in
   else if (type == B2G_JOINT_WELD) weld_solve_velocity(J, j, vel);
   else if (type == B2G_JOINT_PRISMATIC) prismatic_solve_velocity(J, j, vel, dt, inv_dt);
   else if (type == B2G_JOINT_WHEEL) wheel_solve_velocity(J, j, vel, dt, inv_dt);
+  else if (type == B2G_JOINT_MOUSE) mouse_solve_velocity(J, j, vel, dt);
   else if (type == B2G_JOINT_FRICTION) drag_solve_velocity<false>(J, j, vel, dt, inv_dt);
   else if (type == B2G_JOINT_MOTOR_JOINT) drag_solve_velocity<true>(J, j, vel, dt, inv_dt);
   else revolute_solve_velocity(J, j, vel, dt, inv_dt);
@@ -1287,7 +1385,7 @@ __device__ __forceinline__ bool joint_solve_position(const JointArraysDev& J, in
   if (type == B2G_JOINT_WELD) return weld_solve_position(J, j, pos);
   if (type == B2G_JOINT_PRISMATIC) return prismatic_solve_position(J, j, pos);
   if (type == B2G_JOINT_WHEEL) return wheel_solve_position(J, j, pos);
-  if (type == B2G_JOINT_FRICTION || type == B2G_JOINT_MOTOR_JOINT) return true;
+  if (type == B2G_JOINT_FRICTION || type == B2G_JOINT_MOTOR_JOINT || type == B2G_JOINT_MOUSE) return true;
   return revolute_solve_position(J, j, pos);
 }
 #endif

@@ -627,8 +627,8 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   if (IsLocked()) return nullptr;
   if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint &&
       def->type != e_prismaticJoint && def->type != e_wheelJoint && def->type != e_frictionJoint &&
-      def->type != e_motorJoint) {
-    fprintf(stderr, "[b2cuda] only revolute, distance, weld, prismatic, wheel, friction and motor joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
+      def->type != e_motorJoint && def->type != e_mouseJoint) {
+    fprintf(stderr, "[b2cuda] only revolute, distance, weld, prismatic, wheel, friction, motor and mouse joints run on the device (SURVEY.md §8f); joint type %d ignored\n",
             (int)def->type);
     return nullptr;
   }
@@ -640,6 +640,7 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def) {
   else if (def->type == e_wheelJoint) j = new b2WheelJoint(static_cast<const b2WheelJointDef*>(def));
   else if (def->type == e_frictionJoint) j = new b2FrictionJoint(static_cast<const b2FrictionJointDef*>(def));
   else if (def->type == e_motorJoint) j = new b2MotorJoint(static_cast<const b2MotorJointDef*>(def));
+  else if (def->type == e_mouseJoint) j = new b2MouseJoint(static_cast<const b2MouseJointDef*>(def));
   else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
   j->m_index = (int32)m_impl->joints.size();
   m_impl->joints.push_back(j);
@@ -1495,6 +1496,50 @@ void b2PrismaticJoint::SetMaxMotorForce(float force) {
   if (force == m_maxMotorForce) return;
   Touch();
   m_maxMotorForce = force;
+}
+
+// ---- b2MouseJoint (b2_mouse_joint.cpp:35-75, 162-190) --------------------------------------------------
+b2MouseJoint::b2MouseJoint(const b2MouseJointDef* def) : b2Joint(def) {
+  m_targetA = def->target;
+  m_localAnchorB = b2MulT(m_bodyB->GetTransform(), m_targetA);
+  m_maxForce = def->maxForce;
+  m_stiffness = def->stiffness;
+  m_damping = def->damping;
+  m_impulse.SetZero();
+}
+void b2MouseJoint::WriteDevice(float* anchors, float* p, float* st) const {
+  anchors[0] = m_targetA.x; anchors[1] = m_targetA.y; anchors[2] = m_localAnchorB.x; anchors[3] = m_localAnchorB.y;
+  p[0] = m_maxForce; p[1] = m_stiffness; p[2] = m_damping; p[3] = p[4] = 0.0f;
+  uint32_t fl = (m_collideConnected ? 4u : 0u) | (7u << 8);  // type 7
+  memcpy(&p[5], &fl, 4);
+  for (int k = 6; k < 12; ++k) p[k] = 0.0f;
+  st[0] = m_impulse.x; st[1] = m_impulse.y; st[2] = st[3] = st[4] = 0.0f;
+}
+void b2MouseJoint::ReadDeviceState(const float* st) { m_impulse.Set(st[0], st[1]); }
+b2Vec2 b2MouseJoint::GetAnchorA() const { return m_targetA; }
+b2Vec2 b2MouseJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+b2Vec2 b2MouseJoint::GetReactionForce(float inv_dt) const {
+  m_bodyA->GetWorld()->GetImpl()->pullJoints();
+  return inv_dt * m_impulse;
+}
+float b2MouseJoint::GetReactionTorque(float inv_dt) const { return inv_dt * 0.0f; }
+void b2MouseJoint::SetTarget(const b2Vec2& target) {
+  if (target.x == m_targetA.x && target.y == m_targetA.y) return;
+  Touch(false);
+  m_bodyB->SetAwake(true);  // only the dragged body is woken (b2_mouse_joint.cpp:49-56)
+  m_targetA = target;
+}
+void b2MouseJoint::SetMaxForce(float force) {
+  Touch(false);
+  m_maxForce = force;
+}
+void b2MouseJoint::SetStiffness(float stiffness) {
+  Touch(false);
+  m_stiffness = stiffness;
+}
+void b2MouseJoint::SetDamping(float damping) {
+  Touch(false);
+  m_damping = damping;
 }
 
 // ---- b2FrictionJoint (b2_friction_joint.cpp:39-63, 183-226) -------------------------------------------

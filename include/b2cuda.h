@@ -144,7 +144,8 @@ typedef struct b2gContactArrays {
 /* Joints, SURVEY §8(f) rank 1: revolute (src/dynamics/b2_revolute_joint.cpp:73-321), distance
  * (src/dynamics/b2_distance_joint.cpp:76-303), weld (src/dynamics/b2_weld_joint.cpp:62-305),
  * prismatic (src/dynamics/b2_prismatic_joint.cpp:114-451), wheel (src/dynamics/b2_wheel_joint.cpp:87-446),
- * friction (src/dynamics/b2_friction_joint.cpp:65-181) and motor (src/dynamics/b2_motor_joint.cpp:70-208).  The type sits in bits 8-11 of the flags word.
+ * friction (src/dynamics/b2_friction_joint.cpp:65-181), motor (src/dynamics/b2_motor_joint.cpp:70-208) and
+ * mouse (src/dynamics/b2_mouse_joint.cpp:77-160).  The type sits in bits 8-11 of the flags word.
  *   bodies  [n][2] = bodyA, bodyB
  *   anchors [n][4] = localAnchorA.xy, localAnchorB.xy
  *   params  [n][12] (unused trailing entries 0), revolute (type 0): referenceAngle, lowerAngle, upperAngle, maxMotorTorque,
@@ -156,6 +157,8 @@ typedef struct b2gContactArrays {
  *                    motorSpeed, bits(flags | 3 << 8), localXAxisA.x, localXAxisA.y (unit length)
  *                  wheel (type 4): stiffness, lowerTranslation, upperTranslation, maxMotorTorque, motorSpeed,
  *                    bits(flags | 4 << 8), localXAxisA.x, localXAxisA.y, damping, 0, 0, 0
+ *                  mouse (type 7): maxForce, stiffness, damping, 0, 0, bits(flags | 7 << 8), 0...; its anchors record
+ *                    holds targetA.xy, localAnchorB.xy
  *                  friction (type 5): maxForce, maxTorque, 0, 0, 0, bits(flags | 5 << 8), 0...
  *                  motor (type 6): maxForce, maxTorque, correctionFactor, angularOffset, 0, bits(flags | 6 << 8), 0...;
  *                    its anchors record holds linearOffset.xy, 0, 0
@@ -165,6 +168,7 @@ typedef struct b2gContactArrays {
  *                  distance: m_impulse, 0, 0, m_lowerImpulse, m_upperImpulse
  *                    (include/box2d/b2_distance_joint.h:157-159)
  *                  weld: m_impulse.x, .y, .z, 0, 0 (include/box2d/b2_weld_joint.h:112)
+ *                  mouse: m_impulse.x, .y, 0, 0, 0 (include/box2d/b2_mouse_joint.h:113)
  *                  friction, motor: m_linearImpulse.x, .y, m_angularImpulse, 0, 0
  *                    (include/box2d/b2_friction_joint.h:86-87, b2_motor_joint.h:104-105)
  *                  wheel: m_impulse, m_springImpulse, m_motorImpulse, m_lowerImpulse, m_upperImpulse

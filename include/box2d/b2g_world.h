@@ -558,6 +558,51 @@ class b2PrismaticJoint : public b2Joint {
   mutable float m_upperImpulse;
 };
 
+/// b2_mouse_joint.h:30-130: drags a point of bodyB towards a world target with a soft, force-limited constraint
+struct b2MouseJointDef : public b2JointDef {
+  b2MouseJointDef() {
+    type = e_mouseJoint;
+    target.Set(0.0f, 0.0f);
+    maxForce = 0.0f;
+    stiffness = 0.0f;
+    damping = 0.0f;
+  }
+  b2Vec2 target;
+  float maxForce;
+  float stiffness;
+  float damping;
+};
+
+class b2MouseJoint : public b2Joint {
+ public:
+  b2Vec2 GetAnchorA() const override;
+  b2Vec2 GetAnchorB() const override;
+  b2Vec2 GetReactionForce(float inv_dt) const override;
+  float GetReactionTorque(float inv_dt) const override;
+  void SetTarget(const b2Vec2& target);
+  const b2Vec2& GetTarget() const { return m_targetA; }
+  void SetMaxForce(float force);
+  float GetMaxForce() const { return m_maxForce; }
+  void SetStiffness(float stiffness);
+  float GetStiffness() const { return m_stiffness; }
+  void SetDamping(float damping);
+  float GetDamping() const { return m_damping; }
+  const b2Vec2& GetLocalAnchorB() const { return m_localAnchorB; }  // (not in the reference; used by the scene shim)
+
+ protected:
+  friend class b2World;
+  friend struct b2WorldImpl;
+  b2MouseJoint(const b2MouseJointDef* def);
+  void WriteDevice(float* anchors, float* params, float* state) const override;
+  void ReadDeviceState(const float* state) override;
+  b2Vec2 m_localAnchorB;
+  b2Vec2 m_targetA;
+  float m_maxForce;
+  float m_stiffness;
+  float m_damping;
+  mutable b2Vec2 m_impulse;
+};
+
 /// b2_friction_joint.h:30-118: top-down friction between two bodies (clamped linear and angular drag)
 struct b2FrictionJointDef : public b2JointDef {
   b2FrictionJointDef() {

@@ -184,6 +184,9 @@ int b2ref_get_joint_state(void* h, int cap, float* out) {
     } else if ((*it)->GetType() == e_weldJoint) {  // b2_weld_joint.h:112
       b2WeldJoint* wj = static_cast<b2WeldJoint*>(*it);
       o[0] = wj->m_impulse.x; o[1] = wj->m_impulse.y; o[2] = wj->m_impulse.z; o[3] = 0.0f; o[4] = 0.0f;
+    } else if ((*it)->GetType() == e_mouseJoint) {  // b2_mouse_joint.h:113
+      b2MouseJoint* mo = static_cast<b2MouseJoint*>(*it);
+      o[0] = mo->m_impulse.x; o[1] = mo->m_impulse.y; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
     } else if ((*it)->GetType() == e_frictionJoint) {  // b2_friction_joint.h:86-87
       b2FrictionJoint* fj = static_cast<b2FrictionJoint*>(*it);
       o[0] = fj->m_linearImpulse.x; o[1] = fj->m_linearImpulse.y; o[2] = fj->m_angularImpulse; o[3] = 0.0f; o[4] = 0.0f;
@@ -226,7 +229,7 @@ int b2ref_next_step_joint_order(void* h, int cap, int* out) {
     for (auto it = js.rbegin(); it != js.rend(); ++it)
       if ((*it)->GetType() == e_revoluteJoint || (*it)->GetType() == e_distanceJoint || (*it)->GetType() == e_weldJoint ||
           (*it)->GetType() == e_prismaticJoint || (*it)->GetType() == e_wheelJoint ||
-          (*it)->GetType() == e_frictionJoint || (*it)->GetType() == e_motorJoint)
+          (*it)->GetType() == e_frictionJoint || (*it)->GetType() == e_motorJoint || (*it)->GetType() == e_mouseJoint)
         jointIndex[*it] = n++;
   }
   std::unordered_map<const b2Body*, bool> bodySeen;

@@ -252,6 +252,7 @@ int SHIM(scene_joint_count)(void* h) { return static_cast<Scene*>(h)->world->Get
 //   revolute: referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, bits(flags), 0, 0
 //   distance: length, minLength, maxLength, stiffness, damping, bits(flags | 1 << 8), 0, 0
 //   weld:     referenceAngle, stiffness, damping, 0, 0, bits(flags | 2 << 8), 0, 0
+//   mouse:    maxForce, stiffness, damping, 0, 0, bits(flags | 7 << 8), 0...; anchors = target.xy, localAnchorB.xy
 //   friction: maxForce, maxTorque, 0, 0, 0, bits(flags | 5 << 8), 0...
 //   motor:    maxForce, maxTorque, correctionFactor, angularOffset, 0, bits(flags | 6 << 8), 0...;
 //             anchors = linearOffset.xy, 0, 0
@@ -291,6 +292,17 @@ int SHIM(scene_get_joints)(void* h, int cap, int* bodies, float* anchors, float*
       anchors[4 * n + 2] = wj->GetLocalAnchorB().x; anchors[4 * n + 3] = wj->GetLocalAnchorB().y;
       p[0] = wj->GetReferenceAngle(); p[1] = wj->GetStiffness(); p[2] = wj->GetDamping(); p[3] = 0.0f; p[4] = 0.0f;
       fl |= 2u << 8;
+    } else if (j->GetType() == e_mouseJoint) {
+      b2MouseJoint* mo = static_cast<b2MouseJoint*>(j);
+#ifdef B2G_WORLD_H
+      const b2Vec2 lb = mo->GetLocalAnchorB();
+#else  // the reference keeps it protected; the oracle harness is compiled with -fno-access-control
+      const b2Vec2 lb = mo->m_localAnchorB;
+#endif
+      anchors[4 * n] = mo->GetTarget().x; anchors[4 * n + 1] = mo->GetTarget().y;
+      anchors[4 * n + 2] = lb.x; anchors[4 * n + 3] = lb.y;
+      p[0] = mo->GetMaxForce(); p[1] = mo->GetStiffness(); p[2] = mo->GetDamping(); p[3] = p[4] = 0.0f;
+      fl |= 7u << 8;
     } else if (j->GetType() == e_frictionJoint) {
       b2FrictionJoint* fj = static_cast<b2FrictionJoint*>(j);
       anchors[4 * n] = fj->GetLocalAnchorA().x; anchors[4 * n + 1] = fj->GetLocalAnchorA().y;

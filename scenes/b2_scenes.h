@@ -12,6 +12,7 @@
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
 //   welds          weld joints: cantilever beams, a welded compound (b2_weld_joint.cpp)
 //   cars           wheel joints: sprung, motorised cars driving over ramps and loose boxes (b2_wheel_joint.cpp)
+//   mice           mouse joints: bodies dragged to world targets, soft and stiff, strong and too weak (b2_mouse_joint.cpp)
 //   drags          friction joints (braked falling / spinning boxes) and motor joints (platforms driven to an
 //                  offset, carrying boxes) (b2_friction_joint.cpp, b2_motor_joint.cpp)
 //   sliders        prismatic joints: motorised pistons, limited rails, a free slider (b2_prismatic_joint.cpp)
@@ -383,6 +384,46 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
         cd.allowSleep = seed == 0 ? false : true;
         s->addFixture(s->addBody(cd), crate, 0.5f);
       }
+    }
+  } else if (name == "mice") {
+    // mouse joints (b2_mouse_joint.cpp:77-160): boxes and balls resting on the ground are dragged to targets
+    // above and beside them — anchored off-centre, with spring rates from 1 to 5 Hz, force budgets from less
+    // than the weight to a thousand times it — through each other and a row of loose boxes
+    int n = size > 0 ? size : 8;
+    b2BodyDef gd;
+    b2Body* floorBody = s->addBody(gd);
+    b2EdgeShape edge;
+    edge.SetTwoSided(b2Vec2(-60.0f, 0.0f), b2Vec2(60.0f, 0.0f));
+    s->addFixture(floorBody, edge, 0.0f);
+    // the joints hang on a second, shapeless static body: a joint without collideConnected switches off the
+    // contacts between its two bodies, and the dragged bodies must keep colliding with the floor
+    b2Body* ground = s->addBody(gd);
+    b2PolygonShape box;
+    box.SetAsBox(0.4f, 0.4f);
+    b2CircleShape ball;
+    ball.m_radius = 0.35f;
+    for (int i = 0; i < n; ++i) {
+      float x = -12.0f + 3.0f * (float)i;
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(x, 0.41f);
+      bd.allowSleep = seed == 0 ? false : true;
+      b2Body* body = s->addBody(bd);
+      if (i % 2) s->addFixture(body, ball, 2.0f);
+      else s->addFixture(body, box, 2.0f);
+      b2MouseJointDef jd;
+      jd.bodyA = ground;
+      jd.bodyB = body;
+      jd.target.Set(x + 0.3f, 0.6f);                       // grabbed off-centre
+      jd.maxForce = (i % 4 == 3 ? 0.5f : 1000.0f) * body->GetMass() * 10.0f;
+      b2LinearStiffness(jd.stiffness, jd.damping, 1.0f + (float)(i % 5), 0.7f, ground, body);
+      b2MouseJoint* mj = static_cast<b2MouseJoint*>(s->world->CreateJoint(&jd));
+      mj->SetTarget(b2Vec2(x + 2.0f - 1.0f * (float)(i % 3), 3.0f + 0.5f * (float)(i % 4)));
+      b2BodyDef cd;
+      cd.type = b2_dynamicBody;
+      cd.position.Set(x + 1.5f, 0.41f);
+      cd.allowSleep = seed == 0 ? false : true;             // see "cars": keeps the parity run off the ring-order corner
+      s->addFixture(s->addBody(cd), box, 1.0f);             // a loose box in the way
     }
   } else if (name == "drags") {
     // friction joints (b2_friction_joint.cpp:65-181): boxes tied to the ground by a force / torque budget —

@@ -719,6 +719,47 @@ static void friction_and_motor_joint_api() {
   }
 }
 
+// mouse joint: a box is dragged to a target and hangs there, sagging by m g / k; too weak a grip cannot lift it
+static void mouse_joint_api() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2EdgeShape edge;
+  edge.SetTwoSided(b2Vec2(-20.0f, 0.0f), b2Vec2(20.0f, 0.0f));
+  ground->CreateFixture(&edge, 0.0f);
+  b2Body* anchor = world.CreateBody(&gd);   // shapeless: the joint must not switch off the floor contact
+  b2PolygonShape box;
+  box.SetAsBox(0.5f, 0.5f);
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  bd.position.Set(0.0f, 0.51f);
+  b2Body* body = world.CreateBody(&bd);
+  body->CreateFixture(&box, 2.0f);   // mass 2
+  b2MouseJointDef jd;
+  jd.bodyA = anchor;
+  jd.bodyB = body;
+  jd.target = body->GetPosition();
+  jd.maxForce = 1000.0f * body->GetMass();
+  b2LinearStiffness(jd.stiffness, jd.damping, 5.0f, 0.7f, anchor, body);
+  b2MouseJoint* j = static_cast<b2MouseJoint*>(world.CreateJoint(&jd));
+  CHECK(j != nullptr && j->GetTarget().y == 0.51f && j->GetStiffness() == jd.stiffness);
+  j->SetTarget(b2Vec2(3.0f, 4.0f));
+  for (int i = 0; i < 240; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  b2Vec2 p = body->GetPosition();
+  float sag = body->GetMass() * 10.0f / jd.stiffness;
+  CHECK(fabsf(p.x - 3.0f) < 0.01f && fabsf(p.y - (4.0f - sag)) < 0.01f);
+  b2Vec2 F = j->GetReactionForce(60.0f);
+  CHECK(fabsf(F.y - 20.0f) < 0.1f && fabsf(F.x) < 0.1f && j->GetReactionTorque(60.0f) == 0.0f);
+  j->SetMaxForce(10.0f);   // half the weight
+  body->SetAwake(true);    // (it hangs still and has fallen asleep; the setter does not wake it)
+  for (int i = 0; i < 120; ++i) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(body->GetPosition().y < 0.6f && body->GetPosition().y > 0.4f);   // back on the floor
+  b2Vec2 F2 = j->GetReactionForce(60.0f);
+  CHECK(fabsf(F2.Length() - 10.0f) < 1e-3f);
+  printf("mouse: at (%.4f, %.4f), sag %.4f, F=(%.4f, %.4f), weak grip |F|=%.4f y=%.4f\n", p.x, p.y, sag, F.x, F.y, F2.Length(),
+         body->GetPosition().y);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -732,6 +773,7 @@ int main() {
   prismatic_joint_api();
   wheel_joint_api();
   friction_and_motor_joint_api();
+  mouse_joint_api();
   contact_buffers_grow();
   world_editing_session();
   user_contact_filter();

@@ -82,7 +82,9 @@ def rel(a, b):
                                                    # the impact: ring-order corner, tolerance gate only (see below)
                                                    ("cars", 4, 1, 300),
                                                    # friction joints (braked boxes) and motor joints (driven platforms)
-                                                   ("drags", 6, 0, 240)])
+                                                   ("drags", 6, 0, 240),
+                                                   # mouse joints: bodies dragged to targets through loose boxes
+                                                   ("mice", 8, 0, 240)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
     from box2d_optimized_b200 import RefScene
     ref = RefScene(name, size, seed)
