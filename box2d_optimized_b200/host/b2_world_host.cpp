@@ -677,7 +677,14 @@ void b2World::ShiftOrigin(const b2Vec2& newOrigin) {
     b->UpdateAABBs();
     m_impl->touchBody(b->m_index);
   }
-  // revolute joints hold local anchors only (b2_revolute_joint.cpp has no ShiftOrigin state)
+  // joints hold local anchors only, except the mouse joint's world target (b2_mouse_joint.cpp:187-190)
+  for (b2Joint* j : m_impl->joints) {
+    if (j && j->GetType() == e_mouseJoint) {
+      m_impl->pullJoints();
+      static_cast<b2MouseJoint*>(j)->m_targetA -= newOrigin;
+      m_impl->jointsDirty = true;
+    }
+  }
   m_newContacts = true;
 }
 
