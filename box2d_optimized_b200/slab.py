@@ -194,13 +194,9 @@ class SlabRank:
         contact's non-static body with the smallest global id."""
         c = self.arena.download_contacts()
         ga, gb = self.fix_gid[c["fix_a"]], self.fix_gid[c["fix_b"]]
-        ba, bb = self.fix_body_gid[ga].astype(np.int64), self.fix_body_gid[gb].astype(np.int64)
-        big = np.int64(1) << 40
-        lead = np.minimum(np.where(self.body_type[ba] != capi.STATIC, ba, big),
-                          np.where(self.body_type[bb] != capi.STATIC, bb, big))
-        mine = np.zeros(len(self.body_type) + 1, bool)
-        mine[self.slab.global_ids[self.slab.owned_local]] = True
-        keep = mine[np.minimum(lead, len(self.body_type))]
+        owned = np.zeros(len(self.body_type), bool)
+        owned[self.slab.global_ids[self.slab.owned_local]] = True
+        keep = publishes_contact(ga, gb, self.fix_body_gid, self.body_type, owned)
         return dict(fix_a=ga[keep], fix_b=gb[keep], flags=c["flags"][keep], manifold=c["manifold"][keep],
                     material=c["material"][keep])
 
@@ -252,6 +248,16 @@ def exchange_in_process(ranks):
 
 
 # ------------------------------------------------------------------------------- rebalance
+def publishes_contact(fix_a, fix_b, fix_body, body_type, owned):
+    """which contacts (pairs of GLOBAL fixture ids) a rank publishes in a rebalance: those whose non-static
+    body with the smallest global id it owns.  Every contact has at least one movable body and every
+    movable body exactly one owner, so over all ranks each contact is published exactly once."""
+    ba, bb = fix_body[fix_a].astype(np.int64), fix_body[fix_b].astype(np.int64)
+    big = np.int64(len(body_type))
+    lead = np.minimum(np.where(body_type[ba] != capi.STATIC, ba, big), np.where(body_type[bb] != capi.STATIC, bb, big))
+    return np.concatenate([owned, [False]])[lead]
+
+
 def merge_records(glob, records):
     """writes published owner records (SlabRank.owned_record, any order, any number of ranks) into the
     global scene arrays: rows of scene.bodies() = xf(4), c(2), a, v(2), w, awake, type"""

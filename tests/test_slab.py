@@ -91,6 +91,30 @@ def test_two_rank_halo_exchange_over_gloo():
     assert got[0][1] == got[1][2] and got[0][2] == got[1][1] and got[0][1] > 0
 
 
+def test_every_boundary_contact_is_published_exactly_once():
+    """a rebalance publishes each contact once although boundary contacts live in both neighbours' arenas"""
+    from box2d_optimized_b200.slab import publishes_contact
+    rng = np.random.default_rng(11)
+    nb, nf = 400, 400                      # one fixture per body, fixture i on body i
+    btype = np.full(nb, capi.DYNAMIC, np.int32)
+    btype[:5] = capi.STATIC
+    fix_body = np.arange(nf, dtype=np.int32)
+    x = rng.uniform(0, 100, nb)
+    owner, cuts = partition_by_x(x, btype != capi.STATIC, 3)
+    # contacts: random pairs with at least one movable body
+    fa, fb = rng.integers(0, nf, 3000), rng.integers(0, nf, 3000)
+    ok = (fa != fb) & ((btype[fa] != capi.STATIC) | (btype[fb] != capi.STATIC))
+    fa, fb = fa[ok], fb[ok]
+    published = np.zeros(len(fa), np.int32)
+    for r in range(3):
+        owned = owner == r
+        # the rank holds a contact when it owns one of its bodies (the other is then owned, static or a ghost)
+        holds = owned[fa] | owned[fb]
+        keep = publishes_contact(fa[holds], fb[holds], fix_body, btype, owned)
+        published[np.nonzero(holds)[0][keep]] += 1
+    assert (published == 1).all()
+
+
 def _rebalance_worker(rank, port, out):
     """two ranks publish the bodies they own (moved since the last partition), gather, merge, cut again"""
     from box2d_optimized_b200.slab import gather_records, merge_records
