@@ -2,7 +2,7 @@
 # ncu evidence: (1) launch list with device times for a short bench run, (2) one full capture of
 # the dominant kernels.  Numbers printed under ncu are not bench values.
 # -s counts ALL launches, not only the ones the -k filter keeps: at 15 launches per step (many_pyramids) 1350 is
-# step 90, inside the settled window; with -s 400 the r01g capture landed on an early step (at most 2 048 contact slots)
+# step 90, inside the settled window; with -s 400 the r01g capture landed on a step with at most 2 048 contact slots
 # (profiles/r01g_ncu_full_early_step.csv).
 mkdir -p gpurun_out
 WL=${1:-many_pyramids}
