@@ -148,7 +148,7 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU b2World::Step, one world per host thread."""
     if rank != 0:
         return
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     scene, size, seed, desc = WORKLOADS[args.workload]
     # one world per GPU of our arm for the single-world workloads; for the batched workloads a
     # bounded sample of one world per host thread (the per-world cost is identical)
@@ -390,7 +390,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            from box2d_optimized_b200 import RefScene
+            from oracle.bindings import RefScene
             r = RefScene(scene_name, size, seed)
             r.step(PRESTEP.get(args.workload, 0) + args.warmup)  # same spawn phase as the replicated GPU state
             n = min(args.cpu_sample_steps, args.steps)

@@ -7,4 +7,4 @@ Layout (only what the hot path needs):
 """
 from . import capi  # noqa: F401
 from .arena import Arena, arena_from_scene, body_flags  # noqa: F401
-from .scene import GpuScene, RefScene  # noqa: F401
+from .scene import GpuScene  # noqa: F401

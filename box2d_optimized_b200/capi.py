@@ -1,8 +1,8 @@
 """ctypes binding of the C-ABI (include/b2cuda.h) and of the two scene shims.
 
 PyTorch is not involved here: arrays cross as numpy buffers / raw pointers.  The product
-library is libb2cuda.so; importing this module does NOT load anything under oracle/ (the
-oracle is loaded only by tests, smoke() and bench.py's baseline legs through load_ref()).
+library is libb2cuda.so; nothing here knows about oracle/ (the checker's bindings live in
+oracle/bindings.py and are loaded only by tests, smoke() and bench.py's baseline legs).
 """
 import ctypes as C
 import os
@@ -214,61 +214,6 @@ def load_gpu_scenes():
         lib.b2gpu_scene_get_profile.argtypes = [C.c_void_p, f32p]
         _gpu_scenes = lib
     return _gpu_scenes
-
-
-def ref_path():
-    return os.path.join(ROOT, "oracle", "_ref", "libb2ref.so")
-
-
-def load_ref():
-    """TEST/BASELINE ONLY: the compiled reference (oracle/_ref).  Never used by the product path."""
-    global _ref
-    if _ref is None:
-        p = ref_path()
-        if not os.path.exists(p):
-            raise B2GError(f"{p} is missing: `make -C oracle ref` (needs /root/reference)")
-        lib = C.CDLL(p)
-        _declare_shim(lib, "b2ref_")
-        lib.b2ref_polygon_set.argtypes = [f32p, C.c_int, f32p]
-        lib.b2ref_shape_mass.argtypes = [C.c_int, f32p, C.c_float, f32p]
-        lib.b2ref_compute_aabbs.argtypes = [C.c_int, i32p, i32p, f32p, f32p, f32p]
-        lib.b2ref_collide_pairs.argtypes = [C.c_int, i32p, i32p, f32p, i32p, i32p, f32p, f32p, f32p]
-        lib.b2ref_world_collide.argtypes = [C.c_void_p]
-        lib.b2ref_get_body_inv.argtypes = [C.c_void_p, f32p]
-        lib.b2ref_get_inv_dt0.restype = C.c_float
-        lib.b2ref_get_inv_dt0.argtypes = [C.c_void_p]
-        lib.b2ref_get_sleep_times.argtypes = [C.c_void_p, f32p]
-        lib.b2ref_get_joint_state.argtypes = [C.c_void_p, C.c_int, f32p]
-        lib.b2ref_next_step_joint_order.argtypes = [C.c_void_p, C.c_int, i32p]
-        lib.b2ref_step_recording_order.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
-        lib.b2ref_solve.argtypes = [C.c_int, f32p, f32p, f32p, C.c_int, i32p, f32p, f32p, f32p, C.c_float, C.c_float,
-                                    C.c_int, C.c_int, C.c_int, f32p, f32p, i32p]
-        _ref = lib
-    return _ref
-
-
-_oracle = None
-
-
-def oracle_path():
-    return os.path.join(ROOT, "oracle", "libb2oracle.so")
-
-
-def load_oracle():
-    """TEST ONLY: the plain-C restatement (oracle/b2_oracle.c).  Never used by the product path."""
-    global _oracle
-    if _oracle is None:
-        p = oracle_path()
-        if not os.path.exists(p):
-            raise B2GError(f"{p} is missing: `make -C oracle port`")
-        lib = C.CDLL(p)
-        lib.b2o_compute_aabbs.argtypes = [C.c_int, i32p, i32p, f32p, f32p, f32p]
-        lib.b2o_collide_pairs.argtypes = [C.c_int, i32p, i32p, f32p, i32p, i32p, f32p, f32p, f32p]
-        lib.b2o_find_pairs.argtypes = [C.c_int, f32p, i32p, i32p, u8p, i32p, C.c_int, i32p]
-        lib.b2o_solve.argtypes = [C.c_int, f32p, f32p, f32p, C.c_int, i32p, f32p, f32p, f32p, C.c_float, C.c_float,
-                                  C.c_int, C.c_int, C.c_int, f32p, f32p, i32p]
-        _oracle = lib
-    return _oracle
 
 
 def fp(a):

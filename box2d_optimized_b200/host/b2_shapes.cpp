@@ -1,3 +1,10 @@
+// -----------------------------------------------------------------------------------------------
+// Third-party notice.  To stay source- and result-compatible with box2d-optimized, parts of this
+// file restate declarations, inline math and creation-time algorithms of that library (itself a
+// fork of Box2D).  Those parts are covered by the MIT License:
+//   Copyright (c) 2019 Erin Catto, Copyright (c) 2020 Manolis Tsamis
+// The full licence text and permission notice are in LICENSES/box2d-optimized-MIT.txt.
+// -----------------------------------------------------------------------------------------------
 // b2_shapes.cpp — host-side shape geometry of the drop-in C++ API.
 //
 // Same results as the reference's src/collision/b2_circle_shape.cpp:91-105,

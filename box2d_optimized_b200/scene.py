@@ -1,7 +1,7 @@
 """Python views of the two scene shims (same C functions, prefixes b2gpu_ / b2ref_).
 
-`GpuScene` drives this repo's drop-in C++ API (and through it the CUDA step);
-`RefScene` drives the compiled reference and is test/baseline infrastructure only.
+`GpuScene` drives this repo's drop-in C++ API (and through it the CUDA step).  The view of the
+compiled reference (`RefScene`) is test/baseline infrastructure and lives in oracle/bindings.py.
 """
 import ctypes as C
 
@@ -160,51 +160,3 @@ class GpuScene(_Scene):
         out = np.zeros(5, np.float32)
         self.lib.b2gpu_scene_get_profile(self.h, capi.fp(out))
         return dict(zip(("step", "collide", "solve", "broadphase", "solveTOI"), out.tolist()))
-
-
-class RefScene(_Scene):
-    """The reference's own CPU b2World::Step on the same scene.  TEST / BASELINE ONLY."""
-    prefix = "b2ref_"
-
-    def __init__(self, name, size=0, seed=0):
-        super().__init__(capi.load_ref(), name, size, seed)
-
-    def collide_now(self):
-        self.lib.b2ref_world_collide(self.h)
-
-    def body_inv(self):
-        out = np.zeros((self.body_count, 2), np.float32)
-        self.lib.b2ref_get_body_inv(self.h, capi.fp(out))
-        return out
-
-    def inv_dt0(self):
-        return float(self.lib.b2ref_get_inv_dt0(self.h))
-
-    def step_recording_order(self):
-        """one Step with a PostSolve tap: returns the ordered (fixA, fixB) pairs in the order the
-        reference's island solver visited them"""
-        cap = max(self.contact_count, 1) + 16
-        fa = np.zeros(cap, np.int32)
-        fb = np.zeros(cap, np.int32)
-        n = self.lib.b2ref_step_recording_order(self.h, cap, capi.ip(fa), capi.ip(fb))
-        return fa[:n], fb[:n]
-
-    def joint_state(self):
-        """accumulated impulses of the revolute joints [n, 5] (white-box: b2_revolute_joint.h:178-181)"""
-        n = self.lib.b2ref_scene_joint_count(self.h)
-        out = np.zeros((max(n, 1), 5), np.float32)
-        n = self.lib.b2ref_get_joint_state(self.h, n, capi.fp(out))
-        return out[:n]
-
-    def next_step_joint_order(self):
-        """joint indices in the order the NEXT Step's island DFS will add them (oracle/ref_harness.cpp);
-        runs the head of that Step (pair refresh + Collide), which the Step then repeats unchanged"""
-        n = self.lib.b2ref_scene_joint_count(self.h)
-        out = np.zeros(max(n, 1), np.int32)
-        k = self.lib.b2ref_next_step_joint_order(self.h, n, capi.ip(out))
-        return out[:k]
-
-    def sleep_times(self):
-        out = np.zeros(self.body_count, np.float32)
-        self.lib.b2ref_get_sleep_times(self.h, capi.fp(out))
-        return out

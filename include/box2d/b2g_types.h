@@ -1,3 +1,10 @@
+// -----------------------------------------------------------------------------------------------
+// Third-party notice.  To stay source- and result-compatible with box2d-optimized, parts of this
+// file restate declarations, inline math and creation-time algorithms of that library (itself a
+// fork of Box2D).  Those parts are covered by the MIT License:
+//   Copyright (c) 2019 Erin Catto, Copyright (c) 2020 Manolis Tsamis
+// The full licence text and permission notice are in LICENSES/box2d-optimized-MIT.txt.
+// -----------------------------------------------------------------------------------------------
 // b2g_types.h — scalar types, tuning constants and 2-D math of the drop-in C++ API.
 //
 // API mirror of the reference's include/box2d/b2_types.h, b2_common.h:110-182, b2_settings.h:40-80

@@ -1,3 +1,10 @@
+// -----------------------------------------------------------------------------------------------
+// Third-party notice.  To stay source- and result-compatible with box2d-optimized, parts of this
+// file restate declarations, inline math and creation-time algorithms of that library (itself a
+// fork of Box2D).  Those parts are covered by the MIT License:
+//   Copyright (c) 2019 Erin Catto, Copyright (c) 2020 Manolis Tsamis
+// The full licence text and permission notice are in LICENSES/box2d-optimized-MIT.txt.
+// -----------------------------------------------------------------------------------------------
 // b2_scenes.h — the BASELINE.json scenes, written ONCE against the public Box2D API.
 //
 // This file includes only "box2d/box2d.h" and uses only b2World / b2Body / b2Fixture / shape
@@ -53,6 +60,10 @@ struct Scene {
   int positionIterations = 3;
   std::string kind;
   int spawnTarget = 0, spawned = 0;  // tumbler: one box per step until spawnTarget
+  // tumbler variants (seed > 0): every box is spawned at (0, 10) + U[-2, 2]^2 from an LCG seeded per
+  // world, so batched worlds are different worlds, not clones; seed 0 = the reference's b3 scene
+  bool spawnJitter = false;
+  SceneLCG spawnRng{1u};
   int steps = 0;
 
   ~Scene() { delete world; }
@@ -82,6 +93,10 @@ struct Scene {
       b2BodyDef bd;
       bd.type = b2_dynamicBody;
       bd.position.Set(0.0f, 10.0f);
+      if (spawnJitter) {
+        float dx = spawnRng.range(-2.0f, 2.0f), dy = spawnRng.range(-2.0f, 2.0f);
+        bd.position.Set(dx, 10.0f + dy);
+      }
       b2Body* body = addBody(bd);
       b2PolygonShape shape;
       shape.SetAsBox(0.125f, 0.125f);
@@ -181,6 +196,10 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
     }
   } else if (name == "tumbler") {
     s->spawnTarget = size > 0 ? size : 500;
+    if (seed > 0) {
+      s->spawnJitter = true;
+      s->spawnRng = SceneLCG(0x9e3779b9u * (uint32_t)seed + 12345u);
+    }
     b2Body* ground;
     {
       b2BodyDef bd;

@@ -23,7 +23,8 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     args = ap.parse_args()
     import torch
-    from box2d_optimized_b200 import capi, arena_from_scene, RefScene
+    from box2d_optimized_b200 import capi, arena_from_scene
+    from oracle.bindings import RefScene
     lib = capi.load_cuda()
     ref = RefScene("mixed", args.bodies, 12345)
     t0 = time.perf_counter()

@@ -1,6 +1,7 @@
 import sys; sys.path.insert(0, ".")
 import numpy as np
-from box2d_optimized_b200 import RefScene, GpuScene
+from box2d_optimized_b200 import GpuScene
+from oracle.bindings import RefScene
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 ref, gpu = RefScene("chain", n, 0), GpuScene("chain", n, 0)
 for k in range(1, 31):

@@ -1,7 +1,8 @@
 import sys, numpy as np
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 import util
-from box2d_optimized_b200 import capi, Arena, arena_from_scene, RefScene
+from box2d_optimized_b200 import capi, Arena, arena_from_scene
+from oracle.bindings import RefScene
 from test_world_step_parity import mirror_reference_state
 name, size, seed, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 ref = RefScene(name, size, seed); ref.step(size + 2 if name == "tumbler" else 1)

@@ -1,7 +1,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from box2d_optimized_b200 import capi, GpuScene, RefScene
+from box2d_optimized_b200 import capi, GpuScene
+from oracle.bindings import RefScene
 name, size = sys.argv[1], int(sys.argv[2])
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 a = GpuScene(name, size, 99, solver_mode=mode); b = GpuScene(name, size, 99, solver_mode=mode)

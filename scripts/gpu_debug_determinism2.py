@@ -1,7 +1,8 @@
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from box2d_optimized_b200 import capi, Arena, arena_from_scene, RefScene
+from box2d_optimized_b200 import capi, Arena, arena_from_scene
+from oracle.bindings import RefScene
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 ref = RefScene("mixed", 1500, 99)
 A = arena_from_scene(ref); B = arena_from_scene(ref)

@@ -1,6 +1,7 @@
 import sys, numpy as np
 sys.path.insert(0, ".")
-from box2d_optimized_b200 import RefScene, GpuScene, capi
+from box2d_optimized_b200 import GpuScene, capi
+from oracle.bindings import RefScene
 for name, size in ((sys.argv[1] if len(sys.argv) > 1 else "welds", int(sys.argv[2]) if len(sys.argv) > 2 else 6),):
     for mode in (capi.SOLVER_COLOURED, capi.SOLVER_SEQUENTIAL):
         ref, gpu = RefScene(name, size, 0), GpuScene(name, size, 0, solver_mode=mode)

@@ -3,7 +3,8 @@
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from box2d_optimized_b200 import GpuScene, RefScene
+from box2d_optimized_b200 import GpuScene
+from oracle.bindings import RefScene
 
 def pe(b, p):
     dyn = b[:, 11] == 2

@@ -3,7 +3,8 @@ import sys, os, time, traceback
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import ctypes as C
-from box2d_optimized_b200 import capi, Arena, arena_from_scene, GpuScene, RefScene
+from box2d_optimized_b200 import capi, Arena, arena_from_scene, GpuScene
+from oracle.bindings import RefScene
 
 def section(name):
     print(f"\n=== {name} ===", flush=True)

@@ -28,8 +28,8 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def ref_available():
-    from box2d_optimized_b200 import capi
-    return os.path.exists(capi.ref_path())
+    import oracle.bindings as oracle_bindings
+    return os.path.exists(oracle_bindings.ref_path())
 
 
 @pytest.fixture(scope="session")

@@ -1,3 +1,10 @@
+// -----------------------------------------------------------------------------------------------
+// Third-party notice.  To stay source- and result-compatible with box2d-optimized, parts of this
+// file restate declarations, inline math and creation-time algorithms of that library (itself a
+// fork of Box2D).  Those parts are covered by the MIT License:
+//   Copyright (c) 2019 Erin Catto, Copyright (c) 2020 Manolis Tsamis
+// The full licence text and permission notice are in LICENSES/box2d-optimized-MIT.txt.
+// -----------------------------------------------------------------------------------------------
 // api_tests.cpp — acceptance tests of the public C++ API, compiled twice:
 //   against the reference (-I/root/reference/include + its sources): proves the tests are right
 //   against this repo's drop-in API (-Iinclude + libb2gpu_scenes.so): proves the drop-in

@@ -9,12 +9,14 @@ import os
 import sys
 
 import numpy as np
+import oracle.bindings as oracle_bindings  # noqa: E402  (the checker)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
-from box2d_optimized_b200 import capi, RefScene  # noqa: E402
+from box2d_optimized_b200 import capi  # noqa: E402
+from oracle.bindings import RefScene
 import util  # noqa: E402
 
 
@@ -32,7 +34,7 @@ def random_polygon(rng, lib):
 def narrowphase_cases(seed, n_per_type):
     """random ordered pairs of every supported type, mostly near contact"""
     rng = np.random.default_rng(seed)
-    lib = capi.load_ref()
+    lib = oracle_bindings.load_ref()
     pool = util.ShapePool()
     tA, oA, tB, oB, xa, xb = [], [], [], [], [], []
     types = [(0, 0), (2, 0), (2, 2), (1, 0), (1, 2)]
@@ -95,7 +97,7 @@ def solver_case(scene_name, size, seed, steps):
     done = capi.C.c_int32() if hasattr(capi, "C") else None
     import ctypes
     done = ctypes.c_int32()
-    capi.load_ref().b2ref_solve(nb, capi.fp(pos_o), capi.fp(vel_o), capi.fp(mass), len(index), capi.ip(index),
+    oracle_bindings.load_ref().b2ref_solve(nb, capi.fp(pos_o), capi.fp(vel_o), capi.fp(mass), len(index), capi.ip(index),
                                 capi.fp(man_o), capi.fp(mat), capi.fp(radii), float(dt), 1.0, 1, vi, pi,
                                 capi.fp(vit), capi.fp(pit), ctypes.byref(done))
     return dict(pos=pos, vel=vel, mass=mass, index=index, manifold=man, material=mat, radii=radii, dt=dt,

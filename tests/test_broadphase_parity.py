@@ -129,7 +129,7 @@ def test_capacity_overflow_is_reported_not_truncated():
 def test_live_reference_pair_set_and_order(require_ref, name, size, steps):
     """pair set == the reference's contact set on the reference's own transforms; A/B order of
     mixed-type pairs follows the reference's function table"""
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     s = RefScene(name, size, 12345)
     s.step(steps)
     A = arena_from_scene(s)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("mode", [capi.SOLVER_COLOURED, capi.SOLVER_SEQUENTIAL])
 def test_hinged_boxes_track_the_reference(require_ref, name, mode):
     """no contacts, so constraint order cannot differ: trajectories agree to float noise"""
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     r = RefScene(name, 3)
     g = GpuScene(name, 3, solver_mode=mode)
     worst = 0.0
@@ -32,7 +32,7 @@ def test_hinged_boxes_track_the_reference(require_ref, name, mode):
 def test_tumbler_container_is_driven_like_the_reference(require_ref):
     """config 4 shape: motor-driven container (revolute joint to an empty static ground) filling
     with boxes; the container touches hundreds of boxes, which exercises the overflow bucket"""
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     n = 150
     r = RefScene("tumbler", n)
     g = GpuScene("tumbler", n)
@@ -57,7 +57,8 @@ def test_chain_of_joined_links_follows_the_reference(require_ref, name):
     the chain swings and drags over the ground for 6 s.
     Once links touch the ground the contact order (colours vs DFS) differs from the reference, so
     this is a tolerance gate, not an iterate gate."""
-    from box2d_optimized_b200 import RefScene, GpuScene
+    from box2d_optimized_b200 import GpuScene
+    from oracle.bindings import RefScene
     ref, gpu = RefScene(name, 12, 0), GpuScene(name, 12, 0)
     for k in range(30):
         ref.step(1)
@@ -78,7 +79,8 @@ def test_long_chain_has_no_joint_capacity(require_ref):
     through joints alone (no contact yet).  Joints are visited in descending index order, which is
     the order the reference's island DFS discovers a chain built root to tip, so while the chain
     swings freely the production mode reproduces the reference exactly."""
-    from box2d_optimized_b200 import RefScene, GpuScene
+    from box2d_optimized_b200 import GpuScene
+    from oracle.bindings import RefScene
     ref, gpu = RefScene("chain", 150, 0), GpuScene("chain", 150, 0)
     ref.step(60)
     gpu.step(60)
@@ -114,7 +116,8 @@ def test_jointed_scenes_run_free_in_the_production_mode(require_ref, name, size,
     runs the same device functions through the global-memory accessors only.  Free running against the
     reference's CPU Step: contact order differs (colours vs DFS), so an outcome gate: every body stays
     within `tol` metres of the reference's and the joint impulses stay finite."""
-    from box2d_optimized_b200 import RefScene, GpuScene
+    from box2d_optimized_b200 import GpuScene
+    from oracle.bindings import RefScene
     ref, gpu = RefScene(name, size, 0), GpuScene(name, size, 0)
     worst = 0.0
     for k in range(steps // 40):

@@ -61,7 +61,7 @@ def test_live_reference_large_fuzz(require_ref):
 @pytest.mark.parametrize("name,size,steps", [("pyramid", 20, 120), ("mixed", 3000, 200), ("falling_circles", 300, 150),
                                               ("tumbler", 200, 260)])
 def test_live_reference_scene_contacts(require_ref, name, size, steps):
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     s = RefScene(name, size, 12345)
     s.step(steps)
     s.collide_now()

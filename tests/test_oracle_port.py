@@ -6,6 +6,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import oracle.bindings as oracle_bindings  # noqa: E402  (the checker)
 import pytest
 
 import util
@@ -16,10 +17,10 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 @pytest.fixture(scope="module")
 def port():
-    if not os.path.exists(capi.oracle_path()):
+    if not os.path.exists(oracle_bindings.oracle_path()):
         import subprocess
         subprocess.check_call(["make", "-C", os.path.join(capi.ROOT, "oracle"), "port"])
-    return capi.load_oracle()
+    return oracle_bindings.load_oracle()
 
 
 def port_collide(lib, tA, oA, xA, tB, oB, xB, quads):

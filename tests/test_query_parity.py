@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def scene_pair(name, size, seed, steps):
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     ref = RefScene(name, size, seed)
     ref.step(steps)
     A = arena_from_scene(ref, max_contacts=max(4096, 16 * ref.body_count))
@@ -122,7 +122,8 @@ def test_all_hits_and_filters(require_ref):
 def test_queries_through_the_drop_in_api(require_ref):
     """The same shim program (scenes/b2_scene_shim.h) over this repo's b2World: QueryAABB / RayCast
     with user callbacks, replayed from the device results."""
-    from box2d_optimized_b200 import GpuScene, RefScene
+    from box2d_optimized_b200 import GpuScene
+    from oracle.bindings import RefScene
     ref, gpu = RefScene("pyramid", 12, 0), GpuScene("pyramid", 12, 0)
     # identical initial state; no steps, so both sides hold bit-identical transforms
     rays = random_rays(np.random.default_rng(2), scene_bounds(ref), 500)
@@ -146,7 +147,7 @@ def test_queries_through_the_drop_in_api(require_ref):
 def test_queries_respect_worlds_in_a_batched_arena(require_ref):
     """Three copies of one scene in one arena: a query tagged with a world sees only that world's
     fixtures (offset indices), an untagged query sees the three copies."""
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     ref = RefScene("pyramid", 10, 0)
     ref.step(30)
     nf = ref.fixture_count

@@ -7,6 +7,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import oracle.bindings as oracle_bindings  # noqa: E402  (the checker)
 import pytest
 
 from box2d_optimized_b200 import capi
@@ -76,7 +77,7 @@ def test_live_reference_iterates(require_ref, name, size, steps, warm):
         vit = np.zeros((8, nb, 4), np.float32); pit = np.zeros((3, nb, 4), np.float32)
         pos_o, vel_o, man_o = g["pos"].copy(), g["vel"].copy(), g["manifold"].copy()
         done = C.c_int32()
-        capi.load_ref().b2ref_solve(nb, capi.fp(pos_o), capi.fp(vel_o), capi.fp(g["mass"]), len(g["index"]),
+        oracle_bindings.load_ref().b2ref_solve(nb, capi.fp(pos_o), capi.fp(vel_o), capi.fp(g["mass"]), len(g["index"]),
                                     capi.ip(g["index"]), capi.fp(man_o), capi.fp(g["material"]), capi.fp(g["radii"]),
                                     float(g["dt"]), 1.0, 0, 8, 3, capi.fp(vit), capi.fp(pit), C.byref(done))
         g.update(vel_iterates=vit, pos_iterates=pit, pos_out=pos_o, vel_out=vel_o, manifold_out=man_o,

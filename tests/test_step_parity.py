@@ -71,7 +71,7 @@ def test_hello_world_matches_reference_unit_test():
 
 @pytest.mark.parametrize("mode", [capi.SOLVER_COLOURED, capi.SOLVER_SEQUENTIAL])
 def test_pyramid_settles_like_the_reference(require_ref, mode):
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     r = RefScene("pyramid", 20)
     g = GpuScene("pyramid", 20, solver_mode=mode)
     r.step(600)
@@ -97,7 +97,7 @@ def test_pyramid_settles_like_the_reference(require_ref, mode):
 
 def test_mixed_shapes_settle_with_sleeping(require_ref):
     """config 3 at 1/50 scale: circles + convex polygons into a container, sleeping enabled"""
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     n = 2000
     r = RefScene("mixed", n, 12345)
     g = GpuScene("mixed", n, 12345)
@@ -119,7 +119,7 @@ def test_mixed_shapes_settle_with_sleeping(require_ref):
 
 def test_first_steps_track_the_reference_closely(require_ref):
     """before ordering effects accumulate (free fall + first impacts) the trajectories agree tightly"""
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     r = RefScene("falling_circles", 300, 7)
     g = GpuScene("falling_circles", 300, 7)
     r.step(10)
@@ -144,7 +144,7 @@ def test_runs_are_deterministic():
 @pytest.mark.parametrize("name,size,steps", [("pyramid", 20, 80), ("mixed", 3000, 200), ("tumbler", 300, 420)])
 def test_colouring_is_valid(require_ref, name, size, steps):
     """bit-exact integer gate: within one colour no two constraints share a body the solver moves"""
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     s = RefScene(name, size, 12345)
     s.step(steps if name != "tumbler" else steps)
     A = arena_from_scene(s)

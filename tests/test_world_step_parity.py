@@ -86,7 +86,7 @@ def rel(a, b):
                                                    # mouse joints: bodies dragged to targets through loose boxes
                                                    ("mice", 8, 0, 240)])
 def test_every_step_from_the_reference_state(require_ref, name, size, seed, steps):
-    from box2d_optimized_b200 import RefScene
+    from oracle.bindings import RefScene
     ref = RefScene(name, size, seed)
     # the reference creates its first contacts inside the first Step; the tumbler spawns one body per step
     ref.step(size + 2 if name == "tumbler" else 1)
