@@ -272,20 +272,13 @@ class Arena:
         return d
 
 
-def arena_from_scene(scene, max_contacts=None, device=0, num_worlds=1, copies=1):
-    """Builds an arena holding `copies` replicas of a (reference or drop-in) scene's bodies and
-    fixtures, each replica in its own world when num_worlds > 1.  Body state is taken bit-for-bit
-    from the scene, so the arena starts exactly where that scene currently is."""
+def _scene_upload_arrays(scene):
+    """numpy SoA of one scene in the layout the upload calls take"""
     b = scene.bodies()
     p = scene.body_params()
     fx = scene.fixtures()
-    nb, nf, nq = len(b), len(fx["body"]), len(fx["quads"])
-    if max_contacts is None:
-        max_contacts = max(1024, 8 * nb * copies)
     jn = scene.joints()
-    nj = len(jn["bodies"])
-    A = Arena(nb * copies, nf * copies, nq * copies, max_contacts, num_worlds=num_worlds, device=device,
-              max_joints=max(nj * copies, 1))
+    nb = len(b)
     btype = b[:, 11].astype(np.int32)
     mass = p[:, 0]
     inertia_origin = p[:, 1]
@@ -295,24 +288,45 @@ def arena_from_scene(scene, max_contacts=None, device=0, num_worlds=1, copies=1)
     i_center = (inertia_origin - mass * (lc[:, 0] * lc[:, 0] + lc[:, 1] * lc[:, 1])).astype(np.float32)
     inv_i = np.where(i_center > 0, np.float32(1.0) / np.where(i_center > 0, i_center, 1).astype(np.float32), 0).astype(np.float32)
     z = np.zeros(nb, np.float32)
-    pos = np.stack([b[:, 4], b[:, 5], b[:, 6], z], 1)
-    vel = np.stack([b[:, 7], b[:, 8], b[:, 9], z], 1)
-    xf = b[:, 0:4]
-    massq = np.stack([inv_mass, inv_i, mass, p[:, 6]], 1)
-    center = np.stack([lc[:, 0], lc[:, 1], p[:, 4], p[:, 5]], 1)
-    force = np.zeros((nb, 4), np.float32)
-    flags = np.array([body_flags(int(t), awake=bool(a), allow_sleep=bool(s)) for t, a, s in
-                      zip(btype, b[:, 10], p[:, 7])], np.uint32)
     tf = fx["type"].astype(np.uint32) | np.where(fx["sensor"] != 0, capi.FIX_SENSOR, 0).astype(np.uint32)
     filt = np.stack([(fx["filter"][:, 0].astype(np.uint32) & 0xffff) | ((fx["filter"][:, 1].astype(np.uint32) & 0xffff) << 16),
                      fx["filter"][:, 2].astype(np.int32).view(np.uint32)], 1)
+    return dict(
+        nb=nb, nf=len(fx["body"]), nq=len(fx["quads"]), nj=len(jn["bodies"]), fx=fx, jn=jn, tf=tf, filt=filt,
+        pos=np.stack([b[:, 4], b[:, 5], b[:, 6], z], 1), vel=np.stack([b[:, 7], b[:, 8], b[:, 9], z], 1),
+        xf=b[:, 0:4], massq=np.stack([inv_mass, inv_i, mass, p[:, 6]], 1),
+        center=np.stack([lc[:, 0], lc[:, 1], p[:, 4], p[:, 5]], 1), force=np.zeros((nb, 4), np.float32),
+        flags=np.array([body_flags(int(t), awake=bool(a), allow_sleep=bool(s)) for t, a, s in
+                        zip(btype, b[:, 10], p[:, 7])], np.uint32),
+        inv=(inv_mass, inv_i))
+
+
+def arena_from_scene(scene, max_contacts=None, device=0, num_worlds=1, copies=1):
+    """Builds an arena holding `copies` worlds' bodies and fixtures, each in its own world when
+    num_worlds > 1.  `scene` is a (reference or drop-in) scene, or a LIST of scenes with equal body /
+    fixture / shape / joint counts: world k is then scenes[k % len] (batched worlds that are different
+    worlds, not clones).  Body state is taken bit-for-bit from the scene, so the arena starts exactly
+    where that scene currently is."""
+    scenes = list(scene) if isinstance(scene, (list, tuple)) else [scene]
+    arrs = [_scene_upload_arrays(s) for s in scenes]
+    a0 = arrs[0]
+    nb, nf, nq, nj = a0["nb"], a0["nf"], a0["nq"], a0["nj"]
+    for a in arrs[1:]:
+        if (a["nb"], a["nf"], a["nq"], a["nj"]) != (nb, nf, nq, nj):
+            raise ValueError("arena_from_scene: the scenes of one batched arena must have equal counts")
+    if max_contacts is None:
+        max_contacts = max(1024, 8 * nb * copies)
+    A = Arena(nb * copies, nf * copies, nq * copies, max_contacts, num_worlds=num_worlds, device=device,
+              max_joints=max(nj * copies, 1))
     for k in range(copies):
-        A.upload_bodies(k * nb, pos=pos, vel=vel, xf=xf, mass=massq, center=center, force=force, flags=flags,
-                        world=np.full(nb, k if num_worlds > 1 else 0, np.int32))
+        a = arrs[k % len(arrs)]
+        fx, jn = a["fx"], a["jn"]
+        A.upload_bodies(k * nb, pos=a["pos"], vel=a["vel"], xf=a["xf"], mass=a["massq"], center=a["center"],
+                        force=a["force"], flags=a["flags"], world=np.full(nb, k if num_worlds > 1 else 0, np.int32))
         A.upload_shapes(fx["quads"], first=k * nq)
-        A.upload_fixtures(k * nf, body=fx["body"] + k * nb, shape_off=fx["shape_off"] + k * nq, type_flags=tf,
-                          filter=filt, material=fx["material"])
+        A.upload_fixtures(k * nf, body=fx["body"] + k * nb, shape_off=fx["shape_off"] + k * nq, type_flags=a["tf"],
+                          filter=a["filt"], material=fx["material"])
         if nj:
             A.upload_joints(jn["bodies"] + k * nb, jn["anchors"], jn["params"], first=k * nj)
-    A.scene_inv = (inv_mass, inv_i)
+    A.scene_inv = a0["inv"]
     return A
