@@ -37,6 +37,8 @@ struct StepCounts {
   int bpMaxVisits;              // longest single walk
   int numBigBodies;             // bodies of oversize islands (an island can be oversize through joints alone)
   int colourCount[B2G_MAX_COLOURS + 1];
+  int worklistCount;            // uncoloured active constraints of this step (k_mark_active_bins -> k_colour_worklist)
+  int worklistLeft[200];        // per colouring round: somebody is still uncoloured (grid mode)
   unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
 };
 
@@ -105,6 +107,9 @@ struct b2gArena {
   float4 *pos, *vel, *xf, *mass, *center, *force;
   uint32_t* bflags;
   int* bworld;
+  int* worldFixMin;        // [numWorlds] smallest fixture index of each world
+  int* bodyFixBase;        // per body: worldFixMin of its world (colour priorities use world-local pair keys)
+  int fixBaseDirty;
   int* islandParent;       // union-find forest (lock-free unions)
   int* island;             // flattened: island id = smallest body index of the component
   uint32_t* islandAwake;   // per root: some member is awake
@@ -128,6 +133,8 @@ struct b2gArena {
   size_t fusedSmemSet;
   int bigGrid;  // co-resident grid of the persistent big-island kernel
   unsigned int* bigBarrier;  // its grid-barrier counter (zeroed before every launch)
+  int colourGrid;            // co-resident grid of k_colour_worklist
+  unsigned int* colourBarrier;
 
   // fixtures + shapes
   int* fBody;

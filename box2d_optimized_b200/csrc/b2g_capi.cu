@@ -226,6 +226,9 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->force, nb));
   CK(dalloc(&A->bflags, nb));
   CK(dalloc(&A->bworld, nb));
+  CK(dalloc(&A->worldFixMin, A->numWorlds + 1));
+  CK(dalloc(&A->bodyFixBase, nb));
+  A->fixBaseDirty = 1;
   CK(dalloc(&A->island, nb));
   CK(dalloc(&A->islandParent, nb));
   CK(dalloc(&A->islandDirty, nb));
@@ -278,8 +281,10 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->freeStack, nc));
   CK(dalloc(&A->dFreeTop, 1));
   {
+    // >= 4 x max_contacts: live entries (<= max_contacts) plus tombstones (rebuilt away at cap / 4, see
+    // find_new_contacts) can never fill the table, so every probe sequence meets an empty cell
     unsigned int cap = 1024;
-    while (cap < 2u * (unsigned int)nc) cap <<= 1;
+    while (cap < 4u * (unsigned int)nc) cap <<= 1;
     A->hash.mask = cap - 1;
     CK(cudaMalloc((void**)&A->hash.keys, (size_t)cap * 8));
     CK(cudaMalloc((void**)&A->hash.vals, (size_t)cap * 4));
@@ -330,6 +335,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->endEvents, nc));
   CK(dalloc(&A->dCounts, 1));
   CK(dalloc(&A->bigBarrier, 1));
+  CK(dalloc(&A->colourBarrier, 1));
   CK(cudaMallocHost((void**)&A->hCounts, sizeof(StepCounts)));
   memset(A->hCounts, 0, sizeof(StepCounts));
   CK(cudaMallocHost((void**)&A->hostStage, 4096));
@@ -359,7 +365,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   if (!A) return B2G_ERR_INVALID;
   cudaSetDevice(A->device);
   cudaStreamSynchronize(A->stream);
-  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->island, A->islandParent, A->islandDirty, A->islandWasBig,
+  void* ptrs[] = {A->pos, A->vel, A->xf, A->mass, A->center, A->force, A->bflags, A->bworld, A->worldFixMin, A->bodyFixBase, A->island, A->islandParent, A->islandDirty, A->islandWasBig,
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
@@ -369,7 +375,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
                   A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
-                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->cubTemp};
+                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->colourBarrier, A->cubTemp};
   for (void* p : ptrs) cudaFree(p);
   free_contact_buf(A->cb[0]);
   free(A->downloadSlots);
@@ -410,6 +416,7 @@ extern "C" int b2g_upload_bodies(b2gArena* A, int32_t first, int32_t count, cons
   A->aabbAllDirty = 1;
   A->islandsValid = 0;
   if (s->mass || s->flags) A->recolour = 1;
+  if (s->world) A->fixBaseDirty = 1;
   return B2G_OK;
 }
 
@@ -429,6 +436,7 @@ extern "C" int b2g_upload_fixtures(b2gArena* A, int32_t first, int32_t count, co
   if (first + count > A->nFixtures) A->nFixtures = first + count;
   A->aabbAllDirty = 1;
   A->newFixtures = 1;
+  A->fixBaseDirty = 1;
   A->islandsValid = 0;
   return B2G_OK;
 }
@@ -444,6 +452,7 @@ extern "C" int b2g_upload_shapes(b2gArena* A, int32_t first, int32_t count, cons
   CK(cudaStreamSynchronize(A->stream));
   A->aabbAllDirty = 1;
   A->newFixtures = 1;
+  A->fixBaseDirty = 1;
   return B2G_OK;
 }
 
@@ -497,6 +506,7 @@ extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, cons
     A->jointFilterDirty = 1;
     A->aabbAllDirty = 1;
     A->newFixtures = 1;
+    A->fixBaseDirty = 1;
   }
   return B2G_OK;
 }
@@ -525,6 +535,7 @@ extern "C" int b2g_set_counts(b2gArena* A, int32_t nb, int32_t nf, int32_t nj) {
   if (nj != A->nJoints) {
     A->jointFilterDirty = 1;
     A->newFixtures = 1;
+    A->fixBaseDirty = 1;
   }
   A->nJoints = nj;
   A->aabbAllDirty = 1;
@@ -672,19 +683,24 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
     A->nAlive -= A->hCounts->numDead;
     return B2G_ERR_CAPACITY;
   }
+  A->nAlive -= A->hCounts->numDead;
+  // Tombstones keep their cell (a dead pair that comes back revives it) and slow probes down: rebuild the
+  // table from the live contacts once they rival the live entries — BEFORE this step's inserts, so that
+  // live + dead + new entries stay below half of the table whatever died this step.
+  if (A->tombstones > (int)((A->hash.mask + 1) / 4) ||
+      (long long)A->tombstones + A->nAlive + nNew > (long long)(A->hash.mask + 1) / 2) {
+    CK(cudaMemsetAsync(A->hash.keys, 0xff, (size_t)(A->hash.mask + 1) * 8, A->stream));
+    CK(cudaMemsetAsync(A->hash.vals, 0xff, (size_t)(A->hash.mask + 1) * 4, A->stream));
+    if (nSlots > 0)
+      LAUNCH(A, KC_CONTACT_MERGE, nSlots, k_hash_rebuild, div_up(nSlots, 256), 256, nSlots, C, A->hash);
+    A->tombstones = 0;
+  }
   if (nNew > 0) {
     LAUNCH(A, KC_CONTACT_MERGE, nNew, k_contact_insert, div_up(nNew, 256), 256, nNew, A->pairKeys, freeTop, nSlots, C,
            A->persist, A->hash, A->freeStack, A->dFreeTop, A->fBody, A->fTypeFlags, A->fMaterial);
   }
   A->nContacts = nSlots + appended;
-  A->nAlive += nNew - A->hCounts->numDead;
-  // tombstones slow probes down: rebuild the table once they rival the live entries
-  if (A->tombstones > (int)((A->hash.mask + 1) / 4)) {
-    CK(cudaMemsetAsync(A->hash.keys, 0xff, (size_t)(A->hash.mask + 1) * 8, A->stream));
-    CK(cudaMemsetAsync(A->hash.vals, 0xff, (size_t)(A->hash.mask + 1) * 4, A->stream));
-    LAUNCH(A, KC_CONTACT_MERGE, A->nContacts, k_hash_rebuild, div_up(A->nContacts, 256), 256, A->nContacts, C, A->hash);
-    A->tombstones = 0;
-  }
+  A->nAlive += nNew;
   return B2G_OK;
 }
 
@@ -1004,74 +1020,65 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
            A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr, A->dCounts);
 
   int numActive = 0, numBig = 0, rounds = 0;
-  // Colouring rounds.  Constraints of tile-sized islands that are still uncoloured after the rounds
-  // launched simply go to their bin's serial overflow bucket for this step (a handful per bin; they
-  // keep colour -1 and retry next step, when their neighbours are already coloured), so no
-  // convergence loop is needed for them.  Constraints of big islands must all be coloured (their
-  // overflow bucket is one thread for the whole GPU), so there the loop runs to convergence.
-  int round = 0;
-  int cgrid = div_up(nc > 0 ? nc : 1, 256);
-  if (cgrid > 148 * 8) cgrid = 148 * 8;
-  // round 0's proposals were made by k_mark_active_bins; `count` folds the counting pass of the
-  // bucket sort into the last commit (only valid when no further round can follow)
-  auto colour_rounds = [&](int n, bool count) {
-    for (int r = 0; r < n; ++r, ++round) {
-      if (round > 0)
-        LAUNCH(A, KC_COLOUR, nc, k_colour2_propose, cgrid, 256, nc, A->cbin, C, A->mass, A->bodyBest, round);
-      const bool last = r == n - 1;
-      LAUNCH(A, KC_COLOUR, nc, k_colour2_commit, cgrid, 256, nc, A->cbin, C, A->mass, A->colourMask, A->bodyBest,
-             round, A->dCounts, last, bigBin, (last && count) ? A->bucketCount : (int*)nullptr, A->conVals);
+  // Colouring: k_mark_active_bins publishes the persisting colours and lists what is uncoloured,
+  // k_colour_worklist runs every round of the step over that list in one launch, the counting pass of the
+  // (bin, colour) sort rides in both.  The step's counters are copied to the host behind them and only
+  // waited for after the fused kernel has been queued (the answer decides nothing before that point).
+  if (nc > 0) {
+    if (A->numWorlds > 1 && A->fixBaseDirty) {
+      CK(cudaMemsetAsync(A->worldFixMin, 0x7f, sizeof(int) * (size_t)(A->numWorlds + 1), A->stream));
+      LAUNCH(A, KC_COLOUR, A->nFixtures, k_world_fix_min, div_up(A->nFixtures, 256), 256, A->nFixtures, A->fBody, A->bworld,
+             A->worldFixMin);
+      LAUNCH(A, KC_COLOUR, nb, k_body_fix_base, div_up(nb, 256), 256, nb, A->bworld, A->worldFixMin, A->bodyFixBase);
+      A->fixBaseDirty = 0;
     }
-  };
-  auto bucket_sort = [&](bool counted) {
-    if (!counted)
-      LAUNCH(A, KC_COLOUR, nc, k_bucket_count, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketCount, A->conVals);
+    const int* fixBase = A->numWorlds > 1 ? A->bodyFixBase : nullptr;
+    const int nmax = nb > nc ? nb : nc;
+    MarkArgs M;
+    M.nc = nc;
+    M.nb = nb;
+    M.dropColours = A->recolour;
+    M.binSize = binSize;
+    M.bigThreshold = bigThr;
+    M.bigBin = bigBin;
+    M.tileBin0 = -1;
+    M.cutBin = -1;
+    M.tileCap = 1;
+    LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nmax, 256), 256, M, C, A->fTypeFlags, A->bflags, A->island,
+           A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->dCounts, A->mass, A->colourMask, A->islandCursor,
+           A->bodySlot, A->slotBody, A->bodyBest, fixBase, A->activeList, A->bucketCount, A->conVals, (const int*)nullptr,
+           (uint8_t*)nullptr);
+    A->recolour = 0;
+    {
+      if (A->colourGrid == 0) {
+        int perSM = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_colour_worklist, 256, 0));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
+        if (perSM < 1) return B2G_ERR_CUDA;
+        A->colourGrid = sms;
+      }
+      int cutBin = M.cutBin, bb = bigBin;
+      void* args[] = {&C, &A->cbin, &A->mass, &A->colourMask, &A->bodyBest, &fixBase, &A->activeList, &A->dCounts,
+                      &bb, &cutBin, &A->bucketCount, &A->conVals, &A->colourBarrier};
+      CK(cudaMemsetAsync(A->colourBarrier, 0, sizeof(unsigned int), A->stream));
+      ktime_begin(A, KC_COLOUR, nc);
+      // cooperative launch for the co-residency of its grid barrier (the long-worklist mode)
+      CK(cudaLaunchCooperativeKernel((void*)k_colour_worklist, dim3(A->colourGrid), dim3(256), args, 0, A->stream));
+      ktime_end(A);
+      A->launches++;
+    }
+    CK(cudaMemcpyAsync(A->hCounts, A->dCounts, sizeof(StepCounts), cudaMemcpyDeviceToHost, A->stream));
+    CK(cudaEventRecord(A->ev[4], A->stream));
     LAUNCH(A, KC_COLOUR, nbuckets, k_bucket_scan, 1, 1024, nbuckets, A->bucketCount, A->bucketStart);
     LAUNCH(A, KC_COLOUR, nc, k_bucket_scatter, div_up(nc, 256), 256, nc, A->cbin, C, A->bucketStart, A->conVals,
            A->sortedList);
-  };
-  auto converge = [&]() -> int {  // hCounts holds the state after the rounds launched so far
-    while (A->hCounts->remaining != 0 && A->hCounts->numBig != 0) {
-      if (round > 250) {
-        set_err("b2g_step", "graph colouring did not converge");
-        return B2G_ERR_CUDA;
-      }
-      CK(cudaMemsetAsync(&A->dCounts->remaining, 0, sizeof(int), A->stream));
-      colour_rounds(4, false);
-      int rc = read_counts(A);
-      if (rc) return rc;
-    }
-    return B2G_OK;
-  };
-  // The mid-step readback (colouring state, size of the big set).  When the previous step had no
-  // oversize island the answer is almost always "none" again, so the copy is only ENQUEUED and is
-  // waited for after the bucket sort and the fused kernel have been queued behind it: the host
-  // wait then overlaps the GPU's work instead of draining the stream.
-  const bool speculative = nc > 0 && A->lastNumBig == 0 && !A->kernelTiming;
-  if (nc > 0) {
-    const int nmax = nb > nc ? nb : nc;
-    LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nmax, 256), 256, nc, C, A->fTypeFlags, A->bflags, A->island,
-           A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->recolour, binSize, bigThr, bigBin, A->dCounts,
-           A->mass, A->colourMask, nb, A->islandCursor, A->bodySlot, A->slotBody, A->bodyBest);
-    A->recolour = 0;
-    colour_rounds(A->lastNumBig > 0 ? A->roundsHint : 2, speculative);
-    if (speculative) {
-      CK(cudaMemcpyAsync(A->hCounts, A->dCounts, sizeof(StepCounts), cudaMemcpyDeviceToHost, A->stream));
-      CK(cudaEventRecord(A->ev[4], A->stream));
-      bucket_sort(true);
-    } else {
-      int rc = read_counts(A);
-      if (rc) return rc;
-      rc = converge();
-      if (rc) return rc;
-      if (A->hCounts->numActive > 0) bucket_sort(false);
-    }
   }
 
   // ---- every island that fits a tile: one launch -----------------------------------------------
+  int fusedKt = -1;
   {
     FusedParams FP;
-    FP.nc = (speculative || (nc > 0 && A->hCounts->numActive > 0)) ? nc : 0;
+    FP.nc = nc;
     FP.binSize = binSize;
     FP.h = h;
     FP.dtRatio = dtRatio;
@@ -1089,7 +1096,8 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       CK(cudaFuncSetAttribute(k_solve_bins_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       A->fusedSmemSet = smem;
     }
-    ktime_begin(A, KC_FUSED_SOLVE, nc > 0 && !speculative ? (double)A->hCounts->numActive - A->hCounts->numBig : 0.0);
+    fusedKt = A->kernelTiming ? A->ktCount : -1;  // its unit count is only known after the readback below
+    ktime_begin(A, KC_FUSED_SOLVE, 0.0);
     launch_pdl(A->stream, dim3(nbins), dim3(fusedThreads), smem, k_solve_bins_fused,
         FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->bucketStart,
         A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts,
@@ -1099,22 +1107,11 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   }
 
   if (nc > 0) {
-    if (speculative) {
-      CK(cudaEventSynchronize(A->ev[4]));  // the copy finished long ago; the fused kernel is still running
-      if (A->hCounts->numBig > 0) {
-        // an oversize island appeared this step: finish its colouring and sort again (the fused
-        // kernel has consumed its own buckets; the big bin is all the big path reads)
-        int rc = converge();
-        if (rc) return rc;
-        CK(cudaMemsetAsync(A->bucketCount, 0, sizeof(int) * (size_t)nbuckets, A->stream));
-        bucket_sort(false);
-      }
-    }
-    rounds = round;
-    int useful = A->hCounts->lastUsefulRound;
-    A->roundsHint = useful < 1 ? 1 : (useful + 1 < 16 ? useful + 1 : 16);
+    CK(cudaEventSynchronize(A->ev[4]));  // the copy finished long ago; the fused kernel is still running
+    rounds = A->hCounts->lastUsefulRound;
     numActive = A->hCounts->numActive;
     numBig = A->hCounts->numBig;
+    if (fusedKt >= 0 && fusedKt < B2G_KT_MAX) A->ktUnits[fusedKt] = (double)numActive - numBig;
     out.numColours = A->hCounts->numColours;
     out.numOverflow = A->hCounts->numOverflow + A->hCounts->remaining;
     A->lastOverflow = out.numOverflow;

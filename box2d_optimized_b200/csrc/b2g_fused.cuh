@@ -80,16 +80,61 @@ __global__ void k_body_scatter(int nb, const uint32_t* __restrict__ bflags, cons
                    counts);
 }
 
+// ---- colouring -------------------------------------------------------------------------------------
+// Colours persist on the contact from step to step; what has to be coloured in a step is only what was
+// born (or lost its colour) since the last one.  k_mark_active_bins classifies every contact slot, re-
+// publishes the persisting colours and appends the uncoloured active constraints to a WORKLIST;
+// k_colour_worklist then runs every Luby round of the step over that list inside one launch.
+//
+// Two colour domains share the 64-bit per-body mask: bits 0..23 for constraints solved inside one CTA
+// (island bins, tiles of an oversize island), bits 32..55 for the CUT constraints of a tiled oversize
+// island, which are solved in separate grid-wide passes and therefore only have to be conflict-free
+// among themselves.  The stored colour is the bit index; its low five bits select the bucket.
+#define B2G_CUT_DOMAIN_SHIFT 32
+__device__ __forceinline__ unsigned long long colour_domain_mask(int domain) {
+  return ((1ull << B2G_MAX_COLOURS) - 1ull) << (domain ? B2G_CUT_DOMAIN_SHIFT : 0);
+}
+// Pair key with WORLD-LOCAL fixture indices: world k of a batched arena then draws the same priorities,
+// hence the same colours and the same floats, as that world stepped alone.
+__device__ __forceinline__ unsigned long long local_pair_key(unsigned long long key, const int* __restrict__ bodyFixBase,
+                                                            int body) {
+  if (!bodyFixBase) return key;
+  unsigned long long base = (unsigned long long)(unsigned int)bodyFixBase[body];
+  return key - ((base << 32) | base);
+}
+__global__ void k_world_fix_min(int nf, const int* __restrict__ fBody, const int* __restrict__ bworld, int* worldFixMin) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  atomicMin(&worldFixMin[bworld[fBody[f]]], f);
+}
+__global__ void k_body_fix_base(int nb, const int* __restrict__ bworld, const int* __restrict__ worldFixMin,
+                                int* bodyFixBase) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int m = worldFixMin[bworld[b]];
+  bodyFixBase[b] = m == 0x7f7f7f7f ? 0 : m;
+}
+
+struct MarkArgs {
+  int nc, nb;
+  int dropColours, binSize, bigThreshold, bigBin;
+  int tileBin0;   // bin of tile 0 of a tiled oversize island (tile t -> tileBin0 + t), or -1: not tiled
+  int cutBin;     // bin of the cut constraints of the tiled island (the second colour domain)
+  int tileCap;
+};
+
 // Also carries two neighbours that depend on the same inputs and on nothing else, to save their
 // launches: the body scatter (thread i handles body i) and round 0 of the colouring proposals.
-__global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restrict__ fTypeFlags,
+__global__ void k_mark_active_bins(MarkArgs M, ContactBuf C, const uint32_t* __restrict__ fTypeFlags,
                                    const uint32_t* __restrict__ bflags, const int* __restrict__ island,
                                    const uint32_t* __restrict__ islandAwake, const int* __restrict__ islandCount,
-                                   const int* __restrict__ islandStart, int* cbin, int dropColours, int binSize,
-                                   int bigThreshold, int bigBin, StepCounts* counts, const float4* __restrict__ mass,
-                                   unsigned long long* colourMask, int nb, int* islandCursor, int* bodySlot,
-                                   int* slotBody, unsigned long long* bodyBest) {
+                                   const int* __restrict__ islandStart, int* cbin, StepCounts* counts,
+                                   const float4* __restrict__ mass, unsigned long long* colourMask, int* islandCursor,
+                                   int* bodySlot, int* slotBody, unsigned long long* bodyBest,
+                                   const int* __restrict__ bodyFixBase, int* worklist, int* bucketCount, int* rank,
+                                   const int* __restrict__ tileSlot, uint8_t* tileBoundary) {
   B2G_PDL_ENTER();
+  const int nc = M.nc, nb = M.nb, bigThreshold = M.bigThreshold, bigBin = M.bigBin;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nb) body_scatter_one(i, bflags, island, islandAwake, islandCount, islandStart, islandCursor, bodySlot, slotBody,
                                bigThreshold, counts);
@@ -101,7 +146,7 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
   int2 fx = C.fix[i];
   int c = C.colour[i];
   uint32_t tfa = fTypeFlags[fx.x], tfb = fTypeFlags[fx.y];
-  uint32_t bfa = bflags[bd.x];
+  uint32_t bfa = bflags[bd.x], bfb = bflags[bd.y];
   int ia = island[bd.x], ib = island[bd.y];
   float4 massA = mass[bd.x], massB = mass[bd.y];
   int root = B2G_BODY_TYPE(bfa) != B2G_STATIC ? ia : ib;
@@ -112,98 +157,161 @@ __global__ void k_mark_active_bins(int nc, ContactBuf C, const uint32_t* __restr
   if (active) active = awake != 0;
   int bin = -1;
   if (active) {
-    bin = icount > bigThreshold ? bigBin : istart / binSize;
+    if (icount > bigThreshold) {
+      bin = bigBin;
+      if (M.tileBin0 >= 0) {
+        // tiled oversize island: interior to a tile when every non-static body of the constraint sits in
+        // that tile; anything else (two tiles, a body that did not fit its tile) is a cut constraint
+        int ta = B2G_BODY_TYPE(bfa) != B2G_STATIC ? tileSlot[bd.x] : -2;
+        int tb = B2G_BODY_TYPE(bfb) != B2G_STATIC ? tileSlot[bd.y] : -2;
+        int tA = ta >= 0 ? ta / M.tileCap : ta, tB = tb >= 0 ? tb / M.tileCap : tb;
+        if (tA >= 0 && (tB == tA || tB == -2)) bin = M.tileBin0 + tA;
+        else if (tA == -2 && tB >= 0) bin = M.tileBin0 + tB;
+        else {
+          bin = M.cutBin;
+          if (ta >= 0) tileBoundary[ta] = 1;
+          if (tb >= 0) tileBoundary[tb] = 1;
+        }
+      }
+      atomicAdd(&counts->numBig, 1);
+    } else {
+      bin = istart / M.binSize;
+    }
     auto g = cg::coalesced_threads();
     if (g.thread_rank() == 0) atomicAdd(&counts->numActive, (int)g.size());
-    if (bin == bigBin) atomicAdd(&counts->numBig, 1);
   }
   cbin[i] = bin;
-  if (!active || dropColours || c >= B2G_MAX_COLOURS) {
-    // inactive contacts lose their colour; overflow constraints retry every step
+  const int domain = (active && bin == M.cutBin && M.cutBin >= 0) ? 1 : 0;
+  if (!active || M.dropColours || (c & 31) >= B2G_MAX_COLOURS || (c >> 5) != domain) {
+    // inactive contacts lose their colour; overflow constraints retry every step; a constraint that
+    // changed sides (tile interior <-> cut) is coloured again in its new domain
     if (c != -1) C.colour[i] = -1;
     c = -1;
   }
-  // colours persist from step to step: publish the ones still in use (was k_colour_begin)
+  // colours persist from step to step: publish the ones still in use, and count them into their bucket
   if (c >= 0) {
     unsigned long long bit = 1ull << c;
     if (body_movable(massA)) atomicOr(&colourMask[bd.x], bit);
     if (body_movable(massB)) atomicOr(&colourMask[bd.y], bit);
-    if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
-    if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
+    if (bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
+    if ((c & 31) + 1 > counts->numColours) atomicMax(&counts->numColours, (c & 31) + 1);
+    rank[i] = atomicAdd(&bucketCount[(bin << B2G_COLOUR_BITS) | (c & 31)], 1);
   } else if (active) {
-    // round 0 of the colouring (k_colour2_propose with round = 0)
-    unsigned long long pr = colour_priority(0, i, C.key[i]);
+    // to the worklist + round 0 of the proposals
+    {
+      auto g = cg::coalesced_threads();
+      int base = 0;
+      if (g.thread_rank() == 0) base = atomicAdd(&counts->worklistCount, (int)g.size());
+      worklist[g.shfl(base, 0) + g.thread_rank()] = i;
+    }
+    unsigned long long pr = colour_priority(0, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
     if (body_movable(massA)) atomicMax(&bodyBest[bd.x], pr);
     if (body_movable(massB)) atomicMax(&bodyBest[bd.y], pr);
   }
 }
 
-__global__ void k_colour2_propose(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
-                                  unsigned long long* bodyBest, int round) {
-  B2G_PDL_ENTER();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
-    if (cbin[i] < 0 || C.colour[i] >= 0) continue;
-    int2 bd = C.body[i];
-    unsigned long long pr = colour_priority(round, i, C.key[i]);
-    if (body_movable(mass[bd.x])) atomicMax(&bodyBest[bd.x], pr);
-    if (body_movable(mass[bd.y])) atomicMax(&bodyBest[bd.y], pr);
-  }
-}
+// Grid barrier of the persistent kernels (split into arrive / wait further down); forward declarations
+__device__ __forceinline__ void grid_arrive(unsigned int* counter, unsigned int& target);
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int target);
 
-// bucketCount != nullptr (only on the final round of a step without oversize islands): also the
-// counting pass of the (bin, colour) sort — every active constraint knows its final colour here.
-__global__ void k_colour2_commit(int nc, const int* __restrict__ cbin, ContactBuf C, const float4* __restrict__ mass,
-                                 unsigned long long* colourMask, const unsigned long long* __restrict__ bodyBest,
-                                 int round, StepCounts* counts, int lastOfBatch, int bigBin, int* bucketCount,
-                                 int* rank) {
-  B2G_PDL_ENTER();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
-    int bin = cbin[i];
-    if (bin < 0) continue;
-    int c = C.colour[i];
-    if (c < 0) {
-      int2 bd = C.body[i];
-      unsigned long long pr = colour_priority(round, i, C.key[i]);
-      bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
-      bool win = (!movA || bodyBest[bd.x] == pr) && (!movB || bodyBest[bd.y] == pr);
+// Every colouring round of the step in ONE launch.  Deterministic Luby rounds: an uncoloured constraint
+// that holds the highest priority on both of its movable bodies takes the lowest colour free on both (of
+// its domain).  Priorities carry the round number in their top bits, so bodyBest never has to be cleared.
+// A short worklist (the steady state: a few hundred births per step) is handled by block 0 alone with CTA
+// barriers; a long one (first step, an avalanche) by the whole co-resident grid with grid barriers.
+// The last pass counts the newly coloured constraints into their (bin, colour) buckets.
+#define B2G_WL_SINGLE_MAX 8192
+#define B2G_WL_MAX_ROUNDS 200
+__global__ void __launch_bounds__(256)
+k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __restrict__ mass,
+                  unsigned long long* colourMask, unsigned long long* bodyBest, const int* __restrict__ bodyFixBase,
+                  const int* __restrict__ worklist, StepCounts* counts, int bigBin, int cutBin, int* bucketCount,
+                  int* rank, unsigned int* barrier) {
+  const int n = __ldcg(&counts->worklistCount);
+  if (n == 0) return;
+  const bool single = n <= B2G_WL_SINGLE_MAX;
+  if (single && blockIdx.x != 0) return;
+  const int stride = single ? blockDim.x : gridDim.x * blockDim.x;
+  const int t0 = single ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int target = 0;
+  auto sync_all = [&]() {
+    if (single) {
+      __syncthreads();
+    } else {
+      grid_arrive(barrier, target);
+      grid_wait(barrier, target);
+    }
+  };
+  int round = 0;
+  for (;; ++round) {
+    // commit
+    int left = 0;
+    for (int k = t0; k < n; k += stride) {
+      const int i = worklist[k];
+      if (__ldcg(&C.colour[i]) >= 0) continue;
+      const int2 bd = C.body[i];
+      const unsigned long long pr = colour_priority(round, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
+      const bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
+      const bool win = (!movA || __ldcg(&bodyBest[bd.x]) == pr) && (!movB || __ldcg(&bodyBest[bd.y]) == pr);
       if (win) {
-        unsigned long long used = (movA ? colourMask[bd.x] : 0ull) | (movB ? colourMask[bd.y] : 0ull);
-        unsigned long long freeBits = ~used & ((1ull << B2G_MAX_COLOURS) - 1ull);
-        c = freeBits ? (__ffsll((long long)freeBits) - 1) : B2G_OVERFLOW_COLOUR;
-        C.colour[i] = c;
-        if (c < B2G_MAX_COLOURS) {
-          unsigned long long bit = 1ull << c;
-          if (movA) colourMask[bd.x] |= bit;
-          if (movB) colourMask[bd.y] |= bit;
-          if (c + 1 > counts->numColours) atomicMax(&counts->numColours, c + 1);
+        const int bin = cbin[i];
+        const int domain = (bin == cutBin && cutBin >= 0) ? 1 : 0;
+        const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
+        const unsigned long long freeBits = ~used & colour_domain_mask(domain);
+        const int c = freeBits ? (__ffsll((long long)freeBits) - 1)
+                               : B2G_OVERFLOW_COLOUR + (domain ? B2G_CUT_DOMAIN_SHIFT : 0);
+        __stcg(&C.colour[i], c);
+        if ((c & 31) < B2G_MAX_COLOURS) {
+          // the winner is unique on each of its movable bodies, so plain read-modify-write is race free
+          const unsigned long long bit = 1ull << c;
+          if (movA) __stcg(&colourMask[bd.x], __ldcg(&colourMask[bd.x]) | bit);
+          if (movB) __stcg(&colourMask[bd.y], __ldcg(&colourMask[bd.y]) | bit);
+          if ((c & 31) + 1 > counts->numColours) atomicMax(&counts->numColours, (c & 31) + 1);
         } else {
           atomicAdd(&counts->numOverflow, 1);
         }
-        if (bin == bigBin) atomicAdd(&counts->colourCount[c], 1);
-        if (counts->lastUsefulRound < round + 1) atomicMax(&counts->lastUsefulRound, round + 1);
-      } else if (lastOfBatch) {
-        atomicAdd(&counts->remaining, 1);
+        if (bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
+      } else {
+        left = 1;
       }
     }
-    if (bucketCount) {
-      if (c < 0) c = B2G_OVERFLOW_COLOUR;  // not coloured within this step's rounds: serial bucket, retried next step
-      rank[i] = atomicAdd(&bucketCount[(bin << B2G_COLOUR_BITS) | c], 1);
+    if (round + 1 >= B2G_WL_MAX_ROUNDS) break;
+    // anything left anywhere?
+    int any;
+    if (single) {
+      any = __syncthreads_or(left);
+    } else {
+      if (left) atomicOr(&counts->worklistLeft[round], 1);
+      sync_all();
+      any = __ldcg(&counts->worklistLeft[round]);
     }
+    if (!any) break;
+    // propose for the next round
+    for (int k = t0; k < n; k += stride) {
+      const int i = worklist[k];
+      if (__ldcg(&C.colour[i]) >= 0) continue;
+      const int2 bd = C.body[i];
+      const unsigned long long pr = colour_priority(round + 1, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
+      if (body_movable(mass[bd.x])) atomicMax(&bodyBest[bd.x], pr);
+      if (body_movable(mass[bd.y])) atomicMax(&bodyBest[bd.y], pr);
+    }
+    sync_all();
   }
-}
-
-// Counting sort of the active constraints by bucket = bin * 32 + colour.  Order INSIDE a bucket is
-// whatever the atomics give: constraints of one colour never share a movable body, so any order
-// produces bit-identical results.
-__global__ void k_bucket_count(int nc, const int* __restrict__ cbin, ContactBuf C, int* bucketCount, int* rank) {
-  B2G_PDL_ENTER();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nc) return;
-  int bin = cbin[i];
-  if (bin < 0) return;
-  int c = C.colour[i];
-  if (c < 0) c = B2G_OVERFLOW_COLOUR;  // not coloured within this step's rounds: serial bucket, retried next step
-  rank[i] = atomicAdd(&bucketCount[(bin << B2G_COLOUR_BITS) | c], 1);
+  sync_all();
+  // bucket counting of what this launch coloured (constraints left uncoloured after the round limit go to
+  // their bin's serial bucket for this step and retry in the next one)
+  int leftover = 0;
+  for (int k = t0; k < n; k += stride) {
+    const int i = worklist[k];
+    int c = __ldcg(&C.colour[i]);
+    if (c < 0) {
+      c = B2G_OVERFLOW_COLOUR;
+      ++leftover;
+    }
+    rank[i] = atomicAdd(&bucketCount[(cbin[i] << B2G_COLOUR_BITS) | (c & 31)], 1);
+  }
+  if (leftover) atomicAdd(&counts->remaining, leftover);
+  if (t0 == 0) counts->lastUsefulRound = round + 1;
 }
 
 // exclusive scan of the bucket counts by one block (buckets = bins x 32: ~10 k entries for one
@@ -276,7 +384,7 @@ __global__ void k_bucket_scatter(int nc, const int* __restrict__ cbin, ContactBu
   if (bin < 0) return;
   int c = C.colour[i];
   if (c < 0) c = B2G_OVERFLOW_COLOUR;
-  sortedList[bucketStart[(bin << B2G_COLOUR_BITS) | c] + rank[i]] = i;
+  sortedList[bucketStart[(bin << B2G_COLOUR_BITS) | (c & 31)] + rank[i]] = i;
 }
 
 // The overflow bucket is the only place where constraint ORDER matters (one thread, Gauss-Seidel in

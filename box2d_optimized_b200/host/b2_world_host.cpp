@@ -56,6 +56,9 @@ struct b2WorldImpl {
   bool bodiesStale = false;    // device has newer body state than the host copies
   bool contactsStale = true;   // host contact list does not reflect the device
   bool profiling = false;
+  bool deadFixtures = false;   // a fixture was destroyed and the device may still hold contacts naming it
+  float lastInvDt = 0.0f;      // b2World::m_inv_dt0 (b2_world.cpp:1162): survives an arena re-creation
+  bool arenaFresh = false;     // the arena was (re-)created since the last flush
   std::vector<b2Contact*> contacts;                       // current list, device order
   std::unordered_map<uint64_t, b2Contact*> contactPool;   // (fixA,fixB) -> handle, stable across steps
   b2Contact sentinel;
@@ -144,6 +147,7 @@ void b2WorldImpl::ensureArena() {
   fixtureDirtyHi = needFixtures;
   jointsDirty = needJoints > 0;
   jointsOnDevice = 0;
+  arenaFresh = true;
   world->m_newContacts = true;
 }
 
@@ -359,6 +363,12 @@ void b2WorldImpl::flush() {
     saved = SavedContacts();
     world->m_newContacts = true;
   }
+  if (arenaFresh) {
+    // warm starting scales last step's impulses by dt * inv_dt0 (b2_world.cpp:1130): a new arena starts at
+    // the world's inv_dt0, not at zero, or the first step after any growth would drop every impulse
+    b2gCheck(b2g_set_inv_dt0(arena, lastInvDt), "b2g_set_inv_dt0");
+    arenaFresh = false;
+  }
 }
 
 // every site that edits the joint table calls this first, so `joints` and the device agree on order
@@ -398,8 +408,10 @@ void b2WorldImpl::pullBodies() {
     b->m_force.Set(force[(size_t)i * 4], force[(size_t)i * 4 + 1]);
     b->m_torque = force[(size_t)i * 4 + 2];
     b->m_sleepTime = force[(size_t)i * 4 + 3];
-    uint16 keep = b->m_flags & ~(uint16)b2Body::e_awakeFlag;
-    b->m_flags = keep | (uint16)(flags[i] & B2G_BODY_AWAKE);
+    // the device's pending SetAwake(true) (set by Collide, consumed by Solve) rides along, so that an upload
+    // of this body between the two halves of a step does not drop it
+    uint16 keep = b->m_flags & ~(uint16)(b2Body::e_awakeFlag | B2G_BODY_WAKE_REQUEST);
+    b->m_flags = keep | (uint16)(flags[i] & (B2G_BODY_AWAKE | B2G_BODY_WAKE_REQUEST));
   }
 }
 
@@ -423,6 +435,23 @@ static void unpackManifold(b2Manifold& m, const float* q) {
 void b2WorldImpl::pullContacts() {
   if (!contactsStale) return;
   contactsStale = false;
+  if (deadFixtures && arena && !world->m_locked) {
+    // b2Body::DestroyFixture / b2World::DestroyBody remove the fixture's contacts at once in the reference
+    // (b2_body.cpp:244-259).  Here they die with the next pair refresh, so run it now: the list handed out
+    // must never name a destroyed fixture.
+    deadFixtures = false;
+    flush();
+    int rc = b2g_find_new_contacts(arena);
+    for (int attempt = 0; rc == B2G_ERR_CAPACITY && attempt < 8; ++attempt) {
+      growContacts();
+      rc = b2g_find_new_contacts(arena);
+    }
+    b2gCheck(rc, "b2g_find_new_contacts");
+    world->m_newContacts = false;
+    contactsStale = false;
+    applyContactFilter();
+    contactsStale = false;
+  }
   for (b2Body* b : bodies)
     if (b) b->m_contacts.clear();
   int32 n = 0;
@@ -609,6 +638,7 @@ void b2World::DestroyBody(b2Body* b) {
     b2Fixture* nx = f->m_next;
     if (m_destructionListener) m_destructionListener->SayGoodbye(f);
     m_impl->fixtures[f->m_index] = nullptr;
+    m_impl->deadFixtures = true;
     m_impl->touchFixture(f->m_index);
     delete f->m_shape;
     delete f;
@@ -806,6 +836,9 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
 
   if (m_contactListener == nullptr) {
     int rc = b2g_step(I->arena, &P, &I->lastStats);
+    I->bodiesStale = true;
+    I->jointsStale = true;
+    if (dt > 0.0f) I->lastInvDt = 1.0f / dt;
     if (rc == B2G_ERR_CAPACITY) {
       I->growContacts();
       rc = B2G_OK;
@@ -843,7 +876,16 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
       }
     }
     I->pushContactOverrides();
+    // impulses, forces and velocities the callbacks applied act in THIS step's solve, as in the reference
+    // (the listener runs inside Collide, before Solve): upload what they touched.  The host copies are the
+    // device's post-Collide state (every setter pulls before it edits), so the range upload is consistent.
+    if (I->bodyDirtyHi > I->bodyDirtyLo) I->flush();
     int rc = b2g_step_solve(I->arena, &P, &I->lastStats);
+    // from here on getters must see the solved state (PostSolve / EndContact callbacks below read it, and
+    // whatever they edit is an edit of that state, uploaded by the next Step)
+    I->bodiesStale = true;
+    I->jointsStale = true;
+    if (dt > 0.0f) I->lastInvDt = 1.0f / dt;
     if (rc == B2G_ERR_CAPACITY) {
       I->growContacts();
       rc = B2G_OK;
@@ -872,8 +914,6 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
   }
   for (b2Contact* c : I->graveyard) delete c;
   I->graveyard.clear();
-  I->bodiesStale = true;
-  I->jointsStale = true;
   I->contactsStale = true;
   if (I->profiling) {
     m_profile.step = I->lastStats.ms_step;
@@ -1014,6 +1054,7 @@ void b2Body::DestroyFixture(b2Fixture* fixture) {
     node = &(*node)->m_next;
   }
   I->fixtures[fixture->m_index] = nullptr;
+  I->deadFixtures = true;
   I->touchFixture(fixture->m_index);
   for (auto& kv : I->contactPool) delete kv.second;
   I->contactPool.clear();

@@ -16,6 +16,7 @@
 //   many_pyramids  `size` copies of it 30 m apart on one ground edge (config 2)
 //   mixed          circles + convex polygons dropped into a 3-box container, LCG seed (config 3)
 //   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
+//   filters        category / mask / group filtering (b2_world_callbacks.cpp:28-40), all three group signs
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
 //   welds          weld joints: cantilever beams, a welded compound (b2_weld_joint.cpp)
 //   cars           wheel joints: sprung, motorised cars driving over ramps and loose boxes (b2_wheel_joint.cpp)
@@ -733,6 +734,61 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
         sd.shape = &probe;
         s->addFixture(body, sd);
       }
+    }
+  } else if (name == "filters") {
+    // b2ContactFilter::ShouldCollide (b2_world_callbacks.cpp:28-40): category / mask bits and group indices.
+    // Boxes and balls fall through each other or collide depending on their filter:
+    //   group +1 : always collide with each other (even though their masks would say no)
+    //   group -2 : never collide with each other (they pile up INSIDE one another on the floor)
+    //   group  0 : category/mask rule: "red" (0x2) sees floor + blue, "blue" (0x4) sees floor + red + blue,
+    //              "ghost" (0x8, mask 0x1) sees only the floor, and nobody's mask names the ghosts
+    // plus a shelf (category 0x10) that only the blue ones rest on.
+    int n = size > 0 ? size : 120;
+    {
+      b2BodyDef bd;
+      b2Body* ground = s->addBody(bd);
+      b2PolygonShape floor;
+      floor.SetAsBox(30.0f, 1.0f, b2Vec2(0.0f, -1.0f), 0.0f);
+      b2FixtureDef fd;
+      fd.shape = &floor;
+      fd.filter.categoryBits = 0x0001;
+      fd.filter.maskBits = 0xFFFF;
+      s->addFixture(ground, fd);
+      b2PolygonShape shelf;
+      shelf.SetAsBox(12.0f, 0.25f, b2Vec2(0.0f, 6.0f), 0.0f);
+      fd.shape = &shelf;
+      fd.filter.categoryBits = 0x0010;
+      fd.filter.maskBits = 0x0004;
+      s->addFixture(ground, fd);
+    }
+    SceneLCG rng((uint32_t)(seed > 0 ? seed : 99));
+    int cols = 12;
+    for (int i = 0; i < n; ++i) {
+      b2BodyDef bd;
+      bd.type = b2_dynamicBody;
+      bd.position.Set(-10.0f + 1.7f * (float)(i % cols) + rng.range(-0.3f, 0.3f), 8.0f + 1.4f * (float)(i / cols));
+      bd.angle = rng.range(-0.5f, 0.5f);
+      b2Body* body = s->addBody(bd);
+      b2FixtureDef fd;
+      fd.density = 1.0f;
+      fd.friction = 0.3f;
+      b2PolygonShape box;
+      b2CircleShape ball;
+      if (i & 1) {
+        ball.m_radius = rng.range(0.3f, 0.55f);
+        fd.shape = &ball;
+      } else {
+        box.SetAsBox(rng.range(0.3f, 0.6f), rng.range(0.3f, 0.6f));
+        fd.shape = &box;
+      }
+      switch (i % 5) {
+        case 0: fd.filter.categoryBits = 0x0002; fd.filter.maskBits = 0x0001 | 0x0004; break;            // red
+        case 1: fd.filter.categoryBits = 0x0004; fd.filter.maskBits = 0x0001 | 0x0002 | 0x0004 | 0x0010; break;  // blue
+        case 2: fd.filter.categoryBits = 0x0008; fd.filter.maskBits = 0x0001; break;                     // ghost
+        case 3: fd.filter.categoryBits = 0x0020; fd.filter.maskBits = 0x0001; fd.filter.groupIndex = 1; break;   // group +1
+        default: fd.filter.categoryBits = 0x0040; fd.filter.maskBits = 0xFFFF; fd.filter.groupIndex = -2; break;  // group -2
+      }
+      s->addFixture(body, fd);
     }
   } else if (name == "hello") {
     s->velocityIterations = 6;

@@ -767,6 +767,82 @@ static void mouse_joint_api() {
          body->GetPosition().y);
 }
 
+// Body edits made INSIDE contact callbacks (the world is locked, but impulses and velocity setters are
+// allowed there, b2_body.h): an impulse applied in BeginContact acts in the same step's solve, a velocity set
+// in PostSolve survives the step (b2_contact.cpp:197-209, b2_island.cpp:430-441).
+struct KickListener : public b2ContactListener {
+  b2Body* ball = nullptr;
+  b2Body* roller = nullptr;
+  int kicks = 0, spins = 0;
+  float vyAtBegin = 0.0f, rollerYAtPostSolve = 0.0f, rollerVyAtPostSolve = 1.0f;
+  void BeginContact(b2Contact* c) override {
+    b2Body* a = c->GetFixtureA()->GetBody();
+    b2Body* b = c->GetFixtureB()->GetBody();
+    if ((a == ball || b == ball) && kicks == 0) {
+      vyAtBegin = ball->GetLinearVelocity().y;
+      ball->ApplyLinearImpulse(b2Vec2(0.0f, 12.0f * ball->GetMass()), ball->GetWorldCenter(), true);
+      ++kicks;
+    }
+  }
+  void PostSolve(b2Contact* c, const b2ContactImpulse*) override {
+    b2Body* a = c->GetFixtureA()->GetBody();
+    b2Body* b = c->GetFixtureB()->GetBody();
+    if ((a == roller || b == roller) && spins == 0) {
+      rollerYAtPostSolve = roller->GetPosition().y;          // post-solve state: resting on the ground
+      rollerVyAtPostSolve = roller->GetLinearVelocity().y;
+      roller->SetAngularVelocity(-3.0f);
+      ++spins;
+    }
+  }
+};
+static void edits_inside_callbacks() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  KickListener L;
+  world.SetContactListener(&L);
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2EdgeShape edge;
+  edge.SetTwoSided(b2Vec2(-30.0f, 0.0f), b2Vec2(30.0f, 0.0f));
+  ground->CreateFixture(&edge, 0.0f);
+  b2CircleShape circle;
+  circle.m_radius = 0.5f;
+  b2BodyDef bd;
+  bd.type = b2_dynamicBody;
+  bd.position.Set(0.0f, 2.0f);
+  b2Body* ball = world.CreateBody(&bd);
+  ball->CreateFixture(&circle, 1.0f);
+  bd.position.Set(6.0f, 1.0f);
+  b2Body* roller = world.CreateBody(&bd);
+  b2FixtureDef fd;
+  fd.shape = &circle;
+  fd.density = 1.0f;
+  fd.friction = 0.8f;
+  roller->CreateFixture(&fd);
+  L.ball = ball;
+  L.roller = roller;
+  b2Body* b[2] = {ball, roller};
+  float vyAfterKick = 0.0f, top = 0.0f;
+  for (int i = 0; i < 120; ++i) {
+    int before = L.kicks;
+    world.Step(1.0f / 60.0f, 8, 3);
+    if (before == 0 && L.kicks == 1) vyAfterKick = ball->GetLinearVelocity().y;
+    if (ball->GetPosition().y > top) top = ball->GetPosition().y;
+    if (i % 20 == 19) {
+      char tag[32];
+      snprintf(tag, sizeof(tag), "callbacks%d", i + 1);
+      trace(tag, world, b, 2);
+    }
+  }
+  CHECK(L.kicks == 1 && L.spins == 1);
+  CHECK(L.vyAtBegin < -4.0f);                 // it was falling when it touched
+  CHECK(vyAfterKick > 5.0f);                  // the impulse acted in the SAME step: the ball leaves upwards
+  CHECK(top > 2.3f);                          // ... and flies above its drop height (6.33^2 / 2g + 0.5)
+  CHECK(fabsf(L.rollerYAtPostSolve - 0.5f) < 0.05f && fabsf(L.rollerVyAtPostSolve) < 0.5f);  // PostSolve sees the solved state
+  CHECK(roller->GetPosition().x > 6.5f);      // the spin set in PostSolve survived: it rolled to the right
+  printf("callbacks: vy at begin %.4f, after the kick %.4f, apex %.4f, roller x %.4f\n", L.vyAtBegin, vyAfterKick, top,
+         roller->GetPosition().x);
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -784,6 +860,7 @@ int main() {
   contact_buffers_grow();
   world_editing_session();
   user_contact_filter();
+  edits_inside_callbacks();
   printf(g_failed ? "FAILED %d checks\n" : "all API checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }

@@ -1,0 +1,125 @@
+"""Outcome gates of the production (graph-coloured) mode AT THE SIZES of BASELINE.json's configs, against the
+reference's own CPU Step on the identical scene (the small-size gates are in test_step_parity.py):
+
+  config 2  many_pyramids, 100 pyramids (21 001 bodies), 600 steps: every body asleep when the reference's are,
+            positions within POS_TOL of the reference's, same contact count
+  config 3  mixed 20 000 (400 steps) and mixed 100 000 (320 steps, the window bench.py times): potential energy,
+            deepest penetration, height profile, awake fraction, contact count
+  config 4  tumbler, 500 boxes, 1 000 steps through the drop-in API (spawn phase included): container angle,
+            height histogram of the boxes
+
+The coloured mode differs from the reference only in the ORDER constraints are visited (colours instead of the
+island DFS), so these are tolerances on aggregates, stated next to each assert."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from box2d_optimized_b200 import GpuScene
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pe(b, p):
+    dyn = b[:, 11] == 2
+    return float(np.sum(p[dyn, 0] * 10.0 * b[dyn, 5]))
+
+
+def _deepest_circle_overlap(b, fx):
+    """cheap penetration proxy that needs no manifolds: nothing may sink below the container floor"""
+    return float(b[1:, 5].min())
+
+
+def _record(name, d):
+    """kept next to the other GPU outputs (gpurun_out/ is merged back by gpurun)"""
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, f"gate_{name}.json"), "w") as f:
+            json.dump(d, f, indent=1)
+    except OSError:
+        pass
+    print(name, json.dumps(d))
+
+
+def test_many_pyramids_100_settle_and_sleep_like_the_reference(require_ref):
+    from oracle.bindings import RefScene
+    r, g = RefScene("many_pyramids", 100, 0), GpuScene("many_pyramids", 100, 0)
+    r.step(600)
+    g.step(600)
+    rb, gb = r.bodies(), g.bodies()
+    dpos = float(np.abs(gb[:, 4:6] - rb[:, 4:6]).max())
+    d = dict(bodies=len(rb), max_dpos=dpos, awake_ref=int(rb[:, 10].sum()), awake_gpu=int(gb[:, 10].sum()),
+             contacts_ref=int(r.contact_count), contacts_gpu=int(g.contact_count),
+             pe_ref=_pe(rb, r.body_params()), pe_gpu=_pe(gb, g.body_params()))
+    _record("many_pyramids_100", d)
+    assert len(rb) == 21001
+    assert d["awake_ref"] == 0 and d["awake_gpu"] == 0          # all 100 pyramids asleep on both sides
+    assert dpos < 0.15                                            # same gate as the single pyramid (measured ~0.08)
+    assert abs(d["pe_gpu"] - d["pe_ref"]) <= 5e-3 * abs(d["pe_ref"])
+    assert abs(d["contacts_gpu"] - d["contacts_ref"]) <= 0.03 * d["contacts_ref"]
+    assert float(np.abs(gb[:, 7:10]).max()) == 0.0                # asleep = zero velocity
+
+
+def _mixed_gate(n, steps, tag):
+    from oracle.bindings import RefScene
+    r, g = RefScene("mixed", n, 12345), GpuScene("mixed", n, 12345)
+    r.step(steps)
+    g.step(steps)
+    rb, gb = r.bodies(), g.bodies()
+    rp = r.body_params()
+    hr, hg = np.sort(rb[1:, 5]), np.sort(gb[1:, 5])
+    d = dict(bodies=len(rb), steps=steps, pe_ref=_pe(rb, rp), pe_gpu=_pe(gb, rp),
+             lowest_ref=float(hr[0]), lowest_gpu=float(hg[0]), top_ref=float(hr[-1]), top_gpu=float(hg[-1]),
+             height_profile_mean_abs_diff=float(np.abs(hr - hg).mean()),
+             awake_ref=float(rb[1:, 10].mean()), awake_gpu=float(gb[1:, 10].mean()),
+             contacts_ref=int(r.contact_count), contacts_gpu=int(g.contact_count),
+             ke_ref=float(np.sum(rp[1:, 0] * (rb[1:, 7] ** 2 + rb[1:, 8] ** 2)) * 0.5),
+             ke_gpu=float(np.sum(rp[1:, 0] * (gb[1:, 7] ** 2 + gb[1:, 8] ** 2)) * 0.5),
+             x_min_gpu=float(gb[1:, 4].min()), x_max_gpu=float(gb[1:, 4].max()))
+    _record(tag, d)
+    assert np.isfinite(gb).all()
+    assert abs(d["pe_gpu"] - d["pe_ref"]) <= 0.01 * abs(d["pe_ref"])         # pile height / packing within 1 %
+    assert d["height_profile_mean_abs_diff"] < 0.10                           # sorted body heights, metres
+    assert d["lowest_gpu"] > d["lowest_ref"] - 0.02                           # nobody pressed through the floor
+    assert abs(d["contacts_gpu"] - d["contacts_ref"]) <= 0.03 * d["contacts_ref"]
+    assert abs(d["awake_gpu"] - d["awake_ref"]) <= 0.10
+    assert d["ke_gpu"] <= 1.25 * d["ke_ref"] + 1.0                            # not more agitated than the reference
+    return d
+
+
+def test_mixed_20k_settles_like_the_reference(require_ref):
+    _mixed_gate(20000, 400, "mixed_20k")
+
+
+def test_mixed_100k_in_the_timed_window_matches_the_reference(require_ref):
+    """the scene and the step window bench.py's headline is measured on (steps 300..320 are timed there)"""
+    d = _mixed_gate(100000, 320, "mixed_100k")
+    assert d["contacts_gpu"] > 200000
+
+
+def test_tumbler_500_container_angle_and_box_heights(require_ref):
+    from oracle.bindings import RefScene
+    r, g = RefScene("tumbler", 500, 0), GpuScene("tumbler", 500, 0)
+    r.step(1000)
+    g.step(1000)
+    rb, gb = r.bodies(), g.bodies()
+    assert len(rb) == 502 and len(gb) == 502
+    # the motor drives the container at 0.05 pi rad/s whatever the boxes do
+    d = dict(angle_ref=float(rb[1, 6]), angle_gpu=float(gb[1, 6]),
+             contacts_ref=int(r.contact_count), contacts_gpu=int(g.contact_count))
+    boxes_r, boxes_g = rb[2:], gb[2:]
+    bins = np.linspace(0.0, 20.0, 11)
+    hr, _ = np.histogram(boxes_r[:, 5], bins)
+    hg, _ = np.histogram(boxes_g[:, 5], bins)
+    d.update(hist_ref=hr.tolist(), hist_gpu=hg.tolist(), mean_y_ref=float(boxes_r[:, 5].mean()),
+             mean_y_gpu=float(boxes_g[:, 5].mean()), mean_x_ref=float(boxes_r[:, 4].mean()),
+             mean_x_gpu=float(boxes_g[:, 4].mean()))
+    _record("tumbler_500", d)
+    assert abs(d["angle_gpu"] - d["angle_ref"]) < 1e-3
+    assert np.abs(boxes_g[:, 4]).max() < 10.0 and boxes_g[:, 5].min() > 0.0 and boxes_g[:, 5].max() < 20.0  # inside
+    assert int(np.abs(hr - hg).sum()) <= 0.2 * 500          # histogram of box heights (2 m bins): L1 distance <= 20 %
+    assert abs(d["mean_y_gpu"] - d["mean_y_ref"]) < 0.5 and abs(d["mean_x_gpu"] - d["mean_x_ref"]) < 0.5
