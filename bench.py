@@ -377,7 +377,7 @@ def main():
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches = 0
-    contacts_seen, constraints_seen, colours_seen, awake_seen = [], [], [], []
+    contacts_seen, constraints_seen, colours_seen, awake_seen, overflow_seen, rounds_seen = [], [], [], [], [], []
     for k in range(args.steps):
         with torch.cuda.stream(ext):
             flush.zero_()  # evict the step's working set from L2 (outside the timed bracket)
@@ -393,6 +393,8 @@ def main():
         constraints_seen.append(st.num_constraints)
         colours_seen.append(st.num_colours)
         awake_seen.append(st.num_awake)
+        overflow_seen.append(st.num_overflow)
+        rounds_seen.append(st.colour_rounds)
     A.synchronize()
     torch.cuda.synchronize()
     if rank == 0 and not sampler.samples:
@@ -525,7 +527,8 @@ def main():
                        "worlds_per_gpu": per_gpu, "world_variants": W["variants"],
                        "contacts_mean": float(np.mean(contacts_seen)), "constraints_mean": float(np.mean(constraints_seen)),
                        "awake_bodies_mean": float(np.mean(awake_seen)),
-                       "colours_max": int(max(colours_seen)), "velocity_iterations": VEL_ITERS, "position_iterations": POS_ITERS,
+                       "colours_max": int(max(colours_seen)), "serial_bucket_constraints_mean": float(np.mean(overflow_seen)),
+                       "colour_rounds_mean": float(np.mean(rounds_seen)), "velocity_iterations": VEL_ITERS, "position_iterations": POS_ITERS,
                        "dt": 1.0 / 60.0, "sleeping": True, "continuous": False, "solver": "graph-coloured",
                        "l2": "flushed between timed steps (256 MiB memset, outside the event bracket)",
                        "preroll_steps": W["host_prestep"] + W["preroll"],

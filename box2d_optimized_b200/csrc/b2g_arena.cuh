@@ -37,6 +37,8 @@ struct StepCounts {
   int bpMaxVisits;              // longest single walk
   int numBigBodies;             // bodies of oversize islands (an island can be oversize through joints alone)
   int colourCount[B2G_MAX_COLOURS + 1];
+  int spillCount;               // bodies of a tiled oversize island that did not fit their tile
+  int bigJoints;                // joints between bodies of oversize islands
   int worklistCount;            // uncoloured active constraints of this step (k_mark_active_bins -> k_colour_worklist)
   int worklistLeft[200];        // per colouring round: somebody is still uncoloured (grid mode)
   unsigned int boundsLo[2], boundsHi[2];  // ordered-int encoded min/max of 2*centre
@@ -135,6 +137,16 @@ struct b2gArena {
   unsigned int* bigBarrier;  // its grid-barrier counter (zeroed before every launch)
   int colourGrid;            // co-resident grid of k_colour_worklist
   unsigned int* colourBarrier;
+  // oversize islands cut into per-SM tiles (b2g_tiles.cuh)
+  struct TilePlan* tilePlan;
+  int *tileStripOfX, *tileRowOfY, *tileHistX, *tileHistY;
+  int *tileSlot, *tileBodies, *tileCount, *spillList;
+  uint8_t* tileBoundary;
+  unsigned int* tileBarrier;
+  int tileGrid;              // co-resident grid of k_big_tiles (= SM count)
+  int tilePlanValid, tilePlanAge;
+  int lastBigBodies, lastSpill;
+  int tilesDisabled;         // B2G_NO_TILES=1: keep the grid-pass path (measurements)
 
   // fixtures + shapes
   int* fBody;

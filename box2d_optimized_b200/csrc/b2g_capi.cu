@@ -11,7 +11,7 @@
 #include <vector>
 #include <algorithm>
 #include "b2g_broadphase.cuh"
-#include "b2g_fused.cuh"
+#include "b2g_tiles.cuh"
 #include "b2g_query.cuh"
 #include <thrust/iterator/transform_iterator.h>
 
@@ -63,12 +63,12 @@ static int use_device(int device) {
 enum KClass {
   KC_NARROWPHASE, KC_ISLANDS, KC_INTEGRATE, KC_COLOUR, KC_PREPARE, KC_WARM_START, KC_SOLVE_VELOCITY,
   KC_SOLVE_POSITION, KC_STORE_IMPULSES, KC_FINALIZE, KC_BP_BUILD, KC_BP_TRAVERSE, KC_CONTACT_MERGE, KC_SORT_SCAN,
-  KC_FUSED_SOLVE, KC_QUERY, KC_BIG_SOLVE, KC_COUNT
+  KC_FUSED_SOLVE, KC_QUERY, KC_BIG_SOLVE, KC_BIG_TILES, KC_COUNT
 };
 static const char* kClassNames[KC_COUNT] = {
     "narrowphase", "islands", "integrate", "colour", "prepare", "warm_start", "solve_velocity", "solve_position",
     "store_impulses", "finalize", "bp_build", "bp_traverse", "contact_merge", "sort_scan", "fused_solve", "query",
-    "big_solve"};
+    "big_solve", "big_tiles"};
 
 static inline void ktime_begin(b2gArena* A, int cls, double units) {
   if (!A->kernelTiming || A->ktCount >= B2G_KT_MAX) return;
@@ -243,7 +243,7 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->islandCursor, nb));
   CK(dalloc(&A->bodySlot, nb));
   CK(dalloc(&A->slotBody, nb));
-  A->nbinsMax = nb / 32 + 8;
+  A->nbinsMax = nb / 32 + 8 + B2G_TILES_MAX + 2;
   CK(dalloc(&A->binFirst, A->nbinsMax));
   CK(dalloc(&A->binEnd, A->nbinsMax));
   CK(dalloc(&A->bucketCount, (size_t)(A->nbinsMax + 1) * 32 + 1));
@@ -336,6 +336,21 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->dCounts, 1));
   CK(dalloc(&A->bigBarrier, 1));
   CK(dalloc(&A->colourBarrier, 1));
+  CK(dalloc(&A->tilePlan, 1));
+  CK(dalloc(&A->tileStripOfX, B2G_TILE_XBINS));
+  CK(dalloc(&A->tileHistX, B2G_TILE_XBINS));
+  CK(dalloc(&A->tileRowOfY, (size_t)B2G_TILES_MAX * B2G_TILE_YBINS));
+  CK(dalloc(&A->tileHistY, (size_t)B2G_TILES_MAX * B2G_TILE_YBINS));
+  CK(dalloc(&A->tileSlot, nb));
+  CK(dalloc(&A->spillList, nb));
+  CK(dalloc(&A->tileBodies, (size_t)B2G_TILES_MAX * B2G_TILE_CAP));
+  CK(dalloc(&A->tileBoundary, (size_t)B2G_TILES_MAX * B2G_TILE_CAP));
+  CK(dalloc(&A->tileCount, B2G_TILES_MAX));
+  CK(dalloc(&A->tileBarrier, 1));
+  {
+    const char* e = getenv("B2G_NO_TILES");
+    A->tilesDisabled = e ? atoi(e) : 0;
+  }
   CK(cudaMallocHost((void**)&A->hCounts, sizeof(StepCounts)));
   memset(A->hCounts, 0, sizeof(StepCounts));
   CK(cudaMallocHost((void**)&A->hostStage, 4096));
@@ -375,7 +390,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
                   A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
-                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->colourBarrier, A->cubTemp};
+                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->colourBarrier, A->tilePlan, A->tileStripOfX, A->tileHistX, A->tileRowOfY, A->tileHistY, A->tileSlot, A->spillList, A->tileBodies, A->tileBoundary, A->tileCount, A->tileBarrier, A->cubTemp};
   for (void* p : ptrs) cudaFree(p);
   free_contact_buf(A->cb[0]);
   free(A->downloadSlots);
@@ -990,7 +1005,20 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   }
   const int nbins = nb / binSize + 1;
   const int bigBin = nbins;  // sorts after every fused bin
-  if (nbins + 1 > A->nbinsMax) {
+  // Oversize islands: cut into per-SM tiles (b2g_tiles.cuh) when last step's oversize bodies fit the tiles'
+  // shared memory with room to drift; the grid-pass kernel (k_big_solve) otherwise, and on the step an
+  // oversize island first appears (no plan yet).
+  if (A->tileGrid == 0) {
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
+    A->tileGrid = sms < B2G_TILES_MAX ? sms : B2G_TILES_MAX;
+  }
+  const bool useTiles = !A->tilesDisabled && A->lastNumBig > 0 && A->lastBigBodies > 0 &&
+                        (long long)A->lastBigBodies * 4 <= (long long)A->tileGrid * B2G_TILE_CAP * 3;
+  const int tileBin0 = useTiles ? nbins + 1 : -1;
+  const int cutBin = useTiles ? nbins + 1 + A->tileGrid : -1;
+  const int nbinsAll = useTiles ? cutBin + 1 : nbins + 1;  // bins whose buckets the sort covers
+  if (nbinsAll > A->nbinsMax) {
     set_err("b2g_step", "internal: bin table too small");
     return B2G_ERR_CAPACITY;
   }
@@ -1002,11 +1030,11 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   if (conCap < 0) conCap = 0;
   const size_t smem = tileBytes + (size_t)conCap * B2G_PLANES * 16;
 
-  const int nbuckets = (nbins + 1) << B2G_COLOUR_BITS;
+  const int nbuckets = nbinsAll << B2G_COLOUR_BITS;
   LAUNCH(A, KC_ISLANDS, nb, k_body_begin, div_up(nb, 256), 256, nb, A->bflags, A->force, A->islandParent,
          A->islandAwake, A->island, A->islandDirty, A->islandsValid, A->islandWasBig,
          (A->stepCount % B2G_ISLAND_EXACT_PERIOD) == 0, A->islandMinSleep, A->islandPen, A->capBodies, P->position_iterations, A->colourMask,
-         A->bodyBest, A->islandCount, A->islandCursor, A->binFirst, A->binEnd, nbins + 1, A->bucketCount, nbuckets);
+         A->bodyBest, A->islandCount, A->islandCursor, A->binFirst, A->binEnd, nbinsAll, A->bucketCount, nbuckets);
   if (nc > 0)
     LAUNCH(A, KC_ISLANDS, nc, k_island_union, div_up(nc, 256), 256, nc, C, A->bflags, A->fTypeFlags, A->islandParent);
   if (nj > 0)
@@ -1015,6 +1043,40 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
          A->islandAwake, A->islandCount, A->dCounts, A->islandDirty);
   LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandAwake, A->islandCount, A->islandStart,
          A->binFirst, A->binEnd, binSize, bigThr, A->dCounts, A->islandWasBig);
+  if (useTiles) {
+    const bool replan = !A->tilePlanValid || A->tilePlanAge >= B2G_TILE_PLAN_PERIOD ||
+                        (long long)A->lastSpill * 50 > A->lastBigBodies;
+    if (replan) {
+      TilePlan init;
+      memset(&init, 0, sizeof(init));
+      init.lo[0] = init.lo[1] = 0xffffffffu;
+      CK(cudaMemcpyAsync(A->tilePlan, &init, sizeof(init), cudaMemcpyHostToDevice, A->stream));
+      CK(cudaMemsetAsync(A->tileHistX, 0, sizeof(int) * B2G_TILE_XBINS, A->stream));
+      CK(cudaMemsetAsync(A->tileHistY, 0, sizeof(int) * (size_t)B2G_TILES_MAX * B2G_TILE_YBINS, A->stream));
+      LAUNCH(A, KC_ISLANDS, nb, k_tile_bounds, div_up(nb, 256), 256, nb, A->pos, A->bflags, A->island, A->islandAwake,
+             A->islandCount, bigThr, A->tilePlan);
+      LAUNCH(A, KC_ISLANDS, 1, k_tile_plan_begin, 1, 32, A->tilePlan, A->tileGrid);
+      LAUNCH(A, KC_ISLANDS, nb, k_tile_xhist, div_up(nb, 256), 256, nb, A->pos, A->bflags, A->island, A->islandAwake,
+             A->islandCount, bigThr, A->tilePlan, A->tileHistX);
+      LAUNCH(A, KC_ISLANDS, B2G_TILE_XBINS, k_tile_xplan, 1, 1024, A->tilePlan, A->tileHistX, A->tileStripOfX);
+      LAUNCH(A, KC_ISLANDS, nb, k_tile_yhist, div_up(nb, 256), 256, nb, A->pos, A->bflags, A->island, A->islandAwake,
+             A->islandCount, bigThr, A->tilePlan, A->tileStripOfX, A->tileHistY);
+      LAUNCH(A, KC_ISLANDS, B2G_TILE_YBINS, k_tile_yplan, A->tileGrid, 1024, A->tilePlan, A->tileHistY, A->tileRowOfY);
+      A->tilePlanValid = 1;
+      A->tilePlanAge = 0;
+    }
+    A->tilePlanAge++;
+    CK(cudaMemsetAsync(A->tileCount, 0, sizeof(int) * B2G_TILES_MAX, A->stream));
+    CK(cudaMemsetAsync(A->tileBoundary, 0, (size_t)B2G_TILES_MAX * B2G_TILE_CAP, A->stream));
+    LAUNCH(A, KC_ISLANDS, nb, k_tile_assign, div_up(nb, 256), 256, nb, A->pos, A->bflags, A->island, A->islandAwake,
+           A->islandCount, bigThr, A->tilePlan, A->tileStripOfX, A->tileRowOfY, A->tileSlot, A->tileBodies, A->tileCount,
+           A->spillList, A->dCounts);
+    if (nj > 0)
+      LAUNCH(A, KC_ISLANDS, nj, k_tile_joint_marks, div_up(nj, 256), 256, nj, A->jBodies, A->tileSlot, A->tileBoundary,
+             A->dCounts);
+  } else {
+    A->tilePlanValid = 0;
+  }
   if (nc == 0)  // otherwise the scatter rides in k_mark_active_bins
     LAUNCH(A, KC_ISLANDS, nb, k_body_scatter, div_up(nb, 256), 256, nb, A->bflags, A->island, A->islandAwake,
            A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody, bigThr, A->dCounts);
@@ -1041,18 +1103,18 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     M.binSize = binSize;
     M.bigThreshold = bigThr;
     M.bigBin = bigBin;
-    M.tileBin0 = -1;
-    M.cutBin = -1;
-    M.tileCap = 1;
+    M.tileBin0 = tileBin0;
+    M.cutBin = cutBin;
+    M.tileCap = B2G_TILE_CAP;
     LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nmax, 256), 256, M, C, A->fTypeFlags, A->bflags, A->island,
            A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->dCounts, A->mass, A->colourMask, A->islandCursor,
-           A->bodySlot, A->slotBody, A->bodyBest, fixBase, A->activeList, A->bucketCount, A->conVals, (const int*)nullptr,
-           (uint8_t*)nullptr);
+           A->bodySlot, A->slotBody, A->bodyBest, fixBase, A->activeList, A->bucketCount, A->conVals,
+           (const int*)A->tileSlot, A->tileBoundary);
     A->recolour = 0;
     {
       if (A->colourGrid == 0) {
         int perSM = 0, sms = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_colour_worklist, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_colour_worklist, B2G_WL_THREADS, 0));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
         if (perSM < 1) return B2G_ERR_CUDA;
         A->colourGrid = sms;
@@ -1063,7 +1125,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       CK(cudaMemsetAsync(A->colourBarrier, 0, sizeof(unsigned int), A->stream));
       ktime_begin(A, KC_COLOUR, nc);
       // cooperative launch for the co-residency of its grid barrier (the long-worklist mode)
-      CK(cudaLaunchCooperativeKernel((void*)k_colour_worklist, dim3(A->colourGrid), dim3(256), args, 0, A->stream));
+      CK(cudaLaunchCooperativeKernel((void*)k_colour_worklist, dim3(A->colourGrid), dim3(B2G_WL_THREADS), args, 0, A->stream));
       ktime_end(A);
       A->launches++;
     }
@@ -1106,12 +1168,82 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     A->launches++;
   }
 
+  // ---- oversize islands, tiled: one persistent launch, queued before the host looks at any counter ---------
+  int tilesKt = -1;
+  if (useTiles) {
+    TileArgs T;
+    T.tileBin0 = tileBin0;
+    T.cutBin = cutBin;
+    T.nb = nb;
+    T.nj = nj;
+    T.h = h;
+    T.invH = h > 0.0f ? 1.0f / h : 0.0f;
+    T.dtRatio = dtRatio;
+    T.gravity = make_float2(P->gravity_x, P->gravity_y);
+    T.velIters = P->velocity_iterations;
+    T.posIters = P->position_iterations;
+    T.warmStarting = P->warm_starting;
+    T.allowSleep = P->allow_sleep;
+    T.clearForces = P->clear_forces;
+    T.plan = A->tilePlan;
+    T.tileCount = A->tileCount;
+    T.tileBodies = A->tileBodies;
+    T.tileBoundary = A->tileBoundary;
+    T.tileSlot = A->tileSlot;
+    T.spillList = A->spillList;
+    T.bucketStart = A->bucketStart;
+    T.sortedList = A->sortedList;
+    T.orderScratch = (int*)A->conKeys;
+    T.croot = A->croot;
+    T.islandPen = A->islandPen;
+    T.penStride = A->capBodies;
+    T.islandMinSleep = A->islandMinSleep;
+    T.bflags = A->bflags;
+    T.pos = A->pos;
+    T.vel = A->vel;
+    T.xf = A->xf;
+    T.force = A->force;
+    T.mass = A->mass;
+    T.center = A->center;
+    T.fRadius = A->fRadius;
+    T.island = A->island;
+    T.islandAwake = A->islandAwake;
+    T.bodySlot = A->bodySlot;
+    T.counts = A->dCounts;
+    T.barrier = A->tileBarrier;
+    const size_t tileSmemBytes = (size_t)B2G_TILE_CAP * (16 + 16 + 4 + 2) + (size_t)B2G_BIG_STAGE_PLANES * B2G_TILE_THREADS * sizeof(float4);
+    static bool attrSet = false;
+    if (!attrSet) {
+      CK(cudaFuncSetAttribute(k_big_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmemBytes));
+      int perSM = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_big_tiles, B2G_TILE_THREADS, tileSmemBytes));
+      if (perSM < 1) {
+        set_err("b2g_step", "k_big_tiles does not fit an SM");
+        return B2G_ERR_CUDA;
+      }
+      attrSet = true;
+    }
+    JointWalk JW = joint_walk(A, 1);
+    JointArraysDev JV = joint_views(A);
+    void* args[] = {&T, &S, &C, &JW, &JV};
+    CK(cudaMemsetAsync(A->tileBarrier, 0, sizeof(unsigned int), A->stream));
+    tilesKt = A->kernelTiming ? A->ktCount : -1;
+    // units = constraints of the tiled islands (known after the readback below); the launch covers all of
+    // b2Island::Solve for them (bench.py charges SURVEY 8d's 2480 B per constraint at 8/3 iterations)
+    ktime_begin(A, KC_BIG_TILES, 0.0);
+    CK(cudaLaunchCooperativeKernel((void*)k_big_tiles, dim3(A->tileGrid), dim3(B2G_TILE_THREADS), args, tileSmemBytes,
+                                   A->stream));
+    ktime_end(A);
+    A->launches++;
+  }
+
   if (nc > 0) {
     CK(cudaEventSynchronize(A->ev[4]));  // the copy finished long ago; the fused kernel is still running
     rounds = A->hCounts->lastUsefulRound;
     numActive = A->hCounts->numActive;
     numBig = A->hCounts->numBig;
     if (fusedKt >= 0 && fusedKt < B2G_KT_MAX) A->ktUnits[fusedKt] = (double)numActive - numBig;
+    if (tilesKt >= 0 && tilesKt < B2G_KT_MAX) A->ktUnits[tilesKt] = (double)numBig;
     out.numColours = A->hCounts->numColours;
     out.numOverflow = A->hCounts->numOverflow + A->hCounts->remaining;
     A->lastOverflow = out.numOverflow;
@@ -1126,9 +1258,11 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   const int bigBodies = (nc > 0 || nj > 0) ? A->hCounts->numBigBodies : 0;
   A->lastNumBig = numBig > 0 ? numBig : bigBodies;
   A->lastMaxIsland = (nc > 0 || nj > 0) ? A->hCounts->maxIslandBodies : 0;
+  A->lastBigBodies = bigBodies;
+  A->lastSpill = (nc > 0 || nj > 0) ? A->hCounts->spillCount : 0;
 
-  // ---- oversize islands: per-colour launches over the whole GPU --------------------------------
-  if (numBig > 0 || bigBodies > 0) {
+  // ---- oversize islands, not tiled (first appearance, or too many bodies for the tiles): grid-wide passes ----
+  if (!useTiles && (numBig > 0 || bigBodies > 0)) {
     const int bigStart = numActive - numBig;
     int colourFirst[B2G_MAX_COLOURS + 2];
     int acc = bigStart, numColours = 0;

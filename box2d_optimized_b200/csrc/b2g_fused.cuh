@@ -220,9 +220,10 @@ __device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int ta
 // A short worklist (the steady state: a few hundred births per step) is handled by block 0 alone with CTA
 // barriers; a long one (first step, an avalanche) by the whole co-resident grid with grid barriers.
 // The last pass counts the newly coloured constraints into their (bin, colour) buckets.
-#define B2G_WL_SINGLE_MAX 8192
+#define B2G_WL_THREADS 1024
+#define B2G_WL_SINGLE_MAX 2048
 #define B2G_WL_MAX_ROUNDS 200
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(B2G_WL_THREADS)
 k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __restrict__ mass,
                   unsigned long long* colourMask, unsigned long long* bodyBest, const int* __restrict__ bodyFixBase,
                   const int* __restrict__ worklist, StepCounts* counts, int bigBin, int cutBin, int* bucketCount,
@@ -250,26 +251,32 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
       const int i = worklist[k];
       if (__ldcg(&C.colour[i]) >= 0) continue;
       const int2 bd = C.body[i];
-      const unsigned long long pr = colour_priority(round, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
+      const int bin = cbin[i];
+      const int domain = (bin == cutBin && cutBin >= 0) ? 1 : 0;
       const bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
-      const bool win = (!movA || __ldcg(&bodyBest[bd.x]) == pr) && (!movB || __ldcg(&bodyBest[bd.y]) == pr);
-      if (win) {
-        const int bin = cbin[i];
-        const int domain = (bin == cutBin && cutBin >= 0) ? 1 : 0;
-        const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
-        const unsigned long long freeBits = ~used & colour_domain_mask(domain);
-        const int c = freeBits ? (__ffsll((long long)freeBits) - 1)
-                               : B2G_OVERFLOW_COLOUR + (domain ? B2G_CUT_DOMAIN_SHIFT : 0);
-        __stcg(&C.colour[i], c);
-        if ((c & 31) < B2G_MAX_COLOURS) {
+      const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
+      const unsigned long long freeBits = ~used & colour_domain_mask(domain);
+      int c = -1;
+      if (!freeBits) {
+        // Masks only grow within a step, so a constraint that finds no free colour now never will: it
+        // goes to its bin's serial bucket at once instead of waiting for its turn to win.  (A hub body —
+        // the tumbler's container touches ~120 boxes — would otherwise cost one round per contact.)
+        c = B2G_OVERFLOW_COLOUR + (domain ? B2G_CUT_DOMAIN_SHIFT : 0);
+      } else {
+        const unsigned long long pr = colour_priority(round, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
+        const bool win = (!movA || __ldcg(&bodyBest[bd.x]) == pr) && (!movB || __ldcg(&bodyBest[bd.y]) == pr);
+        if (win) {
+          c = __ffsll((long long)freeBits) - 1;
           // the winner is unique on each of its movable bodies, so plain read-modify-write is race free
           const unsigned long long bit = 1ull << c;
           if (movA) __stcg(&colourMask[bd.x], __ldcg(&colourMask[bd.x]) | bit);
           if (movB) __stcg(&colourMask[bd.y], __ldcg(&colourMask[bd.y]) | bit);
           if ((c & 31) + 1 > counts->numColours) atomicMax(&counts->numColours, (c & 31) + 1);
-        } else {
-          atomicAdd(&counts->numOverflow, 1);
         }
+      }
+      if (c >= 0) {
+        __stcg(&C.colour[i], c);
+        if ((c & 31) >= B2G_MAX_COLOURS) atomicAdd(&counts->numOverflow, 1);
         if (bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
       } else {
         left = 1;
@@ -792,6 +799,13 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
 // of one launch per colour per iteration (14 colours x 12 passes = 170 launches of ~16k
 // constraints each were launch-latency bound).  Body state stays in global memory / L2.
 // ---------------------------------------------------------------------------------------------
+// ---- the persistent big-island kernel ----------------------------------------------------------------
+// Body state of an oversize island lives in L2/HBM and is exchanged between SMs every colour pass.
+struct CoherentBodies {  // L2 loads / stores: the other SMs' writes of the previous pass, never a stale L1 line
+  float4* a;
+  __device__ __forceinline__ float4 load(int i) const { return __ldcg(a + i); }
+  __device__ __forceinline__ void store(int i, float4 v) const { __stcg(a + i, v); }
+};
 // ---- joints of islands that are solved through the global arrays (big islands, sequential mode):
 // one thread, joint-index order
 struct JointWalk {
@@ -816,6 +830,7 @@ __device__ __forceinline__ int joint_owner_body(const JointWalk& W, const JointA
   if (W.onlyBig && W.bodySlot[s] != B2G_SLOT_BIG) return -1;
   return s;
 }
+template <class Acc = GlobalBodies>
 __device__ __forceinline__ void joints_init_global(const JointWalk& W, const JointArraysDev& J, float4* pos, float4* vel,
                                                    const float4* __restrict__ mass, const float4* __restrict__ center,
                                                    float dtRatio, int warm) {
@@ -823,16 +838,18 @@ __device__ __forceinline__ void joints_init_global(const JointWalk& W, const Joi
     const int j = joint_walk_at(W, k);
     if (joint_owner_body(W, J, j) < 0) continue;
     int2 bd = J.bodies[j];
-    joint_init(J, j, bd.x, bd.y, GlobalBodies{pos}, GlobalBodies{vel}, mass, center, dtRatio, warm != 0);
+    joint_init(J, j, bd.x, bd.y, Acc{pos}, Acc{vel}, mass, center, dtRatio, warm != 0);
   }
 }
+template <class Acc = GlobalBodies>
 __device__ __forceinline__ void joints_velocity_global(const JointWalk& W, const JointArraysDev& J, float4* vel, float h,
                                                        float invH) {
   for (int k = 0; k < joint_walk_count(W); ++k) {
     const int j = joint_walk_at(W, k);
-    if (joint_owner_body(W, J, j) >= 0) joint_solve_velocity(J, j, GlobalBodies{vel}, h, invH);
+    if (joint_owner_body(W, J, j) >= 0) joint_solve_velocity(J, j, Acc{vel}, h, invH);
   }
 }
+template <class Acc = GlobalBodies>
 __device__ __forceinline__ void joints_position_global(const JointWalk& W, const JointArraysDev& J, float4* pos,
                                                        uint32_t* islandPen, int penStride, int iter) {
   for (int k = 0; k < joint_walk_count(W); ++k) {
@@ -841,7 +858,7 @@ __device__ __forceinline__ void joints_position_global(const JointWalk& W, const
     if (s < 0) continue;
     int root = W.island[s];
     if (island_done(islandPen, penStride, iter, root)) continue;
-    if (!joint_solve_position(J, j, GlobalBodies{pos}))
+    if (!joint_solve_position(J, j, Acc{pos}))
       atomicMax(&islandPen[(size_t)iter * penStride + root], __float_as_uint(1.0f));
   }
 }
@@ -860,13 +877,6 @@ __global__ void k_joints_position_seq(JointWalk W, JointArraysDev J, float4* pos
   joints_position_global(W, J, pos, islandPen, penStride, iter);
 }
 
-// ---- the persistent big-island kernel ----------------------------------------------------------------
-// Body state of an oversize island lives in L2/HBM and is exchanged between SMs every colour pass.
-struct CoherentBodies {  // L2 loads / stores: the other SMs' writes of the previous pass, never a stale L1 line
-  float4* a;
-  __device__ __forceinline__ float4 load(int i) const { return __ldcg(a + i); }
-  __device__ __forceinline__ void store(int i, float4 v) const { __stcg(a + i, v); }
-};
 // Split grid barrier on a monotonic counter (scripts/micro/grid_barrier.cu: 1.28 us vs 1.49 us for
 // cooperative groups at 148 blocks).  arrive: the block's stores are ordered before thread 0's release
 // increment by the CTA barrier (cumulativity); wait: thread 0 spins with acquire loads, the CTA barrier
@@ -1137,13 +1147,13 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
   if (warmStarting) big_sweep<B2G_BIG_WARM>(Z, G, S, R, velAcc, posAcc, Q, velIters > 0);
   const float invH = h > 0.0f ? 1.0f / h : 0.0f;
   if (W.nj > 0) {
-    if (gtid == 0) joints_init_global(W, J, pos, vel, mass, center, dtRatio, warmStarting);
+    if (gtid == 0) joints_init_global<CoherentBodies>(W, J, pos, vel, mass, center, dtRatio, warmStarting);
     grid_arrive(Z.barrier, Z.target);
     grid_wait(Z.barrier, Z.target);
   }
   for (int it = 0; it < velIters; ++it) {
     if (W.nj > 0) {
-      if (gtid == 0) joints_velocity_global(W, J, vel, h, invH);
+      if (gtid == 0) joints_velocity_global<CoherentBodies>(W, J, vel, h, invH);
       grid_arrive(Z.barrier, Z.target);
       grid_wait(Z.barrier, Z.target);
     }
@@ -1207,7 +1217,7 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
     Q.it = it;
     big_sweep<B2G_BIG_POSITION>(Z, G, S, R, velAcc, posAcc, Q, it + 1 < posIters);
     if (W.nj > 0) {
-      if (gtid == 0) joints_position_global(W, J, pos, islandPen, penStride, it);
+      if (gtid == 0) joints_position_global<CoherentBodies>(W, J, pos, islandPen, penStride, it);
       grid_arrive(Z.barrier, Z.target);
       grid_wait(Z.barrier, Z.target);
     }

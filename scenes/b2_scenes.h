@@ -16,6 +16,7 @@
 //   many_pyramids  `size` copies of it 30 m apart on one ground edge (config 2)
 //   mixed          circles + convex polygons dropped into a 3-box container, LCG seed (config 3)
 //   tumbler        testbed/benchmarks/benchmarks.h:137-204 (b3, config 4)
+//   mixed_linked   mixed + a revolute joint between every 16th body and its neighbour (joints in an oversize island)
 //   filters        category / mask / group filtering (b2_world_callbacks.cpp:28-40), all three group signs
 //   chain / chain_collide   testbed/tests/chain.cpp:31-66 shape (collideConnected filter)
 //   welds          weld joints: cantilever beams, a welded compound (b2_weld_joint.cpp)
@@ -146,7 +147,7 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
       s->addFixture(ground, shape, 0.0f);
     }
     for (int k = 0; k < copies; ++k) scene_add_pyramid(*s, rows, 30.0f * (float)k);
-  } else if (name == "mixed") {
+  } else if (name == "mixed" || name == "mixed_linked") {
     int n = size > 0 ? size : 1000;
     SceneLCG rng((uint32_t)(seed > 0 ? seed : 12345));
     int cols = (int)std::ceil(1.5 * std::sqrt((double)n));
@@ -193,6 +194,18 @@ inline Scene* scene_build(const std::string& name, int size, int seed) {
         poly.Set(pts, nv);
         fd.shape = &poly;
         s->addFixture(body, fd);
+      }
+    }
+    if (name == "mixed_linked") {
+      // every 16th body is hinged to its right-hand grid neighbour (collideConnected = false): joints inside
+      // an oversize island
+      for (int i = 0; i + 1 < n; i += 16) {
+        if ((i % cols) + 1 >= cols) continue;
+        b2Body* a = s->bodies[1 + i];
+        b2Body* b = s->bodies[2 + i];
+        b2RevoluteJointDef jd;
+        jd.Initialize(a, b, 0.5f * (a->GetPosition() + b->GetPosition()));
+        s->world->CreateJoint(&jd);
       }
     }
   } else if (name == "tumbler") {
