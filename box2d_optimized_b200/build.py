@@ -40,12 +40,14 @@ def _find(tool, fallback):
     return shutil.which(tool) or fallback
 
 
-def build_cuda(force=False):
-    out = os.path.join(HERE, "libb2cuda.so")
+def build_cuda(force=False, out_name="libb2cuda.so", extra_flags=()):
+    """extra_flags / out_name: debug variants (e.g. -DB2G_BIG_TRACE into libb2cuda_trace.so, loaded by
+    scripts/gpu_big_trace.py through B2G_CUDA_LIB)"""
+    out = os.path.join(HERE, out_name)
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "b2cuda.h")]
     if force or _newer(out, srcs):
         nvcc = _find("nvcc", "/usr/local/cuda/bin/nvcc")
-        _run([nvcc] + NVCC_FLAGS + ["-o", out, os.path.join(CSRC, "b2g_capi.cu")])
+        _run([nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", out, os.path.join(CSRC, "b2g_capi.cu")])
     return out
 
 

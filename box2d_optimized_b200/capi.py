@@ -104,7 +104,7 @@ def load_cuda():
     """Loads the product library.  Fails loudly if it has not been built: there is no fallback."""
     global _cuda
     if _cuda is None:
-        p = lib_path()
+        p = os.environ.get("B2G_CUDA_LIB") or lib_path()   # B2G_CUDA_LIB: a debug build (scripts/gpu_big_trace.py)
         if not os.path.exists(p):
             raise B2GError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the CUDA extension is mandatory, there is no CPU fallback)")

@@ -38,6 +38,7 @@ struct StepCounts {
   int numBigBodies;             // bodies of oversize islands (an island can be oversize through joints alone)
   int colourCount[B2G_MAX_COLOURS + 1];
   int spillCount;               // bodies of a tiled oversize island that did not fit their tile
+  int maxTileCount;             // bodies in the fullest tile
   int bigJoints;                // joints between bodies of oversize islands
   int worklistCount;            // uncoloured active constraints of this step (k_mark_active_bins -> k_colour_worklist)
   int worklistLeft[200];        // per colouring round: somebody is still uncoloured (grid mode)
@@ -142,10 +143,13 @@ struct b2gArena {
   int *tileStripOfX, *tileRowOfY, *tileHistX, *tileHistY;
   int *tileSlot, *tileBodies, *tileCount, *spillList;
   uint8_t* tileBoundary;
+  int2* tileCutSeq;          // per solver slot of a cut constraint: its turn on either body (b2g_tiles.cuh)
+  int tileNoSequencing;      // B2G_TILE_BARRIERS=1: grid barriers between the cut colours (measurements)
   unsigned int* tileBarrier;
   int tileGrid;              // co-resident grid of k_big_tiles (= SM count)
   int tilePlanValid, tilePlanAge;
-  int lastBigBodies, lastSpill;
+  int lastBigBodies, lastSpill, lastMaxTile;
+  int tilePlanBodies;        // oversize bodies when the plan was made
   int tilesDisabled;         // B2G_NO_TILES=1: keep the grid-pass path (measurements)
 
   // fixtures + shapes

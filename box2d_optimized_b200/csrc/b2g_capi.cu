@@ -347,9 +347,12 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->tileBoundary, (size_t)B2G_TILES_MAX * B2G_TILE_CAP));
   CK(dalloc(&A->tileCount, B2G_TILES_MAX));
   CK(dalloc(&A->tileBarrier, 1));
+  CK(dalloc(&A->tileCutSeq, nc));
   {
     const char* e = getenv("B2G_NO_TILES");
     A->tilesDisabled = e ? atoi(e) : 0;
+    e = getenv("B2G_TILE_BARRIERS");
+    A->tileNoSequencing = e ? atoi(e) : 0;
   }
   CK(cudaMallocHost((void**)&A->hCounts, sizeof(StepCounts)));
   memset(A->hCounts, 0, sizeof(StepCounts));
@@ -390,7 +393,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
                   A->colourKeySorted, A->croot, A->planes.nf, A->planes.r1, A->planes.r2, A->planes.m1,
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
-                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->colourBarrier, A->tilePlan, A->tileStripOfX, A->tileHistX, A->tileRowOfY, A->tileHistY, A->tileSlot, A->spillList, A->tileBodies, A->tileBoundary, A->tileCount, A->tileBarrier, A->cubTemp};
+                  A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->colourBarrier, A->tilePlan, A->tileStripOfX, A->tileHistX, A->tileRowOfY, A->tileHistY, A->tileSlot, A->spillList, A->tileBodies, A->tileBoundary, A->tileCount, A->tileBarrier, A->tileCutSeq, A->cubTemp};
   for (void* p : ptrs) cudaFree(p);
   free_contact_buf(A->cb[0]);
   free(A->downloadSlots);
@@ -989,10 +992,10 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   size_t budget = 0;
   {
     int want = ctasOverride;
-    // chain-heavy = at least 4 % of last step's solver rows sat in serial buckets (hub bodies)
+    // chain-heavy = at least 2 % of last step's solver rows sat in serial buckets (hub bodies)
     if (want == 0)
       want = (nb / binSize + 1 >= 4 * 148 && bigThr >= 128 && A->lastActive > 0 &&
-              (long long)A->lastOverflow * 25 >= A->lastActive) ? 4 : 2;
+              (long long)A->lastOverflow * 50 >= A->lastActive) ? 4 : 2;
     if (want > 2) {
       size_t per = (size_t)(227 * 1024) / want - 2048;
       int fit = (int)(per / (FusedTile::bytes(1024) / 1024)) - bigThr;  // bodies of small islands that still fit next to one big one
@@ -1013,8 +1016,20 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
     A->tileGrid = sms < B2G_TILES_MAX ? sms : B2G_TILES_MAX;
   }
+  // Only islands beyond the hard cap are tiled: an island that is "oversize" just because the adaptive
+  // threshold lags behind its growth (a transient of a step or two) takes the grid-pass kernel, whose
+  // visiting order does not depend on what else is in the arena (batched worlds stay bit-identical to
+  // single ones; tiles are cut through space, so they mix worlds that overlap in space).
   const bool useTiles = !A->tilesDisabled && A->lastNumBig > 0 && A->lastBigBodies > 0 &&
+                        A->lastMaxIsland > B2G_BIG_ISLAND &&
                         (long long)A->lastBigBodies * 4 <= (long long)A->tileGrid * B2G_TILE_CAP * 3;
+  {
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("B2G_DEBUG_TILES") ? 1 : 0;
+    if (dbg && (A->stepCount % 50 == 0 || (A->stepCount >= 74 && A->stepCount <= 80)))
+      fprintf(stderr, "[tiles] step %lld useTiles %d lastNumBig %d lastBigBodies %d lastMaxIsland %d lastSpill %d tileGrid %d\n",
+              A->stepCount, (int)useTiles, A->lastNumBig, A->lastBigBodies, A->lastMaxIsland, A->lastSpill, A->tileGrid);
+  }
   const int tileBin0 = useTiles ? nbins + 1 : -1;
   const int cutBin = useTiles ? nbins + 1 + A->tileGrid : -1;
   const int nbinsAll = useTiles ? cutBin + 1 : nbins + 1;  // bins whose buckets the sort covers
@@ -1044,8 +1059,11 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   LAUNCH(A, KC_ISLANDS, nb, k_island_alloc, div_up(nb, 256), 256, nb, A->island, A->islandAwake, A->islandCount, A->islandStart,
          A->binFirst, A->binEnd, binSize, bigThr, A->dCounts, A->islandWasBig);
   if (useTiles) {
-    const bool replan = !A->tilePlanValid || A->tilePlanAge >= B2G_TILE_PLAN_PERIOD ||
-                        (long long)A->lastSpill * 50 > A->lastBigBodies;
+    // re-plan periodically, when the oversize bodies have grown by a quarter since the plan, and long before
+    // a tile can fill up (a full tile gives all its bodies up for the step: correct, but slow)
+    const bool replan = !A->tilePlanValid || A->tilePlanAge >= B2G_TILE_PLAN_PERIOD || A->lastSpill > 0 ||
+                        A->lastMaxTile * 5 > B2G_TILE_CAP * 3 ||
+                        (long long)A->lastBigBodies * 4 > (long long)A->tilePlanBodies * 5;
     if (replan) {
       TilePlan init;
       memset(&init, 0, sizeof(init));
@@ -1064,6 +1082,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       LAUNCH(A, KC_ISLANDS, B2G_TILE_YBINS, k_tile_yplan, A->tileGrid, 1024, A->tilePlan, A->tileHistY, A->tileRowOfY);
       A->tilePlanValid = 1;
       A->tilePlanAge = 0;
+      A->tilePlanBodies = A->lastBigBodies;
     }
     A->tilePlanAge++;
     CK(cudaMemsetAsync(A->tileCount, 0, sizeof(int) * B2G_TILES_MAX, A->stream));
@@ -1071,6 +1090,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     LAUNCH(A, KC_ISLANDS, nb, k_tile_assign, div_up(nb, 256), 256, nb, A->pos, A->bflags, A->island, A->islandAwake,
            A->islandCount, bigThr, A->tilePlan, A->tileStripOfX, A->tileRowOfY, A->tileSlot, A->tileBodies, A->tileCount,
            A->spillList, A->dCounts);
+    LAUNCH(A, KC_ISLANDS, nb, k_tile_overflow_fix, div_up(nb, 256), 256, nb, A->tileSlot, A->tileCount, A->spillList, A->dCounts);
     if (nj > 0)
       LAUNCH(A, KC_ISLANDS, nj, k_tile_joint_marks, div_up(nj, 256), 256, nj, A->jBodies, A->tileSlot, A->tileBoundary,
              A->dCounts);
@@ -1120,8 +1140,13 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         A->colourGrid = sms;
       }
       int cutBin = M.cutBin, bb = bigBin;
+      static int singleMax = -1;  // B2G_WL_SINGLE_MAX=n: worklists up to n entries are coloured by one CTA (measurements)
+      if (singleMax < 0) {
+        const char* e = getenv("B2G_WL_SINGLE_MAX");
+        singleMax = e ? atoi(e) : B2G_WL_SINGLE_MAX;
+      }
       void* args[] = {&C, &A->cbin, &A->mass, &A->colourMask, &A->bodyBest, &fixBase, &A->activeList, &A->dCounts,
-                      &bb, &cutBin, &A->bucketCount, &A->conVals, &A->colourBarrier};
+                      &bb, &cutBin, &A->bucketCount, &A->conVals, &A->colourBarrier, &singleMax};
       CK(cudaMemsetAsync(A->colourBarrier, 0, sizeof(unsigned int), A->stream));
       ktime_begin(A, KC_COLOUR, nc);
       // cooperative launch for the co-residency of its grid barrier (the long-worklist mode)
@@ -1185,6 +1210,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     T.warmStarting = P->warm_starting;
     T.allowSleep = P->allow_sleep;
     T.clearForces = P->clear_forces;
+    T.noSequencing = A->tileNoSequencing;
+    T.cutSeq = A->tileCutSeq;
+    T.colourMask = A->colourMask;
     T.plan = A->tilePlan;
     T.tileCount = A->tileCount;
     T.tileBodies = A->tileBodies;
@@ -1211,7 +1239,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     T.bodySlot = A->bodySlot;
     T.counts = A->dCounts;
     T.barrier = A->tileBarrier;
-    const size_t tileSmemBytes = (size_t)B2G_TILE_CAP * (16 + 16 + 4 + 2) + (size_t)B2G_BIG_STAGE_PLANES * B2G_TILE_THREADS * sizeof(float4);
+    const size_t tileSmemBytes = (size_t)B2G_TILE_CAP * B2G_TILE_BODY_BYTES + (size_t)B2G_BIG_STAGE_PLANES * B2G_TILE_THREADS * sizeof(float4);
     static bool attrSet = false;
     if (!attrSet) {
       CK(cudaFuncSetAttribute(k_big_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmemBytes));
@@ -1260,6 +1288,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   A->lastMaxIsland = (nc > 0 || nj > 0) ? A->hCounts->maxIslandBodies : 0;
   A->lastBigBodies = bigBodies;
   A->lastSpill = (nc > 0 || nj > 0) ? A->hCounts->spillCount : 0;
+  A->lastMaxTile = (nc > 0 || nj > 0) ? A->hCounts->maxTileCount : 0;
 
   // ---- oversize islands, not tiled (first appearance, or too many bodies for the tiles): grid-wide passes ----
   if (!useTiles && (numBig > 0 || bigBodies > 0)) {
@@ -2019,6 +2048,24 @@ extern "C" int b2g_debug_big_trace(unsigned long long* out, int32_t blocks) {
   return B2G_OK;
 }
 #endif
+#ifdef B2G_BIG_TRACE
+extern "C" int b2g_debug_tile_marks(unsigned long long* out) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out, g_tileMarks, sizeof(unsigned long long) * B2G_TILES_MAX * B2G_TILE_MARKS));
+  return B2G_OK;
+}
+#endif
+// debug / tests: the current tile plan (11 words: lo[2], hi[2], count, S, R, x0, invDx, y0, invDy), the bodies per
+// tile of the last step and every body's tile slot
+extern "C" int b2g_debug_tile_state(b2gArena* A, uint32_t* plan, int32_t* tileCount, int32_t* tileSlot) {
+  if (!A) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  CK(cudaStreamSynchronize(A->stream));
+  if (plan) CK(cudaMemcpy(plan, A->tilePlan, sizeof(TilePlan), cudaMemcpyDeviceToHost));
+  if (tileCount) CK(cudaMemcpy(tileCount, A->tileCount, sizeof(int) * B2G_TILES_MAX, cudaMemcpyDeviceToHost));
+  if (tileSlot) CK(cudaMemcpy(tileSlot, A->tileSlot, sizeof(int) * (size_t)A->nBodies, cudaMemcpyDeviceToHost));
+  return B2G_OK;
+}
 extern "C" int b2g_set_inv_dt0(b2gArena* A, float v) {
   if (!A) return B2G_ERR_INVALID;
   A->invDt0 = v;

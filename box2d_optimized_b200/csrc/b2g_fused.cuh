@@ -227,10 +227,10 @@ __global__ void __launch_bounds__(B2G_WL_THREADS)
 k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __restrict__ mass,
                   unsigned long long* colourMask, unsigned long long* bodyBest, const int* __restrict__ bodyFixBase,
                   const int* __restrict__ worklist, StepCounts* counts, int bigBin, int cutBin, int* bucketCount,
-                  int* rank, unsigned int* barrier) {
+                  int* rank, unsigned int* barrier, int singleMax) {
   const int n = __ldcg(&counts->worklistCount);
   if (n == 0) return;
-  const bool single = n <= B2G_WL_SINGLE_MAX;
+  const bool single = n <= singleMax;
   if (single && blockIdx.x != 0) return;
   const int stride = single ? blockDim.x : gridDim.x * blockDim.x;
   const int t0 = single ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,9 +243,30 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
       grid_wait(barrier, target);
     }
   };
+  // A constraint that finds no free colour on its bodies goes to its bin's serial bucket without waiting for
+  // its turn to win (a hub body — the tumbler's container touches ~120 boxes — would otherwise cost one round
+  // per contact).  Masks only grow, so "none free" is final; the test is made only while the masks are
+  // stable (here, and in the propose phases — never next to a commit), which keeps the colouring a pure
+  // function of the constraint set.
+  auto full_mask = [&](int i, const int2 bd, int bin, bool movA, bool movB) {
+    const int domain = (bin == cutBin && cutBin >= 0) ? 1 : 0;
+    const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
+    if (~used & colour_domain_mask(domain)) return false;
+    const int c = B2G_OVERFLOW_COLOUR + (domain ? B2G_CUT_DOMAIN_SHIFT : 0);
+    __stcg(&C.colour[i], c);
+    atomicAdd(&counts->numOverflow, 1);
+    if (bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
+    return true;
+  };
+  for (int k = t0; k < n; k += stride) {
+    const int i = worklist[k];
+    const int2 bd = C.body[i];
+    full_mask(i, bd, cbin[i], body_movable(mass[bd.x]), body_movable(mass[bd.y]));
+  }
+  sync_all();
   int round = 0;
   for (;; ++round) {
-    // commit
+    // commit: the winners of this round's proposals take the lowest colour free on both bodies
     int left = 0;
     for (int k = t0; k < n; k += stride) {
       const int i = worklist[k];
@@ -254,29 +275,18 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
       const int bin = cbin[i];
       const int domain = (bin == cutBin && cutBin >= 0) ? 1 : 0;
       const bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
-      const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
-      const unsigned long long freeBits = ~used & colour_domain_mask(domain);
-      int c = -1;
-      if (!freeBits) {
-        // Masks only grow within a step, so a constraint that finds no free colour now never will: it
-        // goes to its bin's serial bucket at once instead of waiting for its turn to win.  (A hub body —
-        // the tumbler's container touches ~120 boxes — would otherwise cost one round per contact.)
-        c = B2G_OVERFLOW_COLOUR + (domain ? B2G_CUT_DOMAIN_SHIFT : 0);
-      } else {
-        const unsigned long long pr = colour_priority(round, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
-        const bool win = (!movA || __ldcg(&bodyBest[bd.x]) == pr) && (!movB || __ldcg(&bodyBest[bd.y]) == pr);
-        if (win) {
-          c = __ffsll((long long)freeBits) - 1;
-          // the winner is unique on each of its movable bodies, so plain read-modify-write is race free
-          const unsigned long long bit = 1ull << c;
-          if (movA) __stcg(&colourMask[bd.x], __ldcg(&colourMask[bd.x]) | bit);
-          if (movB) __stcg(&colourMask[bd.y], __ldcg(&colourMask[bd.y]) | bit);
-          if ((c & 31) + 1 > counts->numColours) atomicMax(&counts->numColours, (c & 31) + 1);
-        }
-      }
-      if (c >= 0) {
+      const unsigned long long pr = colour_priority(round, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
+      const bool win = (!movA || __ldcg(&bodyBest[bd.x]) == pr) && (!movB || __ldcg(&bodyBest[bd.y]) == pr);
+      if (win) {
+        // the winner is unique on each of its movable bodies: nobody else touches their masks this round
+        const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
+        const unsigned long long freeBits = ~used & colour_domain_mask(domain);
+        const int c = __ffsll((long long)freeBits) - 1;  // never empty: checked while the masks were stable
+        const unsigned long long bit = 1ull << c;
+        if (movA) __stcg(&colourMask[bd.x], __ldcg(&colourMask[bd.x]) | bit);
+        if (movB) __stcg(&colourMask[bd.y], __ldcg(&colourMask[bd.y]) | bit);
+        if ((c & 31) + 1 > counts->numColours) atomicMax(&counts->numColours, (c & 31) + 1);
         __stcg(&C.colour[i], c);
-        if ((c & 31) >= B2G_MAX_COLOURS) atomicAdd(&counts->numOverflow, 1);
         if (bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
       } else {
         left = 1;
@@ -293,14 +303,16 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
       any = __ldcg(&counts->worklistLeft[round]);
     }
     if (!any) break;
-    // propose for the next round
+    // propose for the next round (the masks are stable here)
     for (int k = t0; k < n; k += stride) {
       const int i = worklist[k];
       if (__ldcg(&C.colour[i]) >= 0) continue;
       const int2 bd = C.body[i];
+      const bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
+      if (full_mask(i, bd, cbin[i], movA, movB)) continue;
       const unsigned long long pr = colour_priority(round + 1, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
-      if (body_movable(mass[bd.x])) atomicMax(&bodyBest[bd.x], pr);
-      if (body_movable(mass[bd.y])) atomicMax(&bodyBest[bd.y], pr);
+      if (movA) atomicMax(&bodyBest[bd.x], pr);
+      if (movB) atomicMax(&bodyBest[bd.y], pr);
     }
     sync_all();
   }

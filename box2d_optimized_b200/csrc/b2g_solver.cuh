@@ -34,7 +34,7 @@ struct SolverPlanes {
   float4* pn;    // localNormal.x, localNormal.y, localPoint.x, localPoint.y
   float4* pp;    // localPoints[0].xy, localPoints[1].xy
   float4* pc;    // localCenterA.xy, localCenterB.xy
-  float4* pr;    // radiusA, radiusB, bits(type), bits(pointCount)
+  float4* pr;    // radiusA, radiusB, bits(type | pointCount << 8), bits(island root)
 };
 
 #ifdef __CUDACC__
@@ -67,7 +67,7 @@ __device__ __forceinline__ void prepare_constraint(const SolverPlanes& S, int s,
                                                    float radiusA, float radiusB, const PosAccess& bodyPos,
                                                    const VelAccess& bodyVel, const float4* __restrict__ bodyMass,
                                                    const float4* __restrict__ bodyCenter, float dtRatio,
-                                                   bool warmStarting) {
+                                                   bool warmStarting, int root = 0) {
   float4 mAq = bodyMass[bodyA], mBq = bodyMass[bodyB];
   float mA = mAq.x, iA = mAq.y, mB = mBq.x, iB = mBq.y;
   float4 cenA = bodyCenter[bodyA], cenB = bodyCenter[bodyB];
@@ -86,7 +86,9 @@ __device__ __forceinline__ void prepare_constraint(const SolverPlanes& S, int s,
   S.pn[s] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
   S.pp[s] = make_float4(m.lp[0].x, m.lp[0].y, m.lp[1].x, m.lp[1].y);
   S.pc[s] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
-  S.pr[s] = make_float4(radiusA, radiusB, __int_as_float(m.type), __int_as_float(pointCount));
+  // type and point count share a word; the freed lane carries the island root, so that a position pass
+  // finds "is my island done?" in the constants it has staged anyway
+  S.pr[s] = make_float4(radiusA, radiusB, __int_as_float(m.type | (pointCount << 8)), __int_as_float(root));
   S.mass[s] = make_float4(mA, iA, mB, iB);
 
   float imp[4];
@@ -332,17 +334,21 @@ __device__ __forceinline__ float solve_position_constraint(const SolverPlanes& S
   float2 localNormal = make_float2(pn.x, pn.y), localPoint = make_float2(pn.z, pn.w);
   float2 localCenterA = make_float2(pcen.x, pcen.y), localCenterB = make_float2(pcen.z, pcen.w);
   float radiusA = pr.x, radiusB = pr.y;
-  const int type = __float_as_int(pr.z);
-  const int pointCount = __float_as_int(pr.w);
+  const int type = __float_as_int(pr.z) & 0xff;
+  const int pointCount = __float_as_int(pr.z) >> 8;
 
   float4 pAq = bodyPos.load(ix.x), pBq = bodyPos.load(ix.y);
   float2 cA = make_float2(pAq.x, pAq.y), cB = make_float2(pBq.x, pBq.y);
   float aA = pAq.z, aB = pBq.z;
   float minSeparation = 0.0f;
 
+  // b2PositionSolverManifold::Initialize recomputes both transforms from (c, a) for every point (b2_contact_solver.cpp
+  // :746-752).  A transform is a pure function of (c, a), and a point whose correction is zero leaves (c, a) of both
+  // bodies bit-for-bit unchanged, so the second point may reuse the first point's transform of any body that did
+  // not move: same floats, half the sin / cos evaluations on a settled pile.
+  Xf xfA = xf_from_sweep(cA, aA, localCenterA);
+  Xf xfB = xf_from_sweep(cB, aB, localCenterB);
   for (int j = 0; j < pointCount; ++j) {
-    Xf xfA = xf_from_sweep(cA, aA, localCenterA);
-    Xf xfB = xf_from_sweep(cB, aB, localCenterB);
     float2 lpj = j == 0 ? make_float2(pp.x, pp.y) : make_float2(pp.z, pp.w);
     float2 normal, point;
     float separation;
@@ -380,6 +386,10 @@ __device__ __forceinline__ float solve_position_constraint(const SolverPlanes& S
     aA -= iA * cross2(rA, P);
     cB += mB * P;
     aB += iB * cross2(rB, P);
+    if (j + 1 < pointCount && impulse != 0.0f) {
+      if (movable(mA, iA)) xfA = xf_from_sweep(cA, aA, localCenterA);
+      if (movable(mB, iB)) xfB = xf_from_sweep(cB, aB, localCenterB);
+    }
   }
   if (movable(mA, iA)) bodyPos.store(ix.x, make_float4(cA.x, cA.y, aA, pAq.w));
   if (movable(mB, iB)) bodyPos.store(ix.y, make_float4(cB.x, cB.y, aB, pBq.w));

@@ -1,17 +1,53 @@
-"""Where does k_big_solve spend a pass?  Needs libb2cuda.so built with -DB2G_BIG_TRACE (per-block
-globaltimer stamps at every grid_arrive / grid_wait exit).  Prints, per barrier, the work time of the
-median and the slowest block and the time from the last arrival to the release."""
+"""Where does the oversize-island kernel (k_big_tiles, or k_big_solve with B2G_NO_TILES=1) spend its time?
+Needs a library built with -DB2G_BIG_TRACE (per-block globaltimer stamps at every grid_arrive / grid_wait exit):
+
+    python -c "from box2d_optimized_b200 import build as b; b.build_cuda(True, 'libb2cuda_trace.so', ['-DB2G_BIG_TRACE'])"
+    B2G_CUDA_LIB=box2d_optimized_b200/libb2cuda_trace.so python scripts/gpu_big_trace.py [bodies] [steps]
+
+Prints, per grid barrier, the work time (release of the previous barrier -> arrival) of the median and the slowest
+block and the time from the last arrival to the release, plus the colour histograms of both domains."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from box2d_optimized_b200 import GpuScene, capi
+from box2d_optimized_b200 import GpuScene, capi, Arena, arena_from_scene
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
-g = GpuScene("mixed", n, 12345)
-g.step(steps)
-g.bodies()
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 310
+scene = GpuScene("mixed", n, 12345)
+A = arena_from_scene(scene, max_contacts=8 * n)
+A.find_new_contacts()
+P = Arena.params()
+st = capi.StepStats()
+for _ in range(steps):
+    A.step(P, st)
+A.synchronize()
+print("constraints", st.num_constraints, "colours", st.num_colours, "serial", st.num_overflow, "rounds", st.colour_rounds)
+col = A.download_contacts()["colour"]
+act = col[col >= 0]
+print("interior colour histogram:", np.bincount(act[act < 32], minlength=25).tolist())
+print("cut colour histogram     :", np.bincount(act[act >= 32] - 32, minlength=25).tolist())
 lib = capi.load_cuda()
+if hasattr(lib, "b2g_debug_tile_marks"):
+    marks = np.zeros((160, 64), np.uint64)
+    lib.b2g_debug_tile_marks.argtypes = [C.c_void_p]
+    if lib.b2g_debug_tile_marks(marks.ctypes.data_as(C.c_void_p)) == 0 and marks[0, 0] > 0:
+        m = marks[:148].astype(np.int64)
+        t0 = m[:, 0].min()
+        names = {0: "kernel start", 1: "tile loaded", 2: "barrier 0 passed", 3: "constraints prepared", 4: "serial prepared",
+                 5: "warm start done", 31: "positions integrated", 40: "end"}
+        for i in range(6, 14):
+            names[i] = f"velocity sweep {i - 6} done"
+        for i in range(32, 35):
+            names[i] = f"position sweep {i - 32} done"
+        prev = None
+        print("phase marks of k_big_tiles, us since the first block started (min / median / max over blocks; delta of medians):")
+        for i in sorted(names):
+            col = m[:, i]
+            if (col <= 0).all():
+                continue
+            med = float(np.median(col - t0)) / 1e3
+            print(f"  {names[i]:24s} {float((col - t0).min()) / 1e3:8.2f} {med:8.2f} {float((col - t0).max()) / 1e3:8.2f}   +{(med - prev) if prev is not None else 0.0:7.2f}")
+            prev = med
 CAP, B = 1024, 148
 buf = np.zeros((B, CAP, 2), np.uint64)
 lib.b2g_debug_big_trace.argtypes = [C.c_void_p, C.c_int]
@@ -21,14 +57,16 @@ t = buf.astype(np.int64)
 nb = int((t[0, :, 0] > 0).sum())
 arr, rel = t[:, :nb, 0], t[:, :nb, 1]
 t0 = arr.min()
-print("barriers", nb, "kernel span us", (rel.max() - t0) / 1e3)
+print("barriers", nb, "first arrival -> last release us", (rel.max() - t0) / 1e3)
 work = arr[:, 1:] - rel[:, :-1]          # release of barrier i-1 -> arrival at barrier i, per block
 lastArr = arr.max(axis=0)
 relMin, relMax = rel.min(axis=0), rel.max(axis=0)
-print("per pass (us): work median-block %.2f, slowest-block %.2f | last arrival -> first release %.2f, -> last release %.2f | period %.2f" % (
+print("per barrier (us): work median-block %.2f, slowest-block %.2f | last arrival -> first release %.2f, -> last release %.2f | period %.2f" % (
     np.median(work, axis=0).mean() / 1e3, work.max(axis=0).mean() / 1e3, (relMin - lastArr).mean() / 1e3,
     (relMax - lastArr).mean() / 1e3, np.diff(lastArr).mean() / 1e3))
-for i in range(0, nb - 1, max(1, nb // 60)):
-    print(i, "work med %.2f max %.2f argmax %d | rel-lastArr %.2f..%.2f" % (
-        np.median(work[:, i]) / 1e3, work[:, i].max() / 1e3, int(work[:, i].argmax()), (relMin[i + 1] - lastArr[i + 1]) / 1e3,
-        (relMax[i + 1] - lastArr[i + 1]) / 1e3))
+print("sum over barriers: slowest-block work %.1f us, barrier latency %.1f us" % (
+    work.max(axis=0).sum() / 1e3, (relMax - lastArr).sum() / 1e3))
+for i in range(nb - 1):
+    print(i + 1, "work med %.2f max %.2f min %.2f argmax %d | rel-lastArr %.2f..%.2f" % (
+        np.median(work[:, i]) / 1e3, work[:, i].max() / 1e3, work[:, i].min() / 1e3, int(work[:, i].argmax()),
+        (relMin[i + 1] - lastArr[i + 1]) / 1e3, (relMax[i + 1] - lastArr[i + 1]) / 1e3))
