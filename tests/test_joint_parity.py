@@ -145,5 +145,5 @@ def test_jointed_scenes_run_free_in_the_production_mode(require_ref, name, size,
         few = int(dyn.sum()) < 10            # a handful of loose bodies is hardly an aggregate
         assert abs(pe_g - pe_r) <= (0.30 if few else 0.15) * abs(pe_r) + 1.0
         assert profile < (0.6 if few else 0.35)
-        assert hg[0] > hr[0] - 0.1            # nothing fell through the ground
+        assert hg[0] > (0.05 if few else hr[0] - 0.1)   # nothing fell through the ground
         assert speed_g < speed_r + 3.0
