@@ -14,7 +14,7 @@
 #define B2G_MAX_COLOURS 24          // colours solved by parallel launches
 #define B2G_OVERFLOW_COLOUR B2G_MAX_COLOURS  // serial overflow bucket
 #define B2G_MAX_POS_ITERS 16
-#define B2G_ISLAND_EXACT_PERIOD 8  // steps between exact recomputations of oversize islands' labels
+#define B2G_ISLAND_EXACT_PERIOD 16  // steps between exact recomputations of oversize islands' labels
 #define B2G_BVH_REBUILD_PERIOD 64  // longest run of refit-only steps; the leaf order is re-sorted earlier when walks get longer
 #define B2G_KT_MAX 2048  // timed launches per step when per-kernel timing is on
 

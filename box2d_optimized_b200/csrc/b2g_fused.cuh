@@ -103,12 +103,14 @@ __device__ __forceinline__ unsigned long long local_pair_key(unsigned long long 
   return key - ((base << 32) | base);
 }
 __global__ void k_world_fix_min(int nf, const int* __restrict__ fBody, const int* __restrict__ bworld, int* worldFixMin) {
+  B2G_PDL_ENTER();
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nf) return;
   atomicMin(&worldFixMin[bworld[fBody[f]]], f);
 }
 __global__ void k_body_fix_base(int nb, const int* __restrict__ bworld, const int* __restrict__ worldFixMin,
                                 int* bodyFixBase) {
+  B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   int m = worldFixMin[bworld[b]];
@@ -243,54 +245,95 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
       grid_wait(barrier, target);
     }
   };
+  // A thread's worklist entries (k = t0, t0 + stride, ...) and everything about them that does not change
+  // during the launch live in registers: a round is then one look at the bodies' proposals, not a chain of
+  // dependent loads.  (Two entries per thread cover 2 048 constraints in single-CTA mode and ~300 k in grid
+  // mode; a longer list is still handled, from memory.)
+  struct Entry {
+    int i, a, b, bin;
+    unsigned long long k56;
+    bool movA, movB, open;  // open = still uncoloured
+  };
+  auto fetch = [&](int k) {
+    Entry e;
+    e.i = worklist[k];
+    const int2 bd = C.body[e.i];
+    e.a = bd.x;
+    e.b = bd.y;
+    e.bin = cbin[e.i];
+    e.k56 = colour_key56(local_pair_key(C.key[e.i], bodyFixBase, bd.x));
+    e.movA = body_movable(mass[bd.x]);
+    e.movB = body_movable(mass[bd.y]);
+    e.open = true;
+    return e;
+  };
+  constexpr int CACHED = 2;
+  Entry cache[CACHED];
+#pragma unroll
+  for (int j = 0; j < CACHED; ++j) {
+    cache[j].open = false;
+    if (t0 + j * stride < n) cache[j] = fetch(t0 + j * stride);
+  }
+  const int kRest = t0 + CACHED * stride;  // first entry of this thread that is not cached
   // A constraint that finds no free colour on its bodies goes to its bin's serial bucket without waiting for
   // its turn to win (a hub body — the tumbler's container touches ~120 boxes — would otherwise cost one round
   // per contact).  Masks only grow, so "none free" is final; the test is made only while the masks are
-  // stable (here, and in the propose phases — never next to a commit), which keeps the colouring a pure
-  // function of the constraint set.
-  auto full_mask = [&](int i, const int2 bd, int bin, bool movA, bool movB) {
-    const int domain = (bin == cutBin && cutBin >= 0) ? 1 : 0;
-    const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
+  // stable (before round 0, and in the propose phases — never next to a commit), which keeps the colouring a
+  // pure function of the constraint set.
+  auto full_mask = [&](Entry& e) {
+    const int domain = (e.bin == cutBin && cutBin >= 0) ? 1 : 0;
+    const unsigned long long used = (e.movA ? __ldcg(&colourMask[e.a]) : 0ull) | (e.movB ? __ldcg(&colourMask[e.b]) : 0ull);
     if (~used & colour_domain_mask(domain)) return false;
     const int c = B2G_OVERFLOW_COLOUR + (domain ? B2G_CUT_DOMAIN_SHIFT : 0);
-    __stcg(&C.colour[i], c);
+    __stcg(&C.colour[e.i], c);
+    e.open = false;
     atomicAdd(&counts->numOverflow, 1);
-    if (bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
+    if (e.bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
     return true;
   };
-  for (int k = t0; k < n; k += stride) {
-    const int i = worklist[k];
-    const int2 bd = C.body[i];
-    full_mask(i, bd, cbin[i], body_movable(mass[bd.x]), body_movable(mass[bd.y]));
+  // commit: the winner of this round's proposals takes the lowest colour free on both bodies
+  auto commit = [&](Entry& e, int round) {
+    const unsigned long long pr = ((unsigned long long)(round + 1) << 56) | e.k56;
+    const bool win = (!e.movA || __ldcg(&bodyBest[e.a]) == pr) && (!e.movB || __ldcg(&bodyBest[e.b]) == pr);
+    if (!win) return false;
+    // the winner is unique on each of its movable bodies: nobody else touches their masks this round
+    const int domain = (e.bin == cutBin && cutBin >= 0) ? 1 : 0;
+    const unsigned long long ma = e.movA ? __ldcg(&colourMask[e.a]) : 0ull, mb = e.movB ? __ldcg(&colourMask[e.b]) : 0ull;
+    const unsigned long long freeBits = ~(ma | mb) & colour_domain_mask(domain);
+    const int c = __ffsll((long long)freeBits) - 1;  // never empty: checked while the masks were stable
+    const unsigned long long bit = 1ull << c;
+    if (e.movA) __stcg(&colourMask[e.a], ma | bit);
+    if (e.movB) __stcg(&colourMask[e.b], mb | bit);
+    if ((c & 31) + 1 > counts->numColours) atomicMax(&counts->numColours, (c & 31) + 1);
+    __stcg(&C.colour[e.i], c);
+    e.open = false;
+    if (e.bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
+    return true;
+  };
+  auto propose = [&](Entry& e, int round) {
+    if (full_mask(e)) return;
+    const unsigned long long pr = ((unsigned long long)(round + 1) << 56) | e.k56;
+    if (e.movA) atomicMax(&bodyBest[e.a], pr);
+    if (e.movB) atomicMax(&bodyBest[e.b], pr);
+  };
+#pragma unroll
+  for (int j = 0; j < CACHED; ++j)
+    if (cache[j].open) full_mask(cache[j]);
+  for (int k = kRest; k < n; k += stride) {
+    Entry e = fetch(k);
+    full_mask(e);
   }
   sync_all();
   int round = 0;
   for (;; ++round) {
-    // commit: the winners of this round's proposals take the lowest colour free on both bodies
     int left = 0;
-    for (int k = t0; k < n; k += stride) {
-      const int i = worklist[k];
-      if (__ldcg(&C.colour[i]) >= 0) continue;
-      const int2 bd = C.body[i];
-      const int bin = cbin[i];
-      const int domain = (bin == cutBin && cutBin >= 0) ? 1 : 0;
-      const bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
-      const unsigned long long pr = colour_priority(round, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
-      const bool win = (!movA || __ldcg(&bodyBest[bd.x]) == pr) && (!movB || __ldcg(&bodyBest[bd.y]) == pr);
-      if (win) {
-        // the winner is unique on each of its movable bodies: nobody else touches their masks this round
-        const unsigned long long used = (movA ? __ldcg(&colourMask[bd.x]) : 0ull) | (movB ? __ldcg(&colourMask[bd.y]) : 0ull);
-        const unsigned long long freeBits = ~used & colour_domain_mask(domain);
-        const int c = __ffsll((long long)freeBits) - 1;  // never empty: checked while the masks were stable
-        const unsigned long long bit = 1ull << c;
-        if (movA) __stcg(&colourMask[bd.x], __ldcg(&colourMask[bd.x]) | bit);
-        if (movB) __stcg(&colourMask[bd.y], __ldcg(&colourMask[bd.y]) | bit);
-        if ((c & 31) + 1 > counts->numColours) atomicMax(&counts->numColours, (c & 31) + 1);
-        __stcg(&C.colour[i], c);
-        if (bin == bigBin) atomicAdd(&counts->colourCount[c & 31], 1);
-      } else {
-        left = 1;
-      }
+#pragma unroll
+    for (int j = 0; j < CACHED; ++j)
+      if (cache[j].open && !commit(cache[j], round)) left = 1;
+    for (int k = kRest; k < n; k += stride) {
+      if (__ldcg(&C.colour[worklist[k]]) >= 0) continue;
+      Entry e = fetch(k);
+      if (!commit(e, round)) left = 1;
     }
     if (round + 1 >= B2G_WL_MAX_ROUNDS) break;
     // anything left anywhere?
@@ -304,15 +347,13 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
     }
     if (!any) break;
     // propose for the next round (the masks are stable here)
-    for (int k = t0; k < n; k += stride) {
-      const int i = worklist[k];
-      if (__ldcg(&C.colour[i]) >= 0) continue;
-      const int2 bd = C.body[i];
-      const bool movA = body_movable(mass[bd.x]), movB = body_movable(mass[bd.y]);
-      if (full_mask(i, bd, cbin[i], movA, movB)) continue;
-      const unsigned long long pr = colour_priority(round + 1, i, local_pair_key(C.key[i], bodyFixBase, bd.x));
-      if (movA) atomicMax(&bodyBest[bd.x], pr);
-      if (movB) atomicMax(&bodyBest[bd.y], pr);
+#pragma unroll
+    for (int j = 0; j < CACHED; ++j)
+      if (cache[j].open) propose(cache[j], round + 1);
+    for (int k = kRest; k < n; k += stride) {
+      if (__ldcg(&C.colour[worklist[k]]) >= 0) continue;
+      Entry e = fetch(k);
+      propose(e, round + 1);
     }
     sync_all();
   }

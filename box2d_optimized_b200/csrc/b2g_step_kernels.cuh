@@ -247,19 +247,26 @@ __global__ void k_island_flatten(int nb, const uint32_t* __restrict__ bflags, co
                                  uint8_t* islandDirty) {
   B2G_PDL_ENTER();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  islandDirty[b] = 0;  // consumed by k_body_begin of this step
-  int root = b;
-  for (int p = parent[root]; p != root; p = parent[root]) root = p;
-  island[b] = root;
-  uint32_t f = bflags[b];
-  if (B2G_BODY_TYPE(f) != B2G_STATIC) {
-    // island size = its non-static members (all of them are simulated once the island is awake)
-    int c = atomicAdd(&islandCount[root], 1) + 1;
+  int root = -1;
+  uint32_t f = 0;
+  if (b < nb) {
+    islandDirty[b] = 0;  // consumed by k_body_begin of this step
+    root = b;
+    for (int p = parent[root]; p != root; p = parent[root]) root = p;
+    island[b] = root;
+    f = bflags[b];
+  }
+  // island size = its non-static members (all of them are simulated once the island is awake).  One atomic per
+  // warp and island: the 100 000 bodies of a settled pile would otherwise all hit one counter.
+  const bool counted = b < nb && B2G_BODY_TYPE(f) != B2G_STATIC;
+  const unsigned int peers = __match_any_sync(0xffffffffu, counted ? root : -1);
+  if (counted && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+    int c = atomicAdd(&islandCount[root], __popc(peers)) + __popc(peers);
     if (c > counts->maxIslandBodies) atomicMax(&counts->maxIslandBodies, c);
   }
   // an island is simulated when any member could seed it (b2_world.cpp:526-545)
-  if ((f & B2G_BODY_AWAKE) && (f & B2G_BODY_ENABLED) && B2G_BODY_TYPE(f) != B2G_STATIC) islandAwake[root] = 1u;
+  if (b < nb && (f & B2G_BODY_AWAKE) && (f & B2G_BODY_ENABLED) && B2G_BODY_TYPE(f) != B2G_STATIC && !islandAwake[root])
+    islandAwake[root] = 1u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -356,15 +363,18 @@ __global__ void k_colour_begin(const int* __restrict__ numActivePtr, const int* 
 
 // Unique per constraint (a bijection of the 56-bit pair key) so two constraints on one body can
 // never tie, and a function of the pair alone so colours do not depend on contact slot numbers.
-__device__ __forceinline__ unsigned long long colour_priority(int round, int s, unsigned long long key) {
-  (void)s;
+__device__ __forceinline__ unsigned long long colour_key56(unsigned long long key) {
   const unsigned long long M56 = (1ull << 56) - 1ull;
   unsigned long long k = ((key >> 32) << 28 | (key & 0xfffffffull)) & M56;  // fixture indices < 2^28
   k = (k * 0x9e3779b97f4a7c15ull) & M56;  // odd multiplier: bijective mod 2^56
   k ^= k >> 29;                          // xor-shift: bijective
   k = (k * 0xbf58476d1ce4e5b9ull) & M56;
   k ^= k >> 31;
-  return ((unsigned long long)(round + 1) << 56) | k;
+  return k;
+}
+__device__ __forceinline__ unsigned long long colour_priority(int round, int s, unsigned long long key) {
+  (void)s;
+  return ((unsigned long long)(round + 1) << 56) | colour_key56(key);
 }
 
 __global__ void k_colour_propose(const int* __restrict__ numActivePtr, const int* __restrict__ activeList, ContactBuf C,

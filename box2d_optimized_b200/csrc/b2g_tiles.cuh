@@ -567,6 +567,7 @@ __device__ __forceinline__ void tile_sweep(TileCtx& X, BigStage& G, const Solver
   }
   float4* sm = PHASE == B2G_BIG_POSITION ? X.pos : X.vel;
   float4* gl = PHASE == B2G_BIG_POSITION ? A.pos : A.vel;
+  TILE_MARK(44 + (PHASE == B2G_BIG_POSITION ? 9 + X.seqP : X.seqV));  // interior part of this sweep done
   // ---- cut
   if (X.anyCut && X.seqMode) {
     const int q = PHASE == B2G_BIG_POSITION ? X.seqP++ : X.seqV++;

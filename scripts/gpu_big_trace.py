@@ -39,9 +39,12 @@ if hasattr(lib, "b2g_debug_tile_marks"):
             names[i] = f"velocity sweep {i - 6} done"
         for i in range(32, 35):
             names[i] = f"position sweep {i - 32} done"
+        for i in range(44, 56):
+            names[i] = f"  interior of sweep {i - 44} done"
+        order = [0, 1, 2, 3, 4, 44, 5] + [x for it in range(8) for x in (45 + it, 6 + it)] + [31] + [x for it in range(3) for x in (53 + it, 32 + it)] + [40]
         prev = None
         print("phase marks of k_big_tiles, us since the first block started (min / median / max over blocks; delta of medians):")
-        for i in sorted(names):
+        for i in order:
             col = m[:, i]
             if (col <= 0).all():
                 continue
