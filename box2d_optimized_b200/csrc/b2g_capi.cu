@@ -993,16 +993,27 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   {
     int want = ctasOverride;
     // chain-heavy = at least 2 % of last step's solver rows sat in serial buckets (hub bodies)
-    if (want == 0)
-      want = (nb / binSize + 1 >= 4 * 148 && bigThr >= 128 && A->lastActive > 0 &&
-              (long long)A->lastOverflow * 50 >= A->lastActive) ? 4 : 2;
-    if (want > 2) {
-      size_t per = (size_t)(227 * 1024) / want - 2048;
-      int fit = (int)(per / (FusedTile::bytes(1024) / 1024)) - bigThr;  // bodies of small islands that still fit next to one big one
+    const bool chainHeavy = nb / binSize + 1 >= 4 * 148 && bigThr >= 128 && A->lastActive > 0 &&
+                            (long long)A->lastOverflow * 50 >= A->lastActive;
+    if (want == 0) want = chainHeavy ? 7 : 2;
+    // Try the densest packing first: 7 blocks of 96 threads per SM hold 1036 islands at once (1024 batched
+    // tumbler worlds = ONE wave instead of two), then 6 and 4 blocks of 128 threads.  What decides is the
+    // tile: one island of up to bigThr bodies (+ a few small ones) must fit the block's share of shared
+    // memory.  With many equal islands their size is stable, so the cap follows it tightly (an island that
+    // outgrows it within one step takes the grid-pass kernel for that step).
+    const int tight = A->lastMaxIsland + A->lastMaxIsland / 16 + 8;
+    for (int w = want; w > 2; w = (w > 6 ? 6 : (w > 4 ? 4 : 2))) {
+      const size_t per = (size_t)(227 * 1024) / w - 2048;
+      const int cap = (int)(per / (FusedTile::bytes(1024) / 1024));  // bodies a block's tile can hold
+      int thr = bigThr;
+      if (cap - thr < 32 && w > 4 && tight >= 128 && tight < thr) thr = tight;
+      const int fit = cap - thr;  // bodies of small islands that still fit next to one big one
       if (fit >= 32) {
+        bigThr = thr;
         if (binSize > fit) binSize = fit;
         budget = per;
-        fusedThreads = 128;
+        fusedThreads = w > 6 ? 96 : 128;
+        break;
       }
     }
   }

@@ -641,6 +641,33 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     S.pc = base + 11 * cc - cAll0;
     S.pr = base + 12 * cc - cAll0;
   }
+  // The SERIAL bucket (constraints of a hub body beyond the 24 colours: the tumbler's container touches ~65
+  // boxes) is one thread walking a chain, one dependent L2 / HBM round trip per constraint just to fetch its
+  // constants.  When the planes live in global memory the otherwise unused plane area of this block holds
+  // the bucket's constants instead: velocity planes for warm start + velocity iterations (impulses written
+  // back once), then the position planes.
+  const int ov0 = cstart[B2G_MAX_COLOURS], ov1 = cstart[B2G_MAX_COLOURS + 1];
+  SolverPlanes V = S;  // view of the staged serial bucket (slots ov0 .. ov0 + nStaged)
+  int nStaged = 0;
+  if (cAll1 - cAll0 > P.conCap && ov1 > ov0) {
+    nStaged = min(ov1 - ov0, (P.conCap * B2G_PLANES) / 9);
+    float4* base = (float4*)(smemRaw + FusedTile::bytes(P.tileCap));
+    const ptrdiff_t cc = nStaged;
+    V.idx = (int4*)(base + 0 * cc) - ov0;
+    V.mass = base + 1 * cc - ov0;
+    V.nf = base + 2 * cc - ov0;
+    V.r1 = base + 3 * cc - ov0;
+    V.r2 = base + 4 * cc - ov0;
+    V.m1 = base + 5 * cc - ov0;
+    V.m2 = base + 6 * cc - ov0;
+    V.kk = base + 7 * cc - ov0;
+    V.imp = base + 8 * cc - ov0;
+    V.pn = base + 2 * cc - ov0;  // the position planes reuse the velocity slots
+    V.pp = base + 3 * cc - ov0;
+    V.pc = base + 4 * cc - ov0;
+    V.pr = base + 5 * cc - ov0;
+  }
+  const int ovStaged = ov0 + nStaged;  // serial slots below this one are read from V, the others from S
 
   // ---- phase 1: prepare every constraint of the bin --------------------------------------------
   for (int s = cAll0 + tid; s < cAll1; s += nt) {
@@ -656,6 +683,21 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
                        gmass, gcenter, P.dtRatio, P.warmStarting != 0);
   }
   __syncthreads();
+  if (nStaged > 0) {
+    for (int t = tid; t < nStaged; t += nt) {
+      const int sl = ov0 + t;
+      V.idx[sl] = S.idx[sl];
+      V.mass[sl] = S.mass[sl];
+      V.nf[sl] = S.nf[sl];
+      V.r1[sl] = S.r1[sl];
+      V.r2[sl] = S.r2[sl];
+      V.m1[sl] = S.m1[sl];
+      V.m2[sl] = S.m2[sl];
+      V.kk[sl] = S.kk[sl];
+      V.imp[sl] = S.imp[sl];
+    }
+    __syncthreads();
+  }
 
   // ---- phase 2: warm start, colour by colour ---------------------------------------------------
   if (P.warmStarting) {
@@ -665,8 +707,10 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
       __syncthreads();
     }
     if (cstart[B2G_MAX_COLOURS] != cstart[B2G_MAX_COLOURS + 1]) {
-      if (tid == 0)
-        for (int s = cstart[B2G_MAX_COLOURS]; s < cstart[B2G_MAX_COLOURS + 1]; ++s) warm_start_constraint(S, s, velAcc);
+      if (tid == 0) {
+        for (int s = ov0; s < ovStaged; ++s) warm_start_constraint(V, s, velAcc);
+        for (int s = ovStaged; s < ov1; ++s) warm_start_constraint(S, s, velAcc);
+      }
       __syncthreads();
     }
   }
@@ -696,9 +740,10 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
       __syncthreads();
     }
     if (cstart[B2G_MAX_COLOURS] != cstart[B2G_MAX_COLOURS + 1]) {
-      if (tid == 0)
-        for (int s = cstart[B2G_MAX_COLOURS]; s < cstart[B2G_MAX_COLOURS + 1]; ++s)
-          solve_velocity_constraint(S, s, velAcc);
+      if (tid == 0) {
+        for (int s = ov0; s < ovStaged; ++s) solve_velocity_constraint(V, s, velAcc);
+        for (int s = ovStaged; s < ov1; ++s) solve_velocity_constraint(S, s, velAcc);
+      }
       __syncthreads();
     }
   }
@@ -706,7 +751,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
   // ---- phase 4: store impulses (b2_contact_solver.cpp:641-657) -----------------------------------
   for (int s = cAll0 + tid; s < cAll1; s += nt) {
     int4 ix = S.idx[s];
-    float4 imp = S.imp[s];
+    float4 imp = (s >= ov0 && s < ovStaged) ? V.imp[s] : S.imp[s];
     int i = ix.w;
     float4 q1 = C.m1[i];
     q1.z = imp.x;
@@ -742,7 +787,17 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     T.pos[l] = p4;
     T.vel[l] = make_float4(v.x, v.y, w, v4.w);
   }
-  __syncthreads();
+  __syncthreads();  // (also: phase 4 has read the staged impulses)
+  if (nStaged > 0 && P.posIters > 0) {
+    for (int t = tid; t < nStaged; t += nt) {
+      const int sl = ov0 + t;
+      V.pn[sl] = S.pn[sl];
+      V.pp[sl] = S.pp[sl];
+      V.pc[sl] = S.pc[sl];
+      V.pr[sl] = S.pr[sl];
+    }
+    __syncthreads();
+  }
 
   // ---- phase 6: position iterations with the per-island early exit (b2_island.cpp:391-409) --------
   for (int it = 0; it < P.posIters; ++it) {
@@ -760,11 +815,12 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
         sStep = 1;
       }
       for (int s = sBegin; s < s1; s += sStep) {
-        int4 ix = S.idx[s];
+        const bool staged = k == nUsed && s < ovStaged;
+        int4 ix = staged ? V.idx[s] : S.idx[s];
         int slot = ix.x >= 0 ? ix.x : ix.y;  // a tile member of the island (the other may be static)
         int hd = T.head[slot];
         if (T.done[hd]) continue;
-        float minSep = solve_position_constraint(S, s, posAcc);
+        float minSep = staged ? solve_position_constraint(V, s, posAcc) : solve_position_constraint(S, s, posAcc);
         float pen = minSep < 0.0f ? -minSep : 0.0f;
         atomicMax(&T.pen[hd], __float_as_uint(pen));
       }
