@@ -1,6 +1,7 @@
 """Build recipe for the native libraries (sm_100a only, no other targets).
 
   libb2cuda.so        CUDA kernels + the C-ABI of include/b2cuda.h        (nvcc)
+  libb2cuda_dist.so   NCCL transport of the slab halo exchange (b2g_dist_*)   (nvcc, links NCCL)
   libb2gpu_scenes.so  drop-in C++ API (include/box2d) + scene shim over it  (g++)
 
 Both are built IN-TREE next to this file so they travel with a gpurun snapshot.
@@ -51,6 +52,28 @@ def build_cuda(force=False, out_name="libb2cuda.so", extra_flags=()):
     return out
 
 
+def _nccl_dirs():
+    """NCCL as bundled with torch (the process then holds ONE NCCL, torch's), else the system one"""
+    import sysconfig
+    sp = sysconfig.get_paths()["purelib"]
+    inc, lib = os.path.join(sp, "nvidia", "nccl", "include"), os.path.join(sp, "nvidia", "nccl", "lib")
+    if os.path.exists(os.path.join(inc, "nccl.h")) and os.path.exists(os.path.join(lib, "libnccl.so.2")):
+        return inc, lib
+    return "/usr/include", "/usr/lib/x86_64-linux-gnu"
+
+
+def build_dist(force=False):
+    """libb2cuda_dist.so: the NCCL transport of the halo exchange (b2g_dist_*), over libb2cuda.so"""
+    out = os.path.join(HERE, "libb2cuda_dist.so")
+    src = os.path.join(CSRC, "b2g_dist.cu")
+    if force or _newer(out, [src, os.path.join(ROOT, "include", "b2cuda.h"), os.path.join(HERE, "libb2cuda.so")]):
+        nvcc = _find("nvcc", "/usr/local/cuda/bin/nvcc")
+        inc, lib = _nccl_dirs()
+        _run([nvcc] + NVCC_FLAGS + ["-I" + inc, "-o", out, src, "-L" + HERE, "-lb2cuda", "-L" + lib, "-l:libnccl.so.2",
+                                    "-Xlinker", "-rpath,$ORIGIN", "-Xlinker", "-rpath," + lib])
+    return out
+
+
 def build_host(force=False):
     out = os.path.join(HERE, "libb2gpu_scenes.so")
     srcs = [os.path.join(HOST, f) for f in ("b2_world_host.cpp", "b2_shapes.cpp", "gpu_scene_shim.cpp")]
@@ -81,7 +104,7 @@ def build_oracle(force=False):
 
 
 def build_all(force=False):
-    return [build_cuda(force), build_host(force)] + build_oracle(force)
+    return [build_cuda(force), build_dist(force), build_host(force)] + build_oracle(force)
 
 
 if __name__ == "__main__":

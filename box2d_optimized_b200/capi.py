@@ -85,7 +85,9 @@ CUDA_SYMBOLS = [
     "b2g_set_inv_dt0", "b2g_set_kernel_timing", "b2g_kernel_class_count", "b2g_kernel_class_name",
     "b2g_get_kernel_timing", "b2g_device_views", "b2g_upload_contacts", "b2g_set_sequential_order", "b2g_set_sequential_joint_order", "b2g_host_alloc", "b2g_host_free", "b2g_download_new_pairs", "b2g_set_pair_vetoes", "b2g_download_veto_seen", "b2g_query_aabb", "b2g_ray_cast_closest", "b2g_ray_cast_all", "b2g_download_joints", "b2g_rotations", "b2g_compute_aabbs", "b2g_collide_pairs",
     "b2g_find_pairs", "b2g_solve_sequential",
+    "b2g_halo_set_lists", "b2g_halo_pack", "b2g_halo_recv_buffer", "b2g_halo_unpack", "b2g_debug_tile_state",
 ]
+DIST_SYMBOLS = ["b2g_dist_unique_id", "b2g_dist_init", "b2g_dist_exchange", "b2g_dist_destroy"]
 
 _cuda = None
 _gpu_scenes = None
@@ -137,6 +139,10 @@ def load_cuda():
         lib.b2g_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         lib.b2g_set_inv_dt0.argtypes = [C.c_void_p, C.c_float]
         lib.b2g_device_views.argtypes = [C.c_void_p, C.POINTER(DeviceViews)]
+        lib.b2g_halo_set_lists.argtypes = [C.c_void_p, C.c_int32, C.c_int32, i32p, C.c_int32, i32p]
+        lib.b2g_halo_pack.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        lib.b2g_halo_recv_buffer.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        lib.b2g_halo_unpack.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         lib.b2g_upload_contacts.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ContactArrays)]
         lib.b2g_set_sequential_order.argtypes = [C.c_void_p, C.c_int32, i32p, i32p]
         lib.b2g_set_sequential_joint_order.argtypes = [C.c_void_p, C.c_int32, i32p]
@@ -197,6 +203,26 @@ def _declare_shim(lib, prefix):
     g("scene_time_ray_casts").argtypes = [C.c_void_p, C.c_int, f32p]
     g("scene_joint_count").argtypes = [C.c_void_p]
     g("scene_get_joints").argtypes = [C.c_void_p, C.c_int, i32p, f32p, f32p]
+
+
+_dist = None
+
+
+def load_dist():
+    """libb2cuda_dist.so: the NCCL transport of the halo exchange (one process per GPU)"""
+    global _dist
+    if _dist is None:
+        load_cuda()
+        p = lib_path("libb2cuda_dist.so")
+        if not os.path.exists(p):
+            raise B2GError(f"{p} is missing: run __graft_entry__.build()")
+        lib = C.CDLL(p)
+        lib.b2g_dist_unique_id.argtypes = [C.c_void_p]
+        lib.b2g_dist_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        lib.b2g_dist_exchange.argtypes = [C.c_void_p, C.c_void_p]
+        lib.b2g_dist_destroy.argtypes = [C.c_void_p]
+        _dist = lib
+    return _dist
 
 
 def load_gpu_scenes():

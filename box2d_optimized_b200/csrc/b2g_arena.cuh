@@ -216,6 +216,13 @@ struct b2gArena {
   int* croot;
   SolverPlanes planes;
 
+  // halo exchange of a spatially decomposed world (slot 0 = lower neighbour, 1 = upper neighbour)
+  int* haloSend[2];    // bodies whose state the neighbour holds as ghosts
+  int* haloRecv[2];    // ghost bodies refreshed from the neighbour
+  int haloNumSend[2], haloNumRecv[2];
+  float4* haloOut[2];  // packed messages: 4 quads per body (pos, vel, xf, flags)
+  float4* haloIn[2];
+
   // events
   int2 *beginEvents, *endEvents;
 

@@ -395,6 +395,12 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->planes.m2, A->planes.kk, A->planes.mass, A->planes.idx, A->planes.imp, A->planes.pn,
                   A->planes.pp, A->planes.pc, A->planes.pr, A->beginEvents, A->endEvents, A->dCounts, A->bigBarrier, A->colourBarrier, A->tilePlan, A->tileStripOfX, A->tileHistX, A->tileRowOfY, A->tileHistY, A->tileSlot, A->spillList, A->tileBodies, A->tileBoundary, A->tileCount, A->tileBarrier, A->tileCutSeq, A->cubTemp};
   for (void* p : ptrs) cudaFree(p);
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(A->haloSend[k]);
+    cudaFree(A->haloRecv[k]);
+    cudaFree(A->haloOut[k]);
+    cudaFree(A->haloIn[k]);
+  }
   free_contact_buf(A->cb[0]);
   free(A->downloadSlots);
   cudaFreeHost(A->hCounts);
@@ -2014,6 +2020,95 @@ extern "C" int b2g_device_views(b2gArena* A, b2gDeviceViews* out) {
   out->flags = A->bflags;
   out->capacity = A->capBodies;
   out->device = A->device;
+  return B2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halo exchange of a spatially decomposed world (BASELINE config 5).  The transport (NCCL in
+// libb2cuda_dist.so, or a device-to-device copy in the single-process emulation) moves opaque messages; what
+// is in them is decided here: 4 quads per body — pos, vel, xf, (flags, 0, 0, 0) — gathered and scattered by two
+// kernels on the arena's stream, so an exchange needs no host synchronisation at all.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_halo_pack(int n, const int* __restrict__ bodies, const float4* __restrict__ pos, const float4* __restrict__ vel,
+                            const float4* __restrict__ xf, const uint32_t* __restrict__ bflags, float4* out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int b = bodies[k];
+  out[4 * k + 0] = pos[b];
+  out[4 * k + 1] = vel[b];
+  out[4 * k + 2] = xf[b];
+  out[4 * k + 3] = make_float4(__uint_as_float(bflags[b]), 0.0f, 0.0f, 0.0f);
+}
+__global__ void k_halo_unpack(int n, const int* __restrict__ bodies, const float4* __restrict__ in, float4* pos, float4* vel,
+                              float4* xf, uint32_t* bflags) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int b = bodies[k];
+  pos[b] = in[4 * k + 0];
+  vel[b] = in[4 * k + 1];
+  xf[b] = in[4 * k + 2];
+  bflags[b] = __float_as_uint(in[4 * k + 3].x);
+}
+extern "C" int b2g_halo_set_lists(b2gArena* A, int32_t slot, int32_t n_send, const int32_t* send_bodies, int32_t n_recv,
+                                  const int32_t* recv_bodies) {
+  if (!A || slot < 0 || slot > 1 || n_send < 0 || n_recv < 0 || (n_send > 0 && !send_bodies) || (n_recv > 0 && !recv_bodies))
+    return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  CK(cudaStreamSynchronize(A->stream));
+  cudaFree(A->haloSend[slot]);
+  cudaFree(A->haloRecv[slot]);
+  cudaFree(A->haloOut[slot]);
+  cudaFree(A->haloIn[slot]);
+  A->haloSend[slot] = A->haloRecv[slot] = nullptr;
+  A->haloOut[slot] = A->haloIn[slot] = nullptr;
+  A->haloNumSend[slot] = n_send;
+  A->haloNumRecv[slot] = n_recv;
+  for (int k = 0; k < n_send; ++k)
+    if (send_bodies[k] < 0 || send_bodies[k] >= A->capBodies) return B2G_ERR_INVALID;
+  for (int k = 0; k < n_recv; ++k)
+    if (recv_bodies[k] < 0 || recv_bodies[k] >= A->capBodies) return B2G_ERR_INVALID;
+  if (n_send > 0) {
+    CK(dalloc(&A->haloSend[slot], n_send));
+    CK(dalloc(&A->haloOut[slot], (size_t)n_send * 4));
+    CK(cudaMemcpy(A->haloSend[slot], send_bodies, sizeof(int) * (size_t)n_send, cudaMemcpyHostToDevice));
+  }
+  if (n_recv > 0) {
+    CK(dalloc(&A->haloRecv[slot], n_recv));
+    CK(dalloc(&A->haloIn[slot], (size_t)n_recv * 4));
+    CK(cudaMemcpy(A->haloRecv[slot], recv_bodies, sizeof(int) * (size_t)n_recv, cudaMemcpyHostToDevice));
+  }
+  CK(cudaDeviceSynchronize());
+  return B2G_OK;
+}
+extern "C" int b2g_halo_pack(b2gArena* A, int32_t slot, void** message, int64_t* bytes) {
+  if (!A || slot < 0 || slot > 1) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  const int n = A->haloNumSend[slot];
+  if (n > 0) {
+    k_halo_pack<<<div_up(n, 128), 128, 0, A->stream>>>(n, A->haloSend[slot], A->pos, A->vel, A->xf, A->bflags, A->haloOut[slot]);
+    CK(cudaGetLastError());
+    A->launches++;
+  }
+  if (message) *message = A->haloOut[slot];
+  if (bytes) *bytes = (int64_t)n * 64;
+  return B2G_OK;
+}
+extern "C" int b2g_halo_recv_buffer(b2gArena* A, int32_t slot, void** message, int64_t* bytes) {
+  if (!A || slot < 0 || slot > 1) return B2G_ERR_INVALID;
+  if (message) *message = A->haloIn[slot];
+  if (bytes) *bytes = (int64_t)A->haloNumRecv[slot] * 64;
+  return B2G_OK;
+}
+extern "C" int b2g_halo_unpack(b2gArena* A, int32_t slot, const void* message) {
+  if (!A || slot < 0 || slot > 1) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  const int n = A->haloNumRecv[slot];
+  if (n > 0) {
+    const float4* src = message ? (const float4*)message : A->haloIn[slot];
+    k_halo_unpack<<<div_up(n, 128), 128, 0, A->stream>>>(n, A->haloRecv[slot], src, A->pos, A->vel, A->xf, A->bflags);
+    CK(cudaGetLastError());
+    A->launches++;
+  }
   return B2G_OK;
 }
 

@@ -124,19 +124,14 @@ class _SceneView:
 
 
 # --------------------------------------------------------------------------------- device side
-class _CudaView:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 class SlabRank:
-    """one rank's arena + halo pack / unpack on the device (torch views of the arena arrays)"""
+    """one rank's arena + its halo lists on the device (b2g_halo_*: pack / unpack are kernels of the C-ABI
+    library on the arena's stream; the transport is libb2cuda_dist.so's NCCL, or — single-process emulation
+    — the neighbour arena's send buffer read in place)"""
 
     def __init__(self, glob, slab, device=0, max_contacts=None):
-        import torch
         from .arena import arena_from_scene
         self.slab = slab
-        self.torch = torch
         local = local_scene(glob, slab)
         self.fix_gid = local["fixtures"]["gid"]          # local fixture -> global fixture
         self.fix_body_gid = glob["fixtures"]["body"]     # global fixture -> global body
@@ -144,34 +139,30 @@ class SlabRank:
         self.body_type = glob["bodies"][:, 11].astype(np.int32)
         self.arena = arena_from_scene(_SceneView(local), max_contacts=max_contacts, device=device)
         self.arena.find_new_contacts()
-        v = self.arena.device_views()
-        dev = torch.device("cuda", device)
-        cap = v.capacity
-        self.t_pos = torch.as_tensor(_CudaView(v.pos, (cap, 4), "<f4"), device=dev)
-        self.t_vel = torch.as_tensor(_CudaView(v.vel, (cap, 4), "<f4"), device=dev)
-        self.t_xf = torch.as_tensor(_CudaView(v.xf, (cap, 4), "<f4"), device=dev)
-        self.t_flags = torch.as_tensor(_CudaView(v.flags, (cap,), "<i4"), device=dev)
-        self.send_idx = {nb: torch.as_tensor(ix, device=dev) for nb, ix in slab.send_local.items()}
-        self.recv_idx = {nb: torch.as_tensor(ix, device=dev) for nb, ix in slab.recv_local.items()}
-        self.recv_buf = {nb: torch.empty((len(ix), 13), dtype=torch.float32, device=dev)
-                         for nb, ix in slab.recv_local.items()}
+        lib = self.arena.lib
+        for nb in (slab.rank - 1, slab.rank + 1):
+            send = np.ascontiguousarray(slab.send_local.get(nb, np.zeros(0, np.int64)), np.int32)
+            recv = np.ascontiguousarray(slab.recv_local.get(nb, np.zeros(0, np.int64)), np.int32)
+            capi.check(lib.b2g_halo_set_lists(self.arena.h, self.slot_of(nb), len(send), capi.ip(send), len(recv),
+                                              capi.ip(recv)), "b2g_halo_set_lists")
+
+    def slot_of(self, nb):
+        """C-ABI slot of neighbour rank nb: 0 = lower-x neighbour, 1 = upper-x neighbour"""
+        return 0 if nb < self.slab.rank else 1
 
     def pack(self, nb):
-        """[n, 13] float32: pos(4) vel(4) xf(4) flags-as-float-bits(1) of the bodies `nb` holds as ghosts"""
-        ix = self.send_idx[nb]
-        t = self.torch
-        return t.cat([self.t_pos[ix], self.t_vel[ix], self.t_xf[ix],
-                      self.t_flags[ix].view(t.float32).unsqueeze(1)], dim=1).contiguous()
+        """enqueues the gather of the state `nb` holds as ghosts; returns (device pointer, bytes)"""
+        import ctypes as C
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        capi.check(self.arena.lib.b2g_halo_pack(self.arena.h, self.slot_of(nb), C.byref(ptr), C.byref(nbytes)), "b2g_halo_pack")
+        return ptr, nbytes.value
 
-    def unpack(self, nb, msg):
-        ix = self.recv_idx[nb]
-        self.t_pos[ix] = msg[:, 0:4]
-        self.t_vel[ix] = msg[:, 4:8]
-        self.t_xf[ix] = msg[:, 8:12]
-        self.t_flags[ix] = msg[:, 12].contiguous().view(self.torch.int32)
+    def unpack(self, nb, message=None):
+        """enqueues the scatter of a message from `nb` (None: the arena's receive buffer) into the ghosts"""
+        capi.check(self.arena.lib.b2g_halo_unpack(self.arena.h, self.slot_of(nb), message), "b2g_halo_unpack")
 
     def halo_bytes(self):
-        return sum(len(ix) * 52 for ix in self.slab.send_local.values())
+        return sum(len(ix) * 64 for ix in self.slab.send_local.values())
 
     def owned_state(self):
         bd = self.arena.download_bodies(what=("pos", "vel", "flags"))
@@ -224,27 +215,52 @@ class SlabRank:
         self.arena.close()
 
 
-def exchange_distributed(sr):
-    """once-per-step halo exchange over NCCL point-to-point (one message per neighbour)"""
-    import torch.distributed as dist
-    ops, outs = [], {}
-    for nb in sr.slab.neighbours:
-        outs[nb] = sr.pack(nb)
-        ops.append(dist.P2POp(dist.isend, outs[nb], nb))
-        ops.append(dist.P2POp(dist.irecv, sr.recv_buf[nb], nb))
-    if ops:
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-    for nb in sr.slab.neighbours:
-        sr.unpack(nb, sr.recv_buf[nb])
+class DistTransport:
+    """libb2cuda_dist.so: an NCCL communicator of its own (the unique id travels over torch.distributed,
+    whatever its backend) for the per-step halo exchange; everything it does is enqueued on the arena's stream"""
+
+    def __init__(self, rank, nranks, device):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.lib = capi.load_dist()
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            capi.check(self.lib.b2g_dist_unique_id(ident), "b2g_dist_unique_id")
+        t = torch.tensor(list(bytes(ident)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.to(torch.device("cuda", device))
+        dist.broadcast(t, 0)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.h = C.c_void_p()
+        capi.check(self.lib.b2g_dist_init(ident, rank, nranks, device, C.byref(self.h)), "b2g_dist_init")
+
+    def exchange(self, sr):
+        capi.check(self.lib.b2g_dist_exchange(self.h, sr.arena.h), "b2g_dist_exchange")
+
+    def close(self):
+        if self.h:
+            self.lib.b2g_dist_destroy(self.h)
+            self.h = None
+
+
+def exchange_distributed(sr, transport):
+    """once-per-step halo exchange: pack, ncclSend / ncclRecv per neighbour, unpack — all on the arena's stream"""
+    transport.exchange(sr)
 
 
 def exchange_in_process(ranks):
-    """single-process emulation (all slabs on one GPU): the same pack / unpack, tensor to tensor"""
+    """single-process emulation (all slabs on one GPU): every slab packs, then every slab scatters its
+    neighbours' send buffers, read in place (the arenas' streams are ordered by a synchronise in between)"""
     msgs = {(sr.slab.rank, nb): sr.pack(nb) for sr in ranks for nb in sr.slab.neighbours}
     for sr in ranks:
+        sr.arena.synchronize()
+    for sr in ranks:
         for nb in sr.slab.neighbours:
-            sr.unpack(nb, msgs[(nb, sr.slab.rank)])
+            ptr, _ = msgs[(nb, sr.slab.rank)]
+            sr.unpack(nb, ptr)
+    for sr in ranks:
+        sr.arena.synchronize()
 
 
 # ------------------------------------------------------------------------------- rebalance

@@ -323,6 +323,38 @@ typedef struct b2gDeviceViews {
 } b2gDeviceViews;
 int b2g_device_views(b2gArena* arena, b2gDeviceViews* out);
 
+/* ---- Halo exchange of a spatially decomposed world (BASELINE config 5: one very large world cut
+ * into x-slabs, one arena per GPU).  Each arena holds the bodies its rank owns plus GHOST copies of the
+ * neighbours' bodies near the cut; after every step the owners' states overwrite the ghosts.  `slot` 0 is the
+ * lower-x neighbour, 1 the upper-x one.  A message is 64 bytes per body (pos, vel, xf, flags) in the order of
+ * the lists; pack / unpack are kernels on the arena's stream, so with a stream-ordered transport (NCCL on
+ * b2g_stream(), see b2g_dist_exchange) an exchange needs no host synchronisation.
+ * Replaces nothing in the reference (it has no multi-device path); the body fields exchanged are the ones
+ * b2Island::Solve writes back (src/dynamics/b2_island.cpp:430-438). */
+int b2g_halo_set_lists(b2gArena* arena, int32_t slot, int32_t n_send, const int32_t* send_bodies, int32_t n_recv,
+                       const int32_t* recv_bodies);
+/* gathers the send list into the arena's send buffer; returns that device buffer */
+int b2g_halo_pack(b2gArena* arena, int32_t slot, void** message, int64_t* bytes);
+/* device buffer the transport should receive the neighbour's message into */
+int b2g_halo_recv_buffer(b2gArena* arena, int32_t slot, void** message, int64_t* bytes);
+/* scatters a received message (NULL = the arena's own receive buffer) into the ghost bodies */
+int b2g_halo_unpack(b2gArena* arena, int32_t slot, const void* message);
+
+/* ---- libb2cuda_dist.so: the NCCL transport of the halo exchange (one process per GPU; links NCCL, so it is a
+ * separate library).  b2g_dist_unique_id on rank 0 -> broadcast the 128 bytes by any means -> b2g_dist_init on
+ * every rank.  b2g_dist_exchange = pack, one ncclSend + ncclRecv per neighbour in one group, unpack, all
+ * enqueued on the arena's stream.  Rank r's neighbours are r - 1 (slot 0) and r + 1 (slot 1). */
+typedef struct b2gDist b2gDist;
+int b2g_dist_unique_id(void* out128);
+int b2g_dist_init(const void* unique_id128, int32_t rank, int32_t nranks, int32_t device, b2gDist** out);
+int b2g_dist_exchange(b2gDist* dist, b2gArena* arena);
+int b2g_dist_destroy(b2gDist* dist);
+
+/* Tests / diagnostics: how an oversize island is currently cut into per-SM tiles (csrc/b2g_tiles.cuh): the plan
+ * (11 words: bounds lo[2] hi[2] as order-preserving uints, body count, strips, rows, x0, 1/dx, y0, 1/dy), the
+ * bodies per tile of the last step (160 ints) and every body's tile slot (tile * 2048 + slot, -1 = none). */
+int b2g_debug_tile_state(b2gArena* arena, uint32_t* plan, int32_t* tile_count, int32_t* tile_slot);
+
 int b2g_synchronize(b2gArena* arena);
 /* cudaStream_t the arena launches on (for external CUDA-event timing). */
 void* b2g_stream(b2gArena* arena);

@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 
 from box2d_optimized_b200 import Arena, GpuScene, arena_from_scene
-from box2d_optimized_b200.slab import (SlabRank, exchange_distributed, gather_records, make_slabs, rebalance_distributed,
+from box2d_optimized_b200.slab import (DistTransport, SlabRank, exchange_distributed, gather_records, make_slabs, rebalance_distributed,
                                        scene_arrays)
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
@@ -29,13 +29,12 @@ glob = scene_arrays(scene)
 x_start = glob["bodies"][:, 4].copy()
 slabs, owner0, cuts0 = make_slabs(glob, world, halo=3.0)
 sr = SlabRank(glob, slabs[rank], device=local)
+transport = DistTransport(rank, world, local)
 P = Arena.params(gravity=(5.0, -10.0))
 arrived, cuts = 0, cuts0
 for k in range(steps):
     sr.arena.step(P, None)
-    torch.cuda.synchronize()
-    exchange_distributed(sr)
-    torch.cuda.synchronize()
+    exchange_distributed(sr, transport)
     if (k + 1) % K == 0 and k + 1 < steps:
         sr, owner, cuts, a = rebalance_distributed(glob, sr, halo=3.0, device=local)
         arrived += a

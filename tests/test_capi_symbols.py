@@ -18,13 +18,17 @@ def declared_symbols():
 
 
 def test_header_and_binding_agree():
-    assert declared_symbols() == sorted(capi.CUDA_SYMBOLS)
+    assert declared_symbols() == sorted(capi.CUDA_SYMBOLS + capi.DIST_SYMBOLS)
 
 
 def test_library_exports_every_declared_symbol():
+    """b2g_dist_* (the NCCL transport of the halo exchange) live in libb2cuda_dist.so, everything else in
+    libb2cuda.so"""
     lib = ctypes.CDLL(capi.lib_path())
+    dist = ctypes.CDLL(capi.lib_path("libb2cuda_dist.so"))
     for name in declared_symbols():
-        assert hasattr(lib, name), f"{name} declared in include/b2cuda.h but not exported"
+        home = dist if name in capi.DIST_SYMBOLS else lib
+        assert hasattr(home, name), f"{name} declared in include/b2cuda.h but not exported"
 
 
 def test_host_library_exports_scene_shim():
