@@ -103,8 +103,43 @@ def build_oracle(force=False):
     return built
 
 
+def build_reference_benchmarks(force=False):
+    """The reference's own benchmark programs, compiled UNCHANGED from where they lie under /root/reference
+    (testbed/benchmarks/single.cpp and benchmarks.h: scenes b1..b14) against (a) this repo's drop-in headers +
+    CUDA library and (b) the reference's headers + its CPU objects (oracle/_ref/obj, the checker).  Plus
+    tests/cpp/bench_suite.cpp, which drives the same unchanged benchmarks.h and prints end states.  Only where
+    /root/reference exists; the binaries (tests/cpp/build/, git-ignored) travel to the GPU box."""
+    import glob
+    ref = "/root/reference"
+    bdir = os.path.join(ref, "testbed", "benchmarks")
+    if not os.path.isdir(bdir):
+        return []
+    out = os.path.join(ROOT, "tests", "cpp", "build")
+    os.makedirs(out, exist_ok=True)
+    gxx = _find("g++", "g++")
+    objs = [o for o in sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "obj", "*", "*.o")))
+            if not o.endswith("ref_harness.o")]
+    suite = os.path.join(ROOT, "tests", "cpp", "bench_suite.cpp")
+    gpu_deps = [os.path.join(HERE, "libb2gpu_scenes.so"), os.path.join(HERE, "libb2cuda.so")]
+    built = []
+    for name, src in (("single", os.path.join(bdir, "single.cpp")), ("bench_suite", suite)):
+        deps = [src, os.path.join(bdir, "benchmarks.h")]
+        exe = os.path.join(out, name + "_gpu")
+        if force or _newer(exe, deps + gpu_deps):
+            _run([gxx, "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + bdir, src, "-L" + HERE,
+                  "-lb2gpu_scenes", "-lb2cuda", "-Wl,-rpath,$ORIGIN/../../../box2d_optimized_b200", "-o", exe])
+        built.append(exe)
+        exe = os.path.join(out, name + "_ref")
+        if objs and (force or _newer(exe, deps + objs[:1])):
+            _run([gxx, "-O2", "-std=c++11", "-I" + os.path.join(ref, "include"), "-I" + bdir, src] + objs + ["-o", exe])
+        if objs:
+            built.append(exe)
+    return built
+
+
 def build_all(force=False):
-    return [build_cuda(force), build_dist(force), build_host(force)] + build_oracle(force)
+    return ([build_cuda(force), build_dist(force), build_host(force)] + build_oracle(force) +
+            build_reference_benchmarks(force))
 
 
 if __name__ == "__main__":

@@ -1163,7 +1163,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         singleMax = e ? atoi(e) : B2G_WL_SINGLE_MAX;
       }
       void* args[] = {&C, &A->cbin, &A->mass, &A->colourMask, &A->bodyBest, &fixBase, &A->activeList, &A->dCounts,
-                      &bb, &cutBin, &A->bucketCount, &A->conVals, &A->colourBarrier, &singleMax};
+                      &bb, &cutBin, &A->bucketCount, &A->conVals, &A->colourBarrier, &singleMax, &A->pos};
       CK(cudaMemsetAsync(A->colourBarrier, 0, sizeof(unsigned int), A->stream));
       ktime_begin(A, KC_COLOUR, nc);
       // cooperative launch for the co-residency of its grid barrier (the long-worklist mode)

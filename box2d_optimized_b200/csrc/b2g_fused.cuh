@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(B2G_WL_THREADS)
 k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __restrict__ mass,
                   unsigned long long* colourMask, unsigned long long* bodyBest, const int* __restrict__ bodyFixBase,
                   const int* __restrict__ worklist, StepCounts* counts, int bigBin, int cutBin, int* bucketCount,
-                  int* rank, unsigned int* barrier, int singleMax) {
+                  int* rank, unsigned int* barrier, int singleMax, const float4* __restrict__ pos) {
   const int n = __ldcg(&counts->worklistCount);
   if (n == 0) return;
   const bool single = n <= singleMax;
@@ -251,6 +251,7 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
   // mode; a longer list is still handled, from memory.)
   struct Entry {
     int i, a, b, bin;
+    int pref;  // preferred colour bit (cut domain), -1 = none
     unsigned long long k56;
     bool movA, movB, open;  // open = still uncoloured
   };
@@ -265,6 +266,23 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
     e.movA = body_movable(mass[bd.x]);
     e.movB = body_movable(mass[bd.y]);
     e.open = true;
+    e.pref = -1;
+    if (e.bin == cutBin && cutBin >= 0) {
+      // Cut constraints are solved in turn order = colour order, and what costs is the DEPTH of that order (one
+      // L2 round trip per turn).  First fit on random priorities needs up to 2 deg - 1 colours; the geometry
+      // knows better: across a straight seam a body meets at most one neighbour per ~30 degrees of direction,
+      // so the undirected direction of the contact (6 sectors of 30 degrees) is tried first and the lowest free
+      // colour only when that one is taken.  Bodies on a seam then carry ~3 cut colours, at corners ~6.
+      const float4 pa = pos[bd.x], pb = pos[bd.y];
+      float dx = pb.x - pa.x, dy = pb.y - pa.y;
+      if (dy < 0.0f || (dy == 0.0f && dx < 0.0f)) {
+        dx = -dx;
+        dy = -dy;
+      }
+      int sector = (int)(atan2f(dy, dx) * (6.0f / 3.14159265f));  // [0, pi) -> 0..5
+      sector = sector < 0 ? 0 : (sector > 5 ? 5 : sector);
+      e.pref = B2G_CUT_DOMAIN_SHIFT + sector;
+    }
     return e;
   };
   constexpr int CACHED = 2;
@@ -300,7 +318,8 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
     const int domain = (e.bin == cutBin && cutBin >= 0) ? 1 : 0;
     const unsigned long long ma = e.movA ? __ldcg(&colourMask[e.a]) : 0ull, mb = e.movB ? __ldcg(&colourMask[e.b]) : 0ull;
     const unsigned long long freeBits = ~(ma | mb) & colour_domain_mask(domain);
-    const int c = __ffsll((long long)freeBits) - 1;  // never empty: checked while the masks were stable
+    int c = __ffsll((long long)freeBits) - 1;  // never empty: checked while the masks were stable
+    if (e.pref >= 0 && ((freeBits >> e.pref) & 1ull)) c = e.pref;
     const unsigned long long bit = 1ull << c;
     if (e.movA) __stcg(&colourMask[e.a], ma | bit);
     if (e.movB) __stcg(&colourMask[e.b], mb | bit);

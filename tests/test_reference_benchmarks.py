@@ -1,0 +1,84 @@
+"""The reference's own benchmark scenes b1..b14 (/root/reference/testbed/benchmarks/benchmarks.h:57-843), compiled
+UNCHANGED against the drop-in headers + CUDA library and run beside the reference's CPU build.
+
+tests/cpp/bench_suite.cpp drives benchmarks.h the way testbed/benchmarks/single.cpp:46-63 does (continuous physics
+off, `simulationSteps` steps) and prints an end-state summary per scene.  tests/golden/reference_benchmarks.txt is
+that output from the reference build (`tests/cpp/build/bench_suite_ref > tests/golden/reference_benchmarks.txt`,
+binaries made by box2d_optimized_b200/build.py:build_reference_benchmarks where /root/reference exists).
+
+The scenes are chaotic (thousands of bodies bouncing off each other and then falling for ever), and the GPU solver
+sweeps contacts in colour order, not in the reference's list order, so the comparison is of distributions: body
+counts exactly, then the centroid, the height quantiles and the extent of the cloud within a fraction of the cloud's
+own size."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "cpp", "build")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_benchmarks.txt")
+
+
+def parse(text):
+    out = {}
+    for line in text.splitlines():
+        m = re.match(r'BENCH b(\d+) "([^"]*)" (.*)', line)
+        if m:
+            d = {k: float(v) for k, v in (kv.split("=") for kv in m.group(3).split())}
+            d["name"] = m.group(2)
+            out[int(m.group(1))] = d
+    return out
+
+
+# fraction of the cloud's size (q90_y - q10_y, at least 1 m) allowed on centroid / quantiles, per scene.
+# b5/b6 ("n^2"): every body starts overlapping every other one, the outcome is an explosion whose details depend
+# on the contact order from the first step on, so only its overall extent is comparable.
+TOL = {1: 0.10, 2: 0.10, 3: 0.15, 4: 0.10, 5: 0.5, 6: 0.5, 7: 0.10, 8: 0.10, 9: 0.10, 10: 0.10, 11: 0.10, 12: 0.15,
+       13: 0.05, 14: 0.10}
+
+
+def compare(ref, gpu, k):
+    r, g = ref[k], gpu[k]
+    assert g["bodies"] == r["bodies"] and g["dynamic"] == r["dynamic"], (k, g, r)
+    size = max(1.0, r["q90_y"] - r["q10_y"])
+    tol = TOL[k] * size
+    worst = 0.0
+    for key in ("mean_y", "med_y", "q10_y", "q90_y", "mean_x"):
+        d = abs(g[key] - r[key])
+        worst = max(worst, d / size)
+        assert d <= tol, f"b{k} {r['name']}: {key} gpu {g[key]} vs reference {r[key]} (allowed {tol:.3f})"
+    return worst
+
+
+def test_golden_file_has_all_fourteen_scenes():
+    ref = parse(open(GOLDEN).read())
+    assert sorted(ref) == list(range(1, 15))
+    assert ref[3]["name"] == "Tumbler" and ref[3]["bodies"] == 1002
+
+
+def test_reference_build_reproduces_the_golden_line():
+    """CPU: the quick scene (b8, 0.35 s) through the reference build equals the committed golden line."""
+    exe = os.path.join(BUILD, "bench_suite_ref")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/build/bench_suite_ref has not been built (needs /root/reference)")
+    got = parse(subprocess.run([exe, "8", "8"], stdout=subprocess.PIPE, text=True, check=True).stdout)
+    ref = parse(open(GOLDEN).read())
+    for key in ("bodies", "dynamic", "awake", "contacts", "mean_x", "mean_y", "min_y", "max_y", "ke"):
+        assert got[8][key] == ref[8][key], key
+
+
+@pytest.mark.gpu
+def test_reference_benchmarks_run_unchanged_on_the_gpu_path():
+    exe = os.path.join(BUILD, "bench_suite_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/build/bench_suite_gpu has not been built (needs /root/reference's benchmarks.h)")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    gpu, ref = parse(r.stdout), parse(open(GOLDEN).read())
+    assert sorted(gpu) == list(range(1, 15)), r.stdout[-2000:]
+    for k in range(1, 15):
+        w = compare(ref, gpu, k)
+        print(f"b{k:<2} {ref[k]['name']:<30} worst centroid/quantile difference {w:.3f} of the cloud size; "
+              f"gpu {gpu[k]['total_ms']:.0f} ms, reference (build container) {ref[k]['total_ms']:.0f} ms")
