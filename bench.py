@@ -118,6 +118,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--no-roofline", action="store_true", help="profiling runs: skip the per-kernel pass")
     ap.add_argument("--cpu-sample-steps", type=int, default=40)
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="profiling runs: cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -378,6 +380,8 @@ def main():
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches = 0
     contacts_seen, constraints_seen, colours_seen, awake_seen, overflow_seen, rounds_seen = [], [], [], [], [], []
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     for k in range(args.steps):
         with torch.cuda.stream(ext):
             flush.zero_()  # evict the step's working set from L2 (outside the timed bracket)
@@ -394,6 +398,8 @@ def main():
         rounds_seen.append(st.colour_rounds)
     A.synchronize()
     torch.cuda.synchronize()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     if rank == 0 and not sampler.samples:
         sampler.sample()
     clocks = sampler.result()

@@ -167,6 +167,12 @@ class Arena:
         capi.check(self.lib.b2g_set_sequential_joint_order(self.h, len(joints), capi.ip(joints)),
                    "b2g_set_sequential_joint_order")
 
+    def joint_colours(self, count):
+        """colour of each joint in the production mode's joint colouring (b2g_debug_joint_colours)"""
+        out = np.zeros(max(count, 1), np.int32)
+        capi.check(self.lib.b2g_debug_joint_colours(self.h, capi.ip(out)), "b2g_debug_joint_colours")
+        return out[:count]
+
     def download_joints(self, count, first=0):
         """accumulated joint impulses [count, 5] = impulse.xy, motor, lower, upper"""
         state = np.zeros((count, 5), np.float32)

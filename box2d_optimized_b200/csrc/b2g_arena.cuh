@@ -177,6 +177,13 @@ struct b2gArena {
   float4* forceStage; // [capBodies] host forces land here in one linear copy, then merge into force.xyz
   float4* stateStage; // [capBodies][2] packed xf+vel for b2g_download_body_state_async (one linear D2H)
   JointWork* jWork;  // per-step scratch
+  // joint colouring of the production mode (k_joint_colour), redone when the joint table or a body's mass changes
+  int* jColour;                     // [capJoints]
+  int* jSorted;                     // [capJoints] joints by colour
+  int* jCstart;                     // [B2G_JOINT_COLOURS + 2]
+  unsigned long long* jBodyMask;    // [capBodies] scratch of the colouring
+  unsigned long long* jBodyBest;    // [capBodies]
+  int jointColourDirty;
 
   // contacts
   ContactBuf cb[1];           // stable slots; nContacts = slot high-water mark, nAlive = live contacts

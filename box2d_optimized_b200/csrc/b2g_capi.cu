@@ -266,6 +266,12 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->jState, nj));
   CK(dalloc(&A->jUpper, nj));
   CK(dalloc(&A->jWork, nj));
+  CK(dalloc(&A->jColour, nj));
+  CK(dalloc(&A->jSorted, nj));
+  CK(dalloc(&A->jCstart, B2G_JOINT_COLOURS + 2));
+  CK(dalloc(&A->jBodyMask, nb));
+  CK(dalloc(&A->jBodyBest, nb));
+  A->jointColourDirty = 1;
   CK(dalloc(&A->stateStage, (size_t)nb * 2));
   CK(dalloc(&A->forceStage, (size_t)nb));
   CK(dalloc(&A->jointOrder, nj));
@@ -387,7 +393,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jParams2, A->jState, A->jUpper, A->jWork, A->stateStage, A->forceStage, A->jointOrder, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jParams2, A->jState, A->jUpper, A->jWork, A->jColour, A->jSorted, A->jCstart, A->jBodyMask, A->jBodyBest, A->stateStage, A->forceStage, A->jointOrder, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->worldFirst, A->worldLast, A->bvhBox, A->bvhKey, A->bvhDone,
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -440,6 +446,7 @@ extern "C" int b2g_upload_bodies(b2gArena* A, int32_t first, int32_t count, cons
   A->aabbAllDirty = 1;
   A->islandsValid = 0;
   if (s->mass || s->flags) A->recolour = 1;
+  if (s->mass) A->jointColourDirty = 1;  // which bodies a joint moves decides which joints may share a colour
   if (s->world) A->fixBaseDirty = 1;
   return B2G_OK;
 }
@@ -528,6 +535,7 @@ extern "C" int b2g_upload_joints(b2gArena* A, int32_t first, int32_t count, cons
     // the joint table changed: contacts between the joined bodies are re-filtered before the next
     // Collide (b2World::CreateJoint flags them, b2_world.cpp:307-323)
     A->jointFilterDirty = 1;
+    A->jointColourDirty = 1;
     A->aabbAllDirty = 1;
     A->newFixtures = 1;
     A->fixBaseDirty = 1;
@@ -558,6 +566,7 @@ extern "C" int b2g_set_counts(b2gArena* A, int32_t nb, int32_t nf, int32_t nj) {
   A->nFixtures = nf;
   if (nj != A->nJoints) {
     A->jointFilterDirty = 1;
+    A->jointColourDirty = 1;
     A->newFixtures = 1;
     A->fixBaseDirty = 1;
   }
@@ -768,6 +777,8 @@ static JointWalk joint_walk(b2gArena* A, int onlyBig) {
   W.bodySlot = A->bodySlot;
   W.order = nullptr;
   W.norder = 0;
+  W.sorted = A->jSorted;
+  W.cstart = A->jCstart;
   return W;
 }
 
@@ -972,6 +983,12 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   const float dtRatio = A->invDt0 * h;
   ContactBuf& C = A->cb[0];
   SolverPlanes& S = A->planes;
+  if (nj > 0 && A->jointColourDirty) {
+    // joints that share no movable body get the same colour and are solved side by side (b2g_fused.cuh)
+    LAUNCH(A, KC_COLOUR, nj, k_joint_colour, 1, B2G_JOINT_COLOUR_THREADS, nj, nb, A->jBodies, A->jParams1, A->mass,
+           A->jBodyMask, A->jBodyBest, A->jColour, A->jSorted, A->jCstart);
+    A->jointColourDirty = 0;
+  }
   // Tile capacity follows the largest island of the previous step (x1.5 + slack): small islands
   // leave shared memory for the constraint planes and a second resident block per SM.  An island
   // that outgrows the cap within one step is simply routed to the big path for that step.
@@ -1196,6 +1213,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     FP.conCap = conCap;
     FP.nj = nj;
     FP.invH = h > 0.0f ? 1.0f / h : 0.0f;
+    FP.jColour = A->jColour;
+    FP.jSorted = A->jSorted;
+    FP.jCstart = A->jCstart;
     if (smem > A->fusedSmemSet) {
       CK(cudaFuncSetAttribute(k_solve_bins_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       A->fusedSmemSet = smem;
@@ -2170,6 +2190,20 @@ extern "C" int b2g_debug_tile_state(b2gArena* A, uint32_t* plan, int32_t* tileCo
   if (plan) CK(cudaMemcpy(plan, A->tilePlan, sizeof(TilePlan), cudaMemcpyDeviceToHost));
   if (tileCount) CK(cudaMemcpy(tileCount, A->tileCount, sizeof(int) * B2G_TILES_MAX, cudaMemcpyDeviceToHost));
   if (tileSlot) CK(cudaMemcpy(tileSlot, A->tileSlot, sizeof(int) * (size_t)A->nBodies, cudaMemcpyDeviceToHost));
+  return B2G_OK;
+}
+// debug / tests: the joint colouring the next production-mode step will use (colour per joint; B2G_JOINT_COLOURS =
+// serial tail).  Runs the colouring first if the joint table changed since the last step.
+extern "C" int b2g_debug_joint_colours(b2gArena* A, int32_t* colour) {
+  if (!A || !colour) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  if (A->nJoints > 0 && A->jointColourDirty) {
+    LAUNCH(A, KC_COLOUR, A->nJoints, k_joint_colour, 1, B2G_JOINT_COLOUR_THREADS, A->nJoints, A->nBodies, A->jBodies,
+           A->jParams1, A->mass, A->jBodyMask, A->jBodyBest, A->jColour, A->jSorted, A->jCstart);
+    A->jointColourDirty = 0;
+  }
+  CK(cudaStreamSynchronize(A->stream));
+  if (A->nJoints > 0) CK(cudaMemcpy(colour, A->jColour, sizeof(int) * (size_t)A->nJoints, cudaMemcpyDeviceToHost));
   return B2G_OK;
 }
 extern "C" int b2g_set_inv_dt0(b2gArena* A, float v) {

@@ -499,8 +499,14 @@ struct FusedParams {
   int conCap;          // constraints whose 13 planes fit in shared memory next to the tile
   int nj;              // joints in the arena
   float invH;
+  const int* jColour;  // [nj] colour of each joint (k_joint_colour); B2G_JOINT_COLOURS = serial tail
+  const int* jSorted;  // [nj] joints by colour
+  const int* jCstart;  // [B2G_JOINT_COLOURS + 2]
 };
 #define B2G_TILE_JOINTS 64
+#define B2G_JOINT_COLOURS 60  // parallel joint colours (k_joint_colour); joints of a hub beyond them are walked serially
+#define B2G_JOINT_COLOUR_THREADS 1024
+#define B2G_TILE_JOINTS_SERIAL 64  // a tile (or the set of oversize islands) with at most this many joints walks them in list order
 #define B2G_PLANES 13
 
 // dynamic shared memory layout for a tile of `cap` bodies
@@ -545,8 +551,10 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
   }
   __shared__ int cstart[B2G_MAX_COLOURS + 3];
   __shared__ int sJoint[B2G_TILE_JOINTS];
+  __shared__ unsigned char sJointCol[B2G_TILE_JOINTS];
   __shared__ int sJointCount;
-  if (tid == 0) sJointCount = 0;
+  __shared__ unsigned long long sJointColours;  // colours present among this tile's joints (bit B2G_JOINT_COLOURS: tail)
+  if (tid == 0) sJointCount = 0, sJointColours = 0ull;
 
   // constraint ranges of this bin, one per colour (+ overflow), from the bucket table
   if (tid <= B2G_MAX_COLOURS + 1) cstart[tid] = P.nc > 0 ? bucketStart[(bin << B2G_COLOUR_BITS) + tid] : 0;
@@ -588,7 +596,8 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
       int sl = sa >= 0 ? sa : sb;
       if (sl >= first && sl < first + nbod) {
         int k = atomicAdd(&sJointCount, 1);
-        if (k < B2G_TILE_JOINTS) sJoint[k] = j;  // more than that: the walks below rescan the joint table
+        if (k < B2G_TILE_JOINTS) sJoint[k] = j;  // more than that: the walks below go through the arena's table
+        atomicOr(&sJointColours, 1ull << P.jColour[j]);
       }
     }
     __syncthreads();
@@ -602,23 +611,49 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
         }
         sJoint[b + 1] = v;
       }
+      for (int a = 0; a < n; ++a) sJointCol[a] = (unsigned char)P.jColour[sJoint[a]];
     }
     __syncthreads();
   }
   const int njTile = P.nj > 0 ? sJointCount : 0;
-  // The tile's joints in joint-index order (the serial walk of b2Island::Solve).  Up to
-  // B2G_TILE_JOINTS of them come from the shared list; a joint-heavy tile (a long chain, a crowd of
-  // ragdolls) falls back to rescanning the joint table, slower but without a capacity.
+  const unsigned long long jointColours = P.nj > 0 ? sJointColours : 0ull;
+  // The tile's joints, colour by colour (k_joint_colour: joints of a colour share no movable body), every thread
+  // of the block taking part, a CTA barrier behind each colour; the joints of a hub beyond the colours follow in
+  // descending index order on one thread (the list walk of b2Island::Solve).  Up to B2G_TILE_JOINTS joints come
+  // from the shared list; a joint-heavy tile (a long chain, a crowd of ragdolls) goes through the arena's
+  // colour-sorted table instead, slower but without a capacity.  Called by ALL threads.
+  auto in_tile = [&](int j) {
+    const int2 bd = J.bodies[j];
+    const int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
+    const int sl = sa >= 0 ? sa : sb;
+    return sl >= first && sl < first + nbod;
+  };
   auto for_tile_joints = [&](auto&& f) {
-    if (njTile <= B2G_TILE_JOINTS) {
-      for (int k = njTile - 1; k >= 0; --k) f(sJoint[k]);
-    } else {
-      for (int j = P.nj - 1; j >= 0; --j) {
-        int2 bd = J.bodies[j];
-        int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
-        int sl = sa >= 0 ? sa : sb;
-        if (sl >= first && sl < first + nbod) f(j);
+    // up to a few dozen joints (ragdolls, a chain, the tumbler's hinge): one thread, descending index — the
+    // order the reference's island DFS finds a chain built root to tip.  A sweep along a chain carries a
+    // correction over its whole length where a two-colour sweep moves it two links per iteration (measured on
+    // a 150-link chain: largest hinge gap 0.075 m coloured, under 0.05 m in list order), and costs ~0.5 us per
+    // joint at this size
+    const bool serial = njTile <= B2G_TILE_JOINTS_SERIAL;
+    const bool listed = njTile <= B2G_TILE_JOINTS;
+    for (unsigned long long m = serial ? 1ull : jointColours; m; m &= m - 1ull) {
+      const int c = __ffsll((long long)m) - 1;
+      const bool one = serial || c == B2G_JOINT_COLOURS;  // one thread, descending index
+      const int k0 = listed ? 0 : P.jCstart[c], n = (listed ? njTile : P.jCstart[c + 1]) - k0;
+      for (int t = one ? (tid == 0 ? 0 : n) : tid; t < n; t += one ? 1 : nt) {
+        int j;
+        bool mine;
+        if (listed) {
+          const int k = one ? n - 1 - t : t;
+          j = sJoint[k];
+          mine = serial || sJointCol[k] == c;
+        } else {
+          j = P.jSorted[k0 + t];  // (the tail of the table is in descending index order already)
+          mine = in_tile(j);
+        }
+        if (mine) f(j);
       }
+      __syncthreads();
     }
   };
   // the (few) non-empty parallel colours of this bin, so the pass loops do not walk all 24
@@ -736,23 +771,18 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
 
   // joints: InitVelocityConstraints incl. their warm start (b2_island.cpp:323-325), after the contacts'
   if (njTile > 0) {
-    if (tid == 0) {
-      for_tile_joints([&](int j) {
-        int2 bd = J.bodies[j];
-        int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
-        joint_init(J, j, sa >= 0 ? sa - first : ~bd.x, sb >= 0 ? sb - first : ~bd.y, posAcc, velAcc, gmass, gcenter,
-                   P.dtRatio, P.warmStarting != 0);
-      });
-    }
-    __syncthreads();
+    for_tile_joints([&](int j) {
+      int2 bd = J.bodies[j];
+      int sa = bodySlot[bd.x], sb = bodySlot[bd.y];
+      joint_init(J, j, sa >= 0 ? sa - first : ~bd.x, sb >= 0 ? sb - first : ~bd.y, posAcc, velAcc, gmass, gcenter,
+                 P.dtRatio, P.warmStarting != 0);
+    });
   }
 
   // ---- phase 3: velocity iterations ---------------------------------------------------------------
   for (int it = 0; it < P.velIters; ++it) {
-    if (njTile > 0) {  // joints first, then contacts (b2_island.cpp:330-338)
-      if (tid == 0) for_tile_joints([&](int j) { joint_solve_velocity(J, j, velAcc, P.h, P.invH); });
-      __syncthreads();
-    }
+    if (njTile > 0)  // joints first, then contacts (b2_island.cpp:330-338)
+      for_tile_joints([&](int j) { joint_solve_velocity(J, j, velAcc, P.h, P.invH); });
     for (int k = 0; k < nUsed; ++k) {
       int s0 = usedS0[k], s1 = usedS1[k];
       for (int s = s0 + tid; s < s1; s += nt) solve_velocity_constraint(S, s, velAcc);
@@ -847,16 +877,13 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     }
     if (njTile > 0) {  // contacts first, then joints (b2_island.cpp:392-401); a joint that is not
                        // okay keeps its island iterating, expressed as a large "penetration"
-      if (tid == 0) {
-        for_tile_joints([&](int j) {
-          JointWork w = J.work[j];
-          int slot = w.ia >= 0 ? w.ia : w.ib;
-          int hd = T.head[slot];
-          if (T.done[hd]) return;
-          if (!joint_solve_position(J, j, posAcc)) atomicMax(&T.pen[hd], __float_as_uint(1.0f));
-        });
-      }
-      __syncthreads();
+      for_tile_joints([&](int j) {
+        const int ia = J.work[j].ia, ib = J.work[j].ib;
+        int slot = ia >= 0 ? ia : ib;
+        int hd = T.head[slot];
+        if (T.done[hd]) return;
+        if (!joint_solve_position(J, j, posAcc)) atomicMax(&T.pen[hd], __float_as_uint(1.0f));
+      });
     }
     // island converged? (contactsOkay && jointsOkay: minSeparation >= -3 slop)
     for (int l = tid; l < nbod; l += nt) {
@@ -944,6 +971,10 @@ struct JointWalk {
   const int* bodySlot;
   const int* order;  // explicit visiting order (b2g_set_sequential_joint_order), nullptr = descending index
   int norder;
+  // production mode: joints sorted by colour (k_joint_colour); cstart[c] .. cstart[c + 1] = colour c,
+  // cstart[B2G_JOINT_COLOURS] .. cstart[B2G_JOINT_COLOURS + 1] = joints beyond the colours (index order)
+  const int* sorted;
+  const int* cstart;
 };
 // k-th joint of the walk
 __device__ __forceinline__ int joint_walk_count(const JointWalk& W) { return W.order ? W.norder : W.nj; }
@@ -990,6 +1021,143 @@ __device__ __forceinline__ void joints_position_global(const JointWalk& W, const
       atomicMax(&islandPen[(size_t)iter * penStride + root], __float_as_uint(1.0f));
   }
 }
+// ---- joint colouring (production mode) -------------------------------------------------------------------------
+// The reference walks an island's joints one after the other (b2_island.cpp:323-338, 392-401).  Like the contacts,
+// joints that share no movable body commute, so the joint table is greedily coloured whenever it (or a body's
+// mass) changes and a colour is then solved by many threads at once: a 4 000-link mobile (the reference's
+// "Big mobile" benchmark, a binary tree of revolute joints) needs 3 colours instead of a 4 000-joint serial walk
+// per iteration.  One block, Jones-Plassmann rounds on hashed priorities: an uncoloured joint that holds the
+// highest priority on both of its movable bodies takes the lowest colour free on both.  A body with more than
+// B2G_JOINT_COLOURS joints (a hub) leaves the rest to the serial tail, walked by one thread in index order.
+__device__ __forceinline__ bool joint_moves_body(uint32_t type, int side, float4 m) {
+  // the mouse joint writes bodyB back unconditionally (b2_mouse_joint.cpp:139-158)
+  return body_movable(m) || (type == B2G_JOINT_MOUSE && side == 1);
+}
+__global__ void __launch_bounds__(B2G_JOINT_COLOUR_THREADS)
+k_joint_colour(int nj, int nb, const int2* __restrict__ jBodies, const float4* __restrict__ jParams1,
+               const float4* __restrict__ mass, unsigned long long* bodyMask, unsigned long long* bodyBest, int* colour,
+               int* sorted, int* cstart) {
+  B2G_PDL_ENTER();
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int sRemaining, sCount[B2G_JOINT_COLOURS + 2], sCursor[B2G_JOINT_COLOURS + 2];
+  for (int b = tid; b < nb; b += nt) bodyMask[b] = 0ull, bodyBest[b] = 0ull;
+  for (int j = tid; j < nj; j += nt) colour[j] = -1;
+  if (tid <= B2G_JOINT_COLOURS + 1) sCount[tid] = 0;
+  __syncthreads();
+  auto prio = [](int j) {
+    unsigned int hsh = (unsigned int)j * 2654435761u;
+    hsh ^= hsh >> 15;
+    hsh *= 2246822519u;
+    hsh ^= hsh >> 13;
+    return ((unsigned long long)hsh << 32) | (unsigned long long)(unsigned int)(j + 1);
+  };
+  for (int round = 0; round < nj + 1; ++round) {
+    if (tid == 0) sRemaining = 0;
+    __syncthreads();
+    for (int j = tid; j < nj; j += nt) {
+      if (colour[j] != -1) continue;
+      const int2 bd = jBodies[j];
+      const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(jParams1[j].y));
+      const unsigned long long pr = prio(j);
+      if (joint_moves_body(type, 0, mass[bd.x])) atomicMax(&bodyBest[bd.x], pr);
+      if (joint_moves_body(type, 1, mass[bd.y])) atomicMax(&bodyBest[bd.y], pr);
+    }
+    __syncthreads();
+    for (int j = tid; j < nj; j += nt) {
+      if (colour[j] != -1) continue;
+      const int2 bd = jBodies[j];
+      const uint32_t type = B2G_JOINT_TYPE(__float_as_uint(jParams1[j].y));
+      const unsigned long long pr = prio(j);
+      const bool mvA = joint_moves_body(type, 0, mass[bd.x]), mvB = joint_moves_body(type, 1, mass[bd.y]) && bd.y != bd.x;
+      if ((mvA && bodyBest[bd.x] != pr) || (mvB && bodyBest[bd.y] != pr)) {
+        sRemaining = 1;
+        continue;
+      }
+      const unsigned long long used = (mvA ? bodyMask[bd.x] : 0ull) | (mvB ? bodyMask[bd.y] : 0ull);
+      const unsigned long long freeBits = ~used & ((1ull << B2G_JOINT_COLOURS) - 1ull);
+      const int c = freeBits ? __ffsll((long long)freeBits) - 1 : B2G_JOINT_COLOURS;
+      colour[j] = c;
+      if (c < B2G_JOINT_COLOURS) {  // the winner is alone on both bodies this round: plain stores
+        if (mvA) bodyMask[bd.x] = bodyMask[bd.x] | (1ull << c);
+        if (mvB) bodyMask[bd.y] = bodyMask[bd.y] | (1ull << c);
+      }
+      atomicAdd(&sCount[c], 1);
+    }
+    __syncthreads();
+    if (!sRemaining) break;
+    for (int j = tid; j < nj; j += nt) {  // the losers' bodies forget this round's winner
+      if (colour[j] != -1) continue;
+      const int2 bd = jBodies[j];
+      bodyBest[bd.x] = 0ull;
+      bodyBest[bd.y] = 0ull;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int run = 0;
+    for (int c = 0; c <= B2G_JOINT_COLOURS; ++c) {
+      cstart[c] = run;
+      sCursor[c] = run;
+      run += sCount[c];
+    }
+    cstart[B2G_JOINT_COLOURS + 1] = run;
+  }
+  __syncthreads();
+  for (int j = tid; j < nj; j += nt) {
+    const int c = colour[j];
+    if (c < B2G_JOINT_COLOURS) sorted[atomicAdd(&sCursor[c], 1)] = j;  // order inside a colour is immaterial
+  }
+  if (tid == 0 && sCount[B2G_JOINT_COLOURS] > 0) {  // serial tail: descending index, like the list walk
+    int k = cstart[B2G_JOINT_COLOURS];
+    for (int j = nj - 1; j >= 0; --j)
+      if (colour[j] == B2G_JOINT_COLOURS) sorted[k++] = j;
+  }
+}
+
+// Colour by colour over the whole grid; `sync` is the caller's grid barrier.  cstart is the same for every
+// thread, so all of them take the same barriers.
+template <class Sync, class F>
+__device__ __forceinline__ void joints_coloured_grid(const JointWalk& W, const JointArraysDev& J, int gtid, int gsize,
+                                                     Sync&& sync, F&& f) {
+  const bool serial = W.nj <= B2G_TILE_JOINTS_SERIAL;  // a handful of joints: list order (descending index), one thread
+  for (int c = serial ? B2G_JOINT_COLOURS : 0; c <= B2G_JOINT_COLOURS; ++c) {
+    const int k0 = serial ? 0 : W.cstart[c], n = (serial ? W.nj : W.cstart[c + 1]) - k0;
+    if (n == 0) continue;
+    const bool one = c == B2G_JOINT_COLOURS;
+    for (int t = one ? (gtid == 0 ? 0 : n) : gtid; t < n; t += one ? 1 : gsize) {
+      const int j = serial ? W.nj - 1 - t : W.sorted[k0 + t];
+      const int s = joint_owner_body(W, J, j);
+      if (s >= 0) f(j, s);
+    }
+    sync();
+  }
+}
+template <class Acc, class Sync>
+__device__ __forceinline__ void joints_init_coloured(const JointWalk& W, const JointArraysDev& J, int gtid, int gsize,
+                                                     Sync&& sync, float4* pos, float4* vel,
+                                                     const float4* __restrict__ mass, const float4* __restrict__ center,
+                                                     float dtRatio, int warm) {
+  joints_coloured_grid(W, J, gtid, gsize, sync, [&](int j, int) {
+    const int2 bd = J.bodies[j];
+    joint_init(J, j, bd.x, bd.y, Acc{pos}, Acc{vel}, mass, center, dtRatio, warm != 0);
+  });
+}
+template <class Acc, class Sync>
+__device__ __forceinline__ void joints_velocity_coloured(const JointWalk& W, const JointArraysDev& J, int gtid, int gsize,
+                                                         Sync&& sync, float4* vel, float h, float invH) {
+  joints_coloured_grid(W, J, gtid, gsize, sync, [&](int j, int) { joint_solve_velocity(J, j, Acc{vel}, h, invH); });
+}
+template <class Acc, class Sync>
+__device__ __forceinline__ void joints_position_coloured(const JointWalk& W, const JointArraysDev& J, int gtid, int gsize,
+                                                         Sync&& sync, float4* pos, uint32_t* islandPen, int penStride,
+                                                         int iter) {
+  joints_coloured_grid(W, J, gtid, gsize, sync, [&](int j, int s) {
+    const int root = W.island[s];
+    if (island_done(islandPen, penStride, iter, root)) return;
+    if (!joint_solve_position(J, j, Acc{pos})) atomicMax(&islandPen[(size_t)iter * penStride + root], __float_as_uint(1.0f));
+  });
+}
+
 __global__ void k_joints_init_seq(JointWalk W, JointArraysDev J, float4* pos, float4* vel, const float4* mass,
                                   const float4* center, float dtRatio, int warm) {
   B2G_PDL_ENTER();
@@ -1274,17 +1442,13 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
 
   if (warmStarting) big_sweep<B2G_BIG_WARM>(Z, G, S, R, velAcc, posAcc, Q, velIters > 0);
   const float invH = h > 0.0f ? 1.0f / h : 0.0f;
-  if (W.nj > 0) {
-    if (gtid == 0) joints_init_global<CoherentBodies>(W, J, pos, vel, mass, center, dtRatio, warmStarting);
+  auto jsync = [&]() {
     grid_arrive(Z.barrier, Z.target);
     grid_wait(Z.barrier, Z.target);
-  }
+  };
+  if (W.nj > 0) joints_init_coloured<CoherentBodies>(W, J, gtid, gsize, jsync, pos, vel, mass, center, dtRatio, warmStarting);
   for (int it = 0; it < velIters; ++it) {
-    if (W.nj > 0) {
-      if (gtid == 0) joints_velocity_global<CoherentBodies>(W, J, vel, h, invH);
-      grid_arrive(Z.barrier, Z.target);
-      grid_wait(Z.barrier, Z.target);
-    }
+    if (W.nj > 0) joints_velocity_coloured<CoherentBodies>(W, J, gtid, gsize, jsync, vel, h, invH);
     big_sweep<B2G_BIG_VELOCITY>(Z, G, S, R, velAcc, posAcc, Q, it + 1 < velIters);
   }
   // store impulses (b2_contact_solver.cpp:641-657)
@@ -1344,10 +1508,6 @@ k_big_solve(BigRanges R, SolverPlanes S, ContactBuf C, float4* vel, float4* pos,
   for (int it = 0; it < posIters; ++it) {
     Q.it = it;
     big_sweep<B2G_BIG_POSITION>(Z, G, S, R, velAcc, posAcc, Q, it + 1 < posIters);
-    if (W.nj > 0) {
-      if (gtid == 0) joints_position_global<CoherentBodies>(W, J, pos, islandPen, penStride, it);
-      grid_arrive(Z.barrier, Z.target);
-      grid_wait(Z.barrier, Z.target);
-    }
+    if (W.nj > 0) joints_position_coloured<CoherentBodies>(W, J, gtid, gsize, jsync, pos, islandPen, penStride, it);
   }
 }

@@ -656,8 +656,7 @@ template <class F>
 __device__ __forceinline__ void tile_joint_phase(TileCtx& X, float4* sm, float4* gl, F&& walk) {
   tile_publish(X, sm, gl);
   tile_grid_sync(X);
-  if (X.gtid == 0) walk();
-  tile_grid_sync(X);
+  walk([&]() { tile_grid_sync(X); });  // colour by colour over the grid, a grid barrier behind each colour
   tile_reload(X, sm, gl);
 }
 
@@ -872,11 +871,16 @@ k_big_tiles(TileArgs A, SolverPlanes S, ContactBuf C, JointWalk W, JointArraysDe
   if (A.warmStarting) tile_sweep<B2G_BIG_WARM>(X, G, S, A, Q, A.velIters > 0);
   TILE_MARK(5);
   if (bigJoints)
-    tile_joint_phase(X, X.vel, A.vel, [&]() { joints_init_global<CoherentBodies>(W, J, A.pos, A.vel, A.mass, A.center, A.dtRatio, A.warmStarting); });
+    tile_joint_phase(X, X.vel, A.vel, [&](auto&& sync) {
+      joints_init_coloured<CoherentBodies>(W, J, X.gtid, X.gsize, sync, A.pos, A.vel, A.mass, A.center, A.dtRatio, A.warmStarting);
+    });
 
   // ---- phase 3: velocity iterations: joints, then contacts (b2_island.cpp:330-338) -----------------------------
   for (int it = 0; it < A.velIters; ++it) {
-    if (bigJoints) tile_joint_phase(X, X.vel, A.vel, [&]() { joints_velocity_global<CoherentBodies>(W, J, A.vel, A.h, A.invH); });
+    if (bigJoints)
+      tile_joint_phase(X, X.vel, A.vel, [&](auto&& sync) {
+        joints_velocity_coloured<CoherentBodies>(W, J, X.gtid, X.gsize, sync, A.vel, A.h, A.invH);
+      });
     tile_sweep<B2G_BIG_VELOCITY>(X, G, S, A, Q, it + 1 < A.velIters);
     TILE_MARK(6 + it);
   }
@@ -952,7 +956,9 @@ k_big_tiles(TileArgs A, SolverPlanes S, ContactBuf C, JointWalk W, JointArraysDe
     tile_sweep<B2G_BIG_POSITION>(X, G, S, A, Q, it + 1 < A.posIters);
     TILE_MARK(32 + it);
     if (bigJoints)
-      tile_joint_phase(X, X.pos, A.pos, [&]() { joints_position_global<CoherentBodies>(W, J, A.pos, A.islandPen, A.penStride, it); });
+      tile_joint_phase(X, X.pos, A.pos, [&](auto&& sync) {
+        joints_position_coloured<CoherentBodies>(W, J, X.gtid, X.gsize, sync, A.pos, A.islandPen, A.penStride, it);
+      });
   }
 
   // ---- phase 7: write back, SynchronizeTransform, sleep (b2_island.cpp:430-483), ClearForces -----------------------

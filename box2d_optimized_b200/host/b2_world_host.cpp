@@ -139,6 +139,7 @@ void b2WorldImpl::ensureArena() {
   def.max_joints = capJoints;
   b2gCheck(b2g_arena_create(&def, &arena), "b2g_arena_create");
   b2g_set_profiling(arena, profiling ? 1 : 0);
+  if (getenv("B2G_KERNEL_TIMING")) b2g_set_kernel_timing(arena, 1);  // diagnostics: table printed by ~b2World
   shapesUploaded = 0;
   bodiesOnDevice = 0;
   bodyDirtyLo = 0;
@@ -584,6 +585,17 @@ b2World::~b2World() {
   for (b2Joint* j : m_impl->joints) delete j;
   for (auto& kv : m_impl->contactPool) delete kv.second;
   for (b2Contact* c : m_impl->graveyard) delete c;
+  if (m_impl->arena && getenv("B2G_KERNEL_TIMING")) {
+    b2g_synchronize(m_impl->arena);
+    fprintf(stderr, "[b2cuda] kernel classes of this world (since its last arena re-creation):\n");
+    for (int c = 0; c < b2g_kernel_class_count(); ++c) {
+      double ms = 0.0, units = 0.0;
+      int64_t launches = 0;
+      if (b2g_get_kernel_timing(m_impl->arena, c, &ms, &launches, &units) == B2G_OK && launches > 0)
+        fprintf(stderr, "[b2cuda]   %-16s %10.2f ms %8lld launches %10.2f us/launch\n", b2g_kernel_class_name(c), ms,
+                (long long)launches, 1000.0 * ms / (double)launches);
+    }
+  }
   if (m_impl->arena) b2g_arena_destroy(m_impl->arena);
   delete m_impl;
 }

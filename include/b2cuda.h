@@ -354,6 +354,11 @@ int b2g_dist_destroy(b2gDist* dist);
  * (11 words: bounds lo[2] hi[2] as order-preserving uints, body count, strips, rows, x0, 1/dx, y0, 1/dy), the
  * bodies per tile of the last step (160 ints) and every body's tile slot (tile * 2048 + slot, -1 = none). */
 int b2g_debug_tile_state(b2gArena* arena, uint32_t* plan, int32_t* tile_count, int32_t* tile_slot);
+/* Tests / diagnostics: colour[num_joints] of the production mode's joint colouring (csrc/b2g_fused.cuh,
+ * k_joint_colour): joints of one colour share no movable body and are solved side by side where the reference
+ * walks the island's joint list (b2_island.cpp:323-338, 392-401); 60 = a hub's joints beyond the colours,
+ * walked by one thread. */
+int b2g_debug_joint_colours(b2gArena* arena, int32_t* colour);
 
 int b2g_synchronize(b2gArena* arena);
 /* cudaStream_t the arena launches on (for external CUDA-event timing). */

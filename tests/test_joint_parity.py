@@ -73,12 +73,42 @@ def test_chain_of_joined_links_follows_the_reference(require_ref, name):
     assert err < (0.25 if name == "chain" else 0.5)
 
 
+@pytest.mark.parametrize("name,size,copies", [("chain", 150, 1), ("tumbler", 60, 6), ("mixed_linked", 400, 1),
+                                              ("cars", 4, 3), ("welds", 6, 1)])
+def test_joint_colouring_is_valid(name, size, copies):
+    """k_joint_colour: joints of one colour share no movable body (the mouse joint's bodyB counts as moved
+    whatever its mass), every joint has a colour, and colours are first-fit (no gap below a used colour)."""
+    from box2d_optimized_b200 import GpuScene, arena_from_scene
+    scene = GpuScene(name, size, 12345 if name.startswith("mixed") else 0)
+    A = arena_from_scene(scene, copies=copies, num_worlds=copies)
+    jn = scene.joints()
+    nj, nb = len(jn["bodies"]), scene.body_count
+    assert nj > 0
+    col = A.joint_colours(nj * copies)
+    inv_mass, inv_i = A.scene_inv
+    movable = np.tile((inv_mass != 0) | (inv_i != 0), copies)
+    bodies = np.concatenate([jn["bodies"] + k * nb for k in range(copies)])
+    A.close()
+    assert col.min() >= 0 and col.max() <= 60
+    used = sorted(set(col.tolist()) - {60})
+    assert used == list(range(len(used))), used
+    seen = set()
+    for j, (a, b) in enumerate(bodies):
+        if col[j] == 60:
+            continue
+        for body in {int(a), int(b)}:
+            if movable[body]:
+                assert (body, int(col[j])) not in seen, f"joint {j}: body {body} already has a joint of colour {col[j]}"
+                seen.add((body, int(col[j])))
+    print(f"{name}: {nj * copies} joints, {len(used)} colours, {int((col == 60).sum())} in the serial tail")
+
+
 def test_long_chain_has_no_joint_capacity(require_ref):
     """150 hinges in ONE island: more joints than the fused kernel's shared joint list holds, so the
-    serial joint walk rescans the joint table, and on the first steps an island that is oversize
-    through joints alone (no contact yet).  Joints are visited in descending index order, which is
-    the order the reference's island DFS discovers a chain built root to tip, so while the chain
-    swings freely the production mode reproduces the reference exactly."""
+    joint passes go through the arena's colour-sorted joint table, and on the first steps an island that
+    is oversize through joints alone (no contact yet).  A chain takes two joint colours (odd and even
+    hinges side by side) where the reference sweeps it tip to root, so the free swing is reproduced to a
+    tolerance, not exactly."""
     from box2d_optimized_b200 import GpuScene
     from oracle.bindings import RefScene
     ref, gpu = RefScene("chain", 150, 0), GpuScene("chain", 150, 0)
@@ -88,16 +118,21 @@ def test_long_chain_has_no_joint_capacity(require_ref):
     err = np.abs(rb[:, 4:6] - gb[:, 4:6]).max()
     print(f"150-link chain after 60 steps: max position difference {err:.4f} m")
     assert np.isfinite(gb).all()
-    assert err < 1e-4
+    assert err < 0.05
     # hinge gaps: the world anchors of consecutive links coincide
     gpu.step(120)
-    gb = gpu.bodies()
-    c, a = gb[1:, 4:6], gb[1:, 6]
-    left = c - 0.5 * np.stack([np.cos(a), np.sin(a)], 1)     # anchor at x - 0.5 in the link frame
-    right = c + 0.5 * np.stack([np.cos(a), np.sin(a)], 1)
-    gap = np.linalg.norm(left[1:] - right[:-1], axis=1).max()
-    print(f"largest hinge gap after 180 steps: {gap:.4f} m")
-    assert gap < 0.05
+    ref.step(120)
+
+    def largest_gap(b):
+        c, a = b[1:, 4:6], b[1:, 6]
+        left = c - 0.5 * np.stack([np.cos(a), np.sin(a)], 1)     # anchor at x - 0.5 in the link frame
+        right = c + 0.5 * np.stack([np.cos(a), np.sin(a)], 1)
+        return np.linalg.norm(left[1:] - right[:-1], axis=1).max()
+    gap, ref_gap = largest_gap(gpu.bodies()), largest_gap(ref.bodies())
+    print(f"largest hinge gap after 180 steps: {gap:.4f} m (reference {ref_gap:.4f} m)")
+    # a two-colour sweep carries a correction two links per iteration, the reference's list order the whole
+    # chain: the coloured chain is a little slacker than the reference's, bounded here
+    assert gap < max(0.1, 2.0 * ref_gap)
 
 
 @pytest.mark.parametrize("name,size,steps,tol,gated", [("springs", 8, 240, 0.05, None),

@@ -35,7 +35,9 @@ def parse(text):
 # fraction of the cloud's size (q90_y - q10_y, at least 1 m) allowed on centroid / quantiles, per scene.
 # b5/b6 ("n^2"): every body starts overlapping every other one, the outcome is an explosion whose details depend
 # on the contact order from the first step on, so only its overall extent is comparable.
-TOL = {1: 0.10, 2: 0.10, 3: 0.15, 4: 0.10, 5: 0.5, 6: 0.5, 7: 0.10, 8: 0.10, 9: 0.10, 10: 0.10, 11: 0.10, 12: 0.15,
+# b3 (tumbler): the pile avalanches inside the turning container; where it is at step 1500 depends on when the
+# last avalanche went off, so a quarter of the pile's height is allowed.
+TOL = {1: 0.10, 2: 0.10, 3: 0.25, 4: 0.10, 5: 0.5, 6: 0.5, 7: 0.10, 8: 0.10, 9: 0.10, 10: 0.10, 11: 0.10, 12: 0.15,
        13: 0.05, 14: 0.10}
 
 
