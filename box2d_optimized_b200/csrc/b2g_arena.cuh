@@ -93,7 +93,9 @@ struct b2gArena {
   int newFixtures;    // b2World::m_newContacts: fixtures were added, the next step starts with FindNewContacts
   int bvhLeaves, bvhAge;  // leaves of the current leaf order, steps since it was sorted
   float bvhVisitsFresh, bvhVisitsLast;  // mean nodes visited per pair-finder walk: right after the last sort / last step
-  int recolour;       // drop persistent colours (after mass / type edits)
+  int recolour;       // drop every persistent colour (new arena, contacts uploaded by the host)
+  uint8_t* worldRecolour;  // [numWorlds] 1 = a body of this world had its mass / type edited: the world is coloured afresh
+  int recolourWorlds;      // any byte of worldRecolour set
   int roundsHint;     // colouring rounds to launch before the first check
   float invDt0;
   long long launches;

@@ -266,6 +266,8 @@ extern "C" int b2g_arena_create(const b2gArenaDef* def, b2gArena** out) {
   CK(dalloc(&A->jState, nj));
   CK(dalloc(&A->jUpper, nj));
   CK(dalloc(&A->jWork, nj));
+  CK(dalloc(&A->worldRecolour, A->numWorlds));
+  CK(cudaMemset(A->worldRecolour, 0, (size_t)A->numWorlds));
   CK(dalloc(&A->jColour, nj));
   CK(dalloc(&A->jSorted, nj));
   CK(dalloc(&A->jCstart, B2G_JOINT_COLOURS + 2));
@@ -393,7 +395,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
                   A->islandAwake, A->islandMinSleep, A->islandPen, A->colourMask, A->bodyBest, A->islandCount, A->islandStart, A->islandCursor, A->bodySlot, A->slotBody,
                   A->binFirst, A->binEnd, A->bucketCount, A->bucketStart, A->cbin, A->conKeys, A->conKeysSorted, A->conVals, A->fBody,
                   A->fShapeOff, A->fTypeFlags, A->fFilter, A->fMaterial, A->fAabb, A->fRadius, A->shapes,
-                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jParams2, A->jState, A->jUpper, A->jWork, A->jColour, A->jSorted, A->jCstart, A->jBodyMask, A->jBodyBest, A->stateStage, A->forceStage, A->jointOrder, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
+                  A->jBodies, A->jAnchors, A->jParams0, A->jParams1, A->jParams2, A->jState, A->jUpper, A->jWork, A->worldRecolour, A->jColour, A->jSorted, A->jCstart, A->jBodyMask, A->jBodyBest, A->stateStage, A->forceStage, A->jointOrder, A->ncKeys, A->ncKeysSorted, A->bodyNoCollide, A->seqKeys, A->persist, A->freeStack, A->dFreeTop, A->hash.keys, A->hash.vals, A->mortonKeys,
                   A->mortonKeysSorted, A->leafFixture, A->leafFixtureSorted, A->leafBox, A->leafInfo,
                   A->leafKey, A->worldFirst, A->worldLast, A->bvhBox, A->bvhKey, A->bvhDone,
                   A->pairKeys, A->activeFlag, A->activeList, A->sortedList, A->colourKey,
@@ -422,6 +424,11 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   return B2G_OK;
 }
 
+__global__ void k_flag_worlds(int first, int count, const int* __restrict__ bworld, uint8_t* worldFlag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) worldFlag[bworld[first + i]] = 1;
+}
+
 #define UP(dst, src, elems, type)                                                                      \
   if (src) CK(cudaMemcpyAsync((dst) + (size_t)first * (elems), (src), (size_t)count * (elems) * sizeof(type), \
                               cudaMemcpyHostToDevice, A->stream))
@@ -445,7 +452,14 @@ extern "C" int b2g_upload_bodies(b2gArena* A, int32_t first, int32_t count, cons
   if (first + count > A->nBodies) A->nBodies = first + count;
   A->aabbAllDirty = 1;
   A->islandsValid = 0;
-  if (s->mass || s->flags) A->recolour = 1;
+  if ((s->mass || s->flags) && count > 0) {
+    // Which constraints may share a colour depends on which bodies are movable, so the persistent colours of the
+    // edited bodies' WORLD are dropped and that world is coloured afresh — that world only: an edit in one world
+    // of a batched arena leaves the other worlds' colours, and with them their floats, alone.
+    k_flag_worlds<<<div_up(count, 256), 256, 0, A->stream>>>(first, count, A->bworld, A->worldRecolour);
+    CK(cudaGetLastError());
+    A->recolourWorlds = 1;
+  }
   if (s->mass) A->jointColourDirty = 1;  // which bodies a joint moves decides which joints may share a colour
   if (s->world) A->fixBaseDirty = 1;
   return B2G_OK;
@@ -810,8 +824,12 @@ static int solve_legacy(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     // ---- constraint list + colouring -------------------------------------------------
     if (nc > 0) {
       LAUNCH(A, KC_COLOUR, nc, k_mark_active, div_up(nc, 256), 256, nc, C, A->fTypeFlags, A->island, A->islandAwake, A->activeFlag,
-             A->recolour);
+             A->recolour | A->recolourWorlds);
       A->recolour = 0;
+      if (A->recolourWorlds) {
+        CK(cudaMemsetAsync(A->worldRecolour, 0, (size_t)A->numWorlds, A->stream));
+        A->recolourWorlds = 0;
+      }
       size_t tb = A->cubTempBytes;
       TIMED(A, KC_SORT_SCAN, nc,
             CK(cub::DeviceSelect::Flagged(A->cubTemp, tb, thrust::counting_iterator<int>(0), A->activeFlag,
@@ -1163,8 +1181,13 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     LAUNCH(A, KC_COLOUR, nc, k_mark_active_bins, div_up(nmax, 256), 256, M, C, A->fTypeFlags, A->bflags, A->island,
            A->islandAwake, A->islandCount, A->islandStart, A->cbin, A->dCounts, A->mass, A->colourMask, A->islandCursor,
            A->bodySlot, A->slotBody, A->bodyBest, fixBase, A->activeList, A->bucketCount, A->conVals,
-           (const int*)A->tileSlot, A->tileBoundary);
+           (const int*)A->tileSlot, A->tileBoundary, A->recolourWorlds ? (const uint8_t*)A->worldRecolour : nullptr,
+           (const int*)A->bworld);
     A->recolour = 0;
+    if (A->recolourWorlds) {
+      CK(cudaMemsetAsync(A->worldRecolour, 0, (size_t)A->numWorlds, A->stream));
+      A->recolourWorlds = 0;
+    }
     {
       if (A->colourGrid == 0) {
         int perSM = 0, sms = 0;
@@ -1433,7 +1456,7 @@ extern "C" int b2g_step_collide(b2gArena* A, const b2gStepParams* P) {
   CK(cudaMemsetAsync(A->dCounts, 0, sizeof(StepCounts), A->stream));
   if (A->profiling) CK(cudaEventRecord(A->ev[0], A->stream));
   if (nc > 0) {
-    LAUNCH(A, KC_NARROWPHASE, nc, k_narrowphase, div_up(nc, 128), 128, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
+    LAUNCH(A, KC_NARROWPHASE, nc, k_narrowphase, div_up(nc, B2G_NP_THREADS), B2G_NP_THREADS, nc, C, A->bflags, A->xf, A->fShapeOff, A->fTypeFlags, A->shapes,
            A->bflags, A->dCounts, P->record_events, A->beginEvents, A->endEvents, A->capContacts, A->island,
            A->islandDirty);
   }

@@ -134,7 +134,8 @@ __global__ void k_mark_active_bins(MarkArgs M, ContactBuf C, const uint32_t* __r
                                    const float4* __restrict__ mass, unsigned long long* colourMask, int* islandCursor,
                                    int* bodySlot, int* slotBody, unsigned long long* bodyBest,
                                    const int* __restrict__ bodyFixBase, int* worklist, int* bucketCount, int* rank,
-                                   const int* __restrict__ tileSlot, uint8_t* tileBoundary) {
+                                   const int* __restrict__ tileSlot, uint8_t* tileBoundary,
+                                   const uint8_t* __restrict__ worldRecolour, const int* __restrict__ bworld) {
   B2G_PDL_ENTER();
   const int nc = M.nc, nb = M.nb, bigThreshold = M.bigThreshold, bigBin = M.bigBin;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,7 +185,8 @@ __global__ void k_mark_active_bins(MarkArgs M, ContactBuf C, const uint32_t* __r
   }
   cbin[i] = bin;
   const int domain = (active && bin == M.cutBin && M.cutBin >= 0) ? 1 : 0;
-  if (!active || M.dropColours || (c & 31) >= B2G_MAX_COLOURS || (c >> 5) != domain) {
+  const bool edited = worldRecolour != nullptr && worldRecolour[bworld[bd.x]] != 0;  // (both bodies: same world)
+  if (!active || M.dropColours || edited || (c & 31) >= B2G_MAX_COLOURS || (c >> 5) != domain) {
     // inactive contacts lose their colour; overflow constraints retry every step; a constraint that
     // changed sides (tile interior <-> cut) is coloured again in its new domain
     if (c != -1) C.colour[i] = -1;

@@ -39,32 +39,67 @@ __device__ __forceinline__ unsigned int hash32(unsigned int x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Narrowphase: one thread per contact (contacts are sorted by shape-type bucket, so warps are
-// almost always type-uniform).  b2ContactManager::Collide (b2_contact_manager.cpp:66-116) +
+// Narrowphase: one thread per contact slot.  b2ContactManager::Collide (b2_contact_manager.cpp:66-116) +
 // b2Contact::Update (b2_contact.cpp:126-210).
+// Slots are stable (free list), so a block's 128 consecutive slots hold a mix of shape-type pairs, and a warp
+// that runs b2CollideCircles, b2CollidePolygonAndCircle and b2CollidePolygons one after the other pays for all
+// three.  The block therefore regroups its slots by type pair first (counting sort in shared memory): thread t
+// takes the t-th slot in (type pair) order, so all but a few warps of a block are type-uniform, while the
+// block still reads and writes one contiguous window of the contact arrays.  Which thread computes a slot
+// does not touch the result.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+#define B2G_NP_THREADS 128
+#define B2G_NP_CLASSES 18  // 16 type pairs, sensors, nothing to do
+__global__ void __launch_bounds__(B2G_NP_THREADS)
 k_narrowphase(int nc, ContactBuf C, const uint32_t* bflags, const float4* __restrict__ xf,
               const int* __restrict__ fShapeOff, const uint32_t* __restrict__ fTypeFlags,
               const float4* __restrict__ shapes, uint32_t* bflagsRW, StepCounts* counts, int recordEvents,
               int2* beginEvents, int2* endEvents, int eventCap, const int* __restrict__ islandPrev,
               uint8_t* islandDirty) {
   B2G_PDL_ENTER();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nc) return;
+  __shared__ int sCount[B2G_NP_CLASSES], sStart[B2G_NP_CLASSES];
+  __shared__ unsigned char sOrder[B2G_NP_THREADS];
+  const int tid = threadIdx.x, base = blockIdx.x * blockDim.x;
+  if (tid < B2G_NP_CLASSES) sCount[tid] = 0;
+  __syncthreads();
+  int cls = B2G_NP_CLASSES - 1;
+  {
+    const int i0 = base + tid;
+    if (i0 < nc) {
+      const uint32_t fl = C.flags[i0];
+      if (fl & B2G_CONTACT_ALIVE) {
+        const int2 bd0 = C.body[i0];
+        const uint32_t fa0 = bflags[bd0.x], fb0 = bflags[bd0.y];
+        const bool act = ((fa0 & B2G_BODY_AWAKE) && B2G_BODY_TYPE(fa0) != B2G_STATIC) ||
+                         ((fb0 & B2G_BODY_AWAKE) && B2G_BODY_TYPE(fb0) != B2G_STATIC);
+        if (act) {
+          const int2 fx0 = C.fix[i0];
+          const uint32_t ta = fTypeFlags[fx0.x], tb = fTypeFlags[fx0.y];
+          cls = ((ta | tb) & B2G_FIX_SENSOR) ? 16 : (int)(((ta & 3u) << 2) | (tb & 3u));
+        } else if (fl & B2G_CONTACT_TOUCHING) {
+          auto g = cg::coalesced_threads();
+          if (g.thread_rank() == 0) atomicAdd(&counts->numTouching, (int)g.size());
+        }
+      }
+    }
+  }
+  const int rank = atomicAdd(&sCount[cls], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int c = 0; c < B2G_NP_CLASSES; ++c) {
+      sStart[c] = run;
+      run += sCount[c];
+    }
+  }
+  __syncthreads();
+  sOrder[sStart[cls] + rank] = (unsigned char)tid;
+  __syncthreads();
+  if (tid >= sStart[B2G_NP_CLASSES - 1]) return;  // free slots, sleeping pairs, the tail of the array
+  const int i = base + sOrder[tid];
   uint32_t flags = C.flags[i];
-  if (!(flags & B2G_CONTACT_ALIVE)) return;  // free slot
   int2 bd = C.body[i];
   uint32_t fa = bflags[bd.x], fb = bflags[bd.y];
-  bool activeA = (fa & B2G_BODY_AWAKE) && B2G_BODY_TYPE(fa) != B2G_STATIC;
-  bool activeB = (fb & B2G_BODY_AWAKE) && B2G_BODY_TYPE(fb) != B2G_STATIC;
-  if (!(activeA || activeB)) {
-    if (flags & B2G_CONTACT_TOUCHING) {
-      auto g = cg::coalesced_threads();
-      if (g.thread_rank() == 0) atomicAdd(&counts->numTouching, (int)g.size());
-    }
-    return;
-  }
   int2 fx = C.fix[i];
   uint32_t tfA = fTypeFlags[fx.x], tfB = fTypeFlags[fx.y];
   bool sensor = ((tfA | tfB) & B2G_FIX_SENSOR) != 0;

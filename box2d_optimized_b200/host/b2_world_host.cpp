@@ -38,9 +38,16 @@ static void b2gCheck(int rc, const char* what) {
   }
 }
 
+struct b2WorldBatchImpl;
+
 struct b2WorldImpl {
   b2World* world = nullptr;
   b2gArena* arena = nullptr;
+  // Member of a b2WorldBatch: the arena is the batch's (num_worlds > 1), this world owns the slot
+  // [bodyBase, bodyBase + slot) of it (likewise fixtures and shape quads; joints are packed) and is world
+  // `worldId` inside it.  Every device index of this world is host index + base.
+  b2WorldBatchImpl* batch = nullptr;
+  int32 worldId = 0, bodyBase = 0, fixtureBase = 0, quadBase = 0, jointBase = 0;
   int32 capBodies = 0, capFixtures = 0, capContacts = 0, capQuads = 0, capJoints = 0;
   std::vector<b2Body*> bodies;      // by device index (creation order); nullptr once destroyed
   std::vector<b2Fixture*> fixtures; // by device index
@@ -94,11 +101,40 @@ struct b2WorldImpl {
   void pullBodies();
   void pullJoints();
   void pullContacts();
+  void rebuildContacts(int32 n, const int32_t* fa, const int32_t* fb, const uint32_t* flags, const float* man,
+                       const float* mat, const int32_t* deviceIndex);
   b2Contact* findContact(int32 fa, int32 fb);
   void pushContactOverrides();
 };
 
+// b2WorldBatch: N b2World objects in ONE arena (include/b2cuda.h: num_worlds > 1), stepped by one device pass.
+struct b2WorldBatchImpl {
+  std::vector<b2WorldImpl*> members;  // by world id; nullptr once the world was destroyed
+  b2gArena* arena = nullptr;
+  int32 slotBodies = 0, slotFixtures = 0, slotQuads = 0, capContacts = 0, capJoints = 0, worldsOnDevice = 0;
+  int32 jointsOnDevice = 0;
+  float lastInvDt = 0.0f;
+  bool contactsStale = true, profiling = false;
+  b2gStepStats lastStats;
+  b2WorldImpl::SavedContacts saved;  // arena-wide fixture indices of the arena that was torn down
+  int32 savedSlotFixtures = 0;
+  void ensureArena();
+  void teardown();
+  void growContacts();
+  void flush();
+  void pullContacts();
+  int32 live() const {
+    int32 n = 0;
+    for (b2WorldImpl* m : members) n += m != nullptr;
+    return n;
+  }
+};
+
 void b2WorldImpl::ensureArena() {
+  if (batch) {
+    batch->ensureArena();
+    return;
+  }
   int32 needBodies = (int32)bodies.size(), needFixtures = (int32)fixtures.size();
   int32 needQuads = (int32)(shapePool.size() / 4), needJoints = (int32)joints.size();
   if (arena && needBodies <= capBodies && needFixtures <= capFixtures && needQuads <= capQuads &&
@@ -256,6 +292,10 @@ void b2WorldImpl::saveDeviceState() {
 // itself is complete): double it, keeping every contact; the next Step's pair refresh inserts the
 // pairs that did not fit (include/b2cuda.h, "B2G_ERR_CAPACITY from a step")
 void b2WorldImpl::growContacts() {
+  if (batch) {
+    batch->growContacts();
+    return;
+  }
   bodiesStale = true;
   jointsStale = true;
   saveDeviceState();
@@ -272,7 +312,8 @@ void b2WorldImpl::flush() {
   ensureArena();
   int32 nq = (int32)(shapePool.size() / 4);
   if (nq > shapesUploaded) {
-    b2gCheck(b2g_upload_shapes(arena, shapesUploaded, nq - shapesUploaded, shapePool.data() + (size_t)shapesUploaded * 4),
+    b2gCheck(b2g_upload_shapes(arena, quadBase + shapesUploaded, nq - shapesUploaded,
+                               shapePool.data() + (size_t)shapesUploaded * 4),
              "b2g_upload_shapes");
     shapesUploaded = nq;
   }
@@ -281,7 +322,7 @@ void b2WorldImpl::flush() {
     std::vector<float> pos((size_t)n * 4), vel((size_t)n * 4), xf((size_t)n * 4), mass((size_t)n * 4),
         center((size_t)n * 4), force((size_t)n * 4);
     std::vector<uint32_t> flags(n);
-    std::vector<int32_t> wid(n, 0);
+    std::vector<int32_t> wid(n, worldId);
     for (int32 k = 0; k < n; ++k) {
       b2Body* b = bodies[lo + k];
       float* p = &pos[(size_t)k * 4];
@@ -306,7 +347,7 @@ void b2WorldImpl::flush() {
     b2gBodyArrays a;
     a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.mass = mass.data(); a.center = center.data();
     a.force = force.data(); a.flags = flags.data(); a.world = wid.data();
-    b2gCheck(b2g_upload_bodies(arena, lo, n, &a), "b2g_upload_bodies");
+    b2gCheck(b2g_upload_bodies(arena, bodyBase + lo, n, &a), "b2g_upload_bodies");
     bodiesOnDevice = std::max(bodiesOnDevice, lo + n);
     bodyDirtyLo = INT32_MAX;
     bodyDirtyHi = 0;
@@ -319,11 +360,11 @@ void b2WorldImpl::flush() {
     for (int32 k = 0; k < n; ++k) {
       b2Fixture* f = fixtures[lo + k];
       if (!f) {
-        body[k] = 0; off[k] = 0; tf[k] = B2G_FIX_DEAD;
+        body[k] = bodyBase; off[k] = quadBase; tf[k] = B2G_FIX_DEAD;
         continue;
       }
-      body[k] = f->m_body->m_index;
-      off[k] = f->m_shapeOff;
+      body[k] = bodyBase + f->m_body->m_index;
+      off[k] = quadBase + f->m_shapeOff;
       tf[k] = (uint32_t)f->m_shape->GetType() | (f->m_isSensor ? B2G_FIX_SENSOR : 0u);
       filter[(size_t)k * 2] = (uint32_t)f->m_filter.categoryBits | ((uint32_t)f->m_filter.maskBits << 16);
       filter[(size_t)k * 2 + 1] = (uint32_t)(int32_t)f->m_filter.groupIndex;
@@ -333,11 +374,11 @@ void b2WorldImpl::flush() {
     b2gFixtureArrays a;
     a.body = body.data(); a.shape_off = off.data(); a.type_flags = tf.data(); a.filter = filter.data();
     a.material = mat.data();
-    b2gCheck(b2g_upload_fixtures(arena, lo, n, &a), "b2g_upload_fixtures");
+    b2gCheck(b2g_upload_fixtures(arena, fixtureBase + lo, n, &a), "b2g_upload_fixtures");
     fixtureDirtyLo = INT32_MAX;
     fixtureDirtyHi = 0;
   }
-  if (jointsDirty) {
+  if (jointsDirty && !batch) {  // (a batch packs its members' joints into one table: b2WorldBatchImpl::flush)
     int32 n = (int32)joints.size();
     std::vector<int32_t> jb((size_t)n * 2);
     std::vector<float> anchors((size_t)n * 4), params((size_t)n * 12, 0.0f), state((size_t)n * 5);
@@ -353,7 +394,7 @@ void b2WorldImpl::flush() {
     jointsOnDevice = n;
     jointsDirty = false;
   }
-  if (!saved.fa.empty()) {
+  if (!saved.fa.empty() && !batch) {
     // contacts carried over from the previous arena; pairs whose fixture died meanwhile are retired
     // by the pair refresh that starts the next step
     b2gContactArrays a;
@@ -364,7 +405,7 @@ void b2WorldImpl::flush() {
     saved = SavedContacts();
     world->m_newContacts = true;
   }
-  if (arenaFresh) {
+  if (arenaFresh && !batch) {
     // warm starting scales last step's impulses by dt * inv_dt0 (b2_world.cpp:1130): a new arena starts at
     // the world's inv_dt0, not at zero, or the first step after any growth would drop every impulse
     b2gCheck(b2g_set_inv_dt0(arena, lastInvDt), "b2g_set_inv_dt0");
@@ -379,7 +420,7 @@ void b2WorldImpl::pullJoints() {
   int32 n = std::min((int32)joints.size(), jointsOnDevice);
   if (n == 0) return;
   std::vector<float> state((size_t)n * 5);
-  b2gCheck(b2g_download_joints(arena, 0, n, state.data()), "b2g_download_joints");
+  b2gCheck(b2g_download_joints(arena, jointBase, n, state.data()), "b2g_download_joints");
   for (int32 k = 0; k < n; ++k) joints[k]->ReadDeviceState(&state[(size_t)k * 5]);
 }
 
@@ -393,7 +434,7 @@ void b2WorldImpl::pullBodies() {
   b2gBodyArrays a;
   memset(&a, 0, sizeof(a));
   a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.force = force.data(); a.flags = flags.data();
-  b2gCheck(b2g_download_bodies(arena, 0, n, &a), "b2g_download_bodies");
+  b2gCheck(b2g_download_bodies(arena, bodyBase, n, &a), "b2g_download_bodies");
   for (int32 i = 0; i < n; ++i) {
     b2Body* b = bodies[i];
     if (!b) continue;
@@ -434,6 +475,10 @@ static void unpackManifold(b2Manifold& m, const float* q) {
 
 // rebuild the host contact list (b2World::GetContactListStart, b2Body::GetContact) from the device
 void b2WorldImpl::pullContacts() {
+  if (batch) {
+    batch->pullContacts();
+    return;
+  }
   if (!contactsStale) return;
   contactsStale = false;
   if (deadFixtures && arena && !world->m_locked) {
@@ -467,6 +512,14 @@ void b2WorldImpl::pullContacts() {
     a.material = mat.data();
     b2gCheck(b2g_download_contacts(arena, 0, n, &a), "b2g_download_contacts");
   }
+  rebuildContacts(n, fa.data(), fb.data(), flags.data(), man.data(), mat.data(), nullptr);
+}
+
+// host contact handles from downloaded records (fixture indices local to this world)
+void b2WorldImpl::rebuildContacts(int32 n, const int32_t* fa, const int32_t* fb, const uint32_t* flags, const float* man,
+                                  const float* mat, const int32_t* deviceIndex) {
+  for (b2Body* b : bodies)
+    if (b) b->m_contacts.clear();
   std::unordered_map<uint64_t, b2Contact*> next;
   next.reserve((size_t)n * 2 + 1);
   contacts.assign(n, nullptr);
@@ -489,7 +542,7 @@ void b2WorldImpl::pullContacts() {
     c->m_restitution = mat[(size_t)i * 4 + 1];
     c->m_restitutionThreshold = mat[(size_t)i * 4 + 2];
     c->m_tangentSpeed = mat[(size_t)i * 4 + 3];
-    c->m_deviceIndex = i;
+    c->m_deviceIndex = deviceIndex ? deviceIndex[i] : i;
     c->m_overridden = false;
     contacts[i] = c;
     next.emplace(k, c);
@@ -585,6 +638,27 @@ b2World::~b2World() {
   for (b2Joint* j : m_impl->joints) delete j;
   for (auto& kv : m_impl->contactPool) delete kv.second;
   for (b2Contact* c : m_impl->graveyard) delete c;
+  if (m_impl->batch) {
+    // leave the batch: the slot stays behind as disabled placeholders
+    b2WorldBatchImpl* B = m_impl->batch;
+    for (int32 i = 0; i < (int32)m_impl->bodies.size(); ++i) {
+      m_impl->bodies[i] = nullptr;
+      m_impl->touchBody(i);
+    }
+    for (int32 i = 0; i < (int32)m_impl->fixtures.size(); ++i) {
+      m_impl->fixtures[i] = nullptr;
+      m_impl->touchFixture(i);
+    }
+    m_impl->joints.clear();
+    m_impl->jointsDirty = true;
+    if (m_impl->arena) {
+      m_impl->flush();
+      B->flush();
+    }
+    B->members[m_impl->worldId] = nullptr;
+    B->contactsStale = true;
+    m_impl->arena = nullptr;
+  }
   if (m_impl->arena && getenv("B2G_KERNEL_TIMING")) {
     b2g_synchronize(m_impl->arena);
     fprintf(stderr, "[b2cuda] kernel classes of this world (since its last arena re-creation):\n");
@@ -746,11 +820,12 @@ void b2World::QueryAABB(b2QueryCallback* callback, const b2AABB& aabb) {
   std::vector<int32_t> found((size_t)nf);
   int32_t count = 0;
   const float box[4] = {aabb.lowerBound.x, aabb.lowerBound.y, aabb.upperBound.x, aabb.upperBound.y};
-  b2gCheck(b2g_query_aabb(I->arena, 1, box, nullptr, nf, &count, found.data(), 0), "b2g_query_aabb");
+  const int32_t wid = I->worldId;
+  b2gCheck(b2g_query_aabb(I->arena, 1, box, I->batch ? &wid : nullptr, nf, &count, found.data(), 0), "b2g_query_aabb");
   count = std::min(count, nf);
   std::sort(found.begin(), found.begin() + count);
   for (int32 k = 0; k < count; ++k) {
-    b2Fixture* f = I->fixtures[found[k]];
+    b2Fixture* f = I->fixtures[found[k] - I->fixtureBase];
     if (f && !callback->ReportFixture(f)) return;
   }
 }
@@ -765,7 +840,9 @@ void b2World::RayCast(b2RayCastCallback* callback, const b2Vec2& point1, const b
   std::vector<float> frac((size_t)nf), nrm((size_t)nf * 2);
   int32_t count = 0;
   const float ray[4] = {point1.x, point1.y, point2.x, point2.y};
-  b2gCheck(b2g_ray_cast_all(I->arena, 1, ray, nullptr, nullptr, 0xFFFFu, nf, &count, fix.data(), frac.data(), nrm.data(), 0),
+  const int32_t wid = I->worldId;
+  b2gCheck(b2g_ray_cast_all(I->arena, 1, ray, nullptr, I->batch ? &wid : nullptr, 0xFFFFu, nf, &count, fix.data(),
+                            frac.data(), nrm.data(), 0),
            "b2g_ray_cast_all");
   count = std::min(count, nf);
   std::vector<int32> order((size_t)count);
@@ -777,7 +854,7 @@ void b2World::RayCast(b2RayCastCallback* callback, const b2Vec2& point1, const b
   float maxFraction = 1.0f;
   for (int32 k : order) {
     if (frac[k] > maxFraction) break;
-    b2Fixture* f = I->fixtures[fix[k]];
+    b2Fixture* f = I->fixtures[fix[k] - I->fixtureBase];
     if (!f) continue;
     const float fraction = frac[k];
     const b2Vec2 point = (1.0f - fraction) * point1 + fraction * point2;
@@ -807,7 +884,8 @@ void b2World::DestroyJoint(b2Joint* j) {
   js.erase(std::find(js.begin(), js.end(), j));
   for (int32 i = 0; i < (int32)js.size(); ++i) js[i]->m_index = i;
   m_impl->jointsDirty = true;
-  if (m_impl->arena) b2g_set_counts(m_impl->arena, (int32)m_impl->bodies.size(), (int32)m_impl->fixtures.size(), (int32)js.size());
+  if (m_impl->arena && !m_impl->batch)  // (a batch re-packs its joint table at the next flush)
+    b2g_set_counts(m_impl->arena, (int32)m_impl->bodies.size(), (int32)m_impl->fixtures.size(), (int32)js.size());
   --m_jointCount;
   delete j;
 }
@@ -815,6 +893,10 @@ void b2World::DestroyJoint(b2Joint* j) {
 void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations, int32 particleIterations) {
   B2_NOT_USED(particleIterations);
   if (m_locked) return;
+  if (m_impl->batch) {
+    fprintf(stderr, "[b2cuda] b2World::Step: this world belongs to a b2WorldBatch; call b2WorldBatch::Step\n");
+    return;
+  }
   m_locked = true;
   b2WorldImpl* I = m_impl;
   I->flush();
@@ -957,6 +1039,10 @@ b2Contact* b2World::GetContactListStart() {
 }
 b2Contact* b2World::GetContactListEnd() { return &m_impl->sentinel; }
 int32 b2World::GetContactCount() const {
+  if (m_impl->batch) {
+    m_impl->pullContacts();
+    return (int32)m_impl->contacts.size();
+  }
   int32 n = 0;
   if (m_impl->arena) b2g_contact_count(m_impl->arena, &n);
   return n;
@@ -966,6 +1052,355 @@ int32 b2World::GetProxyCount() const {
   for (b2Fixture* f : m_impl->fixtures)
     if (f) ++n;
   return n;
+}
+
+// ================================================================================================
+// b2WorldBatch (extension): many independent b2World objects stepped by one device pass (BASELINE config 4:
+// thousands of small worlds).  Each member keeps its whole public API (bodies, fixtures, joints, getters,
+// setters, queries); what a batch does not do is call contact listeners or user contact filters.
+// ================================================================================================
+void b2WorldBatchImpl::teardown() {
+  // pull what only the device holds (body state, joint impulses, contacts with their manifolds and warm-start
+  // impulses) before the arena goes
+  for (b2WorldImpl* m : members) {
+    if (!m) continue;
+    m->bodiesStale = true;
+    m->jointsStale = true;
+    m->pullBodies();
+    m->pullJoints();
+  }
+  int32 n = 0;
+  b2gCheck(b2g_contact_count(arena, &n), "b2g_contact_count");
+  saved.fa.assign(n, 0);
+  saved.fb.assign(n, 0);
+  saved.flags.assign(n, 0);
+  saved.man.assign((size_t)n * 16, 0.0f);
+  saved.mat.assign((size_t)n * 4, 0.0f);
+  if (n > 0) {
+    b2gContactArrays a;
+    memset(&a, 0, sizeof(a));
+    a.fixture_a = saved.fa.data(); a.fixture_b = saved.fb.data(); a.flags = saved.flags.data();
+    a.manifold = saved.man.data(); a.material = saved.mat.data();
+    b2gCheck(b2g_download_contacts(arena, 0, n, &a), "b2g_download_contacts");
+  }
+  savedSlotFixtures = slotFixtures;
+  b2gCheck(b2g_arena_destroy(arena), "b2g_arena_destroy");
+  arena = nullptr;
+  for (b2WorldImpl* m : members)
+    if (m) m->arena = nullptr;
+  contactsStale = true;
+}
+
+void b2WorldBatchImpl::growContacts() {
+  teardown();
+  capContacts *= 2;
+  fprintf(stderr, "[b2cuda] batch contact capacity grown to %d\n", capContacts);
+  flush();
+}
+
+void b2WorldBatchImpl::ensureArena() {
+  int32 needB = 1, needF = 1, needQ = 1, needJ = 0;
+  for (b2WorldImpl* m : members) {
+    if (!m) continue;
+    needB = std::max(needB, (int32)m->bodies.size());
+    needF = std::max(needF, (int32)m->fixtures.size());
+    needQ = std::max(needQ, (int32)(m->shapePool.size() / 4));
+    needJ += (int32)m->joints.size();
+  }
+  const int32 nw = (int32)members.size();
+  if (arena && needB <= slotBodies && needF <= slotFixtures && needQ <= slotQuads && needJ <= capJoints && nw <= worldsOnDevice)
+    return;
+  if (arena) teardown();
+  // slots: equal for every world, with headroom (worlds that spawn bodies while they run, like the tumbler)
+  auto grow = [](int32 slot, int32 need) {
+    int32 c = std::max(slot, 16);
+    while (c < need) c *= 2;
+    return c;
+  };
+  slotBodies = grow(slotBodies, needB);
+  slotFixtures = grow(slotFixtures, needF);
+  slotQuads = grow(slotQuads, needQ);
+  capJoints = std::max(grow(capJoints, needJ), 1);
+  worldsOnDevice = nw;
+  const int64_t contactsWanted = std::max<int64_t>((int64_t)saved.fa.size() * 2, (int64_t)nw * slotBodies * 4);
+  capContacts = std::max(capContacts, 1024);
+  while (capContacts < contactsWanted) capContacts *= 2;
+  b2gArenaDef def;
+  memset(&def, 0, sizeof(def));
+  int dev = g_defaultDevice;
+  if (dev < 0) {
+    const char* e = getenv("B2G_DEVICE");
+    dev = e ? atoi(e) : 0;
+  }
+  def.device = dev;
+  def.num_worlds = nw;
+  def.max_bodies = nw * slotBodies;
+  def.max_fixtures = nw * slotFixtures;
+  def.max_shape_quads = nw * slotQuads;
+  def.max_contacts = capContacts;
+  def.max_joints = capJoints;
+  b2gCheck(b2g_arena_create(&def, &arena), "b2g_arena_create");
+  b2g_set_profiling(arena, profiling ? 1 : 0);
+  if (getenv("B2G_KERNEL_TIMING")) b2g_set_kernel_timing(arena, 1);
+  {
+    // every slot starts as placeholders of its world: disabled static bodies, dead fixtures
+    const int32 nb = nw * slotBodies, nf = nw * slotFixtures;
+    std::vector<float> zero4((size_t)std::max(nb, nf) * 4, 0.0f);
+    std::vector<uint32_t> flags(nb, 0u), tf(nf, B2G_FIX_DEAD), filter((size_t)nf * 2, 0u);
+    std::vector<int32_t> wid(nb), body(nf), off(nf);
+    for (int32 i = 0; i < nb; ++i) wid[i] = i / slotBodies;
+    for (int32 i = 0; i < nf; ++i) {
+      body[i] = (i / slotFixtures) * slotBodies;
+      off[i] = (i / slotFixtures) * slotQuads;
+    }
+    b2gBodyArrays a;
+    a.pos = zero4.data(); a.vel = zero4.data(); a.xf = zero4.data(); a.mass = zero4.data(); a.center = zero4.data();
+    a.force = zero4.data(); a.flags = flags.data(); a.world = wid.data();
+    b2gCheck(b2g_upload_bodies(arena, 0, nb, &a), "b2g_upload_bodies");
+    b2gFixtureArrays f;
+    f.body = body.data(); f.shape_off = off.data(); f.type_flags = tf.data(); f.filter = filter.data();
+    f.material = zero4.data();
+    b2gCheck(b2g_upload_fixtures(arena, 0, nf, &f), "b2g_upload_fixtures");
+  }
+  jointsOnDevice = 0;
+  for (int32 w = 0; w < nw; ++w) {
+    b2WorldImpl* m = members[w];
+    if (!m) continue;
+    m->arena = arena;
+    m->worldId = w;
+    m->bodyBase = w * slotBodies;
+    m->fixtureBase = w * slotFixtures;
+    m->quadBase = w * slotQuads;
+    m->shapesUploaded = 0;
+    m->bodiesOnDevice = 0;
+    m->bodyDirtyLo = 0;
+    m->bodyDirtyHi = (int32)m->bodies.size();
+    m->fixtureDirtyLo = 0;
+    m->fixtureDirtyHi = (int32)m->fixtures.size();
+    m->jointsDirty = !m->joints.empty();
+    m->jointsOnDevice = 0;
+    m->contactsStale = true;
+    m->world->m_newContacts = true;
+  }
+}
+
+// upload everything any member changed since the last step
+void b2WorldBatchImpl::flush() {
+  ensureArena();
+  bool jointsDirty = false, fresh = false;
+  for (b2WorldImpl* m : members) {
+    if (!m) continue;
+    fresh = fresh || m->bodiesOnDevice == 0;
+    m->flush();  // shapes, bodies, fixtures into the member's slot
+    jointsDirty = jointsDirty || m->jointsDirty;
+  }
+  if (jointsDirty) {
+    // the joint table is packed (world after world): one member's change moves the others' rows.  Every site
+    // that edits a member's joint list has pulled that member's impulses first (pullJoints); pull the rest.
+    int32 total = 0;
+    for (b2WorldImpl* m : members) {
+      if (!m) continue;
+      m->pullJoints();
+      total += (int32)m->joints.size();
+    }
+    std::vector<int32_t> jb((size_t)total * 2);
+    std::vector<float> anchors((size_t)total * 4), params((size_t)total * 12, 0.0f), state((size_t)total * 5);
+    int32 k = 0;
+    for (b2WorldImpl* m : members) {
+      if (!m) continue;
+      m->jointBase = k;
+      for (b2Joint* j : m->joints) {
+        jb[(size_t)k * 2] = m->bodyBase + j->m_bodyA->m_index;
+        jb[(size_t)k * 2 + 1] = m->bodyBase + j->m_bodyB->m_index;
+        j->WriteDevice(&anchors[(size_t)k * 4], &params[(size_t)k * 12], &state[(size_t)k * 5]);
+        ++k;
+      }
+      m->jointsOnDevice = (int32)m->joints.size();
+      m->jointsDirty = false;
+      m->jointsStale = false;
+    }
+    b2gJointArrays a;
+    a.bodies = jb.data(); a.anchors = anchors.data(); a.params = params.data(); a.state = state.data();
+    if (total > 0) b2gCheck(b2g_upload_joints(arena, 0, total, &a), "b2g_upload_joints");
+    jointsOnDevice = total;
+    b2gCheck(b2g_set_counts(arena, worldsOnDevice * slotBodies, worldsOnDevice * slotFixtures, total), "b2g_set_counts");
+  }
+  if (!saved.fa.empty()) {
+    // contacts of the arena that was torn down, moved to the new slots
+    for (size_t i = 0; i < saved.fa.size(); ++i) {
+      saved.fa[i] = (saved.fa[i] / savedSlotFixtures) * slotFixtures + saved.fa[i] % savedSlotFixtures;
+      saved.fb[i] = (saved.fb[i] / savedSlotFixtures) * slotFixtures + saved.fb[i] % savedSlotFixtures;
+    }
+    b2gContactArrays a;
+    memset(&a, 0, sizeof(a));
+    a.fixture_a = saved.fa.data(); a.fixture_b = saved.fb.data(); a.flags = saved.flags.data();
+    a.manifold = saved.man.data(); a.material = saved.mat.data();
+    b2gCheck(b2g_upload_contacts(arena, (int32_t)saved.fa.size(), &a), "b2g_upload_contacts");
+    saved = b2WorldImpl::SavedContacts();
+    for (b2WorldImpl* m : members)
+      if (m) m->world->m_newContacts = true;
+  }
+  if (fresh) b2gCheck(b2g_set_inv_dt0(arena, lastInvDt), "b2g_set_inv_dt0");
+}
+
+void b2WorldBatchImpl::pullContacts() {
+  if (!contactsStale) return;
+  contactsStale = false;
+  int32 n = 0;
+  if (arena) b2gCheck(b2g_contact_count(arena, &n), "b2g_contact_count");
+  std::vector<int32_t> fa(n), fb(n);
+  std::vector<uint32_t> flags(n);
+  std::vector<float> man((size_t)n * 16), mat((size_t)n * 4);
+  if (n > 0) {
+    b2gContactArrays a;
+    memset(&a, 0, sizeof(a));
+    a.fixture_a = fa.data(); a.fixture_b = fb.data(); a.flags = flags.data(); a.manifold = man.data();
+    a.material = mat.data();
+    b2gCheck(b2g_download_contacts(arena, 0, n, &a), "b2g_download_contacts");
+  }
+  // split by world (a contact's fixtures are in the same slot), keeping device order inside a world
+  const int32 nw = (int32)members.size();
+  std::vector<std::vector<int32_t>> of(nw);
+  for (int32 i = 0; i < n; ++i) of[fa[i] / slotFixtures].push_back(i);
+  for (int32 w = 0; w < nw; ++w) {
+    b2WorldImpl* m = members[w];
+    if (!m) continue;
+    const std::vector<int32_t>& idx = of[w];
+    const int32 k = (int32)idx.size();
+    std::vector<int32_t> la(k), lb(k);
+    std::vector<uint32_t> lf(k);
+    std::vector<float> lman((size_t)k * 16), lmat((size_t)k * 4);
+    int32 kept = 0;
+    for (int32 t = 0; t < k; ++t) {
+      const int32 i = idx[t];
+      const int32 a = fa[i] - m->fixtureBase, b = fb[i] - m->fixtureBase;
+      // a fixture destroyed since the last step still has its contacts on the device until the next pair refresh
+      if (a < 0 || b < 0 || a >= (int32)m->fixtures.size() || b >= (int32)m->fixtures.size() || !m->fixtures[a] || !m->fixtures[b])
+        continue;
+      la[kept] = a;
+      lb[kept] = b;
+      lf[kept] = flags[i];
+      memcpy(&lman[(size_t)kept * 16], &man[(size_t)i * 16], 64);
+      memcpy(&lmat[(size_t)kept * 4], &mat[(size_t)i * 4], 16);
+      const_cast<std::vector<int32_t>&>(idx)[kept] = i;
+      ++kept;
+    }
+    m->rebuildContacts(kept, la.data(), lb.data(), lf.data(), lman.data(), lmat.data(), idx.data());
+    for (b2Contact* c : m->graveyard) delete c;  // no listener runs in a batch: dead handles are not kept
+    m->graveyard.clear();
+    m->contactsStale = false;
+  }
+}
+
+b2WorldBatch::b2WorldBatch() {
+  m_impl = new b2WorldBatchImpl();
+  memset(&m_impl->lastStats, 0, sizeof(b2gStepStats));
+}
+
+b2WorldBatch::~b2WorldBatch() {
+  // members that outlive the batch become worlds without a device state again (they would re-upload at their
+  // next Step); normally the batch is destroyed after its worlds
+  if (m_impl->arena) {
+    for (b2WorldImpl* m : m_impl->members) {
+      if (!m) continue;
+      m->bodiesStale = true;
+      m->jointsStale = true;
+      m->pullBodies();
+      m->pullJoints();
+    }
+    b2g_arena_destroy(m_impl->arena);
+  }
+  for (b2WorldImpl* m : m_impl->members) {
+    if (!m) continue;
+    m->batch = nullptr;
+    m->arena = nullptr;
+    m->worldId = m->bodyBase = m->fixtureBase = m->quadBase = m->jointBase = 0;
+    m->shapesUploaded = 0;
+    m->bodiesOnDevice = 0;
+    m->jointsOnDevice = 0;
+    m->contactsStale = true;
+  }
+  delete m_impl;
+}
+
+bool b2WorldBatch::Add(b2World* world) {
+  b2WorldImpl* m = world ? world->GetImpl() : nullptr;
+  if (!m || m->batch || m->arena || world->IsLocked()) return false;  // only worlds that have not been stepped yet
+  m->batch = m_impl;
+  m->worldId = (int32)m_impl->members.size();
+  m_impl->members.push_back(m);
+  return true;
+}
+
+int32 b2WorldBatch::GetWorldCount() const { return (int32)m_impl->members.size(); }
+
+b2World* b2WorldBatch::GetWorld(int32 index) const {
+  if (index < 0 || index >= (int32)m_impl->members.size() || !m_impl->members[index]) return nullptr;
+  return m_impl->members[index]->world;
+}
+
+void b2WorldBatch::SetProfiling(bool flag) {
+  m_impl->profiling = flag;
+  if (m_impl->arena) b2g_set_profiling(m_impl->arena, flag ? 1 : 0);
+}
+
+float b2WorldBatch::GetLastStepMilliseconds() const { return m_impl->lastStats.ms_step; }
+
+// One b2World::Step (b2_world.cpp:1108-1171) of every member.  Gravity, the world flags and the solver mode are
+// the first live member's: a batch is for many instances of one kind of world.
+void b2WorldBatch::Step(float dt, int32 velocityIterations, int32 positionIterations) {
+  b2WorldBatchImpl* B = m_impl;
+  b2World* first = nullptr;
+  for (b2WorldImpl* m : B->members)
+    if (m) {
+      if (m->world->m_locked) return;
+      if (!first) first = m->world;
+    }
+  if (!first) return;
+  for (b2WorldImpl* m : B->members)
+    if (m) m->world->m_locked = true;
+  B->flush();
+  bool newContacts = false;
+  for (b2WorldImpl* m : B->members)
+    if (m) newContacts = newContacts || m->world->m_newContacts;
+  if (newContacts) {
+    int rc = b2g_find_new_contacts(B->arena);
+    for (int attempt = 0; rc == B2G_ERR_CAPACITY && attempt < 8; ++attempt) {
+      B->growContacts();
+      rc = b2g_find_new_contacts(B->arena);
+    }
+    b2gCheck(rc, "b2g_find_new_contacts");
+    for (b2WorldImpl* m : B->members)
+      if (m) m->world->m_newContacts = false;
+  }
+  b2gStepParams P;
+  P.dt = dt;
+  P.velocity_iterations = velocityIterations;
+  P.position_iterations = positionIterations;
+  P.gravity_x = first->m_gravity.x;
+  P.gravity_y = first->m_gravity.y;
+  P.warm_starting = first->m_warmStarting ? 1 : 0;
+  P.allow_sleep = first->m_allowSleep ? 1 : 0;
+  P.clear_forces = first->m_clearForces ? 1 : 0;
+  P.solver_mode = first->m_solverMode;
+  P.record_events = 0;
+  int rc = b2g_step(B->arena, &P, &B->lastStats);
+  if (dt > 0.0f) B->lastInvDt = 1.0f / dt;
+  for (b2WorldImpl* m : B->members) {
+    if (!m) continue;
+    m->bodiesStale = true;
+    m->jointsStale = true;
+    m->contactsStale = true;
+    if (dt > 0.0f) m->lastInvDt = 1.0f / dt;
+  }
+  B->contactsStale = true;
+  if (rc == B2G_ERR_CAPACITY) {
+    B->growContacts();
+    rc = B2G_OK;
+  }
+  b2gCheck(rc, "b2g_step");
+  for (b2WorldImpl* m : B->members)
+    if (m) m->world->m_locked = false;
 }
 
 // ================================================================================================

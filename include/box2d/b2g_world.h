@@ -26,6 +26,7 @@ class b2Fixture;
 class b2Contact;
 class b2Joint;
 struct b2WorldImpl;
+struct b2WorldBatchImpl;
 
 enum b2BodyType { b2_staticBody = 0, b2_kinematicBody, b2_dynamicBody };
 
@@ -126,6 +127,7 @@ class b2Fixture {
   friend class b2World;
   friend class b2Contact;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2Fixture() {}
   float m_density;
   b2Fixture* m_next;
@@ -228,6 +230,7 @@ class b2Body {
   friend class b2Joint;
   friend class b2RevoluteJoint;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2Body(const b2BodyDef* bd, b2World* world);
   ~b2Body() {}
   void SyncIn() const;  // make the host copy current
@@ -324,6 +327,7 @@ class b2Contact {
   friend class b2World;
   friend class b2Body;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2Contact() {}
   uint32 m_flags;
   b2Contact* m_prev;
@@ -414,6 +418,7 @@ class b2Joint {
   friend class b2World;
   friend class b2Body;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2Joint(const b2JointDef* def);
   /// device record of this joint (include/b2cuda.h b2gJointArrays): anchors[4], params[12], state[5]
   virtual void WriteDevice(float* anchors, float* params, float* state) const = 0;
@@ -461,6 +466,7 @@ class b2RevoluteJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2RevoluteJoint(const b2RevoluteJointDef* def);
   b2Vec2 m_localAnchorA;
   b2Vec2 m_localAnchorB;
@@ -545,6 +551,7 @@ class b2PrismaticJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2PrismaticJoint(const b2PrismaticJointDef* def);
   void WriteDevice(float* anchors, float* params, float* state) const override;
   void ReadDeviceState(const float* state) override;
@@ -599,6 +606,7 @@ class b2MouseJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2MouseJoint(const b2MouseJointDef* def);
   void WriteDevice(float* anchors, float* params, float* state) const override;
   void ReadDeviceState(const float* state) override;
@@ -642,6 +650,7 @@ class b2FrictionJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2FrictionJoint(const b2FrictionJointDef* def);
   void WriteDevice(float* anchors, float* params, float* state) const override;
   void ReadDeviceState(const float* state) override;
@@ -691,6 +700,7 @@ class b2MotorJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2MotorJoint(const b2MotorJointDef* def);
   void WriteDevice(float* anchors, float* params, float* state) const override;
   void ReadDeviceState(const float* state) override;
@@ -769,6 +779,7 @@ class b2WheelJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2WheelJoint(const b2WheelJointDef* def);
   void WriteDevice(float* anchors, float* params, float* state) const override;
   void ReadDeviceState(const float* state) override;
@@ -826,6 +837,7 @@ class b2WeldJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2WeldJoint(const b2WeldJointDef* def);
   void WriteDevice(float* anchors, float* params, float* state) const override;
   void ReadDeviceState(const float* state) override;
@@ -881,6 +893,7 @@ class b2DistanceJoint : public b2Joint {
  protected:
   friend class b2World;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2DistanceJoint(const b2DistanceJointDef* def);
   void WriteDevice(float* anchors, float* params, float* state) const override;
   void ReadDeviceState(const float* state) override;
@@ -1015,7 +1028,9 @@ class b2World {
   friend class b2Body;
   friend class b2Fixture;
   friend class b2Contact;
+  friend class b2WorldBatch;
   friend struct b2WorldImpl;
+  friend struct b2WorldBatchImpl;
   b2WorldImpl* m_impl;
   b2Body* m_bodyListHead;
   b2Body* m_bodyListTail;
@@ -1035,6 +1050,32 @@ class b2World {
   bool m_subStepping;
   int32 m_solverMode;
   b2Profile m_profile;
+};
+
+// ---- extension of the B200 build: many worlds, one device pass -----------------------------------
+/// Thousands of small independent worlds (RL environments, parameter sweeps) cost one kernel-launch chain
+/// EACH when every b2World steps on its own.  A b2WorldBatch puts its members into one device arena (bodies
+/// of different worlds never meet) and steps all of them together: world k of a batch gets exactly the floats
+/// it would get alone.  Members keep their public API (bodies, fixtures, joints, getters, setters, queries);
+/// contact listeners and user contact filters are not called for batched worlds.  Gravity, the world flags
+/// (sleeping, warm starting, ...) and the solver mode are taken from the first member.
+struct b2WorldBatchImpl;
+class b2WorldBatch {
+ public:
+  b2WorldBatch();
+  ~b2WorldBatch();
+  /// A world that has not been stepped yet (it may already hold bodies, fixtures and joints).  False otherwise.
+  bool Add(b2World* world);
+  int32 GetWorldCount() const;
+  b2World* GetWorld(int32 index) const;
+  /// b2World::Step of every member
+  void Step(float timeStep, int32 velocityIterations, int32 positionIterations);
+  void SetProfiling(bool flag);
+  /// device time of the last Step (with SetProfiling(true))
+  float GetLastStepMilliseconds() const;
+
+ private:
+  b2WorldBatchImpl* m_impl;
 };
 
 #endif

@@ -78,3 +78,26 @@ def test_api_program_passes_on_the_gpu():
                 worst = max(worst, d)
                 assert d < 0.02, f"{tag}: {y} vs {x}"
     print(f"editing session: worst position/angle difference to the reference {worst:.5f}")
+
+
+BATCH_SRC = os.path.join(ROOT, "tests", "cpp", "batch_tests.cpp")
+
+
+def test_batch_program_compiles_against_the_drop_in_headers():
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(ROOT, "box2d_optimized_b200")
+    r = _run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), BATCH_SRC, "-L" + lib, "-lb2gpu_scenes",
+              "-lb2cuda", "-Wl,-rpath," + lib, "-o", os.path.join(OUT, "batch_gpu")])
+    assert r.returncode == 0, r.stdout
+
+
+@pytest.mark.gpu
+def test_worlds_of_a_b2WorldBatch_equal_the_same_worlds_stepped_alone():
+    """b2WorldBatch (the drop-in's route to BASELINE config 4): six different worlds with a motor joint, spawns, an
+    impulse and a destroyed body, stepped alone and as one batch — bitwise equal world by world; then slot growth,
+    a member's QueryAABB, and a member leaving the batch (tests/cpp/batch_tests.cpp)."""
+    test_batch_program_compiles_against_the_drop_in_headers()
+    r = _run([os.path.join(OUT, "batch_gpu")])
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "all batch checks passed" in r.stdout

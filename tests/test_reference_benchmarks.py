@@ -37,8 +37,14 @@ def parse(text):
 # on the contact order from the first step on, so only its overall extent is comparable.
 # b3 (tumbler): the pile avalanches inside the turning container; where it is at step 1500 depends on when the
 # last avalanche went off, so a quarter of the pile's height is allowed.
-TOL = {1: 0.10, 2: 0.10, 3: 0.25, 4: 0.10, 5: 0.5, 6: 0.5, 7: 0.10, 8: 0.10, 9: 0.10, 10: 0.10, 11: 0.10, 12: 0.15,
-       13: 0.05, 14: 0.10}
+# b4 ("add pair"): 2 000 circles that start overlapping ~70 neighbours each are blown apart by their own position
+# correction in the first steps; the tails of the cloud (q10, q90) are set by which contacts won those steps.
+TOL = {1: 0.10, 2: 0.10, 3: 0.25, 4: 0.25, 5: 0.5, 6: 0.5, 7: 0.10, 8: 0.10, 9: 0.10, 10: 0.10, 11: 0.10, 12: 0.15,
+       13: 0.05, 14: 0.20}
+# (b14, "partial sleep": boxes shot upwards come down on sleeping stacks and topple some of them; which ones is
+# decided by single collisions.  The bounds are calibrated to let sweep-order noise through — every value seen
+# over four builds is inside them by a factor of ~1.5 — and to catch a broken step: a missed contact class or a
+# body falling through the ground moves these statistics by several cloud sizes.)
 
 
 def compare(ref, gpu, k):
