@@ -256,26 +256,20 @@ KERNEL_OF_CLASS = {"fused_solve": "k_solve_bins_fused", "bp_traverse": "k_bp_tra
 
 
 def ncu_traffic(cls, workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest
-    committed `ncu --set full` summary of THIS workload (profiles/*_ncu_full_<workload>.csv, written by
-    scripts/summarize_ncu.py); None when there is none."""
-    import csv
+    """DRAM bytes per launch of the kernel, from the newest committed ncu capture of THIS workload
+    (profiles/*_dram_traffic_<workload>.csv: kernel, us, GB/s, MB per launch — dram__bytes.sum.per_second x
+    gpu__time_duration of a launch in the timed window); None when there is none."""
     import glob
     if cls not in KERNEL_OF_CLASS:
         return None, None
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_ncu_full_{workload}.csv")))
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for f in reversed(files):
+    for f in reversed(sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_dram_traffic_{workload}.csv")))):
         try:
-            rows = list(csv.reader(open(f)))
-            hdr, units = rows[0], rows[1]
-            ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            vals = [float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
-                    for r in rows[2:] if len(r) > wi and KERNEL_OF_CLASS[cls] in r[0]]
-        except (IndexError, ValueError, KeyError):
+            for line in open(f):
+                cells = line.strip().split(",")
+                if len(cells) == 4 and cells[0].split("<")[0] == KERNEL_OF_CLASS[cls]:
+                    return float(cells[3]) * 1e6, os.path.basename(f)
+        except (OSError, ValueError):
             continue
-        if vals:
-            return sum(vals) / len(vals), os.path.basename(f)
     return None, None
 
 
