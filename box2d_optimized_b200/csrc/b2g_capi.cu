@@ -691,7 +691,12 @@ static int find_new_contacts(b2gArena* A, int recordEvents) {
       A->bvhAge++;
     }
     if (nf > 1) {
-      if (nf < 65536)
+      static int lanesOverride = -1;  // B2G_BP_LANES=1|4 (measurements)
+      if (lanesOverride < 0) {
+        const char* e = getenv("B2G_BP_LANES");
+        lanesOverride = e ? atoi(e) : 0;
+      }
+      if (lanesOverride == 4 || (lanesOverride == 0 && nf < 65536))
         LAUNCH(A, KC_BP_TRAVERSE, nf, k_bp_traverse<4>, div_up(nf * 4, 128), 128, T, A->leafBox, A->leafInfo, A->leafKey,
                A->worldFirst, A->worldLast, A->mortonKeysSorted, A->numWorlds, A->hash, A->persist, A->pairKeys,
                A->capContacts, A->dCounts);
@@ -1066,7 +1071,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   if (A->tileGrid == 0) {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
-    A->tileGrid = sms < B2G_TILES_MAX ? sms : B2G_TILES_MAX;
+    A->tileGrid = sms * B2G_TILES_PER_SM < B2G_TILES_MAX ? sms * B2G_TILES_PER_SM : B2G_TILES_MAX;
   }
   // Only islands beyond the hard cap are tiled: an island that is "oversize" just because the adaptive
   // threshold lags behind its growth (a transient of a step or two) takes the grid-pass kernel, whose
@@ -1202,8 +1207,14 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         const char* e = getenv("B2G_WL_SINGLE_MAX");
         singleMax = e ? atoi(e) : B2G_WL_SINGLE_MAX;
       }
+      static int cutSectors = 0;
+      if (cutSectors == 0) {
+        const char* e = getenv("B2G_CUT_SECTORS");
+        cutSectors = e ? atoi(e) : B2G_CUT_SECTORS;
+        if (cutSectors < 1) cutSectors = 1;
+      }
       void* args[] = {&C, &A->cbin, &A->mass, &A->colourMask, &A->bodyBest, &fixBase, &A->activeList, &A->dCounts,
-                      &bb, &cutBin, &A->bucketCount, &A->conVals, &A->colourBarrier, &singleMax, &A->pos};
+                      &bb, &cutBin, &A->bucketCount, &A->conVals, &A->colourBarrier, &singleMax, &A->pos, &cutSectors};
       CK(cudaMemsetAsync(A->colourBarrier, 0, sizeof(unsigned int), A->stream));
       ktime_begin(A, KC_COLOUR, nc);
       // cooperative launch for the co-residency of its grid barrier (the long-worklist mode)
@@ -1305,8 +1316,8 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
       CK(cudaFuncSetAttribute(k_big_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmemBytes));
       int perSM = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_big_tiles, B2G_TILE_THREADS, tileSmemBytes));
-      if (perSM < 1) {
-        set_err("b2g_step", "k_big_tiles does not fit an SM");
+      if (perSM < B2G_TILES_PER_SM) {
+        set_err("b2g_step", "k_big_tiles: the tiles of an SM do not fit it together");
         return B2G_ERR_CUDA;
       }
       attrSet = true;

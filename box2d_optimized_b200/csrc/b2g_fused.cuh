@@ -227,11 +227,12 @@ __device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int ta
 #define B2G_WL_THREADS 1024
 #define B2G_WL_SINGLE_MAX 2048
 #define B2G_WL_MAX_ROUNDS 200
+#define B2G_CUT_SECTORS 6  // direction classes a cut constraint's preferred colour is drawn from
 __global__ void __launch_bounds__(B2G_WL_THREADS)
 k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __restrict__ mass,
                   unsigned long long* colourMask, unsigned long long* bodyBest, const int* __restrict__ bodyFixBase,
                   const int* __restrict__ worklist, StepCounts* counts, int bigBin, int cutBin, int* bucketCount,
-                  int* rank, unsigned int* barrier, int singleMax, const float4* __restrict__ pos) {
+                  int* rank, unsigned int* barrier, int singleMax, const float4* __restrict__ pos, int cutSectors) {
   const int n = __ldcg(&counts->worklistCount);
   if (n == 0) return;
   const bool single = n <= singleMax;
@@ -281,8 +282,8 @@ k_colour_worklist(ContactBuf C, const int* __restrict__ cbin, const float4* __re
         dx = -dx;
         dy = -dy;
       }
-      int sector = (int)(atan2f(dy, dx) * (6.0f / 3.14159265f));  // [0, pi) -> 0..5
-      sector = sector < 0 ? 0 : (sector > 5 ? 5 : sector);
+      int sector = (int)(atan2f(dy, dx) * ((float)cutSectors / 3.14159265f));  // [0, pi) -> 0 .. cutSectors - 1
+      sector = sector < 0 ? 0 : (sector > cutSectors - 1 ? cutSectors - 1 : sector);
       e.pref = B2G_CUT_DOMAIN_SHIFT + sector;
     }
     return e;

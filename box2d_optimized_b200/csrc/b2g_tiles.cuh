@@ -18,9 +18,12 @@
 #pragma once
 #include "b2g_fused.cuh"
 
-#define B2G_TILES_MAX 160        // >= SM count (one tile per SM)
-#define B2G_TILE_CAP 2048        // bodies a tile can hold in shared memory
-#define B2G_TILE_THREADS 512
+#ifndef B2G_TILES_PER_SM
+#define B2G_TILES_PER_SM 2       // persistent CTAs per SM: two half-size tiles hide each other's barrier / L2 waits
+#endif
+#define B2G_TILES_MAX (160 * B2G_TILES_PER_SM)   // >= SM count x tiles per SM
+#define B2G_TILE_CAP (2048 / B2G_TILES_PER_SM)   // bodies a tile can hold in shared memory
+#define B2G_TILE_THREADS (512 / B2G_TILES_PER_SM)
 #define B2G_TILE_XBINS 4096
 #define B2G_TILE_YBINS 1024
 #define B2G_TILE_MIN_BODIES 128  // do not cut an island into tiles smaller than this
@@ -572,6 +575,7 @@ __device__ __forceinline__ void tile_sweep(TileCtx& X, BigStage& G, const Solver
   if (X.anyCut && X.seqMode) {
     const int q = PHASE == B2G_BIG_POSITION ? X.seqP++ : X.seqV++;
     tile_publish_seq(X, sm, gl, q, false);
+    if (PHASE == B2G_BIG_VELOCITY && q == 5) TILE_MARK(56);  // (trace build) boundary bodies published
     // every cut constraint has its own thread (slot cut[0] + gtid; a second one, + gsize, only beyond ~75 k
     // cut constraints, in slot = colour order), so all colours wait for their turn at the same time and the
     // critical path is the depth of the turn order, not a thread's list
@@ -604,7 +608,9 @@ __device__ __forceinline__ void tile_sweep(TileCtx& X, BigStage& G, const Solver
       }
       if (again && X.nUsed > 0 && X.usedS0[0] + X.tid < X.usedS1[0]) stage_prefetch(G, S, X.usedS0[0] + X.tid, kind);
     }
+    if (PHASE == B2G_BIG_VELOCITY && q == 5) TILE_MARK(57);  // thread 0's cut constraints done
     tile_reload_seq(X, sm, gl, q);
+    if (PHASE == B2G_BIG_VELOCITY && q == 5) TILE_MARK(58);  // boundary bodies back
     if (PHASE == B2G_BIG_POSITION) {
       tile_roots_flush(X, Q);
       tile_grid_sync(X);  // the next iteration's early-exit test reads every tile's penetration
@@ -660,7 +666,7 @@ __device__ __forceinline__ void tile_joint_phase(TileCtx& X, float4* sm, float4*
   tile_reload(X, sm, gl);
 }
 
-__global__ void __launch_bounds__(B2G_TILE_THREADS, 1)
+__global__ void __launch_bounds__(B2G_TILE_THREADS, B2G_TILES_PER_SM)
 k_big_tiles(TileArgs A, SolverPlanes S, ContactBuf C, JointWalk W, JointArraysDev J) {
   extern __shared__ __align__(16) unsigned char tileSmem[];
   __shared__ int cstart[B2G_MAX_COLOURS + 2], cut[B2G_MAX_COLOURS + 2];

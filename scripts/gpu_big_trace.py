@@ -28,10 +28,10 @@ print("interior colour histogram:", np.bincount(act[act < 32], minlength=25).tol
 print("cut colour histogram     :", np.bincount(act[act >= 32] - 32, minlength=25).tolist())
 lib = capi.load_cuda()
 if hasattr(lib, "b2g_debug_tile_marks"):
-    marks = np.zeros((160, 64), np.uint64)
+    marks = np.zeros((320, 64), np.uint64)
     lib.b2g_debug_tile_marks.argtypes = [C.c_void_p]
     if lib.b2g_debug_tile_marks(marks.ctypes.data_as(C.c_void_p)) == 0 and marks[0, 0] > 0:
-        m = marks[:148].astype(np.int64)
+        m = marks[marks[:, 0] > 0].astype(np.int64)
         t0 = m[:, 0].min()
         names = {0: "kernel start", 1: "tile loaded", 2: "barrier 0 passed", 3: "constraints prepared", 4: "serial prepared",
                  5: "warm start done", 31: "positions integrated", 40: "end"}
@@ -41,7 +41,8 @@ if hasattr(lib, "b2g_debug_tile_marks"):
             names[i] = f"position sweep {i - 32} done"
         for i in range(44, 56):
             names[i] = f"  interior of sweep {i - 44} done"
-        order = [0, 1, 2, 3, 4, 44, 5] + [x for it in range(8) for x in (45 + it, 6 + it)] + [31] + [x for it in range(3) for x in (53 + it, 32 + it)] + [40]
+        names.update({56: "    sweep 4: boundary published", 57: "    sweep 4: thread 0's cut constraints done", 58: "    sweep 4: boundary reloaded"})
+        order = [0, 1, 2, 3, 4, 44, 5] + [x for it in range(8) for x in ((45 + it, 56, 57, 58, 6 + it) if it == 4 else (45 + it, 6 + it))] + [31] + [x for it in range(3) for x in (53 + it, 32 + it)] + [40]
         prev = None
         print("phase marks of k_big_tiles, us since the first block started (min / median / max over blocks; delta of medians):")
         for i in order:
@@ -49,7 +50,7 @@ if hasattr(lib, "b2g_debug_tile_marks"):
             if (col <= 0).all():
                 continue
             med = float(np.median(col - t0)) / 1e3
-            print(f"  {names[i]:24s} {float((col - t0).min()) / 1e3:8.2f} {med:8.2f} {float((col - t0).max()) / 1e3:8.2f}   +{(med - prev) if prev is not None else 0.0:7.2f}")
+            print(f"  {names[i]:44s} {float((col - t0).min()) / 1e3:8.2f} {med:8.2f} {float((col - t0).max()) / 1e3:8.2f}   +{(med - prev) if prev is not None else 0.0:7.2f}")
             prev = med
 CAP, B = 1024, 148
 buf = np.zeros((B, CAP, 2), np.uint64)
