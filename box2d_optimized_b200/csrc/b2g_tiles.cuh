@@ -25,9 +25,9 @@
 #define B2G_TILE_CAP (2048 / B2G_TILES_PER_SM)   // bodies a tile can hold in shared memory
 #define B2G_TILE_THREADS (512 / B2G_TILES_PER_SM)
 #define B2G_TILE_XBINS 4096
-#define B2G_TILE_YBINS 1024
+#define B2G_TILE_YBINS 8192        // a pile with stragglers high above it: the rows must still resolve the pile itself
 #define B2G_TILE_MIN_BODIES 128  // do not cut an island into tiles smaller than this
-#define B2G_TILE_PLAN_PERIOD 32  // steps between re-plans (sooner when tiles overflow)
+#define B2G_TILE_PLAN_PERIOD 16  // steps between re-plans (sooner when tiles overflow).  A pile that still grows puts every newcomer above the planned range into the top row: 405 bodies there against 237 elsewhere after 32 steps; balance itself buys little (a tile's sweep time follows its colour count, not its size), headroom against overflow does
 #define B2G_TILE_BODY_BYTES (16 + 16 + 4 + 2 + 1 + 1)  // shared memory per tile body: vel, pos, index, boundary list + degree (+ pad)
 
 struct TilePlan {
@@ -69,7 +69,7 @@ __global__ void k_tile_bounds(int nb, const float4* __restrict__ pos, const uint
 // strips x rows: as many tiles as there are SMs, as square as the pile's aspect ratio allows
 __global__ void k_tile_plan_begin(TilePlan* plan, int maxTiles) {
   B2G_PDL_ENTER();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;  // one warp: the lanes share the candidate strip counts
   const int count = plan->count;
   float x0 = float_unflip(plan->lo[0]), x1 = float_unflip(plan->hi[0]);
   float y0 = float_unflip(plan->lo[1]), y1 = float_unflip(plan->hi[1]);
@@ -82,7 +82,7 @@ __global__ void k_tile_plan_begin(TilePlan* plan, int maxTiles) {
   T = T < 1 ? 1 : (T > maxTiles ? maxTiles : T);
   int bestS = 1, bestR = 1;
   float bestScore = -1e30f;
-  for (int S = 1; S <= T; ++S) {
+  for (int S = 1 + (int)threadIdx.x; S <= T; S += 32) {
     const int R = T / S;
     const float used = (float)(S * R) / (float)T;
     const float aspect = (w / (float)S) / (h / (float)R);
@@ -93,6 +93,16 @@ __global__ void k_tile_plan_begin(TilePlan* plan, int maxTiles) {
       bestR = R;
     }
   }
+  for (int o = 16; o > 0; o >>= 1) {  // best score, the smaller strip count on a tie (what the serial scan kept)
+    const float os = __shfl_xor_sync(0xffffffffu, bestScore, o);
+    const int oS = __shfl_xor_sync(0xffffffffu, bestS, o), oR = __shfl_xor_sync(0xffffffffu, bestR, o);
+    if (os > bestScore || (os == bestScore && oS < bestS)) {
+      bestScore = os;
+      bestS = oS;
+      bestR = oR;
+    }
+  }
+  if (threadIdx.x != 0) return;
   plan->S = bestS;
   plan->R = bestR;
   plan->x0 = x0;
@@ -117,13 +127,13 @@ __global__ void k_tile_xhist(int nb, const float4* __restrict__ pos, const uint3
   if (b >= nb || !tile_is_big_body(b, bflags, island, islandAwake, islandCount, bigThreshold)) return;
   atomicAdd(&histX[tile_xbin(plan, pos[b].x)], 1);
 }
-// exclusive prefix of `n` (<= 4096) counts by one block of 1024 threads; out[k] = min(parts - 1, prefix * parts / total)
+// exclusive prefix of `n` (<= 8192) counts by one block of 1024 threads; out[k] = min(parts - 1, prefix * parts / total)
 __device__ __forceinline__ void tile_partition(const int* __restrict__ hist, int n, int parts, int* out) {
   __shared__ int warpSums[32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int per = (n + 1023) / 1024;  // <= 4
-  int v[4], sum = 0;
-  for (int k = 0; k < 4; ++k) {
+  const int per = (n + 1023) / 1024;  // <= 8
+  int v[8], sum = 0;
+  for (int k = 0; k < 8; ++k) {
     const int i = t * per + k;
     v[k] = (k < per && i < n) ? hist[i] : 0;
     sum += v[k];
@@ -146,7 +156,7 @@ __device__ __forceinline__ void tile_partition(const int* __restrict__ hist, int
   __syncthreads();
   const int total = warpSums[31];
   int prefix = (wid > 0 ? warpSums[wid - 1] : 0) + x - sum;
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 8; ++k) {
     const int i = t * per + k;
     if (k < per && i < n) {
       int p = total > 0 ? (int)(((long long)prefix * parts) / total) : 0;

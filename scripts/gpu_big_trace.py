@@ -52,6 +52,41 @@ if hasattr(lib, "b2g_debug_tile_marks"):
             med = float(np.median(col - t0)) / 1e3
             print(f"  {names[i]:44s} {float((col - t0).min()) / 1e3:8.2f} {med:8.2f} {float((col - t0).max()) / 1e3:8.2f}   +{(med - prev) if prev is not None else 0.0:7.2f}")
             prev = med
+if hasattr(lib, "b2g_debug_tile_marks") and "--tiles" in sys.argv:
+    # per tile: interior time of velocity sweep 4 against what the tile holds
+    nbod = scene.body_count
+    plan = np.zeros(11, np.uint32); tc = np.zeros(320, np.int32); ts = np.zeros(nbod, np.int32)
+    lib.b2g_debug_tile_state.argtypes = [C.c_void_p] * 4
+    lib.b2g_debug_tile_state(A.h, plan.ctypes.data_as(C.c_void_p), tc.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p))
+    ntile = int((marks[:, 0] > 0).sum())
+    cap = int(ts.max()) // ntile + 1
+    cap = 1 << (cap - 1).bit_length()
+    con = A.download_contacts()
+    fx = scene.fixtures()
+    ba, bb = fx["body"][con["fix_a"]], fx["body"][con["fix_b"]]
+    ok = (con["colour"] >= 0) & (con["colour"] < 32)
+    ta = np.where(ts[ba] >= 0, ts[ba] // cap, np.where(ts[bb] >= 0, ts[bb] // cap, -1))
+    m2 = marks[:ntile].astype(np.int64)
+    tin = (m2[:, 49] - m2[:, 9]) / 1e3      # previous sweep done -> interior of sweep 4 done (this block)
+    rows = []
+    for t_ in range(ntile):
+        sel = ok & (ta == t_)
+        cols = con["colour"][sel]
+        hist = np.bincount(cols, minlength=25)
+        rows.append((tin[t_], int(tc[t_]), int(sel.sum()), int((hist > 0).sum()), int(hist.max())))
+    rows = np.array(rows)
+    order = np.argsort(rows[:, 0])
+    print("tile interior time of velocity sweep 4 (us) | bodies | interior constraints | colours used | largest colour")
+    for k in list(order[:5]) + list(order[len(order) // 2 - 2: len(order) // 2 + 3]) + list(order[-8:]):
+        print("  %6.2f | %5d | %5d | %2d | %4d" % tuple(rows[k]))
+    S_, R_ = int(plan[5]), int(plan[6])
+    print("plan: S", S_, "R", R_, "count", int(plan[4]), "bounds x", plan[7:8].view(np.float32), "invDx", plan[8:9].view(np.float32), "y0", plan[9:10].view(np.float32), "invDy", plan[10:11].view(np.float32))
+    grid = tc[:S_ * R_].reshape(S_, R_)
+    print("bodies per strip:", grid.sum(axis=1).tolist())
+    print("strip 0 rows:", grid[0].tolist())
+    print("strip %d rows:" % (S_ // 2), grid[S_ // 2].tolist())
+    print("correlation of interior time with: bodies %.2f, constraints %.2f, colours %.2f, largest colour %.2f" % tuple(
+        np.corrcoef(rows[:, 0], rows[:, j])[0, 1] for j in (1, 2, 3, 4)))
 CAP, B = 1024, 148
 buf = np.zeros((B, CAP, 2), np.uint64)
 lib.b2g_debug_big_trace.argtypes = [C.c_void_p, C.c_int]
