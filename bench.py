@@ -196,7 +196,8 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "window": "pre-roll + warm-up + timed steps (continuous load)"}
 
 
 def window_text(W, warmup, steps):
@@ -342,7 +343,7 @@ def main():
         if slab_mode:
             transport.exchange(A._slab)
 
-    def fresh_arena():
+    def fresh_arena(before_stepping=None):
         """an arena at the start of the timed window: built from the scene(s), perturbed, pre-rolled and warmed
         up — all outside the timed region.  Deterministic: every arena built here reaches the same state."""
         if slab_mode:
@@ -353,6 +354,8 @@ def main():
             A = arena_from_scene(scenes, max_contacts=cap_contacts, device=local_rank, copies=copies, num_worlds=copies)
             perturb(A)
             A.find_new_contacts()
+        if before_stepping is not None:
+            before_stepping()
         for _ in range(W["preroll"] + args.warmup):
             A.step(P, None)
             after_step(A)
@@ -360,7 +363,11 @@ def main():
         return A
 
     # ------------------------------------------------------------------ device-resident value
-    A = fresh_arena()
+    # clocks and throttle reasons are sampled from here on: the pre-roll and warm-up are the same kernels on the same
+    # GPU right before the timed steps, and a 20-step timed region alone (tens of milliseconds) is shorter than one
+    # nvidia-smi query
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
+    A = fresh_arena(before_stepping=sampler.start)
     ext = torch.cuda.ExternalStream(A.stream(), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
     if slab_mode:
@@ -368,8 +375,6 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank, enabled=(rank == 0))
-    sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches = 0
