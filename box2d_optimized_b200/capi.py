@@ -86,7 +86,7 @@ CUDA_SYMBOLS = [
     "b2g_get_kernel_timing", "b2g_device_views", "b2g_upload_contacts", "b2g_set_sequential_order", "b2g_set_sequential_joint_order", "b2g_host_alloc", "b2g_host_free", "b2g_download_new_pairs", "b2g_set_pair_vetoes", "b2g_download_veto_seen", "b2g_query_aabb", "b2g_ray_cast_closest", "b2g_ray_cast_all", "b2g_download_joints", "b2g_rotations", "b2g_compute_aabbs", "b2g_collide_pairs",
     "b2g_find_pairs", "b2g_solve_sequential",
     "b2g_halo_set_lists", "b2g_halo_pack", "b2g_halo_recv_buffer", "b2g_halo_unpack", "b2g_debug_tile_state",
-    "b2g_debug_joint_colours",
+    "b2g_debug_joint_colours", "b2g_upload_bodies_indexed", "b2g_upload_fixtures_indexed", "b2g_upload_shapes_indexed",
 ]
 DIST_SYMBOLS = ["b2g_dist_unique_id", "b2g_dist_init", "b2g_dist_exchange", "b2g_dist_destroy"]
 
@@ -164,6 +164,9 @@ def load_cuda():
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         lib.b2g_download_joints.argtypes = [C.c_void_p, C.c_int32, C.c_int32, f32p]
         lib.b2g_debug_joint_colours.argtypes = [C.c_void_p, i32p]
+        lib.b2g_upload_bodies_indexed.argtypes = [C.c_void_p, C.c_int32, i32p, C.POINTER(BodyArrays)]
+        lib.b2g_upload_fixtures_indexed.argtypes = [C.c_void_p, C.c_int32, i32p, C.POINTER(FixtureArrays)]
+        lib.b2g_upload_shapes_indexed.argtypes = [C.c_void_p, C.c_int32, i32p, f32p]
         lib.b2g_rotations.argtypes = [C.c_int32, C.c_int32, f32p, f32p]
         lib.b2g_compute_aabbs.argtypes = [C.c_int32, C.c_int32, i32p, i32p, f32p, C.c_int32, f32p, f32p]
         lib.b2g_collide_pairs.argtypes = [C.c_int32, C.c_int32, i32p, i32p, f32p, i32p, i32p, f32p, f32p, C.c_int32,

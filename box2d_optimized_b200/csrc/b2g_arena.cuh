@@ -240,4 +240,6 @@ struct b2gArena {
   void* cubTemp;
   size_t cubTempBytes;
   float* hostStage;  // pinned staging for small downloads
+  unsigned char* scatterStage;  // device staging of the indexed uploads (grown on demand)
+  size_t scatterStageBytes;
 };

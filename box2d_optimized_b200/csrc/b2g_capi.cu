@@ -413,6 +413,7 @@ extern "C" int b2g_arena_destroy(b2gArena* A) {
   free(A->downloadSlots);
   cudaFreeHost(A->hCounts);
   cudaFreeHost(A->hostStage);
+  if (A->scatterStage) cudaFree(A->scatterStage);
   for (int i = 0; i < 5; ++i) cudaEventDestroy(A->ev[i]);
   for (int i = 0; i < 2 * B2G_KT_MAX; ++i) cudaEventDestroy(A->ktEv[i]);
   cudaStreamDestroy(A->stream);
@@ -495,6 +496,150 @@ extern "C" int b2g_upload_shapes(b2gArena* A, int32_t first, int32_t count, cons
   CK(cudaSetDevice(A->device));
   UP((float*)A->shapes, quads, 4, float);
   CK(cudaStreamSynchronize(A->stream));
+  A->aabbAllDirty = 1;
+  A->newFixtures = 1;
+  A->fixBaseDirty = 1;
+  return B2G_OK;
+}
+
+// ---- indexed uploads (b2WorldBatch: one edited row in each of many worlds) ------------------------------------
+static int scatter_stage(b2gArena* A, size_t bytes) {
+  if (bytes <= A->scatterStageBytes) return B2G_OK;
+  if (A->scatterStage) {
+    CK(cudaStreamSynchronize(A->stream));
+    CK(cudaFree(A->scatterStage));
+    A->scatterStage = nullptr;
+  }
+  size_t cap = A->scatterStageBytes ? A->scatterStageBytes : 1 << 16;
+  while (cap < bytes) cap *= 2;
+  CK(cudaMalloc((void**)&A->scatterStage, cap));
+  A->scatterStageBytes = cap;
+  return B2G_OK;
+}
+__global__ void k_scatter_bodies(int n, const int* __restrict__ index, const float4* __restrict__ rows, const uint32_t* __restrict__ flags,
+                                 const int* __restrict__ world, float4* pos, float4* vel, float4* xf, float4* mass,
+                                 float4* center, float4* force, uint32_t* bflags, int* bworld, uint8_t* worldFlag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = index[i];
+  pos[b] = rows[i];
+  vel[b] = rows[n + i];
+  xf[b] = rows[2 * n + i];
+  mass[b] = rows[3 * n + i];
+  center[b] = rows[4 * n + i];
+  force[b] = rows[5 * n + i];
+  bflags[b] = flags[i];
+  bworld[b] = world[i];
+  worldFlag[world[i]] = 1;  // mass / type may have changed: this world is coloured afresh (see b2g_upload_bodies)
+}
+__global__ void k_scatter_fixtures(int n, const int* __restrict__ index, const int* __restrict__ body, const int* __restrict__ off,
+                                   const uint32_t* __restrict__ tf, const uint2* __restrict__ filter,
+                                   const float4* __restrict__ material, int* fBody, int* fShapeOff, uint32_t* fTypeFlags,
+                                   uint2* fFilter, float4* fMaterial) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = index[i];
+  fBody[f] = body[i];
+  fShapeOff[f] = off[i];
+  fTypeFlags[f] = tf[i];
+  fFilter[f] = filter[i];
+  fMaterial[f] = material[i];
+}
+__global__ void k_scatter_quads(int n, const int* __restrict__ index, const float4* __restrict__ quads, float4* shapes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) shapes[index[i]] = quads[i];
+}
+
+extern "C" int b2g_upload_bodies_indexed(b2gArena* A, int32_t count, const int32_t* index, const b2gBodyArrays* s) {
+  if (!A || !s || count < 0 || (count > 0 && (!index || !s->pos || !s->vel || !s->xf || !s->mass || !s->center || !s->force ||
+                                              !s->flags || !s->world)))
+    return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
+  int top = 0;
+  for (int i = 0; i < count; ++i) {
+    if (index[i] < 0 || index[i] >= A->capBodies || s->world[i] < 0 || s->world[i] >= A->numWorlds) return B2G_ERR_INVALID;
+    top = index[i] + 1 > top ? index[i] + 1 : top;
+  }
+  CK(cudaSetDevice(A->device));
+  const size_t n = (size_t)count, rowBytes = 6 * 16 + 4 + 4 + 4;
+  int rc = scatter_stage(A, n * rowBytes);
+  if (rc) return rc;
+  float4* dRows = (float4*)A->scatterStage;
+  uint32_t* dFlags = (uint32_t*)(dRows + 6 * n);
+  int* dWorld = (int*)(dFlags + n);
+  int* dIndex = dWorld + n;
+  const float* cols[6] = {s->pos, s->vel, s->xf, s->mass, s->center, s->force};
+  for (int k = 0; k < 6; ++k)
+    CK(cudaMemcpyAsync(dRows + k * n, cols[k], n * 16, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dFlags, s->flags, n * 4, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dWorld, s->world, n * 4, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dIndex, index, n * 4, cudaMemcpyHostToDevice, A->stream));
+  k_scatter_bodies<<<div_up(count, 256), 256, 0, A->stream>>>(count, dIndex, dRows, dFlags, dWorld, A->pos, A->vel, A->xf, A->mass,
+                                                              A->center, A->force, A->bflags, A->bworld, A->worldRecolour);
+  CK(cudaGetLastError());
+  A->launches++;
+  if (top > A->nBodies) A->nBodies = top;
+  A->aabbAllDirty = 1;
+  A->islandsValid = 0;
+  A->recolourWorlds = 1;
+  A->jointColourDirty = 1;
+  A->fixBaseDirty = 1;
+  return B2G_OK;
+}
+
+extern "C" int b2g_upload_fixtures_indexed(b2gArena* A, int32_t count, const int32_t* index, const b2gFixtureArrays* s) {
+  if (!A || !s || count < 0 || (count > 0 && (!index || !s->body || !s->shape_off || !s->type_flags || !s->filter || !s->material)))
+    return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
+  int top = 0;
+  for (int i = 0; i < count; ++i) {
+    if (index[i] < 0 || index[i] >= A->capFixtures) return B2G_ERR_INVALID;
+    top = index[i] + 1 > top ? index[i] + 1 : top;
+  }
+  CK(cudaSetDevice(A->device));
+  const size_t n = (size_t)count;
+  int rc = scatter_stage(A, n * (16 + 8 + 4 * 4));
+  if (rc) return rc;
+  float4* dMat = (float4*)A->scatterStage;
+  uint2* dFilter = (uint2*)(dMat + n);
+  int* dBody = (int*)(dFilter + n);
+  int* dOff = dBody + n;
+  uint32_t* dTf = (uint32_t*)(dOff + n);
+  int* dIndex = (int*)(dTf + n);
+  CK(cudaMemcpyAsync(dMat, s->material, n * 16, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dFilter, s->filter, n * 8, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dBody, s->body, n * 4, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dOff, s->shape_off, n * 4, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dTf, s->type_flags, n * 4, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dIndex, index, n * 4, cudaMemcpyHostToDevice, A->stream));
+  k_scatter_fixtures<<<div_up(count, 256), 256, 0, A->stream>>>(count, dIndex, dBody, dOff, dTf, dFilter, dMat, A->fBody, A->fShapeOff,
+                                                                A->fTypeFlags, (uint2*)A->fFilter, A->fMaterial);
+  CK(cudaGetLastError());
+  A->launches++;
+  if (top > A->nFixtures) A->nFixtures = top;
+  A->aabbAllDirty = 1;
+  A->newFixtures = 1;
+  A->fixBaseDirty = 1;
+  A->islandsValid = 0;
+  return B2G_OK;
+}
+
+extern "C" int b2g_upload_shapes_indexed(b2gArena* A, int32_t count, const int32_t* index, const float* quads) {
+  if (!A || count < 0 || (count > 0 && (!index || !quads))) return B2G_ERR_INVALID;
+  if (count == 0) return B2G_OK;
+  for (int i = 0; i < count; ++i)
+    if (index[i] < 0 || index[i] >= A->capQuads) return B2G_ERR_INVALID;
+  CK(cudaSetDevice(A->device));
+  const size_t n = (size_t)count;
+  int rc = scatter_stage(A, n * 20);
+  if (rc) return rc;
+  float4* dQuads = (float4*)A->scatterStage;
+  int* dIndex = (int*)(dQuads + n);
+  CK(cudaMemcpyAsync(dQuads, quads, n * 16, cudaMemcpyHostToDevice, A->stream));
+  CK(cudaMemcpyAsync(dIndex, index, n * 4, cudaMemcpyHostToDevice, A->stream));
+  k_scatter_quads<<<div_up(count, 256), 256, 0, A->stream>>>(count, dIndex, dQuads, A->shapes);
+  CK(cudaGetLastError());
+  A->launches++;
   A->aabbAllDirty = 1;
   A->newFixtures = 1;
   A->fixBaseDirty = 1;

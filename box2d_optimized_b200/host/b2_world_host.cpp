@@ -96,9 +96,23 @@ struct b2WorldImpl {
   std::vector<int32_t> refilter;
   bool customFilter() const;
   void applyContactFilter();
+  // rows of the SoA upload calls, built from the host handles
+  struct BodyRows {
+    std::vector<float> pos, vel, xf, mass, center, force;
+    std::vector<uint32_t> flags;
+    std::vector<int32_t> wid, index;
+  };
+  struct FixtureRows {
+    std::vector<int32_t> body, off, index;
+    std::vector<uint32_t> tf, filter;
+    std::vector<float> mat;
+  };
+  void appendBodyRows(int32 lo, int32 n, BodyRows& R) const;
+  void appendFixtureRows(int32 lo, int32 n, FixtureRows& R) const;
   void ensureArena();
   void flush();
   void pullBodies();
+  void applyBodyRows(int32 n, const float* pos, const float* vel, const float* xf, const float* force, const uint32_t* flags);
   void pullJoints();
   void pullContacts();
   void rebuildContacts(int32 n, const int32_t* fa, const int32_t* fb, const uint32_t* flags, const float* man,
@@ -118,6 +132,15 @@ struct b2WorldBatchImpl {
   b2gStepStats lastStats;
   b2WorldImpl::SavedContacts saved;  // arena-wide fixture indices of the arena that was torn down
   int32 savedSlotFixtures = 0;
+  // members pulled one by one since the last Step; when that was many, the next step's first pull downloads
+  // every member at once (an RL loop that reads or edits every environment every step)
+  int32 memberPulls = 0;
+  bool bulkPull = false;
+  bool notePull() {
+    ++memberPulls;
+    return bulkPull;
+  }
+  void pullAllBodies();
   void ensureArena();
   void teardown();
   void growContacts();
@@ -307,6 +330,60 @@ void b2WorldImpl::growContacts() {
   contactsStale = true;
 }
 
+void b2WorldImpl::appendBodyRows(int32 lo, int32 n, BodyRows& R) const {
+  const size_t at = R.flags.size();
+  for (std::vector<float>* v : {&R.pos, &R.vel, &R.xf, &R.mass, &R.center, &R.force}) v->resize((at + (size_t)n) * 4, 0.0f);
+  R.flags.resize(at + n, 0u);
+  R.wid.resize(at + n, worldId);
+  R.index.resize(at + n);
+  for (int32 k = 0; k < n; ++k) {
+    const size_t r = at + (size_t)k;
+    R.index[r] = bodyBase + lo + k;
+    b2Body* b = bodies[lo + k];
+    if (!b) continue;  // destroyed: a disabled static placeholder (flags 0)
+    float* p = &R.pos[r * 4];
+    p[0] = b->m_sweep.c.x; p[1] = b->m_sweep.c.y; p[2] = b->m_sweep.a; p[3] = 0.0f;
+    float* v = &R.vel[r * 4];
+    v[0] = b->m_linearVelocity.x; v[1] = b->m_linearVelocity.y; v[2] = b->m_angularVelocity; v[3] = 0.0f;
+    float* x = &R.xf[r * 4];
+    x[0] = b->m_xf.p.x; x[1] = b->m_xf.p.y; x[2] = b->m_xf.q.s; x[3] = b->m_xf.q.c;
+    float* m = &R.mass[r * 4];
+    m[0] = b->m_invMass; m[1] = b->m_invI; m[2] = b->m_mass; m[3] = b->m_gravityScale;
+    float* c = &R.center[r * 4];
+    c[0] = b->m_sweep.localCenter.x; c[1] = b->m_sweep.localCenter.y; c[2] = b->m_linearDamping;
+    c[3] = b->m_angularDamping;
+    float* f = &R.force[r * 4];
+    f[0] = b->m_force.x; f[1] = b->m_force.y; f[2] = b->m_torque; f[3] = b->m_sleepTime;
+    R.flags[r] = (uint32_t)(b->m_flags & ~b2Body::e_islandFlag) | ((uint32_t)b->m_type << B2G_BODY_TYPE_SHIFT);
+  }
+}
+
+void b2WorldImpl::appendFixtureRows(int32 lo, int32 n, FixtureRows& R) const {
+  const size_t at = R.body.size();
+  R.body.resize(at + n);
+  R.off.resize(at + n);
+  R.index.resize(at + n);
+  R.tf.resize(at + n);
+  R.filter.resize((at + (size_t)n) * 2, 0u);
+  R.mat.resize((at + (size_t)n) * 4, 0.0f);
+  for (int32 k = 0; k < n; ++k) {
+    const size_t r = at + (size_t)k;
+    R.index[r] = fixtureBase + lo + k;
+    b2Fixture* f = fixtures[lo + k];
+    if (!f) {
+      R.body[r] = bodyBase; R.off[r] = quadBase; R.tf[r] = B2G_FIX_DEAD;
+      continue;
+    }
+    R.body[r] = bodyBase + f->m_body->m_index;
+    R.off[r] = quadBase + f->m_shapeOff;
+    R.tf[r] = (uint32_t)f->m_shape->GetType() | (f->m_isSensor ? B2G_FIX_SENSOR : 0u);
+    R.filter[r * 2] = (uint32_t)f->m_filter.categoryBits | ((uint32_t)f->m_filter.maskBits << 16);
+    R.filter[r * 2 + 1] = (uint32_t)(int32_t)f->m_filter.groupIndex;
+    R.mat[r * 4] = f->m_friction; R.mat[r * 4 + 1] = f->m_restitution;
+    R.mat[r * 4 + 2] = f->m_restitutionThreshold; R.mat[r * 4 + 3] = f->m_density;
+  }
+}
+
 // upload everything the host changed since the last step
 void b2WorldImpl::flush() {
   ensureArena();
@@ -319,34 +396,11 @@ void b2WorldImpl::flush() {
   }
   if (bodyDirtyHi > bodyDirtyLo) {
     int32 lo = bodyDirtyLo, n = bodyDirtyHi - bodyDirtyLo;
-    std::vector<float> pos((size_t)n * 4), vel((size_t)n * 4), xf((size_t)n * 4), mass((size_t)n * 4),
-        center((size_t)n * 4), force((size_t)n * 4);
-    std::vector<uint32_t> flags(n);
-    std::vector<int32_t> wid(n, worldId);
-    for (int32 k = 0; k < n; ++k) {
-      b2Body* b = bodies[lo + k];
-      float* p = &pos[(size_t)k * 4];
-      if (!b) {  // destroyed: a disabled static placeholder
-        flags[k] = 0;
-        continue;
-      }
-      p[0] = b->m_sweep.c.x; p[1] = b->m_sweep.c.y; p[2] = b->m_sweep.a; p[3] = 0.0f;
-      float* v = &vel[(size_t)k * 4];
-      v[0] = b->m_linearVelocity.x; v[1] = b->m_linearVelocity.y; v[2] = b->m_angularVelocity; v[3] = 0.0f;
-      float* x = &xf[(size_t)k * 4];
-      x[0] = b->m_xf.p.x; x[1] = b->m_xf.p.y; x[2] = b->m_xf.q.s; x[3] = b->m_xf.q.c;
-      float* m = &mass[(size_t)k * 4];
-      m[0] = b->m_invMass; m[1] = b->m_invI; m[2] = b->m_mass; m[3] = b->m_gravityScale;
-      float* c = &center[(size_t)k * 4];
-      c[0] = b->m_sweep.localCenter.x; c[1] = b->m_sweep.localCenter.y; c[2] = b->m_linearDamping;
-      c[3] = b->m_angularDamping;
-      float* f = &force[(size_t)k * 4];
-      f[0] = b->m_force.x; f[1] = b->m_force.y; f[2] = b->m_torque; f[3] = b->m_sleepTime;
-      flags[k] = (uint32_t)(b->m_flags & ~b2Body::e_islandFlag) | ((uint32_t)b->m_type << B2G_BODY_TYPE_SHIFT);
-    }
+    BodyRows R;
+    appendBodyRows(lo, n, R);
     b2gBodyArrays a;
-    a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.mass = mass.data(); a.center = center.data();
-    a.force = force.data(); a.flags = flags.data(); a.world = wid.data();
+    a.pos = R.pos.data(); a.vel = R.vel.data(); a.xf = R.xf.data(); a.mass = R.mass.data(); a.center = R.center.data();
+    a.force = R.force.data(); a.flags = R.flags.data(); a.world = R.wid.data();
     b2gCheck(b2g_upload_bodies(arena, bodyBase + lo, n, &a), "b2g_upload_bodies");
     bodiesOnDevice = std::max(bodiesOnDevice, lo + n);
     bodyDirtyLo = INT32_MAX;
@@ -354,26 +408,11 @@ void b2WorldImpl::flush() {
   }
   if (fixtureDirtyHi > fixtureDirtyLo) {
     int32 lo = fixtureDirtyLo, n = fixtureDirtyHi - fixtureDirtyLo;
-    std::vector<int32_t> body(n), off(n);
-    std::vector<uint32_t> tf(n), filter((size_t)n * 2);
-    std::vector<float> mat((size_t)n * 4);
-    for (int32 k = 0; k < n; ++k) {
-      b2Fixture* f = fixtures[lo + k];
-      if (!f) {
-        body[k] = bodyBase; off[k] = quadBase; tf[k] = B2G_FIX_DEAD;
-        continue;
-      }
-      body[k] = bodyBase + f->m_body->m_index;
-      off[k] = quadBase + f->m_shapeOff;
-      tf[k] = (uint32_t)f->m_shape->GetType() | (f->m_isSensor ? B2G_FIX_SENSOR : 0u);
-      filter[(size_t)k * 2] = (uint32_t)f->m_filter.categoryBits | ((uint32_t)f->m_filter.maskBits << 16);
-      filter[(size_t)k * 2 + 1] = (uint32_t)(int32_t)f->m_filter.groupIndex;
-      mat[(size_t)k * 4] = f->m_friction; mat[(size_t)k * 4 + 1] = f->m_restitution;
-      mat[(size_t)k * 4 + 2] = f->m_restitutionThreshold; mat[(size_t)k * 4 + 3] = f->m_density;
-    }
+    FixtureRows R;
+    appendFixtureRows(lo, n, R);
     b2gFixtureArrays a;
-    a.body = body.data(); a.shape_off = off.data(); a.type_flags = tf.data(); a.filter = filter.data();
-    a.material = mat.data();
+    a.body = R.body.data(); a.shape_off = R.off.data(); a.type_flags = R.tf.data(); a.filter = R.filter.data();
+    a.material = R.mat.data();
     b2gCheck(b2g_upload_fixtures(arena, fixtureBase + lo, n, &a), "b2g_upload_fixtures");
     fixtureDirtyLo = INT32_MAX;
     fixtureDirtyHi = 0;
@@ -426,6 +465,10 @@ void b2WorldImpl::pullJoints() {
 
 void b2WorldImpl::pullBodies() {
   if (!bodiesStale || !arena) return;
+  if (batch && batch->notePull()) {
+    batch->pullAllBodies();  // many members are being read every step: one download for all of them
+    return;
+  }
   bodiesStale = false;
   int32 n = std::min((int32)bodies.size(), bodiesOnDevice);
   if (n == 0) return;
@@ -435,6 +478,12 @@ void b2WorldImpl::pullBodies() {
   memset(&a, 0, sizeof(a));
   a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.force = force.data(); a.flags = flags.data();
   b2gCheck(b2g_download_bodies(arena, bodyBase, n, &a), "b2g_download_bodies");
+  applyBodyRows(n, pos.data(), vel.data(), xf.data(), force.data(), flags.data());
+}
+
+// downloaded device state of this world's first n bodies into the host handles
+void b2WorldImpl::applyBodyRows(int32 n, const float* pos, const float* vel, const float* xf, const float* force,
+                                const uint32_t* flags) {
   for (int32 i = 0; i < n; ++i) {
     b2Body* b = bodies[i];
     if (!b) continue;
@@ -1188,11 +1237,49 @@ void b2WorldBatchImpl::ensureArena() {
 void b2WorldBatchImpl::flush() {
   ensureArena();
   bool jointsDirty = false, fresh = false;
-  for (b2WorldImpl* m : members) {
-    if (!m) continue;
-    fresh = fresh || m->bodiesOnDevice == 0;
-    m->flush();  // shapes, bodies, fixtures into the member's slot
-    jointsDirty = jointsDirty || m->jointsDirty;
+  {
+    // every member's new shapes and edited bodies / fixtures in three scatter uploads, however many worlds
+    // contributed a row (the tumbler benchmark spawns one box per world per step)
+    b2WorldImpl::BodyRows B;
+    b2WorldImpl::FixtureRows F;
+    std::vector<float> quads;
+    std::vector<int32_t> quadIndex;
+    for (b2WorldImpl* m : members) {
+      if (!m) continue;
+      fresh = fresh || m->bodiesOnDevice == 0;
+      jointsDirty = jointsDirty || m->jointsDirty;
+      const int32 nq = (int32)(m->shapePool.size() / 4);
+      for (int32 q = m->shapesUploaded; q < nq; ++q) {
+        quadIndex.push_back(m->quadBase + q);
+        quads.insert(quads.end(), m->shapePool.begin() + (size_t)q * 4, m->shapePool.begin() + (size_t)q * 4 + 4);
+      }
+      m->shapesUploaded = nq;
+      if (m->bodyDirtyHi > m->bodyDirtyLo) {
+        m->appendBodyRows(m->bodyDirtyLo, m->bodyDirtyHi - m->bodyDirtyLo, B);
+        m->bodiesOnDevice = std::max(m->bodiesOnDevice, m->bodyDirtyHi);
+        m->bodyDirtyLo = INT32_MAX;
+        m->bodyDirtyHi = 0;
+      }
+      if (m->fixtureDirtyHi > m->fixtureDirtyLo) {
+        m->appendFixtureRows(m->fixtureDirtyLo, m->fixtureDirtyHi - m->fixtureDirtyLo, F);
+        m->fixtureDirtyLo = INT32_MAX;
+        m->fixtureDirtyHi = 0;
+      }
+    }
+    if (!quadIndex.empty())
+      b2gCheck(b2g_upload_shapes_indexed(arena, (int32_t)quadIndex.size(), quadIndex.data(), quads.data()), "b2g_upload_shapes_indexed");
+    if (!B.index.empty()) {
+      b2gBodyArrays a;
+      a.pos = B.pos.data(); a.vel = B.vel.data(); a.xf = B.xf.data(); a.mass = B.mass.data(); a.center = B.center.data();
+      a.force = B.force.data(); a.flags = B.flags.data(); a.world = B.wid.data();
+      b2gCheck(b2g_upload_bodies_indexed(arena, (int32_t)B.index.size(), B.index.data(), &a), "b2g_upload_bodies_indexed");
+    }
+    if (!F.index.empty()) {
+      b2gFixtureArrays a;
+      a.body = F.body.data(); a.shape_off = F.off.data(); a.type_flags = F.tf.data(); a.filter = F.filter.data();
+      a.material = F.mat.data();
+      b2gCheck(b2g_upload_fixtures_indexed(arena, (int32_t)F.index.size(), F.index.data(), &a), "b2g_upload_fixtures_indexed");
+    }
   }
   if (jointsDirty) {
     // the joint table is packed (world after world): one member's change moves the others' rows.  Every site
@@ -1241,6 +1328,24 @@ void b2WorldBatchImpl::flush() {
       if (m) m->world->m_newContacts = true;
   }
   if (fresh) b2gCheck(b2g_set_inv_dt0(arena, lastInvDt), "b2g_set_inv_dt0");
+}
+
+void b2WorldBatchImpl::pullAllBodies() {
+  if (!arena) return;
+  const int32 n = worldsOnDevice * slotBodies;
+  std::vector<float> pos((size_t)n * 4), vel((size_t)n * 4), xf((size_t)n * 4), force((size_t)n * 4);
+  std::vector<uint32_t> flags(n);
+  b2gBodyArrays a;
+  memset(&a, 0, sizeof(a));
+  a.pos = pos.data(); a.vel = vel.data(); a.xf = xf.data(); a.force = force.data(); a.flags = flags.data();
+  b2gCheck(b2g_download_bodies(arena, 0, n, &a), "b2g_download_bodies");
+  for (b2WorldImpl* m : members) {
+    if (!m || !m->bodiesStale || m->arena != arena) continue;
+    m->bodiesStale = false;
+    const int32 k = std::min((int32)m->bodies.size(), m->bodiesOnDevice);
+    const size_t o = (size_t)m->bodyBase;
+    m->applyBodyRows(k, &pos[o * 4], &vel[o * 4], &xf[o * 4], &force[o * 4], &flags[o]);
+  }
 }
 
 void b2WorldBatchImpl::pullContacts() {
@@ -1394,6 +1499,8 @@ void b2WorldBatch::Step(float dt, int32 velocityIterations, int32 positionIterat
     if (dt > 0.0f) m->lastInvDt = 1.0f / dt;
   }
   B->contactsStale = true;
+  B->bulkPull = B->memberPulls >= std::max(4, B->live() / 8);
+  B->memberPulls = 0;
   if (rc == B2G_ERR_CAPACITY) {
     B->growContacts();
     rc = B2G_OK;
@@ -1446,7 +1553,9 @@ b2Body::b2Body(const b2BodyDef* bd, b2World* world) {
 
 void b2Body::SyncIn() const { m_world->m_impl->pullBodies(); }
 void b2Body::Touch() {
-  m_world->m_impl->pullBodies();
+  // a body the device has not seen yet (created since the last step) has nothing to pull: its host copy is the
+  // only one.  (bodiesStale stays set, so the first edit of an older body still pulls before it marks its range.)
+  if (m_index < m_world->m_impl->bodiesOnDevice) m_world->m_impl->pullBodies();
   m_world->m_impl->touchBody(m_index);
 }
 

@@ -228,6 +228,13 @@ int b2g_upload_bodies(b2gArena* arena, int32_t first, int32_t count, const b2gBo
 /* b2Body::CreateFixture + b2Fixture::Create (b2_body.cpp:230-269, b2_fixture.cpp:44-75). */
 int b2g_upload_fixtures(b2gArena* arena, int32_t first, int32_t count, const b2gFixtureArrays* src);
 int b2g_upload_shapes(b2gArena* arena, int32_t first_quad, int32_t count_quads, const float* quads);
+/* Sparse variants: row i of the given arrays goes to index[i] (indices distinct).  One host-to-device copy per
+ * array and one scatter kernel whatever the spread of the indices — what a b2WorldBatch needs when each of a
+ * thousand worlds edited one body (b2Body setters, CreateBody / CreateFixture while running).  Every array
+ * pointer must be given (there is no "leave this column alone"). */
+int b2g_upload_bodies_indexed(b2gArena* arena, int32_t count, const int32_t* index, const b2gBodyArrays* rows);
+int b2g_upload_fixtures_indexed(b2gArena* arena, int32_t count, const int32_t* index, const b2gFixtureArrays* rows);
+int b2g_upload_shapes_indexed(b2gArena* arena, int32_t count_quads, const int32_t* index, const float* quads);
 /* b2World::CreateJoint for revolute joints (b2_world.cpp:268-323). */
 int b2g_upload_joints(b2gArena* arena, int32_t first, int32_t count, const b2gJointArrays* src);
 /* The joints' accumulated impulses after the last step, state[count][5] as above
