@@ -92,6 +92,36 @@ class Arena:
         capi.check(self.lib.b2g_upload_fixtures(self.h, first, n, C.byref(a)), "b2g_upload_fixtures")
         self.num_fixtures = max(self.num_fixtures, first + n)
 
+    def upload_bodies_indexed(self, index, pos, vel, xf, mass, center, force, flags, world):
+        """row i of the arrays goes to body index[i] (b2g_upload_bodies_indexed)"""
+        index = i32(index)
+        a = capi.BodyArrays()
+        keep = [index]
+        for k, v in dict(pos=pos, vel=vel, xf=xf, mass=mass, center=center, force=force).items():
+            v = f32(v).reshape(-1, 4)
+            keep.append(v)
+            setattr(a, k, capi.fp(v))
+        flags, world = u32(flags), i32(world)
+        keep += [flags, world]
+        a.flags, a.world = capi.up(flags), capi.ip(world)
+        capi.check(self.lib.b2g_upload_bodies_indexed(self.h, len(index), capi.ip(index), C.byref(a)), "b2g_upload_bodies_indexed")
+        if len(index):
+            self.num_bodies = max(self.num_bodies, int(index.max()) + 1)
+
+    def upload_fixtures_indexed(self, index, body, shape_off, type_flags, filter, material):
+        index, body, shape_off = i32(index), i32(body), i32(shape_off)
+        type_flags, filter, material = u32(type_flags), u32(filter).reshape(-1, 2), f32(material).reshape(-1, 4)
+        a = capi.FixtureArrays()
+        a.body, a.shape_off, a.type_flags = capi.ip(body), capi.ip(shape_off), capi.up(type_flags)
+        a.filter, a.material = capi.up(filter), capi.fp(material)
+        capi.check(self.lib.b2g_upload_fixtures_indexed(self.h, len(index), capi.ip(index), C.byref(a)), "b2g_upload_fixtures_indexed")
+        if len(index):
+            self.num_fixtures = max(self.num_fixtures, int(index.max()) + 1)
+
+    def upload_shapes_indexed(self, index, quads):
+        index, quads = i32(index), f32(quads).reshape(-1, 4)
+        capi.check(self.lib.b2g_upload_shapes_indexed(self.h, len(index), capi.ip(index), capi.fp(quads)), "b2g_upload_shapes_indexed")
+
     def upload_shapes(self, quads, first=0):
         quads = f32(quads).reshape(-1, 4)
         capi.check(self.lib.b2g_upload_shapes(self.h, first, len(quads), capi.fp(quads)), "b2g_upload_shapes")

@@ -66,6 +66,19 @@ struct b2WorldImpl {
   bool deadFixtures = false;   // a fixture was destroyed and the device may still hold contacts naming it
   float lastInvDt = 0.0f;      // b2World::m_inv_dt0 (b2_world.cpp:1162): survives an arena re-creation
   bool arenaFresh = false;     // the arena was (re-)created since the last flush
+  // Index recycling.  A destroyed body / fixture / shape record leaves a placeholder row on the device; the row is
+  // reused by a later Create* — but only after a Step, whose pair refresh has retired every contact that named it.
+  struct ShapeSlot { int32 off, quads; };
+  std::vector<int32> freeBodies, freeFixtures, retiredBodies, retiredFixtures;
+  std::vector<ShapeSlot> freeShapes, retiredShapes, dirtyShapes;
+  void releaseRetired() {
+    freeBodies.insert(freeBodies.end(), retiredBodies.begin(), retiredBodies.end());
+    freeFixtures.insert(freeFixtures.end(), retiredFixtures.begin(), retiredFixtures.end());
+    freeShapes.insert(freeShapes.end(), retiredShapes.begin(), retiredShapes.end());
+    retiredBodies.clear();
+    retiredFixtures.clear();
+    retiredShapes.clear();
+  }
   std::vector<b2Contact*> contacts;                       // current list, device order
   std::unordered_map<uint64_t, b2Contact*> contactPool;   // (fixA,fixB) -> handle, stable across steps
   b2Contact sentinel;
@@ -341,6 +354,7 @@ void b2WorldImpl::appendBodyRows(int32 lo, int32 n, BodyRows& R) const {
     R.index[r] = bodyBase + lo + k;
     b2Body* b = bodies[lo + k];
     if (!b) continue;  // destroyed: a disabled static placeholder (flags 0)
+    b->m_onDevice = true;
     float* p = &R.pos[r * 4];
     p[0] = b->m_sweep.c.x; p[1] = b->m_sweep.c.y; p[2] = b->m_sweep.a; p[3] = 0.0f;
     float* v = &R.vel[r * 4];
@@ -394,6 +408,9 @@ void b2WorldImpl::flush() {
              "b2g_upload_shapes");
     shapesUploaded = nq;
   }
+  for (const ShapeSlot& d : dirtyShapes)
+    b2gCheck(b2g_upload_shapes(arena, quadBase + d.off, d.quads, shapePool.data() + (size_t)d.off * 4), "b2g_upload_shapes");
+  dirtyShapes.clear();
   if (bodyDirtyHi > bodyDirtyLo) {
     int32 lo = bodyDirtyLo, n = bodyDirtyHi - bodyDirtyLo;
     BodyRows R;
@@ -486,7 +503,7 @@ void b2WorldImpl::applyBodyRows(int32 n, const float* pos, const float* vel, con
                                 const uint32_t* flags) {
   for (int32 i = 0; i < n; ++i) {
     b2Body* b = bodies[i];
-    if (!b) continue;
+    if (!b || !b->m_onDevice) continue;  // (a body created on a reused index: the device row is still the placeholder)
     b->m_sweep.c.Set(pos[(size_t)i * 4], pos[(size_t)i * 4 + 1]);
     b->m_sweep.a = pos[(size_t)i * 4 + 2];
     b->m_sweep.c0 = b->m_sweep.c;
@@ -738,8 +755,15 @@ void b2World::SetAllowSleeping(bool flag) {
 b2Body* b2World::CreateBody(const b2BodyDef* def) {
   if (IsLocked()) return nullptr;
   b2Body* b = new b2Body(def, this);
-  b->m_index = (int32)m_impl->bodies.size();
-  m_impl->bodies.push_back(b);
+  b->m_onDevice = false;
+  if (!m_impl->freeBodies.empty()) {
+    b->m_index = m_impl->freeBodies.back();
+    m_impl->freeBodies.pop_back();
+    m_impl->bodies[b->m_index] = b;
+  } else {
+    b->m_index = (int32)m_impl->bodies.size();
+    m_impl->bodies.push_back(b);
+  }
   m_impl->touchBody(b->m_index);
   // static bodies go to the tail, everything else to the head (b2_world.cpp:153-171)
   if (m_bodyListHead == nullptr) {
@@ -775,6 +799,8 @@ void b2World::DestroyBody(b2Body* b) {
     m_impl->fixtures[f->m_index] = nullptr;
     m_impl->deadFixtures = true;
     m_impl->touchFixture(f->m_index);
+    m_impl->retiredFixtures.push_back(f->m_index);
+    m_impl->retiredShapes.push_back({f->m_shapeOff, f->m_shape->DeviceQuadCount()});
     delete f->m_shape;
     delete f;
     f = nx;
@@ -785,6 +811,7 @@ void b2World::DestroyBody(b2Body* b) {
   if (b == m_bodyListTail) m_bodyListTail = b->m_prev;
   m_impl->bodies[b->m_index] = nullptr;
   m_impl->touchBody(b->m_index);
+  m_impl->retiredBodies.push_back(b->m_index);
   // host contact handles may point at the dead fixtures: drop them all, they are rebuilt lazily
   for (auto& kv : m_impl->contactPool) delete kv.second;
   m_impl->contactPool.clear();
@@ -1058,6 +1085,7 @@ void b2World::Step(float dt, int32 velocityIterations, int32 positionIterations,
   for (b2Contact* c : I->graveyard) delete c;
   I->graveyard.clear();
   I->contactsStale = true;
+  I->releaseRetired();  // this step's pair refresh has retired the contacts of everything destroyed before it
   if (I->profiling) {
     m_profile.step = I->lastStats.ms_step;
     m_profile.collide = I->lastStats.ms_collide;
@@ -1096,6 +1124,7 @@ int32 b2World::GetContactCount() const {
   if (m_impl->arena) b2g_contact_count(m_impl->arena, &n);
   return n;
 }
+int32 b2World::GetBodyIndexCount() const { return (int32)m_impl->bodies.size(); }
 int32 b2World::GetProxyCount() const {
   int32 n = 0;
   for (b2Fixture* f : m_impl->fixtures)
@@ -1254,6 +1283,12 @@ void b2WorldBatchImpl::flush() {
         quads.insert(quads.end(), m->shapePool.begin() + (size_t)q * 4, m->shapePool.begin() + (size_t)q * 4 + 4);
       }
       m->shapesUploaded = nq;
+      for (const b2WorldImpl::ShapeSlot& d : m->dirtyShapes)
+        for (int32 q = d.off; q < d.off + d.quads; ++q) {
+          quadIndex.push_back(m->quadBase + q);
+          quads.insert(quads.end(), m->shapePool.begin() + (size_t)q * 4, m->shapePool.begin() + (size_t)q * 4 + 4);
+        }
+      m->dirtyShapes.clear();
       if (m->bodyDirtyHi > m->bodyDirtyLo) {
         m->appendBodyRows(m->bodyDirtyLo, m->bodyDirtyHi - m->bodyDirtyLo, B);
         m->bodiesOnDevice = std::max(m->bodiesOnDevice, m->bodyDirtyHi);
@@ -1499,6 +1534,8 @@ void b2WorldBatch::Step(float dt, int32 velocityIterations, int32 positionIterat
     if (dt > 0.0f) m->lastInvDt = 1.0f / dt;
   }
   B->contactsStale = true;
+  for (b2WorldImpl* m : B->members)
+    if (m) m->releaseRetired();
   B->bulkPull = B->memberPulls >= std::max(4, B->live() / 8);
   B->memberPulls = 0;
   if (rc == B2G_ERR_CAPACITY) {
@@ -1555,7 +1592,7 @@ void b2Body::SyncIn() const { m_world->m_impl->pullBodies(); }
 void b2Body::Touch() {
   // a body the device has not seen yet (created since the last step) has nothing to pull: its host copy is the
   // only one.  (bodiesStale stays set, so the first edit of an older body still pulls before it marks its range.)
-  if (m_index < m_world->m_impl->bodiesOnDevice) m_world->m_impl->pullBodies();
+  if (m_onDevice) m_world->m_impl->pullBodies();
   m_world->m_impl->touchBody(m_index);
 }
 
@@ -1574,12 +1611,30 @@ b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
   f->m_shape = def->shape->Clone();
   f->m_density = def->density;
   f->m_id = g_fixtureIdCounter++;
-  f->m_index = (int32)I->fixtures.size();
-  I->fixtures.push_back(f);
+  if (!I->freeFixtures.empty()) {
+    f->m_index = I->freeFixtures.back();
+    I->freeFixtures.pop_back();
+    I->fixtures[f->m_index] = f;
+  } else {
+    f->m_index = (int32)I->fixtures.size();
+    I->fixtures.push_back(f);
+  }
   I->touchFixture(f->m_index);
   int32 nq = f->m_shape->DeviceQuadCount();
-  f->m_shapeOff = (int32)(I->shapePool.size() / 4);
-  I->shapePool.resize(I->shapePool.size() + (size_t)nq * 4);
+  f->m_shapeOff = -1;
+  for (size_t k = I->freeShapes.size(); k-- > 0;) {  // a free shape record of the same length, else a new one
+    if (I->freeShapes[k].quads == nq) {
+      f->m_shapeOff = I->freeShapes[k].off;
+      I->freeShapes.erase(I->freeShapes.begin() + (ptrdiff_t)k);
+      break;
+    }
+  }
+  if (f->m_shapeOff < 0) {
+    f->m_shapeOff = (int32)(I->shapePool.size() / 4);
+    I->shapePool.resize(I->shapePool.size() + (size_t)nq * 4);
+  } else {
+    I->dirtyShapes.push_back({f->m_shapeOff, nq});  // a reused record below the pool's uploaded mark
+  }
   f->m_shape->WriteDeviceQuads(&I->shapePool[(size_t)f->m_shapeOff * 4]);
   f->m_next = m_fixtureList;
   m_fixtureList = f;
@@ -1612,6 +1667,8 @@ void b2Body::DestroyFixture(b2Fixture* fixture) {
   I->fixtures[fixture->m_index] = nullptr;
   I->deadFixtures = true;
   I->touchFixture(fixture->m_index);
+  I->retiredFixtures.push_back(fixture->m_index);
+  I->retiredShapes.push_back({fixture->m_shapeOff, fixture->m_shape->DeviceQuadCount()});
   for (auto& kv : I->contactPool) delete kv.second;
   I->contactPool.clear();
   I->contacts.clear();

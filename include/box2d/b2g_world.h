@@ -243,7 +243,8 @@ class b2Body {
 
   b2BodyType m_type;
   uint16 m_flags;
-  int32 m_index;  // index in the device body arrays (creation order)
+  int32 m_index;  // index in the device body arrays (creation order; indices of destroyed bodies are reused)
+  bool m_onDevice;  // the device holds a copy of this body (false until its first upload)
   mutable b2Transform m_xf;
   mutable b2Sweep m_sweep;
   mutable b2Vec2 m_linearVelocity;
@@ -1022,6 +1023,9 @@ class b2World {
   int32 GetSolverMode() const { return m_solverMode; }
   /// fill GetProfile() from CUDA events (adds a synchronisation per step)
   void SetProfiling(bool flag);
+  /// rows of the device body table in use (live bodies + destroyed ones not yet reused): stays bounded in a world
+  /// that keeps creating and destroying bodies
+  int32 GetBodyIndexCount() const;
   b2WorldImpl* GetImpl() { return m_impl; }
 
  private:

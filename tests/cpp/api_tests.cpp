@@ -843,6 +843,55 @@ static void edits_inside_callbacks() {
          roller->GetPosition().x);
 }
 
+// A world that keeps creating and destroying bodies (projectiles, debris): every newcomer lands on the box left by
+// the one before it.  The results must not depend on whether a body sits on a fresh or on a reused device row, and in
+// the drop-in the device tables must stay bounded (the reference frees the memory in b2World::DestroyBody).
+static void spawn_and_destroy_churn() {
+  b2World world(b2Vec2(0.0f, -10.0f));
+  b2BodyDef gd;
+  b2Body* ground = world.CreateBody(&gd);
+  b2PolygonShape gbox;
+  gbox.SetAsBox(20.0f, 0.5f, b2Vec2(0.0f, -0.5f), 0.0f);
+  ground->CreateFixture(&gbox, 0.0f);
+  b2PolygonShape box;
+  box.SetAsBox(0.5f, 0.5f);
+  b2CircleShape ball;
+  ball.m_radius = 0.4f;
+  const int ALIVE = 10;
+  b2Body* ring[ALIVE] = {nullptr};
+  float landed = 0.0f;
+  for (int i = 0; i < 120; ++i) {
+    b2BodyDef bd;
+    bd.type = b2_dynamicBody;
+    bd.position.Set(1.5f * (float)(i % ALIVE) - 7.0f, 3.0f);
+    b2Body* b = world.CreateBody(&bd);
+    if (i % 3 == 2) b->CreateFixture(&ball, 1.0f);
+    else b->CreateFixture(&box, 1.0f);
+    for (int s = 0; s < 6; ++s) world.Step(1.0f / 60.0f, 8, 3);
+    b2Body*& slot = ring[i % ALIVE];
+    if (slot) {
+      if (i == 118) landed = slot->GetPosition().y;  // body 108: a box, on the ground for most of its 60 steps
+      world.DestroyBody(slot);
+    }
+    slot = b;
+  }
+  for (int s = 0; s < 90; ++s) world.Step(1.0f / 60.0f, 8, 3);
+  CHECK(world.GetBodyCount() == 1 + ALIVE);
+  CHECK(fabsf(landed - 0.505f) < 0.02f);
+  for (int k = 0; k < ALIVE; ++k) {  // bodies 110..119 rest on the ground: boxes at 0.5, balls at 0.4 (+ slop)
+    const int i = 110 + k;
+    const float want = (i % 3 == 2) ? 0.4f : 0.5f;
+    b2Body* b = ring[i % ALIVE];
+    CHECK(fabsf(b->GetPosition().y - want) < 0.03f && fabsf(b->GetLinearVelocity().y) < 0.05f);
+  }
+  CHECK(world.GetContactCount() == ALIVE);
+#ifdef B2G_WORLD_H
+  CHECK(world.GetBodyIndexCount() <= 1 + ALIVE + 3);  // ground + the bodies alive at a time + rows waiting for a step
+  printf("churn: %d device body rows for 121 bodies created\n", world.GetBodyIndexCount());
+#endif
+  printf("churn: body 108 rested at y = %.4f when it was destroyed, %d contacts at the end\n", landed, world.GetContactCount());
+}
+
 int main() {
   hello_world();
   begin_contact_test();
@@ -861,6 +910,7 @@ int main() {
   world_editing_session();
   user_contact_filter();
   edits_inside_callbacks();
+  spawn_and_destroy_churn();
   printf(g_failed ? "FAILED %d checks\n" : "all API checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }

@@ -139,3 +139,30 @@ def test_filter_scene_runs_free_like_the_reference(require_ref):
     for cls in range(5):
         idx = 1 + np.arange(cls, 120, 5)
         assert abs(float(np.mean(rb[idx, 5])) - float(np.mean(gb[idx, 5]))) < 0.15, f"filter class {cls}"
+
+
+def test_indexed_uploads_equal_the_contiguous_ones():
+    """b2g_upload_{bodies,fixtures,shapes}_indexed (the scatter uploads a b2WorldBatch uses): an arena filled row by
+    row in a shuffled order, in three calls, steps bit for bit like the arena filled with the contiguous calls."""
+    from box2d_optimized_b200.arena import _scene_upload_arrays
+    scene = _host_scene("mixed", 700, 12345, 0)
+    ref, _ = _run(scene, 1, capi.SOLVER_COLOURED, 120)
+    a = _scene_upload_arrays(scene)
+    nb, nf, nq = a["nb"], a["nf"], a["nq"]
+    A = Arena(nb, nf, nq, max(1024, 8 * nb), num_worlds=1, max_joints=1)
+    rng = np.random.default_rng(7)
+    pb, pf, pq = rng.permutation(nb), rng.permutation(nf), rng.permutation(nq)
+    fx = a["fx"]
+    A.upload_shapes_indexed(pq, fx["quads"].reshape(-1, 4)[pq])
+    A.upload_bodies_indexed(pb, a["pos"][pb], a["vel"][pb], a["xf"][pb], a["massq"][pb], a["center"][pb], a["force"][pb],
+                            a["flags"][pb], np.zeros(nb, np.int32))
+    A.upload_fixtures_indexed(pf, fx["body"][pf], fx["shape_off"][pf], a["tf"][pf], a["filt"][pf], fx["material"][pf])
+    A.find_new_contacts()
+    P = Arena.params(solver_mode=capi.SOLVER_COLOURED)
+    st = capi.StepStats()
+    for _ in range(120):
+        A.step(P, st)
+    d = A.download_bodies(what=("pos", "vel", "flags", "force"))
+    A.close()
+    for k in ("pos", "vel", "flags", "force"):
+        assert np.array_equal(np.asarray(d[k]).view(np.uint32), np.asarray(ref[k]).view(np.uint32)), k
