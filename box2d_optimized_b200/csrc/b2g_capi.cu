@@ -1345,6 +1345,8 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, A->device));
         if (perSM < 1) return B2G_ERR_CUDA;
         A->colourGrid = sms;
+        const char* e = getenv("B2G_WL_GRID");  // blocks of the worklist colouring (measurements)
+        if (e && atoi(e) > 0 && atoi(e) <= sms * perSM) A->colourGrid = atoi(e);
       }
       int cutBin = M.cutBin, bb = bigBin;
       static int singleMax = -1;  // B2G_WL_SINGLE_MAX=n: worklists up to n entries are coloured by one CTA (measurements)
