@@ -1162,6 +1162,9 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
   // that outgrows the cap within one step is simply routed to the big path for that step.
   int bigThr = A->lastMaxIsland + A->lastMaxIsland / 2 + 64;
   if (bigThr > B2G_BIG_ISLAND) bigThr = B2G_BIG_ISLAND;
+  // nothing known yet (first step, or nothing was awake): allow the largest tile rather than sending a mid-size
+  // island through the grid-pass kernel, whose serial bucket is walked by ONE thread of the grid
+  if (A->lastMaxIsland == 0) bigThr = B2G_BIG_ISLAND;
   // aim at >= 2 bins per SM so the fused kernel fills the chip, within what a tile can hold
   int binSize = nb / (2 * 148);
   if (binSize < 32) binSize = 32;
@@ -1406,7 +1409,7 @@ static int solve_fused(b2gArena* A, const b2gStepParams* P, SolveOut& out) {
     launch_pdl(A->stream, dim3(nbins), dim3(fusedThreads), smem, k_solve_bins_fused,
         FP, A->binFirst, A->binEnd, A->slotBody, A->bodySlot, A->island, A->islandStart, A->bucketStart,
         A->sortedList, (int*)A->conKeys, C, A->fRadius, S, A->bflags, A->pos, A->vel, A->xf, A->force, A->mass, A->center, A->dCounts,
-        joint_views(A));
+        joint_views(A), A->conVals, (int*)A->conKeysSorted);
     ktime_end(A);
     A->launches++;
   }

@@ -475,16 +475,52 @@ __global__ void k_bucket_scatter(int nc, const int* __restrict__ cbin, ContactBu
 __device__ __forceinline__ void order_bucket_by_key(int o0, int o1, int* sortedList, int* scratch, const ContactBuf& C) {
   const int n = o1 - o0;
   if (n <= 1) return;  // block-uniform
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    int i = sortedList[o0 + t];
-    unsigned long long ki = C.key[i];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += C.key[sortedList[o0 + j]] < ki ? 1 : 0;
-    scratch[o0 + rank] = i;
+  if (n <= 96) {
+    // the usual case (a hub body's few dozen extra contacts): rank by counting, O(n^2) compares on cached keys
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      int i = sortedList[o0 + t];
+      unsigned long long ki = C.key[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += C.key[sortedList[o0 + j]] < ki ? 1 : 0;
+      scratch[o0 + rank] = i;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) sortedList[o0 + t] = scratch[o0 + t];
+    __syncthreads();
+    return;
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < n; t += blockDim.x) sortedList[o0 + t] = scratch[o0 + t];
-  __syncthreads();
+  // A large bucket (bodies that start overlapping hundreds of others: the reference's "n^2" benchmarks put tens of
+  // thousands of constraints here) would cost n^2 = billions of compares: bitonic network in place instead,
+  // O(n log^2 n).  Every compare-exchange puts the smaller key at the lower index (the "flip" form of the
+  // network), so the virtual +inf padding up to the next power of two never has to move and is simply skipped.
+  // Keys are unique, so the result is the same order the rank sort gives.
+  int* a = sortedList + o0;
+  int m = 1;
+  while (m < n) m <<= 1;
+  auto exchange = [&](int i, int l) {
+    if (l < n) {
+      const int ia = a[i], il = a[l];
+      if (C.key[ia] > C.key[il]) {
+        a[i] = il;
+        a[l] = ia;
+      }
+    }
+  };
+  for (int k = 2; k <= m; k <<= 1) {
+    const int hk = k >> 1;
+    for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+      const int i = (t / hk) * k + (t % hk);
+      exchange(i, i ^ (k - 1));
+    }
+    __syncthreads();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+        const int i = (t / j) * 2 * j + (t % j);
+        exchange(i, i + j);
+      }
+      __syncthreads();
+    }
+  }
 }
 
 __global__ void k_order_overflow(int o0, int o1, int* sortedList, int* scratch, ContactBuf C) {
@@ -511,6 +547,7 @@ struct FusedParams {
 #define B2G_JOINT_COLOUR_THREADS 1024
 #define B2G_TILE_JOINTS_SERIAL 64  // a tile (or the set of oversize islands) with at most this many joints walks them in list order
 #define B2G_PLANES 13
+#define B2G_LEVELS_MIN_BUCKET 128  // serial buckets from this size on are level-scheduled when their levels are wide
 
 // dynamic shared memory layout for a tile of `cap` bodies
 struct FusedTile {
@@ -532,7 +569,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
                    const int* __restrict__ bucketStart, int* sortedList, int* orderScratch, ContactBuf C,
                    const float* __restrict__ fRadius, SolverPlanes S, uint32_t* bflags, float4* gpos, float4* gvel,
                    float4* gxf, float4* gforce, const float4* __restrict__ gmass, const float4* __restrict__ gcenter,
-                   StepCounts* counts, JointArraysDev J) {
+                   StepCounts* counts, JointArraysDev J, int* levelScratch, int* permScratch) {
   B2G_PDL_ENTER();
   const int bin = blockIdx.x;
   const int first = binFirst[bin];
@@ -756,6 +793,97 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
     __syncthreads();
   }
 
+  // ---- level schedule of a LARGE serial bucket ----------------------------------------------------------------
+  // Bodies that overlap dozens of others at once (the reference's "n^2" and multi-fixture benchmarks) put
+  // thousands of constraints beyond the 24 colours.  Walking them with one thread is a Gauss-Seidel in key
+  // order; the same order is kept — and most of its parallelism recovered — by LEVELS: a constraint's level is
+  // one more than the highest level among the earlier (in key order) constraints of its two bodies, so
+  // constraints of one level share no body and every constraint still comes after all its predecessors.  One
+  // serial pass assigns the levels (a few loads per constraint), a counting sort groups them, and each pass
+  // below walks level by level with the whole block.  Used when it pays (average level width >= 4: a hub's
+  // chain — the tumbler — has width 1 and keeps the plain walk).
+  __shared__ int sLevels;
+  const int nOv = ov1 - ov0;
+  int* const lvl = orderScratch;             // [slot] level (the key sort is done with its scratch)
+  int* const perm = permScratch;             // [ov0 + k] the bucket's slots grouped by level
+  int* const levelStart = levelScratch + ov0;  // [levels + 1], then [levels] cursors: fits, levels <= nOv / 4
+  if (tid == 0) sLevels = 0;
+  __syncthreads();  // (every thread reads sLevels below, also in blocks that skip the scheduling)
+  if (nOv >= B2G_LEVELS_MIN_BUCKET) {  // block-uniform
+    for (int t = tid; t < nOv; t += nt) {
+      const int4 ix = S.idx[ov0 + t];
+      perm[ov0 + t] = (int)(((unsigned int)(ix.x >= 0 ? ix.x : 0xFFFF) << 16) | (unsigned int)(ix.y >= 0 ? ix.y : 0xFFFF));
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // warp 0: 32 entries per coalesced load, lane 0 walks them in key order (the only serial part: two
+      // shared-memory reads and writes per constraint), the levels go back out coalesced
+      int top = 0;
+      for (int base = ov0; base < ov1; base += 32) {
+        const int mine = base + tid < ov1 ? perm[base + tid] : -1;
+        int myLevel = 0;
+        const int cnt = ov1 - base < 32 ? ov1 - base : 32;
+        for (int u = 0; u < cnt; ++u) {
+          const unsigned int pk = (unsigned int)__shfl_sync(0xffffffffu, mine, u);
+          int L = 0;
+          if (tid == 0) {
+            const int a = (int)(pk >> 16), b = (int)(pk & 0xFFFFu);
+            const int la = a != 0xFFFF ? (int)T.pen[a] : 0, lb = b != 0xFFFF ? (int)T.pen[b] : 0;
+            L = la > lb ? la : lb;
+            if (a != 0xFFFF) T.pen[a] = (unsigned int)(L + 1);
+            if (b != 0xFFFF) T.pen[b] = (unsigned int)(L + 1);
+            top = L > top ? L : top;
+          }
+          L = __shfl_sync(0xffffffffu, L, 0);
+          if (tid == u) myLevel = L;
+        }
+        if (base + tid < ov1) lvl[base + tid] = myLevel;
+      }
+      if (tid == 0) sLevels = (long long)(top + 1) * 4 <= (long long)nOv ? top + 1 : 0;
+    }
+    __syncthreads();
+    for (int l = tid; l < nbod; l += nt) T.pen[l] = 0u;  // (borrowed as the bodies' level counters)
+    const int nl = sLevels;
+    if (nl > 0) {
+      for (int t = tid; t <= 2 * nl; t += nt) levelStart[t] = 0;
+      __syncthreads();
+      for (int t = tid; t < nOv; t += nt) atomicAdd(&levelStart[lvl[ov0 + t] + 1], 1);
+      __syncthreads();
+      if (tid == 0)
+        for (int L = 0; L < nl; ++L) levelStart[L + 1] += levelStart[L];
+      __syncthreads();
+      int* const cursor = levelStart + nl + 1;
+      for (int t = tid; t < nOv; t += nt) {  // order inside a level is immaterial: its constraints share no body
+        const int L = lvl[ov0 + t];
+        perm[ov0 + levelStart[L] + atomicAdd(&cursor[L], 1)] = ov0 + t;
+      }
+    }
+    __syncthreads();
+  }
+  const int nLevels = sLevels;
+  // one pass over the serial bucket, by ALL threads: level by level, or (no schedule) one thread in key order
+  auto serial_bucket = [&](auto&& visit) {
+    if (nLevels > 0) {
+      for (int L = 0; L < nLevels; ++L) {
+        const int k1 = levelStart[L + 1];
+        for (int k = levelStart[L] + tid; k < k1; k += nt) {
+          const int s = perm[ov0 + k];
+          visit(s < ovStaged ? V : S, s);
+        }
+        __syncthreads();
+      }
+    } else {
+      if (tid == 0) {
+        for (int half = 0; half < 2; ++half) {  // the staged slots, then the rest: one call site for both
+          const SolverPlanes& PL = half == 0 ? V : S;
+          const int s1 = half == 0 ? ovStaged : ov1;
+          for (int s = half == 0 ? ov0 : ovStaged; s < s1; ++s) visit(PL, s);
+        }
+      }
+      __syncthreads();
+    }
+  };
+
   // ---- phase 2: warm start, colour by colour ---------------------------------------------------
   if (P.warmStarting) {
     for (int k = 0; k < nUsed; ++k) {
@@ -763,13 +891,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
       for (int s = s0 + tid; s < s1; s += nt) warm_start_constraint(S, s, velAcc);
       __syncthreads();
     }
-    if (cstart[B2G_MAX_COLOURS] != cstart[B2G_MAX_COLOURS + 1]) {
-      if (tid == 0) {
-        for (int s = ov0; s < ovStaged; ++s) warm_start_constraint(V, s, velAcc);
-        for (int s = ovStaged; s < ov1; ++s) warm_start_constraint(S, s, velAcc);
-      }
-      __syncthreads();
-    }
+    if (nOv > 0) serial_bucket([&](const SolverPlanes& PL, int s) { warm_start_constraint(PL, s, velAcc); });
   }
 
   // joints: InitVelocityConstraints incl. their warm start (b2_island.cpp:323-325), after the contacts'
@@ -791,13 +913,7 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
       for (int s = s0 + tid; s < s1; s += nt) solve_velocity_constraint(S, s, velAcc);
       __syncthreads();
     }
-    if (cstart[B2G_MAX_COLOURS] != cstart[B2G_MAX_COLOURS + 1]) {
-      if (tid == 0) {
-        for (int s = ov0; s < ovStaged; ++s) solve_velocity_constraint(V, s, velAcc);
-        for (int s = ovStaged; s < ov1; ++s) solve_velocity_constraint(S, s, velAcc);
-      }
-      __syncthreads();
-    }
+    if (nOv > 0) serial_bucket([&](const SolverPlanes& PL, int s) { solve_velocity_constraint(PL, s, velAcc); });
   }
 
   // ---- phase 4: store impulses (b2_contact_solver.cpp:641-657) -----------------------------------
@@ -853,31 +969,21 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
 
   // ---- phase 6: position iterations with the per-island early exit (b2_island.cpp:391-409) --------
   for (int it = 0; it < P.posIters; ++it) {
-    for (int k = 0; k <= nUsed; ++k) {
-      int s0, s1, sBegin, sStep = nt;
-      if (k < nUsed) {
-        s0 = usedS0[k];
-        s1 = usedS1[k];
-        sBegin = s0 + tid;
-      } else {  // overflow bucket: one thread, list order
-        s0 = cstart[B2G_MAX_COLOURS];
-        s1 = cstart[B2G_MAX_COLOURS + 1];
-        if (s0 == s1) continue;
-        sBegin = tid == 0 ? s0 : s1;
-        sStep = 1;
-      }
-      for (int s = sBegin; s < s1; s += sStep) {
-        const bool staged = k == nUsed && s < ovStaged;
-        int4 ix = staged ? V.idx[s] : S.idx[s];
-        int slot = ix.x >= 0 ? ix.x : ix.y;  // a tile member of the island (the other may be static)
-        int hd = T.head[slot];
-        if (T.done[hd]) continue;
-        float minSep = staged ? solve_position_constraint(V, s, posAcc) : solve_position_constraint(S, s, posAcc);
-        float pen = minSep < 0.0f ? -minSep : 0.0f;
-        atomicMax(&T.pen[hd], __float_as_uint(pen));
-      }
+    auto position_visit = [&](const SolverPlanes& PL, int s) {
+      int4 ix = PL.idx[s];
+      int slot = ix.x >= 0 ? ix.x : ix.y;  // a tile member of the island (the other may be static)
+      int hd = T.head[slot];
+      if (T.done[hd]) return;
+      float minSep = solve_position_constraint(PL, s, posAcc);
+      float pen = minSep < 0.0f ? -minSep : 0.0f;
+      atomicMax(&T.pen[hd], __float_as_uint(pen));
+    };
+    for (int k = 0; k < nUsed; ++k) {
+      const int s1 = usedS1[k];
+      for (int s = usedS0[k] + tid; s < s1; s += nt) position_visit(S, s);
       __syncthreads();
     }
+    if (nOv > 0) serial_bucket(position_visit);
     if (njTile > 0) {  // contacts first, then joints (b2_island.cpp:392-401); a joint that is not
                        // okay keeps its island iterating, expressed as a large "penetration"
       for_tile_joints([&](int j) {
