@@ -472,6 +472,37 @@ __global__ void k_bucket_scatter(int nc, const int* __restrict__ cbin, ContactBu
 // The overflow bucket is the only place where constraint ORDER matters (one thread, Gauss-Seidel in
 // list order), and the counting sort above leaves bucket contents in arbitrary order: rank-sort it
 // by pair key so runs stay bit-reproducible.  Block-wide, O(n^2) key compares, n = overflow size.
+// block-wide ascending sort of n ints in place (bitonic network, "flip" form: see order_bucket_by_key)
+__device__ __forceinline__ void sort_ints_ascending(int* a, int n) {
+  if (n <= 1) return;  // block-uniform
+  int m = 1;
+  while (m < n) m <<= 1;
+  auto exchange = [&](int i, int l) {
+    if (l < n) {
+      const int x = a[i], y = a[l];
+      if (x > y) {
+        a[i] = y;
+        a[l] = x;
+      }
+    }
+  };
+  for (int k = 2; k <= m; k <<= 1) {
+    const int hk = k >> 1;
+    for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+      const int i = (t / hk) * k + (t % hk);
+      exchange(i, i ^ (k - 1));
+    }
+    __syncthreads();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+        const int i = (t / j) * 2 * j + (t % j);
+        exchange(i, i + j);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __device__ __forceinline__ void order_bucket_by_key(int o0, int o1, int* sortedList, int* scratch, const ContactBuf& C) {
   const int n = o1 - o0;
   if (n <= 1) return;  // block-uniform
@@ -547,7 +578,8 @@ struct FusedParams {
 #define B2G_JOINT_COLOUR_THREADS 1024
 #define B2G_TILE_JOINTS_SERIAL 64  // a tile (or the set of oversize islands) with at most this many joints walks them in list order
 #define B2G_PLANES 13
-#define B2G_LEVELS_MIN_BUCKET 128  // serial buckets from this size on are level-scheduled when their levels are wide
+#define B2G_LEVELS_MIN_BUCKET 128  // serial buckets from this size on are level-scheduled when that pays
+#define B2G_LEVELS_MAX 96          // levels of the schedule (three borrowed 32-bit words per body)
 
 // dynamic shared memory layout for a tile of `cap` bodies
 struct FusedTile {
@@ -795,30 +827,32 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
 
   // ---- level schedule of a LARGE serial bucket ----------------------------------------------------------------
   // Bodies that overlap dozens of others at once (the reference's "n^2" and multi-fixture benchmarks) put
-  // thousands of constraints beyond the 24 colours.  Walking them with one thread is a Gauss-Seidel in key
-  // order; the same order is kept — and most of its parallelism recovered — by LEVELS: a constraint's level is
-  // one more than the highest level among the earlier (in key order) constraints of its two bodies, so
-  // constraints of one level share no body and every constraint still comes after all its predecessors.  One
-  // serial pass assigns the levels (a few loads per constraint), a counting sort groups them, and each pass
-  // below walks level by level with the whole block.  Used when it pays (average level width >= 4: a hub's
-  // chain — the tumbler — has width 1 and keeps the plain walk).
-  __shared__ int sLevels;
+  // thousands of constraints beyond the 24 colours, and walking them with one thread is what such a step then
+  // costs.  They are given LEVELS here — a second, per-bin colouring with 96 more colours: lane 0 of warp 0
+  // walks the bucket in key order and gives each constraint the lowest level free on both of its bodies (the
+  // bodies' used levels are 96-bit sets in three borrowed per-body words of the tile); constraints of one level
+  // share no body and are solved by the whole block, level after level.  What finds none of the 96 free (a body
+  // with more than ~100 extra contacts) gets a chain level above them: one more than the highest chain level
+  // either of its bodies has reached.  Deterministic: levels are a function of the key-ordered bucket, the
+  // order inside a level is immaterial.  Used when it pays (a hub's chain — the tumbler container's ~40 extra
+  // contacts — stays below the size limit and keeps the plain walk).
+  __shared__ int sLevels, sTail;  // levels walked by the whole block; constraints of the serial tail behind them
   const int nOv = ov1 - ov0;
   int* const lvl = orderScratch;             // [slot] level (the key sort is done with its scratch)
   int* const perm = permScratch;             // [ov0 + k] the bucket's slots grouped by level
-  int* const levelStart = levelScratch + ov0;  // [levels + 1], then [levels] cursors: fits, levels <= nOv / 4
-  if (tid == 0) sLevels = 0;
+  int* const levelStart = levelScratch + ov0;  // [levels + 2] starts (the tail is group `levels`), then [levels + 1] cursors
+  if (tid == 0) sLevels = 0, sTail = 0;
   __syncthreads();  // (every thread reads sLevels below, also in blocks that skip the scheduling)
   if (nOv >= B2G_LEVELS_MIN_BUCKET) {  // block-uniform
     for (int t = tid; t < nOv; t += nt) {
       const int4 ix = S.idx[ov0 + t];
       perm[ov0 + t] = (int)(((unsigned int)(ix.x >= 0 ? ix.x : 0xFFFF) << 16) | (unsigned int)(ix.y >= 0 ? ix.y : 0xFFFF));
     }
+    for (int l = tid; l < nbod; l += nt) T.sleepMin[l] = 0u, T.head[l] = 0;  // borrowed with T.pen and T.done (both zero here)
     __syncthreads();
     if (tid < 32) {
-      // warp 0: 32 entries per coalesced load, lane 0 walks them in key order (the only serial part: two
-      // shared-memory reads and writes per constraint), the levels go back out coalesced
-      int top = 0;
+      // 32 entries per coalesced load; the serial part is a few shared-memory words per constraint
+      int top = -1, chainTop = -1, beyond = 0;  // highest first-fit level, highest chain level, constraints beyond the 96
       for (int base = ov0; base < ov1; base += 32) {
         const int mine = base + tid < ov1 ? perm[base + tid] : -1;
         int myLevel = 0;
@@ -828,35 +862,80 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
           int L = 0;
           if (tid == 0) {
             const int a = (int)(pk >> 16), b = (int)(pk & 0xFFFFu);
-            const int la = a != 0xFFFF ? (int)T.pen[a] : 0, lb = b != 0xFFFF ? (int)T.pen[b] : 0;
-            L = la > lb ? la : lb;
-            if (a != 0xFFFF) T.pen[a] = (unsigned int)(L + 1);
-            if (b != 0xFFFF) T.pen[b] = (unsigned int)(L + 1);
-            top = L > top ? L : top;
+            unsigned int u0 = 0u, u1 = 0u, u2 = 0u;
+            if (a != 0xFFFF) u0 |= T.pen[a], u1 |= T.sleepMin[a], u2 |= (unsigned int)T.done[a];
+            if (b != 0xFFFF) u0 |= T.pen[b], u1 |= T.sleepMin[b], u2 |= (unsigned int)T.done[b];
+            L = ~u0 ? __ffs((int)~u0) - 1 : (~u1 ? 32 + __ffs((int)~u1) - 1 : (~u2 ? 64 + __ffs((int)~u2) - 1 : B2G_LEVELS_MAX));
+            if (L == B2G_LEVELS_MAX) {
+              // no level left on these bodies: chain levels above the 96 — one more than the highest chain level
+              // either body has reached (T.head borrowed as that counter)
+              const int ca = a != 0xFFFF ? T.head[a] : 0, cb = b != 0xFFFF ? T.head[b] : 0;
+              const int c = ca > cb ? ca : cb;
+              L = B2G_LEVELS_MAX + c;
+              if (a != 0xFFFF) T.head[a] = c + 1;
+              if (b != 0xFFFF) T.head[b] = c + 1;
+              chainTop = c > chainTop ? c : chainTop;
+              ++beyond;
+            } else if (L < B2G_LEVELS_MAX) {
+              const unsigned int bit = 1u << (L & 31);
+              if (a != 0xFFFF) {
+                if (L < 32) T.pen[a] |= bit;
+                else if (L < 64) T.sleepMin[a] |= bit;
+                else T.done[a] = (int)((unsigned int)T.done[a] | bit);
+              }
+              if (b != 0xFFFF) {
+                if (L < 32) T.pen[b] |= bit;
+                else if (L < 64) T.sleepMin[b] |= bit;
+                else T.done[b] = (int)((unsigned int)T.done[b] | bit);
+              }
+              top = L > top ? L : top;
+            }
           }
           L = __shfl_sync(0xffffffffu, L, 0);
           if (tid == u) myLevel = L;
         }
         if (base + tid < ov1) lvl[base + tid] = myLevel;
       }
-      if (tid == 0) sLevels = (long long)(top + 1) * 4 <= (long long)nOv ? top + 1 : 0;
+      // one level pass costs about four serial visits
+      if (tid == 0 && top >= 0) {
+        // What lies beyond the 96 levels is either walked as chain levels (wide chains: bodies piled on one spot)
+        // or by one thread in key order (narrow ones: dozens of contacts between the same two bodies); a level
+        // pass costs about four serial visits.
+        const bool chain = beyond > 0 && (long long)(chainTop + 1) * 4 <= (long long)beyond;
+        const int levels = chain ? B2G_LEVELS_MAX + chainTop + 1 : top + 1;
+        const int tail = chain ? 0 : beyond;
+        if ((long long)levels * 4 + tail <= (long long)nOv * 3 / 4) sLevels = levels, sTail = tail;
+      }
     }
     __syncthreads();
-    for (int l = tid; l < nbod; l += nt) T.pen[l] = 0u;  // (borrowed as the bodies' level counters)
+    for (int l = tid; l < nbod; l += nt) {  // give the borrowed words back as the tile load left them
+      T.pen[l] = 0u;
+      T.sleepMin[l] = __float_as_uint(B2G_MAX_FLOAT);
+      T.done[l] = 0;
+      T.head[l] = islandStart[island[T.body[l]]] - first;
+    }
     const int nl = sLevels;
     if (nl > 0) {
-      for (int t = tid; t <= 2 * nl; t += nt) levelStart[t] = 0;
+      const bool hasTail = sTail > 0;  // then every level >= 96 is the tail = group `nl`
+      for (int t = tid; t <= 2 * nl + 2; t += nt) levelStart[t] = 0;
       __syncthreads();
-      for (int t = tid; t < nOv; t += nt) atomicAdd(&levelStart[lvl[ov0 + t] + 1], 1);
+      for (int t = tid; t < nOv; t += nt) {
+        const int L = lvl[ov0 + t];
+        atomicAdd(&levelStart[(hasTail && L >= B2G_LEVELS_MAX ? nl : L) + 1], 1);
+      }
       __syncthreads();
       if (tid == 0)
-        for (int L = 0; L < nl; ++L) levelStart[L + 1] += levelStart[L];
+        for (int L = 0; L <= nl; ++L) levelStart[L + 1] += levelStart[L];
       __syncthreads();
-      int* const cursor = levelStart + nl + 1;
+      int* const cursor = levelStart + nl + 2;
       for (int t = tid; t < nOv; t += nt) {  // order inside a level is immaterial: its constraints share no body
-        const int L = lvl[ov0 + t];
+        const int L0 = lvl[ov0 + t];
+        const int L = hasTail && L0 >= B2G_LEVELS_MAX ? nl : L0;
         perm[ov0 + levelStart[L] + atomicAdd(&cursor[L], 1)] = ov0 + t;
       }
+      __syncthreads();
+      // the tail is walked by one thread, so its order matters: ascending slot = key order
+      sort_ints_ascending(perm + ov0 + levelStart[nl], hasTail ? sTail : 0);
     }
     __syncthreads();
   }
@@ -864,9 +943,11 @@ k_solve_bins_fused(FusedParams P, const int* __restrict__ binFirst, const int* _
   // one pass over the serial bucket, by ALL threads: level by level, or (no schedule) one thread in key order
   auto serial_bucket = [&](auto&& visit) {
     if (nLevels > 0) {
-      for (int L = 0; L < nLevels; ++L) {
+      // levels 0 .. nLevels - 1 with the whole block; group nLevels is the tail (empty without one): one thread
+      for (int L = 0; L <= nLevels; ++L) {
         const int k1 = levelStart[L + 1];
-        for (int k = levelStart[L] + tid; k < k1; k += nt) {
+        const bool tail = L == nLevels;
+        for (int k = tail ? (tid == 0 ? levelStart[L] : k1) : levelStart[L] + tid; k < k1; k += tail ? 1 : nt) {
           const int s = perm[ov0 + k];
           visit(s < ovStaged ? V : S, s);
         }
