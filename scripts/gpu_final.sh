@@ -1,7 +1,7 @@
 #!/bin/bash
 # final validation of the round-2 build
 mkdir -p gpurun_out
-TAG=r02w
+TAG=${1:-final}
 ( time python -m pytest tests -q -m gpu 2>&1 | tail -25 ) > gpurun_out/${TAG}_pytest_gpu.txt 2>&1; tail -5 gpurun_out/${TAG}_pytest_gpu.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 for wl in mixed_100k many_pyramids tumbler_worlds; do
