@@ -1499,6 +1499,17 @@ void b2WorldBatch::Step(float dt, int32 velocityIterations, int32 positionIterat
   if (!first) return;
   for (b2WorldImpl* m : B->members)
     if (m) m->world->m_locked = true;
+  {
+    static bool warned = false;
+    if (!warned)
+      for (b2WorldImpl* m : B->members)
+        if (m && (m->world->m_contactListener != nullptr || m->customFilter())) {
+          fprintf(stderr, "[b2cuda] b2WorldBatch::Step: contact listeners and user contact filters are not called for "
+                          "batched worlds (step such a world on its own)\n");
+          warned = true;
+          break;
+        }
+  }
   B->flush();
   bool newContacts = false;
   for (b2WorldImpl* m : B->members)
