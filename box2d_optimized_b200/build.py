@@ -134,6 +134,13 @@ def build_reference_benchmarks(force=False):
             _run([gxx, "-O2", "-std=c++11", "-I" + os.path.join(ref, "include"), "-I" + bdir, src] + objs + ["-o", exe])
         if objs:
             built.append(exe)
+    # config 4 through b2WorldBatch: W instances of the reference's unchanged b3 in one batch (drop-in build only)
+    src = os.path.join(ROOT, "tests", "cpp", "batch_tumbler.cpp")
+    exe = os.path.join(out, "batch_tumbler_gpu")
+    if force or _newer(exe, [src, os.path.join(bdir, "benchmarks.h")] + gpu_deps):
+        _run([gxx, "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + bdir, src, "-L" + HERE,
+              "-lb2gpu_scenes", "-lb2cuda", "-Wl,-rpath,$ORIGIN/../../../box2d_optimized_b200", "-o", exe])
+    built.append(exe)
     return built
 
 
